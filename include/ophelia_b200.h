@@ -1,0 +1,147 @@
+/* libophelia_sm100.so -- C ABI of the B200-native dc_tts hot path (Text2Mel + SSRN).
+ *
+ * The reference (CSTR-Edinburgh/ophelia) has no FFI/plugin API: its operator boundary is the Python
+ * surface of modules.py / networks.py / architectures.py on top of TensorFlow-1.12 ops.  Each entry point
+ * below replaces the TF ops behind one of those functions; the Python mirror in ophelia_b200/ binds them
+ * with ctypes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (the library never allocates or frees);
+ *   - activations are fp32, channels-last [B, time, C] with an explicit row stride `ld*` in elements
+ *     (multiple of 4, rows 16-byte aligned);
+ *   - conv kernels keep the reference layouts: [k, Cin, Cout] (tf.layers.conv1d) and [1,3,Cout,Cin]
+ *     (tf.layers.conv2d_transpose);
+ *   - all calls are asynchronous on `stream`, never synchronise, and are legal under CUDA-graph capture;
+ *   - return 0 on success, a negative OPH_E* code otherwise; oph_last_error() returns a thread-local message.
+ */
+#ifndef OPHELIA_B200_H
+#define OPHELIA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* oph_stream_t; /* cudaStream_t */
+
+#define OPH_OK 0
+#define OPH_EINVAL (-1)
+#define OPH_ECUDA (-2)
+
+#define OPH_ACT_NONE 0
+#define OPH_ACT_RELU 1
+
+#define OPH_PAD_SAME 0
+#define OPH_PAD_CAUSAL 1
+
+int oph_version(void);
+const char* oph_last_error(void);
+
+/* ---- weight packing: fp32 kernels -> split-bf16 (hi,lo) SWIZZLE_128B shared-memory images ----------------
+ * `deconv`=0: w is [k][Cin][Cout] (modules.py:134-136).  `deconv`=1: w is [3][Cout][Cin] (modules.py:243-250).
+ * fwd image feeds oph_*_fwd, bwd image feeds the input-gradient GEMM of oph_*_bwd.
+ * Re-pack after every optimiser step (weights changed) or once for inference. */
+size_t oph_conv_pack_bytes(int k, int Cin, int Cout, int deconv, int backward);
+int oph_conv_pack(const float* w, int k, int Cin, int Cout, int deconv, void* packed_fwd, void* packed_bwd,
+                  oph_stream_t stream);
+
+/* ---- modules.conv1d (modules.py:91-146), hot-path uses are k=1 -------------------------------------------
+ * y = dropout(act(LN(conv(x) + bias))).  z [B*L][ldz] receives the pre-LN conv output (saved for backward,
+ * scratch otherwise), stats [B*L][2] = (mean, rstd) (nullable in inference), y_sig (nullable) = sigmoid(LN(..)).
+ * in_shift: extra time shift applied to the input rows (AudioEnc C_1 reads mels delayed by one frame,
+ * architectures.py:191).  norm: 1 = layer norm (eps 1e-12), 0 = none.  step (nullable, device int64) is mixed
+ * into the dropout seed so that a captured graph draws a fresh mask every replay. */
+int oph_conv1d_fwd(const float* x, long long ldx, const void* packed_w, const float* bias, const float* gamma,
+                   const float* beta, float* z, long long ldz, float* stats, float* y, long long ldy, float* y_sig,
+                   long long ldys, int B, int L, int Cin, int Cout, int k, int rate, int padding, int in_shift,
+                   int act, int norm, float drop_p, uint64_t seed, const long long* step, oph_stream_t stream);
+
+/* Backward of oph_conv1d_fwd.  dz [B*L][lddz] is scratch (>= Cout wide).  dx may be NULL (first layer);
+ * dw/dbias/dgamma/dbeta are ACCUMULATED into (caller zeroes the flat gradient buffer once per step). */
+int oph_conv1d_bwd(const float* dy, long long lddy, const float* x, long long ldx, const float* z, long long ldz,
+                   const float* stats, const void* packed_w_bwd, const float* gamma, const float* beta, float* dz,
+                   long long lddz, float* dx, long long lddx, float* dw, float* dbias, float* dgamma, float* dbeta,
+                   int B, int L, int Cin, int Cout, int k, int rate, int padding, int in_shift, int act, int norm,
+                   float drop_p, uint64_t seed, const long long* step, oph_stream_t stream);
+
+/* ---- modules.hc (modules.py:148-207): highway conv, C -> 2C -> C ------------------------------------------
+ * z [B*L][ldz] (>= 2C wide) pre-LN conv output; stats [B*L][4] = (mean1, rstd1, mean2, rstd2). */
+int oph_hc_fwd(const float* x, long long ldx, const void* packed_w, const float* bias, const float* g1,
+               const float* b1, const float* g2, const float* b2, float* z, long long ldz, float* stats, float* y,
+               long long ldy, int B, int L, int C, int k, int rate, int padding, int norm, float drop_p,
+               uint64_t seed, const long long* step, oph_stream_t stream);
+
+/* dz [B*L][lddz] (>= 2C) and dxres [B*L][ldxr] (>= C) are scratch. */
+int oph_hc_bwd(const float* dy, long long lddy, const float* x, long long ldx, const float* z, long long ldz,
+               const float* stats, const void* packed_w_bwd, const float* g1, const float* b1, const float* g2,
+               const float* b2, float* dz, long long lddz, float* dxres, long long ldxr, float* dx, long long lddx,
+               float* dw, float* dbias, float* dg1, float* db1, float* dg2, float* db2, int B, int L, int C, int k,
+               int rate, int padding, int norm, float drop_p, uint64_t seed, const long long* step,
+               oph_stream_t stream);
+
+/* ---- modules.conv1d_transpose (modules.py:209-258): stride-2, k=3, always layer-normed ---------------------
+ * out[2i] = W0.x[i] + W2.x[i-1], out[2i+1] = W1.x[i]; y is [B][2L][C].  z [B*2L][ldz], stats [B*2L][2]. */
+int oph_deconv_fwd(const float* x, long long ldx, const void* packed_w, const float* bias, const float* gamma,
+                   const float* beta, float* z, long long ldz, float* stats, float* y, long long ldy, int B, int L,
+                   int C, float drop_p, uint64_t seed, const long long* step, oph_stream_t stream);
+int oph_deconv_bwd(const float* dy, long long lddy, const float* x, long long ldx, const float* z, long long ldz,
+                   const float* stats, const void* packed_w_bwd, const float* gamma, const float* beta, float* dz,
+                   long long lddz, float* dx, long long lddx, float* dw, float* dbias, float* dgamma, float* dbeta,
+                   int B, int L, int C, float drop_p, uint64_t seed, const long long* step, oph_stream_t stream);
+
+/* ---- modules.embed (modules.py:15-44) -------------------------------------------------------------------- */
+int oph_embed_fwd(const int32_t* ids, const float* table, float* out, long long ldo, int rows, int E,
+                  oph_stream_t stream);
+int oph_embed_bwd(const int32_t* ids, const float* dout, long long ldo, float* dtable, int rows, int E,
+                  oph_stream_t stream);
+
+/* ---- networks.Attention (networks.py:286-325) --------------------------------------------------------------
+ * A = softmax(Q K^T / sqrt(d)) [B][T][ldA] (ldA >= N), R = A V written with row stride ldr (so it can land in
+ * the first half of the [R, Q] buffer, networks.py:317-319).  prev_max (nullable, int32 [B]) + win enable the
+ * forcibly-incremental window: keys outside [prev, prev+win) get -2^32+1 (networks.py:304-313).
+ * align_t (nullable) = alignments [B][N][T]; argmax (nullable) int32 [B][T] (first maximum);
+ * att_acc (nullable, device double) += sum A*W over n<maxN, t<maxT with the analytic guide (utils.py:155-161). */
+int oph_attention_fwd(const float* Q, long long ldq, const float* K, long long ldk, const float* V, long long ldv,
+                      float* A, long long ldA, float* R, long long ldr, float* align_t, int32_t* argmax,
+                      const int32_t* prev_max, int win, double* att_acc, int maxN, int maxT, float g, int B, int T,
+                      int N, int d, oph_stream_t stream);
+/* dR [B][T][lddr].  dA [B][T][ldA] scratch.  dq_addend (nullable) is added into dQ (the direct [R,Q] concat path).
+ * att_coef = lw_att / (B*min(N,maxN)*min(T,maxT)) injects the guided-attention gradient. */
+int oph_attention_bwd(const float* dR, long long lddr, const float* Q, long long ldq, const float* K, long long ldk,
+                      const float* V, long long ldv, const float* A, long long ldA, float* dA, float* dQ,
+                      long long lddq, const float* dq_addend, long long ldqa, float* dK, long long lddk, float* dV,
+                      long long lddv, float att_coef, int maxN, int maxT, float g, int B, int T, int N, int d,
+                      oph_stream_t stream);
+
+/* ---- losses (architectures.py:147-173, 245-355) ------------------------------------------------------------
+ * acc: device double[4] zeroed by the caller: sum|Y-t|, sum BCE, sum (Y-t)^2, (attention sum).
+ * dlogits (nullable) receives d(loss)/d(logits) for the weighted sum of the three reconstruction terms. */
+int oph_recon_loss(const float* logits, long long ldl, const float* target, long long ldt, float* dlogits,
+                   long long ldd, long long rows, int C, int squash, float w_l1, float w_bd, float w_l2,
+                   double* acc, oph_stream_t stream);
+int oph_loss_finalize(const double* acc, float* out, double n_recon, double n_att, float w_l1, float w_bd,
+                      float w_att, float w_l2, int has_att, int squash, oph_stream_t stream);
+
+/* ---- optimiser (architectures.py:96-131, utils.py:167-170) ------------------------------------------------
+ * lr_t: device float[2] = (Adam step size incl. bias correction, scheduled lr). */
+int oph_adam_prepare(const long long* global_step, float* lr_t, float lr0, float beta1, float beta2, int decay_lr,
+                     float warmup, oph_stream_t stream);
+int oph_adam_clip(float* p, float* m, float* v, const float* g, long long n, const float* lr_t, float beta1,
+                  float beta2, float eps, float clip, float grad_scale, oph_stream_t stream);
+int oph_step_inc(long long* global_step, oph_stream_t stream);
+
+/* ---- raw access to the tcgen05 GEMM core (tests / diagnostics) --------------------------------------------
+ * C[M][N] = alpha * A[M][K] * op(B) (+ bias) with 3-term split-bf16; b_mode 1: B is [N][K]; 2: B is [K][N]. */
+int oph_gemm_nt(const float* A, long long lda, const float* Bm, long long ldb, float* C, long long ldc,
+                const float* bias, int M, int N, int K, int b_mode, float alpha, int batch, long long a_bs,
+                long long b_bs, long long c_bs, oph_stream_t stream);
+/* C[M][N] (+)= A^T B with A [R][lda] (M columns), B [R][ldb] (N columns): the weight-gradient form. */
+int oph_gemm_tn(const float* A, long long lda, const float* Bm, long long ldb, float* C, long long ldc, int M,
+                int N, int R, int splits, oph_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,74 @@
+"""ctypes binding of libophelia_sm100.so (declared in include/ophelia_b200.h).
+
+The product path has NO CPU fallback: if the shared library is missing or a call fails, we raise.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libophelia_sm100.so")
+
+P, LL, I, F, D, U64, SZ = (ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_float, ctypes.c_double,
+                          ctypes.c_uint64, ctypes.c_size_t)
+
+# name -> (restype, argtypes); must list every symbol of include/ophelia_b200.h
+SIGNATURES = {
+    "oph_version": (I, []),
+    "oph_last_error": (ctypes.c_char_p, []),
+    "oph_conv_pack_bytes": (SZ, [I, I, I, I, I]),
+    "oph_conv_pack": (I, [P, I, I, I, I, P, P, P]),
+    "oph_conv1d_fwd": (I, [P, LL, P, P, P, P, P, LL, P, P, LL, P, LL, I, I, I, I, I, I, I, I, I, I, F, U64, P, P]),
+    "oph_conv1d_bwd": (I, [P, LL, P, LL, P, LL, P, P, P, P, P, LL, P, LL, P, P, P, P,
+                           I, I, I, I, I, I, I, I, I, I, F, U64, P, P]),
+    "oph_hc_fwd": (I, [P, LL, P, P, P, P, P, P, P, LL, P, P, LL, I, I, I, I, I, I, I, F, U64, P, P]),
+    "oph_hc_bwd": (I, [P, LL, P, LL, P, LL, P, P, P, P, P, P, P, LL, P, LL, P, LL, P, P, P, P, P, P,
+                       I, I, I, I, I, I, I, F, U64, P, P]),
+    "oph_deconv_fwd": (I, [P, LL, P, P, P, P, P, LL, P, P, LL, I, I, I, F, U64, P, P]),
+    "oph_deconv_bwd": (I, [P, LL, P, LL, P, LL, P, P, P, P, P, LL, P, LL, P, P, P, P, I, I, I, F, U64, P, P]),
+    "oph_embed_fwd": (I, [P, P, P, LL, I, I, P]),
+    "oph_embed_bwd": (I, [P, P, LL, P, I, I, P]),
+    "oph_attention_fwd": (I, [P, LL, P, LL, P, LL, P, LL, P, LL, P, P, P, I, P, I, I, F, I, I, I, I, P]),
+    "oph_attention_bwd": (I, [P, LL, P, LL, P, LL, P, LL, P, LL, P, P, LL, P, LL, P, LL, P, LL,
+                              F, I, I, F, I, I, I, I, P]),
+    "oph_recon_loss": (I, [P, LL, P, LL, P, LL, LL, I, I, F, F, F, P, P]),
+    "oph_loss_finalize": (I, [P, P, D, D, F, F, F, F, I, I, P]),
+    "oph_adam_prepare": (I, [P, P, F, F, F, I, F, P]),
+    "oph_adam_clip": (I, [P, P, P, P, LL, P, F, F, F, F, F, P]),
+    "oph_step_inc": (I, [P, P]),
+    "oph_gemm_nt": (I, [P, LL, P, LL, P, LL, P, I, I, I, I, F, I, LL, LL, LL, P]),
+    "oph_gemm_tn": (I, [P, LL, P, LL, P, LL, I, I, I, I, P]),
+}
+
+_lib = None
+
+
+class OpheliaError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (raises if it has not been built: no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise OpheliaError("%s not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(the CUDA path has no CPU fallback)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def call(name, *args):
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise OpheliaError("%s failed (%d): %s" % (name, rc, lib.oph_last_error().decode()))
+
+
+def pack_bytes(k, cin, cout, deconv, backward):
+    return int(load().oph_conv_pack_bytes(k, cin, cout, int(deconv), int(backward)))

@@ -1,0 +1,470 @@
+// C ABI of libophelia_sm100.so: composes the tcgen05 implicit-GEMM core with the row-wise kernels into the
+// reference's operators (modules.conv1d / hc / conv1d_transpose / embed, networks.Attention, losses, Adam).
+#include "../../include/ophelia_b200.h"
+#include "gemm_tc.cuh"
+#include "rowwise.cuh"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+using namespace oph;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, const char* detail = "") {
+    snprintf(g_err, sizeof(g_err), fmt, detail);
+    return code;
+}
+int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+        return OPH_ECUDA;
+    }
+    return OPH_OK;
+}
+#define OPH_TRY(expr) do { int _rc = (expr); if (_rc != OPH_OK) return _rc; } while (0)
+
+inline cudaStream_t S(oph_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+inline int nh_for(int N) { return N > GEMM_BNH ? 2 : 1; }
+
+int launch_gemm(GemmArgs& a, int zdim, cudaStream_t st) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        if (cudaFuncSetAttribute(gemm_bf16x3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM) != cudaSuccess ||
+            cudaFuncSetAttribute(gemm_bf16x3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM) != cudaSuccess)
+            return check_launch("cudaFuncSetAttribute(gemm)");
+        attr_done = true;
+    }
+    if (a.M <= 0 || a.N <= 0 || a.Kc <= 0) return fail(OPH_EINVAL, "gemm: empty problem%s");
+    if ((a.A.ld & 3) || (a.b_mode != B_PACKED && (a.Bm.ld & 3))) return fail(OPH_EINVAL, "gemm: row strides must be multiples of 4%s");
+    const int NH = nh_for(a.N);
+    const int NT = GEMM_BNH * NH;
+    const int nblocks = cdiv(a.N, NT);
+    if (a.ytaps < 1) a.ytaps = 1;
+    dim3 grid(cdiv(a.M, GEMM_BM), nblocks * a.ytaps, zdim < 1 ? 1 : zdim);
+    if (NH == 1) gemm_bf16x3_kernel<1><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(a);
+    else         gemm_bf16x3_kernel<2><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(a);
+    return check_launch("gemm_bf16x3_kernel");
+}
+
+GemmArgs blank() {
+    GemmArgs a;
+    memset(&a, 0, sizeof(a));
+    a.ntaps = 1; a.ytaps = 1; a.c_mul = 1; a.alpha = 1.f;
+    a.A.L = a.A.Ls = 1; a.A.mul = 1; a.Bm.L = a.Bm.Ls = 1; a.Bm.mul = 1;
+    return a;
+}
+
+// ------------------------------------------------------------------------------------------------ packing
+struct PackArgs {
+    const float* w;
+    int ntaps, tap_idx[3];
+    long long s_tap, s_c, s_n;
+    int Cvalid, Nvalid, NH;
+    uint8_t* out;
+};
+
+__global__ void pack_kernel(const PackArgs p, long long total) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int KBc = (p.Cvalid + GEMM_BK - 1) / GEMM_BK, KB = p.ntaps * KBc, NT = GEMM_BNH * p.NH;
+    const int nl = (int)(idx & 255);
+    const int chunk = (int)((idx >> 8) & 7);
+    long long rest = idx >> 11;
+    const int h = (int)(rest % p.NH); rest /= p.NH;
+    const int kb = (int)(rest % KB);
+    const int nb = (int)(rest / KB);
+    const int tap = kb / KBc, cb = kb - tap * KBc;
+    const int n = nb * NT + h * GEMM_BNH + nl;
+    const int c0 = cb * GEMM_BK + chunk * 8;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int c = c0 + e;
+        v[e] = (n < p.Nvalid && c < p.Cvalid) ? p.w[p.tap_idx[tap] * p.s_tap + c * p.s_c + n * p.s_n] : 0.f;
+    }
+    uint8_t* img = p.out + ((size_t)((size_t)nb * KB + kb) * p.NH + h) * B_SLOT;
+    store_split(img, img + B_PLANE, nl * 128 + ((chunk ^ (nl & 7)) << 4), v);
+}
+
+size_t pack_image_bytes(int ntaps, int Cvalid, int Nvalid) {
+    const int NH = nh_for(Nvalid);
+    return (size_t)cdiv(Nvalid, GEMM_BNH * NH) * ntaps * cdiv(Cvalid, GEMM_BK) * NH * B_SLOT;
+}
+
+int pack_image(const float* w, int ntaps, const int* tap_idx, long long s_tap, long long s_c, long long s_n,
+               int Cvalid, int Nvalid, void* out, cudaStream_t st) {
+    PackArgs p;
+    p.w = w; p.ntaps = ntaps;
+    for (int i = 0; i < 3; ++i) p.tap_idx[i] = i < ntaps ? tap_idx[i] : 0;
+    p.s_tap = s_tap; p.s_c = s_c; p.s_n = s_n; p.Cvalid = Cvalid; p.Nvalid = Nvalid; p.NH = nh_for(Nvalid);
+    p.out = reinterpret_cast<uint8_t*>(out);
+    const long long total = (long long)(pack_image_bytes(ntaps, Cvalid, Nvalid) / B_SLOT) * 2048;
+    pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p, total);
+    return check_launch("pack_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------ helpers
+void conv_offsets(int k, int rate, int padding, int in_shift, int* off) {
+    const int total = (k - 1) * rate;
+    const int left = padding == OPH_PAD_CAUSAL ? total : total / 2;
+    for (int j = 0; j < 3; ++j) off[j] = j < k ? j * rate - left - in_shift : 0;
+}
+
+int rows_grid(long long rows, int wpb) {
+    long long g = (rows + wpb - 1) / wpb;
+    const long long cap = 148 * 8;
+    return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
+}
+
+// weight gradient: dW[tap][m][n] += sum_r Amap(r,tap)[m] * Bmap(r,tap)[n]
+int launch_wgrad(const float* a, long long lda, int M, const int* a_off, int aL, int aLs, int a_mul,
+                 const float* b, long long ldb, int N, const int* b_off, int bL, int bLs, int b_mul,
+                 int R, int taps, float* dw, long long ldc, cudaStream_t st) {
+    GemmArgs g = blank();
+    g.a_mode = A_MNMAJOR; g.b_mode = B_MNMAJOR;
+    g.A.ptr = a; g.A.ld = lda; g.A.L = aL; g.A.Ls = aLs; g.A.mul = a_mul;
+    g.Bm.ptr = b; g.Bm.ld = ldb; g.Bm.L = bL; g.Bm.Ls = bLs; g.Bm.mul = b_mul;
+    for (int j = 0; j < 3; ++j) { g.A.off[j] = j < taps ? a_off[j] : 0; g.Bm.off[j] = j < taps ? b_off[j] : 0; }
+    g.M = M; g.N = N; g.Kc = R; g.ytaps = taps; g.c_tap_stride = (long long)M * ldc;
+    g.C = dw; g.ldc = ldc; g.atomic = 1; g.z_mode = Z_SPLITK;
+    const int base = cdiv(M, GEMM_BM) * cdiv(N, GEMM_BNH * nh_for(N)) * taps;
+    int splits = cdiv(2 * 148, base);
+    const int max_splits = cdiv(R, 4 * GEMM_BK);
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    g.k_chunk = cdiv(cdiv(R, splits), GEMM_BK) * GEMM_BK;
+    splits = cdiv(R, g.k_chunk);
+    return launch_gemm(g, splits, st);
+}
+
+}  // namespace
+
+// ================================================================================================ C ABI
+extern "C" {
+
+int oph_version(void) { return 100; }
+const char* oph_last_error(void) { return g_err; }
+
+size_t oph_conv_pack_bytes(int k, int Cin, int Cout, int deconv, int backward) {
+    if (!deconv) return backward ? pack_image_bytes(k, Cout, Cin) : pack_image_bytes(k, Cin, Cout);
+    if (backward) return pack_image_bytes(3, Cout, Cin);
+    return pack_image_bytes(2, Cin, Cout) + pack_image_bytes(1, Cin, Cout);
+}
+
+int oph_conv_pack(const float* w, int k, int Cin, int Cout, int deconv, void* packed_fwd, void* packed_bwd,
+                  oph_stream_t stream) {
+    const int t012[3] = {0, 1, 2};
+    if (!deconv) {
+        if (k < 1 || k > 3) return fail(OPH_EINVAL, "conv_pack: k must be 1..3%s");
+        const long long s_tap = (long long)Cin * Cout;
+        if (packed_fwd) OPH_TRY(pack_image(w, k, t012, s_tap, Cout, 1, Cin, Cout, packed_fwd, S(stream)));
+        if (packed_bwd) OPH_TRY(pack_image(w, k, t012, s_tap, 1, Cout, Cout, Cin, packed_bwd, S(stream)));
+        return OPH_OK;
+    }
+    // [3][Cout][Cin]: forward B[n=co][c=ci]; even rows use taps (0,2), odd rows tap 1
+    const long long s_tap = (long long)Cin * Cout;
+    if (packed_fwd) {
+        const int even[3] = {0, 2, 0}, odd[3] = {1, 0, 0};
+        OPH_TRY(pack_image(w, 2, even, s_tap, 1, Cin, Cin, Cout, packed_fwd, S(stream)));
+        uint8_t* second = reinterpret_cast<uint8_t*>(packed_fwd) + pack_image_bytes(2, Cin, Cout);
+        OPH_TRY(pack_image(w, 1, odd, s_tap, 1, Cin, Cin, Cout, second, S(stream)));
+    }
+    if (packed_bwd) OPH_TRY(pack_image(w, 3, t012, s_tap, Cin, 1, Cout, Cin, packed_bwd, S(stream)));
+    return OPH_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ conv1d
+int oph_conv1d_fwd(const float* x, long long ldx, const void* packed_w, const float* bias, const float* gamma,
+                   const float* beta, float* z, long long ldz, float* stats, float* y, long long ldy, float* y_sig,
+                   long long ldys, int B, int L, int Cin, int Cout, int k, int rate, int padding, int in_shift,
+                   int act, int norm, float drop_p, uint64_t seed, const long long* step, oph_stream_t stream) {
+    if (k < 1 || k > 3) return fail(OPH_EINVAL, "conv1d_fwd: k must be 1..3%s");
+    GemmArgs g = blank();
+    g.a_mode = A_KMAJOR; g.b_mode = B_PACKED;
+    g.A.ptr = x; g.A.ld = ldx; g.A.L = L; g.A.Ls = L; g.A.mul = 1;
+    conv_offsets(k, rate, padding, in_shift, g.A.off);
+    g.Bpacked = packed_w; g.M = B * L; g.N = Cout; g.Kc = Cin; g.ntaps = k;
+    g.C = z; g.ldc = ldz; g.bias = bias;
+    OPH_TRY(launch_gemm(g, 1, S(stream)));
+    const long long rows = (long long)B * L;
+    ln_act_fwd_kernel<<<rows_grid(rows, 8), 256, 0, S(stream)>>>(z, ldz, gamma, beta, y, ldy, y_sig, ldys, stats,
+                                                                (int)rows, Cout, act, norm, drop_p, seed, step);
+    return check_launch("ln_act_fwd_kernel");
+}
+
+int oph_conv1d_bwd(const float* dy, long long lddy, const float* x, long long ldx, const float* z, long long ldz,
+                   const float* stats, const void* packed_w_bwd, const float* gamma, const float* beta, float* dz,
+                   long long lddz, float* dx, long long lddx, float* dw, float* dbias, float* dgamma, float* dbeta,
+                   int B, int L, int Cin, int Cout, int k, int rate, int padding, int in_shift, int act, int norm,
+                   float drop_p, uint64_t seed, const long long* step, oph_stream_t stream) {
+    const long long rows = (long long)B * L;
+    ln_act_bwd_kernel<<<rows_grid(rows, 8), 256, 3 * Cout * sizeof(float), S(stream)>>>(
+        dy, lddy, z, ldz, stats, gamma, beta, dz, lddz, dgamma, dbeta, dbias, (int)rows, Cout, act, norm, drop_p, seed, step);
+    OPH_TRY(check_launch("ln_act_bwd_kernel"));
+    int off[3];
+    conv_offsets(k, rate, padding, in_shift, off);
+    if (dx) {
+        GemmArgs g = blank();
+        g.a_mode = A_KMAJOR; g.b_mode = B_PACKED;
+        g.A.ptr = dz; g.A.ld = lddz; g.A.L = L; g.A.Ls = L; g.A.mul = 1;
+        for (int j = 0; j < 3; ++j) g.A.off[j] = -off[j];
+        g.Bpacked = packed_w_bwd; g.M = B * L; g.N = Cin; g.Kc = Cout; g.ntaps = k;
+        g.C = dx; g.ldc = lddx;
+        OPH_TRY(launch_gemm(g, 1, S(stream)));
+    }
+    if (dw) {
+        const int zero[3] = {0, 0, 0};
+        OPH_TRY(launch_wgrad(x, ldx, Cin, off, L, L, 1, dz, lddz, Cout, zero, L, L, 1, B * L, k, dw, Cout, S(stream)));
+    }
+    return OPH_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ highway conv
+int oph_hc_fwd(const float* x, long long ldx, const void* packed_w, const float* bias, const float* g1,
+               const float* b1, const float* g2, const float* b2, float* z, long long ldz, float* stats, float* y,
+               long long ldy, int B, int L, int C, int k, int rate, int padding, int norm, float drop_p,
+               uint64_t seed, const long long* step, oph_stream_t stream) {
+    if (k < 1 || k > 3) return fail(OPH_EINVAL, "hc_fwd: k must be 1..3%s");
+    GemmArgs g = blank();
+    g.a_mode = A_KMAJOR; g.b_mode = B_PACKED;
+    g.A.ptr = x; g.A.ld = ldx; g.A.L = L; g.A.Ls = L; g.A.mul = 1;
+    conv_offsets(k, rate, padding, 0, g.A.off);
+    g.Bpacked = packed_w; g.M = B * L; g.N = 2 * C; g.Kc = C; g.ntaps = k;
+    g.C = z; g.ldc = ldz; g.bias = bias;
+    OPH_TRY(launch_gemm(g, 1, S(stream)));
+    const long long rows = (long long)B * L;
+    hc_post_fwd_kernel<<<rows_grid(rows, 8), 256, 0, S(stream)>>>(z, ldz, x, ldx, g1, b1, g2, b2, y, ldy, stats,
+                                                                 (int)rows, C, norm, drop_p, seed, step);
+    return check_launch("hc_post_fwd_kernel");
+}
+
+int oph_hc_bwd(const float* dy, long long lddy, const float* x, long long ldx, const float* z, long long ldz,
+               const float* stats, const void* packed_w_bwd, const float* g1, const float* b1, const float* g2,
+               const float* b2, float* dz, long long lddz, float* dxres, long long ldxr, float* dx, long long lddx,
+               float* dw, float* dbias, float* dg1, float* db1, float* dg2, float* db2, int B, int L, int C, int k,
+               int rate, int padding, int norm, float drop_p, uint64_t seed, const long long* step,
+               oph_stream_t stream) {
+    const long long rows = (long long)B * L;
+    hc_post_bwd_kernel<<<rows_grid(rows, 8), 256, 6 * C * sizeof(float), S(stream)>>>(
+        dy, lddy, z, ldz, x, ldx, stats, g1, b1, g2, b2, dz, lddz, dxres, ldxr, dg1, db1, dg2, db2, dbias,
+        (int)rows, C, norm, drop_p, seed, step);
+    OPH_TRY(check_launch("hc_post_bwd_kernel"));
+    int off[3];
+    conv_offsets(k, rate, padding, 0, off);
+    {
+        GemmArgs g = blank();
+        g.a_mode = A_KMAJOR; g.b_mode = B_PACKED;
+        g.A.ptr = dz; g.A.ld = lddz; g.A.L = L; g.A.Ls = L; g.A.mul = 1;
+        for (int j = 0; j < 3; ++j) g.A.off[j] = -off[j];
+        g.Bpacked = packed_w_bwd; g.M = B * L; g.N = C; g.Kc = 2 * C; g.ntaps = k;
+        g.C = dx; g.ldc = lddx; g.addend = dxres; g.ld_add = ldxr;
+        OPH_TRY(launch_gemm(g, 1, S(stream)));
+    }
+    if (dw) {
+        const int zero[3] = {0, 0, 0};
+        OPH_TRY(launch_wgrad(x, ldx, C, off, L, L, 1, dz, lddz, 2 * C, zero, L, L, 1, B * L, k, dw, 2 * C, S(stream)));
+    }
+    return OPH_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ transposed conv
+int oph_deconv_fwd(const float* x, long long ldx, const void* packed_w, const float* bias, const float* gamma,
+                   const float* beta, float* z, long long ldz, float* stats, float* y, long long ldy, int B, int L,
+                   int C, float drop_p, uint64_t seed, const long long* step, oph_stream_t stream) {
+    for (int parity = 0; parity < 2; ++parity) {
+        GemmArgs g = blank();
+        g.a_mode = A_KMAJOR; g.b_mode = B_PACKED;
+        g.A.ptr = x; g.A.ld = ldx; g.A.L = L; g.A.Ls = L; g.A.mul = 1;
+        g.A.off[0] = 0; g.A.off[1] = -1; g.A.off[2] = 0;       // even: W0.x[i] + W2.x[i-1]; odd: W1.x[i]
+        g.ntaps = parity == 0 ? 2 : 1;
+        g.Bpacked = reinterpret_cast<const uint8_t*>(packed_w) + (parity ? pack_image_bytes(2, C, C) : 0);
+        g.M = B * L; g.N = C; g.Kc = C;
+        g.C = z; g.ldc = ldz; g.c_mul = 2; g.c_off = parity; g.bias = bias;
+        OPH_TRY(launch_gemm(g, 1, S(stream)));
+    }
+    const long long rows = 2LL * B * L;
+    ln_act_fwd_kernel<<<rows_grid(rows, 8), 256, 0, S(stream)>>>(z, ldz, gamma, beta, y, ldy, nullptr, 0, stats,
+                                                                (int)rows, C, OPH_ACT_NONE, 1, drop_p, seed, step);
+    return check_launch("ln_act_fwd_kernel(deconv)");
+}
+
+int oph_deconv_bwd(const float* dy, long long lddy, const float* x, long long ldx, const float* z, long long ldz,
+                   const float* stats, const void* packed_w_bwd, const float* gamma, const float* beta, float* dz,
+                   long long lddz, float* dx, long long lddx, float* dw, float* dbias, float* dgamma, float* dbeta,
+                   int B, int L, int C, float drop_p, uint64_t seed, const long long* step, oph_stream_t stream) {
+    const long long rows = 2LL * B * L;
+    ln_act_bwd_kernel<<<rows_grid(rows, 8), 256, 3 * C * sizeof(float), S(stream)>>>(
+        dy, lddy, z, ldz, stats, gamma, beta, dz, lddz, dgamma, dbeta, dbias, (int)rows, C, OPH_ACT_NONE, 1, drop_p, seed, step);
+    OPH_TRY(check_launch("ln_act_bwd_kernel(deconv)"));
+    if (dx) {   // dx[i] = W0^T dz[2i] + W1^T dz[2i+1] + W2^T dz[2i+2]
+        GemmArgs g = blank();
+        g.a_mode = A_KMAJOR; g.b_mode = B_PACKED;
+        g.A.ptr = dz; g.A.ld = lddz; g.A.L = L; g.A.Ls = 2 * L; g.A.mul = 2;
+        g.A.off[0] = 0; g.A.off[1] = 1; g.A.off[2] = 2;
+        g.Bpacked = packed_w_bwd; g.M = B * L; g.N = C; g.Kc = C; g.ntaps = 3;
+        g.C = dx; g.ldc = lddx;
+        OPH_TRY(launch_gemm(g, 1, S(stream)));
+    }
+    if (dw) {   // dW[j][co][ci]: j=0: dz[2i] x[i]; j=1: dz[2i+1] x[i]; j=2: dz[2i] x[i-1]
+        const int a_off[3] = {0, 1, 0}, b_off[3] = {0, 0, -1};
+        OPH_TRY(launch_wgrad(dz, lddz, C, a_off, L, 2 * L, 2, x, ldx, C, b_off, L, L, 1, B * L, 3, dw, C, S(stream)));
+    }
+    return OPH_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ embedding
+int oph_embed_fwd(const int32_t* ids, const float* table, float* out, long long ldo, int rows, int E, oph_stream_t stream) {
+    embed_fwd_kernel<<<rows_grid(rows, 8), 256, 0, S(stream)>>>(ids, table, out, ldo, rows, E);
+    return check_launch("embed_fwd_kernel");
+}
+int oph_embed_bwd(const int32_t* ids, const float* dout, long long ldo, float* dtable, int rows, int E, oph_stream_t stream) {
+    embed_bwd_kernel<<<rows_grid(rows, 8), 256, 0, S(stream)>>>(ids, dout, ldo, dtable, rows, E);
+    return check_launch("embed_bwd_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------ attention
+int oph_attention_fwd(const float* Q, long long ldq, const float* K, long long ldk, const float* V, long long ldv,
+                      float* A, long long ldA, float* R, long long ldr, float* align_t, int32_t* argmax,
+                      const int32_t* prev_max, int win, double* att_acc, int maxN, int maxT, float g_, int B, int T,
+                      int N, int d, oph_stream_t stream) {
+    if (ldA < N) return fail(OPH_EINVAL, "attention_fwd: ldA < N%s");
+    {   // S = Q K^T / sqrt(d)
+        GemmArgs g = blank();
+        g.a_mode = A_KMAJOR; g.b_mode = B_KMAJOR;
+        g.A.ptr = Q; g.A.ld = ldq; g.A.L = T; g.A.Ls = T;
+        g.Bm.ptr = K; g.Bm.ld = ldk;
+        g.M = T; g.N = N; g.Kc = d;
+        g.z_mode = Z_BATCH; g.a_zs = (long long)T * ldq; g.b_zs = (long long)N * ldk; g.c_zs = (long long)T * ldA;
+        g.C = A; g.ldc = ldA; g.alpha = 1.0f / sqrtf((float)d);
+        OPH_TRY(launch_gemm(g, B, S(stream)));
+    }
+    softmax_fwd_kernel<<<rows_grid((long long)B * T, 8), 256, 0, S(stream)>>>(A, ldA, B, T, N, prev_max, win, align_t,
+                                                                            argmax, att_acc, maxN, maxT, g_);
+    OPH_TRY(check_launch("softmax_fwd_kernel"));
+    {   // R = A V
+        GemmArgs g = blank();
+        g.a_mode = A_KMAJOR; g.b_mode = B_MNMAJOR;
+        g.A.ptr = A; g.A.ld = ldA; g.A.L = T; g.A.Ls = T;
+        g.Bm.ptr = V; g.Bm.ld = ldv; g.Bm.L = N; g.Bm.Ls = N;
+        g.M = T; g.N = d; g.Kc = N;
+        g.z_mode = Z_BATCH; g.a_zs = (long long)T * ldA; g.b_zs = (long long)N * ldv; g.c_zs = (long long)T * ldr;
+        g.C = R; g.ldc = ldr;
+        OPH_TRY(launch_gemm(g, B, S(stream)));
+    }
+    return OPH_OK;
+}
+
+int oph_attention_bwd(const float* dR, long long lddr, const float* Q, long long ldq, const float* K, long long ldk,
+                      const float* V, long long ldv, const float* A, long long ldA, float* dA, float* dQ,
+                      long long lddq, const float* dq_addend, long long ldqa, float* dK, long long lddk, float* dV,
+                      long long lddv, float att_coef, int maxN, int maxT, float g_, int B, int T, int N, int d,
+                      oph_stream_t stream) {
+    const float scale = 1.0f / sqrtf((float)d);
+    {   // dV[n][:] = sum_t A[t][n] dR[t][:]
+        GemmArgs g = blank();
+        g.a_mode = A_MNMAJOR; g.b_mode = B_MNMAJOR;
+        g.A.ptr = A; g.A.ld = ldA; g.A.L = T; g.A.Ls = T;
+        g.Bm.ptr = dR; g.Bm.ld = lddr; g.Bm.L = T; g.Bm.Ls = T;
+        g.M = N; g.N = d; g.Kc = T;
+        g.z_mode = Z_BATCH; g.a_zs = (long long)T * ldA; g.b_zs = (long long)T * lddr; g.c_zs = (long long)N * lddv;
+        g.C = dV; g.ldc = lddv;
+        OPH_TRY(launch_gemm(g, B, S(stream)));
+    }
+    {   // dA = dR V^T
+        GemmArgs g = blank();
+        g.a_mode = A_KMAJOR; g.b_mode = B_KMAJOR;
+        g.A.ptr = dR; g.A.ld = lddr; g.A.L = T; g.A.Ls = T;
+        g.Bm.ptr = V; g.Bm.ld = ldv;
+        g.M = T; g.N = N; g.Kc = d;
+        g.z_mode = Z_BATCH; g.a_zs = (long long)T * lddr; g.b_zs = (long long)N * ldv; g.c_zs = (long long)T * ldA;
+        g.C = dA; g.ldc = ldA;
+        OPH_TRY(launch_gemm(g, B, S(stream)));
+    }
+    softmax_bwd_kernel<<<rows_grid((long long)B * T, 8), 256, 0, S(stream)>>>(A, ldA, dA, ldA, B, T, N, att_coef, maxN, maxT, g_);
+    OPH_TRY(check_launch("softmax_bwd_kernel"));
+    {   // dQ = dS K / sqrt(d) (+ direct path)
+        GemmArgs g = blank();
+        g.a_mode = A_KMAJOR; g.b_mode = B_MNMAJOR;
+        g.A.ptr = dA; g.A.ld = ldA; g.A.L = T; g.A.Ls = T;
+        g.Bm.ptr = K; g.Bm.ld = ldk; g.Bm.L = N; g.Bm.Ls = N;
+        g.M = T; g.N = d; g.Kc = N;
+        g.z_mode = Z_BATCH; g.a_zs = (long long)T * ldA; g.b_zs = (long long)N * ldk; g.c_zs = (long long)T * lddq;
+        g.C = dQ; g.ldc = lddq; g.alpha = scale;
+        if (dq_addend) {
+            if ((long long)T * ldqa != g.c_zs || ldqa != lddq) return fail(OPH_EINVAL, "attention_bwd: dq_addend must share dQ's layout%s");
+            g.addend = dq_addend; g.ld_add = ldqa;
+        }
+        OPH_TRY(launch_gemm(g, B, S(stream)));
+    }
+    {   // dK[n][:] = sum_t dS[t][n] Q[t][:] / sqrt(d)
+        GemmArgs g = blank();
+        g.a_mode = A_MNMAJOR; g.b_mode = B_MNMAJOR;
+        g.A.ptr = dA; g.A.ld = ldA; g.A.L = T; g.A.Ls = T;
+        g.Bm.ptr = Q; g.Bm.ld = ldq; g.Bm.L = T; g.Bm.Ls = T;
+        g.M = N; g.N = d; g.Kc = T;
+        g.z_mode = Z_BATCH; g.a_zs = (long long)T * ldA; g.b_zs = (long long)T * ldq; g.c_zs = (long long)N * lddk;
+        g.C = dK; g.ldc = lddk; g.alpha = scale;
+        OPH_TRY(launch_gemm(g, B, S(stream)));
+    }
+    return OPH_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ losses / optimiser
+int oph_recon_loss(const float* logits, long long ldl, const float* target, long long ldt, float* dlogits,
+                   long long ldd, long long rows, int C, int squash, float w_l1, float w_bd, float w_l2,
+                   double* acc, oph_stream_t stream) {
+    recon_loss_kernel<<<rows_grid(rows, 8), 256, 0, S(stream)>>>(logits, ldl, target, ldt, dlogits, ldd, rows, C, squash,
+                                                                w_l1, w_bd, w_l2, acc);
+    return check_launch("recon_loss_kernel");
+}
+int oph_loss_finalize(const double* acc, float* out, double n_recon, double n_att, float w_l1, float w_bd,
+                      float w_att, float w_l2, int has_att, int squash, oph_stream_t stream) {
+    loss_finalize_kernel<<<1, 1, 0, S(stream)>>>(acc, out, n_recon, n_att, w_l1, w_bd, w_att, w_l2, has_att, squash);
+    return check_launch("loss_finalize_kernel");
+}
+int oph_adam_prepare(const long long* global_step, float* lr_t, float lr0, float beta1, float beta2, int decay_lr,
+                     float warmup, oph_stream_t stream) {
+    adam_prepare_kernel<<<1, 1, 0, S(stream)>>>(global_step, lr_t, lr0, beta1, beta2, decay_lr, warmup);
+    return check_launch("adam_prepare_kernel");
+}
+int oph_adam_clip(float* p, float* m, float* v, const float* g, long long n, const float* lr_t, float beta1,
+                  float beta2, float eps, float clip, float grad_scale, oph_stream_t stream) {
+    adam_clip_kernel<<<148 * 4, 256, 0, S(stream)>>>(p, m, v, g, n, lr_t, beta1, beta2, eps, clip, grad_scale);
+    return check_launch("adam_clip_kernel");
+}
+int oph_step_inc(long long* global_step, oph_stream_t stream) {
+    step_inc_kernel<<<1, 1, 0, S(stream)>>>(global_step);
+    return check_launch("step_inc_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------ raw GEMM (tests)
+int oph_gemm_nt(const float* A, long long lda, const float* Bm, long long ldb, float* C, long long ldc,
+                const float* bias, int M, int N, int K, int b_mode, float alpha, int batch, long long a_bs,
+                long long b_bs, long long c_bs, oph_stream_t stream) {
+    GemmArgs g = blank();
+    g.a_mode = A_KMAJOR; g.b_mode = b_mode == 2 ? B_MNMAJOR : B_KMAJOR;
+    g.A.ptr = A; g.A.ld = lda; g.A.L = M; g.A.Ls = M;
+    g.Bm.ptr = Bm; g.Bm.ld = ldb; g.Bm.L = K; g.Bm.Ls = K;
+    g.M = M; g.N = N; g.Kc = K; g.C = C; g.ldc = ldc; g.bias = bias; g.alpha = alpha;
+    if (batch > 1) { g.z_mode = Z_BATCH; g.a_zs = a_bs; g.b_zs = b_bs; g.c_zs = c_bs; }
+    return launch_gemm(g, batch, S(stream));
+}
+int oph_gemm_tn(const float* A, long long lda, const float* Bm, long long ldb, float* C, long long ldc, int M,
+                int N, int R, int splits, oph_stream_t stream) {
+    GemmArgs g = blank();
+    g.a_mode = A_MNMAJOR; g.b_mode = B_MNMAJOR;
+    g.A.ptr = A; g.A.ld = lda; g.A.L = R; g.A.Ls = R;
+    g.Bm.ptr = Bm; g.Bm.ld = ldb; g.Bm.L = R; g.Bm.Ls = R;
+    g.M = M; g.N = N; g.Kc = R; g.C = C; g.ldc = ldc; g.atomic = 1; g.z_mode = Z_SPLITK;
+    if (splits < 1) splits = 1;
+    g.k_chunk = cdiv(cdiv(R, splits), GEMM_BK) * GEMM_BK;
+    return launch_gemm(g, cdiv(R, g.k_chunk), S(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,424 @@
+// Row-wise (HBM-bound) kernels of the dc_tts path: layer-norm / activation / highway mix (+ their backward),
+// softmax with the monotonic window mask and guided-attention loss, embedding, losses, Adam.
+// One warp owns one [C]-row; reductions along channels are warp shuffles; loads are lane-contiguous.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace oph {
+
+constexpr float LN_EPS = 1e-12f;                 // tf.contrib.layers.layer_norm (modules.py:65)
+constexpr float ATT_MASK_VALUE = -4294967295.0f; // -2**32+1 (networks.py:312)
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+
+// counter-based dropout mask (recomputed in backward): keep iff u >= rate; kept values scaled by 1/(1-rate)
+__device__ __forceinline__ float drop_scale(unsigned long long seed, unsigned long long idx, float rate, float inv_keep) {
+    unsigned long long z = seed + idx * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    const float u = (float)(z >> 40) * (1.0f / 16777216.0f);
+    return u >= rate ? inv_keep : 0.f;
+}
+__device__ __forceinline__ unsigned long long eff_seed(unsigned long long seed, const long long* step) {
+    return step ? seed + (unsigned long long)(*step) * 0xD1342543DE82EF95ull : seed;
+}
+
+struct RowStats { float mean, rstd; };
+
+// two-pass moments like tf.nn.moments: mean, then mean of squared deviations (biased)
+__device__ __forceinline__ RowStats row_stats(const float* __restrict__ z, int C, int lane) {
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += z[c];
+    const float mean = warp_sum(s) / (float)C;
+    float q = 0.f;
+    for (int c = lane; c < C; c += 32) { const float d = z[c] - mean; q += d * d; }
+    const float var = warp_sum(q) / (float)C;
+    return {mean, rsqrtf(var + LN_EPS)};
+}
+
+// ------------------------------------------------------------------------------------------------
+// conv1d tail (modules.py:137-141): y = dropout(act(LN(z)));  optional y_sig = sigmoid(LN(z)) (networks.py:430-433)
+__global__ void ln_act_fwd_kernel(const float* __restrict__ z, long long ldz, const float* __restrict__ gamma,
+                                  const float* __restrict__ beta, float* __restrict__ y, long long ldy,
+                                  float* __restrict__ y_sig, long long ldys, float* __restrict__ stats,
+                                  int rows, int C, int act, int norm, float drop_p, unsigned long long seed,
+                                  const long long* step) {
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+    const unsigned long long sd = eff_seed(seed, step);
+    for (long long row = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * wpb) {
+        const float* zr = z + row * ldz;
+        RowStats st = {0.f, 1.f};
+        if (norm) st = row_stats(zr, C, lane);
+        if (stats && lane == 0) { stats[row * 2] = st.mean; stats[row * 2 + 1] = st.rstd; }
+        for (int c = lane; c < C; c += 32) {
+            float u = zr[c];
+            if (norm) u = (u - st.mean) * st.rstd * gamma[c] + beta[c];
+            if (y_sig) y_sig[row * ldys + c] = sigmoidf_(u);
+            float a = act == 1 ? fmaxf(u, 0.f) : u;
+            if (drop_p > 0.f) a *= drop_scale(sd, (unsigned long long)row * C + c, drop_p, inv_keep);
+            y[row * ldy + c] = a;
+        }
+    }
+}
+
+// highway tail (modules.py:194-205): z = [H1 | H2]; g = sigmoid(LN1(H1)); h = LN2(H2); y = dropout(g*h + (1-g)*x)
+__global__ void hc_post_fwd_kernel(const float* __restrict__ z, long long ldz, const float* __restrict__ x, long long ldx,
+                                   const float* __restrict__ g1, const float* __restrict__ b1,
+                                   const float* __restrict__ g2, const float* __restrict__ b2,
+                                   float* __restrict__ y, long long ldy, float* __restrict__ stats,
+                                   int rows, int C, int norm, float drop_p, unsigned long long seed, const long long* step) {
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+    const unsigned long long sd = eff_seed(seed, step);
+    for (long long row = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * wpb) {
+        const float* z1 = z + row * ldz;
+        const float* z2 = z1 + C;
+        const float* xr = x + row * ldx;
+        RowStats s1 = {0.f, 1.f}, s2 = {0.f, 1.f};
+        if (norm) { s1 = row_stats(z1, C, lane); s2 = row_stats(z2, C, lane); }
+        if (stats && lane == 0) {
+            stats[row * 4] = s1.mean; stats[row * 4 + 1] = s1.rstd; stats[row * 4 + 2] = s2.mean; stats[row * 4 + 3] = s2.rstd;
+        }
+        for (int c = lane; c < C; c += 32) {
+            float u1 = z1[c], u2 = z2[c];
+            if (norm) {
+                u1 = (u1 - s1.mean) * s1.rstd * g1[c] + b1[c];
+                u2 = (u2 - s2.mean) * s2.rstd * g2[c] + b2[c];
+            }
+            const float g = sigmoidf_(u1);
+            float o = g * u2 + (1.f - g) * xr[c];
+            if (drop_p > 0.f) o *= drop_scale(sd, (unsigned long long)row * C + c, drop_p, inv_keep);
+            y[row * ldy + c] = o;
+        }
+    }
+}
+
+// backward of ln_act: dz (pre-LN conv output gradient); column sums dgamma/dbeta/dbias via shared atomics
+__global__ void ln_act_bwd_kernel(const float* __restrict__ dy, long long lddy, const float* __restrict__ z, long long ldz,
+                                  const float* __restrict__ stats, const float* __restrict__ gamma,
+                                  const float* __restrict__ beta, float* __restrict__ dz, long long lddz,
+                                  float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias,
+                                  int rows, int C, int act, int norm, float drop_p, unsigned long long seed,
+                                  const long long* step) {
+    extern __shared__ float sacc[];            // [3][C]: dgamma, dbeta, dbias
+    for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) sacc[i] = 0.f;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+    const float invC = 1.f / (float)C;
+    const unsigned long long sd = eff_seed(seed, step);
+    for (long long row = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * wpb) {
+        const float* zr = z + row * ldz;
+        const float* dyr = dy + row * lddy;
+        float* dzr = dz + row * lddz;
+        float mean = 0.f, rstd = 1.f;
+        if (norm) { mean = stats[row * 2]; rstd = stats[row * 2 + 1]; }
+        float s1 = 0.f, s2 = 0.f;
+        for (int c = lane; c < C; c += 32) {
+            const float xh = norm ? (zr[c] - mean) * rstd : zr[c];
+            const float u = norm ? xh * gamma[c] + beta[c] : xh;
+            float du = dyr[c];
+            if (drop_p > 0.f) du *= drop_scale(sd, (unsigned long long)row * C + c, drop_p, inv_keep);
+            if (act == 1 && !(u > 0.f)) du = 0.f;
+            if (norm) {
+                atomicAdd(&sacc[c], du * xh);
+                atomicAdd(&sacc[C + c], du);
+                const float dxh = du * gamma[c];
+                s1 += dxh; s2 += dxh * xh;
+                dzr[c] = dxh;                  // staged; finished below
+            } else {
+                dzr[c] = du;
+                atomicAdd(&sacc[2 * C + c], du);
+            }
+        }
+        if (norm) {
+            s1 = warp_sum(s1) * invC; s2 = warp_sum(s2) * invC;
+            for (int c = lane; c < C; c += 32) {
+                const float xh = (zr[c] - mean) * rstd;
+                const float d = rstd * (dzr[c] - s1 - xh * s2);
+                dzr[c] = d;
+                atomicAdd(&sacc[2 * C + c], d);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+        if (norm) { atomicAdd(dgamma + i, sacc[i]); atomicAdd(dbeta + i, sacc[C + i]); }
+        if (dbias) atomicAdd(dbias + i, sacc[2 * C + i]);
+    }
+}
+
+// backward of the highway tail: dz [rows][2C] and the residual-path gradient dxres = do*(1-g)
+__global__ void hc_post_bwd_kernel(const float* __restrict__ dy, long long lddy, const float* __restrict__ z, long long ldz,
+                                   const float* __restrict__ x, long long ldx, const float* __restrict__ stats,
+                                   const float* __restrict__ g1, const float* __restrict__ b1,
+                                   const float* __restrict__ g2, const float* __restrict__ b2,
+                                   float* __restrict__ dz, long long lddz, float* __restrict__ dxres, long long lddx,
+                                   float* __restrict__ dg1, float* __restrict__ db1, float* __restrict__ dg2,
+                                   float* __restrict__ db2, float* __restrict__ dbias,
+                                   int rows, int C, int norm, float drop_p, unsigned long long seed, const long long* step) {
+    extern __shared__ float sacc[];            // [6][C]: dg1, db1, dg2, db2, dbias(H1), dbias(H2)
+    for (int i = threadIdx.x; i < 6 * C; i += blockDim.x) sacc[i] = 0.f;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+    const float invC = 1.f / (float)C;
+    const unsigned long long sd = eff_seed(seed, step);
+    for (long long row = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * wpb) {
+        const float* z1 = z + row * ldz;
+        const float* z2 = z1 + C;
+        const float* xr = x + row * ldx;
+        const float* dyr = dy + row * lddy;
+        float* dz1 = dz + row * lddz;
+        float* dz2 = dz1 + C;
+        float m1 = 0.f, r1 = 1.f, m2 = 0.f, r2 = 1.f;
+        if (norm) { m1 = stats[row * 4]; r1 = stats[row * 4 + 1]; m2 = stats[row * 4 + 2]; r2 = stats[row * 4 + 3]; }
+        float a1 = 0.f, a2 = 0.f, c1 = 0.f, c2 = 0.f;
+        for (int c = lane; c < C; c += 32) {
+            const float xh1 = norm ? (z1[c] - m1) * r1 : z1[c];
+            const float xh2 = norm ? (z2[c] - m2) * r2 : z2[c];
+            const float u1 = norm ? xh1 * g1[c] + b1[c] : xh1;
+            const float h = norm ? xh2 * g2[c] + b2[c] : xh2;
+            const float g = sigmoidf_(u1);
+            float d_o = dyr[c];
+            if (drop_p > 0.f) d_o *= drop_scale(sd, (unsigned long long)row * C + c, drop_p, inv_keep);
+            dxres[row * lddx + c] = d_o * (1.f - g);
+            const float du1 = d_o * (h - xr[c]) * g * (1.f - g);
+            const float du2 = d_o * g;
+            if (norm) {
+                atomicAdd(&sacc[c], du1 * xh1); atomicAdd(&sacc[C + c], du1);
+                atomicAdd(&sacc[2 * C + c], du2 * xh2); atomicAdd(&sacc[3 * C + c], du2);
+                const float e1 = du1 * g1[c], e2 = du2 * g2[c];
+                a1 += e1; a2 += e1 * xh1; c1 += e2; c2 += e2 * xh2;
+                dz1[c] = e1; dz2[c] = e2;
+            } else {
+                dz1[c] = du1; dz2[c] = du2;
+                atomicAdd(&sacc[4 * C + c], du1); atomicAdd(&sacc[5 * C + c], du2);
+            }
+        }
+        if (norm) {
+            a1 = warp_sum(a1) * invC; a2 = warp_sum(a2) * invC; c1 = warp_sum(c1) * invC; c2 = warp_sum(c2) * invC;
+            for (int c = lane; c < C; c += 32) {
+                const float xh1 = (z1[c] - m1) * r1, xh2 = (z2[c] - m2) * r2;
+                const float d1 = r1 * (dz1[c] - a1 - xh1 * a2);
+                const float d2 = r2 * (dz2[c] - c1 - xh2 * c2);
+                dz1[c] = d1; dz2[c] = d2;
+                atomicAdd(&sacc[4 * C + c], d1); atomicAdd(&sacc[5 * C + c], d2);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+        if (norm) {
+            atomicAdd(dg1 + i, sacc[i]); atomicAdd(db1 + i, sacc[C + i]);
+            atomicAdd(dg2 + i, sacc[2 * C + i]); atomicAdd(db2 + i, sacc[3 * C + i]);
+        }
+        if (dbias) { atomicAdd(dbias + i, sacc[4 * C + i]); atomicAdd(dbias + C + i, sacc[5 * C + i]); }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ attention
+__device__ __forceinline__ float guide_w(int n, int t, float inv_maxN, float inv_maxT, float inv_2g2) {
+    const float d = (float)t * inv_maxT - (float)n * inv_maxN;           // utils.py:155-161
+    return 1.f - __expf(-d * d * inv_2g2);
+}
+
+// in: S[b][t][0..N) scaled scores.  out: probabilities in place, optional transposed alignments [B][N][T],
+// argmax (first maximum), guided-attention partial sum  sum_{n<maxN,t<maxT} A*W  (architectures.py:258-270)
+__global__ void softmax_fwd_kernel(float* __restrict__ S, long long ldS, int B, int T, int N,
+                                   const int* __restrict__ prev_max, int win,
+                                   float* __restrict__ align_t, int* __restrict__ argmax_out,
+                                   double* __restrict__ att_acc, int maxN, int maxT, float g) {
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    const float inv_maxN = 1.f / (float)maxN, inv_maxT = 1.f / (float)maxT, inv_2g2 = 1.f / (2.f * g * g);
+    float att_part = 0.f;
+    const long long rows = (long long)B * T;
+    for (long long row = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * wpb) {
+        const int b = (int)(row / T), t = (int)(row - (long long)b * T);
+        float* sr = S + row * ldS;
+        int lo = 0, hi = N;
+        if (prev_max) { lo = prev_max[b]; hi = lo + win; }        // allowed keys: lo <= n < hi (networks.py:304-306)
+        float mx = -INFINITY; int arg = 0x7fffffff;
+        for (int n = lane; n < N; n += 32) {
+            float v = sr[n];
+            if (n < lo || n >= hi) v = ATT_MASK_VALUE;
+            if (v > mx) { mx = v; arg = n; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+            const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+            if (om > mx || (om == mx && oa < arg)) { mx = om; arg = oa; }
+        }
+        float sum = 0.f;
+        for (int n = lane; n < N; n += 32) {
+            float v = sr[n];
+            if (n < lo || n >= hi) v = ATT_MASK_VALUE;
+            const float e = __expf(v - mx);
+            sr[n] = e; sum += e;
+        }
+        const float inv = 1.f / warp_sum(sum);
+        for (int n = lane; n < N; n += 32) {
+            const float a = sr[n] * inv;
+            sr[n] = a;
+            if (align_t) align_t[((long long)b * N + n) * T + t] = a;
+            if (att_acc && n < maxN && t < maxT) att_part += a * guide_w(n, t, inv_maxN, inv_maxT, inv_2g2);
+        }
+        if (argmax_out && lane == 0) argmax_out[row] = arg;
+    }
+    if (att_acc) {
+        __shared__ float red[32];
+        att_part = warp_sum(att_part);
+        if (lane == 0) red[threadIdx.x >> 5] = att_part;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            float v = threadIdx.x < wpb ? red[threadIdx.x] : 0.f;
+            v = warp_sum(v);
+            if (threadIdx.x == 0) atomicAdd(att_acc, (double)v);
+        }
+    }
+}
+
+// dA (in) -> dS (in place):  dS = A * (dA' - sum_n A*dA'),  dA' = dA + att_coef * W[n][t]
+__global__ void softmax_bwd_kernel(const float* __restrict__ A, long long ldA, float* __restrict__ dA, long long lddA,
+                                   int B, int T, int N, float att_coef, int maxN, int maxT, float g) {
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    const float inv_maxN = 1.f / (float)maxN, inv_maxT = 1.f / (float)maxT, inv_2g2 = 1.f / (2.f * g * g);
+    const long long rows = (long long)B * T;
+    for (long long row = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * wpb) {
+        const int b = (int)(row / T), t = (int)(row - (long long)b * T);
+        const float* ar = A + row * ldA;
+        float* dr = dA + row * lddA;
+        float dot = 0.f;
+        for (int n = lane; n < N; n += 32) {
+            float d = dr[n];
+            if (att_coef != 0.f && n < maxN && t < maxT) d += att_coef * guide_w(n, t, inv_maxN, inv_maxT, inv_2g2);
+            dr[n] = d;
+            dot += ar[n] * d;
+        }
+        dot = warp_sum(dot);
+        for (int n = lane; n < N; n += 32) dr[n] = ar[n] * (dr[n] - dot);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ embedding
+// modules.py:38-42: row 0 of the table reads as zeros and receives no gradient.
+__global__ void embed_fwd_kernel(const int* __restrict__ ids, const float* __restrict__ table, float* __restrict__ out,
+                                 long long ldo, int rows, int E) {
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (long long row = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * wpb) {
+        const int id = ids[row];
+        for (int c = lane; c < E; c += 32) out[row * ldo + c] = id == 0 ? 0.f : table[(long long)id * E + c];
+    }
+}
+__global__ void embed_bwd_kernel(const int* __restrict__ ids, const float* __restrict__ dout, long long ldo,
+                                 float* __restrict__ dtable, int rows, int E) {
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (long long row = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * wpb) {
+        const int id = ids[row];
+        if (id == 0) continue;
+        for (int c = lane; c < E; c += 32) atomicAdd(dtable + (long long)id * E + c, dout[row * ldo + c]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ losses
+// architectures.py:147-170 / :245-255.  acc[0..2] += sum|Y-t|, sum BCE(logits,t), sum (Y-t)^2.
+// dlogits = (w_l1*sign(Y-t)*Y' + w_bd*(Y-t) + w_l2*2(Y-t)*Y') / n   with Y' = Y(1-Y) (1 if not squashed)
+__global__ void recon_loss_kernel(const float* __restrict__ logits, long long ldl, const float* __restrict__ target,
+                                  long long ldt, float* __restrict__ dlogits, long long ldd,
+                                  long long rows, int C, int squash, float w_l1, float w_bd, float w_l2,
+                                  double* __restrict__ acc) {
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    const float inv_n = 1.f / ((float)rows * (float)C);
+    float s1 = 0.f, sb = 0.f, s2 = 0.f;
+    for (long long row = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * wpb) {
+        for (int c = lane; c < C; c += 32) {
+            const float x = logits[row * ldl + c], t = target[row * ldt + c];
+            const float y = squash ? sigmoidf_(x) : x;
+            const float d = y - t;
+            s1 += fabsf(d); s2 += d * d;
+            if (squash) sb += fmaxf(x, 0.f) - x * t + log1pf(__expf(-fabsf(x)));
+            if (dlogits) {
+                const float yp = squash ? y * (1.f - y) : 1.f;
+                const float sg = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+                float gsum = w_l1 * sg * yp + w_l2 * 2.f * d * yp;
+                if (squash) gsum += w_bd * d;
+                dlogits[row * ldd + c] = gsum * inv_n;
+            }
+        }
+    }
+    __shared__ float red[3][32];
+    s1 = warp_sum(s1); sb = warp_sum(sb); s2 = warp_sum(s2);
+    if (lane == 0) { red[0][threadIdx.x >> 5] = s1; red[1][threadIdx.x >> 5] = sb; red[2][threadIdx.x >> 5] = s2; }
+    __syncthreads();
+    if (threadIdx.x < 96) {
+        const int k = threadIdx.x >> 5;
+        float v = lane < wpb ? red[k][lane] : 0.f;
+        v = warp_sum(v);
+        if (lane == 0) atomicAdd(acc + k, (double)v);
+    }
+}
+
+// loss_components (architectures.py:173, :352-355): out = [loss, L1, BD, (att,) L2]
+__global__ void loss_finalize_kernel(const double* __restrict__ acc, float* __restrict__ out, double n_recon, double n_att,
+                                     float w_l1, float w_bd, float w_att, float w_l2, int has_att, int squash) {
+    const double l1 = acc[0] / n_recon, bd = squash ? acc[1] / n_recon : 0.0, l2 = acc[2] / n_recon;
+    const double att = has_att ? acc[3] / n_att : 0.0;
+    const double loss = w_l1 * l1 + w_bd * bd + w_att * att + w_l2 * l2;
+    out[0] = (float)loss; out[1] = (float)l1; out[2] = (float)bd;
+    if (has_att) { out[3] = (float)att; out[4] = (float)l2; } else { out[3] = (float)l2; }
+}
+
+// ------------------------------------------------------------------------------------------------ optimiser
+// architectures.py:101-128 + utils.py:167-170: Noam lr on step+1, TF Adam bias correction folded into lr_t.
+__global__ void adam_prepare_kernel(const long long* __restrict__ global_step, float* __restrict__ lr_t, float lr0,
+                                    float beta1, float beta2, int decay_lr, float warmup) {
+    const double t = (double)(*global_step + 1);
+    double lr = lr0;
+    if (decay_lr) lr = (double)lr0 * sqrt((double)warmup) * fmin(t * pow((double)warmup, -1.5), 1.0 / sqrt(t));
+    lr_t[0] = (float)(lr * sqrt(1.0 - pow((double)beta2, t)) / (1.0 - pow((double)beta1, t)));
+    lr_t[1] = (float)lr;
+}
+__global__ void step_inc_kernel(long long* global_step) { *global_step += 1; }
+
+// clip_by_value(g*grad_scale, +-clip) -> m,v update -> theta -= lr_t * m / (sqrt(v) + eps)   (TF epsilon placement)
+__global__ void adam_clip_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
+                                 const float* __restrict__ g, long long n, const float* __restrict__ lr_t,
+                                 float beta1, float beta2, float eps, float clip, float grad_scale) {
+    const float lr = lr_t[0];
+    const long long n4 = n >> 2;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float4 pg = reinterpret_cast<const float4*>(g)[i];
+        float4 pp = reinterpret_cast<float4*>(p)[i], pm = reinterpret_cast<float4*>(m)[i], pv = reinterpret_cast<float4*>(v)[i];
+        float* gg = &pg.x; float* ppp = &pp.x; float* mm = &pm.x; float* vv = &pv.x;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float gr = fminf(fmaxf(gg[e] * grad_scale, -clip), clip);
+            mm[e] = beta1 * mm[e] + (1.f - beta1) * gr;
+            vv[e] = beta2 * vv[e] + (1.f - beta2) * gr * gr;
+            ppp[e] -= lr * mm[e] / (sqrtf(vv[e]) + eps);
+        }
+        reinterpret_cast<float4*>(p)[i] = pp; reinterpret_cast<float4*>(m)[i] = pm; reinterpret_cast<float4*>(v)[i] = pv;
+    }
+    for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float gr = fminf(fmaxf(g[i] * grad_scale, -clip), clip);
+        const float mi = beta1 * m[i] + (1.f - beta1) * gr;
+        const float vi = beta2 * v[i] + (1.f - beta2) * gr * gr;
+        m[i] = mi; v[i] = vi;
+        p[i] -= lr * mi / (sqrtf(vi) + eps);
+    }
+}
+
+}  // namespace oph

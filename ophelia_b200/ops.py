@@ -1,0 +1,269 @@
+"""Tensor-level wrappers over the C ABI (include/ophelia_b200.h).
+
+torch is used for device memory and streams only; every arithmetic op below is one call into
+libophelia_sm100.so.  Activations are fp32 CUDA tensors `[B, time, C]` whose rows may be strided
+(`stride(-1) == 1`, `stride(0) == time * stride(1)`), which is how K/V, R/Q share buffers.
+"""
+import torch
+
+from . import _lib
+
+SAME, CAUSAL = 0, 1
+ACT_NONE, ACT_RELU = 0, 1
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _rows(t):
+    """(ld, B, L, C) of a [B, L, C] activation; checks the layout contract."""
+    assert t.is_cuda and t.dtype == torch.float32 and t.dim() == 3, "expected fp32 CUDA [B, time, C]"
+    B, L, C = t.shape
+    assert t.stride(2) == 1 and (B == 1 or t.stride(0) == L * t.stride(1)), "rows must be uniformly strided"
+    ld = t.stride(1)
+    assert ld % 4 == 0 and t.data_ptr() % 16 == 0, "rows must be 16-byte aligned"
+    return ld, B, L, C
+
+
+def _pad4(c):
+    return (c + 3) // 4 * 4
+
+
+def new_act(B, L, C, device):
+    """[B, L, C] view over a buffer whose row stride is padded to a multiple of 4 floats."""
+    ld = _pad4(C)
+    if ld == C:
+        return torch.empty(B, L, C, device=device, dtype=torch.float32)
+    return torch.zeros(B, L, ld, device=device, dtype=torch.float32)[:, :, :C]
+
+
+class PackedConv(object):
+    """Split-bf16 shared-memory images of one conv kernel (forward GEMM + input-gradient GEMM)."""
+
+    def __init__(self, w, deconv=False, need_bwd=True):
+        self.deconv = bool(deconv)
+        if deconv:
+            assert w.dim() == 4 and w.shape[0] == 1 and w.shape[1] == 3      # [1,3,Cout,Cin]
+            self.k, self.cout, self.cin = 3, int(w.shape[2]), int(w.shape[3])
+        else:
+            assert w.dim() == 3                                              # [k,Cin,Cout]
+            self.k, self.cin, self.cout = (int(s) for s in w.shape)
+        self.w = w
+        dev = w.device
+        self.fwd = torch.empty(_lib.pack_bytes(self.k, self.cin, self.cout, deconv, 0), dtype=torch.uint8, device=dev)
+        self.bwd = (torch.empty(_lib.pack_bytes(self.k, self.cin, self.cout, deconv, 1), dtype=torch.uint8, device=dev)
+                    if need_bwd else None)
+        self.repack()
+
+    def repack(self):
+        assert self.w.is_contiguous()
+        _lib.call("oph_conv_pack", _p(self.w), self.k, self.cin, self.cout, int(self.deconv), _p(self.fwd),
+                  _p(self.bwd), _stream())
+
+
+# ---------------------------------------------------------------------------------------------- conv1d
+def conv1d_fwd(x, pk, bias, gamma, beta, rate=1, padding=SAME, in_shift=0, act=ACT_NONE, norm=True,
+               drop_p=0.0, seed=0, step=None, save=False, y=None, want_sigmoid=False):
+    ldx, B, L, cin = _rows(x)
+    assert cin == pk.cin
+    cout = pk.cout
+    dev = x.device
+    z = new_act(B, L, cout, dev)
+    stats = torch.empty(B * L, 2, device=dev, dtype=torch.float32) if (save and norm) else None
+    if y is None:
+        y = new_act(B, L, cout, dev)
+    ysig = new_act(B, L, cout, dev) if want_sigmoid else None
+    _lib.call("oph_conv1d_fwd", _p(x), ldx, _p(pk.fwd), _p(bias), _p(gamma), _p(beta), _p(z), z.stride(1), _p(stats),
+              _p(y), y.stride(1), _p(ysig), ysig.stride(1) if ysig is not None else 0, B, L, cin, cout, pk.k, rate,
+              padding, in_shift, act, int(bool(norm)), float(drop_p), int(seed), _p(step), _stream())
+    return y, ysig, (z, stats)
+
+
+def conv1d_bwd(dy, x, saved, pk, gamma, beta, dw, dbias, dgamma, dbeta, rate=1, padding=SAME, in_shift=0,
+               act=ACT_NONE, norm=True, drop_p=0.0, seed=0, step=None, need_dx=True, dx=None):
+    z, stats = saved
+    ldx, B, L, cin = _rows(x)
+    lddy = _rows(dy)[0]
+    dev = x.device
+    dz = new_act(B, L, pk.cout, dev)
+    if need_dx and dx is None:
+        dx = new_act(B, L, cin, dev)
+    _lib.call("oph_conv1d_bwd", _p(dy), lddy, _p(x), ldx, _p(z), z.stride(1), _p(stats), _p(pk.bwd), _p(gamma),
+              _p(beta), _p(dz), dz.stride(1), _p(dx) if need_dx else None, dx.stride(1) if need_dx else 0, _p(dw),
+              _p(dbias), _p(dgamma), _p(dbeta), B, L, cin, pk.cout, pk.k, rate, padding, in_shift, act,
+              int(bool(norm)), float(drop_p), int(seed), _p(step), _stream())
+    return dx if need_dx else None
+
+
+# ---------------------------------------------------------------------------------------------- highway conv
+def hc_fwd(x, pk, bias, g1, b1, g2, b2, rate=1, padding=SAME, norm=True, drop_p=0.0, seed=0, step=None,
+           save=False, y=None):
+    ldx, B, L, C = _rows(x)
+    assert pk.cin == C and pk.cout == 2 * C
+    dev = x.device
+    z = torch.empty(B, L, 2 * C, device=dev, dtype=torch.float32)
+    stats = torch.empty(B * L, 4, device=dev, dtype=torch.float32) if (save and norm) else None
+    if y is None:
+        y = torch.empty(B, L, C, device=dev, dtype=torch.float32)
+    _lib.call("oph_hc_fwd", _p(x), ldx, _p(pk.fwd), _p(bias), _p(g1), _p(b1), _p(g2), _p(b2), _p(z), z.stride(1),
+              _p(stats), _p(y), y.stride(1), B, L, C, pk.k, rate, padding, int(bool(norm)), float(drop_p),
+              int(seed), _p(step), _stream())
+    return y, (z, stats)
+
+
+def hc_bwd(dy, x, saved, pk, g1, b1, g2, b2, dw, dbias, dg1, db1, dg2, db2, rate=1, padding=SAME, norm=True,
+           drop_p=0.0, seed=0, step=None, dx=None):
+    z, stats = saved
+    ldx, B, L, C = _rows(x)
+    lddy = _rows(dy)[0]
+    dev = x.device
+    dz = torch.empty(B, L, 2 * C, device=dev, dtype=torch.float32)
+    dxres = torch.empty(B, L, C, device=dev, dtype=torch.float32)
+    if dx is None:
+        dx = torch.empty(B, L, C, device=dev, dtype=torch.float32)
+    _lib.call("oph_hc_bwd", _p(dy), lddy, _p(x), ldx, _p(z), z.stride(1), _p(stats), _p(pk.bwd), _p(g1), _p(b1),
+              _p(g2), _p(b2), _p(dz), dz.stride(1), _p(dxres), dxres.stride(1), _p(dx), dx.stride(1), _p(dw),
+              _p(dbias), _p(dg1), _p(db1), _p(dg2), _p(db2), B, L, C, pk.k, rate, padding, int(bool(norm)),
+              float(drop_p), int(seed), _p(step), _stream())
+    return dx
+
+
+# ---------------------------------------------------------------------------------------------- transposed conv
+def deconv_fwd(x, pk, bias, gamma, beta, drop_p=0.0, seed=0, step=None, save=False):
+    ldx, B, L, C = _rows(x)
+    assert pk.deconv and pk.cin == C and pk.cout == C
+    dev = x.device
+    z = torch.empty(B, 2 * L, C, device=dev, dtype=torch.float32)
+    stats = torch.empty(B * 2 * L, 2, device=dev, dtype=torch.float32) if save else None
+    y = torch.empty(B, 2 * L, C, device=dev, dtype=torch.float32)
+    _lib.call("oph_deconv_fwd", _p(x), ldx, _p(pk.fwd), _p(bias), _p(gamma), _p(beta), _p(z), z.stride(1), _p(stats),
+              _p(y), y.stride(1), B, L, C, float(drop_p), int(seed), _p(step), _stream())
+    return y, (z, stats)
+
+
+def deconv_bwd(dy, x, saved, pk, gamma, beta, dw, dbias, dgamma, dbeta, drop_p=0.0, seed=0, step=None):
+    z, stats = saved
+    ldx, B, L, C = _rows(x)
+    lddy = _rows(dy)[0]
+    dev = x.device
+    dz = torch.empty(B, 2 * L, C, device=dev, dtype=torch.float32)
+    dx = torch.empty(B, L, C, device=dev, dtype=torch.float32)
+    _lib.call("oph_deconv_bwd", _p(dy), lddy, _p(x), ldx, _p(z), z.stride(1), _p(stats), _p(pk.bwd), _p(gamma),
+              _p(beta), _p(dz), dz.stride(1), _p(dx), dx.stride(1), _p(dw), _p(dbias), _p(dgamma), _p(dbeta),
+              B, L, C, float(drop_p), int(seed), _p(step), _stream())
+    return dx
+
+
+# ---------------------------------------------------------------------------------------------- embedding
+def embed_fwd(ids, table):
+    assert ids.dtype == torch.int32 and ids.is_contiguous()
+    B, N = ids.shape
+    E = table.shape[1]
+    out = torch.empty(B, N, E, device=table.device, dtype=torch.float32)
+    _lib.call("oph_embed_fwd", _p(ids), _p(table), _p(out), E, B * N, E, _stream())
+    return out
+
+
+def embed_bwd(ids, dout, dtable):
+    ld = _rows(dout)[0]
+    _lib.call("oph_embed_bwd", _p(ids), _p(dout), ld, _p(dtable), ids.numel(), dout.shape[2], _stream())
+
+
+# ---------------------------------------------------------------------------------------------- attention
+def attention_fwd(Q, K, V, R=None, prev_max=None, win=3, want_alignments=False, want_argmax=True, att_acc=None,
+                  maxN=1, maxT=1, g=0.2):
+    ldq, B, T, d = _rows(Q)
+    ldk, _, N, _ = _rows(K)
+    ldv = _rows(V)[0]
+    dev = Q.device
+    ldA = _pad4(N)
+    A = torch.zeros(B, T, ldA, device=dev, dtype=torch.float32)
+    if R is None:
+        R = torch.empty(B, T, d, device=dev, dtype=torch.float32)
+    align = torch.empty(B, N, T, device=dev, dtype=torch.float32) if want_alignments else None
+    argmax = torch.empty(B, T, device=dev, dtype=torch.int32) if want_argmax else None
+    _lib.call("oph_attention_fwd", _p(Q), ldq, _p(K), ldk, _p(V), ldv, _p(A), ldA, _p(R), R.stride(1), _p(align),
+              _p(argmax), _p(prev_max), int(win), _p(att_acc), int(maxN), int(maxT), float(g), B, T, N, d, _stream())
+    return R, A, align, argmax
+
+
+def attention_bwd(dR, Q, K, V, A, dq_addend=None, att_coef=0.0, maxN=1, maxT=1, g=0.2, dK=None, dV=None):
+    ldq, B, T, d = _rows(Q)
+    ldk, _, N, _ = _rows(K)
+    ldv = _rows(V)[0]
+    dev = Q.device
+    ldA = A.stride(1)
+    dA = torch.zeros_like(A)
+    if dq_addend is not None:   # may be a strided view (second half of the [R,Q] gradient): mirror its layout
+        _rows(dq_addend)
+        dQ = torch.empty_strided(dq_addend.shape, dq_addend.stride(), device=dev, dtype=torch.float32)
+    else:
+        dQ = torch.empty(B, T, d, device=dev, dtype=torch.float32)
+    if dK is None:
+        dK = torch.empty(B, N, d, device=dev, dtype=torch.float32)
+    if dV is None:
+        dV = torch.empty(B, N, d, device=dev, dtype=torch.float32)
+    _lib.call("oph_attention_bwd", _p(dR), _rows(dR)[0], _p(Q), ldq, _p(K), ldk, _p(V), ldv, _p(A), ldA, _p(dA),
+              _p(dQ), dQ.stride(1), _p(dq_addend), dq_addend.stride(1) if dq_addend is not None else 0,
+              _p(dK), dK.stride(1), _p(dV), dV.stride(1), float(att_coef), int(maxN), int(maxT), float(g),
+              B, T, N, d, _stream())
+    return dQ, dK, dV
+
+
+# ---------------------------------------------------------------------------------------------- losses / optimiser
+def recon_loss(logits, target, acc, squash, w_l1, w_bd, w_l2, want_grad=True):
+    ldl, B, L, C = _rows(logits)
+    ldt = target.stride(1)
+    assert target.stride(2) == 1 and target.dtype == torch.float32
+    dl = new_act(B, L, C, logits.device) if want_grad else None
+    _lib.call("oph_recon_loss", _p(logits), ldl, _p(target), ldt, _p(dl), dl.stride(1) if want_grad else 0,
+              B * L, C, int(bool(squash)), float(w_l1), float(w_bd), float(w_l2), _p(acc), _stream())
+    return dl
+
+
+def loss_finalize(acc, out, n_recon, n_att, w_l1, w_bd, w_att, w_l2, has_att, squash):
+    _lib.call("oph_loss_finalize", _p(acc), _p(out), float(n_recon), float(n_att), float(w_l1), float(w_bd),
+              float(w_att), float(w_l2), int(bool(has_att)), int(bool(squash)), _stream())
+
+
+def adam_prepare(global_step, lr_t, lr0, beta1, beta2, decay_lr, warmup=4000.0):
+    _lib.call("oph_adam_prepare", _p(global_step), _p(lr_t), float(lr0), float(beta1), float(beta2),
+              int(bool(decay_lr)), float(warmup), _stream())
+
+
+def adam_clip(p, m, v, g, lr_t, beta1, beta2, eps, clip=1.0, grad_scale=1.0):
+    _lib.call("oph_adam_clip", _p(p), _p(m), _p(v), _p(g), p.numel(), _p(lr_t), float(beta1), float(beta2),
+              float(eps), float(clip), float(grad_scale), _stream())
+
+
+def step_inc(global_step):
+    _lib.call("oph_step_inc", _p(global_step), _stream())
+
+
+# ---------------------------------------------------------------------------------------------- raw GEMM (tests)
+def gemm_nt(A, Bm, b_mode=1, bias=None, alpha=1.0):
+    """A [.., M, K] @ (Bm [.., N, K]^T if b_mode == 1 else Bm [.., K, N])."""
+    batched = A.dim() == 3
+    A3 = A if batched else A[None]
+    B3 = Bm if batched else Bm[None]
+    nb, M, K = A3.shape
+    N = B3.shape[1] if b_mode == 1 else B3.shape[2]
+    C = torch.zeros(nb, M, _pad4(N), device=A.device, dtype=torch.float32)
+    _lib.call("oph_gemm_nt", _p(A3), A3.stride(1), _p(B3), B3.stride(1), _p(C), C.stride(1), _p(bias), M, N, K, b_mode,
+              float(alpha), nb, A3.stride(0), B3.stride(0), C.stride(0), _stream())
+    C = C[:, :, :N]
+    return C if batched else C[0]
+
+
+def gemm_tn(A, Bm, splits=1):
+    """A [R, M]^T @ Bm [R, N] with split-K atomics."""
+    R, M = A.shape
+    N = Bm.shape[1]
+    C = torch.zeros(M, _pad4(N), device=A.device, dtype=torch.float32)
+    _lib.call("oph_gemm_tn", _p(A), A.stride(0), _p(Bm), Bm.stride(0), _p(C), C.stride(0), M, N, R, int(splits), _stream())
+    return C[:, :N]
