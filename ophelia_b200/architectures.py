@@ -1,0 +1,333 @@
+"""Graph classes with the reference's constructor and attribute surface (`architectures.py:12-362`):
+`Text2MelGraph(hp, mode, reuse)`, `SSRNGraph(hp, mode, reuse)` with attributes L, mels, mags, K, V, Q, R,
+alignments, max_attentions, Y_logits, Y, Z_logits, Z, loss, loss_components, train_op, global_step, num_batch,
+prev_max_attentions.  Attributes are symbolic `Node`s evaluated by `Session.run(fetches, feed_dict)` (session.py),
+so the reference's drivers keep their call sites:
+
+    gs, loss_components, _ = sess.run([g.global_step, g.loss_components, g.train_op])              # train.py:273
+    _Y, _max, _ali = sess.run([g.Y, g.max_attentions, g.alignments], {g.K: K, g.V: V, g.mels: Y,
+                                                                     g.prev_max_attentions: prev})  # synthesize.py:182
+
+Execution is eager on CUDA; one training step = forward (tape), fused losses, explicit backward, allreduce (DP),
+clip + TF-Adam, all in kernels of libophelia_sm100.so.
+"""
+import numpy as np
+import torch
+
+from . import ops
+from .modules import Tape
+from .networks import SSRN, Attention, AudioDec, AudioEnc, TextEnc
+from .variables import VariableStore, use_store, variable_scope
+
+_default_stores = {}
+
+
+def _conv_specs(out, prefix, name, k, cin, cout, norm=True):
+    s = "%s/%s" % (prefix, name)
+    out.append((s + "/conv1d/kernel", (k, cin, cout), "kernel"))
+    out.append((s + "/conv1d/bias", (cout,), "zeros"))
+    if norm:
+        out.append((s + "/normalize/beta", (cout,), "zeros"))
+        out.append((s + "/normalize/gamma", (cout,), "ones"))
+
+
+def _hc_specs(out, prefix, name, k, c, norm=True):
+    s = "%s/%s" % (prefix, name)
+    out.append((s + "/conv1d/kernel", (k, c, 2 * c), "kernel"))
+    out.append((s + "/conv1d/bias", (2 * c,), "zeros"))
+    if norm:
+        for h in ("H1", "H2"):
+            out.append((s + "/%s/beta" % h, (c,), "zeros"))
+            out.append((s + "/%s/gamma" % h, (c,), "ones"))
+
+
+def text2mel_variables(hp):
+    """Creation-ordered variable inventory of `Text2MelGraph` (TF names; 209 variables / 23 974 512 values for
+    the LJ configs, cf. the structural known answers at train.py:194)."""
+    V, e, d, nm, nrm = len(hp.vocab), hp.e, hp.d, hp.n_mels, hp.norm == 'layer'
+    out = [("Text2Mel/TextEnc/embed_1/lookup_table", (V, e), "embed")]
+    p = "Text2Mel/TextEnc"
+    _conv_specs(out, p, "C_2", 1, e, 2 * d, nrm)
+    _conv_specs(out, p, "C_3", 1, 2 * d, 2 * d, nrm)
+    for i in range(4, 14):
+        _hc_specs(out, p, "HC_%d" % i, 3, 2 * d, nrm)
+    for i in range(14, 16):
+        _hc_specs(out, p, "HC_%d" % i, 1, 2 * d, nrm)
+    p = "Text2Mel/AudioEnc"
+    _conv_specs(out, p, "C_1", 1, nm, d, nrm)
+    _conv_specs(out, p, "C_2", 1, d, d, nrm)
+    _conv_specs(out, p, "C_3", 1, d, d, nrm)
+    for i in range(4, 14):
+        _hc_specs(out, p, "HC_%d" % i, 3, d, nrm)
+    p = "Text2Mel/AudioDec"
+    _conv_specs(out, p, "C_1", 1, 2 * d if hp.concatenate_query else d, d, nrm)
+    for i in range(2, 8):
+        _hc_specs(out, p, "HC_%d" % i, 3, d, nrm)
+    for i in range(8, 11):
+        _conv_specs(out, p, "C_%d" % i, 1, d, d, nrm)
+    _conv_specs(out, p, "C_11", 1, d, nm, nrm)
+    return out
+
+
+def ssrn_variables(hp):
+    c, nm, F, nrm = hp.c, hp.n_mels, hp.full_dim, hp.norm == 'layer'
+    out, p, i = [], "SSRN", 1
+    _conv_specs(out, p, "C_%d" % i, 1, nm, c, nrm); i += 1
+    for _ in range(2):
+        _hc_specs(out, p, "HC_%d" % i, 3, c, nrm); i += 1
+    for _ in range({4: 2, 8: 3}[hp.r]):
+        s = "%s/D_%d" % (p, i); i += 1
+        out.append((s + "/conv2d_transpose/kernel", (1, 3, c, c), "kernel_t"))
+        out.append((s + "/conv2d_transpose/bias", (c,), "zeros"))
+        out.append((s + "/normalize/beta", (c,), "zeros"))
+        out.append((s + "/normalize/gamma", (c,), "ones"))
+        for _ in range(2):
+            _hc_specs(out, p, "HC_%d" % i, 3, c, nrm); i += 1
+    _conv_specs(out, p, "C_%d" % i, 1, c, 2 * c, nrm); i += 1
+    for _ in range(2):
+        _hc_specs(out, p, "HC_%d" % i, 3, 2 * c, nrm); i += 1
+    _conv_specs(out, p, "C_%d" % i, 1, 2 * c, F, nrm); i += 1
+    for _ in range(3):
+        _conv_specs(out, p, "C_%d" % i, 1, F, F, nrm); i += 1
+    return out
+
+
+class Node(object):
+    """Symbolic handle standing in for a tf.Tensor / tf.placeholder / tf.Operation of the reference graph."""
+    __slots__ = ("graph", "name")
+
+    def __init__(self, graph, name):
+        self.graph, self.name = graph, name
+
+    def __repr__(self):
+        return "<Node %s/%s>" % (type(self.graph).__name__, self.name)
+
+
+def _loss_weights(hp, which):
+    lw = getattr(hp, "loss_weights", None)
+    if which == "t2m":
+        if lw and "t2m" in lw:                                   # architectures.py:325-331
+            w = lw["t2m"]
+            return w["L1"], w["binary_divergence"], w["attention"], w["L2"]
+        return hp.lw_mel, hp.lw_bd1, hp.lw_att, hp.lw_t2m_l2     # :333-340
+    if lw and "ssrn" in lw:                                      # :156-160
+        w = lw["ssrn"]
+        return w["L1"], w["binary_divergence"], 0.0, w["L2"]
+    return hp.lw_mag, hp.lw_bd2, 0.0, hp.lw_ssrn_l2              # :163-166
+
+
+class Graph(object):
+    """architectures.py:12-131.  `reuse=True` shares the variable store of the graph built first for the same
+    model (train.py:187-189 builds train / synthesize / generate_attention graphs over one set of weights)."""
+    scope_name = None
+    node_names = ()
+
+    def __init__(self, hp, mode="train", reuse=None, store=None, data=None, device=None, process_group=None):
+        assert mode in ['train', 'synthesize', 'generate_attention']
+        self.mode = mode
+        self.training = True if mode == "train" else False
+        self.reuse = reuse
+        self.hp = hp
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.process_group = process_group
+        key = (self.scope_name, str(self.device))
+        if store is None:
+            store = _default_stores.get(key) if reuse else None
+            if store is None:
+                store = VariableStore(self.device, seed=getattr(hp, "seed", 0))
+                _default_stores[key] = store
+        self.store = store
+        self.store.declare_all(self.variable_specs(hp))
+        self.store.finalize(with_optimizer=self.training)
+        for n in self.node_names:
+            setattr(self, n, Node(self, n))
+        self.add_data(data)
+        if self.training:
+            self.build_training_scheme()
+
+    # ---- data (architectures.py:28-93): training batches come from an iterator of host dicts
+    #      {'text': int32 [B,N], 'mel': fp32 [B,T,n_mels], 'mag': fp32 [B,T*r,full_dim]} (data_load.get_batch contract)
+    def add_data(self, data):
+        self.batch_source = None
+        self.num_batch = 0
+        if self.mode == 'train':
+            if data is None:
+                data = getattr(self.hp, "batch_source", None)
+            assert data is not None, "training graphs need `data=` (iterator of host batches) or hp.batch_source"
+            self.batch_source = iter(data)
+            self.num_batch = getattr(data, "num_batch", getattr(self.hp, "num_batch", 1))
+
+    def build_training_scheme(self):
+        hp = self.hp
+        assert not hp.update_weights, "hp.update_weights (partial fine-tuning) is outside the path"
+        self.lr0 = hp.lr
+
+    # ---- optimiser step shared by both models (architectures.py:110-128)
+    def _apply_gradients(self):
+        hp, st = self.hp, self.store
+        scale = 1.0
+        if self.process_group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(st.grad_flat, group=self.process_group)      # NCCL sum over NVLink; only collective
+            scale = 1.0 / dist.get_world_size(self.process_group)
+        ops.adam_prepare(st.global_step, st.lr_t, hp.lr, hp.beta1, hp.beta2, hp.decay_lr)
+        ops.adam_clip(st.flat, st.m_flat, st.v_flat, st.grad_flat, st.lr_t, hp.beta1, hp.beta2, hp.epsilon, 1.0, scale)
+        ops.step_inc(st.global_step)
+        st.version += 1
+
+    def _to_device(self, x, dtype):
+        if isinstance(x, torch.Tensor):
+            return x.to(self.device, dtype, non_blocking=True)
+        return torch.as_tensor(np.ascontiguousarray(x)).to(self.device, dtype, non_blocking=True)
+
+
+# ====================================================================================================== SSRN
+class SSRNGraph(Graph):
+    scope_name = "SSRN"
+    node_names = ("mels", "mags", "Z_logits", "Z", "loss", "loss_components", "train_op", "global_step")
+
+    def variable_specs(self, hp):
+        return ssrn_variables(hp)
+
+    def get_batchsize(self):
+        return self.hp.batchsize['ssrn']
+
+    def build_model(self, mels, training):
+        with use_store(self.store), variable_scope("SSRN"):
+            return SSRN(self.hp, mels, training=training, speaker_codes=None, reuse=self.reuse)
+
+    def forward(self, feeds):
+        mels = self._to_device(feeds["mels"], torch.float32)
+        logits, Z = self.build_model(mels, False)
+        return {"mels": mels, "Z_logits": logits, "Z": Z}
+
+    def train_step(self, batch=None):
+        hp, st = self.hp, self.store
+        if batch is None:
+            batch = next(self.batch_source)
+        mels = self._to_device(batch["mel"], torch.float32)
+        mags = self._to_device(batch["mag"], torch.float32)
+        return self.train_step_device(mels, mags)
+
+    def train_step_device(self, mels, mags):
+        hp, st = self.hp, self.store
+        mels._oph_no_grad = True
+        st.grad_flat.zero_()
+        acc = torch.zeros(4, dtype=torch.float64, device=self.device)
+        with Tape() as tape:
+            logits, Z = self.build_model(mels, True)
+        w1, wbd, _, w2 = _loss_weights(hp, "ssrn")
+        squash = hp.squash_output_ssrn
+        dlogits = ops.recon_loss(logits, mags, acc, squash, w1, wbd if squash else 0.0, w2)
+        comps = torch.empty(4, device=self.device, dtype=torch.float32)
+        ops.loss_finalize(acc, comps, logits.shape[0] * logits.shape[1] * logits.shape[2], 1.0, w1, wbd, 0.0, w2,
+                          False, squash)
+        tape.backward(dlogits)
+        self._apply_gradients()
+        return comps
+
+
+# ====================================================================================================== Text2Mel
+class Text2MelGraph(Graph):
+    scope_name = "Text2Mel"
+    node_names = ("L", "mels", "prev_max_attentions", "K", "V", "Q", "R", "alignments", "max_attentions",
+                  "Y_logits", "Y", "loss", "loss_components", "train_op", "global_step")
+
+    def variable_specs(self, hp):
+        assert hp.text_encoder_type == 'DCTTS_standard' and hp.history_type == 'DCTTS_standard' \
+            and not hp.use_external_durations, "label-input / fixed-attention variants are outside the path"
+        return text2mel_variables(hp)
+
+    def get_batchsize(self):
+        return self.hp.batchsize['t2m']
+
+    # architectures.py:188-239
+    def build_model(self, L, mels, training, K=None, V=None, prev_max_attentions=None, att_acc=None,
+                    want_alignments=True, tapes=None):
+        hp = self.hp
+        mono = self.mode == 'synthesize'
+        out = {}
+        t_text, t_aenc, t_dec = tapes if tapes else (None, None, None)
+
+        def on(tape):
+            return tape if tape is not None else _NullCtx()
+        with use_store(self.store), variable_scope("Text2Mel"):
+            # S = mels shifted one frame to the right (:191) is folded into AudioEnc C_1 (in_shift=1)
+            if K is None:
+                with variable_scope("TextEnc"), on(t_text):
+                    K, V = TextEnc(hp, L, training=training, speaker_codes=None, reuse=self.reuse)
+            with variable_scope("AudioEnc"), on(t_aenc):
+                Q = AudioEnc(hp, mels, training=training, speaker_codes=None, reuse=self.reuse, in_shift=1)
+            with variable_scope("Attention"), on(t_dec):
+                R, alignments, max_attentions = Attention(
+                    hp, Q, K, V, monotonic_attention=mono, prev_max_attentions=prev_max_attentions if mono else None,
+                    training=training, att_acc=att_acc, want_alignments=want_alignments)
+            with variable_scope("AudioDec"), on(t_dec):
+                Y_logits, Y = AudioDec(hp, R, training=training, speaker_codes=None, reuse=self.reuse)
+        out.update(K=K, V=V, Q=Q, R=R, alignments=alignments, max_attentions=max_attentions, Y_logits=Y_logits, Y=Y)
+        return out
+
+    def encode_text(self, feeds):
+        L = self._to_device(feeds["L"], torch.int32)
+        with use_store(self.store), variable_scope("Text2Mel"), variable_scope("TextEnc"):
+            K, V = TextEnc(self.hp, L, training=False, speaker_codes=None, reuse=self.reuse)
+        return {"L": L, "K": K, "V": V}
+
+    def forward(self, feeds, want_alignments=True):
+        mels = self._to_device(feeds["mels"], torch.float32)
+        K = V = L = prev = None
+        if "K" in feeds:
+            K = self._to_device(feeds["K"], torch.float32)
+            V = self._to_device(feeds["V"], torch.float32)
+        else:
+            L = self._to_device(feeds["L"], torch.int32)
+        if self.mode == 'synthesize':
+            prev = self._to_device(feeds["prev_max_attentions"], torch.int32)
+        out = self.build_model(L, mels, False, K=K, V=V, prev_max_attentions=prev, want_alignments=want_alignments)
+        out["mels"] = mels
+        return out
+
+    def train_step(self, batch=None):
+        if batch is None:
+            batch = next(self.batch_source)
+        L = self._to_device(batch["text"], torch.int32)
+        mels = self._to_device(batch["mel"], torch.float32)
+        return self.train_step_device(L, mels)
+
+    def train_step_device(self, L, mels):
+        """One `sess.run([global_step, loss_components, train_op])` with inputs already on the device.
+        Returns loss_components [loss, L1, BD, att, L2] as a device tensor (architectures.py:352-355)."""
+        hp, st = self.hp, self.store
+        assert not hp.attention_guide_dir and not hp.attention_guide_fa, \
+            "per-utterance / MSE attention guides are outside the path (global analytic guide only)"
+        assert hp.lw_cdp == 0.0 and hp.lw_ain == 0.0 and hp.lw_aout == 0.0
+        mels._oph_no_grad = True
+        st.grad_flat.zero_()
+        acc = torch.zeros(4, dtype=torch.float64, device=self.device)
+        tapes = (Tape(), Tape(), Tape())
+        out = self.build_model(L, mels, True, att_acc=acc[3:], want_alignments=False, tapes=tapes)
+        w1, wbd, watt, w2 = _loss_weights(hp, "t2m")
+        squash = hp.squash_output_t2m
+        logits = out["Y_logits"]
+        B, T, nm = logits.shape
+        N = L.shape[1]
+        n_att = float(B * min(N, hp.max_N) * min(T, hp.max_T))        # mask_sum of architectures.py:266-268
+        dlogits = ops.recon_loss(logits, mels, acc, squash, w1, wbd if squash else 0.0, w2)
+        comps = torch.empty(5, device=self.device, dtype=torch.float32)
+        ops.loss_finalize(acc, comps, B * T * nm, n_att, w1, wbd, watt, w2, True, squash)
+        # backward: AudioDec -> Attention -> (AudioEnc, TextEnc)
+        t_text, t_aenc, t_dec = tapes
+        dRp = t_dec.backward(dlogits)
+        dQ, dKV = out["R"]._oph_attention_bwd(dRp, watt / n_att)
+        t_aenc.backward(dQ)
+        t_text.backward(dKV)
+        self._apply_gradients()
+        return comps
+
+
+class _NullCtx(object):
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False

@@ -1,0 +1,195 @@
+"""Network stacks with the reference's names, arguments and return tuples (`networks.py:121-537`):
+TextEnc, AudioEnc, Attention, AudioDec, SSRN.  Layer order, scope names (= checkpoint variable prefixes) and
+padding modes follow the reference line by line; the speaker-embedding / Merlin-label branches
+(`hp.multispeaker`, `MerlinTextEnc`, `FixedAttention`, `LinearTransformLabels`) are outside this path.
+"""
+import sys
+
+import torch
+
+from . import ops
+from .modules import Tape, _record, conv1d, conv1d_transpose, embed, hc, relu
+
+
+def _no_speakers(hp, speaker_codes):
+    assert not getattr(hp, "multispeaker", []), "multispeaker variants are outside the B200 hot path (SURVEY 8f)"
+
+
+def TextEnc(hp, L, training=True, speaker_codes=None, reuse=None):
+    '''
+    Args:
+      L: Text inputs. (B, N) int32
+    Return:
+      K: Keys. (B, N, d)     V: Values. (B, N, d)   -- two views of one (B, N, 2d) buffer (tf.split, networks.py:211)
+    '''
+    _no_speakers(hp, speaker_codes)
+    i = 1
+    tensor = embed(L, vocab_size=len(hp.vocab), num_units=hp.e, scope="embed_{}".format(i), reuse=reuse); i += 1
+    tensor = conv1d(tensor, filters=2 * hp.d, size=1, rate=1, dropout_rate=hp.dropout_rate, activation_fn=relu,
+                    training=training, scope="C_{}".format(i), normtype=hp.norm, reuse=reuse); i += 1
+    tensor = conv1d(tensor, size=1, rate=1, dropout_rate=hp.dropout_rate, training=training,
+                    scope="C_{}".format(i), normtype=hp.norm, reuse=reuse); i += 1
+    for _ in range(2):
+        for j in range(4):
+            tensor = hc(tensor, size=3, rate=3 ** j, dropout_rate=hp.dropout_rate, activation_fn=None,
+                        training=training, scope="HC_{}".format(i), normtype=hp.norm, reuse=reuse); i += 1
+    for _ in range(2):
+        tensor = hc(tensor, size=3, rate=1, dropout_rate=hp.dropout_rate, activation_fn=None, training=training,
+                    scope="HC_{}".format(i), normtype=hp.norm, reuse=reuse); i += 1
+    for _ in range(2):
+        tensor = hc(tensor, size=1, rate=1, dropout_rate=hp.dropout_rate, activation_fn=None, training=training,
+                    scope="HC_{}".format(i), normtype=hp.norm, reuse=reuse); i += 1
+    d = tensor.shape[-1] // 2
+    K, V = tensor[:, :, :d], tensor[:, :, d:]
+    K._oph_kv = V._oph_kv = tensor
+    return K, V
+
+
+def AudioEnc(hp, S, training=True, speaker_codes=None, reuse=None, *, in_shift=0):
+    '''
+    Args:
+      S: melspectrogram. (B, T/r, n_mels).  With in_shift=1 the caller passes the un-shifted mels and the
+         one-frame delay of architectures.py:191 is folded into the first layer's row addressing.
+    Returns
+      Q: Queries. (B, T/r, d) -- written straight into the second half of the [R, Q] decoder input buffer
+    '''
+    _no_speakers(hp, speaker_codes)
+    i = 1
+    tensor = conv1d(S, filters=hp.d, size=1, rate=1, padding="CAUSAL", dropout_rate=hp.dropout_rate,
+                    activation_fn=relu, training=training, scope="C_{}".format(i), normtype=hp.norm, reuse=reuse,
+                    in_shift=in_shift); i += 1
+    tensor = conv1d(tensor, size=1, rate=1, padding="CAUSAL", dropout_rate=hp.dropout_rate, activation_fn=relu,
+                    training=training, scope="C_{}".format(i), normtype=hp.norm, reuse=reuse); i += 1
+    tensor = conv1d(tensor, size=1, rate=1, padding="CAUSAL", dropout_rate=hp.dropout_rate, training=training,
+                    scope="C_{}".format(i), normtype=hp.norm, reuse=reuse); i += 1
+    for _ in range(2):
+        for j in range(4):
+            tensor = hc(tensor, size=3, rate=3 ** j, padding="CAUSAL", dropout_rate=hp.dropout_rate,
+                        training=training, scope="HC_{}".format(i), normtype=hp.norm, reuse=reuse); i += 1
+    rq = None
+    for n in range(2):
+        out = None
+        if n == 1 and getattr(hp, "concatenate_query", True):
+            B, T, d = tensor.shape
+            rq = torch.empty(B, T, 2 * d, device=tensor.device, dtype=torch.float32)
+            out = rq[:, :, d:]
+        tensor = hc(tensor, size=3, rate=3, padding="CAUSAL", dropout_rate=hp.dropout_rate, training=training,
+                    scope="HC_{}".format(i), normtype=hp.norm, reuse=reuse, out=out); i += 1
+    if rq is not None:
+        tensor._oph_rq = rq
+    return tensor
+
+
+def Attention(hp, Q, K, V, monotonic_attention=False, prev_max_attentions=None, *, training=False, att_acc=None,
+              want_alignments=True):
+    '''
+    Args:
+      Q: Queries. (B, T/r, d)   K: Keys. (B, N, d)   V: Values. (B, N, d)
+      monotonic_attention: A boolean. At training, it is False.
+      prev_max_attentions: (B,). At training, it is set to None.
+    Returns:
+      R: [Context Vectors; Q]. (B, T/r, 2d)   alignments: (B, N, T/r)   max_attentions: (B, T/r)
+    '''
+    B, T, d = Q.shape
+    N = K.shape[1]
+    prev = None
+    if monotonic_attention:
+        if getattr(hp, "turn_off_monotonic_for_synthesis", False):
+            raise NotImplementedError("turn_off_monotonic_for_synthesis needs hp.text_lengths (outside the path)")
+        assert N == hp.max_N and T == hp.max_T, "networks.py:304-311 builds the mask with hp.max_N / hp.max_T"
+        prev = prev_max_attentions.to(torch.int32).contiguous()
+    concat = getattr(hp, "concatenate_query", True)
+    rq = getattr(Q, "_oph_rq", None) if concat else None
+    if concat and rq is None:                       # Q did not come from AudioEnc: build the [R, Q] buffer here
+        rq = torch.empty(B, T, 2 * d, device=Q.device, dtype=torch.float32)
+        rq[:, :, d:].copy_(Q)
+        Q = rq[:, :, d:]
+    R_out = rq[:, :, :d] if concat else None
+    R, A, alignments, max_attentions = ops.attention_fwd(
+        Q, K, V, R=R_out, prev_max=prev, win=hp.attention_win_size, want_alignments=want_alignments,
+        att_acc=att_acc, maxN=hp.max_N, maxT=hp.max_T, g=hp.g)
+    result = rq if concat else R
+    if training and Tape.current is not None:
+        kv = getattr(K, "_oph_kv", None)
+
+        def bwd(dRp, att_coef=0.0):
+            dKV = torch.empty(B, N, 2 * d, device=Q.device, dtype=torch.float32)
+            dR = dRp[:, :, :d] if concat else dRp
+            dq_add = dRp[:, :, d:] if concat else None
+            dQ, _dK, _dV = ops.attention_bwd(dR, Q, K, V, A, dq_addend=dq_add, att_coef=att_coef, maxN=hp.max_N,
+                                             maxT=hp.max_T, g=hp.g, dK=dKV[:, :, :d], dV=dKV[:, :, d:])
+            return dQ, dKV
+        result._oph_attention_bwd = bwd
+    return result, alignments, max_attentions
+
+
+def AudioDec(hp, R, training=True, speaker_codes=None, reuse=None):
+    '''
+    Args:
+      R: [Context Vectors; Q]. (B, T/r, 2d)
+    Returns:
+      logits, Y: Melspectrogram predictions. (B, T/r, n_mels)
+    '''
+    _no_speakers(hp, speaker_codes)
+    i = 1
+    tensor = conv1d(R, filters=hp.d, size=1, rate=1, padding="CAUSAL", dropout_rate=hp.dropout_rate,
+                    training=training, scope="C_{}".format(i), normtype=hp.norm, reuse=reuse); i += 1
+    for j in range(4):
+        tensor = hc(tensor, size=3, rate=3 ** j, padding="CAUSAL", dropout_rate=hp.dropout_rate, training=training,
+                    scope="HC_{}".format(i), normtype=hp.norm, reuse=reuse); i += 1
+    for _ in range(2):
+        tensor = hc(tensor, size=3, rate=1, padding="CAUSAL", dropout_rate=hp.dropout_rate, training=training,
+                    scope="HC_{}".format(i), normtype=hp.norm, reuse=reuse); i += 1
+    for _ in range(3):
+        tensor = conv1d(tensor, size=1, rate=1, padding="CAUSAL", dropout_rate=hp.dropout_rate, activation_fn=relu,
+                        training=training, scope="C_{}".format(i), normtype=hp.norm, reuse=reuse); i += 1
+    # mel_hats
+    squash = hp.squash_output_t2m
+    out = conv1d(tensor, filters=hp.n_mels, size=1, rate=1, padding="CAUSAL", dropout_rate=hp.dropout_rate,
+                 training=training, scope="C_{}".format(i), normtype=hp.norm, reuse=reuse,
+                 want_sigmoid=squash); i += 1
+    logits, Y = out if squash else (out, out)
+    return logits, Y
+
+
+def SSRN(hp, Y, training=True, speaker_codes=None, reuse=None):
+    '''
+    Args:
+      Y: Melspectrogram Predictions. (B, T/r, n_mels)
+    Returns:
+      logits, Z: Spectrogram Predictions. (B, T, 1+n_fft/2)
+    '''
+    _no_speakers(hp, speaker_codes)
+    i = 1
+    tensor = conv1d(Y, filters=hp.c, size=1, rate=1, dropout_rate=hp.dropout_rate, training=training,
+                    scope="C_{}".format(i), normtype=hp.norm, reuse=reuse); i += 1
+    for j in range(2):
+        tensor = hc(tensor, size=3, rate=3 ** j, dropout_rate=hp.dropout_rate, training=training,
+                    scope="HC_{}".format(i), normtype=hp.norm, reuse=reuse); i += 1
+    if hp.r == 4:
+        n_transposes = 2
+    elif hp.r == 8:
+        n_transposes = 3
+    else:
+        sys.exit('reduction factor not handled by SSRN!')
+    for _ in range(n_transposes):
+        tensor = conv1d_transpose(tensor, scope="D_{}".format(i), dropout_rate=hp.dropout_rate, training=training,
+                                  reuse=reuse); i += 1
+        for j in range(2):
+            tensor = hc(tensor, size=3, rate=3 ** j, dropout_rate=hp.dropout_rate, training=training,
+                        scope="HC_{}".format(i), normtype=hp.norm, reuse=reuse); i += 1
+    tensor = conv1d(tensor, filters=2 * hp.c, size=1, rate=1, dropout_rate=hp.dropout_rate, training=training,
+                    scope="C_{}".format(i), normtype=hp.norm, reuse=reuse); i += 1
+    for _ in range(2):
+        tensor = hc(tensor, size=3, rate=1, dropout_rate=hp.dropout_rate, training=training,
+                    scope="HC_{}".format(i), normtype=hp.norm, reuse=reuse); i += 1
+    tensor = conv1d(tensor, filters=hp.full_dim, size=1, rate=1, dropout_rate=hp.dropout_rate, training=training,
+                    scope="C_{}".format(i), normtype=hp.norm, reuse=reuse); i += 1
+    for _ in range(2):
+        tensor = conv1d(tensor, size=1, rate=1, dropout_rate=hp.dropout_rate, activation_fn=relu, training=training,
+                        scope="C_{}".format(i), normtype=hp.norm, reuse=reuse); i += 1
+    squash = hp.squash_output_ssrn
+    out = conv1d(tensor, size=1, rate=1, dropout_rate=hp.dropout_rate, training=training, scope="C_{}".format(i),
+                 normtype=hp.norm, reuse=reuse, want_sigmoid=squash)
+    logits, Z = out if squash else (out, out)
+    return logits, Z

@@ -1,0 +1,67 @@
+"""`Session.run(fetches, feed_dict)` over the Graph attribute surface, so that the reference's drivers
+(`train.py:273`, `train.py:60-67`, `synthesize.py:83-96,172-183,234-239,259`, `copy_synth_SSRN_GL.py:34-41`)
+keep their call sites.  Arrays cross the boundary as numpy, like `tf.Session.run` (host buffers in, host out).
+"""
+import numpy as np
+import torch
+
+from .architectures import Node, SSRNGraph, Text2MelGraph
+
+
+class Session(object):
+    def __init__(self, *args, **kwargs):
+        pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+    def close(self):
+        pass
+
+    def run(self, fetches, feed_dict=None):
+        single = isinstance(fetches, Node)
+        flat = [fetches] if single else list(fetches)
+        nodes = []
+        for f in flat:
+            nodes.extend(f if isinstance(f, (list, tuple)) else [f])
+        graphs = {id(n.graph): n.graph for n in nodes}
+        assert len(graphs) == 1, "one Session.run call evaluates nodes of one graph"
+        g = next(iter(graphs.values()))
+        feeds = {}
+        for k, v in (feed_dict or {}).items():
+            assert isinstance(k, Node) and k.graph is g, "feed_dict keys must be nodes of the fetched graph"
+            feeds[k.name] = v
+        values = self._evaluate(g, set(n.name for n in nodes), feeds)
+        out = [values[f.name] for f in flat]
+        return out[0] if single else out
+
+    @staticmethod
+    def _host(t):
+        if t is None:
+            return None
+        a = t.detach().cpu().numpy()
+        return a.astype(np.int64) if a.dtype == np.int32 else a
+
+    def _evaluate(self, g, names, feeds):
+        if "train_op" in names or "loss" in names or "loss_components" in names:
+            assert g.training, "loss/train_op exist only on mode='train' graphs"
+            gs = int(g.store.global_step.item()) if "global_step" in names else None   # value before the step (tf semantics of fetching alongside train_op are unordered; the reference only logs it)
+            comps = g.train_step().cpu().numpy()
+            return {"train_op": None, "loss": float(comps[0]), "loss_components": [float(c) for c in comps],
+                    "global_step": gs if gs is None else gs + 1}
+        if names == {"global_step"}:
+            return {"global_step": int(g.store.global_step.item())}
+        if isinstance(g, SSRNGraph):
+            out = g.forward(feeds)
+        elif isinstance(g, Text2MelGraph):
+            if names <= {"K", "V"} and "K" not in feeds:
+                out = g.encode_text(feeds)
+            else:
+                out = g.forward(feeds, want_alignments="alignments" in names)
+        else:
+            raise TypeError(type(g))
+        torch.cuda.current_stream().synchronize()
+        return {n: self._host(out[n]) for n in names}

@@ -1,0 +1,117 @@
+"""Synthesis drivers with the reference's names and semantics (`synthesize.py:62-260`):
+synth_text2mel, synth_codedtext2mel, encode_text, get_text_lengths, synth_mel2mag (+ split_batch).
+
+Two routes produce identical results:
+  * the Session route keeps the reference's call pattern (one `sess.run` per mel frame, numpy in/out);
+  * `synth_codedtext2mel_device` keeps Y / alignments / prev_max_attentions resident in HBM and only reads the
+    B argmax values back per frame for the reference's end-of-sentence test.
+Both re-run AudioEnc + Attention + AudioDec over all max_T frames every step, because the reference applies the
+monotonic window derived from the *latest* prev_max_attentions to every time row (networks.py:304-313).
+Vocoding (Griffin-Lim / WORLD) is outside the hot path.
+"""
+import numpy as np
+import torch
+
+
+def get_text_lengths(L):
+    """Index of the first padding symbol (0) in each row (synthesize.py:242-247)."""
+    return np.array([int(np.where(L[i, :] == 0)[0][0]) for i in range(len(L))])
+
+
+def encode_text(hp, L, g, sess, speaker_data=None, labels=None):
+    """One TextEnc pass -> (K, V) (synthesize.py:232-240)."""
+    assert not hp.multispeaker and not hp.merlin_label_dir
+    K, V = sess.run([g.K, g.V], {g.L: L})
+    return (K, V)
+
+
+def _update_ends(hp, max_att_j, ends, endcounts, t_ends, j, endcount_threshold=1):
+    """End-of-sentence bookkeeping of synthesize.py:218-228: a sentence ends at the first frame whose attention
+    argmax reaches the first padding position; returns True when every sentence has ended."""
+    endcounts += (max_att_j >= ends)
+    for i in range(len(t_ends)):
+        if t_ends[i] == hp.max_T and endcounts[i] >= endcount_threshold:
+            t_ends[i] = j
+    return bool((t_ends < hp.max_T).all())
+
+
+def synth_text2mel(hp, L, g, sess, speaker_data=None, duration_data=None, labels=None, position_in_phone_data=None):
+    """Route that re-runs TextEnc every frame (synthesize.py:62-132).  Returns (Y, t_ends)."""
+    assert not hp.multispeaker and not hp.use_external_durations and not hp.merlin_label_dir
+    B = len(L)
+    Y = np.zeros((B, hp.max_T, hp.n_mels), np.float32)
+    prev_max_attentions = np.zeros((B,), np.int32)
+    ends = get_text_lengths(L)
+    endcounts = np.zeros(ends.shape, dtype=int)
+    t_ends = np.ones(ends.shape, dtype=int) * hp.max_T
+    feeddict = {g.L: L, g.mels: Y, g.prev_max_attentions: prev_max_attentions}
+    for j in range(hp.max_T):
+        _Y, _max_attentions, _alignments = sess.run([g.Y, g.max_attentions, g.alignments], feeddict)
+        Y[:, j, :] = _Y[:, j, :]
+        prev_max_attentions = _max_attentions[:, j]
+        feeddict[g.mels] = Y
+        feeddict[g.prev_max_attentions] = prev_max_attentions
+        if _update_ends(hp, _max_attentions[:, j], ends, endcounts, t_ends, j):
+            break
+    return (Y, t_ends.tolist())
+
+
+def synth_codedtext2mel(hp, K, V, ends, g, sess, speaker_data=None, duration_data=None, labels=None,
+                        position_in_phone_data=None):
+    """Route with K, V encoded once and fed (synthesize.py:150-230).  Returns (Y, t_ends, alignments)."""
+    assert not hp.multispeaker and not hp.use_external_durations and not hp.merlin_label_dir
+    B = len(K)
+    Y = np.zeros((B, hp.max_T, hp.n_mels), np.float32)
+    alignments = np.zeros((len(ends), hp.max_N, hp.max_T), np.float32)
+    prev_max_attentions = np.zeros((B,), np.int32)
+    ends = np.asarray(ends)
+    endcounts = np.zeros(ends.shape, dtype=int)
+    t_ends = np.ones(ends.shape, dtype=int) * hp.max_T
+    feeddict = {g.K: K, g.V: V, g.mels: Y, g.prev_max_attentions: prev_max_attentions}
+    for j in range(hp.max_T):
+        _Y, _max_attentions, _alignments = sess.run([g.Y, g.max_attentions, g.alignments], feeddict)
+        Y[:, j, :] = _Y[:, j, :]
+        alignments[:, :, j] = _alignments[:, :, j]
+        prev_max_attentions = _max_attentions[:, j]
+        feeddict[g.mels] = Y
+        feeddict[g.prev_max_attentions] = prev_max_attentions
+        if _update_ends(hp, _max_attentions[:, j], ends, endcounts, t_ends, j):
+            break
+    return (Y, t_ends.tolist(), alignments)
+
+
+def synth_codedtext2mel_device(hp, K, V, ends, g):
+    """Same loop with every tensor resident on the GPU; per frame only B int32 argmax values cross to the host."""
+    dev = g.device
+    K = g._to_device(K, torch.float32)
+    V = g._to_device(V, torch.float32)
+    B = K.shape[0]
+    Y = torch.zeros(B, hp.max_T, hp.n_mels, device=dev, dtype=torch.float32)
+    alignments = torch.zeros(B, hp.max_N, hp.max_T, device=dev, dtype=torch.float32)
+    prev = torch.zeros(B, device=dev, dtype=torch.int32)
+    ends = np.asarray(ends)
+    endcounts = np.zeros(ends.shape, dtype=int)
+    t_ends = np.ones(ends.shape, dtype=int) * hp.max_T
+    for j in range(hp.max_T):
+        out = g.build_model(None, Y, False, K=K, V=V, prev_max_attentions=prev, want_alignments=True)
+        Y[:, j, :].copy_(out["Y"][:, j, :])
+        alignments[:, :, j].copy_(out["alignments"][:, :, j])
+        prev = out["max_attentions"][:, j].contiguous()
+        if _update_ends(hp, prev.cpu().numpy().astype(np.int64), ends, endcounts, t_ends, j):
+            break
+    return (Y.cpu().numpy(), t_ends.tolist(), alignments.cpu().numpy())
+
+
+def synth_mel2mag(hp, Y, g, sess, batchsize=128):
+    """SSRN over the padded mel batch in chunks of <= batchsize utterances (synthesize.py:250-260)."""
+    if batchsize > 0:
+        nbatches = max(1, len(Y) // batchsize)
+        batches = np.array_split(Y, nbatches)
+    else:
+        batches = [Y]
+    Z = np.concatenate([sess.run(g.Z, {g.mels: Y_batch}) for Y_batch in batches])
+    return Z
+
+
+def split_batch(synth_batch, end_indices):
+    return [predmel[:end_indices[i], :] for i, predmel in enumerate(synth_batch)]

@@ -1,0 +1,123 @@
+"""Whole-graph parity of the CUDA Text2Mel path against the fp64 oracles (config C1: B=2, N=60, T=200)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import make_hp, maxabs, oracle_params, relerr
+from oracle import dctts_numpy as on
+from oracle import dctts_torch as ot
+from oracle.params import synthetic_batch
+
+pytestmark = pytest.mark.gpu
+
+
+def _graph(hp, mode, P, **kw):
+    from ophelia_b200.architectures import Text2MelGraph
+    from ophelia_b200.variables import VariableStore
+    store = kw.pop("store", None) or VariableStore("cuda:0")
+    g = Text2MelGraph(hp, mode=mode, store=store, **kw)
+    if P is not None:
+        store.load_state_dict(P)
+    return g
+
+
+def test_forward_matches_oracle_c1():
+    from ophelia_b200.session import Session
+    hp = make_hp(max_N=60, max_T=200)
+    P = oracle_params(hp, "t2m", seed=0)
+    b = synthetic_batch(hp, 2, 60, 200, text_len=50)
+    ref = on.text2mel_forward(hp, P, b["L"], b["mels"], "generate_attention")
+    g = _graph(hp, "generate_attention", P)
+    sess = Session()
+    Y, ali, mx, K, V = sess.run([g.Y, g.alignments, g.max_attentions, g.K, g.V], {g.L: b["L"], g.mels: b["mels"]})
+    assert Y.shape == (2, 200, 80) and ali.shape == (2, 60, 200) and mx.shape == (2, 200)
+    assert maxabs(K, ref["K"]) < 1e-3 and maxabs(V, ref["V"]) < 1e-3
+    assert maxabs(Y, ref["Y"]) < 1e-3            # north-star tolerance: mels within 1e-3 max-abs
+    assert maxabs(ali, ref["alignments"]) < 1e-4
+    assert (mx == ref["max_attentions"]).mean() > 0.995      # exact except near-ties
+
+
+def test_forward_matches_golden_fixture():
+    import os
+    from ophelia_b200.session import Session
+    path = os.path.join(os.path.dirname(__file__), "golden", "t2m_c1.npz")
+    z = np.load(path)
+    hp = make_hp(max_N=60, max_T=200)
+    P = oracle_params(hp, "t2m", seed=int(z["param_seed"]))
+    b = synthetic_batch(hp, 2, 60, 200, seed=int(z["data_seed"]), text_len=50)
+    g = _graph(hp, "generate_attention", P)
+    Y, ali = Session().run([g.Y, g.alignments], {g.L: b["L"], g.mels: b["mels"]})
+    assert maxabs(Y, z["Y"]) < 1e-3
+    assert maxabs(ali, z["alignments"]) < 1e-4
+
+
+def test_synthesis_mode_window_mask():
+    from ophelia_b200.session import Session
+    hp = make_hp(max_N=60, max_T=200)
+    P = oracle_params(hp, "t2m", seed=1)
+    b = synthetic_batch(hp, 2, 60, 200, text_len=50)
+    prev = np.array([3, 41], np.int32)
+    ref = on.text2mel_forward(hp, P, b["L"], b["mels"], "synthesize", prev)
+    g = _graph(hp, "synthesize", P)
+    sess = Session()
+    K, V = sess.run([g.K, g.V], {g.L: b["L"]})
+    Y, mx, ali = sess.run([g.Y, g.max_attentions, g.alignments],
+                          {g.K: K, g.V: V, g.mels: b["mels"], g.prev_max_attentions: prev})
+    assert maxabs(Y, ref["Y"]) < 1e-3
+    assert maxabs(ali, ref["alignments"]) < 1e-4
+    assert (ali[0, :3] == 0).all() and (ali[0, 6:] == 0).all()       # only keys [prev, prev+3) survive
+    assert (mx == ref["max_attentions"]).mean() > 0.995
+
+
+@pytest.mark.parametrize("shape", [(2, 60, 200), (3, 37, 131)])
+def test_train_step_matches_oracle(shape):
+    B, N, T = shape
+    hp = make_hp(max_N=N, max_T=T, dropout_rate=0.0)
+    P = oracle_params(hp, "t2m", seed=2)
+    b = synthetic_batch(hp, B, N, T, ragged=True)
+    Pt = ot.to_torch(P, torch.float64, requires_grad=True)
+    opt = ot.TFAdam(hp, Pt)
+    L = torch.tensor(b["L"].astype(np.int64))
+    mels = torch.tensor(b["mels"], dtype=torch.float64)
+    g = _graph(hp, "train", P, data=iter([]))
+    Ld = torch.tensor(b["L"]).cuda()
+    md = torch.tensor(b["mels"]).cuda()
+    for step in range(3):
+        comps_ref, grads_ref = ot.text2mel_train_step(hp, Pt, opt, L, mels)
+        comps = g.train_step_device(Ld, md).cpu().numpy()
+        np.testing.assert_allclose(comps, comps_ref, rtol=2e-4, atol=1e-6)
+        if step == 0:
+            sd = g.store.grads
+            worst = 0.0
+            for name, gr in grads_ref.items():
+                e = relerr(sd[name].cpu().numpy(), gr.numpy())
+                worst = max(worst, e)
+                assert e < 2e-3, (name, e)
+            row0 = sd["Text2Mel/TextEnc/embed_1/lookup_table"][0].abs().max().item()
+            assert row0 == 0.0                                   # zero-pad row gets no gradient (modules.py:38-40)
+    assert int(g.store.global_step.item()) == 3
+    new = g.store.state_dict()
+    for name, p in Pt.items():
+        # Adam's first steps move every weight by ~lr_t regardless of gradient size, so compare absolutely
+        assert maxabs(new[name], p.detach().numpy()) < 5e-6 + 0.2 * 3 * ot.noam(hp.lr, 2), name
+
+
+def test_autoregressive_loop_matches_oracle():
+    from ophelia_b200.session import Session
+    from ophelia_b200 import synthesize as syn
+    hp = make_hp(max_N=24, max_T=14)
+    P = oracle_params(hp, "t2m", seed=3)
+    b = synthetic_batch(hp, 3, 24, 14, text_len=5)
+    g = _graph(hp, "synthesize", P)
+    sess = Session()
+    K, V = syn.encode_text(hp, b["L"], g, sess)
+    ends = syn.get_text_lengths(b["L"])
+    Kr, Vr = on.TextEnc(hp, P, b["L"])
+    Yr, tr, ar = on.synth_codedtext2mel(hp, P, Kr, Vr, ends)
+    Y1, t1, a1 = syn.synth_codedtext2mel(hp, K, V, ends, g, sess)
+    Y2, t2, a2 = syn.synth_codedtext2mel_device(hp, K, V, ends, g)
+    assert t1 == tr and t2 == tr
+    assert maxabs(Y1, Yr) < 1e-3 and maxabs(Y2, Yr) < 1e-3
+    assert maxabs(a1, ar) < 1e-4 and maxabs(a2, ar) < 1e-4
+    Y3, t3 = syn.synth_text2mel(hp, b["L"], g, sess)
+    assert t3 == tr and maxabs(Y3, Yr) < 1e-3

@@ -126,6 +126,9 @@ def case_conv1d(B, L, cin, cout, act, padding, in_shift=0, norm=True):
         dg, dbe = torch.zeros_like(gamma), torch.zeros_like(beta)
         dx = ops.conv1d_bwd(act32(dy), xg, saved, pk, gamma, beta, dw, db, dg, dbe, 1, padding, in_shift, act, norm)
         report(tag + " dx", maxerr(dx, x.grad), 5e-4)
+        e = (dx.detach().double().cpu() - x.grad).abs().amax(-1)
+        if float(e.max()) > 5e-4:
+            print("   bad dx rows (b,t):", [(int(i[0]), int(i[1]), float(e[i[0], i[1]])) for i in (e > 5e-4).nonzero()[:12]])
         gw = P["c/conv1d/kernel"].grad
         report(tag + " dw", maxerr(dw, gw), 1e-3 * max(1.0, float(gw.abs().max())))
         report(tag + " dbias", maxerr(db, P["c/conv1d/bias"].grad), 2e-3)
@@ -239,7 +242,7 @@ def case_embed():
     ref = table.clone()
     ref[0] = 0
     out = ops.embed_fwd(ids.to(dev), f32(table))
-    report("embed fwd", maxerr(out, ref[ids.long()]), 1e-7)
+    report("embed fwd", maxerr(out, ref[ids.long()]), 1e-6)
     dout = rnd(3, 50, 128)
     dt = torch.zeros(65, 128, device=dev)
     ops.embed_bwd(ids.to(dev), f32(dout), dt)
@@ -326,6 +329,10 @@ def main():
     for a in [(1000, 256, 512, 3), (870, 180, 256, 1), (5000, 80, 256, 4), (400, 516, 1028, 2)]:
         run("gemm_tn", case_gemm_tn(*a))
     run("conv1d", case_conv1d(2, 200, 80, 256, 1, 1, in_shift=1))
+    run("conv1d", case_conv1d(2, 200, 80, 256, 1, 1, in_shift=1))
+    run("conv1d", case_conv1d(2, 200, 80, 256, 1, 1, in_shift=0))
+    run("conv1d", case_conv1d(2, 200, 80, 256, 0, 1, in_shift=1))
+    run("conv1d", case_conv1d(2, 200, 128, 256, 1, 1, in_shift=1))
     run("conv1d", case_conv1d(2, 200, 256, 80, 0, 1))
     run("conv1d", case_conv1d(2, 60, 128, 512, 1, 0))
     run("conv1d", case_conv1d(1, 150, 1024, 513, 0, 0))
