@@ -1,0 +1,287 @@
+#!/usr/bin/env python
+"""Benchmark of the dc_tts hot path on B200: Text2Mel training (BASELINE.json configs[1]: batch 32 per GPU,
+180 phonemes, 870 mel frames, d=256, guided-attention loss, dropout 0.05, synthetic LJ-shape data).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload t2m_train|ssrn_train]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
+
+One JSON line on rank 0.  `value` = whole-job mel-frames/s with inputs resident in HBM; `e2e` = same metric through
+the reference-facing Session.run call with pinned host batches (H2D + loss D2H inside the timed region);
+`roofline` = the tcgen05 GEMM core timed per launch with CUDA events inside the timed region;
+`cpu_baseline` = the torch-CPU fp32 restatement of the reference's path on this host (N=1 only).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "Text2Mel train mel-frames/sec (B=32 per GPU, N=180, T=870)"
+UNIT = "mel-frames/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm=d["hbm_gbs"], tensor_burst=d["bf16_tflops"], tensor_sustained=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tensor_burst=1590.0, tensor_sustained=1400.0, src="fallback")
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed regions run."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference(args, model, batch, steps, warmup, threads=None):
+    """The reference's path on host cores: torch-CPU fp32 restatement (oracle/dctts_torch.py) of one training
+    step at the benchmark's N/T with a bounded batch.  Returns (value, seconds per step, cores, sample text)."""
+    import numpy as np
+    import torch
+    from oracle import dctts_torch as ot
+    from oracle.params import HP, init_params, ssrn_specs, synthetic_batch, text2mel_specs
+    if threads:
+        torch.set_num_threads(threads)
+    cores = torch.get_num_threads()
+    N, T = args.N, args.T
+    hp = HP(max_N=N, max_T=T, full_dim=args.full_dim)
+    gen = torch.Generator().manual_seed(0)
+    if model == "t2m":
+        P = ot.to_torch(init_params(text2mel_specs(hp), 0), torch.float32, requires_grad=True)
+        b = synthetic_batch(hp, batch, N, T, ragged=True)
+        L, mels = torch.tensor(b["L"].astype(np.int64)), torch.tensor(b["mels"])
+        opt = ot.TFAdam(hp, P)
+        step = lambda: ot.text2mel_train_step(hp, P, opt, L, mels, gen)   # noqa: E731
+    else:
+        P = ot.to_torch(init_params(ssrn_specs(hp), 0), torch.float32, requires_grad=True)
+        b = synthetic_batch(hp, batch, 8, T, with_mags=True)
+        mels, mags = torch.tensor(b["mels"]), torch.tensor(b["mags"])
+        opt = ot.TFAdam(hp, P)
+        step = lambda: ot.ssrn_train_step(hp, P, opt, mels, mags, gen)    # noqa: E731
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    sample = "torch-CPU fp32 restatement, %s train step (fwd+bwd+clip+TF-Adam, dropout 0.05), batch %d x N=%d x T=%d, " \
+             "%d timed step(s), %d threads" % (model, batch, N, T, steps, cores)
+    return batch * T / dt, dt, cores, sample
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    model = "t2m" if args.workload == "t2m_train" else "ssrn"
+    value, dt, cores, sample = cpu_reference(args, model, args.ref_batch, max(1, args.steps), max(0, min(args.warmup, 1)))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, 1),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "reference = TensorFlow-1.12/Python-2.7 code that cannot run here; this arm times the CPU "
+                    "restatement of the same graph (oracle/, kind=port) on a bounded batch"}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    if args.workload == "t2m_train":
+        wl = "Text2Mel training step (TextEnc+AudioEnc+Attention+AudioDec fwd, L1+BD+guided-attention loss, bwd, " \
+             "clip+Adam): batch %d per GPU, %d phonemes, %d mel frames, d=256, dropout 0.05" % (args.batch, args.N, args.T)
+    else:
+        wl = "SSRN training step: batch %d per GPU, %d->%d frames, 80 mels -> %d bins" % (args.batch, args.T, 4 * args.T, args.full_dim)
+    return {"workload": wl, "global_batch": args.batch * world, "parallelism": "dp%d" % world,
+            "l2": "per-step working set (saved activations, several GB) exceeds the 126 MB L2; no explicit flush",
+            "precision": "fp32 I/O; GEMMs as 3-term split-bf16 on tcgen05 (fp32-grade, 3 tensor passes per algorithmic FLOP)"}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__
+    from ophelia_b200 import _lib
+    from ophelia_b200.architectures import SSRNGraph, Text2MelGraph
+    from ophelia_b200.configuration import default_hparams
+    from ophelia_b200.data import SyntheticBatches
+    from ophelia_b200.parallel import init_from_env
+    from ophelia_b200.session import Session
+    from ophelia_b200.variables import VariableStore
+
+    rank, world, local = init_from_env("nccl")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if rank == 0:
+        __graft_entry__.build()
+    if world > 1:
+        dist.barrier()
+    lib = _lib.load()
+    group = dist.group.WORLD if world > 1 else None
+    t2m = args.workload == "t2m_train"
+    hp = default_hparams(max_N=args.N, max_T=args.T, full_dim=args.full_dim, seed=0)
+    src = SyntheticBatches(hp, "t2m" if t2m else "ssrn", args.batch, N=args.N, T=args.T, seed=1234 + rank)
+    store = VariableStore(dev, seed=0)
+    Graph = Text2MelGraph if t2m else SSRNGraph
+    g = Graph(hp, mode="train", store=store, data=src, device=dev, process_group=group)
+    sess = Session()
+    frames_per_step = args.batch * args.T * world
+
+    b0 = src.batches[0]
+    if t2m:
+        dev_in = (b0["text"].to(dev), b0["mel"].to(dev))
+    else:
+        dev_in = (b0["mel"].to(dev), b0["mag"].to(dev))
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        g.train_step_device(*dev_in)
+    for _ in range(2):
+        sess.run([g.global_step, g.loss_components, g.train_op])
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+
+    # ---- timed region 1: device-resident inputs
+    import ctypes
+    sync_all()
+    launches0 = lib.oph_launch_count()
+    lib.oph_profile_begin()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        comps = g.train_step_device(*dev_in)
+    e1.record()
+    sync_all()
+    ms = e0.elapsed_time(e1) / args.steps
+    prof = (ctypes.c_double * 15)()
+    lib.oph_profile_end(prof)
+    launches = (lib.oph_launch_count() - launches0) // args.steps
+    last_loss = [float(c) for c in comps.cpu().numpy()]
+
+    # ---- timed region 2: end to end through Session.run with pinned host batches
+    sync_all()
+    t_e2e0 = torch.cuda.Event(enable_timing=True); t_e2e1 = torch.cuda.Event(enable_timing=True)
+    t_e2e0.record()
+    for _ in range(args.steps):
+        gs, loss_components, _ = sess.run([g.global_step, g.loss_components, g.train_op])
+    t_e2e1.record()
+    sync_all()
+    ms_e2e = t_e2e0.elapsed_time(t_e2e1) / args.steps
+    clk = clocks.stop() if rank == 0 else None
+
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+        return
+
+    pk = peaks()
+    names = ["other", "conv_fwd", "dgrad", "wgrad", "attention"]
+    tot_n = sum(prof[i * 3] for i in range(5)); tot_ms = sum(prof[i * 3 + 1] for i in range(5)); tot_fl = sum(prof[i * 3 + 2] for i in range(5))
+    achieved = tot_fl / (tot_ms * 1e-3) / 1e12 if tot_ms > 0 else 0.0
+    breakdown = {names[i]: {"launches_per_step": prof[i * 3] / args.steps, "ms_per_step": prof[i * 3 + 1] / args.steps,
+                            "tflops": (prof[i * 3 + 2] / (prof[i * 3 + 1] * 1e-3) / 1e12) if prof[i * 3 + 1] > 0 else 0.0}
+                 for i in range(5) if prof[i * 3] > 0}
+    line = {
+        "metric": METRIC, "value": frames_per_step / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
+        "per_gpu": frames_per_step / world / (ms * 1e-3),
+        "e2e": {"value": frames_per_step / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": src.bytes_per_batch(), "d2h_bytes_per_step": 4 * len(last_loss) + 8},
+        "gpu_launches": int(launches) * args.steps,
+        "gpu_launches_per_step": int(launches),
+        "roofline": {"kernel": "gemm_bf16x3_kernel (tcgen05 implicit GEMM: conv fwd / dgrad / wgrad / attention)",
+                     "bound": "tensor", "achieved": achieved, "peak": pk["tensor_sustained"], "unit": "TFLOP/s",
+                     "frac": achieved / pk["tensor_sustained"], "traffic": None,
+                     "peak_source": pk["src"] + " bf16 cuBLAS sustained",
+                     "launches_per_step": tot_n / args.steps, "avg_launch_ms": tot_ms / max(tot_n, 1),
+                     "share_of_step": (tot_ms / args.steps) / ms,
+                     "note": "achieved counts ALGORITHMIC FLOPs once; the split-bf16 scheme issues 3 tensor passes per "
+                             "FLOP, so the ceiling of this number is peak/3"},
+        "gemm_breakdown": breakdown,
+        "clocks": clk, "loss_components": last_loss, "global_step": int(gs),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        v, dt, cores, sample = cpu_reference(args, "t2m" if t2m else "ssrn", args.ref_batch, 1, 1)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "s_per_step": dt}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="t2m_train", choices=["t2m_train", "ssrn_train"])
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--N", type=int, default=180)
+    ap.add_argument("--T", type=int, default=870)
+    ap.add_argument("--full-dim", dest="full_dim", type=int, default=513)
+    ap.add_argument("--ref-batch", dest="ref_batch", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", "29411", os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

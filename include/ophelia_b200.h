@@ -39,6 +39,20 @@ typedef void* oph_stream_t; /* cudaStream_t */
 int oph_version(void);
 const char* oph_last_error(void);
 
+/* ---- instrumentation used by bench.py ---------------------------------------------------------------------
+ * oph_launch_count: kernels launched by this library so far (all streams).
+ * oph_profile_begin/end: time every launch of the tcgen05 GEMM core with CUDA events on its own stream;
+ * out is double[OPH_NUM_TAGS*3] = per tag (launches, summed milliseconds, summed algorithmic FLOPs). */
+#define OPH_TAG_OTHER 0
+#define OPH_TAG_CONV_FWD 1
+#define OPH_TAG_DGRAD 2
+#define OPH_TAG_WGRAD 3
+#define OPH_TAG_ATTENTION 4
+#define OPH_NUM_TAGS 5
+long long oph_launch_count(void);
+int oph_profile_begin(void);
+int oph_profile_end(double* out);
+
 /* ---- weight packing: fp32 kernels -> split-bf16 (hi,lo) SWIZZLE_128B shared-memory images ----------------
  * `deconv`=0: w is [k][Cin][Cout] (modules.py:134-136).  `deconv`=1: w is [3][Cout][Cin] (modules.py:243-250).
  * fwd image feeds oph_*_fwd, bwd image feeds the input-gradient GEMM of oph_*_bwd.

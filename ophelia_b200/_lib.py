@@ -15,6 +15,9 @@ P, LL, I, F, D, U64, SZ = (ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, cty
 SIGNATURES = {
     "oph_version": (I, []),
     "oph_last_error": (ctypes.c_char_p, []),
+    "oph_launch_count": (LL, []),
+    "oph_profile_begin": (I, []),
+    "oph_profile_end": (I, [P]),
     "oph_conv_pack_bytes": (SZ, [I, I, I, I, I]),
     "oph_conv_pack": (I, [P, I, I, I, I, P, P, P]),
     "oph_conv1d_fwd": (I, [P, LL, P, P, P, P, P, LL, P, P, LL, P, LL, I, I, I, I, I, I, I, I, I, I, F, U64, P, P]),

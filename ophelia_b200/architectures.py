@@ -167,9 +167,8 @@ class Graph(object):
         hp, st = self.hp, self.store
         scale = 1.0
         if self.process_group is not None:
-            import torch.distributed as dist
-            dist.all_reduce(st.grad_flat, group=self.process_group)      # NCCL sum over NVLink; only collective
-            scale = 1.0 / dist.get_world_size(self.process_group)
+            from .parallel import allreduce_gradients
+            scale = allreduce_gradients(st.grad_flat, self.process_group)  # NCCL sum over NVLink; only collective
         ops.adam_prepare(st.global_step, st.lr_t, hp.lr, hp.beta1, hp.beta2, hp.decay_lr)
         ops.adam_clip(st.flat, st.m_flat, st.v_flat, st.grad_flat, st.lr_t, hp.beta1, hp.beta2, hp.epsilon, 1.0, scale)
         ops.step_inc(st.global_step)

@@ -4,21 +4,32 @@
 #include "gemm_tc.cuh"
 #include "rowwise.cuh"
 
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
+#include <vector>
 
 using namespace oph;
 
 namespace {
 
 thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+
+// Optional per-launch timing of the GEMM core (bench.py roofline): CUDA events around every launch, by tag.
+struct ProfRec { cudaEvent_t e0, e1; int tag; double flops; };
+std::mutex g_prof_mu;
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof;
 
 int fail(int code, const char* fmt, const char* detail = "") {
     snprintf(g_err, sizeof(g_err), fmt, detail);
     return code;
 }
 int check_launch(const char* what) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
@@ -47,8 +58,26 @@ int launch_gemm(GemmArgs& a, int zdim, cudaStream_t st) {
     const int nblocks = cdiv(a.N, NT);
     if (a.ytaps < 1) a.ytaps = 1;
     dim3 grid(cdiv(a.M, GEMM_BM), nblocks * a.ytaps, zdim < 1 ? 1 : zdim);
+    ProfRec rec{};
+    bool prof = false;
+    if (g_prof_on) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(st, &cs);
+        if (cs == cudaStreamCaptureStatusNone) {
+            prof = true;
+            cudaEventCreate(&rec.e0); cudaEventCreate(&rec.e1);
+            rec.tag = a.tag;
+            rec.flops = 2.0 * a.M * a.N * a.Kc * (a.a_mode == A_KMAJOR ? a.ntaps : a.ytaps) * (a.z_mode == Z_BATCH ? zdim : 1);
+            cudaEventRecord(rec.e0, st);
+        }
+    }
     if (NH == 1) gemm_bf16x3_kernel<1><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(a);
     else         gemm_bf16x3_kernel<2><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(a);
+    if (prof) {
+        cudaEventRecord(rec.e1, st);
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        g_prof.push_back(rec);
+    }
     return check_launch("gemm_bf16x3_kernel");
 }
 
@@ -132,7 +161,7 @@ int launch_wgrad(const float* a, long long lda, int M, const int* a_off, int aL,
     g.Bm.ptr = b; g.Bm.ld = ldb; g.Bm.L = bL; g.Bm.Ls = bLs; g.Bm.mul = b_mul;
     for (int j = 0; j < 3; ++j) { g.A.off[j] = j < taps ? a_off[j] : 0; g.Bm.off[j] = j < taps ? b_off[j] : 0; }
     g.M = M; g.N = N; g.Kc = R; g.ytaps = taps; g.c_tap_stride = (long long)M * ldc;
-    g.C = dw; g.ldc = ldc; g.atomic = 1; g.z_mode = Z_SPLITK;
+    g.C = dw; g.ldc = ldc; g.atomic = 1; g.z_mode = Z_SPLITK; g.tag = OPH_TAG_WGRAD;
     const int base = cdiv(M, GEMM_BM) * cdiv(N, GEMM_BNH * nh_for(N)) * taps;
     int splits = cdiv(2 * 148, base);
     const int max_splits = cdiv(R, 4 * GEMM_BK);
@@ -150,6 +179,32 @@ extern "C" {
 
 int oph_version(void) { return 100; }
 const char* oph_last_error(void) { return g_err; }
+long long oph_launch_count(void) { return g_launches.load(); }
+
+int oph_profile_begin(void) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (auto& r : g_prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    g_prof.clear();
+    g_prof_on = true;
+    return OPH_OK;
+}
+
+// out[tag*3 + {0,1,2}] = launches, summed device milliseconds, summed algorithmic FLOPs; tags 0..OPH_NUM_TAGS-1
+int oph_profile_end(double* out) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof_on = false;
+    for (int i = 0; i < OPH_NUM_TAGS * 3; ++i) out[i] = 0.0;
+    for (auto& r : g_prof) {
+        if (cudaEventSynchronize(r.e1) != cudaSuccess) return check_launch("profile_end");
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.e0, r.e1);
+        const int t = (r.tag >= 0 && r.tag < OPH_NUM_TAGS) ? r.tag : 0;
+        out[t * 3] += 1.0; out[t * 3 + 1] += ms; out[t * 3 + 2] += r.flops;
+        cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
+    }
+    g_prof.clear();
+    return OPH_OK;
+}
 
 size_t oph_conv_pack_bytes(int k, int Cin, int Cout, int deconv, int backward) {
     if (!deconv) return backward ? pack_image_bytes(k, Cout, Cin) : pack_image_bytes(k, Cin, Cout);
@@ -190,7 +245,7 @@ int oph_conv1d_fwd(const float* x, long long ldx, const void* packed_w, const fl
     g.A.ptr = x; g.A.ld = ldx; g.A.L = L; g.A.Ls = L; g.A.mul = 1;
     conv_offsets(k, rate, padding, in_shift, g.A.off);
     g.Bpacked = packed_w; g.M = B * L; g.N = Cout; g.Kc = Cin; g.ntaps = k;
-    g.C = z; g.ldc = ldz; g.bias = bias;
+    g.C = z; g.ldc = ldz; g.bias = bias; g.tag = OPH_TAG_CONV_FWD;
     OPH_TRY(launch_gemm(g, 1, S(stream)));
     const long long rows = (long long)B * L;
     ln_act_fwd_kernel<<<rows_grid(rows, 8), 256, 0, S(stream)>>>(z, ldz, gamma, beta, y, ldy, y_sig, ldys, stats,
@@ -214,7 +269,7 @@ int oph_conv1d_bwd(const float* dy, long long lddy, const float* x, long long ld
         g.a_mode = A_KMAJOR; g.b_mode = B_PACKED;
         g.A.ptr = dz; g.A.ld = lddz; g.A.L = L; g.A.Ls = L; g.A.mul = 1;
         for (int j = 0; j < 3; ++j) g.A.off[j] = -off[j];
-        g.Bpacked = packed_w_bwd; g.M = B * L; g.N = Cin; g.Kc = Cout; g.ntaps = k;
+        g.tag = OPH_TAG_DGRAD; g.Bpacked = packed_w_bwd; g.M = B * L; g.N = Cin; g.Kc = Cout; g.ntaps = k;
         g.C = dx; g.ldc = lddx;
         OPH_TRY(launch_gemm(g, 1, S(stream)));
     }
@@ -236,7 +291,7 @@ int oph_hc_fwd(const float* x, long long ldx, const void* packed_w, const float*
     g.A.ptr = x; g.A.ld = ldx; g.A.L = L; g.A.Ls = L; g.A.mul = 1;
     conv_offsets(k, rate, padding, 0, g.A.off);
     g.Bpacked = packed_w; g.M = B * L; g.N = 2 * C; g.Kc = C; g.ntaps = k;
-    g.C = z; g.ldc = ldz; g.bias = bias;
+    g.C = z; g.ldc = ldz; g.bias = bias; g.tag = OPH_TAG_CONV_FWD;
     OPH_TRY(launch_gemm(g, 1, S(stream)));
     const long long rows = (long long)B * L;
     hc_post_fwd_kernel<<<rows_grid(rows, 8), 256, 0, S(stream)>>>(z, ldz, x, ldx, g1, b1, g2, b2, y, ldy, stats,
@@ -262,7 +317,7 @@ int oph_hc_bwd(const float* dy, long long lddy, const float* x, long long ldx, c
         g.a_mode = A_KMAJOR; g.b_mode = B_PACKED;
         g.A.ptr = dz; g.A.ld = lddz; g.A.L = L; g.A.Ls = L; g.A.mul = 1;
         for (int j = 0; j < 3; ++j) g.A.off[j] = -off[j];
-        g.Bpacked = packed_w_bwd; g.M = B * L; g.N = C; g.Kc = 2 * C; g.ntaps = k;
+        g.tag = OPH_TAG_DGRAD; g.Bpacked = packed_w_bwd; g.M = B * L; g.N = C; g.Kc = 2 * C; g.ntaps = k;
         g.C = dx; g.ldc = lddx; g.addend = dxres; g.ld_add = ldxr;
         OPH_TRY(launch_gemm(g, 1, S(stream)));
     }
@@ -285,7 +340,7 @@ int oph_deconv_fwd(const float* x, long long ldx, const void* packed_w, const fl
         g.ntaps = parity == 0 ? 2 : 1;
         g.Bpacked = reinterpret_cast<const uint8_t*>(packed_w) + (parity ? pack_image_bytes(2, C, C) : 0);
         g.M = B * L; g.N = C; g.Kc = C;
-        g.C = z; g.ldc = ldz; g.c_mul = 2; g.c_off = parity; g.bias = bias;
+        g.C = z; g.ldc = ldz; g.c_mul = 2; g.c_off = parity; g.bias = bias; g.tag = OPH_TAG_CONV_FWD;
         OPH_TRY(launch_gemm(g, 1, S(stream)));
     }
     const long long rows = 2LL * B * L;
@@ -307,7 +362,7 @@ int oph_deconv_bwd(const float* dy, long long lddy, const float* x, long long ld
         g.a_mode = A_KMAJOR; g.b_mode = B_PACKED;
         g.A.ptr = dz; g.A.ld = lddz; g.A.L = L; g.A.Ls = 2 * L; g.A.mul = 2;
         g.A.off[0] = 0; g.A.off[1] = 1; g.A.off[2] = 2;
-        g.Bpacked = packed_w_bwd; g.M = B * L; g.N = C; g.Kc = C; g.ntaps = 3;
+        g.tag = OPH_TAG_DGRAD; g.Bpacked = packed_w_bwd; g.M = B * L; g.N = C; g.Kc = C; g.ntaps = 3;
         g.C = dx; g.ldc = lddx;
         OPH_TRY(launch_gemm(g, 1, S(stream)));
     }
@@ -340,7 +395,7 @@ int oph_attention_fwd(const float* Q, long long ldq, const float* K, long long l
         g.A.ptr = Q; g.A.ld = ldq; g.A.L = T; g.A.Ls = T;
         g.Bm.ptr = K; g.Bm.ld = ldk;
         g.M = T; g.N = N; g.Kc = d;
-        g.z_mode = Z_BATCH; g.a_zs = (long long)T * ldq; g.b_zs = (long long)N * ldk; g.c_zs = (long long)T * ldA;
+        g.tag = OPH_TAG_ATTENTION; g.z_mode = Z_BATCH; g.a_zs = (long long)T * ldq; g.b_zs = (long long)N * ldk; g.c_zs = (long long)T * ldA;
         g.C = A; g.ldc = ldA; g.alpha = 1.0f / sqrtf((float)d);
         OPH_TRY(launch_gemm(g, B, S(stream)));
     }
@@ -353,7 +408,7 @@ int oph_attention_fwd(const float* Q, long long ldq, const float* K, long long l
         g.A.ptr = A; g.A.ld = ldA; g.A.L = T; g.A.Ls = T;
         g.Bm.ptr = V; g.Bm.ld = ldv; g.Bm.L = N; g.Bm.Ls = N;
         g.M = T; g.N = d; g.Kc = N;
-        g.z_mode = Z_BATCH; g.a_zs = (long long)T * ldA; g.b_zs = (long long)N * ldv; g.c_zs = (long long)T * ldr;
+        g.tag = OPH_TAG_ATTENTION; g.z_mode = Z_BATCH; g.a_zs = (long long)T * ldA; g.b_zs = (long long)N * ldv; g.c_zs = (long long)T * ldr;
         g.C = R; g.ldc = ldr;
         OPH_TRY(launch_gemm(g, B, S(stream)));
     }
@@ -372,7 +427,7 @@ int oph_attention_bwd(const float* dR, long long lddr, const float* Q, long long
         g.A.ptr = A; g.A.ld = ldA; g.A.L = T; g.A.Ls = T;
         g.Bm.ptr = dR; g.Bm.ld = lddr; g.Bm.L = T; g.Bm.Ls = T;
         g.M = N; g.N = d; g.Kc = T;
-        g.z_mode = Z_BATCH; g.a_zs = (long long)T * ldA; g.b_zs = (long long)T * lddr; g.c_zs = (long long)N * lddv;
+        g.tag = OPH_TAG_ATTENTION; g.z_mode = Z_BATCH; g.a_zs = (long long)T * ldA; g.b_zs = (long long)T * lddr; g.c_zs = (long long)N * lddv;
         g.C = dV; g.ldc = lddv;
         OPH_TRY(launch_gemm(g, B, S(stream)));
     }
@@ -382,7 +437,7 @@ int oph_attention_bwd(const float* dR, long long lddr, const float* Q, long long
         g.A.ptr = dR; g.A.ld = lddr; g.A.L = T; g.A.Ls = T;
         g.Bm.ptr = V; g.Bm.ld = ldv;
         g.M = T; g.N = N; g.Kc = d;
-        g.z_mode = Z_BATCH; g.a_zs = (long long)T * lddr; g.b_zs = (long long)N * ldv; g.c_zs = (long long)T * ldA;
+        g.tag = OPH_TAG_ATTENTION; g.z_mode = Z_BATCH; g.a_zs = (long long)T * lddr; g.b_zs = (long long)N * ldv; g.c_zs = (long long)T * ldA;
         g.C = dA; g.ldc = ldA;
         OPH_TRY(launch_gemm(g, B, S(stream)));
     }
@@ -394,7 +449,7 @@ int oph_attention_bwd(const float* dR, long long lddr, const float* Q, long long
         g.A.ptr = dA; g.A.ld = ldA; g.A.L = T; g.A.Ls = T;
         g.Bm.ptr = K; g.Bm.ld = ldk; g.Bm.L = N; g.Bm.Ls = N;
         g.M = T; g.N = d; g.Kc = N;
-        g.z_mode = Z_BATCH; g.a_zs = (long long)T * ldA; g.b_zs = (long long)N * ldk; g.c_zs = (long long)T * lddq;
+        g.tag = OPH_TAG_ATTENTION; g.z_mode = Z_BATCH; g.a_zs = (long long)T * ldA; g.b_zs = (long long)N * ldk; g.c_zs = (long long)T * lddq;
         g.C = dQ; g.ldc = lddq; g.alpha = scale;
         if (dq_addend) {
             if ((long long)T * ldqa != g.c_zs || ldqa != lddq) return fail(OPH_EINVAL, "attention_bwd: dq_addend must share dQ's layout%s");
@@ -408,7 +463,7 @@ int oph_attention_bwd(const float* dR, long long lddr, const float* Q, long long
         g.A.ptr = dA; g.A.ld = ldA; g.A.L = T; g.A.Ls = T;
         g.Bm.ptr = Q; g.Bm.ld = ldq; g.Bm.L = T; g.Bm.Ls = T;
         g.M = N; g.N = d; g.Kc = T;
-        g.z_mode = Z_BATCH; g.a_zs = (long long)T * ldA; g.b_zs = (long long)T * ldq; g.c_zs = (long long)N * lddk;
+        g.tag = OPH_TAG_ATTENTION; g.z_mode = Z_BATCH; g.a_zs = (long long)T * ldA; g.b_zs = (long long)T * ldq; g.c_zs = (long long)N * lddk;
         g.C = dK; g.ldc = lddk; g.alpha = scale;
         OPH_TRY(launch_gemm(g, B, S(stream)));
     }
@@ -452,7 +507,7 @@ int oph_gemm_nt(const float* A, long long lda, const float* Bm, long long ldb, f
     g.A.ptr = A; g.A.ld = lda; g.A.L = M; g.A.Ls = M;
     g.Bm.ptr = Bm; g.Bm.ld = ldb; g.Bm.L = K; g.Bm.Ls = K;
     g.M = M; g.N = N; g.Kc = K; g.C = C; g.ldc = ldc; g.bias = bias; g.alpha = alpha;
-    if (batch > 1) { g.z_mode = Z_BATCH; g.a_zs = a_bs; g.b_zs = b_bs; g.c_zs = c_bs; }
+    if (batch > 1) { g.tag = OPH_TAG_ATTENTION; g.z_mode = Z_BATCH; g.a_zs = a_bs; g.b_zs = b_bs; g.c_zs = c_bs; }
     return launch_gemm(g, batch, S(stream));
 }
 int oph_gemm_tn(const float* A, long long lda, const float* Bm, long long ldb, float* C, long long ldc, int M,

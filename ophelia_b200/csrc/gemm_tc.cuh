@@ -40,6 +40,7 @@ struct GemmArgs {
     long long ld_add;
     float alpha;
     int atomic;            // 1: atomicAdd into C (split-K)
+    int tag;               // host-side profiling category (OPH_TAG_*)
 };
 
 constexpr int GEMM_BM = 128;

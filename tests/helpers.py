@@ -23,3 +23,22 @@ def maxabs(a, b):
 def relerr(a, b):
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def check_grads(ours, ref, strict_prefix, median_tol=1.5e-2, max_tol=5e-2, strict_tol=2e-4):
+    """Whole-network gradient parity vs the fp64 oracle.
+
+    The 3-term split-bf16 GEMMs reproduce the fp32 forward pass to ~2e-5, so a handful of ReLU units whose
+    pre-activation lies within 2e-5 of the kink take the other branch than in the fp64 oracle.  Each flip perturbs
+    every upstream gradient by ~sqrt(flips / units) in Frobenius norm.  Measured on B200 (tools/grad_table.py,
+    B=2, T=200): AudioDec C_11 (no ReLU between it and the loss) 1.4e-5, C_10 2.4e-4, C_9 2.7e-3, C_8 and
+    everything upstream 4-6e-3 -- the error steps up exactly at the three ReLU layers and nowhere else.  So:
+    a tight bound on the ReLU-free tail (`strict_prefix`), loose bounds elsewhere; every operator's backward is
+    pinned on its own to the 1e-5..1e-4 level in test_gpu_ops.py with near-kink units masked out."""
+    errs = sorted(((relerr(ours[n], np.asarray(ref[n])), n) for n in ref), reverse=True)
+    vals = [e for e, _ in errs]
+    strict = [(e, n) for e, n in errs if n.startswith(strict_prefix)]
+    assert strict and max(e for e, _ in strict) < strict_tol, strict
+    assert errs[0][0] < max_tol, errs[:5]
+    assert float(np.median(vals)) < median_tol, (float(np.median(vals)), errs[:5])
+    return errs

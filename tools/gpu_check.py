@@ -15,7 +15,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from ophelia_b200 import ops  # noqa: E402
 from oracle import dctts_torch as ot  # noqa: E402
 
-dev = torch.device("cuda:0")
+dev = torch.device("cuda:0" if torch.cuda.is_available() else "cpu")
 torch.manual_seed(0)
 RESULTS = []
 
@@ -113,6 +113,10 @@ def case_conv1d(B, L, cin, cout, act, padding, in_shift=0, norm=True):
         ref = ot.conv1d(P, xs, "c", 1, 1, "CAUSAL" if padding else "SAME", "relu" if act else None,
                         "layer" if norm else None)
         dy = rnd(B, L, cout)
+        if act:   # a ReLU unit within fp32 noise of its kink may take the other branch: give those no gradient
+            with torch.no_grad():
+                pre = ot.conv1d(P, xs, "c", 1, 1, "CAUSAL" if padding else "SAME", None, "layer" if norm else None)
+                dy[pre.abs() < 1e-3] = 0.0
         ref.backward(dy)
         w = f32(P["c/conv1d/kernel"])
         pk = ops.PackedConv(w)
@@ -317,37 +321,31 @@ def summary():
         print("FAILED:", r[0], r[1], r[2])
 
 
+GROUPS = {
+    "gemm_nt": [case_gemm_nt(*a) for a in [(128, 256, 64, 1, 0), (200, 180, 256, 1, 0), (870, 180, 256, 1, 3),
+                                          (1000, 512, 192, 1, 0), (130, 80, 80, 1, 0), (300, 1025, 128, 1, 0),
+                                          (200, 256, 180, 2, 0), (870, 256, 180, 2, 2), (64, 512, 60, 2, 0)]],
+    "gemm_tn": [case_gemm_tn(*a) for a in [(1000, 256, 512, 3), (870, 180, 256, 1), (5000, 80, 256, 4),
+                                          (400, 516, 1028, 2)]],
+    "conv1d": [case_conv1d(2, 200, 80, 256, 1, 1, in_shift=1), case_conv1d(2, 200, 256, 80, 0, 1),
+               case_conv1d(2, 60, 128, 512, 1, 0), case_conv1d(1, 150, 1024, 513, 0, 0),
+               case_conv1d(1, 150, 513, 513, 1, 0), case_conv1d(2, 100, 256, 256, 0, 1, norm=False),
+               case_conv1d(1, 37, 1025, 1025, 1, 0)],
+    "hc": [case_hc(*a) for a in [(2, 200, 256, 3, 1, 1), (2, 200, 256, 3, 27, 1), (2, 60, 512, 3, 9, 0),
+                                 (2, 60, 512, 1, 1, 0), (1, 130, 1024, 3, 1, 0), (3, 129, 256, 3, 3, 0)]],
+    "deconv": [case_deconv(2, 50, 512), case_deconv(1, 131, 256)],
+    "attention": [case_attention(2, 200, 60, False), case_attention(2, 210, 180, True),
+                  case_attention(3, 130, 47, False)],
+    "misc": [case_embed, case_loss_adam],
+}
+
+
 def main():
     print(torch.cuda.get_device_name(0), flush=True)
     t0 = time.time()
-    run("gemm_nt basic", case_gemm_nt(128, 256, 64, 1))
-    if RESULTS and not RESULTS[-1][3]:
-        print("basic GEMM wrong -- descriptor/layout bug; continuing for diagnostics", flush=True)
-    for a in [(200, 180, 256, 1, 0), (870, 180, 256, 1, 3), (1000, 512, 192, 1, 0), (130, 80, 80, 1, 0),
-              (300, 1025, 128, 1, 0), (200, 256, 180, 2, 0), (870, 256, 180, 2, 2), (64, 512, 60, 2, 0)]:
-        run("gemm_nt", case_gemm_nt(*a))
-    for a in [(1000, 256, 512, 3), (870, 180, 256, 1), (5000, 80, 256, 4), (400, 516, 1028, 2)]:
-        run("gemm_tn", case_gemm_tn(*a))
-    run("conv1d", case_conv1d(2, 200, 80, 256, 1, 1, in_shift=1))
-    run("conv1d", case_conv1d(2, 200, 80, 256, 1, 1, in_shift=1))
-    run("conv1d", case_conv1d(2, 200, 80, 256, 1, 1, in_shift=0))
-    run("conv1d", case_conv1d(2, 200, 80, 256, 0, 1, in_shift=1))
-    run("conv1d", case_conv1d(2, 200, 128, 256, 1, 1, in_shift=1))
-    run("conv1d", case_conv1d(2, 200, 256, 80, 0, 1))
-    run("conv1d", case_conv1d(2, 60, 128, 512, 1, 0))
-    run("conv1d", case_conv1d(1, 150, 1024, 513, 0, 0))
-    run("conv1d", case_conv1d(1, 150, 513, 513, 1, 0))
-    run("conv1d", case_conv1d(2, 100, 256, 256, 0, 1, norm=False))
-    for a in [(2, 200, 256, 3, 1, 1), (2, 200, 256, 3, 27, 1), (2, 60, 512, 3, 9, 0), (2, 60, 512, 1, 1, 0),
-              (1, 130, 1024, 3, 1, 0), (3, 129, 256, 3, 3, 0)]:
-        run("hc", case_hc(*a))
-    run("deconv", case_deconv(2, 50, 512))
-    run("deconv", case_deconv(1, 131, 256))
-    run("attention", case_attention(2, 200, 60, False))
-    run("attention", case_attention(2, 210, 180, True))
-    run("attention", case_attention(3, 130, 47, False))
-    run("embed", case_embed)
-    run("loss/adam", case_loss_adam)
+    for name, cases in GROUPS.items():
+        for fn in cases:
+            run(name, fn)
     print("checks took %.1fs" % (time.time() - t0), flush=True)
     if "--perf" in sys.argv:
         run("perf", perf)
