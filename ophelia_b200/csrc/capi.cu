@@ -17,6 +17,7 @@ namespace {
 
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
+int g_cluster = 4;     // cluster size (CTAs along M) for GEMMs with packed weights; 1, 2 or 4
 
 // Optional per-launch timing of the GEMM core (bench.py roofline): CUDA events around every launch, by tag.
 struct ProfRec { cudaEvent_t e0, e1; int tag; double flops; };
@@ -57,7 +58,17 @@ int launch_gemm(GemmArgs& a, int zdim, cudaStream_t st) {
     const int NT = GEMM_BNH * NH;
     const int nblocks = cdiv(a.N, NT);
     if (a.ytaps < 1) a.ytaps = 1;
-    dim3 grid(cdiv(a.M, GEMM_BM), nblocks * a.ytaps, zdim < 1 ? 1 : zdim);
+    // CTAs of a cluster work on consecutive M tiles and share every packed-weight stage through one multicast copy
+    int cs = (a.b_mode == B_PACKED) ? g_cluster : 1;
+    const int mtiles = cdiv(a.M, GEMM_BM);
+    while (cs > 1 && mtiles < cs) cs >>= 1;
+    dim3 grid(cdiv(mtiles, cs) * cs, nblocks * a.ytaps, zdim < 1 ? 1 : zdim);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = GEMM_SMEM; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
     ProfRec rec{};
     bool prof = false;
     if (g_prof_on) {
@@ -71,8 +82,9 @@ int launch_gemm(GemmArgs& a, int zdim, cudaStream_t st) {
             cudaEventRecord(rec.e0, st);
         }
     }
-    if (NH == 1) gemm_bf16x3_kernel<1><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(a);
-    else         gemm_bf16x3_kernel<2><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(a);
+    cudaError_t le = (NH == 1) ? cudaLaunchKernelEx(&cfg, gemm_bf16x3_kernel<1>, a)
+                               : cudaLaunchKernelEx(&cfg, gemm_bf16x3_kernel<2>, a);
+    if (le != cudaSuccess) { snprintf(g_err, sizeof(g_err), "gemm launch: %s", cudaGetErrorString(le)); cudaGetLastError(); return OPH_ECUDA; }
     if (prof) {
         cudaEventRecord(rec.e1, st);
         std::lock_guard<std::mutex> lk(g_prof_mu);
@@ -151,6 +163,43 @@ int rows_grid(long long rows, int wpb) {
     return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
 }
 
+bool vec_ok(int C, long long ld0, long long ld1 = 4, long long ld2 = 4, long long ld3 = 4, long long ld4 = 4) {
+    return (C == 256 || C == 512 || C == 1024) && !((ld0 | ld1 | ld2 | ld3 | ld4) & 3);
+}
+int bwd_grid(long long rows) {          // few, long-lived warps so that per-channel sums stay in registers
+    long long g = (rows + 8 * 8 - 1) / (8 * 8);
+    return (int)(g < 1 ? 1 : (g > 148 * 2 ? 148 * 2 : g));
+}
+
+int launch_ln_act_fwd(const float* z, long long ldz, const float* gamma, const float* beta, float* y, long long ldy,
+                      float* y_sig, long long ldys, float* stats, long long rows, int C, int act, int norm, float drop_p,
+                      uint64_t seed, const long long* step, cudaStream_t st) {
+    const int grid = rows_grid(rows, 8);
+    if (vec_ok(C, ldz, ldy, y_sig ? ldys : 4)) {
+#define OPH_LAUNCH(V) ln_act_fwd_vec_kernel<V><<<grid, 256, 0, st>>>(z, ldz, gamma, beta, y, ldy, y_sig, ldys, stats, (int)rows, act, norm, drop_p, seed, step)
+        if (C == 256) OPH_LAUNCH(2); else if (C == 512) OPH_LAUNCH(4); else OPH_LAUNCH(8);
+#undef OPH_LAUNCH
+    } else {
+        ln_act_fwd_kernel<<<grid, 256, 0, st>>>(z, ldz, gamma, beta, y, ldy, y_sig, ldys, stats, (int)rows, C, act, norm, drop_p, seed, step);
+    }
+    return check_launch("ln_act_fwd_kernel");
+}
+
+int launch_ln_act_bwd(const float* dy, long long lddy, const float* z, long long ldz, const float* stats,
+                      const float* gamma, const float* beta, float* dz, long long lddz, float* dgamma, float* dbeta,
+                      float* dbias, long long rows, int C, int act, int norm, float drop_p, uint64_t seed,
+                      const long long* step, cudaStream_t st) {
+    const size_t smem = 3 * (size_t)C * sizeof(float);
+    if (vec_ok(C, lddy, ldz, lddz) && C <= 512) {
+        const int grid = bwd_grid(rows);
+        if (C == 256) ln_act_bwd_vec_kernel<2><<<grid, 256, smem, st>>>(dy, lddy, z, ldz, stats, gamma, beta, dz, lddz, dgamma, dbeta, dbias, (int)rows, act, norm, drop_p, seed, step);
+        else          ln_act_bwd_vec_kernel<4><<<grid, 256, smem, st>>>(dy, lddy, z, ldz, stats, gamma, beta, dz, lddz, dgamma, dbeta, dbias, (int)rows, act, norm, drop_p, seed, step);
+    } else {
+        ln_act_bwd_kernel<<<rows_grid(rows, 8), 256, smem, st>>>(dy, lddy, z, ldz, stats, gamma, beta, dz, lddz, dgamma, dbeta, dbias, (int)rows, C, act, norm, drop_p, seed, step);
+    }
+    return check_launch("ln_act_bwd_kernel");
+}
+
 // weight gradient: dW[tap][m][n] += sum_r Amap(r,tap)[m] * Bmap(r,tap)[n]
 int launch_wgrad(const float* a, long long lda, int M, const int* a_off, int aL, int aLs, int a_mul,
                  const float* b, long long ldb, int N, const int* b_off, int bL, int bLs, int b_mul,
@@ -180,6 +229,11 @@ extern "C" {
 int oph_version(void) { return 100; }
 const char* oph_last_error(void) { return g_err; }
 long long oph_launch_count(void) { return g_launches.load(); }
+int oph_set_cluster(int cluster) {
+    if (cluster != 1 && cluster != 2 && cluster != 4) return fail(OPH_EINVAL, "cluster must be 1, 2 or 4%s");
+    g_cluster = cluster;
+    return OPH_OK;
+}
 
 int oph_profile_begin(void) {
     std::lock_guard<std::mutex> lk(g_prof_mu);
@@ -247,10 +301,8 @@ int oph_conv1d_fwd(const float* x, long long ldx, const void* packed_w, const fl
     g.Bpacked = packed_w; g.M = B * L; g.N = Cout; g.Kc = Cin; g.ntaps = k;
     g.C = z; g.ldc = ldz; g.bias = bias; g.tag = OPH_TAG_CONV_FWD;
     OPH_TRY(launch_gemm(g, 1, S(stream)));
-    const long long rows = (long long)B * L;
-    ln_act_fwd_kernel<<<rows_grid(rows, 8), 256, 0, S(stream)>>>(z, ldz, gamma, beta, y, ldy, y_sig, ldys, stats,
-                                                                (int)rows, Cout, act, norm, drop_p, seed, step);
-    return check_launch("ln_act_fwd_kernel");
+    return launch_ln_act_fwd(z, ldz, gamma, beta, y, ldy, y_sig, ldys, stats, (long long)B * L, Cout, act, norm, drop_p,
+                             seed, step, S(stream));
 }
 
 int oph_conv1d_bwd(const float* dy, long long lddy, const float* x, long long ldx, const float* z, long long ldz,
@@ -258,10 +310,8 @@ int oph_conv1d_bwd(const float* dy, long long lddy, const float* x, long long ld
                    long long lddz, float* dx, long long lddx, float* dw, float* dbias, float* dgamma, float* dbeta,
                    int B, int L, int Cin, int Cout, int k, int rate, int padding, int in_shift, int act, int norm,
                    float drop_p, uint64_t seed, const long long* step, oph_stream_t stream) {
-    const long long rows = (long long)B * L;
-    ln_act_bwd_kernel<<<rows_grid(rows, 8), 256, 3 * Cout * sizeof(float), S(stream)>>>(
-        dy, lddy, z, ldz, stats, gamma, beta, dz, lddz, dgamma, dbeta, dbias, (int)rows, Cout, act, norm, drop_p, seed, step);
-    OPH_TRY(check_launch("ln_act_bwd_kernel"));
+    OPH_TRY(launch_ln_act_bwd(dy, lddy, z, ldz, stats, gamma, beta, dz, lddz, dgamma, dbeta, dbias, (long long)B * L, Cout,
+                              act, norm, drop_p, seed, step, S(stream)));
     int off[3];
     conv_offsets(k, rate, padding, in_shift, off);
     if (dx) {
@@ -294,8 +344,14 @@ int oph_hc_fwd(const float* x, long long ldx, const void* packed_w, const float*
     g.C = z; g.ldc = ldz; g.bias = bias; g.tag = OPH_TAG_CONV_FWD;
     OPH_TRY(launch_gemm(g, 1, S(stream)));
     const long long rows = (long long)B * L;
-    hc_post_fwd_kernel<<<rows_grid(rows, 8), 256, 0, S(stream)>>>(z, ldz, x, ldx, g1, b1, g2, b2, y, ldy, stats,
-                                                                 (int)rows, C, norm, drop_p, seed, step);
+    const int grid = rows_grid(rows, 8);
+    if (vec_ok(C, ldz, ldx, ldy)) {
+#define OPH_LAUNCH(V) hc_post_fwd_vec_kernel<V><<<grid, 256, 0, S(stream)>>>(z, ldz, x, ldx, g1, b1, g2, b2, y, ldy, stats, (int)rows, norm, drop_p, seed, step)
+        if (C == 256) OPH_LAUNCH(2); else if (C == 512) OPH_LAUNCH(4); else OPH_LAUNCH(8);
+#undef OPH_LAUNCH
+    } else {
+        hc_post_fwd_kernel<<<grid, 256, 0, S(stream)>>>(z, ldz, x, ldx, g1, b1, g2, b2, y, ldy, stats, (int)rows, C, norm, drop_p, seed, step);
+    }
     return check_launch("hc_post_fwd_kernel");
 }
 
@@ -306,9 +362,16 @@ int oph_hc_bwd(const float* dy, long long lddy, const float* x, long long ldx, c
                int rate, int padding, int norm, float drop_p, uint64_t seed, const long long* step,
                oph_stream_t stream) {
     const long long rows = (long long)B * L;
-    hc_post_bwd_kernel<<<rows_grid(rows, 8), 256, 6 * C * sizeof(float), S(stream)>>>(
-        dy, lddy, z, ldz, x, ldx, stats, g1, b1, g2, b2, dz, lddz, dxres, ldxr, dg1, db1, dg2, db2, dbias,
-        (int)rows, C, norm, drop_p, seed, step);
+    const size_t smem = 6 * (size_t)C * sizeof(float);
+    if (vec_ok(C, lddy, ldz, ldx, lddz, ldxr) && C <= 512) {
+        const int grid = bwd_grid(rows);
+        if (C == 256) hc_post_bwd_vec_kernel<2><<<grid, 256, smem, S(stream)>>>(dy, lddy, z, ldz, x, ldx, stats, g1, b1, g2, b2, dz, lddz, dxres, ldxr, dg1, db1, dg2, db2, dbias, (int)rows, norm, drop_p, seed, step);
+        else          hc_post_bwd_vec_kernel<4><<<grid, 256, smem, S(stream)>>>(dy, lddy, z, ldz, x, ldx, stats, g1, b1, g2, b2, dz, lddz, dxres, ldxr, dg1, db1, dg2, db2, dbias, (int)rows, norm, drop_p, seed, step);
+    } else {
+        hc_post_bwd_kernel<<<rows_grid(rows, 8), 256, smem, S(stream)>>>(
+            dy, lddy, z, ldz, x, ldx, stats, g1, b1, g2, b2, dz, lddz, dxres, ldxr, dg1, db1, dg2, db2, dbias,
+            (int)rows, C, norm, drop_p, seed, step);
+    }
     OPH_TRY(check_launch("hc_post_bwd_kernel"));
     int off[3];
     conv_offsets(k, rate, padding, 0, off);
@@ -343,20 +406,16 @@ int oph_deconv_fwd(const float* x, long long ldx, const void* packed_w, const fl
         g.C = z; g.ldc = ldz; g.c_mul = 2; g.c_off = parity; g.bias = bias; g.tag = OPH_TAG_CONV_FWD;
         OPH_TRY(launch_gemm(g, 1, S(stream)));
     }
-    const long long rows = 2LL * B * L;
-    ln_act_fwd_kernel<<<rows_grid(rows, 8), 256, 0, S(stream)>>>(z, ldz, gamma, beta, y, ldy, nullptr, 0, stats,
-                                                                (int)rows, C, OPH_ACT_NONE, 1, drop_p, seed, step);
-    return check_launch("ln_act_fwd_kernel(deconv)");
+    return launch_ln_act_fwd(z, ldz, gamma, beta, y, ldy, nullptr, 0, stats, 2LL * B * L, C, OPH_ACT_NONE, 1, drop_p, seed,
+                             step, S(stream));
 }
 
 int oph_deconv_bwd(const float* dy, long long lddy, const float* x, long long ldx, const float* z, long long ldz,
                    const float* stats, const void* packed_w_bwd, const float* gamma, const float* beta, float* dz,
                    long long lddz, float* dx, long long lddx, float* dw, float* dbias, float* dgamma, float* dbeta,
                    int B, int L, int C, float drop_p, uint64_t seed, const long long* step, oph_stream_t stream) {
-    const long long rows = 2LL * B * L;
-    ln_act_bwd_kernel<<<rows_grid(rows, 8), 256, 3 * C * sizeof(float), S(stream)>>>(
-        dy, lddy, z, ldz, stats, gamma, beta, dz, lddz, dgamma, dbeta, dbias, (int)rows, C, OPH_ACT_NONE, 1, drop_p, seed, step);
-    OPH_TRY(check_launch("ln_act_bwd_kernel(deconv)"));
+    OPH_TRY(launch_ln_act_bwd(dy, lddy, z, ldz, stats, gamma, beta, dz, lddz, dgamma, dbeta, dbias, 2LL * B * L, C,
+                              OPH_ACT_NONE, 1, drop_p, seed, step, S(stream)));
     if (dx) {   // dx[i] = W0^T dz[2i] + W1^T dz[2i+1] + W2^T dz[2i+2]
         GemmArgs g = blank();
         g.a_mode = A_KMAJOR; g.b_mode = B_PACKED;

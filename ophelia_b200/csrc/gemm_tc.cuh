@@ -50,8 +50,11 @@ constexpr int A_PLANE = GEMM_BM * GEMM_BK * 2;      // 16 KiB  (one bf16 plane)
 constexpr int B_PLANE = GEMM_BNH * GEMM_BK * 2;     // 32 KiB
 constexpr int A_SLOT = 2 * A_PLANE;                 // hi + lo
 constexpr int B_SLOT = 2 * B_PLANE;
+constexpr int NA_SLOTS = 3;                         // A ring depth
+constexpr int NB_SLOTS = 2;                         // B ring depth
 constexpr int GEMM_THREADS = 320;                   // 8 producer/epilogue warps + MMA warp + bulk-copy warp
-constexpr int GEMM_SMEM = 2 * A_SLOT + 2 * B_SLOT + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int GEMM_SMEM = NA_SLOTS * A_SLOT + NB_SLOTS * B_SLOT + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int GEMM_MAX_CLUSTER = 4;                 // CTAs (consecutive M tiles) sharing multicast weight stages
 
 __device__ __forceinline__ void load8(const float* src, bool row_ok, int first, int limit, float (&v)[8]) {
     if (row_ok && first + 8 <= limit) {
@@ -80,16 +83,23 @@ __device__ __forceinline__ bool map_row(const OperandMap& o, int r, int tap, lon
     return ts >= 0 && ts < o.Ls;
 }
 
+// barrier indices
+constexpr int BAR_FULL_A = 0;                          // [NA_SLOTS]
+constexpr int BAR_EMPTY_A = BAR_FULL_A + NA_SLOTS;     // [NA_SLOTS]
+constexpr int BAR_FULL_B = BAR_EMPTY_A + NA_SLOTS;     // [NB_SLOTS]
+constexpr int BAR_EMPTY_B = BAR_FULL_B + NB_SLOTS;     // [NB_SLOTS]
+constexpr int BAR_ACCUM = BAR_EMPTY_B + NB_SLOTS;
+constexpr int NUM_BARS = BAR_ACCUM + 1;
+
 template <int NH>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
-    uint8_t* sA = smem;                       // 2 slots
-    uint8_t* sB = smem + 2 * A_SLOT;          // 2 slots
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * A_SLOT + 2 * B_SLOT);
-    // bars: [0,1] fullA  [2,3] emptyA  [4,5] fullB  [6,7] emptyB  [8] accum  ; then tmem address word
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + NA_SLOTS * A_SLOT;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NA_SLOTS * A_SLOT + NB_SLOTS * B_SLOT);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NUM_BARS);
     const uint32_t bar0 = smem_u32(bars);
     auto BAR = [&](int i) { return bar0 + 8u * i; };
 
@@ -98,9 +108,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
     const int nblocks = (p.N + NT - 1) / NT;
     const int nb = blockIdx.y % nblocks;
     const int ytap = blockIdx.y / nblocks;
-    const int m0 = blockIdx.x * GEMM_BM;
+    const int m0 = blockIdx.x * GEMM_BM;               // may lie beyond M for cluster-padding CTAs (they only feed the ring)
     const int n0 = nb * NT;
     const int z = blockIdx.z;
+    const uint32_t csize = cluster_nctarank();         // CTAs of one cluster share the packed-B stages by multicast
+    const uint32_t crank = cluster_ctarank();
+    const uint16_t cmask = (uint16_t)((1u << csize) - 1u);
 
     int k_begin = 0, k_end = p.Kc;
     long long a_z = 0, b_z = 0, c_z = 0;
@@ -109,22 +122,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
     const int KBc = (k_end - k_begin + GEMM_BK - 1) / GEMM_BK;
     const int ntl = (p.a_mode == A_KMAJOR) ? p.ntaps : 1;
     const int KB = ntl * KBc;
-    if (KB <= 0) return;
+    if (KB <= 0) return;                               // uniform over the cluster (depends on z only)
 
     if (tid == 0) {
         const uint32_t nprod = 8;
-        mbar_init(BAR(0), nprod); mbar_init(BAR(1), nprod);
-        mbar_init(BAR(2), 1); mbar_init(BAR(3), 1);
-        const uint32_t nb_arr = (p.b_mode == B_PACKED) ? 1u : nprod;
-        mbar_init(BAR(4), nb_arr); mbar_init(BAR(5), nb_arr);
-        mbar_init(BAR(6), 1); mbar_init(BAR(7), 1);
-        mbar_init(BAR(8), 1);
+        for (int i = 0; i < NA_SLOTS; ++i) { mbar_init(BAR(BAR_FULL_A + i), nprod); mbar_init(BAR(BAR_EMPTY_A + i), 1); }
+        const uint32_t full_b = (p.b_mode == B_PACKED) ? 1u : nprod;
+        const uint32_t empty_b = (p.b_mode == B_PACKED) ? csize : 1u;   // every CTA of the cluster must release a multicast slot
+        for (int i = 0; i < NB_SLOTS; ++i) { mbar_init(BAR(BAR_FULL_B + i), full_b); mbar_init(BAR(BAR_EMPTY_B + i), empty_b); }
+        mbar_init(BAR(BAR_ACCUM), 1);
         mbar_fence_init();
         fence_proxy_async();
     }
     if (warp == 8) tmem_alloc<NT>(smem_u32(tmem_slot));
     tc_fence_before();
-    __syncthreads();
+    if (csize > 1) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -132,8 +144,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
         // ================================================================ producers
         const float* Ap = p.A.ptr + a_z;
         const float* Bp = (p.b_mode == B_PACKED) ? nullptr : (p.Bm.ptr + b_z);
-        // conv-style A: 4 rows per thread, fixed for the whole tile
-        int a_t[4]; long long a_base[4]; bool a_ok[4];
+        int a_t[4]; long long a_base[4]; bool a_ok[4];   // conv-style A: 4 rows per thread, fixed for the whole tile
         if (p.a_mode == A_KMAJOR) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -144,52 +155,61 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
                 a_base[i] = (long long)b * p.A.Ls;
             }
         }
-        for (int kb = 0; kb < KB; ++kb) {
+        // global -> register load of this thread's 4 chunks of the A tile of k-block kb
+        auto load_a = [&](int kb, float (&v)[4][8]) {
             const int tap = (p.a_mode == A_KMAJOR) ? kb / KBc : ytap;
-            const int cb = kb - (kb / KBc) * KBc;
-            const int kk0 = k_begin + cb * GEMM_BK;
-            // ---------------- A tile
-            {
-                float v[4][8];
-                uint32_t soff[4];
-                if (p.a_mode == A_KMAJOR) {
-                    const int chunk = tid & 7, c = kk0 + chunk * 8;
+            const int kk0 = k_begin + (kb - (kb / KBc) * KBc) * GEMM_BK;
+            if (p.a_mode == A_KMAJOR) {
+                const int c = kk0 + (tid & 7) * 8;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int rl = (tid >> 3) + 32 * i;
-                        const int ts = a_t[i] * p.A.mul + p.A.off[tap];
-                        const bool ok = a_ok[i] && ts >= 0 && ts < p.A.Ls;
-                        const float* src = Ap + (a_base[i] + ts) * p.A.ld + c;
-                        load8(src, ok, c, k_end, v[i]);
-                        soff[i] = rl * 128 + ((chunk ^ (rl & 7)) << 4);
-                    }
-                } else {
-                    const int j = tid & 15, m = m0 + j * 8;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int rl = (tid >> 4) + 16 * i;
-                        const int r = kk0 + rl;
-                        long long srow;
-                        bool ok = map_row(p.A, r, tap, srow) && r < k_end;
-                        const float* src = Ap + srow * p.A.ld + m;
-                        load8(src, ok, m, p.M, v[i]);
-                        soff[i] = (j >> 3) * 8192 + (rl >> 3) * 1024 + (rl & 7) * 128 + (((j & 7) ^ (rl & 7)) << 4);
-                    }
+                for (int i = 0; i < 4; ++i) {
+                    const int ts = a_t[i] * p.A.mul + p.A.off[tap];
+                    const bool ok = a_ok[i] && ts >= 0 && ts < p.A.Ls;
+                    load8(Ap + (a_base[i] + ts) * p.A.ld + c, ok, c, k_end, v[i]);
                 }
-                const int slot = kb & 1;
-                mbar_wait(BAR(2 + slot), ((kb >> 1) & 1) ^ 1);
+            } else {
+                const int m = m0 + (tid & 15) * 8;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int r = kk0 + (tid >> 4) + 16 * i;
+                    long long srow;
+                    const bool ok = map_row(p.A, r, tap, srow) && r < k_end;
+                    load8(Ap + srow * p.A.ld + m, ok, m, p.M, v[i]);
+                }
+            }
+        };
+        uint32_t a_soff[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (p.a_mode == A_KMAJOR) {
+                const int rl = (tid >> 3) + 32 * i, chunk = tid & 7;
+                a_soff[i] = rl * 128 + ((chunk ^ (rl & 7)) << 4);
+            } else {
+                const int rl = (tid >> 4) + 16 * i, j = tid & 15;
+                a_soff[i] = (j >> 3) * 8192 + (rl >> 3) * 1024 + (rl & 7) * 128 + (((j & 7) ^ (rl & 7)) << 4);
+            }
+        }
+        float va[4][8], vn[4][8];
+        load_a(0, va);
+        for (int kb = 0; kb < KB; ++kb) {
+            if (kb + 1 < KB) load_a(kb + 1, vn);           // next tile's loads are in flight while this one is converted
+            {
+                const int slot = kb % NA_SLOTS;
+                mbar_wait(BAR(BAR_EMPTY_A + slot), ((kb / NA_SLOTS) & 1) ^ 1);
                 uint8_t* hi = sA + slot * A_SLOT;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) store_split(hi, hi + A_PLANE, soff[i], v[i]);
+                for (int i = 0; i < 4; ++i) store_split(hi, hi + A_PLANE, a_soff[i], va[i]);
                 fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(BAR(0 + slot));
+                if (lane == 0) mbar_arrive(BAR(BAR_FULL_A + slot));
             }
             // ---------------- B tile(s) from fp32 activations
             if (p.b_mode != B_PACKED) {
+                const int tap = (p.a_mode == A_KMAJOR) ? kb / KBc : ytap;
+                const int kk0 = k_begin + (kb - (kb / KBc) * KBc) * GEMM_BK;
 #pragma unroll 1
                 for (int h = 0; h < NH; ++h) {
-                    const int bi = kb * NH + h, slot = bi & 1;
+                    const int bi = kb * NH + h, slot = bi % NB_SLOTS;
                     uint8_t* hi = sB + slot * B_SLOT;
 #pragma unroll 1
                     for (int half = 0; half < 2; ++half) {      // 2 x 4 chunks per thread keeps registers bounded
@@ -201,8 +221,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
                             for (int i = 0; i < 4; ++i) {
                                 const int nl = (tid >> 3) + 32 * (i + 4 * half);
                                 const int n = n0 + h * GEMM_BNH + nl;
-                                const float* src = Bp + (long long)n * p.Bm.ld + c;
-                                load8(src, n < p.N, c, k_end, v[i]);
+                                load8(Bp + (long long)n * p.Bm.ld + c, n < p.N, c, k_end, v[i]);
                                 soff[i] = nl * 128 + ((chunk ^ (nl & 7)) << 4);
                             }
                         } else {
@@ -212,20 +231,25 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
                                 const int rl = (tid >> 5) + 8 * (i + 4 * half);
                                 const int r = kk0 + rl;
                                 long long srow;
-                                bool ok = map_row(p.Bm, r, tap, srow) && r < k_end;
-                                const float* src = Bp + srow * p.Bm.ld + n;
-                                load8(src, ok, n, p.N, v[i]);
+                                const bool ok = map_row(p.Bm, r, tap, srow) && r < k_end;
+                                load8(Bp + srow * p.Bm.ld + n, ok, n, p.N, v[i]);
                                 soff[i] = (j >> 3) * 8192 + (rl >> 3) * 1024 + (rl & 7) * 128 + (((j & 7) ^ (rl & 7)) << 4);
                             }
                         }
-                        if (half == 0) mbar_wait(BAR(6 + slot), ((bi >> 1) & 1) ^ 1);
+                        if (half == 0) mbar_wait(BAR(BAR_EMPTY_B + slot), ((bi / NB_SLOTS) & 1) ^ 1);
 #pragma unroll
                         for (int i = 0; i < 4; ++i) store_split(hi, hi + B_PLANE, soff[i], v[i]);
                     }
                     fence_proxy_async();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(BAR(4 + slot));
+                    if (lane == 0) mbar_arrive(BAR(BAR_FULL_B + slot));
                 }
+            }
+            if (kb + 1 < KB) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) va[i][e] = vn[i][e];
             }
         }
     } else if (warp == 8) {
@@ -237,13 +261,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
             const uint32_t b_step = (p.b_mode == B_MNMAJOR) ? 2048u : 32u;
             const uint32_t b_lbo = (p.b_mode == B_MNMAJOR) ? 8192u : 16u;
             const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
+            const bool mcast = (p.b_mode == B_PACKED) && csize > 1;
             for (int kb = 0; kb < KB; ++kb) {
-                const int as = kb & 1;
-                mbar_wait(BAR(0 + as), (kb >> 1) & 1);
+                const int as = kb % NA_SLOTS;
+                mbar_wait(BAR(BAR_FULL_A + as), (kb / NA_SLOTS) & 1);
                 const uint32_t a_hi = sA_addr + as * A_SLOT, a_lo = a_hi + A_PLANE;
                 for (int h = 0; h < NH; ++h) {
-                    const int bi = kb * NH + h, bs = bi & 1;
-                    mbar_wait(BAR(4 + bs), (bi >> 1) & 1);
+                    const int bi = kb * NH + h, bs = bi % NB_SLOTS;
+                    mbar_wait(BAR(BAR_FULL_B + bs), (bi / NB_SLOTS) & 1);
                     tc_fence_after();
                     const uint32_t b_hi = sB_addr + bs * B_SLOT, b_lo = b_hi + B_PLANE;
                     const uint32_t d = tmem_base + h * GEMM_BNH;
@@ -257,11 +282,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
                         umma_bf16(d, dah, dbl, idesc, 1);
                         umma_bf16(d, dal, dbh, idesc, 1);
                     }
-                    umma_commit(BAR(6 + bs));       // B slot free once these MMAs retire
+                    // B slot free once these MMAs retire; a multicast slot must be released in every CTA of the cluster
+                    if (mcast) umma_commit_mcast(BAR(BAR_EMPTY_B + bs), cmask); else umma_commit(BAR(BAR_EMPTY_B + bs));
                 }
-                umma_commit(BAR(2 + as));           // A slot free
+                umma_commit(BAR(BAR_EMPTY_A + as));    // A slot free
             }
-            umma_commit(BAR(8));                    // accumulator complete
+            umma_commit(BAR(BAR_ACCUM));               // accumulator complete
         }
         __syncwarp();
     } else {
@@ -269,11 +295,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
         if (lane == 0 && p.b_mode == B_PACKED) {
             const uint8_t* src = reinterpret_cast<const uint8_t*>(p.Bpacked) + (size_t)nb * KB * NH * B_SLOT;
             const int total = KB * NH;
+            const uint32_t share = B_SLOT / csize;      // each CTA fetches 1/csize of a stage and multicasts it
             for (int bi = 0; bi < total; ++bi) {
-                const int slot = bi & 1;
-                mbar_wait(BAR(6 + slot), ((bi >> 1) & 1) ^ 1);
-                mbar_arrive_expect_tx(BAR(4 + slot), B_SLOT);
-                bulk_g2s(smem_u32(sB + slot * B_SLOT), src + (size_t)bi * B_SLOT, B_SLOT, BAR(4 + slot));
+                const int slot = bi % NB_SLOTS;
+                mbar_wait(BAR(BAR_EMPTY_B + slot), ((bi / NB_SLOTS) & 1) ^ 1);
+                mbar_arrive_expect_tx(BAR(BAR_FULL_B + slot), B_SLOT);
+                const uint32_t dst = smem_u32(sB + slot * B_SLOT) + crank * share;
+                const uint8_t* s_ = src + (size_t)bi * B_SLOT + crank * share;
+                if (csize > 1) bulk_g2s_mcast(dst, s_, share, BAR(BAR_FULL_B + slot), cmask);
+                else bulk_g2s(dst, s_, share, BAR(BAR_FULL_B + slot));
             }
         }
         __syncwarp();
@@ -281,41 +311,44 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
 
     // ==================================================================== epilogue (warps 0..7)
     if (warp < 8) {
-        mbar_wait(BAR(8), 0);
+        mbar_wait(BAR(BAR_ACCUM), 0);
         tc_fence_after();
         const int q = warp & 3, colhalf = warp >> 2;
         float* stage = reinterpret_cast<float*>(sA) + warp * (32 * 33);   // operand ring is idle now
         float* Cb = p.C + c_z + (long long)ytap * p.c_tap_stride;
         const float* addb = p.addend ? p.addend + c_z + (long long)ytap * p.c_tap_stride : nullptr;
         constexpr int CH = NT / 2 / 32;
-        for (int ch = 0; ch < CH; ++ch) {
-            const int col0 = colhalf * (NT / 2) + ch * 32;
-            if (n0 + col0 >= p.N) break;           // warp-uniform
-            uint32_t r[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + col0, r);
-            tmem_ld_wait();
+        if (m0 + q * 32 < p.M) {
+            for (int ch = 0; ch < CH; ++ch) {
+                const int col0 = colhalf * (NT / 2) + ch * 32;
+                if (n0 + col0 >= p.N) break;           // warp-uniform
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + col0, r);
+                tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = __uint_as_float(r[j]);
-            __syncwarp();
-            const int gcol = n0 + col0 + lane;
-            const bool col_ok = gcol < p.N;
-            const float bv = (p.bias && col_ok) ? __ldg(p.bias + gcol) : 0.f;
-            for (int rr = 0; rr < 32; ++rr) {
-                const int grow = m0 + q * 32 + rr;
-                if (grow >= p.M) break;            // warp-uniform
-                if (col_ok) {
-                    const long long crow = (long long)grow * p.c_mul + p.c_off;
-                    float val = stage[rr * 33 + lane] * p.alpha + bv;
-                    if (addb) val += __ldg(addb + crow * p.ld_add + gcol);
-                    float* dst = Cb + crow * p.ldc + gcol;
-                    if (p.atomic) atomicAdd(dst, val); else *dst = val;
+                for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = __uint_as_float(r[j]);
+                __syncwarp();
+                const int gcol = n0 + col0 + lane;
+                const bool col_ok = gcol < p.N;
+                const float bv = (p.bias && col_ok) ? __ldg(p.bias + gcol) : 0.f;
+                for (int rr = 0; rr < 32; ++rr) {
+                    const int grow = m0 + q * 32 + rr;
+                    if (grow >= p.M) break;            // warp-uniform
+                    if (col_ok) {
+                        const long long crow = (long long)grow * p.c_mul + p.c_off;
+                        float val = stage[rr * 33 + lane] * p.alpha + bv;
+                        if (addb) val += __ldg(addb + crow * p.ld_add + gcol);
+                        float* dst = Cb + crow * p.ldc + gcol;
+                        if (p.atomic) atomicAdd(dst, val); else *dst = val;
+                    }
                 }
+                __syncwarp();
             }
-            __syncwarp();
         }
         tc_fence_before();
     }
-    __syncthreads();
+    // peers may still multicast-arrive on this CTA's barriers until they are done too
+    if (csize > 1) cluster_sync_all(); else __syncthreads();
     if (warp == 8) tmem_dealloc<NT>(tmem_base);
 }
 

@@ -422,3 +422,269 @@ __global__ void adam_clip_kernel(float* __restrict__ p, float* __restrict__ m, f
 }
 
 }  // namespace oph
+
+// =================================================================================================
+// Vectorised fast paths for C = 128*VEC (256, 512, 1024): each lane owns 4*VEC channels as float4s, the row lives
+// in registers (one HBM read per element), per-channel sums of the backward pass accumulate in registers across
+// the rows a warp owns and are flushed once per warp.
+namespace oph {
+
+template <int VEC>
+__device__ __forceinline__ void ld_row(const float* __restrict__ p, int lane, float4 (&v)[VEC]) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) v[i] = __ldg(reinterpret_cast<const float4*>(p + i * 128 + lane * 4));
+}
+template <int VEC>
+__device__ __forceinline__ void st_row(float* __restrict__ p, int lane, const float4 (&v)[VEC]) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) *reinterpret_cast<float4*>(p + i * 128 + lane * 4) = v[i];
+}
+template <int VEC>
+__device__ __forceinline__ RowStats reg_stats(const float4 (&v)[VEC]) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    const float mean = warp_sum(s) * (1.f / (128.f * VEC));
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+        q += (a * a + b * b) + (c * c + d * d);
+    }
+    const float var = warp_sum(q) * (1.f / (128.f * VEC));
+    return {mean, rsqrtf(var + LN_EPS)};
+}
+#define OPH_F4(v, e) (reinterpret_cast<float*>(&(v))[e])
+
+template <int VEC>
+__global__ void __launch_bounds__(256) hc_post_fwd_vec_kernel(
+        const float* __restrict__ z, long long ldz, const float* __restrict__ x, long long ldx,
+        const float* __restrict__ g1, const float* __restrict__ b1, const float* __restrict__ g2,
+        const float* __restrict__ b2, float* __restrict__ y, long long ldy, float* __restrict__ stats,
+        int rows, int norm, float drop_p, unsigned long long seed, const long long* step) {
+    constexpr int C = 128 * VEC;
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+    const unsigned long long sd = eff_seed(seed, step);
+    float4 G1[VEC], B1[VEC], G2[VEC], B2[VEC];
+    if (norm) { ld_row<VEC>(g1, lane, G1); ld_row<VEC>(b1, lane, B1); ld_row<VEC>(g2, lane, G2); ld_row<VEC>(b2, lane, B2); }
+    for (long long row = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * wpb) {
+        float4 z1[VEC], z2[VEC], xv[VEC], o[VEC];
+        ld_row<VEC>(z + row * ldz, lane, z1);
+        ld_row<VEC>(z + row * ldz + C, lane, z2);
+        ld_row<VEC>(x + row * ldx, lane, xv);
+        RowStats s1 = {0.f, 1.f}, s2 = {0.f, 1.f};
+        if (norm) { s1 = reg_stats<VEC>(z1); s2 = reg_stats<VEC>(z2); }
+        if (stats && lane == 0) *reinterpret_cast<float4*>(stats + row * 4) = make_float4(s1.mean, s1.rstd, s2.mean, s2.rstd);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float u1 = OPH_F4(z1[i], e), u2 = OPH_F4(z2[i], e);
+                if (norm) {
+                    u1 = (u1 - s1.mean) * s1.rstd * OPH_F4(G1[i], e) + OPH_F4(B1[i], e);
+                    u2 = (u2 - s2.mean) * s2.rstd * OPH_F4(G2[i], e) + OPH_F4(B2[i], e);
+                }
+                const float g = sigmoidf_(u1);
+                float r = g * u2 + (1.f - g) * OPH_F4(xv[i], e);
+                if (drop_p > 0.f) r *= drop_scale(sd, (unsigned long long)row * C + i * 128 + lane * 4 + e, drop_p, inv_keep);
+                OPH_F4(o[i], e) = r;
+            }
+        st_row<VEC>(y + row * ldy, lane, o);
+    }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256) ln_act_fwd_vec_kernel(
+        const float* __restrict__ z, long long ldz, const float* __restrict__ gamma, const float* __restrict__ beta,
+        float* __restrict__ y, long long ldy, float* __restrict__ y_sig, long long ldys, float* __restrict__ stats,
+        int rows, int act, int norm, float drop_p, unsigned long long seed, const long long* step) {
+    constexpr int C = 128 * VEC;
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+    const unsigned long long sd = eff_seed(seed, step);
+    float4 G[VEC], Bt[VEC];
+    if (norm) { ld_row<VEC>(gamma, lane, G); ld_row<VEC>(beta, lane, Bt); }
+    for (long long row = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * wpb) {
+        float4 zv[VEC], o[VEC], sg[VEC];
+        ld_row<VEC>(z + row * ldz, lane, zv);
+        RowStats st = {0.f, 1.f};
+        if (norm) st = reg_stats<VEC>(zv);
+        if (stats && lane == 0) *reinterpret_cast<float2*>(stats + row * 2) = make_float2(st.mean, st.rstd);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float u = OPH_F4(zv[i], e);
+                if (norm) u = (u - st.mean) * st.rstd * OPH_F4(G[i], e) + OPH_F4(Bt[i], e);
+                if (y_sig) OPH_F4(sg[i], e) = sigmoidf_(u);
+                float a = act == 1 ? fmaxf(u, 0.f) : u;
+                if (drop_p > 0.f) a *= drop_scale(sd, (unsigned long long)row * C + i * 128 + lane * 4 + e, drop_p, inv_keep);
+                OPH_F4(o[i], e) = a;
+            }
+        st_row<VEC>(y + row * ldy, lane, o);
+        if (y_sig) st_row<VEC>(y_sig + row * ldys, lane, sg);
+    }
+}
+
+// flush per-lane register accumulators: shared atomics (one per lane and channel per warp), then global atomics
+template <int VEC, int NACC>
+__device__ __forceinline__ void flush_acc(float (&acc)[NACC][VEC * 4], float* sacc, int lane, float* const (&dst)[NACC]) {
+    constexpr int C = 128 * VEC;
+#pragma unroll
+    for (int k = 0; k < NACC; ++k)
+#pragma unroll
+        for (int i = 0; i < VEC; ++i)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) atomicAdd(&sacc[k * C + i * 128 + lane * 4 + e], acc[k][i * 4 + e]);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < NACC * C; idx += blockDim.x) {
+        float* d = dst[idx / C];
+        if (d) atomicAdd(d + (idx % C), sacc[idx]);
+    }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256) hc_post_bwd_vec_kernel(
+        const float* __restrict__ dy, long long lddy, const float* __restrict__ z, long long ldz,
+        const float* __restrict__ x, long long ldx, const float* __restrict__ stats,
+        const float* __restrict__ g1, const float* __restrict__ b1, const float* __restrict__ g2,
+        const float* __restrict__ b2, float* __restrict__ dz, long long lddz, float* __restrict__ dxres, long long lddx,
+        float* __restrict__ dg1, float* __restrict__ db1, float* __restrict__ dg2, float* __restrict__ db2,
+        float* __restrict__ dbias, int rows, int norm, float drop_p, unsigned long long seed, const long long* step) {
+    constexpr int C = 128 * VEC;
+    extern __shared__ float sacc[];            // [6][C]
+    for (int i = threadIdx.x; i < 6 * C; i += blockDim.x) sacc[i] = 0.f;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+    const float invC = 1.f / (float)C;
+    const unsigned long long sd = eff_seed(seed, step);
+    float4 G1[VEC], B1[VEC], G2[VEC], B2[VEC];
+    if (norm) { ld_row<VEC>(g1, lane, G1); ld_row<VEC>(b1, lane, B1); ld_row<VEC>(g2, lane, G2); ld_row<VEC>(b2, lane, B2); }
+    float acc[6][VEC * 4];                     // dg1, db1, dg2, db2, dbias(H1), dbias(H2)
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+#pragma unroll
+        for (int i = 0; i < VEC * 4; ++i) acc[k][i] = 0.f;
+    for (long long row = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * wpb) {
+        float4 z1[VEC], z2[VEC], xv[VEC], dv[VEC];
+        ld_row<VEC>(z + row * ldz, lane, z1);
+        ld_row<VEC>(z + row * ldz + C, lane, z2);
+        ld_row<VEC>(x + row * ldx, lane, xv);
+        ld_row<VEC>(dy + row * lddy, lane, dv);
+        float m1 = 0.f, r1 = 1.f, m2 = 0.f, r2 = 1.f;
+        if (norm) { const float4 s = __ldg(reinterpret_cast<const float4*>(stats + row * 4)); m1 = s.x; r1 = s.y; m2 = s.z; r2 = s.w; }
+        float a1 = 0.f, a2 = 0.f, c1 = 0.f, c2 = 0.f;
+        float4 e1v[VEC], e2v[VEC], xr[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float xh1 = norm ? (OPH_F4(z1[i], e) - m1) * r1 : OPH_F4(z1[i], e);
+                const float xh2 = norm ? (OPH_F4(z2[i], e) - m2) * r2 : OPH_F4(z2[i], e);
+                const float u1 = norm ? xh1 * OPH_F4(G1[i], e) + OPH_F4(B1[i], e) : xh1;
+                const float h = norm ? xh2 * OPH_F4(G2[i], e) + OPH_F4(B2[i], e) : xh2;
+                const float g = sigmoidf_(u1);
+                float d_o = OPH_F4(dv[i], e);
+                if (drop_p > 0.f) d_o *= drop_scale(sd, (unsigned long long)row * C + i * 128 + lane * 4 + e, drop_p, inv_keep);
+                OPH_F4(xr[i], e) = d_o * (1.f - g);
+                const float du1 = d_o * (h - OPH_F4(xv[i], e)) * g * (1.f - g);
+                const float du2 = d_o * g;
+                if (norm) {
+                    acc[0][i * 4 + e] += du1 * xh1; acc[1][i * 4 + e] += du1;
+                    acc[2][i * 4 + e] += du2 * xh2; acc[3][i * 4 + e] += du2;
+                    const float e1 = du1 * OPH_F4(G1[i], e), e2 = du2 * OPH_F4(G2[i], e);
+                    a1 += e1; a2 += e1 * xh1; c1 += e2; c2 += e2 * xh2;
+                    OPH_F4(e1v[i], e) = e1; OPH_F4(e2v[i], e) = e2;
+                    OPH_F4(z1[i], e) = xh1; OPH_F4(z2[i], e) = xh2;     // keep x-hat for the second half
+                } else {
+                    OPH_F4(e1v[i], e) = du1; OPH_F4(e2v[i], e) = du2;
+                    acc[4][i * 4 + e] += du1; acc[5][i * 4 + e] += du2;
+                }
+            }
+        st_row<VEC>(dxres + row * lddx, lane, xr);
+        if (norm) {
+            a1 = warp_sum(a1) * invC; a2 = warp_sum(a2) * invC; c1 = warp_sum(c1) * invC; c2 = warp_sum(c2) * invC;
+#pragma unroll
+            for (int i = 0; i < VEC; ++i)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float d1 = r1 * (OPH_F4(e1v[i], e) - a1 - OPH_F4(z1[i], e) * a2);
+                    const float d2 = r2 * (OPH_F4(e2v[i], e) - c1 - OPH_F4(z2[i], e) * c2);
+                    OPH_F4(e1v[i], e) = d1; OPH_F4(e2v[i], e) = d2;
+                    acc[4][i * 4 + e] += d1; acc[5][i * 4 + e] += d2;
+                }
+        }
+        st_row<VEC>(dz + row * lddz, lane, e1v);
+        st_row<VEC>(dz + row * lddz + C, lane, e2v);
+    }
+    float* const dst[6] = {norm ? dg1 : nullptr, norm ? db1 : nullptr, norm ? dg2 : nullptr, norm ? db2 : nullptr,
+                           dbias, dbias ? dbias + C : nullptr};
+    flush_acc<VEC, 6>(acc, sacc, lane, dst);
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256) ln_act_bwd_vec_kernel(
+        const float* __restrict__ dy, long long lddy, const float* __restrict__ z, long long ldz,
+        const float* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
+        float* __restrict__ dz, long long lddz, float* __restrict__ dgamma, float* __restrict__ dbeta,
+        float* __restrict__ dbias, int rows, int act, int norm, float drop_p, unsigned long long seed,
+        const long long* step) {
+    constexpr int C = 128 * VEC;
+    extern __shared__ float sacc[];            // [3][C]
+    for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) sacc[i] = 0.f;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+    const float invC = 1.f / (float)C;
+    const unsigned long long sd = eff_seed(seed, step);
+    float4 G[VEC], Bt[VEC];
+    if (norm) { ld_row<VEC>(gamma, lane, G); ld_row<VEC>(beta, lane, Bt); }
+    float acc[3][VEC * 4];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int i = 0; i < VEC * 4; ++i) acc[k][i] = 0.f;
+    for (long long row = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * wpb) {
+        float4 zv[VEC], dv[VEC], ev[VEC];
+        ld_row<VEC>(z + row * ldz, lane, zv);
+        ld_row<VEC>(dy + row * lddy, lane, dv);
+        float mean = 0.f, rstd = 1.f;
+        if (norm) { const float2 s = __ldg(reinterpret_cast<const float2*>(stats + row * 2)); mean = s.x; rstd = s.y; }
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float xh = norm ? (OPH_F4(zv[i], e) - mean) * rstd : OPH_F4(zv[i], e);
+                const float u = norm ? xh * OPH_F4(G[i], e) + OPH_F4(Bt[i], e) : xh;
+                float du = OPH_F4(dv[i], e);
+                if (drop_p > 0.f) du *= drop_scale(sd, (unsigned long long)row * C + i * 128 + lane * 4 + e, drop_p, inv_keep);
+                if (act == 1 && !(u > 0.f)) du = 0.f;
+                if (norm) {
+                    acc[0][i * 4 + e] += du * xh; acc[1][i * 4 + e] += du;
+                    const float dxh = du * OPH_F4(G[i], e);
+                    s1 += dxh; s2 += dxh * xh;
+                    OPH_F4(ev[i], e) = dxh; OPH_F4(zv[i], e) = xh;
+                } else {
+                    OPH_F4(ev[i], e) = du; acc[2][i * 4 + e] += du;
+                }
+            }
+        if (norm) {
+            s1 = warp_sum(s1) * invC; s2 = warp_sum(s2) * invC;
+#pragma unroll
+            for (int i = 0; i < VEC; ++i)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float d = rstd * (OPH_F4(ev[i], e) - s1 - OPH_F4(zv[i], e) * s2);
+                    OPH_F4(ev[i], e) = d; acc[2][i * 4 + e] += d;
+                }
+        }
+        st_row<VEC>(dz + row * lddz, lane, ev);
+    }
+    float* const dst[3] = {norm ? dgamma : nullptr, norm ? dbeta : nullptr, dbias};
+    flush_acc<VEC, 3>(acc, sacc, lane, dst);
+}
+
+}  // namespace oph

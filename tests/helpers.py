@@ -32,7 +32,9 @@ def check_grads(ours, ref, strict_prefix, median_tol=1.5e-2, max_tol=5e-2, stric
     pre-activation lies within 2e-5 of the kink take the other branch than in the fp64 oracle.  Each flip perturbs
     every upstream gradient by ~sqrt(flips / units) in Frobenius norm.  Measured on B200 (tools/grad_table.py,
     B=2, T=200): AudioDec C_11 (no ReLU between it and the loss) 1.4e-5, C_10 2.4e-4, C_9 2.7e-3, C_8 and
-    everything upstream 4-6e-3 -- the error steps up exactly at the three ReLU layers and nowhere else.  So:
+    everything upstream 4-6e-3 -- the error steps up exactly at the three ReLU layers and nowhere else.  The L1
+    loss |Y - target| has the same kind of kink (sign flips where |Y - target| < 2e-5), so the tail is only tight
+    when the L1 weight is zero.  So:
     a tight bound on the ReLU-free tail (`strict_prefix`), loose bounds elsewhere; every operator's backward is
     pinned on its own to the 1e-5..1e-4 level in test_gpu_ops.py with near-kink units masked out."""
     errs = sorted(((relerr(ours[n], np.asarray(ref[n])), n) for n in ref), reverse=True)

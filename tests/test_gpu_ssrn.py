@@ -46,8 +46,11 @@ def test_forward_matches_golden_fixture():
     assert maxabs(Zg, z["Z"]) < 1e-3
 
 
-def test_train_step_matches_oracle():
+@pytest.mark.parametrize("l1", [True, False])
+def test_train_step_matches_oracle(l1):
     hp = make_hp(full_dim=513, dropout_rate=0.0)
+    if not l1:
+        hp.lw_mag, hp.lw_bd2, hp.lw_ssrn_l2 = 0.0, 0.7, 0.3
     P = oracle_params(hp, "ssrn", seed=6)
     b = synthetic_batch(hp, 2, 8, 33, seed=12, with_mags=True)
     Pt = ot.to_torch(P, torch.float64, requires_grad=True)
@@ -61,4 +64,5 @@ def test_train_step_matches_oracle():
         comps = g.train_step_device(md, gd).cpu().numpy()
         np.testing.assert_allclose(comps, comps_ref, rtol=2e-4, atol=1e-6)
         if step == 0:
-            check_grads({n: g.store.grads[n].cpu().numpy() for n in grads_ref}, grads_ref, "SSRN/C_16/")
+            check_grads({n: g.store.grads[n].cpu().numpy() for n in grads_ref}, grads_ref, "SSRN/C_16/",
+                        strict_tol=1e-2 if l1 else 2e-4)

@@ -69,10 +69,12 @@ def test_synthesis_mode_window_mask():
     assert (mx == ref["max_attentions"]).mean() > 0.995
 
 
-@pytest.mark.parametrize("shape", [(2, 60, 200), (3, 37, 131)])
-def test_train_step_matches_oracle(shape):
+@pytest.mark.parametrize("shape,l1", [((2, 60, 200), True), ((3, 37, 131), True), ((3, 37, 131), False)])
+def test_train_step_matches_oracle(shape, l1):
     B, N, T = shape
     hp = make_hp(max_N=N, max_T=T, dropout_rate=0.0)
+    if not l1:      # |Y - mel| has a kink too: without the L1 term the ReLU-free tail must match tightly
+        hp.lw_mel, hp.lw_bd1, hp.lw_att, hp.lw_t2m_l2 = 0.0, 0.5, 0.3, 0.2
     P = oracle_params(hp, "t2m", seed=2)
     b = synthetic_batch(hp, B, N, T, ragged=True)
     Pt = ot.to_torch(P, torch.float64, requires_grad=True)
@@ -88,7 +90,8 @@ def test_train_step_matches_oracle(shape):
         np.testing.assert_allclose(comps, comps_ref, rtol=2e-4, atol=1e-6)
         if step == 0:
             sd = g.store.grads
-            check_grads({n: sd[n].cpu().numpy() for n in grads_ref}, grads_ref, "Text2Mel/AudioDec/C_11/")
+            check_grads({n: sd[n].cpu().numpy() for n in grads_ref}, grads_ref, "Text2Mel/AudioDec/C_11/",
+                            strict_tol=1e-2 if l1 else 2e-4)
             row0 = sd["Text2Mel/TextEnc/embed_1/lookup_table"][0].abs().max().item()
             assert row0 == 0.0                                   # zero-pad row gets no gradient (modules.py:38-40)
     assert int(g.store.global_step.item()) == 3

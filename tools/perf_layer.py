@@ -1,0 +1,73 @@
+"""Time (CUDA events) or expose to ncu one layer-shaped call of the hot path.
+  python tools/perf_layer.py --op hc_fwd --B 32 --L 870 --C 256 --k 3 --iters 20
+ops: hc_fwd, hc_bwd, conv_fwd (k=1, C->C), attn_fwd"""
+import argparse
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from ophelia_b200 import _lib, ops  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--op", default="hc_fwd")
+ap.add_argument("--B", type=int, default=32)
+ap.add_argument("--L", type=int, default=870)
+ap.add_argument("--C", type=int, default=256)
+ap.add_argument("--k", type=int, default=3)
+ap.add_argument("--rate", type=int, default=3)
+ap.add_argument("--iters", type=int, default=20)
+ap.add_argument("--warmup", type=int, default=3)
+ap.add_argument("--cluster", type=int, default=4)
+a = ap.parse_args()
+dev = torch.device("cuda:0")
+_lib.call("oph_set_cluster", a.cluster)
+torch.manual_seed(0)
+B, L, C, k = a.B, a.L, a.C, a.k
+x = torch.randn(B, L, C, device=dev)
+w = torch.randn(k, C, 2 * C, device=dev) * (2.6 / (k * C)) ** 0.5
+pk = ops.PackedConv(w)
+bias = torch.zeros(2 * C, device=dev)
+g1 = torch.ones(C, device=dev); b1 = torch.zeros(C, device=dev); g2 = torch.ones(C, device=dev); b2 = torch.zeros(C, device=dev)
+y = torch.empty_like(x)
+dy = torch.randn_like(x)
+grads = [torch.zeros_like(t) for t in (w, bias, g1, b1, g2, b2)]
+_, saved = ops.hc_fwd(x, pk, bias, g1, b1, g2, b2, a.rate, 1, True, save=True, y=y)
+if a.op == "conv_fwd":
+    w1 = torch.randn(1, C, C, device=dev) * (2.6 / C) ** 0.5
+    pk1 = ops.PackedConv(w1)
+
+
+def run():
+    if a.op == "hc_fwd":
+        ops.hc_fwd(x, pk, bias, g1, b1, g2, b2, a.rate, 1, True, y=y)
+    elif a.op == "hc_bwd":
+        ops.hc_bwd(dy, x, saved, pk, g1, b1, g2, b2, *grads, a.rate, 1, True)
+    elif a.op == "conv_fwd":
+        ops.conv1d_fwd(x, pk1, bias[:C], g1, b1, 1, 1, 0, 0, True, y=y)
+    elif a.op == "attn_fwd":
+        Q = x[:, :, :256]; K = torch.randn(B, 180, 256, device=dev); V = torch.randn(B, 180, 256, device=dev)
+        ops.attention_fwd(Q, K, V)
+
+
+for _ in range(a.warmup):
+    run()
+torch.cuda.synchronize()
+lib = _lib.load()
+import ctypes
+lib.oph_profile_begin()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(a.iters):
+    run()
+e1.record()
+torch.cuda.synchronize()
+prof = (ctypes.c_double * 15)()
+lib.oph_profile_end(prof)
+ms = e0.elapsed_time(e1) / a.iters
+print("%s B%d L%d C%d k%d cluster%d: %.3f ms per call" % (a.op, B, L, C, k, a.cluster, ms))
+for i, n in enumerate(["other", "conv_fwd", "dgrad", "wgrad", "attention"]):
+    if prof[3 * i] > 0:
+        print("   gemm[%s]: %d launches/call, %.3f ms each, %.1f TFLOP/s algorithmic" %
+              (n, prof[3 * i] / a.iters, prof[3 * i + 1] / prof[3 * i], prof[3 * i + 2] / prof[3 * i + 1] / 1e9))
