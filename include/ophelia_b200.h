@@ -50,8 +50,6 @@ const char* oph_last_error(void);
 #define OPH_TAG_ATTENTION 4
 #define OPH_NUM_TAGS 5
 long long oph_launch_count(void);
-/* tuning knob: CTAs per cluster (consecutive 128-row tiles) that share each packed-weight stage by multicast */
-int oph_set_cluster(int cluster);
 int oph_profile_begin(void);
 int oph_profile_end(double* out);
 

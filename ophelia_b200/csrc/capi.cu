@@ -17,7 +17,6 @@ namespace {
 
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
-int g_cluster = 4;     // cluster size (CTAs along M) for GEMMs with packed weights; 1, 2 or 4
 
 // Optional per-launch timing of the GEMM core (bench.py roofline): CUDA events around every launch, by tag.
 struct ProfRec { cudaEvent_t e0, e1; int tag; double flops; };
@@ -58,17 +57,9 @@ int launch_gemm(GemmArgs& a, int zdim, cudaStream_t st) {
     const int NT = GEMM_BNH * NH;
     const int nblocks = cdiv(a.N, NT);
     if (a.ytaps < 1) a.ytaps = 1;
-    // CTAs of a cluster work on consecutive M tiles and share every packed-weight stage through one multicast copy
-    int cs = (a.b_mode == B_PACKED) ? g_cluster : 1;
+    // CTA pairs (compile-time cluster of 2) cover two consecutive 128-row tiles; odd tile counts get a padding CTA
     const int mtiles = cdiv(a.M, GEMM_BM);
-    while (cs > 1 && mtiles < cs) cs >>= 1;
-    dim3 grid(cdiv(mtiles, cs) * cs, nblocks * a.ytaps, zdim < 1 ? 1 : zdim);
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = grid; cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = GEMM_SMEM; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    dim3 grid(cdiv(mtiles, 2) * 2, nblocks * a.ytaps, zdim < 1 ? 1 : zdim);
     ProfRec rec{};
     bool prof = false;
     if (g_prof_on) {
@@ -82,9 +73,8 @@ int launch_gemm(GemmArgs& a, int zdim, cudaStream_t st) {
             cudaEventRecord(rec.e0, st);
         }
     }
-    cudaError_t le = (NH == 1) ? cudaLaunchKernelEx(&cfg, gemm_bf16x3_kernel<1>, a)
-                               : cudaLaunchKernelEx(&cfg, gemm_bf16x3_kernel<2>, a);
-    if (le != cudaSuccess) { snprintf(g_err, sizeof(g_err), "gemm launch: %s", cudaGetErrorString(le)); cudaGetLastError(); return OPH_ECUDA; }
+    if (NH == 1) gemm_bf16x3_kernel<1><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(a);
+    else         gemm_bf16x3_kernel<2><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(a);
     if (prof) {
         cudaEventRecord(rec.e1, st);
         std::lock_guard<std::mutex> lk(g_prof_mu);
@@ -129,13 +119,15 @@ __global__ void pack_kernel(const PackArgs p, long long total) {
         const int c = c0 + e;
         v[e] = (n < p.Nvalid && c < p.Cvalid) ? p.w[p.tap_idx[tap] * p.s_tap + c * p.s_c + n * p.s_n] : 0.f;
     }
-    uint8_t* img = p.out + ((size_t)((size_t)nb * KB + kb) * p.NH + h) * B_SLOT;
-    store_split(img, img + B_PLANE, nl * 128 + ((chunk ^ (nl & 7)) << 4), v);
+    // stage image = [CTA 0: hi | lo][CTA 1: hi | lo]; each CTA of the pair stages 128 of the 256 rows
+    uint8_t* img = p.out + ((size_t)((size_t)nb * KB + kb) * p.NH + h) * B_STAGE + (size_t)(nl >> 7) * B_SLOT;
+    const int nr = nl & 127;
+    store_split(img, img + B_PLANE, nr * 128 + ((chunk ^ (nr & 7)) << 4), v);
 }
 
 size_t pack_image_bytes(int ntaps, int Cvalid, int Nvalid) {
     const int NH = nh_for(Nvalid);
-    return (size_t)cdiv(Nvalid, GEMM_BNH * NH) * ntaps * cdiv(Cvalid, GEMM_BK) * NH * B_SLOT;
+    return (size_t)cdiv(Nvalid, GEMM_BNH * NH) * ntaps * cdiv(Cvalid, GEMM_BK) * NH * B_STAGE;
 }
 
 int pack_image(const float* w, int ntaps, const int* tap_idx, long long s_tap, long long s_c, long long s_n,
@@ -145,7 +137,7 @@ int pack_image(const float* w, int ntaps, const int* tap_idx, long long s_tap, l
     for (int i = 0; i < 3; ++i) p.tap_idx[i] = i < ntaps ? tap_idx[i] : 0;
     p.s_tap = s_tap; p.s_c = s_c; p.s_n = s_n; p.Cvalid = Cvalid; p.Nvalid = Nvalid; p.NH = nh_for(Nvalid);
     p.out = reinterpret_cast<uint8_t*>(out);
-    const long long total = (long long)(pack_image_bytes(ntaps, Cvalid, Nvalid) / B_SLOT) * 2048;
+    const long long total = (long long)(pack_image_bytes(ntaps, Cvalid, Nvalid) / B_STAGE) * 2048;
     pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p, total);
     return check_launch("pack_kernel");
 }
@@ -211,8 +203,8 @@ int launch_wgrad(const float* a, long long lda, int M, const int* a_off, int aL,
     for (int j = 0; j < 3; ++j) { g.A.off[j] = j < taps ? a_off[j] : 0; g.Bm.off[j] = j < taps ? b_off[j] : 0; }
     g.M = M; g.N = N; g.Kc = R; g.ytaps = taps; g.c_tap_stride = (long long)M * ldc;
     g.C = dw; g.ldc = ldc; g.atomic = 1; g.z_mode = Z_SPLITK; g.tag = OPH_TAG_WGRAD;
-    const int base = cdiv(M, GEMM_BM) * cdiv(N, GEMM_BNH * nh_for(N)) * taps;
-    int splits = cdiv(2 * 148, base);
+    const int base = cdiv(cdiv(M, GEMM_BM), 2) * cdiv(N, GEMM_BNH * nh_for(N)) * taps;     // CTA pairs before split-K
+    int splits = cdiv(2 * 74, base);
     const int max_splits = cdiv(R, 4 * GEMM_BK);
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
@@ -229,11 +221,6 @@ extern "C" {
 int oph_version(void) { return 100; }
 const char* oph_last_error(void) { return g_err; }
 long long oph_launch_count(void) { return g_launches.load(); }
-int oph_set_cluster(int cluster) {
-    if (cluster != 1 && cluster != 2 && cluster != 4) return fail(OPH_EINVAL, "cluster must be 1, 2 or 4%s");
-    g_cluster = cluster;
-    return OPH_OK;
-}
 
 int oph_profile_begin(void) {
     std::lock_guard<std::mutex> lk(g_prof_mu);

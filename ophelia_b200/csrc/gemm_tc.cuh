@@ -1,9 +1,14 @@
 // Generic implicit-GEMM on tcgen05 with 3-term split-bf16 operands (fp32-grade accuracy):
 //     C[m][n] (+)= alpha * sum_kk A[m][kk] * B[n][kk]  (+ bias[n] + addend[m][n])
 //     A*B ~= Ahi*Bhi + Ahi*Blo + Alo*Bhi   (bf16 operands, fp32 accumulate in TMEM)
-// One CTA owns a 128-row x (256*NH)-column accumulator tile in tensor memory.  fp32 activations are split
-// into (hi, lo) bf16 planes by the producer warps on their way into SWIZZLE_128B shared-memory tiles;
-// pre-packed weight images arrive through the bulk-copy (TMA) engine.  One thread issues tcgen05.mma.
+//
+// A CTA PAIR (cluster of 2, tcgen05 cta_group::2) owns a 256-row x (256*NH)-column tile: each CTA holds its own 128
+// rows of the accumulator in its tensor memory and stages its own 128 rows of A plus HALF of every B stage; the MMA
+// unit reads the other half from the partner's shared memory.  That halves the B bytes that have to be delivered
+// into each SM per MMA cycle -- the binding limit of the 1-CTA version was the L2->SM fabric (profiles/), not the
+// tensor pipe.  fp32 activations are split into (hi, lo) bf16 planes by the producer warps on their way into
+// SWIZZLE_128B shared-memory tiles; pre-packed weight images arrive through the bulk-copy (TMA) engine.
+// One thread of the leader CTA issues every tcgen05.mma of the pair.
 #pragma once
 #include "oph_ptx.cuh"
 
@@ -23,7 +28,7 @@ struct OperandMap {        // logical row r -> (item b, step t) = divmod(r, L); 
 struct GemmArgs {
     int a_mode, b_mode;
     OperandMap A, Bm;
-    const void* Bpacked;   // B_PACKED: [nblock][kb][half][hi 32 KiB | lo 32 KiB] shared-memory images
+    const void* Bpacked;   // B_PACKED: [nblock][kb][half][cta 0: hi 16 KiB | lo 16 KiB][cta 1: hi | lo] smem images
     int M, N;              // valid output rows / columns
     int Kc;                // reduction extent per tap (channels for conv-style A, rows for MN-major A)
     int ntaps;             // taps looped inside the CTA (conv-style A)
@@ -43,18 +48,19 @@ struct GemmArgs {
     int tag;               // host-side profiling category (OPH_TAG_*)
 };
 
-constexpr int GEMM_BM = 128;
+constexpr int GEMM_BM = 128;                        // rows per CTA (256 per pair)
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_BNH = 256;
+constexpr int GEMM_BNH = 256;                       // columns per MMA instruction
+constexpr int GEMM_BNC = GEMM_BNH / 2;              // B rows staged by each CTA of the pair
 constexpr int A_PLANE = GEMM_BM * GEMM_BK * 2;      // 16 KiB  (one bf16 plane)
-constexpr int B_PLANE = GEMM_BNH * GEMM_BK * 2;     // 32 KiB
+constexpr int B_PLANE = GEMM_BNC * GEMM_BK * 2;     // 16 KiB
 constexpr int A_SLOT = 2 * A_PLANE;                 // hi + lo
-constexpr int B_SLOT = 2 * B_PLANE;
-constexpr int NA_SLOTS = 3;                         // A ring depth
-constexpr int NB_SLOTS = 2;                         // B ring depth
-constexpr int GEMM_THREADS = 320;                   // 8 producer/epilogue warps + MMA warp + bulk-copy warp
+constexpr int B_SLOT = 2 * B_PLANE;                 // per CTA
+constexpr int B_STAGE = 2 * B_SLOT;                 // both CTAs: one (k-block, half) of the packed image
+constexpr int NA_SLOTS = 3;
+constexpr int NB_SLOTS = 4;
+constexpr int GEMM_THREADS = 352;                   // 8 producer/epilogue warps + MMA + bulk-copy + relay warps
 constexpr int GEMM_SMEM = NA_SLOTS * A_SLOT + NB_SLOTS * B_SLOT + 1024 /*align*/ + 256 /*barriers*/;
-constexpr int GEMM_MAX_CLUSTER = 4;                 // CTAs (consecutive M tiles) sharing multicast weight stages
 
 __device__ __forceinline__ void load8(const float* src, bool row_ok, int first, int limit, float (&v)[8]) {
     if (row_ok && first + 8 <= limit) {
@@ -83,16 +89,18 @@ __device__ __forceinline__ bool map_row(const OperandMap& o, int r, int tap, lon
     return ts >= 0 && ts < o.Ls;
 }
 
-// barrier indices
-constexpr int BAR_FULL_A = 0;                          // [NA_SLOTS]
-constexpr int BAR_EMPTY_A = BAR_FULL_A + NA_SLOTS;     // [NA_SLOTS]
+// barrier indices (same layout in both CTAs; FULL_* are only used in the leader, LAND_B only in the partner)
+constexpr int BAR_FULL_A = 0;                          // [NA_SLOTS] 16 producer-warp arrivals (8 per CTA)
+constexpr int BAR_EMPTY_A = BAR_FULL_A + NA_SLOTS;     // [NA_SLOTS] leader's commit, multicast to both CTAs
 constexpr int BAR_FULL_B = BAR_EMPTY_A + NA_SLOTS;     // [NB_SLOTS]
 constexpr int BAR_EMPTY_B = BAR_FULL_B + NB_SLOTS;     // [NB_SLOTS]
-constexpr int BAR_ACCUM = BAR_EMPTY_B + NB_SLOTS;
+constexpr int BAR_LAND_B = BAR_EMPTY_B + NB_SLOTS;     // [NB_SLOTS] partner: its bulk copy landed (relayed to the leader)
+constexpr int BAR_ACCUM = BAR_LAND_B + NB_SLOTS;
 constexpr int NUM_BARS = BAR_ACCUM + 1;
 
 template <int NH>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -108,12 +116,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
     const int nblocks = (p.N + NT - 1) / NT;
     const int nb = blockIdx.y % nblocks;
     const int ytap = blockIdx.y / nblocks;
-    const int m0 = blockIdx.x * GEMM_BM;               // may lie beyond M for cluster-padding CTAs (they only feed the ring)
+    const uint32_t crank = cluster_ctarank();          // 0 = leader (issues the MMAs), 1 = partner
+    const int m0 = blockIdx.x * GEMM_BM;               // may lie beyond M for the padding CTA of the last pair
     const int n0 = nb * NT;
     const int z = blockIdx.z;
-    const uint32_t csize = cluster_nctarank();         // CTAs of one cluster share the packed-B stages by multicast
-    const uint32_t crank = cluster_ctarank();
-    const uint16_t cmask = (uint16_t)((1u << csize) - 1u);
 
     int k_begin = 0, k_end = p.Kc;
     long long a_z = 0, b_z = 0, c_z = 0;
@@ -122,128 +128,185 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
     const int KBc = (k_end - k_begin + GEMM_BK - 1) / GEMM_BK;
     const int ntl = (p.a_mode == A_KMAJOR) ? p.ntaps : 1;
     const int KB = ntl * KBc;
-    if (KB <= 0) return;                               // uniform over the cluster (depends on z only)
+    if (KB <= 0) return;                               // uniform over the pair (depends on z only)
+    const bool packed = p.b_mode == B_PACKED;
 
     if (tid == 0) {
-        const uint32_t nprod = 8;
-        for (int i = 0; i < NA_SLOTS; ++i) { mbar_init(BAR(BAR_FULL_A + i), nprod); mbar_init(BAR(BAR_EMPTY_A + i), 1); }
-        const uint32_t full_b = (p.b_mode == B_PACKED) ? 1u : nprod;
-        const uint32_t empty_b = (p.b_mode == B_PACKED) ? csize : 1u;   // every CTA of the cluster must release a multicast slot
-        for (int i = 0; i < NB_SLOTS; ++i) { mbar_init(BAR(BAR_FULL_B + i), full_b); mbar_init(BAR(BAR_EMPTY_B + i), empty_b); }
+        for (int i = 0; i < NA_SLOTS; ++i) { mbar_init(BAR(BAR_FULL_A + i), 16); mbar_init(BAR(BAR_EMPTY_A + i), 1); }
+        for (int i = 0; i < NB_SLOTS; ++i) {
+            mbar_init(BAR(BAR_FULL_B + i), packed ? 2 : 16);     // packed: leader's expect_tx arrive + partner's relay
+            mbar_init(BAR(BAR_EMPTY_B + i), 1);
+            mbar_init(BAR(BAR_LAND_B + i), 1);
+        }
         mbar_init(BAR(BAR_ACCUM), 1);
         mbar_fence_init();
         fence_proxy_async();
     }
-    if (warp == 8) tmem_alloc<NT>(smem_u32(tmem_slot));
+    if (warp == 8) tmem_alloc2<NT>(smem_u32(tmem_slot));
     tc_fence_before();
-    if (csize > 1) cluster_sync_all(); else __syncthreads();
+    cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp < 8) {
-        // ================================================================ producers
+        // ================================================================ producers (both CTAs)
+        // Each thread owns 4 chunks (8 consecutive elements each) of every operand tile.  All address arithmetic is
+        // hoisted: row pointers are set up once per tap (conv-style A) or advanced incrementally (row-reduction
+        // operands), so that a k-block costs loads + conversion + stores and little else.
         const float* Ap = p.A.ptr + a_z;
-        const float* Bp = (p.b_mode == B_PACKED) ? nullptr : (p.Bm.ptr + b_z);
-        int a_t[4]; long long a_base[4]; bool a_ok[4];   // conv-style A: 4 rows per thread, fixed for the whole tile
-        if (p.a_mode == A_KMAJOR) {
+        const float* Bp = packed ? nullptr : (p.Bm.ptr + b_z);
+        const bool a_k = p.a_mode == A_KMAJOR;
+
+        // ---- shared-memory offsets of the 4 chunks: K-major [128 rows][64 k] or MN-major [64 k][128 mn] tiles
+        uint32_t off_a[4], off_b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int rl = (tid >> 3) + 32 * i, chunk = tid & 7;
+            const uint32_t ok_ = rl * 128 + ((chunk ^ (rl & 7)) << 4);
+            const int kl = (tid >> 4) + 16 * i, j = tid & 15;
+            const uint32_t omn = (j >> 3) * 8192 + (kl >> 3) * 1024 + (kl & 7) * 128 + (((j & 7) ^ (kl & 7)) << 4);
+            off_a[i] = a_k ? ok_ : omn;
+            off_b[i] = (p.b_mode == B_KMAJOR) ? ok_ : omn;
+        }
+
+        // ---- A load stream state (runs one k-block ahead of the store stream)
+        int la_tap = 0, la_cb = 0;
+        const float* a_cur[4]; bool a_val[4];
+        int a_t[4]; long long a_base[4]; bool a_ok[4];       // conv rows (K-major) / reduction rows (MN-major)
+        int ar_b[4], ar_t[4], ar_r[4];
+        if (a_k) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                int g = m0 + (tid >> 3) + 32 * i;
+                const int g = m0 + (tid >> 3) + 32 * i;
                 a_ok[i] = g < p.M;
-                int b = g / p.A.L;
+                const int b = g / p.A.L;
                 a_t[i] = g - b * p.A.L;
                 a_base[i] = (long long)b * p.A.Ls;
             }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                ar_r[i] = k_begin + (tid >> 4) + 16 * i;
+                ar_b[i] = ar_r[i] / p.A.L;
+                ar_t[i] = ar_r[i] - ar_b[i] * p.A.L;
+            }
         }
-        // global -> register load of this thread's 4 chunks of the A tile of k-block kb
-        auto load_a = [&](int kb, float (&v)[4][8]) {
-            const int tap = (p.a_mode == A_KMAJOR) ? kb / KBc : ytap;
-            const int kk0 = k_begin + (kb - (kb / KBc) * KBc) * GEMM_BK;
-            if (p.a_mode == A_KMAJOR) {
-                const int c = kk0 + (tid & 7) * 8;
+        auto a_set_tap = [&](int tap) {                        // K-major: row pointers of this tap
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int ts = a_t[i] * p.A.mul + p.A.off[tap];
+                a_val[i] = a_ok[i] && ts >= 0 && ts < p.A.Ls;
+                a_cur[i] = Ap + (a_base[i] + ts) * p.A.ld + (tid & 7) * 8;
+            }
+        };
+        if (a_k) a_set_tap(0);
+        auto load_a = [&](float (&v)[4][8]) {                  // loads the next k-block of the stream, then advances it
+            if (a_k) {
+                const int c = k_begin + la_cb * GEMM_BK + (tid & 7) * 8;
+                const bool full = c + 8 <= k_end;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const int ts = a_t[i] * p.A.mul + p.A.off[tap];
-                    const bool ok = a_ok[i] && ts >= 0 && ts < p.A.Ls;
-                    load8(Ap + (a_base[i] + ts) * p.A.ld + c, ok, c, k_end, v[i]);
+                    const float* src = a_cur[i] + (k_begin + la_cb * GEMM_BK);
+                    if (full) {
+                        float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
+                        if (a_val[i]) { x0 = __ldg(reinterpret_cast<const float4*>(src)); x1 = __ldg(reinterpret_cast<const float4*>(src) + 1); }
+                        v[i][0] = x0.x; v[i][1] = x0.y; v[i][2] = x0.z; v[i][3] = x0.w;
+                        v[i][4] = x1.x; v[i][5] = x1.y; v[i][6] = x1.z; v[i][7] = x1.w;
+                    } else {
+                        load8(src, a_val[i], c, k_end, v[i]);
+                    }
                 }
+                if (++la_cb == KBc) { la_cb = 0; if (++la_tap < ntl) a_set_tap(la_tap); }
             } else {
                 const int m = m0 + (tid & 15) * 8;
+                const bool full = m + 8 <= p.M;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const int r = kk0 + (tid >> 4) + 16 * i;
-                    long long srow;
-                    const bool ok = map_row(p.A, r, tap, srow) && r < k_end;
-                    load8(Ap + srow * p.A.ld + m, ok, m, p.M, v[i]);
+                    const int ts = ar_t[i] * p.A.mul + p.A.off[ytap];
+                    const bool ok = ts >= 0 && ts < p.A.Ls && ar_r[i] < k_end;
+                    const float* src = Ap + ((long long)ar_b[i] * p.A.Ls + ts) * p.A.ld + m;
+                    if (full) {
+                        float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
+                        if (ok) { x0 = __ldg(reinterpret_cast<const float4*>(src)); x1 = __ldg(reinterpret_cast<const float4*>(src) + 1); }
+                        v[i][0] = x0.x; v[i][1] = x0.y; v[i][2] = x0.z; v[i][3] = x0.w;
+                        v[i][4] = x1.x; v[i][5] = x1.y; v[i][6] = x1.z; v[i][7] = x1.w;
+                    } else {
+                        load8(src, ok, m, p.M, v[i]);
+                    }
+                    ar_r[i] += GEMM_BK; ar_t[i] += GEMM_BK;
+                    while (ar_t[i] >= p.A.L) { ar_t[i] -= p.A.L; ++ar_b[i]; }
                 }
             }
         };
-        uint32_t a_soff[4];
+
+        // ---- B from fp32 activations: this CTA stages rows/columns [n0 + h*256 + crank*128, +128) of every stage
+        int br_b[4], br_t[4], br_r[4];                         // MN-major B: reduction rows, advanced once per k-block
+        if (p.b_mode == B_MNMAJOR) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            if (p.a_mode == A_KMAJOR) {
-                const int rl = (tid >> 3) + 32 * i, chunk = tid & 7;
-                a_soff[i] = rl * 128 + ((chunk ^ (rl & 7)) << 4);
-            } else {
-                const int rl = (tid >> 4) + 16 * i, j = tid & 15;
-                a_soff[i] = (j >> 3) * 8192 + (rl >> 3) * 1024 + (rl & 7) * 128 + (((j & 7) ^ (rl & 7)) << 4);
+            for (int i = 0; i < 4; ++i) {
+                br_r[i] = k_begin + (tid >> 4) + 16 * i;
+                br_b[i] = br_r[i] / p.Bm.L;
+                br_t[i] = br_r[i] - br_b[i] * p.Bm.L;
             }
         }
-        float va[4][8], vn[4][8];
-        load_a(0, va);
-        for (int kb = 0; kb < KB; ++kb) {
-            if (kb + 1 < KB) load_a(kb + 1, vn);           // next tile's loads are in flight while this one is converted
-            {
-                const int slot = kb % NA_SLOTS;
-                mbar_wait(BAR(BAR_EMPTY_A + slot), ((kb / NA_SLOTS) & 1) ^ 1);
-                uint8_t* hi = sA + slot * A_SLOT;
+        auto load_b = [&](int kb, int h, float (&v)[4][8]) {
+            const int nbase = n0 + h * GEMM_BNH + (int)crank * GEMM_BNC;
+            if (p.b_mode == B_KMAJOR) {
+                const int c = k_begin + (kb - (kb / KBc) * KBc) * GEMM_BK + (tid & 7) * 8;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) store_split(hi, hi + A_PLANE, a_soff[i], va[i]);
+                for (int i = 0; i < 4; ++i) {
+                    const int n = nbase + (tid >> 3) + 32 * i;
+                    load8(Bp + (long long)n * p.Bm.ld + c, n < p.N, c, k_end, v[i]);
+                }
+            } else {
+                const int tap = a_k ? kb / KBc : ytap;
+                const int n = nbase + (tid & 15) * 8;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int ts = br_t[i] * p.Bm.mul + p.Bm.off[tap];
+                    const bool ok = ts >= 0 && ts < p.Bm.Ls && br_r[i] < k_end;
+                    load8(Bp + ((long long)br_b[i] * p.Bm.Ls + ts) * p.Bm.ld + n, ok, n, p.N, v[i]);
+                }
+            }
+        };
+        auto advance_b = [&]() {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                br_r[i] += GEMM_BK; br_t[i] += GEMM_BK;
+                while (br_t[i] >= p.Bm.L) { br_t[i] -= p.Bm.L; ++br_b[i]; }
+            }
+        };
+
+        float va[4][8], vn[4][8];
+        load_a(va);
+        int a_slot = 0, a_par = 1, b_slot = 0, b_par = 1;      // ring cursors: parity to wait for on the EMPTY barriers
+        for (int kb = 0; kb < KB; ++kb) {
+            if (kb + 1 < KB) load_a(vn);                       // next tile's loads are in flight while this one is converted
+            {
+                mbar_wait(BAR(BAR_EMPTY_A + a_slot), a_par);
+                uint8_t* hi = sA + a_slot * A_SLOT;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) store_split(hi, hi + A_PLANE, off_a[i], va[i]);
                 fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(BAR(BAR_FULL_A + slot));
+                if (lane == 0) mbar_arrive_remote(BAR(BAR_FULL_A + a_slot), 0);
+                if (++a_slot == NA_SLOTS) { a_slot = 0; a_par ^= 1; }
             }
-            // ---------------- B tile(s) from fp32 activations
-            if (p.b_mode != B_PACKED) {
-                const int tap = (p.a_mode == A_KMAJOR) ? kb / KBc : ytap;
-                const int kk0 = k_begin + (kb - (kb / KBc) * KBc) * GEMM_BK;
+            if (!packed) {
 #pragma unroll 1
                 for (int h = 0; h < NH; ++h) {
-                    const int bi = kb * NH + h, slot = bi % NB_SLOTS;
-                    uint8_t* hi = sB + slot * B_SLOT;
-#pragma unroll 1
-                    for (int half = 0; half < 2; ++half) {      // 2 x 4 chunks per thread keeps registers bounded
-                        float v[4][8];
-                        uint32_t soff[4];
-                        if (p.b_mode == B_KMAJOR) {
-                            const int chunk = tid & 7, c = kk0 + chunk * 8;
+                    float v[4][8];
+                    load_b(kb, h, v);
+                    mbar_wait(BAR(BAR_EMPTY_B + b_slot), b_par);
+                    uint8_t* hi = sB + b_slot * B_SLOT;
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const int nl = (tid >> 3) + 32 * (i + 4 * half);
-                                const int n = n0 + h * GEMM_BNH + nl;
-                                load8(Bp + (long long)n * p.Bm.ld + c, n < p.N, c, k_end, v[i]);
-                                soff[i] = nl * 128 + ((chunk ^ (nl & 7)) << 4);
-                            }
-                        } else {
-                            const int j = tid & 31, n = n0 + h * GEMM_BNH + j * 8;
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const int rl = (tid >> 5) + 8 * (i + 4 * half);
-                                const int r = kk0 + rl;
-                                long long srow;
-                                const bool ok = map_row(p.Bm, r, tap, srow) && r < k_end;
-                                load8(Bp + srow * p.Bm.ld + n, ok, n, p.N, v[i]);
-                                soff[i] = (j >> 3) * 8192 + (rl >> 3) * 1024 + (rl & 7) * 128 + (((j & 7) ^ (rl & 7)) << 4);
-                            }
-                        }
-                        if (half == 0) mbar_wait(BAR(BAR_EMPTY_B + slot), ((bi / NB_SLOTS) & 1) ^ 1);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) store_split(hi, hi + B_PLANE, soff[i], v[i]);
-                    }
+                    for (int i = 0; i < 4; ++i) store_split(hi, hi + B_PLANE, off_b[i], v[i]);
                     fence_proxy_async();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(BAR(BAR_FULL_B + slot));
+                    if (lane == 0) mbar_arrive_remote(BAR(BAR_FULL_B + b_slot), 0);
+                    if (++b_slot == NB_SLOTS) { b_slot = 0; b_par ^= 1; }
                 }
+                if (p.b_mode == B_MNMAJOR) advance_b();
             }
             if (kb + 1 < KB) {
 #pragma unroll
@@ -253,22 +316,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
             }
         }
     } else if (warp == 8) {
-        // ================================================================ MMA issuer (one thread)
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc_bf16(GEMM_BM, GEMM_BNH, p.a_mode == A_MNMAJOR, p.b_mode == B_MNMAJOR);
+        // ================================================================ MMA issuer: one thread of the leader CTA
+        if (lane == 0 && crank == 0) {
+            const uint32_t idesc = make_idesc_bf16(2 * GEMM_BM, GEMM_BNH, p.a_mode == A_MNMAJOR, p.b_mode == B_MNMAJOR);
             const uint32_t a_step = (p.a_mode == A_MNMAJOR) ? 2048u : 32u;
             const uint32_t a_lbo = (p.a_mode == A_MNMAJOR) ? 8192u : 16u;
             const uint32_t b_step = (p.b_mode == B_MNMAJOR) ? 2048u : 32u;
             const uint32_t b_lbo = (p.b_mode == B_MNMAJOR) ? 8192u : 16u;
             const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
-            const bool mcast = (p.b_mode == B_PACKED) && csize > 1;
+            int as = 0, a_par = 0, bs = 0, b_par = 0;
             for (int kb = 0; kb < KB; ++kb) {
-                const int as = kb % NA_SLOTS;
-                mbar_wait(BAR(BAR_FULL_A + as), (kb / NA_SLOTS) & 1);
+                mbar_wait(BAR(BAR_FULL_A + as), a_par);
                 const uint32_t a_hi = sA_addr + as * A_SLOT, a_lo = a_hi + A_PLANE;
                 for (int h = 0; h < NH; ++h) {
-                    const int bi = kb * NH + h, bs = bi % NB_SLOTS;
-                    mbar_wait(BAR(BAR_FULL_B + bs), (bi / NB_SLOTS) & 1);
+                    mbar_wait(BAR(BAR_FULL_B + bs), b_par);
                     tc_fence_after();
                     const uint32_t b_hi = sB_addr + bs * B_SLOT, b_lo = b_hi + B_PLANE;
                     const uint32_t d = tmem_base + h * GEMM_BNH;
@@ -278,38 +339,47 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
                         const uint64_t dal = make_sdesc(a_lo + ks * a_step, a_lbo, 1024);
                         const uint64_t dbh = make_sdesc(b_hi + ks * b_step, b_lbo, 1024);
                         const uint64_t dbl = make_sdesc(b_lo + ks * b_step, b_lbo, 1024);
-                        umma_bf16(d, dah, dbh, idesc, (kb | ks) != 0);
-                        umma_bf16(d, dah, dbl, idesc, 1);
-                        umma_bf16(d, dal, dbh, idesc, 1);
+                        umma2_bf16(d, dah, dbh, idesc, (kb | ks) != 0);
+                        umma2_bf16(d, dah, dbl, idesc, 1);
+                        umma2_bf16(d, dal, dbh, idesc, 1);
                     }
-                    // B slot free once these MMAs retire; a multicast slot must be released in every CTA of the cluster
-                    if (mcast) umma_commit_mcast(BAR(BAR_EMPTY_B + bs), cmask); else umma_commit(BAR(BAR_EMPTY_B + bs));
+                    umma2_commit_mcast(BAR(BAR_EMPTY_B + bs), 3);   // frees the B slot in both CTAs
+                    if (++bs == NB_SLOTS) { bs = 0; b_par ^= 1; }
                 }
-                umma_commit(BAR(BAR_EMPTY_A + as));    // A slot free
+                umma2_commit_mcast(BAR(BAR_EMPTY_A + as), 3);       // frees the A slot in both CTAs
+                if (++as == NA_SLOTS) { as = 0; a_par ^= 1; }
             }
-            umma_commit(BAR(BAR_ACCUM));               // accumulator complete
+            umma2_commit_mcast(BAR(BAR_ACCUM), 3);                  // accumulators of both CTAs complete
         }
         __syncwarp();
-    } else {
+    } else if (warp == 9) {
         // ================================================================ packed-weight loader (bulk copy engine)
-        if (lane == 0 && p.b_mode == B_PACKED) {
-            const uint8_t* src = reinterpret_cast<const uint8_t*>(p.Bpacked) + (size_t)nb * KB * NH * B_SLOT;
+        if (lane == 0 && packed) {
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(p.Bpacked) + (size_t)nb * KB * NH * B_STAGE + crank * B_SLOT;
             const int total = KB * NH;
-            const uint32_t share = B_SLOT / csize;      // each CTA fetches 1/csize of a stage and multicasts it
             for (int bi = 0; bi < total; ++bi) {
                 const int slot = bi % NB_SLOTS;
                 mbar_wait(BAR(BAR_EMPTY_B + slot), ((bi / NB_SLOTS) & 1) ^ 1);
-                mbar_arrive_expect_tx(BAR(BAR_FULL_B + slot), B_SLOT);
-                const uint32_t dst = smem_u32(sB + slot * B_SLOT) + crank * share;
-                const uint8_t* s_ = src + (size_t)bi * B_SLOT + crank * share;
-                if (csize > 1) bulk_g2s_mcast(dst, s_, share, BAR(BAR_FULL_B + slot), cmask);
-                else bulk_g2s(dst, s_, share, BAR(BAR_FULL_B + slot));
+                const uint32_t bar = BAR((crank == 0 ? BAR_FULL_B : BAR_LAND_B) + slot);
+                mbar_arrive_expect_tx(bar, B_SLOT);
+                bulk_g2s(smem_u32(sB + slot * B_SLOT), src + (size_t)bi * B_STAGE, B_SLOT, bar);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ================================================================ partner: tell the leader a B stage has landed
+        if (lane == 0 && packed && crank == 1) {
+            const int total = KB * NH;
+            for (int bi = 0; bi < total; ++bi) {
+                const int slot = bi % NB_SLOTS;
+                mbar_wait(BAR(BAR_LAND_B + slot), (bi / NB_SLOTS) & 1);
+                mbar_arrive_remote(BAR(BAR_FULL_B + slot), 0);
             }
         }
         __syncwarp();
     }
 
-    // ==================================================================== epilogue (warps 0..7)
+    // ==================================================================== epilogue (warps 0..7 of both CTAs)
     if (warp < 8) {
         mbar_wait(BAR(BAR_ACCUM), 0);
         tc_fence_after();
@@ -331,15 +401,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
                 const int gcol = n0 + col0 + lane;
                 const bool col_ok = gcol < p.N;
                 const float bv = (p.bias && col_ok) ? __ldg(p.bias + gcol) : 0.f;
-                for (int rr = 0; rr < 32; ++rr) {
-                    const int grow = m0 + q * 32 + rr;
-                    if (grow >= p.M) break;            // warp-uniform
-                    if (col_ok) {
-                        const long long crow = (long long)grow * p.c_mul + p.c_off;
-                        float val = stage[rr * 33 + lane] * p.alpha + bv;
-                        if (addb) val += __ldg(addb + crow * p.ld_add + gcol);
-                        float* dst = Cb + crow * p.ldc + gcol;
-                        if (p.atomic) atomicAdd(dst, val); else *dst = val;
+                const int grow0 = m0 + q * 32;
+                const int nrows = min(32, p.M - grow0);
+                const long long crow0 = (long long)grow0 * p.c_mul + p.c_off;
+                float* dst = Cb + crow0 * p.ldc + gcol;
+                const float* add = addb ? addb + crow0 * p.ld_add + gcol : nullptr;
+                const long long dstep = (long long)p.c_mul * p.ldc, astep = (long long)p.c_mul * p.ld_add;
+                if (col_ok) {
+                    if (p.atomic) {
+                        for (int rr = 0; rr < nrows; ++rr, dst += dstep) atomicAdd(dst, stage[rr * 33 + lane] * p.alpha + bv);
+                    } else if (add) {
+                        for (int rr = 0; rr < nrows; ++rr, dst += dstep, add += astep) *dst = stage[rr * 33 + lane] * p.alpha + bv + __ldg(add);
+                    } else {
+#pragma unroll 4
+                        for (int rr = 0; rr < nrows; ++rr, dst += dstep) *dst = stage[rr * 33 + lane] * p.alpha + bv;
                     }
                 }
                 __syncwarp();
@@ -347,9 +422,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
         }
         tc_fence_before();
     }
-    // peers may still multicast-arrive on this CTA's barriers until they are done too
-    if (csize > 1) cluster_sync_all(); else __syncthreads();
-    if (warp == 8) tmem_dealloc<NT>(tmem_base);
+    cluster_sync_all();                                // the partner's smem/barriers stay alive until both are done
+    if (warp == 8) tmem_dealloc2<NT>(tmem_base);
 }
 
 }  // namespace oph

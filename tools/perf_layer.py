@@ -22,7 +22,6 @@ ap.add_argument("--warmup", type=int, default=3)
 ap.add_argument("--cluster", type=int, default=4)
 a = ap.parse_args()
 dev = torch.device("cuda:0")
-_lib.call("oph_set_cluster", a.cluster)
 torch.manual_seed(0)
 B, L, C, k = a.B, a.L, a.C, a.k
 x = torch.randn(B, L, C, device=dev)
