@@ -41,25 +41,22 @@ int check_launch(const char* what) {
 
 inline cudaStream_t S(oph_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
-inline int nh_for(int N) { return N > GEMM_BNH ? 2 : 1; }
 
 int launch_gemm(GemmArgs& a, int zdim, cudaStream_t st) {
     static bool attr_done = false;
     if (!attr_done) {
-        if (cudaFuncSetAttribute(gemm_bf16x3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM) != cudaSuccess ||
-            cudaFuncSetAttribute(gemm_bf16x3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM) != cudaSuccess)
+        if (cudaFuncSetAttribute(gemm_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM) != cudaSuccess)
             return check_launch("cudaFuncSetAttribute(gemm)");
         attr_done = true;
     }
     if (a.M <= 0 || a.N <= 0 || a.Kc <= 0) return fail(OPH_EINVAL, "gemm: empty problem%s");
     if ((a.A.ld & 3) || (a.b_mode != B_PACKED && (a.Bm.ld & 3))) return fail(OPH_EINVAL, "gemm: row strides must be multiples of 4%s");
-    const int NH = nh_for(a.N);
-    const int NT = GEMM_BNH * NH;
-    const int nblocks = cdiv(a.N, NT);
     if (a.ytaps < 1) a.ytaps = 1;
-    // CTA pairs (compile-time cluster of 2) cover two consecutive 128-row tiles; odd tile counts get a padding CTA
-    const int mtiles = cdiv(a.M, GEMM_BM);
-    dim3 grid(cdiv(mtiles, 2) * 2, nblocks * a.ytaps, zdim < 1 ? 1 : zdim);
+    a.zdim = zdim < 1 ? 1 : zdim;
+    // persistent CTA pairs: work units = (pair of 128-row tiles) x (256-column block) x tap x z slice
+    const long long units = (long long)cdiv(cdiv(a.M, GEMM_BM), 2) * cdiv(a.N, GEMM_BN) * a.ytaps * a.zdim;
+    const int pairs = (int)(units < GEMM_MAX_PAIRS ? units : GEMM_MAX_PAIRS);
+    dim3 grid(2 * pairs);
     ProfRec rec{};
     bool prof = false;
     if (g_prof_on) {
@@ -69,12 +66,11 @@ int launch_gemm(GemmArgs& a, int zdim, cudaStream_t st) {
             prof = true;
             cudaEventCreate(&rec.e0); cudaEventCreate(&rec.e1);
             rec.tag = a.tag;
-            rec.flops = 2.0 * a.M * a.N * a.Kc * (a.a_mode == A_KMAJOR ? a.ntaps : a.ytaps) * (a.z_mode == Z_BATCH ? zdim : 1);
+            rec.flops = 2.0 * a.M * a.N * a.Kc * (a.a_mode == A_KMAJOR ? a.ntaps : a.ytaps) * (a.z_mode == Z_BATCH ? a.zdim : 1);
             cudaEventRecord(rec.e0, st);
         }
     }
-    if (NH == 1) gemm_bf16x3_kernel<1><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(a);
-    else         gemm_bf16x3_kernel<2><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(a);
+    gemm_bf16x3_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(a);
     if (prof) {
         cudaEventRecord(rec.e1, st);
         std::lock_guard<std::mutex> lk(g_prof_mu);
@@ -96,22 +92,21 @@ struct PackArgs {
     const float* w;
     int ntaps, tap_idx[3];
     long long s_tap, s_c, s_n;
-    int Cvalid, Nvalid, NH;
+    int Cvalid, Nvalid;
     uint8_t* out;
 };
 
 __global__ void pack_kernel(const PackArgs p, long long total) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
-    const int KBc = (p.Cvalid + GEMM_BK - 1) / GEMM_BK, KB = p.ntaps * KBc, NT = GEMM_BNH * p.NH;
+    const int KBc = (p.Cvalid + GEMM_BK - 1) / GEMM_BK, KB = p.ntaps * KBc;
     const int nl = (int)(idx & 255);
     const int chunk = (int)((idx >> 8) & 7);
-    long long rest = idx >> 11;
-    const int h = (int)(rest % p.NH); rest /= p.NH;
+    const long long rest = idx >> 11;
     const int kb = (int)(rest % KB);
     const int nb = (int)(rest / KB);
     const int tap = kb / KBc, cb = kb - tap * KBc;
-    const int n = nb * NT + h * GEMM_BNH + nl;
+    const int n = nb * GEMM_BN + nl;
     const int c0 = cb * GEMM_BK + chunk * 8;
     float v[8];
 #pragma unroll
@@ -120,14 +115,13 @@ __global__ void pack_kernel(const PackArgs p, long long total) {
         v[e] = (n < p.Nvalid && c < p.Cvalid) ? p.w[p.tap_idx[tap] * p.s_tap + c * p.s_c + n * p.s_n] : 0.f;
     }
     // stage image = [CTA 0: hi | lo][CTA 1: hi | lo]; each CTA of the pair stages 128 of the 256 rows
-    uint8_t* img = p.out + ((size_t)((size_t)nb * KB + kb) * p.NH + h) * B_STAGE + (size_t)(nl >> 7) * B_SLOT;
+    uint8_t* img = p.out + ((size_t)nb * KB + kb) * B_STAGE + (size_t)(nl >> 7) * B_SLOT;
     const int nr = nl & 127;
     store_split(img, img + B_PLANE, nr * 128 + ((chunk ^ (nr & 7)) << 4), v);
 }
 
 size_t pack_image_bytes(int ntaps, int Cvalid, int Nvalid) {
-    const int NH = nh_for(Nvalid);
-    return (size_t)cdiv(Nvalid, GEMM_BNH * NH) * ntaps * cdiv(Cvalid, GEMM_BK) * NH * B_STAGE;
+    return (size_t)cdiv(Nvalid, GEMM_BN) * ntaps * cdiv(Cvalid, GEMM_BK) * B_STAGE;
 }
 
 int pack_image(const float* w, int ntaps, const int* tap_idx, long long s_tap, long long s_c, long long s_n,
@@ -135,7 +129,7 @@ int pack_image(const float* w, int ntaps, const int* tap_idx, long long s_tap, l
     PackArgs p;
     p.w = w; p.ntaps = ntaps;
     for (int i = 0; i < 3; ++i) p.tap_idx[i] = i < ntaps ? tap_idx[i] : 0;
-    p.s_tap = s_tap; p.s_c = s_c; p.s_n = s_n; p.Cvalid = Cvalid; p.Nvalid = Nvalid; p.NH = nh_for(Nvalid);
+    p.s_tap = s_tap; p.s_c = s_c; p.s_n = s_n; p.Cvalid = Cvalid; p.Nvalid = Nvalid;
     p.out = reinterpret_cast<uint8_t*>(out);
     const long long total = (long long)(pack_image_bytes(ntaps, Cvalid, Nvalid) / B_STAGE) * 2048;
     pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p, total);
@@ -203,9 +197,12 @@ int launch_wgrad(const float* a, long long lda, int M, const int* a_off, int aL,
     for (int j = 0; j < 3; ++j) { g.A.off[j] = j < taps ? a_off[j] : 0; g.Bm.off[j] = j < taps ? b_off[j] : 0; }
     g.M = M; g.N = N; g.Kc = R; g.ytaps = taps; g.c_tap_stride = (long long)M * ldc;
     g.C = dw; g.ldc = ldc; g.atomic = 1; g.z_mode = Z_SPLITK; g.tag = OPH_TAG_WGRAD;
-    const int base = cdiv(cdiv(M, GEMM_BM), 2) * cdiv(N, GEMM_BNH * nh_for(N)) * taps;     // CTA pairs before split-K
-    int splits = cdiv(2 * 74, base);
+    // split the reduction so that the work units fill whole rounds of the 74 persistent CTA pairs (never 2 rounds + a sliver)
+    const int base = cdiv(cdiv(M, GEMM_BM), 2) * cdiv(N, GEMM_BN) * taps;     // work units before split-K
     const int max_splits = cdiv(R, 4 * GEMM_BK);
+    int rounds = cdiv(base, GEMM_MAX_PAIRS);
+    if (rounds < 2 && base * max_splits >= 2 * GEMM_MAX_PAIRS) rounds = 2;
+    int splits = (rounds * GEMM_MAX_PAIRS) / base;
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
     g.k_chunk = cdiv(cdiv(R, splits), GEMM_BK) * GEMM_BK;

@@ -2,13 +2,13 @@
 //     C[m][n] (+)= alpha * sum_kk A[m][kk] * B[n][kk]  (+ bias[n] + addend[m][n])
 //     A*B ~= Ahi*Bhi + Ahi*Blo + Alo*Bhi   (bf16 operands, fp32 accumulate in TMEM)
 //
-// A CTA PAIR (cluster of 2, tcgen05 cta_group::2) owns a 256-row x (256*NH)-column tile: each CTA holds its own 128
-// rows of the accumulator in its tensor memory and stages its own 128 rows of A plus HALF of every B stage; the MMA
-// unit reads the other half from the partner's shared memory.  That halves the B bytes that have to be delivered
-// into each SM per MMA cycle -- the binding limit of the 1-CTA version was the L2->SM fabric (profiles/), not the
-// tensor pipe.  fp32 activations are split into (hi, lo) bf16 planes by the producer warps on their way into
-// SWIZZLE_128B shared-memory tiles; pre-packed weight images arrive through the bulk-copy (TMA) engine.
-// One thread of the leader CTA issues every tcgen05.mma of the pair.
+// PERSISTENT kernel, one CTA pair (cluster of 2, tcgen05 cta_group::2) per two SMs.  A work unit is a 256-row x
+// 256-column output tile (x one tap / batch item / split-K slice): each CTA of the pair owns 128 rows of the fp32
+// accumulator in its tensor memory and stages its own 128 rows of A plus HALF of every B stage; the MMA unit reads
+// the other half from the partner's shared memory.  The 512 TMEM columns hold TWO accumulator stages, so the
+// epilogue of unit i (dedicated warps) overlaps the main loop of unit i+1.  fp32 activations are split into
+// (hi, lo) bf16 planes by the producer warps on their way into SWIZZLE_128B shared-memory tiles; pre-packed weight
+// images arrive through the bulk-copy (TMA) engine.  One thread of the leader CTA issues every tcgen05.mma.
 #pragma once
 #include "oph_ptx.cuh"
 
@@ -28,11 +28,12 @@ struct OperandMap {        // logical row r -> (item b, step t) = divmod(r, L); 
 struct GemmArgs {
     int a_mode, b_mode;
     OperandMap A, Bm;
-    const void* Bpacked;   // B_PACKED: [nblock][kb][half][cta 0: hi 16 KiB | lo 16 KiB][cta 1: hi | lo] smem images
+    const void* Bpacked;   // B_PACKED: [n-block of 256][kb][cta 0: hi 16 KiB | lo 16 KiB][cta 1: hi | lo] smem images
     int M, N;              // valid output rows / columns
     int Kc;                // reduction extent per tap (channels for conv-style A, rows for MN-major A)
     int ntaps;             // taps looped inside the CTA (conv-style A)
-    int z_mode;            // grid.z meaning
+    int z_mode;            // meaning of the z index of a work unit
+    int zdim;              // number of z slices (batch items or split-K slices)
     long long a_zs, b_zs, c_zs;
     int k_chunk;           // Z_SPLITK: reduction rows per z slice (multiple of 64)
     int ytaps;             // taps spread over grid.y (wgrad); output moves by c_tap_stride per tap
@@ -50,17 +51,20 @@ struct GemmArgs {
 
 constexpr int GEMM_BM = 128;                        // rows per CTA (256 per pair)
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_BNH = 256;                       // columns per MMA instruction
-constexpr int GEMM_BNC = GEMM_BNH / 2;              // B rows staged by each CTA of the pair
+constexpr int GEMM_BN = 256;                        // columns per work unit = one MMA instruction's N
+constexpr int GEMM_BNC = GEMM_BN / 2;               // B rows staged by each CTA of the pair
 constexpr int A_PLANE = GEMM_BM * GEMM_BK * 2;      // 16 KiB  (one bf16 plane)
 constexpr int B_PLANE = GEMM_BNC * GEMM_BK * 2;     // 16 KiB
 constexpr int A_SLOT = 2 * A_PLANE;                 // hi + lo
 constexpr int B_SLOT = 2 * B_PLANE;                 // per CTA
-constexpr int B_STAGE = 2 * B_SLOT;                 // both CTAs: one (k-block, half) of the packed image
+constexpr int B_STAGE = 2 * B_SLOT;                 // both CTAs: one k-block of the packed image of a 256-column block
 constexpr int NA_SLOTS = 3;
-constexpr int NB_SLOTS = 4;
-constexpr int GEMM_THREADS = 352;                   // 8 producer/epilogue warps + MMA + bulk-copy + relay warps
-constexpr int GEMM_SMEM = NA_SLOTS * A_SLOT + NB_SLOTS * B_SLOT + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int NB_SLOTS = 3;
+constexpr int N_ACC = 2;                            // accumulator stages in tensor memory (2 x 256 columns)
+constexpr int EPI_STAGE_BYTES = 4 * 32 * 33 * 4;    // per-warp transposition buffers of the 4 epilogue warps
+constexpr int GEMM_THREADS = 512;                   // warps 0-7 producers, 8-11 epilogue, 12 MMA, 13 bulk copy, 14 relay
+constexpr int GEMM_SMEM = NA_SLOTS * A_SLOT + NB_SLOTS * B_SLOT + EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int GEMM_MAX_PAIRS = 74;                  // 148 SMs
 
 __device__ __forceinline__ void load8(const float* src, bool row_ok, int first, int limit, float (&v)[8]) {
     if (row_ok && first + 8 <= limit) {
@@ -89,16 +93,37 @@ __device__ __forceinline__ bool map_row(const OperandMap& o, int r, int tap, lon
     return ts >= 0 && ts < o.Ls;
 }
 
-// barrier indices (same layout in both CTAs; FULL_* are only used in the leader, LAND_B only in the partner)
+// barrier indices (same layout in both CTAs; FULL_* / T_EMPTY are only used in the leader, LAND_B only in the partner)
 constexpr int BAR_FULL_A = 0;                          // [NA_SLOTS] 16 producer-warp arrivals (8 per CTA)
 constexpr int BAR_EMPTY_A = BAR_FULL_A + NA_SLOTS;     // [NA_SLOTS] leader's commit, multicast to both CTAs
 constexpr int BAR_FULL_B = BAR_EMPTY_A + NA_SLOTS;     // [NB_SLOTS]
 constexpr int BAR_EMPTY_B = BAR_FULL_B + NB_SLOTS;     // [NB_SLOTS]
 constexpr int BAR_LAND_B = BAR_EMPTY_B + NB_SLOTS;     // [NB_SLOTS] partner: its bulk copy landed (relayed to the leader)
-constexpr int BAR_ACCUM = BAR_LAND_B + NB_SLOTS;
-constexpr int NUM_BARS = BAR_ACCUM + 1;
+constexpr int BAR_T_FULL = BAR_LAND_B + NB_SLOTS;      // [N_ACC] accumulator stage complete (commit, multicast)
+constexpr int BAR_T_EMPTY = BAR_T_FULL + N_ACC;        // [N_ACC] accumulator stage drained by 4+4 epilogue warps
+constexpr int NUM_BARS = BAR_T_EMPTY + N_ACC;
 
-template <int NH>
+struct Unit {               // one 256x256 output tile of one tap / z slice
+    int m0, n0, nb, ytap, k_begin, k_end, KBc, KB;
+    long long a_z, b_z, c_z;
+};
+
+__device__ __forceinline__ Unit decode_unit(const GemmArgs& p, int u, int MP, int nblocks, uint32_t crank) {
+    Unit t;
+    const int mp = u % MP; int rest = u / MP;
+    t.nb = rest % nblocks; rest /= nblocks;
+    t.ytap = rest % p.ytaps;
+    const int z = rest / p.ytaps;
+    t.m0 = (mp * 2 + (int)crank) * GEMM_BM;            // may lie beyond M for the padding CTA of the last pair
+    t.n0 = t.nb * GEMM_BN;
+    t.k_begin = 0; t.k_end = p.Kc; t.a_z = t.b_z = t.c_z = 0;
+    if (p.z_mode == Z_BATCH) { t.a_z = z * p.a_zs; t.b_z = z * p.b_zs; t.c_z = z * p.c_zs; }
+    if (p.z_mode == Z_SPLITK) { t.k_begin = z * p.k_chunk; t.k_end = min(p.Kc, t.k_begin + p.k_chunk); }
+    t.KBc = (t.k_end - t.k_begin + GEMM_BK - 1) / GEMM_BK;
+    t.KB = ((p.a_mode == A_KMAJOR) ? p.ntaps : 1) * t.KBc;
+    return t;
+}
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
     extern __shared__ uint8_t smem_raw[];
@@ -106,30 +131,20 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
     uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
     uint8_t* sA = smem;
     uint8_t* sB = smem + NA_SLOTS * A_SLOT;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NA_SLOTS * A_SLOT + NB_SLOTS * B_SLOT);
+    float* sStage = reinterpret_cast<float*>(smem + NA_SLOTS * A_SLOT + NB_SLOTS * B_SLOT);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NA_SLOTS * A_SLOT + NB_SLOTS * B_SLOT + EPI_STAGE_BYTES);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NUM_BARS);
     const uint32_t bar0 = smem_u32(bars);
     auto BAR = [&](int i) { return bar0 + 8u * i; };
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    constexpr int NT = GEMM_BNH * NH;
-    const int nblocks = (p.N + NT - 1) / NT;
-    const int nb = blockIdx.y % nblocks;
-    const int ytap = blockIdx.y / nblocks;
     const uint32_t crank = cluster_ctarank();          // 0 = leader (issues the MMAs), 1 = partner
-    const int m0 = blockIdx.x * GEMM_BM;               // may lie beyond M for the padding CTA of the last pair
-    const int n0 = nb * NT;
-    const int z = blockIdx.z;
-
-    int k_begin = 0, k_end = p.Kc;
-    long long a_z = 0, b_z = 0, c_z = 0;
-    if (p.z_mode == Z_BATCH) { a_z = z * p.a_zs; b_z = z * p.b_zs; c_z = z * p.c_zs; }
-    if (p.z_mode == Z_SPLITK) { k_begin = z * p.k_chunk; k_end = min(p.Kc, k_begin + p.k_chunk); }
-    const int KBc = (k_end - k_begin + GEMM_BK - 1) / GEMM_BK;
-    const int ntl = (p.a_mode == A_KMAJOR) ? p.ntaps : 1;
-    const int KB = ntl * KBc;
-    if (KB <= 0) return;                               // uniform over the pair (depends on z only)
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    const int MP = ((p.M + GEMM_BM - 1) / GEMM_BM + 1) / 2;
+    const int nblocks = (p.N + GEMM_BN - 1) / GEMM_BN;
+    const int total = MP * nblocks * p.ytaps * p.zdim;
     const bool packed = p.b_mode == B_PACKED;
+    const bool a_k = p.a_mode == A_KMAJOR;
 
     if (tid == 0) {
         for (int i = 0; i < NA_SLOTS; ++i) { mbar_init(BAR(BAR_FULL_A + i), 16); mbar_init(BAR(BAR_EMPTY_A + i), 1); }
@@ -138,27 +153,25 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
             mbar_init(BAR(BAR_EMPTY_B + i), 1);
             mbar_init(BAR(BAR_LAND_B + i), 1);
         }
-        mbar_init(BAR(BAR_ACCUM), 1);
+        for (int i = 0; i < N_ACC; ++i) { mbar_init(BAR(BAR_T_FULL + i), 1); mbar_init(BAR(BAR_T_EMPTY + i), 8); }
         mbar_fence_init();
         fence_proxy_async();
     }
-    if (warp == 8) tmem_alloc2<NT>(smem_u32(tmem_slot));
+    if (warp == 12) tmem_alloc2<N_ACC * GEMM_BN>(smem_u32(tmem_slot));
     tc_fence_before();
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // Register budget per role (the kernel launches at 128 regs/thread x 512 threads = the whole register file):
+    // warpgroups 0,1 (producers) grow to 168, warpgroup 2 (epilogue) shrinks to 88, warpgroup 3 (MMA / copy) to 56.
     if (warp < 8) {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
         // ================================================================ producers (both CTAs)
-        // Each thread owns 4 chunks (8 consecutive elements each) of every operand tile.  All address arithmetic is
+        // Each thread owns 4 chunks (8 consecutive elements each) of every operand tile.  Address arithmetic is
         // hoisted: row pointers are set up once per tap (conv-style A) or advanced incrementally (row-reduction
         // operands), so that a k-block costs loads + conversion + stores and little else.
-        const float* Ap = p.A.ptr + a_z;
-        const float* Bp = packed ? nullptr : (p.Bm.ptr + b_z);
-        const bool a_k = p.a_mode == A_KMAJOR;
-
-        // ---- shared-memory offsets of the 4 chunks: K-major [128 rows][64 k] or MN-major [64 k][128 mn] tiles
-        uint32_t off_a[4], off_b[4];
+        uint32_t off_a[4], off_b[4];                         // smem offsets: K-major [128][64 k] / MN-major [64 k][128]
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int rl = (tid >> 3) + 32 * i, chunk = tid & 7;
@@ -168,171 +181,227 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
             off_a[i] = a_k ? ok_ : omn;
             off_b[i] = (p.b_mode == B_KMAJOR) ? ok_ : omn;
         }
-
-        // ---- A load stream state (runs one k-block ahead of the store stream)
-        int la_tap = 0, la_cb = 0;
-        const float* a_cur[4]; bool a_val[4];
-        int a_t[4]; long long a_base[4]; bool a_ok[4];       // conv rows (K-major) / reduction rows (MN-major)
-        int ar_b[4], ar_t[4], ar_r[4];
-        if (a_k) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int g = m0 + (tid >> 3) + 32 * i;
-                a_ok[i] = g < p.M;
-                const int b = g / p.A.L;
-                a_t[i] = g - b * p.A.L;
-                a_base[i] = (long long)b * p.A.Ls;
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                ar_r[i] = k_begin + (tid >> 4) + 16 * i;
-                ar_b[i] = ar_r[i] / p.A.L;
-                ar_t[i] = ar_r[i] - ar_b[i] * p.A.L;
-            }
-        }
-        auto a_set_tap = [&](int tap) {                        // K-major: row pointers of this tap
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int ts = a_t[i] * p.A.mul + p.A.off[tap];
-                a_val[i] = a_ok[i] && ts >= 0 && ts < p.A.Ls;
-                a_cur[i] = Ap + (a_base[i] + ts) * p.A.ld + (tid & 7) * 8;
-            }
-        };
-        if (a_k) a_set_tap(0);
-        auto load_a = [&](float (&v)[4][8]) {                  // loads the next k-block of the stream, then advances it
-            if (a_k) {
-                const int c = k_begin + la_cb * GEMM_BK + (tid & 7) * 8;
-                const bool full = c + 8 <= k_end;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float* src = a_cur[i] + (k_begin + la_cb * GEMM_BK);
-                    if (full) {
-                        float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
-                        if (a_val[i]) { x0 = __ldg(reinterpret_cast<const float4*>(src)); x1 = __ldg(reinterpret_cast<const float4*>(src) + 1); }
-                        v[i][0] = x0.x; v[i][1] = x0.y; v[i][2] = x0.z; v[i][3] = x0.w;
-                        v[i][4] = x1.x; v[i][5] = x1.y; v[i][6] = x1.z; v[i][7] = x1.w;
-                    } else {
-                        load8(src, a_val[i], c, k_end, v[i]);
-                    }
-                }
-                if (++la_cb == KBc) { la_cb = 0; if (++la_tap < ntl) a_set_tap(la_tap); }
-            } else {
-                const int m = m0 + (tid & 15) * 8;
-                const bool full = m + 8 <= p.M;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int ts = ar_t[i] * p.A.mul + p.A.off[ytap];
-                    const bool ok = ts >= 0 && ts < p.A.Ls && ar_r[i] < k_end;
-                    const float* src = Ap + ((long long)ar_b[i] * p.A.Ls + ts) * p.A.ld + m;
-                    if (full) {
-                        float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
-                        if (ok) { x0 = __ldg(reinterpret_cast<const float4*>(src)); x1 = __ldg(reinterpret_cast<const float4*>(src) + 1); }
-                        v[i][0] = x0.x; v[i][1] = x0.y; v[i][2] = x0.z; v[i][3] = x0.w;
-                        v[i][4] = x1.x; v[i][5] = x1.y; v[i][6] = x1.z; v[i][7] = x1.w;
-                    } else {
-                        load8(src, ok, m, p.M, v[i]);
-                    }
-                    ar_r[i] += GEMM_BK; ar_t[i] += GEMM_BK;
-                    while (ar_t[i] >= p.A.L) { ar_t[i] -= p.A.L; ++ar_b[i]; }
-                }
-            }
-        };
-
-        // ---- B from fp32 activations: this CTA stages rows/columns [n0 + h*256 + crank*128, +128) of every stage
-        int br_b[4], br_t[4], br_r[4];                         // MN-major B: reduction rows, advanced once per k-block
-        if (p.b_mode == B_MNMAJOR) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                br_r[i] = k_begin + (tid >> 4) + 16 * i;
-                br_b[i] = br_r[i] / p.Bm.L;
-                br_t[i] = br_r[i] - br_b[i] * p.Bm.L;
-            }
-        }
-        auto load_b = [&](int kb, int h, float (&v)[4][8]) {
-            const int nbase = n0 + h * GEMM_BNH + (int)crank * GEMM_BNC;
-            if (p.b_mode == B_KMAJOR) {
-                const int c = k_begin + (kb - (kb / KBc) * KBc) * GEMM_BK + (tid & 7) * 8;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int n = nbase + (tid >> 3) + 32 * i;
-                    load8(Bp + (long long)n * p.Bm.ld + c, n < p.N, c, k_end, v[i]);
-                }
-            } else {
-                const int tap = a_k ? kb / KBc : ytap;
-                const int n = nbase + (tid & 15) * 8;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int ts = br_t[i] * p.Bm.mul + p.Bm.off[tap];
-                    const bool ok = ts >= 0 && ts < p.Bm.Ls && br_r[i] < k_end;
-                    load8(Bp + ((long long)br_b[i] * p.Bm.Ls + ts) * p.Bm.ld + n, ok, n, p.N, v[i]);
-                }
-            }
-        };
-        auto advance_b = [&]() {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                br_r[i] += GEMM_BK; br_t[i] += GEMM_BK;
-                while (br_t[i] >= p.Bm.L) { br_t[i] -= p.Bm.L; ++br_b[i]; }
-            }
-        };
-
-        float va[4][8], vn[4][8];
-        load_a(va);
         int a_slot = 0, a_par = 1, b_slot = 0, b_par = 1;      // ring cursors: parity to wait for on the EMPTY barriers
-        for (int kb = 0; kb < KB; ++kb) {
-            if (kb + 1 < KB) load_a(vn);                       // next tile's loads are in flight while this one is converted
-            {
-                mbar_wait(BAR(BAR_EMPTY_A + a_slot), a_par);
-                uint8_t* hi = sA + a_slot * A_SLOT;
+        for (int u = pair; u < total; u += npairs) {
+            const Unit t = decode_unit(p, u, MP, nblocks, crank);
+            if (t.KB <= 0) continue;
+            const float* Ap = p.A.ptr + t.a_z;
+            const float* Bp = packed ? nullptr : (p.Bm.ptr + t.b_z);
+            const int ntl = a_k ? p.ntaps : 1;
+
+            // ---- A load stream state (runs one k-block ahead of the store stream)
+            int la_tap = 0, la_cb = 0;
+            const float* a_cur[4]; bool a_val[4];
+            int a_t[4]; long long a_base[4]; bool a_ok[4];
+            int ar_b[4], ar_t[4], ar_r[4];
+            if (a_k) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) store_split(hi, hi + A_PLANE, off_a[i], va[i]);
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_remote(BAR(BAR_FULL_A + a_slot), 0);
-                if (++a_slot == NA_SLOTS) { a_slot = 0; a_par ^= 1; }
+                for (int i = 0; i < 4; ++i) {
+                    const int g = t.m0 + (tid >> 3) + 32 * i;
+                    a_ok[i] = g < p.M;
+                    const int b = g / p.A.L;
+                    a_t[i] = g - b * p.A.L;
+                    a_base[i] = (long long)b * p.A.Ls;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    ar_r[i] = t.k_begin + (tid >> 4) + 16 * i;
+                    ar_b[i] = ar_r[i] / p.A.L;
+                    ar_t[i] = ar_r[i] - ar_b[i] * p.A.L;
+                }
             }
-            if (!packed) {
-#pragma unroll 1
-                for (int h = 0; h < NH; ++h) {
-                    float v[4][8];
-                    load_b(kb, h, v);
+            auto a_set_tap = [&](int tap) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int ts = a_t[i] * p.A.mul + p.A.off[tap];
+                    a_val[i] = a_ok[i] && ts >= 0 && ts < p.A.Ls;
+                    a_cur[i] = Ap + (a_base[i] + ts) * p.A.ld + (tid & 7) * 8;
+                }
+            };
+            if (a_k) a_set_tap(0);
+            auto load_a = [&](float (&v)[4][8]) {              // loads the next k-block of the stream, then advances it
+                if (a_k) {
+                    const int c = t.k_begin + la_cb * GEMM_BK + (tid & 7) * 8;
+                    const bool full = c + 8 <= t.k_end;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float* src = a_cur[i] + (t.k_begin + la_cb * GEMM_BK);
+                        if (full) {
+                            float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
+                            if (a_val[i]) { x0 = __ldg(reinterpret_cast<const float4*>(src)); x1 = __ldg(reinterpret_cast<const float4*>(src) + 1); }
+                            v[i][0] = x0.x; v[i][1] = x0.y; v[i][2] = x0.z; v[i][3] = x0.w;
+                            v[i][4] = x1.x; v[i][5] = x1.y; v[i][6] = x1.z; v[i][7] = x1.w;
+                        } else {
+                            load8(src, a_val[i], c, t.k_end, v[i]);
+                        }
+                    }
+                    if (++la_cb == t.KBc) { la_cb = 0; if (++la_tap < ntl) a_set_tap(la_tap); }
+                } else {
+                    const int m = t.m0 + (tid & 15) * 8;
+                    const bool full = m + 8 <= p.M;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int ts = ar_t[i] * p.A.mul + p.A.off[t.ytap];
+                        const bool ok = ts >= 0 && ts < p.A.Ls && ar_r[i] < t.k_end;
+                        const float* src = Ap + ((long long)ar_b[i] * p.A.Ls + ts) * p.A.ld + m;
+                        if (full) {
+                            float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
+                            if (ok) { x0 = __ldg(reinterpret_cast<const float4*>(src)); x1 = __ldg(reinterpret_cast<const float4*>(src) + 1); }
+                            v[i][0] = x0.x; v[i][1] = x0.y; v[i][2] = x0.z; v[i][3] = x0.w;
+                            v[i][4] = x1.x; v[i][5] = x1.y; v[i][6] = x1.z; v[i][7] = x1.w;
+                        } else {
+                            load8(src, ok, m, p.M, v[i]);
+                        }
+                        ar_r[i] += GEMM_BK; ar_t[i] += GEMM_BK;
+                        while (ar_t[i] >= p.A.L) { ar_t[i] -= p.A.L; ++ar_b[i]; }
+                    }
+                }
+            };
+
+            // ---- B from fp32 activations: this CTA stages rows/columns [n0 + crank*128, +128) of every stage
+            int br_b[4], br_t[4], br_r[4];
+            if (p.b_mode == B_MNMAJOR) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    br_r[i] = t.k_begin + (tid >> 4) + 16 * i;
+                    br_b[i] = br_r[i] / p.Bm.L;
+                    br_t[i] = br_r[i] - br_b[i] * p.Bm.L;
+                }
+            }
+            const int nbase = t.n0 + (int)crank * GEMM_BNC;
+            auto load_b = [&](int kb, float (&v)[4][8]) {
+                if (p.b_mode == B_KMAJOR) {
+                    const int c = t.k_begin + (kb - (kb / t.KBc) * t.KBc) * GEMM_BK + (tid & 7) * 8;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int n = nbase + (tid >> 3) + 32 * i;
+                        load8(Bp + (long long)n * p.Bm.ld + c, n < p.N, c, t.k_end, v[i]);
+                    }
+                } else {
+                    const int tap = a_k ? kb / t.KBc : t.ytap;
+                    const int n = nbase + (tid & 15) * 8;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int ts = br_t[i] * p.Bm.mul + p.Bm.off[tap];
+                        const bool ok = ts >= 0 && ts < p.Bm.Ls && br_r[i] < t.k_end;
+                        load8(Bp + ((long long)br_b[i] * p.Bm.Ls + ts) * p.Bm.ld + n, ok, n, p.N, v[i]);
+                        br_r[i] += GEMM_BK; br_t[i] += GEMM_BK;
+                        while (br_t[i] >= p.Bm.L) { br_t[i] -= p.Bm.L; ++br_b[i]; }
+                    }
+                }
+            };
+
+            // one k-block: convert + store the A tile held in registers, then (activation x activation products) B
+            auto emit = [&](int kb, float (&v)[4][8]) {
+                {
+                    mbar_wait(BAR(BAR_EMPTY_A + a_slot), a_par);
+                    uint8_t* hi = sA + a_slot * A_SLOT;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) store_split(hi, hi + A_PLANE, off_a[i], v[i]);
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) { if (crank == 0) mbar_arrive(BAR(BAR_FULL_A + a_slot)); else mbar_arrive_remote(BAR(BAR_FULL_A + a_slot), 0); }
+                    if (++a_slot == NA_SLOTS) { a_slot = 0; a_par ^= 1; }
+                }
+                if (!packed) {
+                    float w[4][8];
+                    load_b(kb, w);
                     mbar_wait(BAR(BAR_EMPTY_B + b_slot), b_par);
                     uint8_t* hi = sB + b_slot * B_SLOT;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) store_split(hi, hi + B_PLANE, off_b[i], v[i]);
+                    for (int i = 0; i < 4; ++i) store_split(hi, hi + B_PLANE, off_b[i], w[i]);
                     fence_proxy_async();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive_remote(BAR(BAR_FULL_B + b_slot), 0);
+                    if (lane == 0) { if (crank == 0) mbar_arrive(BAR(BAR_FULL_B + b_slot)); else mbar_arrive_remote(BAR(BAR_FULL_B + b_slot), 0); }
                     if (++b_slot == NB_SLOTS) { b_slot = 0; b_par ^= 1; }
                 }
-                if (p.b_mode == B_MNMAJOR) advance_b();
-            }
-            if (kb + 1 < KB) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) va[i][e] = vn[i][e];
+            };
+            float v0[4][8], v1[4][8];                          // register double buffer: loads run one k-block ahead
+            load_a(v0);
+            for (int kb = 0; kb < t.KB; kb += 2) {
+                if (kb + 1 < t.KB) load_a(v1);
+                emit(kb, v0);
+                if (kb + 1 < t.KB) {
+                    if (kb + 2 < t.KB) load_a(v0);
+                    emit(kb + 1, v1);
+                }
             }
         }
-    } else if (warp == 8) {
+    } else if (warp < 12) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+        // ================================================================ epilogue warps (both CTAs): TMEM -> global
+        const int q = warp & 3;                                // TMEM lane quadrant this warp may access
+        float* stage = sStage + q * (32 * 33);
+        int acc = 0, acc_par = 0;
+        for (int u = pair; u < total; u += npairs) {
+            const Unit t = decode_unit(p, u, MP, nblocks, crank);
+            if (t.KB <= 0) continue;
+            mbar_wait(BAR(BAR_T_FULL + acc), acc_par);
+            tc_fence_after();
+            float* Cb = p.C + t.c_z + (long long)t.ytap * p.c_tap_stride;
+            const float* addb = p.addend ? p.addend + t.c_z + (long long)t.ytap * p.c_tap_stride : nullptr;
+            const int grow0 = t.m0 + q * 32;
+            const int nrows = min(32, p.M - grow0);            // <= 0 for padding rows
+            const long long crow0 = (long long)grow0 * p.c_mul + p.c_off;
+            const long long dstep = (long long)p.c_mul * p.ldc, astep = (long long)p.c_mul * p.ld_add;
+#pragma unroll 1
+            for (int ch = 0; ch < GEMM_BN / 32; ++ch) {
+                const int col0 = ch * 32;
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * GEMM_BN + col0, r);
+                tmem_ld_wait();
+                if (ch == GEMM_BN / 32 - 1) {                  // accumulator stage fully read: hand it back to the MMA thread
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) { if (crank == 0) mbar_arrive(BAR(BAR_T_EMPTY + acc)); else mbar_arrive_remote(BAR(BAR_T_EMPTY + acc), 0); }
+                }
+                if (nrows <= 0 || t.n0 + col0 >= p.N) continue;   // warp-uniform
+#pragma unroll
+                for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = __uint_as_float(r[j]);
+                __syncwarp();
+                const int gcol = t.n0 + col0 + lane;
+                if (gcol < p.N) {
+                    const float bv = p.bias ? __ldg(p.bias + gcol) : 0.f;
+                    float* dst = Cb + crow0 * p.ldc + gcol;
+                    if (p.atomic) {
+                        for (int rr = 0; rr < nrows; ++rr, dst += dstep) atomicAdd(dst, stage[rr * 33 + lane] * p.alpha + bv);
+                    } else if (addb) {
+                        const float* add = addb + crow0 * p.ld_add + gcol;
+                        for (int rr = 0; rr < nrows; ++rr, dst += dstep, add += astep) *dst = stage[rr * 33 + lane] * p.alpha + bv + __ldg(add);
+                    } else {
+#pragma unroll 4
+                        for (int rr = 0; rr < nrows; ++rr, dst += dstep) *dst = stage[rr * 33 + lane] * p.alpha + bv;
+                    }
+                }
+                __syncwarp();
+            }
+            if (++acc == N_ACC) { acc = 0; acc_par ^= 1; }
+        }
+    } else {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+      if (warp == 12) {
         // ================================================================ MMA issuer: one thread of the leader CTA
         if (lane == 0 && crank == 0) {
-            const uint32_t idesc = make_idesc_bf16(2 * GEMM_BM, GEMM_BNH, p.a_mode == A_MNMAJOR, p.b_mode == B_MNMAJOR);
+            const uint32_t idesc = make_idesc_bf16(2 * GEMM_BM, GEMM_BN, p.a_mode == A_MNMAJOR, p.b_mode == B_MNMAJOR);
             const uint32_t a_step = (p.a_mode == A_MNMAJOR) ? 2048u : 32u;
             const uint32_t a_lbo = (p.a_mode == A_MNMAJOR) ? 8192u : 16u;
             const uint32_t b_step = (p.b_mode == B_MNMAJOR) ? 2048u : 32u;
             const uint32_t b_lbo = (p.b_mode == B_MNMAJOR) ? 8192u : 16u;
             const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
-            int as = 0, a_par = 0, bs = 0, b_par = 0;
-            for (int kb = 0; kb < KB; ++kb) {
-                mbar_wait(BAR(BAR_FULL_A + as), a_par);
-                const uint32_t a_hi = sA_addr + as * A_SLOT, a_lo = a_hi + A_PLANE;
-                for (int h = 0; h < NH; ++h) {
+            int as = 0, a_par = 0, bs = 0, b_par = 0, acc = 0, acc_par = 1;
+            for (int u = pair; u < total; u += npairs) {
+                const Unit t = decode_unit(p, u, MP, nblocks, crank);
+                if (t.KB <= 0) continue;
+                mbar_wait(BAR(BAR_T_EMPTY + acc), acc_par);    // epilogue of the unit that last used this stage is done
+                tc_fence_after();
+                const uint32_t d = tmem_base + acc * GEMM_BN;
+                for (int kb = 0; kb < t.KB; ++kb) {
+                    mbar_wait(BAR(BAR_FULL_A + as), a_par);
                     mbar_wait(BAR(BAR_FULL_B + bs), b_par);
                     tc_fence_after();
+                    const uint32_t a_hi = sA_addr + as * A_SLOT, a_lo = a_hi + A_PLANE;
                     const uint32_t b_hi = sB_addr + bs * B_SLOT, b_lo = b_hi + B_PLANE;
-                    const uint32_t d = tmem_base + h * GEMM_BNH;
 #pragma unroll
                     for (int ks = 0; ks < GEMM_BK / 16; ++ks) {
                         const uint64_t dah = make_sdesc(a_hi + ks * a_step, a_lbo, 1024);
@@ -344,86 +413,52 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
                         umma2_bf16(d, dal, dbh, idesc, 1);
                     }
                     umma2_commit_mcast(BAR(BAR_EMPTY_B + bs), 3);   // frees the B slot in both CTAs
+                    umma2_commit_mcast(BAR(BAR_EMPTY_A + as), 3);   // frees the A slot in both CTAs
                     if (++bs == NB_SLOTS) { bs = 0; b_par ^= 1; }
+                    if (++as == NA_SLOTS) { as = 0; a_par ^= 1; }
                 }
-                umma2_commit_mcast(BAR(BAR_EMPTY_A + as), 3);       // frees the A slot in both CTAs
-                if (++as == NA_SLOTS) { as = 0; a_par ^= 1; }
+                umma2_commit_mcast(BAR(BAR_T_FULL + acc), 3);       // accumulators of both CTAs complete
+                if (++acc == N_ACC) { acc = 0; acc_par ^= 1; }
             }
-            umma2_commit_mcast(BAR(BAR_ACCUM), 3);                  // accumulators of both CTAs complete
         }
         __syncwarp();
-    } else if (warp == 9) {
+      } else if (warp == 13) {
         // ================================================================ packed-weight loader (bulk copy engine)
         if (lane == 0 && packed) {
-            const uint8_t* src = reinterpret_cast<const uint8_t*>(p.Bpacked) + (size_t)nb * KB * NH * B_STAGE + crank * B_SLOT;
-            const int total = KB * NH;
-            for (int bi = 0; bi < total; ++bi) {
-                const int slot = bi % NB_SLOTS;
-                mbar_wait(BAR(BAR_EMPTY_B + slot), ((bi / NB_SLOTS) & 1) ^ 1);
-                const uint32_t bar = BAR((crank == 0 ? BAR_FULL_B : BAR_LAND_B) + slot);
-                mbar_arrive_expect_tx(bar, B_SLOT);
-                bulk_g2s(smem_u32(sB + slot * B_SLOT), src + (size_t)bi * B_STAGE, B_SLOT, bar);
+            int slot = 0, par = 1;
+            for (int u = pair; u < total; u += npairs) {
+                const Unit t = decode_unit(p, u, MP, nblocks, crank);
+                const uint8_t* src = reinterpret_cast<const uint8_t*>(p.Bpacked) + (size_t)t.nb * t.KB * B_STAGE + crank * B_SLOT;
+                for (int kb = 0; kb < t.KB; ++kb) {
+                    mbar_wait(BAR(BAR_EMPTY_B + slot), par);
+                    const uint32_t bar = BAR((crank == 0 ? BAR_FULL_B : BAR_LAND_B) + slot);
+                    mbar_arrive_expect_tx(bar, B_SLOT);
+                    bulk_g2s(smem_u32(sB + slot * B_SLOT), src + (size_t)kb * B_STAGE, B_SLOT, bar);
+                    if (++slot == NB_SLOTS) { slot = 0; par ^= 1; }
+                }
             }
         }
         __syncwarp();
-    } else {
+      } else if (warp == 14) {
         // ================================================================ partner: tell the leader a B stage has landed
         if (lane == 0 && packed && crank == 1) {
-            const int total = KB * NH;
-            for (int bi = 0; bi < total; ++bi) {
-                const int slot = bi % NB_SLOTS;
-                mbar_wait(BAR(BAR_LAND_B + slot), (bi / NB_SLOTS) & 1);
-                mbar_arrive_remote(BAR(BAR_FULL_B + slot), 0);
+            int slot = 0, par = 0;
+            for (int u = pair; u < total; u += npairs) {
+                const Unit t = decode_unit(p, u, MP, nblocks, crank);
+                for (int kb = 0; kb < t.KB; ++kb) {
+                    mbar_wait(BAR(BAR_LAND_B + slot), par);
+                    mbar_arrive_remote(BAR(BAR_FULL_B + slot), 0);
+                    if (++slot == NB_SLOTS) { slot = 0; par ^= 1; }
+                }
             }
         }
         __syncwarp();
+      }
     }
 
-    // ==================================================================== epilogue (warps 0..7 of both CTAs)
-    if (warp < 8) {
-        mbar_wait(BAR(BAR_ACCUM), 0);
-        tc_fence_after();
-        const int q = warp & 3, colhalf = warp >> 2;
-        float* stage = reinterpret_cast<float*>(sA) + warp * (32 * 33);   // operand ring is idle now
-        float* Cb = p.C + c_z + (long long)ytap * p.c_tap_stride;
-        const float* addb = p.addend ? p.addend + c_z + (long long)ytap * p.c_tap_stride : nullptr;
-        constexpr int CH = NT / 2 / 32;
-        if (m0 + q * 32 < p.M) {
-            for (int ch = 0; ch < CH; ++ch) {
-                const int col0 = colhalf * (NT / 2) + ch * 32;
-                if (n0 + col0 >= p.N) break;           // warp-uniform
-                uint32_t r[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + col0, r);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = __uint_as_float(r[j]);
-                __syncwarp();
-                const int gcol = n0 + col0 + lane;
-                const bool col_ok = gcol < p.N;
-                const float bv = (p.bias && col_ok) ? __ldg(p.bias + gcol) : 0.f;
-                const int grow0 = m0 + q * 32;
-                const int nrows = min(32, p.M - grow0);
-                const long long crow0 = (long long)grow0 * p.c_mul + p.c_off;
-                float* dst = Cb + crow0 * p.ldc + gcol;
-                const float* add = addb ? addb + crow0 * p.ld_add + gcol : nullptr;
-                const long long dstep = (long long)p.c_mul * p.ldc, astep = (long long)p.c_mul * p.ld_add;
-                if (col_ok) {
-                    if (p.atomic) {
-                        for (int rr = 0; rr < nrows; ++rr, dst += dstep) atomicAdd(dst, stage[rr * 33 + lane] * p.alpha + bv);
-                    } else if (add) {
-                        for (int rr = 0; rr < nrows; ++rr, dst += dstep, add += astep) *dst = stage[rr * 33 + lane] * p.alpha + bv + __ldg(add);
-                    } else {
-#pragma unroll 4
-                        for (int rr = 0; rr < nrows; ++rr, dst += dstep) *dst = stage[rr * 33 + lane] * p.alpha + bv;
-                    }
-                }
-                __syncwarp();
-            }
-        }
-        tc_fence_before();
-    }
+    tc_fence_before();
     cluster_sync_all();                                // the partner's smem/barriers stay alive until both are done
-    if (warp == 8) tmem_dealloc2<NT>(tmem_base);
+    if (warp == 12) tmem_dealloc2<N_ACC * GEMM_BN>(tmem_base);
 }
 
 }  // namespace oph

@@ -70,12 +70,13 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-// arrive on the mbarrier at the same offset in CTA `rank` of this cluster (release at cluster scope)
+// arrive on the mbarrier at the same offset in CTA `rank` of this cluster.  Default semantics (release, as in the
+// cluster pipelines of CUTLASS); an explicit `.release.cluster` costs a MEMBAR.ALL.GPU per arrival.
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
     asm volatile(
         "{\n\t.reg .b32 ra;\n\t"
         "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
         ::"r"(bar), "r"(rank) : "memory");
 }
 
