@@ -50,6 +50,9 @@ const char* oph_last_error(void);
 #define OPH_TAG_ATTENTION 4
 #define OPH_NUM_TAGS 5
 long long oph_launch_count(void);
+/* diagnostics: device buffer long long[74][8]; every GEMM launch overwrites per CTA pair
+ * (total cycles, cycles waiting for an accumulator stage, for A, for B, k-blocks). NULL disables. */
+int oph_gemm_debug_buffer(long long* dev_buf);
 int oph_profile_begin(void);
 int oph_profile_end(double* out);
 

@@ -16,6 +16,7 @@ SIGNATURES = {
     "oph_version": (I, []),
     "oph_last_error": (ctypes.c_char_p, []),
     "oph_launch_count": (LL, []),
+    "oph_gemm_debug_buffer": (I, [P]),
     "oph_profile_begin": (I, []),
     "oph_profile_end": (I, [P]),
     "oph_conv_pack_bytes": (SZ, [I, I, I, I, I]),

@@ -17,6 +17,7 @@ namespace {
 
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
+long long* g_gemm_dbg = nullptr;   // optional device buffer [74][8] for in-kernel wait-cycle counters
 
 // Optional per-launch timing of the GEMM core (bench.py roofline): CUDA events around every launch, by tag.
 struct ProfRec { cudaEvent_t e0, e1; int tag; double flops; };
@@ -53,6 +54,7 @@ int launch_gemm(GemmArgs& a, int zdim, cudaStream_t st) {
     if ((a.A.ld & 3) || (a.b_mode != B_PACKED && (a.Bm.ld & 3))) return fail(OPH_EINVAL, "gemm: row strides must be multiples of 4%s");
     if (a.ytaps < 1) a.ytaps = 1;
     a.zdim = zdim < 1 ? 1 : zdim;
+    a.dbg = g_gemm_dbg;
     // persistent CTA pairs: work units = (pair of 128-row tiles) x (256-column block) x tap x z slice
     const long long units = (long long)cdiv(cdiv(a.M, GEMM_BM), 2) * cdiv(a.N, GEMM_BN) * a.ytaps * a.zdim;
     const int pairs = (int)(units < GEMM_MAX_PAIRS ? units : GEMM_MAX_PAIRS);
@@ -218,6 +220,7 @@ extern "C" {
 int oph_version(void) { return 100; }
 const char* oph_last_error(void) { return g_err; }
 long long oph_launch_count(void) { return g_launches.load(); }
+int oph_gemm_debug_buffer(long long* dev_buf) { g_gemm_dbg = dev_buf; return OPH_OK; }
 
 int oph_profile_begin(void) {
     std::lock_guard<std::mutex> lk(g_prof_mu);

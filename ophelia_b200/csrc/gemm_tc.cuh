@@ -47,6 +47,7 @@ struct GemmArgs {
     float alpha;
     int atomic;            // 1: atomicAdd into C (split-K)
     int tag;               // host-side profiling category (OPH_TAG_*)
+    long long* dbg;        // optional [pairs][8] cycle counters of the MMA / producer waits (diagnostics)
 };
 
 constexpr int GEMM_BM = 128;                        // rows per CTA (256 per pair)
@@ -62,7 +63,9 @@ constexpr int NA_SLOTS = 3;
 constexpr int NB_SLOTS = 3;
 constexpr int N_ACC = 2;                            // accumulator stages in tensor memory (2 x 256 columns)
 constexpr int EPI_STAGE_BYTES = 4 * 32 * 33 * 4;    // per-warp transposition buffers of the 4 epilogue warps
-constexpr int GEMM_THREADS = 512;                   // warps 0-7 producers, 8-11 epilogue, 12 MMA, 13 bulk copy, 14 relay
+constexpr int NPW = 16;                             // producer warps (each thread owns NCH chunks of 8 elements per tile)
+constexpr int NCH = 1024 / (NPW * 32);
+constexpr int GEMM_THREADS = (NPW + 8) * 32;        // producers, then 4 epilogue warps, then MMA / bulk copy / relay / idle
 constexpr int GEMM_SMEM = NA_SLOTS * A_SLOT + NB_SLOTS * B_SLOT + EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int GEMM_MAX_PAIRS = 74;                  // 148 SMs
 
@@ -94,7 +97,7 @@ __device__ __forceinline__ bool map_row(const OperandMap& o, int r, int tap, lon
 }
 
 // barrier indices (same layout in both CTAs; FULL_* / T_EMPTY are only used in the leader, LAND_B only in the partner)
-constexpr int BAR_FULL_A = 0;                          // [NA_SLOTS] 16 producer-warp arrivals (8 per CTA)
+constexpr int BAR_FULL_A = 0;                          // [NA_SLOTS] 2*NPW producer-warp arrivals (NPW per CTA)
 constexpr int BAR_EMPTY_A = BAR_FULL_A + NA_SLOTS;     // [NA_SLOTS] leader's commit, multicast to both CTAs
 constexpr int BAR_FULL_B = BAR_EMPTY_A + NA_SLOTS;     // [NB_SLOTS]
 constexpr int BAR_EMPTY_B = BAR_FULL_B + NB_SLOTS;     // [NB_SLOTS]
@@ -147,9 +150,9 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
     const bool a_k = p.a_mode == A_KMAJOR;
 
     if (tid == 0) {
-        for (int i = 0; i < NA_SLOTS; ++i) { mbar_init(BAR(BAR_FULL_A + i), 16); mbar_init(BAR(BAR_EMPTY_A + i), 1); }
+        for (int i = 0; i < NA_SLOTS; ++i) { mbar_init(BAR(BAR_FULL_A + i), 2 * NPW); mbar_init(BAR(BAR_EMPTY_A + i), 1); }
         for (int i = 0; i < NB_SLOTS; ++i) {
-            mbar_init(BAR(BAR_FULL_B + i), packed ? 2 : 16);     // packed: leader's expect_tx arrive + partner's relay
+            mbar_init(BAR(BAR_FULL_B + i), packed ? 2 : 2 * NPW);     // packed: leader's expect_tx arrive + partner's relay
             mbar_init(BAR(BAR_EMPTY_B + i), 1);
             mbar_init(BAR(BAR_LAND_B + i), 1);
         }
@@ -157,26 +160,27 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
         mbar_fence_init();
         fence_proxy_async();
     }
-    if (warp == 12) tmem_alloc2<N_ACC * GEMM_BN>(smem_u32(tmem_slot));
+    if (warp == NPW + 4) tmem_alloc2<N_ACC * GEMM_BN>(smem_u32(tmem_slot));
     tc_fence_before();
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    // Register budget per role (the kernel launches at 128 regs/thread x 512 threads = the whole register file):
-    // warpgroups 0,1 (producers) grow to 168, warpgroup 2 (epilogue) shrinks to 88, warpgroup 3 (MMA / copy) to 56.
-    if (warp < 8) {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
+    // Register budget per role (768 threads launch at 80 regs): producer warpgroups grow to 88, the epilogue
+    // warpgroup shrinks to 72 and the MMA / copy warpgroup to 40 (512*88 + 128*72 + 128*40 <= 768*80: setmaxnreg can
+    // only hand out what the CTA got at launch).
+    if (warp < NPW) {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
         // ================================================================ producers (both CTAs)
-        // Each thread owns 4 chunks (8 consecutive elements each) of every operand tile.  Address arithmetic is
+        // Each thread owns NCH chunks (8 consecutive elements each) of every operand tile.  Address arithmetic is
         // hoisted: row pointers are set up once per tap (conv-style A) or advanced incrementally (row-reduction
         // operands), so that a k-block costs loads + conversion + stores and little else.
-        uint32_t off_a[4], off_b[4];                         // smem offsets: K-major [128][64 k] / MN-major [64 k][128]
+        uint32_t off_a[NCH], off_b[NCH];                         // smem offsets: K-major [128][64 k] / MN-major [64 k][128]
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int rl = (tid >> 3) + 32 * i, chunk = tid & 7;
+        for (int i = 0; i < NCH; ++i) {
+            const int rl = (tid >> 3) + (NPW * 4) * i, chunk = tid & 7;
             const uint32_t ok_ = rl * 128 + ((chunk ^ (rl & 7)) << 4);
-            const int kl = (tid >> 4) + 16 * i, j = tid & 15;
+            const int kl = (tid >> 4) + (NPW * 2) * i, j = tid & 15;
             const uint32_t omn = (j >> 3) * 8192 + (kl >> 3) * 1024 + (kl & 7) * 128 + (((j & 7) ^ (kl & 7)) << 4);
             off_a[i] = a_k ? ok_ : omn;
             off_b[i] = (p.b_mode == B_KMAJOR) ? ok_ : omn;
@@ -191,13 +195,13 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
 
             // ---- A load stream state (runs one k-block ahead of the store stream)
             int la_tap = 0, la_cb = 0;
-            const float* a_cur[4]; bool a_val[4];
-            int a_t[4]; long long a_base[4]; bool a_ok[4];
-            int ar_b[4], ar_t[4], ar_r[4];
+            const float* a_cur[NCH]; bool a_val[NCH];
+            int a_t[NCH]; long long a_base[NCH]; bool a_ok[NCH];
+            int ar_b[NCH], ar_t[NCH], ar_r[NCH];
             if (a_k) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int g = t.m0 + (tid >> 3) + 32 * i;
+                for (int i = 0; i < NCH; ++i) {
+                    const int g = t.m0 + (tid >> 3) + (NPW * 4) * i;
                     a_ok[i] = g < p.M;
                     const int b = g / p.A.L;
                     a_t[i] = g - b * p.A.L;
@@ -205,33 +209,33 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
                 }
             } else {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    ar_r[i] = t.k_begin + (tid >> 4) + 16 * i;
+                for (int i = 0; i < NCH; ++i) {
+                    ar_r[i] = t.k_begin + (tid >> 4) + (NPW * 2) * i;
                     ar_b[i] = ar_r[i] / p.A.L;
                     ar_t[i] = ar_r[i] - ar_b[i] * p.A.L;
                 }
             }
             auto a_set_tap = [&](int tap) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
+                for (int i = 0; i < NCH; ++i) {
                     const int ts = a_t[i] * p.A.mul + p.A.off[tap];
                     a_val[i] = a_ok[i] && ts >= 0 && ts < p.A.Ls;
                     a_cur[i] = Ap + (a_base[i] + ts) * p.A.ld + (tid & 7) * 8;
                 }
             };
             if (a_k) a_set_tap(0);
-            auto load_a = [&](float (&v)[4][8]) {              // loads the next k-block of the stream, then advances it
+            auto load_a = [&](float (&v)[NCH][8]) {              // loads the next k-block of the stream, then advances it
                 if (a_k) {
                     const int c = t.k_begin + la_cb * GEMM_BK + (tid & 7) * 8;
                     const bool full = c + 8 <= t.k_end;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
+                    for (int i = 0; i < NCH; ++i) {
                         const float* src = a_cur[i] + (t.k_begin + la_cb * GEMM_BK);
                         if (full) {
                             float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
                             if (a_val[i]) { x0 = __ldg(reinterpret_cast<const float4*>(src)); x1 = __ldg(reinterpret_cast<const float4*>(src) + 1); }
                             v[i][0] = x0.x; v[i][1] = x0.y; v[i][2] = x0.z; v[i][3] = x0.w;
-                            v[i][4] = x1.x; v[i][5] = x1.y; v[i][6] = x1.z; v[i][7] = x1.w;
+                            v[i][NCH] = x1.x; v[i][5] = x1.y; v[i][6] = x1.z; v[i][7] = x1.w;
                         } else {
                             load8(src, a_val[i], c, t.k_end, v[i]);
                         }
@@ -241,7 +245,7 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
                     const int m = t.m0 + (tid & 15) * 8;
                     const bool full = m + 8 <= p.M;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
+                    for (int i = 0; i < NCH; ++i) {
                         const int ts = ar_t[i] * p.A.mul + p.A.off[t.ytap];
                         const bool ok = ts >= 0 && ts < p.A.Ls && ar_r[i] < t.k_end;
                         const float* src = Ap + ((long long)ar_b[i] * p.A.Ls + ts) * p.A.ld + m;
@@ -249,7 +253,7 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
                             float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
                             if (ok) { x0 = __ldg(reinterpret_cast<const float4*>(src)); x1 = __ldg(reinterpret_cast<const float4*>(src) + 1); }
                             v[i][0] = x0.x; v[i][1] = x0.y; v[i][2] = x0.z; v[i][3] = x0.w;
-                            v[i][4] = x1.x; v[i][5] = x1.y; v[i][6] = x1.z; v[i][7] = x1.w;
+                            v[i][NCH] = x1.x; v[i][5] = x1.y; v[i][6] = x1.z; v[i][7] = x1.w;
                         } else {
                             load8(src, ok, m, p.M, v[i]);
                         }
@@ -260,29 +264,29 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
             };
 
             // ---- B from fp32 activations: this CTA stages rows/columns [n0 + crank*128, +128) of every stage
-            int br_b[4], br_t[4], br_r[4];
+            int br_b[NCH], br_t[NCH], br_r[NCH];
             if (p.b_mode == B_MNMAJOR) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    br_r[i] = t.k_begin + (tid >> 4) + 16 * i;
+                for (int i = 0; i < NCH; ++i) {
+                    br_r[i] = t.k_begin + (tid >> 4) + (NPW * 2) * i;
                     br_b[i] = br_r[i] / p.Bm.L;
                     br_t[i] = br_r[i] - br_b[i] * p.Bm.L;
                 }
             }
             const int nbase = t.n0 + (int)crank * GEMM_BNC;
-            auto load_b = [&](int kb, float (&v)[4][8]) {
+            auto load_b = [&](int kb, float (&v)[NCH][8]) {
                 if (p.b_mode == B_KMAJOR) {
                     const int c = t.k_begin + (kb - (kb / t.KBc) * t.KBc) * GEMM_BK + (tid & 7) * 8;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int n = nbase + (tid >> 3) + 32 * i;
+                    for (int i = 0; i < NCH; ++i) {
+                        const int n = nbase + (tid >> 3) + (NPW * 4) * i;
                         load8(Bp + (long long)n * p.Bm.ld + c, n < p.N, c, t.k_end, v[i]);
                     }
                 } else {
                     const int tap = a_k ? kb / t.KBc : t.ytap;
                     const int n = nbase + (tid & 15) * 8;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
+                    for (int i = 0; i < NCH; ++i) {
                         const int ts = br_t[i] * p.Bm.mul + p.Bm.off[tap];
                         const bool ok = ts >= 0 && ts < p.Bm.Ls && br_r[i] < t.k_end;
                         load8(Bp + ((long long)br_b[i] * p.Bm.Ls + ts) * p.Bm.ld + n, ok, n, p.N, v[i]);
@@ -293,31 +297,31 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
             };
 
             // one k-block: convert + store the A tile held in registers, then (activation x activation products) B
-            auto emit = [&](int kb, float (&v)[4][8]) {
+            auto emit = [&](int kb, float (&v)[NCH][8]) {
                 {
                     mbar_wait(BAR(BAR_EMPTY_A + a_slot), a_par);
                     uint8_t* hi = sA + a_slot * A_SLOT;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) store_split(hi, hi + A_PLANE, off_a[i], v[i]);
+                    for (int i = 0; i < NCH; ++i) store_split(hi, hi + A_PLANE, off_a[i], v[i]);
                     fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) { if (crank == 0) mbar_arrive(BAR(BAR_FULL_A + a_slot)); else mbar_arrive_remote(BAR(BAR_FULL_A + a_slot), 0); }
                     if (++a_slot == NA_SLOTS) { a_slot = 0; a_par ^= 1; }
                 }
                 if (!packed) {
-                    float w[4][8];
+                    float w[NCH][8];
                     load_b(kb, w);
                     mbar_wait(BAR(BAR_EMPTY_B + b_slot), b_par);
                     uint8_t* hi = sB + b_slot * B_SLOT;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) store_split(hi, hi + B_PLANE, off_b[i], w[i]);
+                    for (int i = 0; i < NCH; ++i) store_split(hi, hi + B_PLANE, off_b[i], w[i]);
                     fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) { if (crank == 0) mbar_arrive(BAR(BAR_FULL_B + b_slot)); else mbar_arrive_remote(BAR(BAR_FULL_B + b_slot), 0); }
                     if (++b_slot == NB_SLOTS) { b_slot = 0; b_par ^= 1; }
                 }
             };
-            float v0[4][8], v1[4][8];                          // register double buffer: loads run one k-block ahead
+            float v0[NCH][8], v1[NCH][8];                          // register double buffer: loads run one k-block ahead
             load_a(v0);
             for (int kb = 0; kb < t.KB; kb += 2) {
                 if (kb + 1 < t.KB) load_a(v1);
@@ -328,8 +332,8 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
                 }
             }
         }
-    } else if (warp < 12) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+    } else if (warp < NPW + 4) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
         // ================================================================ epilogue warps (both CTAs): TMEM -> global
         const int q = warp & 3;                                // TMEM lane quadrant this warp may access
         float* stage = sStage + q * (32 * 33);
@@ -379,8 +383,8 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
             if (++acc == N_ACC) { acc = 0; acc_par ^= 1; }
         }
     } else {
-      asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-      if (warp == 12) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+      if (warp == NPW + 4) {
         // ================================================================ MMA issuer: one thread of the leader CTA
         if (lane == 0 && crank == 0) {
             const uint32_t idesc = make_idesc_bf16(2 * GEMM_BM, GEMM_BN, p.a_mode == A_MNMAJOR, p.b_mode == B_MNMAJOR);
@@ -390,15 +394,21 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
             const uint32_t b_lbo = (p.b_mode == B_MNMAJOR) ? 8192u : 16u;
             const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
             int as = 0, a_par = 0, bs = 0, b_par = 0, acc = 0, acc_par = 1;
+            long long w_t = 0, w_a = 0, w_b = 0, t_begin = clock64(), nkb = 0;
             for (int u = pair; u < total; u += npairs) {
                 const Unit t = decode_unit(p, u, MP, nblocks, crank);
                 if (t.KB <= 0) continue;
+                long long c0 = clock64();
                 mbar_wait(BAR(BAR_T_EMPTY + acc), acc_par);    // epilogue of the unit that last used this stage is done
+                w_t += clock64() - c0;
                 tc_fence_after();
                 const uint32_t d = tmem_base + acc * GEMM_BN;
                 for (int kb = 0; kb < t.KB; ++kb) {
+                    c0 = clock64();
                     mbar_wait(BAR(BAR_FULL_A + as), a_par);
+                    const long long c1 = clock64();
                     mbar_wait(BAR(BAR_FULL_B + bs), b_par);
+                    w_a += c1 - c0; w_b += clock64() - c1; ++nkb;
                     tc_fence_after();
                     const uint32_t a_hi = sA_addr + as * A_SLOT, a_lo = a_hi + A_PLANE;
                     const uint32_t b_hi = sB_addr + bs * B_SLOT, b_lo = b_hi + B_PLANE;
@@ -420,9 +430,13 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
                 umma2_commit_mcast(BAR(BAR_T_FULL + acc), 3);       // accumulators of both CTAs complete
                 if (++acc == N_ACC) { acc = 0; acc_par ^= 1; }
             }
+            if (p.dbg) {
+                long long* o = p.dbg + pair * 8;
+                o[0] = clock64() - t_begin; o[1] = w_t; o[2] = w_a; o[3] = w_b; o[4] = nkb;
+            }
         }
         __syncwarp();
-      } else if (warp == 13) {
+      } else if (warp == NPW + 5) {
         // ================================================================ packed-weight loader (bulk copy engine)
         if (lane == 0 && packed) {
             int slot = 0, par = 1;
@@ -439,7 +453,7 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
             }
         }
         __syncwarp();
-      } else if (warp == 14) {
+      } else if (warp == NPW + 6) {
         // ================================================================ partner: tell the leader a B stage has landed
         if (lane == 0 && packed && crank == 1) {
             int slot = 0, par = 0;
@@ -458,7 +472,7 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
 
     tc_fence_before();
     cluster_sync_all();                                // the partner's smem/barriers stay alive until both are done
-    if (warp == 12) tmem_dealloc2<N_ACC * GEMM_BN>(tmem_base);
+    if (warp == NPW + 4) tmem_dealloc2<N_ACC * GEMM_BN>(tmem_base);
 }
 
 }  // namespace oph

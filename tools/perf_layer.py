@@ -50,6 +50,8 @@ def run():
         ops.attention_fwd(Q, K, V)
 
 
+dbg = torch.zeros(74, 8, dtype=torch.int64, device=dev)
+_lib.call("oph_gemm_debug_buffer", dbg.data_ptr())
 for _ in range(a.warmup):
     run()
 torch.cuda.synchronize()
@@ -70,3 +72,9 @@ for i, n in enumerate(["other", "conv_fwd", "dgrad", "wgrad", "attention"]):
     if prof[3 * i] > 0:
         print("   gemm[%s]: %d launches/call, %.3f ms each, %.1f TFLOP/s algorithmic" %
               (n, prof[3 * i] / a.iters, prof[3 * i + 1] / prof[3 * i], prof[3 * i + 2] / prof[3 * i + 1] / 1e9))
+
+d = dbg.cpu().double()
+d = d[d[:, 0] > 0]
+if len(d):
+    print("   last GEMM, per CTA pair (mean cycles): total %.0f  wait_acc %.0f  wait_A %.0f  wait_B %.0f  k-blocks %.0f  -> %.0f cyc/k-block (MMA needs 1536)" %
+          (d[:, 0].mean(), d[:, 1].mean(), d[:, 2].mean(), d[:, 3].mean(), d[:, 4].mean(), (d[:, 0] / d[:, 4]).mean()))
