@@ -53,6 +53,9 @@ long long oph_launch_count(void);
 /* diagnostics: device buffer long long[74][8]; every GEMM launch overwrites per CTA pair
  * (total cycles, cycles waiting for an accumulator stage, for A, for B, k-blocks). NULL disables. */
 int oph_gemm_debug_buffer(long long* dev_buf);
+/* diagnostics (results become garbage): 1 = operand producers skip loads/stores, 2 = weight loader skips copies,
+ * 4 = force the register-staged producer path for pre-split operands */
+int oph_gemm_debug_flags(int flags);
 int oph_profile_begin(void);
 int oph_profile_end(double* out);
 
@@ -64,34 +67,48 @@ size_t oph_conv_pack_bytes(int k, int Cin, int Cout, int deconv, int backward);
 int oph_conv_pack(const float* w, int k, int Cin, int Cout, int deconv, void* packed_fwd, void* packed_bwd,
                   oph_stream_t stream);
 
+/* An activation [B*L rows][C]: an fp32 view and/or the same values as split-bf16 planes (hi = bf16(v),
+ * lo = bf16(v - hi), row stride ldp elements, ldp % 8 == 0).  Planes are the operand format of the GEMM producers:
+ * a layer that receives them copies instead of converting, a layer asked for them (y->hi != NULL, only for
+ * C in {256, 512, 1024}) writes them next to the fp32 output.  Unused members are NULL. */
+typedef struct {
+    float* f32;
+    long long ld;
+    unsigned short* hi;
+    unsigned short* lo;
+    long long ldp;
+} oph_act;
+
 /* ---- modules.conv1d (modules.py:91-146), hot-path uses are k=1 -------------------------------------------
  * y = dropout(act(LN(conv(x) + bias))).  z [B*L][ldz] receives the pre-LN conv output (saved for backward,
  * scratch otherwise), stats [B*L][2] = (mean, rstd) (nullable in inference), y_sig (nullable) = sigmoid(LN(..)).
  * in_shift: extra time shift applied to the input rows (AudioEnc C_1 reads mels delayed by one frame,
  * architectures.py:191).  norm: 1 = layer norm (eps 1e-12), 0 = none.  step (nullable, device int64) is mixed
  * into the dropout seed so that a captured graph draws a fresh mask every replay. */
-int oph_conv1d_fwd(const float* x, long long ldx, const void* packed_w, const float* bias, const float* gamma,
-                   const float* beta, float* z, long long ldz, float* stats, float* y, long long ldy, float* y_sig,
-                   long long ldys, int B, int L, int Cin, int Cout, int k, int rate, int padding, int in_shift,
-                   int act, int norm, float drop_p, uint64_t seed, const long long* step, oph_stream_t stream);
+int oph_conv1d_fwd(const oph_act* x, const void* packed_w, const float* bias, const float* gamma, const float* beta,
+                   float* z, long long ldz, float* stats, const oph_act* y, float* y_sig, long long ldys, int B, int L,
+                   int Cin, int Cout, int k, int rate, int padding, int in_shift, int act, int norm, float drop_p,
+                   uint64_t seed, const long long* step, oph_stream_t stream);
 
-/* Backward of oph_conv1d_fwd.  dz [B*L][lddz] is scratch (>= Cout wide).  dx may be NULL (first layer);
- * dw/dbias/dgamma/dbeta are ACCUMULATED into (caller zeroes the flat gradient buffer once per step). */
-int oph_conv1d_bwd(const float* dy, long long lddy, const float* x, long long ldx, const float* z, long long ldz,
+/* Backward of oph_conv1d_fwd.  dz [B*L][lddz] is scratch (>= Cout wide; it is rewritten as split-bf16 planes
+ * when Cout is 256 or 512).  dx may be NULL (first layer); dw/dbias/dgamma/dbeta are ACCUMULATED into (the
+ * caller zeroes the flat gradient buffer once per step). */
+int oph_conv1d_bwd(const float* dy, long long lddy, const oph_act* x, const float* z, long long ldz,
                    const float* stats, const void* packed_w_bwd, const float* gamma, const float* beta, float* dz,
                    long long lddz, float* dx, long long lddx, float* dw, float* dbias, float* dgamma, float* dbeta,
                    int B, int L, int Cin, int Cout, int k, int rate, int padding, int in_shift, int act, int norm,
                    float drop_p, uint64_t seed, const long long* step, oph_stream_t stream);
 
 /* ---- modules.hc (modules.py:148-207): highway conv, C -> 2C -> C ------------------------------------------
- * z [B*L][ldz] (>= 2C wide) pre-LN conv output; stats [B*L][4] = (mean1, rstd1, mean2, rstd2). */
-int oph_hc_fwd(const float* x, long long ldx, const void* packed_w, const float* bias, const float* g1,
-               const float* b1, const float* g2, const float* b2, float* z, long long ldz, float* stats, float* y,
-               long long ldy, int B, int L, int C, int k, int rate, int padding, int norm, float drop_p,
-               uint64_t seed, const long long* step, oph_stream_t stream);
+ * z [B*L][ldz] (>= 2C wide) pre-LN conv output; stats [B*L][4] = (mean1, rstd1, mean2, rstd2).
+ * x needs its fp32 view (highway residual); its planes, when present, feed the GEMM. */
+int oph_hc_fwd(const oph_act* x, const void* packed_w, const float* bias, const float* g1, const float* b1,
+               const float* g2, const float* b2, float* z, long long ldz, float* stats, const oph_act* y, int B, int L,
+               int C, int k, int rate, int padding, int norm, float drop_p, uint64_t seed, const long long* step,
+               oph_stream_t stream);
 
 /* dz [B*L][lddz] (>= 2C) and dxres [B*L][ldxr] (>= C) are scratch. */
-int oph_hc_bwd(const float* dy, long long lddy, const float* x, long long ldx, const float* z, long long ldz,
+int oph_hc_bwd(const float* dy, long long lddy, const oph_act* x, const float* z, long long ldz,
                const float* stats, const void* packed_w_bwd, const float* g1, const float* b1, const float* g2,
                const float* b2, float* dz, long long lddz, float* dxres, long long ldxr, float* dx, long long lddx,
                float* dw, float* dbias, float* dg1, float* db1, float* dg2, float* db2, int B, int L, int C, int k,
@@ -100,10 +117,10 @@ int oph_hc_bwd(const float* dy, long long lddy, const float* x, long long ldx, c
 
 /* ---- modules.conv1d_transpose (modules.py:209-258): stride-2, k=3, always layer-normed ---------------------
  * out[2i] = W0.x[i] + W2.x[i-1], out[2i+1] = W1.x[i]; y is [B][2L][C].  z [B*2L][ldz], stats [B*2L][2]. */
-int oph_deconv_fwd(const float* x, long long ldx, const void* packed_w, const float* bias, const float* gamma,
-                   const float* beta, float* z, long long ldz, float* stats, float* y, long long ldy, int B, int L,
-                   int C, float drop_p, uint64_t seed, const long long* step, oph_stream_t stream);
-int oph_deconv_bwd(const float* dy, long long lddy, const float* x, long long ldx, const float* z, long long ldz,
+int oph_deconv_fwd(const oph_act* x, const void* packed_w, const float* bias, const float* gamma, const float* beta,
+                   float* z, long long ldz, float* stats, const oph_act* y, int B, int L, int C, float drop_p,
+                   uint64_t seed, const long long* step, oph_stream_t stream);
+int oph_deconv_bwd(const float* dy, long long lddy, const oph_act* x, const float* z, long long ldz,
                    const float* stats, const void* packed_w_bwd, const float* gamma, const float* beta, float* dz,
                    long long lddz, float* dx, long long lddx, float* dw, float* dbias, float* dgamma, float* dbeta,
                    int B, int L, int C, float drop_p, uint64_t seed, const long long* step, oph_stream_t stream);

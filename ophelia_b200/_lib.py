@@ -11,24 +11,32 @@ LIB_PATH = os.path.join(_HERE, "libophelia_sm100.so")
 P, LL, I, F, D, U64, SZ = (ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_float, ctypes.c_double,
                           ctypes.c_uint64, ctypes.c_size_t)
 
+class Act(ctypes.Structure):
+    """`oph_act`: fp32 view and/or split-bf16 planes of one activation (include/ophelia_b200.h)."""
+    _fields_ = [("f32", P), ("ld", LL), ("hi", P), ("lo", P), ("ldp", LL)]
+
+
+AP = ctypes.POINTER(Act)
+
 # name -> (restype, argtypes); must list every symbol of include/ophelia_b200.h
 SIGNATURES = {
     "oph_version": (I, []),
     "oph_last_error": (ctypes.c_char_p, []),
     "oph_launch_count": (LL, []),
     "oph_gemm_debug_buffer": (I, [P]),
+    "oph_gemm_debug_flags": (I, [I]),
     "oph_profile_begin": (I, []),
     "oph_profile_end": (I, [P]),
     "oph_conv_pack_bytes": (SZ, [I, I, I, I, I]),
     "oph_conv_pack": (I, [P, I, I, I, I, P, P, P]),
-    "oph_conv1d_fwd": (I, [P, LL, P, P, P, P, P, LL, P, P, LL, P, LL, I, I, I, I, I, I, I, I, I, I, F, U64, P, P]),
-    "oph_conv1d_bwd": (I, [P, LL, P, LL, P, LL, P, P, P, P, P, LL, P, LL, P, P, P, P,
+    "oph_conv1d_fwd": (I, [AP, P, P, P, P, P, LL, P, AP, P, LL, I, I, I, I, I, I, I, I, I, I, F, U64, P, P]),
+    "oph_conv1d_bwd": (I, [P, LL, AP, P, LL, P, P, P, P, P, LL, P, LL, P, P, P, P,
                            I, I, I, I, I, I, I, I, I, I, F, U64, P, P]),
-    "oph_hc_fwd": (I, [P, LL, P, P, P, P, P, P, P, LL, P, P, LL, I, I, I, I, I, I, I, F, U64, P, P]),
-    "oph_hc_bwd": (I, [P, LL, P, LL, P, LL, P, P, P, P, P, P, P, LL, P, LL, P, LL, P, P, P, P, P, P,
+    "oph_hc_fwd": (I, [AP, P, P, P, P, P, P, P, LL, P, AP, I, I, I, I, I, I, I, F, U64, P, P]),
+    "oph_hc_bwd": (I, [P, LL, AP, P, LL, P, P, P, P, P, P, P, LL, P, LL, P, LL, P, P, P, P, P, P,
                        I, I, I, I, I, I, I, F, U64, P, P]),
-    "oph_deconv_fwd": (I, [P, LL, P, P, P, P, P, LL, P, P, LL, I, I, I, F, U64, P, P]),
-    "oph_deconv_bwd": (I, [P, LL, P, LL, P, LL, P, P, P, P, P, LL, P, LL, P, P, P, P, I, I, I, F, U64, P, P]),
+    "oph_deconv_fwd": (I, [AP, P, P, P, P, P, LL, P, AP, I, I, I, F, U64, P, P]),
+    "oph_deconv_bwd": (I, [P, LL, AP, P, LL, P, P, P, P, P, LL, P, LL, P, P, P, P, I, I, I, F, U64, P, P]),
     "oph_embed_fwd": (I, [P, P, P, LL, I, I, P]),
     "oph_embed_bwd": (I, [P, P, LL, P, I, I, P]),
     "oph_attention_fwd": (I, [P, LL, P, LL, P, LL, P, LL, P, LL, P, P, P, I, P, I, I, F, I, I, I, I, P]),

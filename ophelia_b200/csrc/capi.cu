@@ -17,6 +17,7 @@ namespace {
 
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
+int g_gemm_dbg_flags = 0;
 long long* g_gemm_dbg = nullptr;   // optional device buffer [74][8] for in-kernel wait-cycle counters
 
 // Optional per-launch timing of the GEMM core (bench.py roofline): CUDA events around every launch, by tag.
@@ -25,7 +26,7 @@ std::mutex g_prof_mu;
 bool g_prof_on = false;
 std::vector<ProfRec> g_prof;
 
-int fail(int code, const char* fmt, const char* detail = "") {
+int fail(int code, const char* fmt, const char* detail = "") {   // fmt contains exactly one %s
     snprintf(g_err, sizeof(g_err), fmt, detail);
     return code;
 }
@@ -51,10 +52,15 @@ int launch_gemm(GemmArgs& a, int zdim, cudaStream_t st) {
         attr_done = true;
     }
     if (a.M <= 0 || a.N <= 0 || a.Kc <= 0) return fail(OPH_EINVAL, "gemm: empty problem%s");
-    if ((a.A.ld & 3) || (a.b_mode != B_PACKED && (a.Bm.ld & 3))) return fail(OPH_EINVAL, "gemm: row strides must be multiples of 4%s");
+    if ((a.A.ld & (a.A.hi ? 7 : 3)) || (a.b_mode != B_PACKED && (a.Bm.ld & (a.Bm.hi ? 7 : 3))))
+        return fail(OPH_EINVAL, "gemm: row strides must be multiples of 4 (fp32) / 8 (bf16 planes)%s");
+    if ((a.A.hi && a.a_mode == A_KMAJOR && (a.Kc & 7)) || (a.A.hi && a.a_mode == A_MNMAJOR && (a.M & 7)) ||
+        (a.Bm.hi && a.b_mode == B_KMAJOR && (a.Kc & 7)) || (a.Bm.hi && a.b_mode == B_MNMAJOR && (a.N & 7)))
+        return fail(OPH_EINVAL, "gemm: plane operands need channel counts that are multiples of 8%s");
     if (a.ytaps < 1) a.ytaps = 1;
     a.zdim = zdim < 1 ? 1 : zdim;
     a.dbg = g_gemm_dbg;
+    a.dbg_flags = g_gemm_dbg_flags;
     // persistent CTA pairs: work units = (pair of 128-row tiles) x (256-column block) x tap x z slice
     const long long units = (long long)cdiv(cdiv(a.M, GEMM_BM), 2) * cdiv(a.N, GEMM_BN) * a.ytaps * a.zdim;
     const int pairs = (int)(units < GEMM_MAX_PAIRS ? units : GEMM_MAX_PAIRS);
@@ -159,12 +165,15 @@ int bwd_grid(long long rows) {          // few, long-lived warps so that per-cha
     return (int)(g < 1 ? 1 : (g > 148 * 2 ? 148 * 2 : g));
 }
 
-int launch_ln_act_fwd(const float* z, long long ldz, const float* gamma, const float* beta, float* y, long long ldy,
+int launch_ln_act_fwd(const float* z, long long ldz, const float* gamma, const float* beta, const oph_act* yo,
                       float* y_sig, long long ldys, float* stats, long long rows, int C, int act, int norm, float drop_p,
                       uint64_t seed, const long long* step, cudaStream_t st) {
     const int grid = rows_grid(rows, 8);
+    float* y = yo->f32; const long long ldy = yo->ld;
+    if (yo->hi && !(vec_ok(C, ldz, ldy, y_sig ? ldys : 4) && !(yo->ldp & 7)))
+        return fail(OPH_EINVAL, "split-bf16 output planes need C in {256,512,1024} and 16-byte aligned rows%s");
     if (vec_ok(C, ldz, ldy, y_sig ? ldys : 4)) {
-#define OPH_LAUNCH(V) ln_act_fwd_vec_kernel<V><<<grid, 256, 0, st>>>(z, ldz, gamma, beta, y, ldy, y_sig, ldys, stats, (int)rows, act, norm, drop_p, seed, step)
+#define OPH_LAUNCH(V) ln_act_fwd_vec_kernel<V><<<grid, 256, 0, st>>>(z, ldz, gamma, beta, y, ldy, y_sig, ldys, yo->hi, yo->lo, yo->ldp, stats, (int)rows, act, norm, drop_p, seed, step)
         if (C == 256) OPH_LAUNCH(2); else if (C == 512) OPH_LAUNCH(4); else OPH_LAUNCH(8);
 #undef OPH_LAUNCH
     } else {
@@ -173,29 +182,40 @@ int launch_ln_act_fwd(const float* z, long long ldz, const float* gamma, const f
     return check_launch("ln_act_fwd_kernel");
 }
 
+// dz planes: when the vectorised kernel applies, dz is written ONLY as split-bf16 planes into the caller's scratch
+// (hi plane [rows][C] followed by the lo plane: the same bytes as fp32 [rows][C]); *dzp tells the GEMMs what to read.
+void dz_as_planes(float* dz, long long rows, int C, OperandMap* m) {
+    m->hi = reinterpret_cast<const unsigned short*>(dz);
+    m->lo = m->hi + rows * C;
+    m->ld = C; m->ptr = nullptr;
+}
+
 int launch_ln_act_bwd(const float* dy, long long lddy, const float* z, long long ldz, const float* stats,
                       const float* gamma, const float* beta, float* dz, long long lddz, float* dgamma, float* dbeta,
                       float* dbias, long long rows, int C, int act, int norm, float drop_p, uint64_t seed,
-                      const long long* step, cudaStream_t st) {
+                      const long long* step, OperandMap* dzmap, cudaStream_t st) {
     const size_t smem = 3 * (size_t)C * sizeof(float);
-    if (vec_ok(C, lddy, ldz, lddz) && C <= 512) {
+    dzmap->ptr = dz; dzmap->ld = lddz; dzmap->hi = dzmap->lo = nullptr;
+    if (vec_ok(C, lddy, ldz, lddz) && C <= 512 && lddz >= C) {
         const int grid = bwd_grid(rows);
-        if (C == 256) ln_act_bwd_vec_kernel<2><<<grid, 256, smem, st>>>(dy, lddy, z, ldz, stats, gamma, beta, dz, lddz, dgamma, dbeta, dbias, (int)rows, act, norm, drop_p, seed, step);
-        else          ln_act_bwd_vec_kernel<4><<<grid, 256, smem, st>>>(dy, lddy, z, ldz, stats, gamma, beta, dz, lddz, dgamma, dbeta, dbias, (int)rows, act, norm, drop_p, seed, step);
+        dz_as_planes(dz, rows, C, dzmap);
+        unsigned short* h = const_cast<unsigned short*>(dzmap->hi); unsigned short* l = const_cast<unsigned short*>(dzmap->lo);
+        if (C == 256) ln_act_bwd_vec_kernel<2><<<grid, 256, smem, st>>>(dy, lddy, z, ldz, stats, gamma, beta, nullptr, 0, h, l, C, dgamma, dbeta, dbias, (int)rows, act, norm, drop_p, seed, step);
+        else          ln_act_bwd_vec_kernel<4><<<grid, 256, smem, st>>>(dy, lddy, z, ldz, stats, gamma, beta, nullptr, 0, h, l, C, dgamma, dbeta, dbias, (int)rows, act, norm, drop_p, seed, step);
     } else {
         ln_act_bwd_kernel<<<rows_grid(rows, 8), 256, smem, st>>>(dy, lddy, z, ldz, stats, gamma, beta, dz, lddz, dgamma, dbeta, dbias, (int)rows, C, act, norm, drop_p, seed, step);
     }
     return check_launch("ln_act_bwd_kernel");
 }
 
-// weight gradient: dW[tap][m][n] += sum_r Amap(r,tap)[m] * Bmap(r,tap)[n]
-int launch_wgrad(const float* a, long long lda, int M, const int* a_off, int aL, int aLs, int a_mul,
-                 const float* b, long long ldb, int N, const int* b_off, int bL, int bLs, int b_mul,
+// weight gradient: dW[tap][m][n] += sum_r Amap(r,tap)[m] * Bmap(r,tap)[n]   (operands: fp32 or split-bf16 planes)
+int launch_wgrad(const OperandMap& a, int M, const int* a_off, int aL, int aLs, int a_mul,
+                 const OperandMap& b, int N, const int* b_off, int bL, int bLs, int b_mul,
                  int R, int taps, float* dw, long long ldc, cudaStream_t st) {
     GemmArgs g = blank();
     g.a_mode = A_MNMAJOR; g.b_mode = B_MNMAJOR;
-    g.A.ptr = a; g.A.ld = lda; g.A.L = aL; g.A.Ls = aLs; g.A.mul = a_mul;
-    g.Bm.ptr = b; g.Bm.ld = ldb; g.Bm.L = bL; g.Bm.Ls = bLs; g.Bm.mul = b_mul;
+    g.A = a; g.A.L = aL; g.A.Ls = aLs; g.A.mul = a_mul;
+    g.Bm = b; g.Bm.L = bL; g.Bm.Ls = bLs; g.Bm.mul = b_mul;
     for (int j = 0; j < 3; ++j) { g.A.off[j] = j < taps ? a_off[j] : 0; g.Bm.off[j] = j < taps ? b_off[j] : 0; }
     g.M = M; g.N = N; g.Kc = R; g.ytaps = taps; g.c_tap_stride = (long long)M * ldc;
     g.C = dw; g.ldc = ldc; g.atomic = 1; g.z_mode = Z_SPLITK; g.tag = OPH_TAG_WGRAD;
@@ -221,6 +241,7 @@ int oph_version(void) { return 100; }
 const char* oph_last_error(void) { return g_err; }
 long long oph_launch_count(void) { return g_launches.load(); }
 int oph_gemm_debug_buffer(long long* dev_buf) { g_gemm_dbg = dev_buf; return OPH_OK; }
+int oph_gemm_debug_flags(int flags) { g_gemm_dbg_flags = flags; return OPH_OK; }
 
 int oph_profile_begin(void) {
     std::lock_guard<std::mutex> lk(g_prof_mu);
@@ -276,35 +297,49 @@ int oph_conv_pack(const float* w, int k, int Cin, int Cout, int deconv, void* pa
 }
 
 // ------------------------------------------------------------------------------------------------ conv1d
-int oph_conv1d_fwd(const float* x, long long ldx, const void* packed_w, const float* bias, const float* gamma,
-                   const float* beta, float* z, long long ldz, float* stats, float* y, long long ldy, float* y_sig,
-                   long long ldys, int B, int L, int Cin, int Cout, int k, int rate, int padding, int in_shift,
-                   int act, int norm, float drop_p, uint64_t seed, const long long* step, oph_stream_t stream) {
+static void set_operand(OperandMap& m, const oph_act* a) {
+    m.ptr = a->f32; m.ld = a->ld; m.hi = m.lo = nullptr;
+    if (a->hi) { m.hi = a->hi; m.lo = a->lo; m.ld = a->ldp; m.ptr = nullptr; }   // pre-split planes win: no conversion in the GEMM
+}
+static int check_act(const oph_act* a, const char* who) {
+    if (!a || (!a->f32 && !a->hi)) return fail(OPH_EINVAL, "%s: activation has neither an fp32 view nor planes", who);
+    if (a->hi && (!a->lo || (a->ldp & 7))) return fail(OPH_EINVAL, "%s: plane rows must be 16-byte aligned (ldp % 8 == 0)", who);
+    return OPH_OK;
+}
+
+int oph_conv1d_fwd(const oph_act* x, const void* packed_w, const float* bias, const float* gamma, const float* beta,
+                   float* z, long long ldz, float* stats, const oph_act* y, float* y_sig, long long ldys, int B, int L,
+                   int Cin, int Cout, int k, int rate, int padding, int in_shift, int act, int norm, float drop_p,
+                   uint64_t seed, const long long* step, oph_stream_t stream) {
     if (k < 1 || k > 3) return fail(OPH_EINVAL, "conv1d_fwd: k must be 1..3%s");
+    OPH_TRY(check_act(x, "conv1d_fwd x"));
+    if (x->hi && (Cin & 7)) return fail(OPH_EINVAL, "conv1d_fwd: planes need Cin % 8 == 0%s");
     GemmArgs g = blank();
     g.a_mode = A_KMAJOR; g.b_mode = B_PACKED;
-    g.A.ptr = x; g.A.ld = ldx; g.A.L = L; g.A.Ls = L; g.A.mul = 1;
+    set_operand(g.A, x); g.A.L = L; g.A.Ls = L; g.A.mul = 1;
     conv_offsets(k, rate, padding, in_shift, g.A.off);
     g.Bpacked = packed_w; g.M = B * L; g.N = Cout; g.Kc = Cin; g.ntaps = k;
     g.C = z; g.ldc = ldz; g.bias = bias; g.tag = OPH_TAG_CONV_FWD;
     OPH_TRY(launch_gemm(g, 1, S(stream)));
-    return launch_ln_act_fwd(z, ldz, gamma, beta, y, ldy, y_sig, ldys, stats, (long long)B * L, Cout, act, norm, drop_p,
+    return launch_ln_act_fwd(z, ldz, gamma, beta, y, y_sig, ldys, stats, (long long)B * L, Cout, act, norm, drop_p,
                              seed, step, S(stream));
 }
 
-int oph_conv1d_bwd(const float* dy, long long lddy, const float* x, long long ldx, const float* z, long long ldz,
+int oph_conv1d_bwd(const float* dy, long long lddy, const oph_act* x, const float* z, long long ldz,
                    const float* stats, const void* packed_w_bwd, const float* gamma, const float* beta, float* dz,
                    long long lddz, float* dx, long long lddx, float* dw, float* dbias, float* dgamma, float* dbeta,
                    int B, int L, int Cin, int Cout, int k, int rate, int padding, int in_shift, int act, int norm,
                    float drop_p, uint64_t seed, const long long* step, oph_stream_t stream) {
+    OPH_TRY(check_act(x, "conv1d_bwd x"));
+    OperandMap dzm;
     OPH_TRY(launch_ln_act_bwd(dy, lddy, z, ldz, stats, gamma, beta, dz, lddz, dgamma, dbeta, dbias, (long long)B * L, Cout,
-                              act, norm, drop_p, seed, step, S(stream)));
+                              act, norm, drop_p, seed, step, &dzm, S(stream)));
     int off[3];
     conv_offsets(k, rate, padding, in_shift, off);
     if (dx) {
         GemmArgs g = blank();
         g.a_mode = A_KMAJOR; g.b_mode = B_PACKED;
-        g.A.ptr = dz; g.A.ld = lddz; g.A.L = L; g.A.Ls = L; g.A.mul = 1;
+        g.A = dzm; g.A.L = L; g.A.Ls = L; g.A.mul = 1;
         for (int j = 0; j < 3; ++j) g.A.off[j] = -off[j];
         g.tag = OPH_TAG_DGRAD; g.Bpacked = packed_w_bwd; g.M = B * L; g.N = Cin; g.Kc = Cout; g.ntaps = k;
         g.C = dx; g.ldc = lddx;
@@ -312,51 +347,61 @@ int oph_conv1d_bwd(const float* dy, long long lddy, const float* x, long long ld
     }
     if (dw) {
         const int zero[3] = {0, 0, 0};
-        OPH_TRY(launch_wgrad(x, ldx, Cin, off, L, L, 1, dz, lddz, Cout, zero, L, L, 1, B * L, k, dw, Cout, S(stream)));
+        OperandMap xm; set_operand(xm, x);
+        OPH_TRY(launch_wgrad(xm, Cin, off, L, L, 1, dzm, Cout, zero, L, L, 1, B * L, k, dw, Cout, S(stream)));
     }
     return OPH_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ highway conv
-int oph_hc_fwd(const float* x, long long ldx, const void* packed_w, const float* bias, const float* g1,
-               const float* b1, const float* g2, const float* b2, float* z, long long ldz, float* stats, float* y,
-               long long ldy, int B, int L, int C, int k, int rate, int padding, int norm, float drop_p,
-               uint64_t seed, const long long* step, oph_stream_t stream) {
+int oph_hc_fwd(const oph_act* x, const void* packed_w, const float* bias, const float* g1, const float* b1,
+               const float* g2, const float* b2, float* z, long long ldz, float* stats, const oph_act* y, int B, int L,
+               int C, int k, int rate, int padding, int norm, float drop_p, uint64_t seed, const long long* step,
+               oph_stream_t stream) {
     if (k < 1 || k > 3) return fail(OPH_EINVAL, "hc_fwd: k must be 1..3%s");
+    OPH_TRY(check_act(x, "hc_fwd x"));
+    if (!x->f32) return fail(OPH_EINVAL, "hc_fwd: the highway residual needs the fp32 view of x%s");
     GemmArgs g = blank();
     g.a_mode = A_KMAJOR; g.b_mode = B_PACKED;
-    g.A.ptr = x; g.A.ld = ldx; g.A.L = L; g.A.Ls = L; g.A.mul = 1;
+    set_operand(g.A, x); g.A.L = L; g.A.Ls = L; g.A.mul = 1;
     conv_offsets(k, rate, padding, 0, g.A.off);
     g.Bpacked = packed_w; g.M = B * L; g.N = 2 * C; g.Kc = C; g.ntaps = k;
     g.C = z; g.ldc = ldz; g.bias = bias; g.tag = OPH_TAG_CONV_FWD;
     OPH_TRY(launch_gemm(g, 1, S(stream)));
     const long long rows = (long long)B * L;
     const int grid = rows_grid(rows, 8);
-    if (vec_ok(C, ldz, ldx, ldy)) {
-#define OPH_LAUNCH(V) hc_post_fwd_vec_kernel<V><<<grid, 256, 0, S(stream)>>>(z, ldz, x, ldx, g1, b1, g2, b2, y, ldy, stats, (int)rows, norm, drop_p, seed, step)
+    const bool vec = vec_ok(C, ldz, x->ld, y->ld);
+    if (y->hi && !(vec && !(y->ldp & 7))) return fail(OPH_EINVAL, "hc_fwd: output planes need C in {256,512,1024}%s");
+    if (vec) {
+#define OPH_LAUNCH(V) hc_post_fwd_vec_kernel<V><<<grid, 256, 0, S(stream)>>>(z, ldz, x->f32, x->ld, g1, b1, g2, b2, y->f32, y->ld, y->hi, y->lo, y->ldp, stats, (int)rows, norm, drop_p, seed, step)
         if (C == 256) OPH_LAUNCH(2); else if (C == 512) OPH_LAUNCH(4); else OPH_LAUNCH(8);
 #undef OPH_LAUNCH
     } else {
-        hc_post_fwd_kernel<<<grid, 256, 0, S(stream)>>>(z, ldz, x, ldx, g1, b1, g2, b2, y, ldy, stats, (int)rows, C, norm, drop_p, seed, step);
+        hc_post_fwd_kernel<<<grid, 256, 0, S(stream)>>>(z, ldz, x->f32, x->ld, g1, b1, g2, b2, y->f32, y->ld, stats, (int)rows, C, norm, drop_p, seed, step);
     }
     return check_launch("hc_post_fwd_kernel");
 }
 
-int oph_hc_bwd(const float* dy, long long lddy, const float* x, long long ldx, const float* z, long long ldz,
+int oph_hc_bwd(const float* dy, long long lddy, const oph_act* x, const float* z, long long ldz,
                const float* stats, const void* packed_w_bwd, const float* g1, const float* b1, const float* g2,
                const float* b2, float* dz, long long lddz, float* dxres, long long ldxr, float* dx, long long lddx,
                float* dw, float* dbias, float* dg1, float* db1, float* dg2, float* db2, int B, int L, int C, int k,
                int rate, int padding, int norm, float drop_p, uint64_t seed, const long long* step,
                oph_stream_t stream) {
+    OPH_TRY(check_act(x, "hc_bwd x"));
+    if (!x->f32) return fail(OPH_EINVAL, "hc_bwd: needs the fp32 view of x%s");
     const long long rows = (long long)B * L;
     const size_t smem = 6 * (size_t)C * sizeof(float);
-    if (vec_ok(C, lddy, ldz, ldx, lddz, ldxr) && C <= 512) {
+    OperandMap dzm; dzm.ptr = dz; dzm.ld = lddz; dzm.hi = dzm.lo = nullptr;
+    if (vec_ok(C, lddy, ldz, x->ld, lddz, ldxr) && C <= 512 && lddz >= 2 * C) {
         const int grid = bwd_grid(rows);
-        if (C == 256) hc_post_bwd_vec_kernel<2><<<grid, 256, smem, S(stream)>>>(dy, lddy, z, ldz, x, ldx, stats, g1, b1, g2, b2, dz, lddz, dxres, ldxr, dg1, db1, dg2, db2, dbias, (int)rows, norm, drop_p, seed, step);
-        else          hc_post_bwd_vec_kernel<4><<<grid, 256, smem, S(stream)>>>(dy, lddy, z, ldz, x, ldx, stats, g1, b1, g2, b2, dz, lddz, dxres, ldxr, dg1, db1, dg2, db2, dbias, (int)rows, norm, drop_p, seed, step);
+        dz_as_planes(dz, rows, 2 * C, &dzm);
+        unsigned short* h = const_cast<unsigned short*>(dzm.hi); unsigned short* l = const_cast<unsigned short*>(dzm.lo);
+        if (C == 256) hc_post_bwd_vec_kernel<2><<<grid, 256, smem, S(stream)>>>(dy, lddy, z, ldz, x->f32, x->ld, stats, g1, b1, g2, b2, nullptr, 0, h, l, 2 * C, dxres, ldxr, dg1, db1, dg2, db2, dbias, (int)rows, norm, drop_p, seed, step);
+        else          hc_post_bwd_vec_kernel<4><<<grid, 256, smem, S(stream)>>>(dy, lddy, z, ldz, x->f32, x->ld, stats, g1, b1, g2, b2, nullptr, 0, h, l, 2 * C, dxres, ldxr, dg1, db1, dg2, db2, dbias, (int)rows, norm, drop_p, seed, step);
     } else {
         hc_post_bwd_kernel<<<rows_grid(rows, 8), 256, smem, S(stream)>>>(
-            dy, lddy, z, ldz, x, ldx, stats, g1, b1, g2, b2, dz, lddz, dxres, ldxr, dg1, db1, dg2, db2, dbias,
+            dy, lddy, z, ldz, x->f32, x->ld, stats, g1, b1, g2, b2, dz, lddz, dxres, ldxr, dg1, db1, dg2, db2, dbias,
             (int)rows, C, norm, drop_p, seed, step);
     }
     OPH_TRY(check_launch("hc_post_bwd_kernel"));
@@ -365,7 +410,7 @@ int oph_hc_bwd(const float* dy, long long lddy, const float* x, long long ldx, c
     {
         GemmArgs g = blank();
         g.a_mode = A_KMAJOR; g.b_mode = B_PACKED;
-        g.A.ptr = dz; g.A.ld = lddz; g.A.L = L; g.A.Ls = L; g.A.mul = 1;
+        g.A = dzm; g.A.L = L; g.A.Ls = L; g.A.mul = 1;
         for (int j = 0; j < 3; ++j) g.A.off[j] = -off[j];
         g.tag = OPH_TAG_DGRAD; g.Bpacked = packed_w_bwd; g.M = B * L; g.N = C; g.Kc = 2 * C; g.ntaps = k;
         g.C = dx; g.ldc = lddx; g.addend = dxres; g.ld_add = ldxr;
@@ -373,19 +418,21 @@ int oph_hc_bwd(const float* dy, long long lddy, const float* x, long long ldx, c
     }
     if (dw) {
         const int zero[3] = {0, 0, 0};
-        OPH_TRY(launch_wgrad(x, ldx, C, off, L, L, 1, dz, lddz, 2 * C, zero, L, L, 1, B * L, k, dw, 2 * C, S(stream)));
+        OperandMap xm; set_operand(xm, x);
+        OPH_TRY(launch_wgrad(xm, C, off, L, L, 1, dzm, 2 * C, zero, L, L, 1, B * L, k, dw, 2 * C, S(stream)));
     }
     return OPH_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ transposed conv
-int oph_deconv_fwd(const float* x, long long ldx, const void* packed_w, const float* bias, const float* gamma,
-                   const float* beta, float* z, long long ldz, float* stats, float* y, long long ldy, int B, int L,
-                   int C, float drop_p, uint64_t seed, const long long* step, oph_stream_t stream) {
+int oph_deconv_fwd(const oph_act* x, const void* packed_w, const float* bias, const float* gamma, const float* beta,
+                   float* z, long long ldz, float* stats, const oph_act* y, int B, int L, int C, float drop_p,
+                   uint64_t seed, const long long* step, oph_stream_t stream) {
+    OPH_TRY(check_act(x, "deconv_fwd x"));
     for (int parity = 0; parity < 2; ++parity) {
         GemmArgs g = blank();
         g.a_mode = A_KMAJOR; g.b_mode = B_PACKED;
-        g.A.ptr = x; g.A.ld = ldx; g.A.L = L; g.A.Ls = L; g.A.mul = 1;
+        set_operand(g.A, x); g.A.L = L; g.A.Ls = L; g.A.mul = 1;
         g.A.off[0] = 0; g.A.off[1] = -1; g.A.off[2] = 0;       // even: W0.x[i] + W2.x[i-1]; odd: W1.x[i]
         g.ntaps = parity == 0 ? 2 : 1;
         g.Bpacked = reinterpret_cast<const uint8_t*>(packed_w) + (parity ? pack_image_bytes(2, C, C) : 0);
@@ -393,20 +440,22 @@ int oph_deconv_fwd(const float* x, long long ldx, const void* packed_w, const fl
         g.C = z; g.ldc = ldz; g.c_mul = 2; g.c_off = parity; g.bias = bias; g.tag = OPH_TAG_CONV_FWD;
         OPH_TRY(launch_gemm(g, 1, S(stream)));
     }
-    return launch_ln_act_fwd(z, ldz, gamma, beta, y, ldy, nullptr, 0, stats, 2LL * B * L, C, OPH_ACT_NONE, 1, drop_p, seed,
+    return launch_ln_act_fwd(z, ldz, gamma, beta, y, nullptr, 0, stats, 2LL * B * L, C, OPH_ACT_NONE, 1, drop_p, seed,
                              step, S(stream));
 }
 
-int oph_deconv_bwd(const float* dy, long long lddy, const float* x, long long ldx, const float* z, long long ldz,
+int oph_deconv_bwd(const float* dy, long long lddy, const oph_act* x, const float* z, long long ldz,
                    const float* stats, const void* packed_w_bwd, const float* gamma, const float* beta, float* dz,
                    long long lddz, float* dx, long long lddx, float* dw, float* dbias, float* dgamma, float* dbeta,
                    int B, int L, int C, float drop_p, uint64_t seed, const long long* step, oph_stream_t stream) {
+    OPH_TRY(check_act(x, "deconv_bwd x"));
+    OperandMap dzm;
     OPH_TRY(launch_ln_act_bwd(dy, lddy, z, ldz, stats, gamma, beta, dz, lddz, dgamma, dbeta, dbias, 2LL * B * L, C,
-                              OPH_ACT_NONE, 1, drop_p, seed, step, S(stream)));
+                              OPH_ACT_NONE, 1, drop_p, seed, step, &dzm, S(stream)));
     if (dx) {   // dx[i] = W0^T dz[2i] + W1^T dz[2i+1] + W2^T dz[2i+2]
         GemmArgs g = blank();
         g.a_mode = A_KMAJOR; g.b_mode = B_PACKED;
-        g.A.ptr = dz; g.A.ld = lddz; g.A.L = L; g.A.Ls = 2 * L; g.A.mul = 2;
+        g.A = dzm; g.A.L = L; g.A.Ls = 2 * L; g.A.mul = 2;
         g.A.off[0] = 0; g.A.off[1] = 1; g.A.off[2] = 2;
         g.tag = OPH_TAG_DGRAD; g.Bpacked = packed_w_bwd; g.M = B * L; g.N = C; g.Kc = C; g.ntaps = 3;
         g.C = dx; g.ldc = lddx;
@@ -414,7 +463,8 @@ int oph_deconv_bwd(const float* dy, long long lddy, const float* x, long long ld
     }
     if (dw) {   // dW[j][co][ci]: j=0: dz[2i] x[i]; j=1: dz[2i+1] x[i]; j=2: dz[2i] x[i-1]
         const int a_off[3] = {0, 1, 0}, b_off[3] = {0, 0, -1};
-        OPH_TRY(launch_wgrad(dz, lddz, C, a_off, L, 2 * L, 2, x, ldx, C, b_off, L, L, 1, B * L, 3, dw, C, S(stream)));
+        OperandMap xm; set_operand(xm, x);
+        OPH_TRY(launch_wgrad(dzm, C, a_off, L, 2 * L, 2, xm, C, b_off, L, L, 1, B * L, 3, dw, C, S(stream)));
     }
     return OPH_OK;
 }

@@ -20,7 +20,9 @@ enum { Z_NONE = 0, Z_BATCH = 1, Z_SPLITK = 2 };
 
 struct OperandMap {        // logical row r -> (item b, step t) = divmod(r, L);  source step ts = t*mul + off[tap]
     const float* ptr;      // valid iff 0 <= ts < Ls;  source row = b*Ls + ts
-    long long ld;          // row stride in elements (multiple of 4, rows 16-byte aligned)
+    const unsigned short* hi;   // optional pre-split operand: bf16 planes hi / lo with the same [row][ld] indexing
+    const unsigned short* lo;   //   (written by the row-wise kernels); then ptr is unused and ld % 8 == 0
+    long long ld;          // row stride in elements (fp32: multiple of 4; planes: multiple of 8)
     int L, Ls, mul;
     int off[3];
 };
@@ -48,6 +50,7 @@ struct GemmArgs {
     int atomic;            // 1: atomicAdd into C (split-K)
     int tag;               // host-side profiling category (OPH_TAG_*)
     long long* dbg;        // optional [pairs][8] cycle counters of the MMA / producer waits (diagnostics)
+    int dbg_flags;         // diagnostics only: 1 = producers skip data movement, 2 = weight loader skips copies
 };
 
 constexpr int GEMM_BM = 128;                        // rows per CTA (256 per pair)
@@ -62,10 +65,9 @@ constexpr int B_STAGE = 2 * B_SLOT;                 // both CTAs: one k-block of
 constexpr int NA_SLOTS = 3;
 constexpr int NB_SLOTS = 3;
 constexpr int N_ACC = 2;                            // accumulator stages in tensor memory (2 x 256 columns)
-constexpr int EPI_STAGE_BYTES = 4 * 32 * 33 * 4;    // per-warp transposition buffers of the 4 epilogue warps
-constexpr int NPW = 16;                             // producer warps (each thread owns NCH chunks of 8 elements per tile)
-constexpr int NCH = 1024 / (NPW * 32);
+constexpr int NPW = 16;                             // producer warps
 constexpr int GEMM_THREADS = (NPW + 8) * 32;        // producers, then 4 epilogue warps, then MMA / bulk copy / relay / idle
+constexpr int EPI_STAGE_BYTES = 4 * 32 * 33 * 4;    // per-warp transposition buffers of the 4 epilogue warps
 constexpr int GEMM_SMEM = NA_SLOTS * A_SLOT + NB_SLOTS * B_SLOT + EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int GEMM_MAX_PAIRS = 74;                  // 148 SMs
 
@@ -77,6 +79,41 @@ __device__ __forceinline__ void load8(const float* src, bool row_ok, int first, 
     } else {
 #pragma unroll
         for (int e = 0; e < 8; ++e) v[e] = (row_ok && first + e < limit) ? __ldg(src + e) : 0.f;
+    }
+}
+
+// one 8-element chunk of an operand into registers: fp32 source -> 8 floats; pre-split source -> hi uint4 | lo uint4
+__device__ __forceinline__ void load_chunk(const OperandMap& o, long long z_off, long long off, bool ok, int first, int limit, float (&v)[8]) {
+    if (o.hi) {
+        uint4 h = make_uint4(0u, 0u, 0u, 0u), l = h;
+        if (ok && first < limit) {
+            h = __ldg(reinterpret_cast<const uint4*>(o.hi + z_off + off));
+            l = __ldg(reinterpret_cast<const uint4*>(o.lo + z_off + off));
+        }
+        v[0] = __uint_as_float(h.x); v[1] = __uint_as_float(h.y); v[2] = __uint_as_float(h.z); v[3] = __uint_as_float(h.w);
+        v[4] = __uint_as_float(l.x); v[5] = __uint_as_float(l.y); v[6] = __uint_as_float(l.z); v[7] = __uint_as_float(l.w);
+    } else {
+        const float* src = o.ptr + z_off + off;
+        if (ok && first + 8 <= limit) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(src));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = (ok && first + e < limit) ? __ldg(src + e) : 0.f;
+        }
+    }
+}
+// registers -> the hi / lo planes of a shared-memory tile (conversion only for fp32 sources)
+__device__ __forceinline__ void store_chunk(bool split_src, uint8_t* plane_hi, uint8_t* plane_lo, uint32_t off, const float (&v)[8]) {
+    if (split_src) {
+        *reinterpret_cast<uint4*>(plane_hi + off) = make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
+        *reinterpret_cast<uint4*>(plane_lo + off) = make_uint4(__float_as_uint(v[4]), __float_as_uint(v[5]), __float_as_uint(v[6]), __float_as_uint(v[7]));
+    } else {
+        uint4 hi, lo;
+        split8(v, hi, lo);
+        *reinterpret_cast<uint4*>(plane_hi + off) = hi;
+        *reinterpret_cast<uint4*>(plane_lo + off) = lo;
     }
 }
 
@@ -141,6 +178,8 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
     auto BAR = [&](int i) { return bar0 + 8u * i; };
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    unsigned long long gt_start = 0;
+    if (p.dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_start));
     const uint32_t crank = cluster_ctarank();          // 0 = leader (issues the MMAs), 1 = partner
     const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
     const int MP = ((p.M + GEMM_BM - 1) / GEMM_BM + 1) / 2;
@@ -172,10 +211,11 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
     if (warp < NPW) {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
         // ================================================================ producers (both CTAs)
-        // Each thread owns NCH chunks (8 consecutive elements each) of every operand tile.  Address arithmetic is
-        // hoisted: row pointers are set up once per tap (conv-style A) or advanced incrementally (row-reduction
-        // operands), so that a k-block costs loads + conversion + stores and little else.
-        uint32_t off_a[NCH], off_b[NCH];                         // smem offsets: K-major [128][64 k] / MN-major [64 k][128]
+        // Each thread owns NCH chunks (8 consecutive elements) of every operand tile.  Global loads run one k-block
+        // ahead of the shared-memory stores (register double buffer); address arithmetic is hoisted out of the chunk
+        // loop: row offsets are set up once per tap (conv-style A) or advanced incrementally (row-reduction operands).
+        constexpr int NCH = 1024 / (NPW * 32);
+        uint32_t off_a[NCH], off_b[NCH];                       // smem offsets: K-major [128][64 k] / MN-major [64 k][128]
 #pragma unroll
         for (int i = 0; i < NCH; ++i) {
             const int rl = (tid >> 3) + (NPW * 4) * i, chunk = tid & 7;
@@ -185,34 +225,35 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
             off_a[i] = a_k ? ok_ : omn;
             off_b[i] = (p.b_mode == B_KMAJOR) ? ok_ : omn;
         }
+        const bool a_split = p.A.hi != nullptr, b_split = p.Bm.hi != nullptr;
         int a_slot = 0, a_par = 1, b_slot = 0, b_par = 1;      // ring cursors: parity to wait for on the EMPTY barriers
         for (int u = pair; u < total; u += npairs) {
             const Unit t = decode_unit(p, u, MP, nblocks, crank);
             if (t.KB <= 0) continue;
-            const float* Ap = p.A.ptr + t.a_z;
-            const float* Bp = packed ? nullptr : (p.Bm.ptr + t.b_z);
             const int ntl = a_k ? p.ntaps : 1;
 
-            // ---- A load stream state (runs one k-block ahead of the store stream)
+            // ---- A load stream (runs one k-block ahead of the store stream)
             int la_tap = 0, la_cb = 0;
-            const float* a_cur[NCH]; bool a_val[NCH];
+            long long a_cur[NCH]; bool a_val[NCH];             // element offsets of this thread's rows for the current tap
             int a_t[NCH]; long long a_base[NCH]; bool a_ok[NCH];
-            int ar_b[NCH], ar_t[NCH], ar_r[NCH];
-            if (a_k) {
+            int ar_b[NCH], ar_t[NCH], ar_r[NCH], br_b[NCH], br_t[NCH], br_r[NCH];
 #pragma unroll
-                for (int i = 0; i < NCH; ++i) {
+            for (int i = 0; i < NCH; ++i) {
+                if (a_k) {
                     const int g = t.m0 + (tid >> 3) + (NPW * 4) * i;
                     a_ok[i] = g < p.M;
                     const int b = g / p.A.L;
                     a_t[i] = g - b * p.A.L;
                     a_base[i] = (long long)b * p.A.Ls;
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < NCH; ++i) {
+                } else {
                     ar_r[i] = t.k_begin + (tid >> 4) + (NPW * 2) * i;
                     ar_b[i] = ar_r[i] / p.A.L;
                     ar_t[i] = ar_r[i] - ar_b[i] * p.A.L;
+                }
+                if (p.b_mode == B_MNMAJOR) {
+                    br_r[i] = t.k_begin + (tid >> 4) + (NPW * 2) * i;
+                    br_b[i] = br_r[i] / p.Bm.L;
+                    br_t[i] = br_r[i] - br_b[i] * p.Bm.L;
                 }
             }
             auto a_set_tap = [&](int tap) {
@@ -220,67 +261,38 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
                 for (int i = 0; i < NCH; ++i) {
                     const int ts = a_t[i] * p.A.mul + p.A.off[tap];
                     a_val[i] = a_ok[i] && ts >= 0 && ts < p.A.Ls;
-                    a_cur[i] = Ap + (a_base[i] + ts) * p.A.ld + (tid & 7) * 8;
+                    a_cur[i] = (a_base[i] + ts) * p.A.ld + (tid & 7) * 8;
                 }
             };
             if (a_k) a_set_tap(0);
-            auto load_a = [&](float (&v)[NCH][8]) {              // loads the next k-block of the stream, then advances it
+            auto load_a = [&](float (&v)[NCH][8]) {              // next k-block of the stream: global -> registers
+                if (p.dbg_flags & 1) return;
                 if (a_k) {
-                    const int c = t.k_begin + la_cb * GEMM_BK + (tid & 7) * 8;
-                    const bool full = c + 8 <= t.k_end;
+                    const int kk = t.k_begin + la_cb * GEMM_BK;
+                    const int c = kk + (tid & 7) * 8;
 #pragma unroll
-                    for (int i = 0; i < NCH; ++i) {
-                        const float* src = a_cur[i] + (t.k_begin + la_cb * GEMM_BK);
-                        if (full) {
-                            float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
-                            if (a_val[i]) { x0 = __ldg(reinterpret_cast<const float4*>(src)); x1 = __ldg(reinterpret_cast<const float4*>(src) + 1); }
-                            v[i][0] = x0.x; v[i][1] = x0.y; v[i][2] = x0.z; v[i][3] = x0.w;
-                            v[i][NCH] = x1.x; v[i][5] = x1.y; v[i][6] = x1.z; v[i][7] = x1.w;
-                        } else {
-                            load8(src, a_val[i], c, t.k_end, v[i]);
-                        }
-                    }
+                    for (int i = 0; i < NCH; ++i) load_chunk(p.A, t.a_z, a_cur[i] + kk, a_val[i], c, t.k_end, v[i]);
                     if (++la_cb == t.KBc) { la_cb = 0; if (++la_tap < ntl) a_set_tap(la_tap); }
                 } else {
                     const int m = t.m0 + (tid & 15) * 8;
-                    const bool full = m + 8 <= p.M;
 #pragma unroll
                     for (int i = 0; i < NCH; ++i) {
                         const int ts = ar_t[i] * p.A.mul + p.A.off[t.ytap];
                         const bool ok = ts >= 0 && ts < p.A.Ls && ar_r[i] < t.k_end;
-                        const float* src = Ap + ((long long)ar_b[i] * p.A.Ls + ts) * p.A.ld + m;
-                        if (full) {
-                            float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
-                            if (ok) { x0 = __ldg(reinterpret_cast<const float4*>(src)); x1 = __ldg(reinterpret_cast<const float4*>(src) + 1); }
-                            v[i][0] = x0.x; v[i][1] = x0.y; v[i][2] = x0.z; v[i][3] = x0.w;
-                            v[i][NCH] = x1.x; v[i][5] = x1.y; v[i][6] = x1.z; v[i][7] = x1.w;
-                        } else {
-                            load8(src, ok, m, p.M, v[i]);
-                        }
+                        load_chunk(p.A, t.a_z, ((long long)ar_b[i] * p.A.Ls + ts) * p.A.ld + m, ok, m, p.M, v[i]);
                         ar_r[i] += GEMM_BK; ar_t[i] += GEMM_BK;
                         while (ar_t[i] >= p.A.L) { ar_t[i] -= p.A.L; ++ar_b[i]; }
                     }
                 }
             };
-
-            // ---- B from fp32 activations: this CTA stages rows/columns [n0 + crank*128, +128) of every stage
-            int br_b[NCH], br_t[NCH], br_r[NCH];
-            if (p.b_mode == B_MNMAJOR) {
-#pragma unroll
-                for (int i = 0; i < NCH; ++i) {
-                    br_r[i] = t.k_begin + (tid >> 4) + (NPW * 2) * i;
-                    br_b[i] = br_r[i] / p.Bm.L;
-                    br_t[i] = br_r[i] - br_b[i] * p.Bm.L;
-                }
-            }
-            const int nbase = t.n0 + (int)crank * GEMM_BNC;
-            auto load_b = [&](int kb, float (&v)[NCH][8]) {
+            const int nbase = t.n0 + (int)crank * GEMM_BNC;    // this CTA stages B rows/columns [nbase, nbase + 128)
+            auto load_b = [&](int kb, float (&v)[NCH][8]) {      // B from activations (attention / weight-gradient products)
                 if (p.b_mode == B_KMAJOR) {
                     const int c = t.k_begin + (kb - (kb / t.KBc) * t.KBc) * GEMM_BK + (tid & 7) * 8;
 #pragma unroll
                     for (int i = 0; i < NCH; ++i) {
                         const int n = nbase + (tid >> 3) + (NPW * 4) * i;
-                        load8(Bp + (long long)n * p.Bm.ld + c, n < p.N, c, t.k_end, v[i]);
+                        load_chunk(p.Bm, t.b_z, (long long)n * p.Bm.ld + c, n < p.N, c, t.k_end, v[i]);
                     }
                 } else {
                     const int tap = a_k ? kb / t.KBc : t.ytap;
@@ -289,20 +301,21 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
                     for (int i = 0; i < NCH; ++i) {
                         const int ts = br_t[i] * p.Bm.mul + p.Bm.off[tap];
                         const bool ok = ts >= 0 && ts < p.Bm.Ls && br_r[i] < t.k_end;
-                        load8(Bp + ((long long)br_b[i] * p.Bm.Ls + ts) * p.Bm.ld + n, ok, n, p.N, v[i]);
+                        load_chunk(p.Bm, t.b_z, ((long long)br_b[i] * p.Bm.Ls + ts) * p.Bm.ld + n, ok, n, p.N, v[i]);
                         br_r[i] += GEMM_BK; br_t[i] += GEMM_BK;
                         while (br_t[i] >= p.Bm.L) { br_t[i] -= p.Bm.L; ++br_b[i]; }
                     }
                 }
             };
-
-            // one k-block: convert + store the A tile held in registers, then (activation x activation products) B
+            // one k-block: (convert +) store the A tile held in registers, then B for activation x activation products
             auto emit = [&](int kb, float (&v)[NCH][8]) {
                 {
                     mbar_wait(BAR(BAR_EMPTY_A + a_slot), a_par);
                     uint8_t* hi = sA + a_slot * A_SLOT;
+                    if (!(p.dbg_flags & 1)) {
 #pragma unroll
-                    for (int i = 0; i < NCH; ++i) store_split(hi, hi + A_PLANE, off_a[i], v[i]);
+                        for (int i = 0; i < NCH; ++i) store_chunk(a_split, hi, hi + A_PLANE, off_a[i], v[i]);
+                    }
                     fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) { if (crank == 0) mbar_arrive(BAR(BAR_FULL_A + a_slot)); else mbar_arrive_remote(BAR(BAR_FULL_A + a_slot), 0); }
@@ -314,14 +327,14 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
                     mbar_wait(BAR(BAR_EMPTY_B + b_slot), b_par);
                     uint8_t* hi = sB + b_slot * B_SLOT;
 #pragma unroll
-                    for (int i = 0; i < NCH; ++i) store_split(hi, hi + B_PLANE, off_b[i], w[i]);
+                    for (int i = 0; i < NCH; ++i) store_chunk(b_split, hi, hi + B_PLANE, off_b[i], w[i]);
                     fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) { if (crank == 0) mbar_arrive(BAR(BAR_FULL_B + b_slot)); else mbar_arrive_remote(BAR(BAR_FULL_B + b_slot), 0); }
                     if (++b_slot == NB_SLOTS) { b_slot = 0; b_par ^= 1; }
                 }
             };
-            float v0[NCH][8], v1[NCH][8];                          // register double buffer: loads run one k-block ahead
+            float v0[NCH][8], v1[NCH][8];
             load_a(v0);
             for (int kb = 0; kb < t.KB; kb += 2) {
                 if (kb + 1 < t.KB) load_a(v1);
@@ -336,7 +349,6 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
         // ================================================================ epilogue warps (both CTAs): TMEM -> global
         const int q = warp & 3;                                // TMEM lane quadrant this warp may access
-        float* stage = sStage + q * (32 * 33);
         int acc = 0, acc_par = 0;
         for (int u = pair; u < total; u += npairs) {
             const Unit t = decode_unit(p, u, MP, nblocks, crank);
@@ -349,6 +361,7 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
             const int nrows = min(32, p.M - grow0);            // <= 0 for padding rows
             const long long crow0 = (long long)grow0 * p.c_mul + p.c_off;
             const long long dstep = (long long)p.c_mul * p.ldc, astep = (long long)p.c_mul * p.ld_add;
+            float* stage = sStage + q * (32 * 33);             // transposition buffer: coalesced 128-byte row segments
 #pragma unroll 1
             for (int ch = 0; ch < GEMM_BN / 32; ++ch) {
                 const int col0 = ch * 32;
@@ -372,9 +385,10 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
                         for (int rr = 0; rr < nrows; ++rr, dst += dstep) atomicAdd(dst, stage[rr * 33 + lane] * p.alpha + bv);
                     } else if (addb) {
                         const float* add = addb + crow0 * p.ld_add + gcol;
+#pragma unroll 4
                         for (int rr = 0; rr < nrows; ++rr, dst += dstep, add += astep) *dst = stage[rr * 33 + lane] * p.alpha + bv + __ldg(add);
                     } else {
-#pragma unroll 4
+#pragma unroll 8
                         for (int rr = 0; rr < nrows; ++rr, dst += dstep) *dst = stage[rr * 33 + lane] * p.alpha + bv;
                     }
                 }
@@ -432,7 +446,9 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
             }
             if (p.dbg) {
                 long long* o = p.dbg + pair * 8;
+                unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
                 o[0] = clock64() - t_begin; o[1] = w_t; o[2] = w_a; o[3] = w_b; o[4] = nkb;
+                o[5] = (long long)(gt - gt_start);      // ns from kernel entry to the end of the MMA issue loop
             }
         }
         __syncwarp();
@@ -446,8 +462,11 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
                 for (int kb = 0; kb < t.KB; ++kb) {
                     mbar_wait(BAR(BAR_EMPTY_B + slot), par);
                     const uint32_t bar = BAR((crank == 0 ? BAR_FULL_B : BAR_LAND_B) + slot);
-                    mbar_arrive_expect_tx(bar, B_SLOT);
-                    bulk_g2s(smem_u32(sB + slot * B_SLOT), src + (size_t)kb * B_STAGE, B_SLOT, bar);
+                    if (p.dbg_flags & 2) { mbar_arrive(bar); }
+                    else {
+                        mbar_arrive_expect_tx(bar, B_SLOT);
+                        bulk_g2s(smem_u32(sB + slot * B_SLOT), src + (size_t)kb * B_STAGE, B_SLOT, bar);
+                    }
                     if (++slot == NB_SLOTS) { slot = 0; par ^= 1; }
                 }
             }
@@ -471,7 +490,15 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
     }
 
     tc_fence_before();
+    if (p.dbg && crank == 0 && tid == 256) {           // an epilogue-free producer thread: time until its role loop ended
+        unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        p.dbg[pair * 8 + 6] = (long long)(gt - gt_start);
+    }
     cluster_sync_all();                                // the partner's smem/barriers stay alive until both are done
+    if (p.dbg && crank == 0 && tid == 0) {
+        unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        p.dbg[pair * 8 + 7] = (long long)(gt - gt_start);      // ns from kernel entry to after the final cluster barrier
+    }
     if (warp == NPW + 4) tmem_dealloc2<N_ACC * GEMM_BN>(tmem_base);
 }
 

@@ -3,6 +3,7 @@
 // One warp owns one [C]-row; reductions along channels are warp shuffles; loads are lane-contiguous.
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_bf16.h>
 #include <stdint.h>
 
 namespace oph {
@@ -439,6 +440,22 @@ __device__ __forceinline__ void st_row(float* __restrict__ p, int lane, const fl
 #pragma unroll
     for (int i = 0; i < VEC; ++i) *reinterpret_cast<float4*>(p + i * 128 + lane * 4) = v[i];
 }
+// same row as split-bf16 planes (hi = bf16(x), lo = bf16(x - hi)): the operand format the GEMM producers copy verbatim
+template <int VEC>
+__device__ __forceinline__ void st_row_planes(unsigned short* __restrict__ hi, unsigned short* __restrict__ lo, int lane,
+                                              const float4 (&v)[VEC]) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        const __nv_bfloat162 h0 = __floats2bfloat162_rn(v[i].x, v[i].y), h1 = __floats2bfloat162_rn(v[i].z, v[i].w);
+        const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+        const __nv_bfloat162 l0 = __floats2bfloat162_rn(v[i].x - f0.x, v[i].y - f0.y), l1 = __floats2bfloat162_rn(v[i].z - f1.x, v[i].w - f1.y);
+        uint2 hh, ll;
+        hh.x = *reinterpret_cast<const uint32_t*>(&h0); hh.y = *reinterpret_cast<const uint32_t*>(&h1);
+        ll.x = *reinterpret_cast<const uint32_t*>(&l0); ll.y = *reinterpret_cast<const uint32_t*>(&l1);
+        *reinterpret_cast<uint2*>(hi + i * 128 + lane * 4) = hh;
+        *reinterpret_cast<uint2*>(lo + i * 128 + lane * 4) = ll;
+    }
+}
 template <int VEC>
 __device__ __forceinline__ RowStats reg_stats(const float4 (&v)[VEC]) {
     float s = 0.f;
@@ -460,7 +477,8 @@ template <int VEC>
 __global__ void __launch_bounds__(256) hc_post_fwd_vec_kernel(
         const float* __restrict__ z, long long ldz, const float* __restrict__ x, long long ldx,
         const float* __restrict__ g1, const float* __restrict__ b1, const float* __restrict__ g2,
-        const float* __restrict__ b2, float* __restrict__ y, long long ldy, float* __restrict__ stats,
+        const float* __restrict__ b2, float* __restrict__ y, long long ldy, unsigned short* __restrict__ y_hi,
+        unsigned short* __restrict__ y_lo, long long ldp, float* __restrict__ stats,
         int rows, int norm, float drop_p, unsigned long long seed, const long long* step) {
     constexpr int C = 128 * VEC;
     const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
@@ -491,13 +509,15 @@ __global__ void __launch_bounds__(256) hc_post_fwd_vec_kernel(
                 OPH_F4(o[i], e) = r;
             }
         st_row<VEC>(y + row * ldy, lane, o);
+        if (y_hi) st_row_planes<VEC>(y_hi + row * ldp, y_lo + row * ldp, lane, o);
     }
 }
 
 template <int VEC>
 __global__ void __launch_bounds__(256) ln_act_fwd_vec_kernel(
         const float* __restrict__ z, long long ldz, const float* __restrict__ gamma, const float* __restrict__ beta,
-        float* __restrict__ y, long long ldy, float* __restrict__ y_sig, long long ldys, float* __restrict__ stats,
+        float* __restrict__ y, long long ldy, float* __restrict__ y_sig, long long ldys,
+        unsigned short* __restrict__ y_hi, unsigned short* __restrict__ y_lo, long long ldp, float* __restrict__ stats,
         int rows, int act, int norm, float drop_p, unsigned long long seed, const long long* step) {
     constexpr int C = 128 * VEC;
     const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
@@ -523,6 +543,7 @@ __global__ void __launch_bounds__(256) ln_act_fwd_vec_kernel(
                 OPH_F4(o[i], e) = a;
             }
         st_row<VEC>(y + row * ldy, lane, o);
+        if (y_hi) st_row_planes<VEC>(y_hi + row * ldp, y_lo + row * ldp, lane, o);
         if (y_sig) st_row<VEC>(y_sig + row * ldys, lane, sg);
     }
 }
@@ -549,7 +570,8 @@ __global__ void __launch_bounds__(256) hc_post_bwd_vec_kernel(
         const float* __restrict__ dy, long long lddy, const float* __restrict__ z, long long ldz,
         const float* __restrict__ x, long long ldx, const float* __restrict__ stats,
         const float* __restrict__ g1, const float* __restrict__ b1, const float* __restrict__ g2,
-        const float* __restrict__ b2, float* __restrict__ dz, long long lddz, float* __restrict__ dxres, long long lddx,
+        const float* __restrict__ b2, float* __restrict__ dz, long long lddz, unsigned short* __restrict__ dz_hi,
+        unsigned short* __restrict__ dz_lo, long long ldp, float* __restrict__ dxres, long long lddx,
         float* __restrict__ dg1, float* __restrict__ db1, float* __restrict__ dg2, float* __restrict__ db2,
         float* __restrict__ dbias, int rows, int norm, float drop_p, unsigned long long seed, const long long* step) {
     constexpr int C = 128 * VEC;
@@ -616,8 +638,13 @@ __global__ void __launch_bounds__(256) hc_post_bwd_vec_kernel(
                     acc[4][i * 4 + e] += d1; acc[5][i * 4 + e] += d2;
                 }
         }
-        st_row<VEC>(dz + row * lddz, lane, e1v);
-        st_row<VEC>(dz + row * lddz + C, lane, e2v);
+        if (dz_hi) {                           // the GEMMs are the only consumers of dz: write it in their operand format
+            st_row_planes<VEC>(dz_hi + row * ldp, dz_lo + row * ldp, lane, e1v);
+            st_row_planes<VEC>(dz_hi + row * ldp + C, dz_lo + row * ldp + C, lane, e2v);
+        } else {
+            st_row<VEC>(dz + row * lddz, lane, e1v);
+            st_row<VEC>(dz + row * lddz + C, lane, e2v);
+        }
     }
     float* const dst[6] = {norm ? dg1 : nullptr, norm ? db1 : nullptr, norm ? dg2 : nullptr, norm ? db2 : nullptr,
                            dbias, dbias ? dbias + C : nullptr};
@@ -628,7 +655,8 @@ template <int VEC>
 __global__ void __launch_bounds__(256) ln_act_bwd_vec_kernel(
         const float* __restrict__ dy, long long lddy, const float* __restrict__ z, long long ldz,
         const float* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
-        float* __restrict__ dz, long long lddz, float* __restrict__ dgamma, float* __restrict__ dbeta,
+        float* __restrict__ dz, long long lddz, unsigned short* __restrict__ dz_hi, unsigned short* __restrict__ dz_lo,
+        long long ldp, float* __restrict__ dgamma, float* __restrict__ dbeta,
         float* __restrict__ dbias, int rows, int act, int norm, float drop_p, unsigned long long seed,
         const long long* step) {
     constexpr int C = 128 * VEC;
@@ -681,7 +709,8 @@ __global__ void __launch_bounds__(256) ln_act_bwd_vec_kernel(
                     OPH_F4(ev[i], e) = d; acc[2][i * 4 + e] += d;
                 }
         }
-        st_row<VEC>(dz + row * lddz, lane, ev);
+        if (dz_hi) st_row_planes<VEC>(dz_hi + row * ldp, dz_lo + row * ldp, lane, ev);
+        else st_row<VEC>(dz + row * lddz, lane, ev);
     }
     float* const dst[3] = {norm ? dgamma : nullptr, norm ? dbeta : nullptr, dbias};
     flush_acc<VEC, 3>(acc, sacc, lane, dst);

@@ -127,7 +127,7 @@ def conv1d(inputs, filters=None, size=1, rate=1, padding="SAME", dropout_rate=0,
     step = _step_ptr(store, training)
     rec = _recording(training)
     y, ysig, saved = ops.conv1d_fwd(inputs, pk, store.get(bn), gamma, beta, rate, pad, in_shift, act, norm, drop, seed,
-                                    step, save=rec, y=out, want_sigmoid=want_sigmoid)
+                                    step, save=rec, y=out, want_sigmoid=want_sigmoid, planes=out is None)
     if rec:
         need_dx = not getattr(inputs, "_oph_no_grad", False)
 
@@ -171,7 +171,8 @@ def hc(inputs, filters=None, size=1, rate=1, padding="SAME", dropout_rate=0, use
     seed = layer_seed(kn)
     step = _step_ptr(store, training)
     rec = _recording(training)
-    y, saved = ops.hc_fwd(inputs, pk, store.get(bn), g1, b1, g2, b2, rate, pad, norm, drop, seed, step, save=rec, y=out)
+    y, saved = ops.hc_fwd(inputs, pk, store.get(bn), g1, b1, g2, b2, rate, pad, norm, drop, seed, step, save=rec, y=out,
+                          planes=out is None)
     if rec:
         def bwd(dy):
             gr = [store.grad(n) for n in names] if norm else [None] * 4

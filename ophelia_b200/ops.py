@@ -34,6 +34,32 @@ def _pad4(c):
     return (c + 3) // 4 * 4
 
 
+PLANE_WIDTHS = (256, 512, 1024)      # channel counts for which the row-wise kernels can emit split-bf16 planes
+
+
+def _act(t, use_planes=True):
+    """oph_act for a [B, L, C] activation; planes ride along as `t._oph_planes = (hi, lo)` (bf16 [B, L, C])."""
+    a = _lib.Act()
+    ld = _rows(t)[0]
+    a.f32, a.ld = t.data_ptr(), ld
+    pl = getattr(t, "_oph_planes", None) if use_planes else None
+    if pl is not None:
+        a.hi, a.lo, a.ldp = pl[0].data_ptr(), pl[1].data_ptr(), pl[0].stride(1)
+    return a
+
+
+def _out_act(y, want_planes):
+    """oph_act for an output; allocates (and attaches) the planes when the width supports them."""
+    a = _lib.Act()
+    a.f32, a.ld = y.data_ptr(), y.stride(1)
+    if want_planes and y.shape[2] in PLANE_WIDTHS:
+        hi = torch.empty(y.shape, device=y.device, dtype=torch.bfloat16)
+        lo = torch.empty(y.shape, device=y.device, dtype=torch.bfloat16)
+        a.hi, a.lo, a.ldp = hi.data_ptr(), lo.data_ptr(), hi.stride(1)
+        y._oph_planes = (hi, lo)
+    return a
+
+
 def new_act(B, L, C, device):
     """[B, L, C] view over a buffer whose row stride is padded to a multiple of 4 floats."""
     ld = _pad4(C)
@@ -68,7 +94,7 @@ class PackedConv(object):
 
 # ---------------------------------------------------------------------------------------------- conv1d
 def conv1d_fwd(x, pk, bias, gamma, beta, rate=1, padding=SAME, in_shift=0, act=ACT_NONE, norm=True,
-               drop_p=0.0, seed=0, step=None, save=False, y=None, want_sigmoid=False):
+               drop_p=0.0, seed=0, step=None, save=False, y=None, want_sigmoid=False, planes=True):
     ldx, B, L, cin = _rows(x)
     assert cin == pk.cin
     cout = pk.cout
@@ -78,8 +104,9 @@ def conv1d_fwd(x, pk, bias, gamma, beta, rate=1, padding=SAME, in_shift=0, act=A
     if y is None:
         y = new_act(B, L, cout, dev)
     ysig = new_act(B, L, cout, dev) if want_sigmoid else None
-    _lib.call("oph_conv1d_fwd", _p(x), ldx, _p(pk.fwd), _p(bias), _p(gamma), _p(beta), _p(z), z.stride(1), _p(stats),
-              _p(y), y.stride(1), _p(ysig), ysig.stride(1) if ysig is not None else 0, B, L, cin, cout, pk.k, rate,
+    ya = _out_act(y, planes)
+    _lib.call("oph_conv1d_fwd", _act(x), _p(pk.fwd), _p(bias), _p(gamma), _p(beta), _p(z), z.stride(1), _p(stats),
+              ya, _p(ysig), ysig.stride(1) if ysig is not None else 0, B, L, cin, cout, pk.k, rate,
               padding, in_shift, act, int(bool(norm)), float(drop_p), int(seed), _p(step), _stream())
     return y, ysig, (z, stats)
 
@@ -93,7 +120,7 @@ def conv1d_bwd(dy, x, saved, pk, gamma, beta, dw, dbias, dgamma, dbeta, rate=1, 
     dz = new_act(B, L, pk.cout, dev)
     if need_dx and dx is None:
         dx = new_act(B, L, cin, dev)
-    _lib.call("oph_conv1d_bwd", _p(dy), lddy, _p(x), ldx, _p(z), z.stride(1), _p(stats), _p(pk.bwd), _p(gamma),
+    _lib.call("oph_conv1d_bwd", _p(dy), lddy, _act(x), _p(z), z.stride(1), _p(stats), _p(pk.bwd), _p(gamma),
               _p(beta), _p(dz), dz.stride(1), _p(dx) if need_dx else None, dx.stride(1) if need_dx else 0, _p(dw),
               _p(dbias), _p(dgamma), _p(dbeta), B, L, cin, pk.cout, pk.k, rate, padding, in_shift, act,
               int(bool(norm)), float(drop_p), int(seed), _p(step), _stream())
@@ -102,7 +129,7 @@ def conv1d_bwd(dy, x, saved, pk, gamma, beta, dw, dbias, dgamma, dbeta, rate=1, 
 
 # ---------------------------------------------------------------------------------------------- highway conv
 def hc_fwd(x, pk, bias, g1, b1, g2, b2, rate=1, padding=SAME, norm=True, drop_p=0.0, seed=0, step=None,
-           save=False, y=None):
+           save=False, y=None, planes=True):
     ldx, B, L, C = _rows(x)
     assert pk.cin == C and pk.cout == 2 * C
     dev = x.device
@@ -110,8 +137,9 @@ def hc_fwd(x, pk, bias, g1, b1, g2, b2, rate=1, padding=SAME, norm=True, drop_p=
     stats = torch.empty(B * L, 4, device=dev, dtype=torch.float32) if (save and norm) else None
     if y is None:
         y = torch.empty(B, L, C, device=dev, dtype=torch.float32)
-    _lib.call("oph_hc_fwd", _p(x), ldx, _p(pk.fwd), _p(bias), _p(g1), _p(b1), _p(g2), _p(b2), _p(z), z.stride(1),
-              _p(stats), _p(y), y.stride(1), B, L, C, pk.k, rate, padding, int(bool(norm)), float(drop_p),
+    ya = _out_act(y, planes)
+    _lib.call("oph_hc_fwd", _act(x), _p(pk.fwd), _p(bias), _p(g1), _p(b1), _p(g2), _p(b2), _p(z), z.stride(1),
+              _p(stats), ya, B, L, C, pk.k, rate, padding, int(bool(norm)), float(drop_p),
               int(seed), _p(step), _stream())
     return y, (z, stats)
 
@@ -126,7 +154,7 @@ def hc_bwd(dy, x, saved, pk, g1, b1, g2, b2, dw, dbias, dg1, db1, dg2, db2, rate
     dxres = torch.empty(B, L, C, device=dev, dtype=torch.float32)
     if dx is None:
         dx = torch.empty(B, L, C, device=dev, dtype=torch.float32)
-    _lib.call("oph_hc_bwd", _p(dy), lddy, _p(x), ldx, _p(z), z.stride(1), _p(stats), _p(pk.bwd), _p(g1), _p(b1),
+    _lib.call("oph_hc_bwd", _p(dy), lddy, _act(x), _p(z), z.stride(1), _p(stats), _p(pk.bwd), _p(g1), _p(b1),
               _p(g2), _p(b2), _p(dz), dz.stride(1), _p(dxres), dxres.stride(1), _p(dx), dx.stride(1), _p(dw),
               _p(dbias), _p(dg1), _p(db1), _p(dg2), _p(db2), B, L, C, pk.k, rate, padding, int(bool(norm)),
               float(drop_p), int(seed), _p(step), _stream())
@@ -141,8 +169,9 @@ def deconv_fwd(x, pk, bias, gamma, beta, drop_p=0.0, seed=0, step=None, save=Fal
     z = torch.empty(B, 2 * L, C, device=dev, dtype=torch.float32)
     stats = torch.empty(B * 2 * L, 2, device=dev, dtype=torch.float32) if save else None
     y = torch.empty(B, 2 * L, C, device=dev, dtype=torch.float32)
-    _lib.call("oph_deconv_fwd", _p(x), ldx, _p(pk.fwd), _p(bias), _p(gamma), _p(beta), _p(z), z.stride(1), _p(stats),
-              _p(y), y.stride(1), B, L, C, float(drop_p), int(seed), _p(step), _stream())
+    ya = _out_act(y, True)
+    _lib.call("oph_deconv_fwd", _act(x), _p(pk.fwd), _p(bias), _p(gamma), _p(beta), _p(z), z.stride(1), _p(stats),
+              ya, B, L, C, float(drop_p), int(seed), _p(step), _stream())
     return y, (z, stats)
 
 
@@ -153,7 +182,7 @@ def deconv_bwd(dy, x, saved, pk, gamma, beta, dw, dbias, dgamma, dbeta, drop_p=0
     dev = x.device
     dz = torch.empty(B, 2 * L, C, device=dev, dtype=torch.float32)
     dx = torch.empty(B, L, C, device=dev, dtype=torch.float32)
-    _lib.call("oph_deconv_bwd", _p(dy), lddy, _p(x), ldx, _p(z), z.stride(1), _p(stats), _p(pk.bwd), _p(gamma),
+    _lib.call("oph_deconv_bwd", _p(dy), lddy, _act(x), _p(z), z.stride(1), _p(stats), _p(pk.bwd), _p(gamma),
               _p(beta), _p(dz), dz.stride(1), _p(dx), dx.stride(1), _p(dw), _p(dbias), _p(dgamma), _p(dbeta),
               B, L, C, float(drop_p), int(seed), _p(step), _stream())
     return dx

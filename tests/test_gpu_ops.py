@@ -13,7 +13,7 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("group", ["gemm_nt", "gemm_tn", "conv1d", "hc", "deconv", "attention", "misc"])
+@pytest.mark.parametrize("group", ["gemm_nt", "gemm_tn", "conv1d", "hc", "hc_planes", "deconv", "attention", "misc"])
 def test_ops_match_oracle(group):
     import gpu_check
     del gpu_check.RESULTS[:]

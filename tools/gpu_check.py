@@ -168,6 +168,38 @@ def case_hc(B, L, C, k, rate, padding):
     return fn
 
 
+def case_hc_planes(B, L, C, k, rate, padding):
+    """Second layer of a chain: its input arrives with split-bf16 planes (copied, not converted, by the GEMMs)."""
+    def fn():
+        P0 = conv_params("p", 1, C, C)
+        P = conv_params("h", k, C, 2 * C, hc=True)
+        x0 = act32(rnd(B, L, C))
+        pk0 = ops.PackedConv(f32(P0["p/conv1d/kernel"]))
+        x, _, _ = ops.conv1d_fwd(x0, pk0, f32(P0["p/conv1d/bias"]), f32(P0["p/normalize/gamma"]), f32(P0["p/normalize/beta"]))
+        assert getattr(x, "_oph_planes", None) is not None
+        hi, lo = x._oph_planes
+        report("planes hi+lo == fp32 (C%d)" % C, maxerr(hi.float() + lo.float(), x), 2e-5 * float(x.abs().max()))
+        xr = x.detach().double().cpu().requires_grad_(True)
+        ref = ot.hc(P, xr, "h", k, rate, "CAUSAL" if padding else "SAME")
+        dy = rnd(B, L, C)
+        ref.backward(dy)
+        w = f32(P["h/conv1d/kernel"])
+        pk = ops.PackedConv(w)
+        prm = [f32(P[n]) for n in ("h/conv1d/bias", "h/H1/gamma", "h/H1/beta", "h/H2/gamma", "h/H2/beta")]
+        bias, g1, b1, g2, b2 = prm
+        y, saved = ops.hc_fwd(x, pk, bias, g1, b1, g2, b2, rate, padding, True, save=True)
+        tag = "hc(planes in) %dx%d C%d k%d r%d pad%d" % (B, L, C, k, rate, padding)
+        report(tag + " fwd", maxerr(y, ref), 2e-4)
+        grads = [torch.zeros_like(t) for t in [w] + prm]
+        dx = ops.hc_bwd(f32(dy), x, saved, pk, g1, b1, g2, b2, grads[0], grads[1], grads[2], grads[3], grads[4],
+                        grads[5], rate, padding, True)
+        report(tag + " dx", maxerr(dx, xr.grad), 5e-4)
+        gw = P["h/conv1d/kernel"].grad
+        report(tag + " dw", maxerr(grads[0], gw), 1e-3 * max(1.0, float(gw.abs().max())))
+        report(tag + " dbias", maxerr(grads[1], P["h/conv1d/bias"].grad), 2e-3)
+    return fn
+
+
 def case_deconv(B, L, C):
     def fn():
         P = conv_params("d", 3, C, C, deconv=True)
@@ -333,6 +365,7 @@ GROUPS = {
                case_conv1d(1, 37, 1025, 1025, 1, 0)],
     "hc": [case_hc(*a) for a in [(2, 200, 256, 3, 1, 1), (2, 200, 256, 3, 27, 1), (2, 60, 512, 3, 9, 0),
                                  (2, 60, 512, 1, 1, 0), (1, 130, 1024, 3, 1, 0), (3, 129, 256, 3, 3, 0)]],
+    "hc_planes": [case_hc_planes(2, 200, 256, 3, 3, 1), case_hc_planes(2, 70, 512, 3, 27, 0), case_hc_planes(1, 130, 1024, 3, 1, 0)],
     "deconv": [case_deconv(2, 50, 512), case_deconv(1, 131, 256)],
     "attention": [case_attention(2, 200, 60, False), case_attention(2, 210, 180, True),
                   case_attention(3, 130, 47, False)],

@@ -20,11 +20,16 @@ ap.add_argument("--rate", type=int, default=3)
 ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--warmup", type=int, default=3)
 ap.add_argument("--cluster", type=int, default=4)
+ap.add_argument("--planes", type=int, default=1)
+ap.add_argument("--dbg", type=int, default=0)
 a = ap.parse_args()
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
 B, L, C, k = a.B, a.L, a.C, a.k
 x = torch.randn(B, L, C, device=dev)
+if a.planes:    # like inside a network: the previous layer's row-wise kernel attached split-bf16 planes to x
+    w0 = torch.randn(1, C, C, device=dev) * (2.6 / C) ** 0.5
+    x, _, _ = ops.conv1d_fwd(x, ops.PackedConv(w0), torch.zeros(C, device=dev), torch.ones(C, device=dev), torch.zeros(C, device=dev))
 w = torch.randn(k, C, 2 * C, device=dev) * (2.6 / (k * C)) ** 0.5
 pk = ops.PackedConv(w)
 bias = torch.zeros(2 * C, device=dev)
@@ -52,6 +57,7 @@ def run():
 
 dbg = torch.zeros(74, 8, dtype=torch.int64, device=dev)
 _lib.call("oph_gemm_debug_buffer", dbg.data_ptr())
+_lib.call("oph_gemm_debug_flags", a.dbg)
 for _ in range(a.warmup):
     run()
 torch.cuda.synchronize()
@@ -67,7 +73,7 @@ torch.cuda.synchronize()
 prof = (ctypes.c_double * 15)()
 lib.oph_profile_end(prof)
 ms = e0.elapsed_time(e1) / a.iters
-print("%s B%d L%d C%d k%d cluster%d: %.3f ms per call" % (a.op, B, L, C, k, a.cluster, ms))
+print("%s B%d L%d C%d k%d planes%d dbg%d: %.3f ms per call" % (a.op, B, L, C, k, a.planes, a.dbg, ms))
 for i, n in enumerate(["other", "conv_fwd", "dgrad", "wgrad", "attention"]):
     if prof[3 * i] > 0:
         print("   gemm[%s]: %d launches/call, %.3f ms each, %.1f TFLOP/s algorithmic" %
