@@ -162,7 +162,7 @@ bool vec_ok(int C, long long ld0, long long ld1 = 4, long long ld2 = 4, long lon
 }
 int bwd_grid(long long rows) {          // few, long-lived warps so that per-channel sums stay in registers
     long long g = (rows + 8 * 8 - 1) / (8 * 8);
-    return (int)(g < 1 ? 1 : (g > 148 * 2 ? 148 * 2 : g));
+    return (int)(g < 1 ? 1 : (g > 148 * 4 ? 148 * 4 : g));
 }
 
 int launch_ln_act_fwd(const float* z, long long ldz, const float* gamma, const float* beta, const oph_act* yo,

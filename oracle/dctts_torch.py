@@ -255,7 +255,7 @@ def text2mel_train_step(hp, P, opt, L, mels, gen=None):
     comps[0].backward()
     grads = {k: p.grad for k, p in P.items() if p.grad is not None}
     opt.step(grads)
-    return [float(c) for c in comps], grads
+    return [float(c.detach()) for c in comps], grads
 
 
 def ssrn_train_step(hp, P, opt, mels, mags, gen=None):
@@ -266,4 +266,4 @@ def ssrn_train_step(hp, P, opt, mels, mags, gen=None):
     comps[0].backward()
     grads = {k: p.grad for k, p in P.items() if p.grad is not None}
     opt.step(grads)
-    return [float(c) for c in comps], grads
+    return [float(c.detach()) for c in comps], grads

@@ -48,6 +48,8 @@ def run():
         ops.hc_fwd(x, pk, bias, g1, b1, g2, b2, a.rate, 1, True, y=y)
     elif a.op == "hc_bwd":
         ops.hc_bwd(dy, x, saved, pk, g1, b1, g2, b2, *grads, a.rate, 1, True)
+    elif a.op == "hc_dgrad":
+        ops.hc_bwd(dy, x, saved, pk, g1, b1, g2, b2, None, *grads[1:], a.rate, 1, True)
     elif a.op == "conv_fwd":
         ops.conv1d_fwd(x, pk1, bias[:C], g1, b1, 1, 1, 0, 0, True, y=y)
     elif a.op == "attn_fwd":
