@@ -205,6 +205,22 @@ def run_ours(args):
     launches = (lib.oph_launch_count() - launches0) // args.steps
     last_loss = [float(c) for c in comps.cpu().numpy()]
 
+    # ---- timed region 1b: the same steps replayed from one CUDA graph (kernel-for-kernel identical work)
+    ms_graph = None
+    if not args.no_graph:
+        step = g.capture_train_step(*dev_in)
+        for _ in range(3):
+            step(*dev_in)
+        sync_all()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(args.steps):
+            comps = step(*dev_in)
+        g1.record()
+        sync_all()
+        ms_graph = g0.elapsed_time(g1) / args.steps
+        last_loss = [float(c) for c in comps.cpu().numpy()]
+
     # ---- timed region 2: end to end through Session.run with pinned host batches
     sync_all()
     t_e2e0 = torch.cuda.Event(enable_timing=True); t_e2e1 = torch.cuda.Event(enable_timing=True)
@@ -217,9 +233,13 @@ def run_ours(args):
     clk = clocks.stop() if rank == 0 else None
 
     if world > 1:
-        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms, ms_e2e, ms_graph if ms_graph is not None else 0.0], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e = float(t[0]), float(t[1])
+        ms_graph = float(t[2]) if ms_graph is not None else None
+    ms_eager = ms
+    if ms_graph is not None and ms_graph < ms:
+        ms = ms_graph                      # headline: the faster of the two launch modes over the same kernels
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -237,6 +257,9 @@ def run_ours(args):
         "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
         "per_gpu": frames_per_step / world / (ms * 1e-3),
+        "launch_mode": {"headline": "cuda_graph" if ms is ms_graph else "eager", "ms_per_step_eager": ms_eager,
+                        "ms_per_step_cuda_graph": ms_graph,
+                        "note": "roofline/gemm_breakdown are CUDA-event timings of every GEMM launch in the eager steps"},
         "e2e": {"value": frames_per_step / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": src.bytes_per_batch(), "d2h_bytes_per_step": 4 * len(last_loss) + 8},
         "gpu_launches": int(launches) * args.steps,
@@ -246,7 +269,7 @@ def run_ours(args):
                      "frac": achieved / pk["tensor_sustained"], "traffic": None,
                      "peak_source": pk["src"] + " bf16 cuBLAS sustained",
                      "launches_per_step": tot_n / args.steps, "avg_launch_ms": tot_ms / max(tot_n, 1),
-                     "share_of_step": (tot_ms / args.steps) / ms,
+                     "share_of_step": (tot_ms / args.steps) / ms_eager,
                      "note": "achieved counts ALGORITHMIC FLOPs once; the split-bf16 scheme issues 3 tensor passes per "
                              "FLOP, so the ceiling of this number is peak/3"},
         "gemm_breakdown": breakdown,
@@ -263,7 +286,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="t2m_train", choices=["t2m_train", "ssrn_train"])
@@ -273,6 +296,7 @@ def main():
     ap.add_argument("--full-dim", dest="full_dim", type=int, default=513)
     ap.add_argument("--ref-batch", dest="ref_batch", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="skip the CUDA-graph replay of the training step")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

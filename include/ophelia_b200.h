@@ -54,7 +54,7 @@ long long oph_launch_count(void);
  * (total cycles, cycles waiting for an accumulator stage, for A, for B, k-blocks). NULL disables. */
 int oph_gemm_debug_buffer(long long* dev_buf);
 /* diagnostics (results become garbage): 1 = operand producers skip loads/stores, 2 = weight loader skips copies,
- * 4 = force the register-staged producer path for pre-split operands */
+ * 4 = unused, 8 = do not feed pre-split operands with TMA tensor copies (producer warps copy them instead) */
 int oph_gemm_debug_flags(int flags);
 int oph_profile_begin(void);
 int oph_profile_end(double* out);

@@ -174,6 +174,48 @@ class Graph(object):
         ops.step_inc(st.global_step)
         st.version += 1
 
+    # ---- whole-step CUDA graph: one launch replays the ~280 kernels of a training step (static shapes only)
+    def capture_train_step(self, *example_inputs, warmup=2):
+        """Capture `train_step_device` into a CUDA graph.  Returns `step(*inputs) -> loss_components` (device tensor,
+        overwritten by every replay).  Inputs are copied into static device buffers; shapes must not change."""
+        static = [torch.empty_like(t) for t in example_inputs]
+        for s_, t in zip(static, example_inputs):
+            s_.copy_(t)
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                 # warm-up outside the capture (lazy packing, attribute calls);
+            for _ in range(warmup):                    # these are real optimiser steps on the example batch
+                self.train_step_device(*static)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            comps = self.train_step_device(*static)
+
+        def step(*inputs):
+            for s_, t in zip(static, inputs):
+                s_.copy_(t, non_blocking=True)
+            graph.replay()
+            return comps
+        step.graph, step.static_inputs, step.loss_components = graph, static, comps
+        return step
+
+    def _step_maybe_graphed(self, *dev_inputs):
+        """Static shapes (the usual case once batches are bucketed/padded to a fixed size) replay one CUDA graph per
+        step; the first two calls and any call with new shapes run eagerly.  hp.use_cuda_graph=False disables it."""
+        if not getattr(self.hp, "use_cuda_graph", True):
+            return self.train_step_device(*dev_inputs)
+        key = tuple(tuple(t.shape) for t in dev_inputs)
+        seen = self.__dict__.setdefault("_graph_seen", {})
+        steps = self.__dict__.setdefault("_graph_steps", {})
+        if key in steps:
+            return steps[key](*dev_inputs)
+        seen[key] = seen.get(key, 0) + 1
+        if seen[key] > 2:
+            steps[key] = self.capture_train_step(*dev_inputs, warmup=0)     # two eager calls already warmed everything
+            return steps[key](*dev_inputs)
+        return self.train_step_device(*dev_inputs)
+
     def _to_device(self, x, dtype):
         if isinstance(x, torch.Tensor):
             return x.to(self.device, dtype, non_blocking=True)
@@ -206,7 +248,7 @@ class SSRNGraph(Graph):
             batch = next(self.batch_source)
         mels = self._to_device(batch["mel"], torch.float32)
         mags = self._to_device(batch["mag"], torch.float32)
-        return self.train_step_device(mels, mags)
+        return self._step_maybe_graphed(mels, mags)
 
     def train_step_device(self, mels, mags):
         hp, st = self.hp, self.store
@@ -291,7 +333,7 @@ class Text2MelGraph(Graph):
             batch = next(self.batch_source)
         L = self._to_device(batch["text"], torch.int32)
         mels = self._to_device(batch["mel"], torch.float32)
-        return self.train_step_device(L, mels)
+        return self._step_maybe_graphed(L, mels)
 
     def train_step_device(self, L, mels):
         """One `sess.run([global_step, loss_components, train_op])` with inputs already on the device.

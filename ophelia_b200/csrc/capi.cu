@@ -44,6 +44,37 @@ int check_launch(const char* what) {
 inline cudaStream_t S(oph_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
+// ---- TMA tensor maps (driver entry point resolved at run time: no link dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+        cudaGetLastError();
+    }
+    return fn;
+}
+// bf16 plane [items][L][ld] viewed as (channels, time, item); box = 64 channels x box_rows steps, SWIZZLE_128B, zero fill
+bool make_plane_tmap(CUtensorMap* out, const unsigned short* base, int C, int L, int items, long long ld, int box_rows) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn || (reinterpret_cast<uintptr_t>(base) & 15) || (ld & 7)) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)L, (cuuint64_t)items};
+    const cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)L * ld * 2};
+    const cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<unsigned short*>(base), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+bool g_use_tma = true;
+
 int launch_gemm(GemmArgs& a, int zdim, cudaStream_t st) {
     static bool attr_done = false;
     if (!attr_done) {
@@ -59,10 +90,21 @@ int launch_gemm(GemmArgs& a, int zdim, cudaStream_t st) {
         return fail(OPH_EINVAL, "gemm: plane operands need channel counts that are multiples of 8%s");
     if (a.ytaps < 1) a.ytaps = 1;
     a.zdim = zdim < 1 ? 1 : zdim;
+    // conv-style A already split into planes: feed it with TMA tensor copies (per-item tiles, padding = out-of-range)
+    a.a_tma = 0; if (!a.r_tma) a.items = 1;
+    if (g_use_tma && a.a_mode == A_KMAJOR && a.A.hi && a.A.mul == 1 && a.A.L == a.A.Ls && a.z_mode == Z_NONE &&
+        !(a.Kc & 63) && a.M % a.A.L == 0) {
+        const int items = a.M / a.A.L;
+        if (make_plane_tmap(&a.tmA_hi, a.A.hi, a.Kc, a.A.L, items, a.A.ld, GEMM_BM) &&
+            make_plane_tmap(&a.tmA_lo, a.A.lo, a.Kc, a.A.L, items, a.A.ld, GEMM_BM)) {
+            a.a_tma = 1; a.items = items;
+        }
+    }
     a.dbg = g_gemm_dbg;
     a.dbg_flags = g_gemm_dbg_flags;
     // persistent CTA pairs: work units = (pair of 128-row tiles) x (256-column block) x tap x z slice
-    const long long units = (long long)cdiv(cdiv(a.M, GEMM_BM), 2) * cdiv(a.N, GEMM_BN) * a.ytaps * a.zdim;
+    const int mtiles = a.a_tma ? a.items * cdiv(a.A.L, GEMM_BM) : cdiv(a.M, GEMM_BM);
+    const long long units = (long long)cdiv(mtiles, 2) * cdiv(a.N, GEMM_BN) * a.ytaps * a.zdim;
     const int pairs = (int)(units < GEMM_MAX_PAIRS ? units : GEMM_MAX_PAIRS);
     dim3 grid(2 * pairs);
     ProfRec rec{};
@@ -74,7 +116,7 @@ int launch_gemm(GemmArgs& a, int zdim, cudaStream_t st) {
             prof = true;
             cudaEventCreate(&rec.e0); cudaEventCreate(&rec.e1);
             rec.tag = a.tag;
-            rec.flops = 2.0 * a.M * a.N * a.Kc * (a.a_mode == A_KMAJOR ? a.ntaps : a.ytaps) * (a.z_mode == Z_BATCH ? a.zdim : 1);
+            rec.flops = 2.0 * a.M * a.N * (a.prof_k ? a.prof_k : a.Kc) * (a.a_mode == A_KMAJOR ? a.ntaps : a.ytaps) * (a.z_mode == Z_BATCH ? a.zdim : 1);
             cudaEventRecord(rec.e0, st);
         }
     }
@@ -219,16 +261,28 @@ int launch_wgrad(const OperandMap& a, int M, const int* a_off, int aL, int aLs, 
     for (int j = 0; j < 3; ++j) { g.A.off[j] = j < taps ? a_off[j] : 0; g.Bm.off[j] = j < taps ? b_off[j] : 0; }
     g.M = M; g.N = N; g.Kc = R; g.ytaps = taps; g.c_tap_stride = (long long)M * ldc;
     g.C = dw; g.ldc = ldc; g.atomic = 1; g.z_mode = Z_SPLITK; g.tag = OPH_TAG_WGRAD;
+    // both operands pre-split and un-strided: feed them with TMA; the reduction then runs over (item, 64-step block) pairs
+    g.r_tma = 0;
+    const int items = aL > 0 ? R / aL : 0;
+    if (g_use_tma && g.A.hi && g.Bm.hi && a_mul == 1 && b_mul == 1 && aL == aLs && bL == bLs && aL == bL && items * aL == R &&
+        !(M & 127) && !(N & 127) &&
+        make_plane_tmap(&g.tmA_hi, g.A.hi, M, aL, items, g.A.ld, GEMM_BK) && make_plane_tmap(&g.tmA_lo, g.A.lo, M, aL, items, g.A.ld, GEMM_BK) &&
+        make_plane_tmap(&g.tmB_hi, g.Bm.hi, N, bL, items, g.Bm.ld, GEMM_BK) && make_plane_tmap(&g.tmB_lo, g.Bm.lo, N, bL, items, g.Bm.ld, GEMM_BK)) {
+        g.r_tma = 1; g.items = items;
+    }
     // split the reduction so that the work units fill whole rounds of the 74 persistent CTA pairs (never 2 rounds + a sliver)
     const int base = cdiv(cdiv(M, GEMM_BM), 2) * cdiv(N, GEMM_BN) * taps;     // work units before split-K
-    const int max_splits = cdiv(R, 4 * GEMM_BK);
+    const int kblocks = g.r_tma ? items * cdiv(aL, GEMM_BK) : cdiv(R, GEMM_BK);
+    const int max_splits = cdiv(kblocks, 4);
     int rounds = cdiv(base, GEMM_MAX_PAIRS);
     if (rounds < 2 && base * max_splits >= 2 * GEMM_MAX_PAIRS) rounds = 2;
     int splits = (rounds * GEMM_MAX_PAIRS) / base;
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
-    g.k_chunk = cdiv(cdiv(R, splits), GEMM_BK) * GEMM_BK;
-    splits = cdiv(R, g.k_chunk);
+    const int kb_chunk = cdiv(kblocks, splits);
+    splits = cdiv(kblocks, kb_chunk);
+    if (g.r_tma) { g.k_chunk = kb_chunk; g.Kc = kblocks; g.prof_k = R; }       // units of k-blocks
+    else g.k_chunk = kb_chunk * GEMM_BK;
     return launch_gemm(g, splits, st);
 }
 
@@ -241,7 +295,7 @@ int oph_version(void) { return 100; }
 const char* oph_last_error(void) { return g_err; }
 long long oph_launch_count(void) { return g_launches.load(); }
 int oph_gemm_debug_buffer(long long* dev_buf) { g_gemm_dbg = dev_buf; return OPH_OK; }
-int oph_gemm_debug_flags(int flags) { g_gemm_dbg_flags = flags; return OPH_OK; }
+int oph_gemm_debug_flags(int flags) { g_gemm_dbg_flags = flags & 7; g_use_tma = !(flags & 8); return OPH_OK; }
 
 int oph_profile_begin(void) {
     std::lock_guard<std::mutex> lk(g_prof_mu);
@@ -393,15 +447,16 @@ int oph_hc_bwd(const float* dy, long long lddy, const oph_act* x, const float* z
     const long long rows = (long long)B * L;
     const size_t smem = 6 * (size_t)C * sizeof(float);
     OperandMap dzm; dzm.ptr = dz; dzm.ld = lddz; dzm.hi = dzm.lo = nullptr;
-    if (vec_ok(C, lddy, ldz, x->ld, lddz, ldxr) && C <= 512 && lddz >= 2 * C) {
+    (void)dxres; (void)ldxr;
+    if (vec_ok(C, lddy, ldz, x->ld, lddz, lddx) && C <= 512 && lddz >= 2 * C) {
         const int grid = bwd_grid(rows);
         dz_as_planes(dz, rows, 2 * C, &dzm);
         unsigned short* h = const_cast<unsigned short*>(dzm.hi); unsigned short* l = const_cast<unsigned short*>(dzm.lo);
-        if (C == 256) hc_post_bwd_vec_kernel<2><<<grid, 256, smem, S(stream)>>>(dy, lddy, z, ldz, x->f32, x->ld, stats, g1, b1, g2, b2, nullptr, 0, h, l, 2 * C, dxres, ldxr, dg1, db1, dg2, db2, dbias, (int)rows, norm, drop_p, seed, step);
-        else          hc_post_bwd_vec_kernel<4><<<grid, 256, smem, S(stream)>>>(dy, lddy, z, ldz, x->f32, x->ld, stats, g1, b1, g2, b2, nullptr, 0, h, l, 2 * C, dxres, ldxr, dg1, db1, dg2, db2, dbias, (int)rows, norm, drop_p, seed, step);
+        if (C == 256) hc_post_bwd_vec_kernel<2><<<grid, 256, smem, S(stream)>>>(dy, lddy, z, ldz, x->f32, x->ld, stats, g1, b1, g2, b2, nullptr, 0, h, l, 2 * C, dx, lddx, dg1, db1, dg2, db2, dbias, (int)rows, norm, drop_p, seed, step);
+        else          hc_post_bwd_vec_kernel<4><<<grid, 256, smem, S(stream)>>>(dy, lddy, z, ldz, x->f32, x->ld, stats, g1, b1, g2, b2, nullptr, 0, h, l, 2 * C, dx, lddx, dg1, db1, dg2, db2, dbias, (int)rows, norm, drop_p, seed, step);
     } else {
         hc_post_bwd_kernel<<<rows_grid(rows, 8), 256, smem, S(stream)>>>(
-            dy, lddy, z, ldz, x->f32, x->ld, stats, g1, b1, g2, b2, dz, lddz, dxres, ldxr, dg1, db1, dg2, db2, dbias,
+            dy, lddy, z, ldz, x->f32, x->ld, stats, g1, b1, g2, b2, dz, lddz, dx, lddx, dg1, db1, dg2, db2, dbias,
             (int)rows, C, norm, drop_p, seed, step);
     }
     OPH_TRY(check_launch("hc_post_bwd_kernel"));
@@ -413,7 +468,9 @@ int oph_hc_bwd(const float* dy, long long lddy, const oph_act* x, const float* z
         g.A = dzm; g.A.L = L; g.A.Ls = L; g.A.mul = 1;
         for (int j = 0; j < 3; ++j) g.A.off[j] = -off[j];
         g.tag = OPH_TAG_DGRAD; g.Bpacked = packed_w_bwd; g.M = B * L; g.N = C; g.Kc = 2 * C; g.ntaps = k;
-        g.C = dx; g.ldc = lddx; g.addend = dxres; g.ld_add = ldxr;
+        // the row-wise kernel left do*(1-g) in dx; the GEMM accumulates W^T dz onto it with fire-and-forget RED.ADDs
+        // (one add per element: deterministic), so the epilogue never waits on a global load
+        g.C = dx; g.ldc = lddx; g.atomic = 1;
         OPH_TRY(launch_gemm(g, 1, S(stream)));
     }
     if (dw) {

@@ -10,6 +10,7 @@
 // (hi, lo) bf16 planes by the producer warps on their way into SWIZZLE_128B shared-memory tiles; pre-packed weight
 // images arrive through the bulk-copy (TMA) engine.  One thread of the leader CTA issues every tcgen05.mma.
 #pragma once
+#include <cuda.h>
 #include "oph_ptx.cuh"
 
 namespace oph {
@@ -50,7 +51,19 @@ struct GemmArgs {
     int atomic;            // 1: atomicAdd into C (split-K)
     int tag;               // host-side profiling category (OPH_TAG_*)
     long long* dbg;        // optional [pairs][8] cycle counters of the MMA / producer waits (diagnostics)
+    int prof_k;            // host-side: true reduction length for the FLOP count when Kc is in k-blocks (r_tma)
     int dbg_flags;         // diagnostics only: 1 = producers skip data movement, 2 = weight loader skips copies
+    // TMA feed of a pre-split conv-style A operand: tiles are cut per batch item (rows [t0, t0+128) of item b) so that
+    // conv padding and tile tails are out-of-range coordinates of the (channels, time, item) tensor maps.
+    // Weight-gradient products with both operands pre-split (r_tma): the reduction runs over (item, 64-step block) pairs
+    // so that tap shifts and item boundaries are out-of-range coordinates too; k_chunk then counts k-blocks.
+    int a_tma;             // 1: conv-style A tiles come from tmA_hi / tmA_lo, the producer warps do not touch A
+    int r_tma;             // 1: MN-major A and B tiles (64 steps x 128 channels each) come from tmA_* / tmB_*
+    int items;             // number of batch items (M = items * A.L)
+    alignas(64) CUtensorMap tmA_hi;
+    alignas(64) CUtensorMap tmA_lo;
+    alignas(64) CUtensorMap tmB_hi;
+    alignas(64) CUtensorMap tmB_lo;
 };
 
 constexpr int GEMM_BM = 128;                        // rows per CTA (256 per pair)
@@ -139,12 +152,15 @@ constexpr int BAR_EMPTY_A = BAR_FULL_A + NA_SLOTS;     // [NA_SLOTS] leader's co
 constexpr int BAR_FULL_B = BAR_EMPTY_A + NA_SLOTS;     // [NB_SLOTS]
 constexpr int BAR_EMPTY_B = BAR_FULL_B + NB_SLOTS;     // [NB_SLOTS]
 constexpr int BAR_LAND_B = BAR_EMPTY_B + NB_SLOTS;     // [NB_SLOTS] partner: its bulk copy landed (relayed to the leader)
-constexpr int BAR_T_FULL = BAR_LAND_B + NB_SLOTS;      // [N_ACC] accumulator stage complete (commit, multicast)
+constexpr int BAR_LAND_A = BAR_LAND_B + NB_SLOTS;      // [NA_SLOTS] partner: its TMA copy of A landed (relayed to the leader)
+constexpr int BAR_T_FULL = BAR_LAND_A + NA_SLOTS;      // [N_ACC] accumulator stage complete (commit, multicast)
 constexpr int BAR_T_EMPTY = BAR_T_FULL + N_ACC;        // [N_ACC] accumulator stage drained by 4+4 epilogue warps
 constexpr int NUM_BARS = BAR_T_EMPTY + N_ACC;
 
 struct Unit {               // one 256x256 output tile of one tap / z slice
     int m0, n0, nb, ytap, k_begin, k_end, KBc, KB;
+    int rows;               // valid rows of this CTA's 128-row tile (<= 0: padding CTA)
+    int item, t0;           // TMA mode: batch item and first time step of the tile
     long long a_z, b_z, c_z;
 };
 
@@ -154,11 +170,25 @@ __device__ __forceinline__ Unit decode_unit(const GemmArgs& p, int u, int MP, in
     t.nb = rest % nblocks; rest /= nblocks;
     t.ytap = rest % p.ytaps;
     const int z = rest / p.ytaps;
-    t.m0 = (mp * 2 + (int)crank) * GEMM_BM;            // may lie beyond M for the padding CTA of the last pair
+    const int mt = mp * 2 + (int)crank;
+    if (p.a_tma) {                                     // tiles never straddle batch items
+        const int tpi = (p.A.L + GEMM_BM - 1) / GEMM_BM;
+        t.item = mt / tpi; t.t0 = (mt - t.item * tpi) * GEMM_BM;
+        t.m0 = t.item * p.A.L + t.t0;
+        t.rows = t.item < p.items ? min(GEMM_BM, p.A.L - t.t0) : 0;
+    } else {
+        t.item = 0; t.t0 = 0;
+        t.m0 = mt * GEMM_BM;                           // may lie beyond M for the padding CTA of the last pair
+        t.rows = min(GEMM_BM, p.M - t.m0);
+    }
     t.n0 = t.nb * GEMM_BN;
     t.k_begin = 0; t.k_end = p.Kc; t.a_z = t.b_z = t.c_z = 0;
     if (p.z_mode == Z_BATCH) { t.a_z = z * p.a_zs; t.b_z = z * p.b_zs; t.c_z = z * p.c_zs; }
     if (p.z_mode == Z_SPLITK) { t.k_begin = z * p.k_chunk; t.k_end = min(p.Kc, t.k_begin + p.k_chunk); }
+    if (p.r_tma) {                                     // k_begin / k_end count (item, 64-step block) pairs
+        t.KBc = t.KB = t.k_end - t.k_begin;
+        return t;
+    }
     t.KBc = (t.k_end - t.k_begin + GEMM_BK - 1) / GEMM_BK;
     t.KB = ((p.a_mode == A_KMAJOR) ? p.ntaps : 1) * t.KBc;
     return t;
@@ -182,16 +212,20 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
     if (p.dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_start));
     const uint32_t crank = cluster_ctarank();          // 0 = leader (issues the MMAs), 1 = partner
     const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-    const int MP = ((p.M + GEMM_BM - 1) / GEMM_BM + 1) / 2;
+    const int MP = p.a_tma ? (p.items * ((p.A.L + GEMM_BM - 1) / GEMM_BM) + 1) / 2 : ((p.M + GEMM_BM - 1) / GEMM_BM + 1) / 2;
     const int nblocks = (p.N + GEMM_BN - 1) / GEMM_BN;
     const int total = MP * nblocks * p.ytaps * p.zdim;
     const bool packed = p.b_mode == B_PACKED;
     const bool a_k = p.a_mode == A_KMAJOR;
 
     if (tid == 0) {
-        for (int i = 0; i < NA_SLOTS; ++i) { mbar_init(BAR(BAR_FULL_A + i), 2 * NPW); mbar_init(BAR(BAR_EMPTY_A + i), 1); }
+        for (int i = 0; i < NA_SLOTS; ++i) {
+            mbar_init(BAR(BAR_FULL_A + i), (p.a_tma || p.r_tma) ? 2 : 2 * NPW);      // TMA: leader's expect_tx arrive + partner's relay
+            mbar_init(BAR(BAR_EMPTY_A + i), 1);
+            mbar_init(BAR(BAR_LAND_A + i), 1);
+        }
         for (int i = 0; i < NB_SLOTS; ++i) {
-            mbar_init(BAR(BAR_FULL_B + i), packed ? 2 : 2 * NPW);     // packed: leader's expect_tx arrive + partner's relay
+            mbar_init(BAR(BAR_FULL_B + i), (packed || p.r_tma) ? 2 : 2 * NPW);     // packed: leader's expect_tx arrive + partner's relay
             mbar_init(BAR(BAR_EMPTY_B + i), 1);
             mbar_init(BAR(BAR_LAND_B + i), 1);
         }
@@ -230,6 +264,7 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
         for (int u = pair; u < total; u += npairs) {
             const Unit t = decode_unit(p, u, MP, nblocks, crank);
             if (t.KB <= 0) continue;
+            if ((p.a_tma && packed) || p.r_tma) continue;      // both operands arrive through the copy engines
             const int ntl = a_k ? p.ntaps : 1;
 
             // ---- A load stream (runs one k-block ahead of the store stream)
@@ -266,7 +301,7 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
             };
             if (a_k) a_set_tap(0);
             auto load_a = [&](float (&v)[NCH][8]) {              // next k-block of the stream: global -> registers
-                if (p.dbg_flags & 1) return;
+                if ((p.dbg_flags & 1) || p.a_tma) return;
                 if (a_k) {
                     const int kk = t.k_begin + la_cb * GEMM_BK;
                     const int c = kk + (tid & 7) * 8;
@@ -309,7 +344,7 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
             };
             // one k-block: (convert +) store the A tile held in registers, then B for activation x activation products
             auto emit = [&](int kb, float (&v)[NCH][8]) {
-                {
+                if (!p.a_tma) {
                     mbar_wait(BAR(BAR_EMPTY_A + a_slot), a_par);
                     uint8_t* hi = sA + a_slot * A_SLOT;
                     if (!(p.dbg_flags & 1)) {
@@ -358,7 +393,7 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
             float* Cb = p.C + t.c_z + (long long)t.ytap * p.c_tap_stride;
             const float* addb = p.addend ? p.addend + t.c_z + (long long)t.ytap * p.c_tap_stride : nullptr;
             const int grow0 = t.m0 + q * 32;
-            const int nrows = min(32, p.M - grow0);            // <= 0 for padding rows
+            const int nrows = min(32, t.rows - q * 32);        // <= 0 for padding rows
             const long long crow0 = (long long)grow0 * p.c_mul + p.c_off;
             const long long dstep = (long long)p.c_mul * p.ldc, astep = (long long)p.c_mul * p.ld_add;
             float* stage = sStage + q * (32 * 33);             // transposition buffer: coalesced 128-byte row segments
@@ -384,9 +419,16 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
                     if (p.atomic) {
                         for (int rr = 0; rr < nrows; ++rr, dst += dstep) atomicAdd(dst, stage[rr * 33 + lane] * p.alpha + bv);
                     } else if (addb) {
+                        // 16 independent addend loads in flight per lane: the loop is bound by their latency otherwise
                         const float* add = addb + crow0 * p.ld_add + gcol;
-#pragma unroll 4
-                        for (int rr = 0; rr < nrows; ++rr, dst += dstep, add += astep) *dst = stage[rr * 33 + lane] * p.alpha + bv + __ldg(add);
+                        for (int r0 = 0; r0 < nrows; r0 += 16) {
+                            float av[16];
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) av[e] = (r0 + e < nrows) ? __ldg(add + (long long)(r0 + e) * astep) : 0.f;
+#pragma unroll
+                            for (int e = 0; e < 16; ++e)
+                                if (r0 + e < nrows) dst[(long long)(r0 + e) * dstep] = stage[(r0 + e) * 33 + lane] * p.alpha + bv + av[e];
+                        }
                     } else {
 #pragma unroll 8
                         for (int rr = 0; rr < nrows; ++rr, dst += dstep) *dst = stage[rr * 33 + lane] * p.alpha + bv;
@@ -454,12 +496,56 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
         __syncwarp();
       } else if (warp == NPW + 5) {
         // ================================================================ packed-weight loader (bulk copy engine)
-        if (lane == 0 && packed) {
-            int slot = 0, par = 1;
+        if (lane == 0 && (packed || p.a_tma || p.r_tma)) {
+            int slot = 0, par = 1, as = 0, a_par = 1;
+            if (p.a_tma || p.r_tma) { tma_prefetch_desc(&p.tmA_hi); tma_prefetch_desc(&p.tmA_lo); }
+            if (p.r_tma) { tma_prefetch_desc(&p.tmB_hi); tma_prefetch_desc(&p.tmB_lo); }
+            const int KBI = (p.A.L + GEMM_BK - 1) / GEMM_BK;       // 64-step blocks per batch item (r_tma)
             for (int u = pair; u < total; u += npairs) {
                 const Unit t = decode_unit(p, u, MP, nblocks, crank);
+                if (p.r_tma) {
+                    for (int kb = 0; kb < t.KB; ++kb) {
+                        const int g = t.k_begin + kb, item = g / KBI, tb = (g - item * KBI) * GEMM_BK;
+                        {   // A: x^T tile = 64 steps x 128 channels [m0, m0+128) as two 64-channel boxes per plane
+                            mbar_wait(BAR(BAR_EMPTY_A + as), a_par);
+                            const uint32_t bar = BAR((crank == 0 ? BAR_FULL_A : BAR_LAND_A) + as);
+                            const uint32_t dst = smem_u32(sA + as * A_SLOT);
+                            mbar_arrive_expect_tx(bar, A_SLOT);
+                            const int ta = tb + p.A.off[t.ytap];
+                            tma_load_3d(dst, &p.tmA_hi, t.m0, ta, item, bar);
+                            tma_load_3d(dst + 8192, &p.tmA_hi, t.m0 + 64, ta, item, bar);
+                            tma_load_3d(dst + A_PLANE, &p.tmA_lo, t.m0, ta, item, bar);
+                            tma_load_3d(dst + A_PLANE + 8192, &p.tmA_lo, t.m0 + 64, ta, item, bar);
+                            if (++as == NA_SLOTS) { as = 0; a_par ^= 1; }
+                        }
+                        {   // B: this CTA's 128 of the 256 output columns
+                            mbar_wait(BAR(BAR_EMPTY_B + slot), par);
+                            const uint32_t bar = BAR((crank == 0 ? BAR_FULL_B : BAR_LAND_B) + slot);
+                            const uint32_t dst = smem_u32(sB + slot * B_SLOT);
+                            mbar_arrive_expect_tx(bar, B_SLOT);
+                            const int tbb = tb + p.Bm.off[t.ytap], n = t.n0 + (int)crank * GEMM_BNC;
+                            tma_load_3d(dst, &p.tmB_hi, n, tbb, item, bar);
+                            tma_load_3d(dst + 8192, &p.tmB_hi, n + 64, tbb, item, bar);
+                            tma_load_3d(dst + B_PLANE, &p.tmB_lo, n, tbb, item, bar);
+                            tma_load_3d(dst + B_PLANE + 8192, &p.tmB_lo, n + 64, tbb, item, bar);
+                            if (++slot == NB_SLOTS) { slot = 0; par ^= 1; }
+                        }
+                    }
+                    continue;
+                }
                 const uint8_t* src = reinterpret_cast<const uint8_t*>(p.Bpacked) + (size_t)t.nb * t.KB * B_STAGE + crank * B_SLOT;
                 for (int kb = 0; kb < t.KB; ++kb) {
+                    if (p.a_tma) {                             // A tile: two boxes (hi / lo plane) of 64 channels x 128 steps
+                        const int tap = kb / t.KBc, cb = kb - tap * t.KBc;
+                        mbar_wait(BAR(BAR_EMPTY_A + as), a_par);
+                        const uint32_t bar = BAR((crank == 0 ? BAR_FULL_A : BAR_LAND_A) + as);
+                        const uint32_t dst = smem_u32(sA + as * A_SLOT);
+                        mbar_arrive_expect_tx(bar, A_SLOT);
+                        tma_load_3d(dst, &p.tmA_hi, t.k_begin + cb * GEMM_BK, t.t0 + p.A.off[tap], t.item, bar);
+                        tma_load_3d(dst + A_PLANE, &p.tmA_lo, t.k_begin + cb * GEMM_BK, t.t0 + p.A.off[tap], t.item, bar);
+                        if (++as == NA_SLOTS) { as = 0; a_par ^= 1; }
+                    }
+                    if (!packed) continue;
                     mbar_wait(BAR(BAR_EMPTY_B + slot), par);
                     const uint32_t bar = BAR((crank == 0 ? BAR_FULL_B : BAR_LAND_B) + slot);
                     if (p.dbg_flags & 2) { mbar_arrive(bar); }
@@ -474,14 +560,21 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
         __syncwarp();
       } else if (warp == NPW + 6) {
         // ================================================================ partner: tell the leader a B stage has landed
-        if (lane == 0 && packed && crank == 1) {
-            int slot = 0, par = 0;
+        if (lane == 0 && (packed || p.a_tma || p.r_tma) && crank == 1) {
+            int slot = 0, par = 0, as = 0, a_par = 0;
             for (int u = pair; u < total; u += npairs) {
                 const Unit t = decode_unit(p, u, MP, nblocks, crank);
                 for (int kb = 0; kb < t.KB; ++kb) {
-                    mbar_wait(BAR(BAR_LAND_B + slot), par);
-                    mbar_arrive_remote(BAR(BAR_FULL_B + slot), 0);
-                    if (++slot == NB_SLOTS) { slot = 0; par ^= 1; }
+                    if (p.a_tma || p.r_tma) {
+                        mbar_wait(BAR(BAR_LAND_A + as), a_par);
+                        mbar_arrive_remote(BAR(BAR_FULL_A + as), 0);
+                        if (++as == NA_SLOTS) { as = 0; a_par ^= 1; }
+                    }
+                    if (packed || p.r_tma) {
+                        mbar_wait(BAR(BAR_LAND_B + slot), par);
+                        mbar_arrive_remote(BAR(BAR_FULL_B + slot), 0);
+                        if (++slot == NB_SLOTS) { slot = 0; par ^= 1; }
+                    }
                 }
             }
         }

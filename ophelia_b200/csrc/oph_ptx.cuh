@@ -62,6 +62,17 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
         ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
+// TMA tensor copy: one [box] of a 3-D tensor map (channels, time, batch item) -> shared memory (SWIZZLE_128B applied by
+// the map); out-of-range coordinates (conv padding, tile tails) are filled with zeros and still count as full bytes.
+__device__ __forceinline__ void tma_load_3d(uint32_t dst_smem, const void* tmap, int c0, int c1, int c2, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(dst_smem), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+
 // multicast variant: the bytes land at the same CTA-relative offset in every CTA of `mask`, and complete_tx is
 // signalled on the mbarrier at the same offset in each of them
 __device__ __forceinline__ void bulk_g2s_mcast(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
