@@ -182,7 +182,7 @@ def run_ours(args):
 
     for _ in range(max(args.warmup, 3)):
         g.train_step_device(*dev_in)
-    for _ in range(2):
+    for _ in range(5):      # eager twice, then the step is captured into a CUDA graph and replayed
         sess.run([g.global_step, g.loss_components, g.train_op])
     clocks = ClockSampler(local)
     if rank == 0:

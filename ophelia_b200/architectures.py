@@ -216,6 +216,32 @@ class Graph(object):
             return steps[key](*dev_inputs)
         return self.train_step_device(*dev_inputs)
 
+    # ---- input prefetch: the host->device copy of batch i+1 rides a copy stream while step i computes (the role of the
+    #      reference's queue runners, data_load.py:534-541); every step still performs exactly one H2D of its inputs
+    def _prefetch(self, fields):
+        batch = next(self.batch_source)
+        main = torch.cuda.current_stream(self.device)
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        with torch.cuda.stream(self._copy_stream):
+            dev = tuple(self._to_device(batch[k], dt) for k, dt in fields)
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        for t in dev:
+            t.record_stream(main)
+        self._prefetched = (dev, ev)
+
+    def _next_inputs(self, fields):
+        if getattr(self, "_prefetched", None) is None:
+            self._prefetch(fields)
+        dev, ev = self._prefetched
+        torch.cuda.current_stream(self.device).wait_event(ev)
+        try:
+            self._prefetch(fields)
+        except StopIteration:
+            self._prefetched = None
+        return dev
+
     def _to_device(self, x, dtype):
         if isinstance(x, torch.Tensor):
             return x.to(self.device, dtype, non_blocking=True)
@@ -243,11 +269,11 @@ class SSRNGraph(Graph):
         return {"mels": mels, "Z_logits": logits, "Z": Z}
 
     def train_step(self, batch=None):
-        hp, st = self.hp, self.store
         if batch is None:
-            batch = next(self.batch_source)
-        mels = self._to_device(batch["mel"], torch.float32)
-        mags = self._to_device(batch["mag"], torch.float32)
+            mels, mags = self._next_inputs((("mel", torch.float32), ("mag", torch.float32)))
+        else:
+            mels = self._to_device(batch["mel"], torch.float32)
+            mags = self._to_device(batch["mag"], torch.float32)
         return self._step_maybe_graphed(mels, mags)
 
     def train_step_device(self, mels, mags):
@@ -330,9 +356,10 @@ class Text2MelGraph(Graph):
 
     def train_step(self, batch=None):
         if batch is None:
-            batch = next(self.batch_source)
-        L = self._to_device(batch["text"], torch.int32)
-        mels = self._to_device(batch["mel"], torch.float32)
+            L, mels = self._next_inputs((("text", torch.int32), ("mel", torch.float32)))
+        else:
+            L = self._to_device(batch["text"], torch.int32)
+            mels = self._to_device(batch["mel"], torch.float32)
         return self._step_maybe_graphed(L, mels)
 
     def train_step_device(self, L, mels):

@@ -73,7 +73,20 @@ bool make_plane_tmap(CUtensorMap* out, const unsigned short* base, int C, int L,
               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
+// bf16 plane [rows][ld] viewed as (channels, rows); box = 64 channels x 128 rows, SWIZZLE_128B, zero fill
+bool make_plane_tmap2d(CUtensorMap* out, const unsigned short* base, int C, long long rows, long long ld) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn || (reinterpret_cast<uintptr_t>(base) & 15) || (ld & 7)) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    const cuuint32_t box[2] = {64, (cuuint32_t)GEMM_BM};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<unsigned short*>(base), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 bool g_use_tma = true;
+bool g_use_split = true;
 
 int launch_gemm(GemmArgs& a, int zdim, cudaStream_t st) {
     static bool attr_done = false;
@@ -94,18 +107,31 @@ int launch_gemm(GemmArgs& a, int zdim, cudaStream_t st) {
     a.a_tma = 0; if (!a.r_tma) a.items = 1;
     if (g_use_tma && a.a_mode == A_KMAJOR && a.A.hi && a.A.mul == 1 && a.A.L == a.A.Ls && a.z_mode == Z_NONE &&
         !(a.Kc & 63) && a.M % a.A.L == 0) {
-        const int items = a.M / a.A.L;
-        if (make_plane_tmap(&a.tmA_hi, a.A.hi, a.Kc, a.A.L, items, a.A.ld, GEMM_BM) &&
-            make_plane_tmap(&a.tmA_lo, a.A.lo, a.Kc, a.A.L, items, a.A.ld, GEMM_BM)) {
-            a.a_tma = 1; a.items = items;
+        if (make_plane_tmap2d(&a.tmA_hi, a.A.hi, a.Kc, a.M, a.A.ld) && make_plane_tmap2d(&a.tmA_lo, a.A.lo, a.Kc, a.M, a.A.ld)) {
+            a.a_tma = 1; a.items = a.M / a.A.L;
         }
     }
     a.dbg = g_gemm_dbg;
     a.dbg_flags = g_gemm_dbg_flags;
     // persistent CTA pairs: work units = (pair of 128-row tiles) x (256-column block) x tap x z slice
-    const int mtiles = a.a_tma ? a.items * cdiv(a.A.L, GEMM_BM) : cdiv(a.M, GEMM_BM);
-    const long long units = (long long)cdiv(mtiles, 2) * cdiv(a.N, GEMM_BN) * a.ytaps * a.zdim;
-    const int pairs = (int)(units < GEMM_MAX_PAIRS ? units : GEMM_MAX_PAIRS);
+    const long long units = (long long)cdiv(cdiv(a.M, GEMM_BM), 2) * cdiv(a.N, GEMM_BN) * a.ytaps * a.zdim;
+    // RED outputs fed by the copy engines: split the units of the last (partial) round into k-block slices so that it
+    // costs a fraction of a round; s minimises rounds x (slice length + 1 k-block of per-item overhead)
+    long long items = units;
+    a.split_from = (int)units; a.split_s = 1;
+    if (g_use_split && a.a_tma && a.b_mode == B_PACKED && a.atomic && !a.bias && a.z_mode == Z_NONE && a.ytaps == 1) {
+        const int P = GEMM_MAX_PAIRS, KB = a.ntaps * cdiv(a.Kc, GEMM_BK);
+        const int rem = (int)(units % P);
+        if (rem > 0) {
+            int best_s = 1; long long best = (long long)KB + 1;
+            for (int sl = 2; sl <= KB / 4; ++sl) {
+                const long long cost = (long long)cdiv(rem * sl, P) * (cdiv(KB, sl) + 1);
+                if (cost < best) { best = cost; best_s = sl; }
+            }
+            if (best_s > 1) { a.split_from = (int)(units - rem); a.split_s = best_s; items = a.split_from + (long long)rem * best_s; }
+        }
+    }
+    const int pairs = (int)(items < GEMM_MAX_PAIRS ? items : GEMM_MAX_PAIRS);
     dim3 grid(2 * pairs);
     ProfRec rec{};
     bool prof = false;
@@ -295,7 +321,7 @@ int oph_version(void) { return 100; }
 const char* oph_last_error(void) { return g_err; }
 long long oph_launch_count(void) { return g_launches.load(); }
 int oph_gemm_debug_buffer(long long* dev_buf) { g_gemm_dbg = dev_buf; return OPH_OK; }
-int oph_gemm_debug_flags(int flags) { g_gemm_dbg_flags = flags & 7; g_use_tma = !(flags & 8); return OPH_OK; }
+int oph_gemm_debug_flags(int flags) { g_gemm_dbg_flags = flags & 7; g_use_tma = !(flags & 8); g_use_split = !(flags & 16); return OPH_OK; }
 
 int oph_profile_begin(void) {
     std::lock_guard<std::mutex> lk(g_prof_mu);
@@ -448,12 +474,16 @@ int oph_hc_bwd(const float* dy, long long lddy, const oph_act* x, const float* z
     const size_t smem = 6 * (size_t)C * sizeof(float);
     OperandMap dzm; dzm.ptr = dz; dzm.ld = lddz; dzm.hi = dzm.lo = nullptr;
     (void)dxres; (void)ldxr;
-    if (vec_ok(C, lddy, ldz, x->ld, lddz, lddx) && C <= 512 && lddz >= 2 * C) {
-        const int grid = bwd_grid(rows);
+    if (norm && vec_ok(C, lddy, ldz, x->ld, lddz, lddx) && lddz >= 2 * C) {
         dz_as_planes(dz, rows, 2 * C, &dzm);
         unsigned short* h = const_cast<unsigned short*>(dzm.hi); unsigned short* l = const_cast<unsigned short*>(dzm.lo);
-        if (C == 256) hc_post_bwd_vec_kernel<2><<<grid, 256, smem, S(stream)>>>(dy, lddy, z, ldz, x->f32, x->ld, stats, g1, b1, g2, b2, nullptr, 0, h, l, 2 * C, dx, lddx, dg1, db1, dg2, db2, dbias, (int)rows, norm, drop_p, seed, step);
-        else          hc_post_bwd_vec_kernel<4><<<grid, 256, smem, S(stream)>>>(dy, lddy, z, ldz, x->f32, x->ld, stats, g1, b1, g2, b2, nullptr, 0, h, l, 2 * C, dx, lddx, dg1, db1, dg2, db2, dbias, (int)rows, norm, drop_p, seed, step);
+        const int wpr = C / 256, groups = 8 / wpr;
+        long long gl = (rows + groups * 4 - 1) / (groups * 4);             // >= 4 rows per row group
+        const int grid = (int)(gl < 1 ? 1 : (gl > 148 ? 148 : gl));
+        const size_t sm2 = (10 * (size_t)C + 64) * sizeof(float);
+#define OPH_LAUNCH(W) hc_post_bwd_wide_kernel<W><<<grid, 256, sm2, S(stream)>>>(dy, lddy, z, ldz, x->f32, x->ld, stats, g1, b1, g2, b2, h, l, 2 * C, dx, lddx, dg1, db1, dg2, db2, dbias, (int)rows, drop_p, seed, step)
+        if (C == 256) OPH_LAUNCH(1); else if (C == 512) OPH_LAUNCH(2); else OPH_LAUNCH(4);
+#undef OPH_LAUNCH
     } else {
         hc_post_bwd_kernel<<<rows_grid(rows, 8), 256, smem, S(stream)>>>(
             dy, lddy, z, ldz, x->f32, x->ld, stats, g1, b1, g2, b2, dz, lddz, dx, lddx, dg1, db1, dg2, db2, dbias,

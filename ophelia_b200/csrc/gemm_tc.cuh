@@ -53,13 +53,18 @@ struct GemmArgs {
     long long* dbg;        // optional [pairs][8] cycle counters of the MMA / producer waits (diagnostics)
     int prof_k;            // host-side: true reduction length for the FLOP count when Kc is in k-blocks (r_tma)
     int dbg_flags;         // diagnostics only: 1 = producers skip data movement, 2 = weight loader skips copies
-    // TMA feed of a pre-split conv-style A operand: tiles are cut per batch item (rows [t0, t0+128) of item b) so that
-    // conv padding and tile tails are out-of-range coordinates of the (channels, time, item) tensor maps.
+    // TMA feed of a pre-split conv-style A operand: FLAT 128-row tiles over the (channels, items*time) tensor map (the
+    // fewest tiles, no per-item tail tiles).  A tap shifts the row coordinate; rows shifted beyond either end of the
+    // whole tensor are out-of-range zeros, rows shifted across an item boundary are zeroed in shared memory by the
+    // fix-up warp before the MMA sees the stage.
     // Weight-gradient products with both operands pre-split (r_tma): the reduction runs over (item, 64-step block) pairs
     // so that tap shifts and item boundaries are out-of-range coordinates too; k_chunk then counts k-blocks.
     int a_tma;             // 1: conv-style A tiles come from tmA_hi / tmA_lo, the producer warps do not touch A
     int r_tma;             // 1: MN-major A and B tiles (64 steps x 128 channels each) come from tmA_* / tmB_*
     int items;             // number of batch items (M = items * A.L)
+    // remainder K-split (RED outputs only): work items >= split_from are split_s k-block slices of the remaining units,
+    // so that the last round of the persistent CTA pairs is short instead of mostly idle
+    int split_from, split_s;
     alignas(64) CUtensorMap tmA_hi;
     alignas(64) CUtensorMap tmA_lo;
     alignas(64) CUtensorMap tmB_hi;
@@ -80,7 +85,8 @@ constexpr int NB_SLOTS = 3;
 constexpr int N_ACC = 2;                            // accumulator stages in tensor memory (2 x 256 columns)
 constexpr int NPW = 16;                             // producer warps
 constexpr int GEMM_THREADS = (NPW + 8) * 32;        // producers, then 4 epilogue warps, then MMA / bulk copy / relay / idle
-constexpr int EPI_STAGE_BYTES = 4 * 32 * 33 * 4;    // per-warp transposition buffers of the 4 epilogue warps
+constexpr int EPI_WARPS = 16;                       // epilogue workers when both operands come from the copy engines
+constexpr int EPI_STAGE_BYTES = EPI_WARPS * 2048;   // per-warp [32 rows][16 columns] fp32 transposition buffers
 constexpr int GEMM_SMEM = NA_SLOTS * A_SLOT + NB_SLOTS * B_SLOT + EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int GEMM_MAX_PAIRS = 74;                  // 148 SMs
 
@@ -159,38 +165,37 @@ constexpr int NUM_BARS = BAR_T_EMPTY + N_ACC;
 
 struct Unit {               // one 256x256 output tile of one tap / z slice
     int m0, n0, nb, ytap, k_begin, k_end, KBc, KB;
+    int kb0, kb1;           // k-block range of this work item (the whole unit unless it is a remainder slice)
     int rows;               // valid rows of this CTA's 128-row tile (<= 0: padding CTA)
-    int item, t0;           // TMA mode: batch item and first time step of the tile
     long long a_z, b_z, c_z;
 };
 
-__device__ __forceinline__ Unit decode_unit(const GemmArgs& p, int u, int MP, int nblocks, uint32_t crank) {
+__device__ __forceinline__ Unit decode_unit(const GemmArgs& p, int v, int MP, int nblocks, uint32_t crank) {
     Unit t;
+    int u = v, slice = 0, nslices = 1;
+    if (p.split_s > 1 && v >= p.split_from) {
+        const int w = v - p.split_from;
+        u = p.split_from + w / p.split_s; slice = w - (w / p.split_s) * p.split_s; nslices = p.split_s;
+    }
     const int mp = u % MP; int rest = u / MP;
     t.nb = rest % nblocks; rest /= nblocks;
     t.ytap = rest % p.ytaps;
     const int z = rest / p.ytaps;
     const int mt = mp * 2 + (int)crank;
-    if (p.a_tma) {                                     // tiles never straddle batch items
-        const int tpi = (p.A.L + GEMM_BM - 1) / GEMM_BM;
-        t.item = mt / tpi; t.t0 = (mt - t.item * tpi) * GEMM_BM;
-        t.m0 = t.item * p.A.L + t.t0;
-        t.rows = t.item < p.items ? min(GEMM_BM, p.A.L - t.t0) : 0;
-    } else {
-        t.item = 0; t.t0 = 0;
-        t.m0 = mt * GEMM_BM;                           // may lie beyond M for the padding CTA of the last pair
-        t.rows = min(GEMM_BM, p.M - t.m0);
-    }
+    t.m0 = mt * GEMM_BM;                               // may lie beyond M for the padding CTA of the last pair
+    t.rows = min(GEMM_BM, p.M - t.m0);
     t.n0 = t.nb * GEMM_BN;
     t.k_begin = 0; t.k_end = p.Kc; t.a_z = t.b_z = t.c_z = 0;
     if (p.z_mode == Z_BATCH) { t.a_z = z * p.a_zs; t.b_z = z * p.b_zs; t.c_z = z * p.c_zs; }
     if (p.z_mode == Z_SPLITK) { t.k_begin = z * p.k_chunk; t.k_end = min(p.Kc, t.k_begin + p.k_chunk); }
     if (p.r_tma) {                                     // k_begin / k_end count (item, 64-step block) pairs
         t.KBc = t.KB = t.k_end - t.k_begin;
-        return t;
+    } else {
+        t.KBc = (t.k_end - t.k_begin + GEMM_BK - 1) / GEMM_BK;
+        t.KB = ((p.a_mode == A_KMAJOR) ? p.ntaps : 1) * t.KBc;
     }
-    t.KBc = (t.k_end - t.k_begin + GEMM_BK - 1) / GEMM_BK;
-    t.KB = ((p.a_mode == A_KMAJOR) ? p.ntaps : 1) * t.KBc;
+    t.kb0 = (int)((long long)slice * t.KB / nslices);
+    t.kb1 = (int)((long long)(slice + 1) * t.KB / nslices);
     return t;
 }
 
@@ -212,11 +217,15 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
     if (p.dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_start));
     const uint32_t crank = cluster_ctarank();          // 0 = leader (issues the MMAs), 1 = partner
     const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-    const int MP = p.a_tma ? (p.items * ((p.A.L + GEMM_BM - 1) / GEMM_BM) + 1) / 2 : ((p.M + GEMM_BM - 1) / GEMM_BM + 1) / 2;
+    const int MP = ((p.M + GEMM_BM - 1) / GEMM_BM + 1) / 2;
     const int nblocks = (p.N + GEMM_BN - 1) / GEMM_BN;
-    const int total = MP * nblocks * p.ytaps * p.zdim;
+    const int units = MP * nblocks * p.ytaps * p.zdim;
+    const int total = p.split_s > 1 ? p.split_from + (units - p.split_from) * p.split_s : units;   // work items
     const bool packed = p.b_mode == B_PACKED;
     const bool a_k = p.a_mode == A_KMAJOR;
+    // both operands arrive through the copy engines: the 16 producer warps have nothing to stage and drain the
+    // accumulators instead (4 x more epilogue warps, the dedicated epilogue warps then idle)
+    const bool copy_fed = (p.a_tma && packed) || p.r_tma;
 
     if (tid == 0) {
         for (int i = 0; i < NA_SLOTS; ++i) {
@@ -229,7 +238,7 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
             mbar_init(BAR(BAR_EMPTY_B + i), 1);
             mbar_init(BAR(BAR_LAND_B + i), 1);
         }
-        for (int i = 0; i < N_ACC; ++i) { mbar_init(BAR(BAR_T_FULL + i), 1); mbar_init(BAR(BAR_T_EMPTY + i), 8); }
+        for (int i = 0; i < N_ACC; ++i) { mbar_init(BAR(BAR_T_FULL + i), 1); mbar_init(BAR(BAR_T_EMPTY + i), copy_fed ? 2 * EPI_WARPS : 8); }
         mbar_fence_init();
         fence_proxy_async();
     }
@@ -239,11 +248,88 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+
+    // ================================================================ epilogue worker: TMEM -> global
+    // One warp drains the 32 accumulator rows of its TMEM lane quadrant q for the 16-column blocks cg, cg + ncg, ...
+    // Each block goes through a swizzled [32][16] shared-memory buffer so that a lane ends up with 4 consecutive
+    // columns of one row: every global access is a 16-byte vector and a warp instruction covers 8 rows x 64 bytes.
+    auto epilogue = [&](const int q, const int cg, const int ncg, float* stage) {
+        const int cb_last = cg + ncg * ((GEMM_BN / 16 - 1 - cg) / ncg);
+        const int rsub = lane >> 2, c4 = lane & 3;             // this lane's row within a group of 8 / float4 within the 16 columns
+        const bool vec_ok = !(p.ldc & 3) && !(reinterpret_cast<uintptr_t>(p.C) & 15) && !(p.c_zs & 3) && !(p.c_tap_stride & 3) &&
+                            (!p.addend || (!(p.ld_add & 3) && !(reinterpret_cast<uintptr_t>(p.addend) & 15)));
+        int acc = 0, acc_par = 0;
+        for (int u = pair; u < total; u += npairs) {
+            const Unit t = decode_unit(p, u, MP, nblocks, crank);
+            if (t.KB <= 0) continue;
+            mbar_wait(BAR(BAR_T_FULL + acc), acc_par);
+            tc_fence_after();
+            float* Cb = p.C + t.c_z + (long long)t.ytap * p.c_tap_stride;
+            const float* addb = p.addend ? p.addend + t.c_z + (long long)t.ytap * p.c_tap_stride : nullptr;
+            const int grow0 = t.m0 + q * 32;
+            const int nrows = min(32, t.rows - q * 32);        // <= 0 for padding rows
+            const long long crow0 = (long long)grow0 * p.c_mul + p.c_off;
+#pragma unroll 1
+            for (int cb = cg; cb < GEMM_BN / 16; cb += ncg) {
+                const int col0 = cb * 16;
+                uint32_t r[16];
+                tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + acc * GEMM_BN + col0, r);
+                tmem_ld_wait();
+                if (cb == cb_last) {                           // accumulator stage fully read by this warp: hand it back
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) { if (crank == 0) mbar_arrive(BAR(BAR_T_EMPTY + acc)); else mbar_arrive_remote(BAR(BAR_T_EMPTY + acc), 0); }
+                }
+                if (nrows <= 0 || t.n0 + col0 >= p.N) continue;   // warp-uniform
+                // lane = row: float4 j of the row goes to slot j ^ ((row >> 1) & 3) (conflict-free both ways)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    *reinterpret_cast<uint4*>(stage + lane * 16 + ((j ^ ((lane >> 1) & 3)) << 2)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+                __syncwarp();
+                const int gcol = t.n0 + col0 + c4 * 4;
+                float bv[4] = {0.f, 0.f, 0.f, 0.f};
+                if (p.bias) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) if (gcol + e < p.N) bv[e] = __ldg(p.bias + gcol + e);
+                }
+                const bool full = vec_ok && gcol + 4 <= p.N;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int rr = rsub + 8 * i;
+                    if (rr >= nrows || gcol >= p.N) continue;
+                    const float4 v = *reinterpret_cast<const float4*>(stage + rr * 16 + ((c4 ^ ((rr >> 1) & 3)) << 2));
+                    float o[4] = {v.x * p.alpha + bv[0], v.y * p.alpha + bv[1], v.z * p.alpha + bv[2], v.w * p.alpha + bv[3]};
+                    float* dst = Cb + (crow0 + (long long)rr * p.c_mul) * p.ldc + gcol;
+                    if (full) {
+                        if (p.atomic) red_add_v4(dst, o[0], o[1], o[2], o[3]);
+                        else {
+                            if (addb) {
+                                const float4 a = __ldg(reinterpret_cast<const float4*>(addb + (crow0 + (long long)rr * p.c_mul) * p.ld_add + gcol));
+                                o[0] += a.x; o[1] += a.y; o[2] += a.z; o[3] += a.w;
+                            }
+                            *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            if (gcol + e >= p.N) break;
+                            if (p.atomic) atomicAdd(dst + e, o[e]);
+                            else dst[e] = o[e] + (addb ? __ldg(addb + (crow0 + (long long)rr * p.c_mul) * p.ld_add + gcol + e) : 0.f);
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            if (++acc == N_ACC) { acc = 0; acc_par ^= 1; }
+        }
+    };
+
     // Register budget per role (768 threads launch at 80 regs): producer warpgroups grow to 88, the epilogue
     // warpgroup shrinks to 72 and the MMA / copy warpgroup to 40 (512*88 + 128*72 + 128*40 <= 768*80: setmaxnreg can
     // only hand out what the CTA got at launch).
     if (warp < NPW) {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
+        if (copy_fed) epilogue(warp & 3, warp >> 2, EPI_WARPS / 4, sStage + warp * 512);
         // ================================================================ producers (both CTAs)
         // Each thread owns NCH chunks (8 consecutive elements) of every operand tile.  Global loads run one k-block
         // ahead of the shared-memory stores (register double buffer); address arithmetic is hoisted out of the chunk
@@ -261,10 +347,9 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
         }
         const bool a_split = p.A.hi != nullptr, b_split = p.Bm.hi != nullptr;
         int a_slot = 0, a_par = 1, b_slot = 0, b_par = 1;      // ring cursors: parity to wait for on the EMPTY barriers
-        for (int u = pair; u < total; u += npairs) {
+        for (int u = copy_fed ? total : pair; u < total; u += npairs) {
             const Unit t = decode_unit(p, u, MP, nblocks, crank);
             if (t.KB <= 0) continue;
-            if ((p.a_tma && packed) || p.r_tma) continue;      // both operands arrive through the copy engines
             const int ntl = a_k ? p.ntaps : 1;
 
             // ---- A load stream (runs one k-block ahead of the store stream)
@@ -382,62 +467,7 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
         }
     } else if (warp < NPW + 4) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
-        // ================================================================ epilogue warps (both CTAs): TMEM -> global
-        const int q = warp & 3;                                // TMEM lane quadrant this warp may access
-        int acc = 0, acc_par = 0;
-        for (int u = pair; u < total; u += npairs) {
-            const Unit t = decode_unit(p, u, MP, nblocks, crank);
-            if (t.KB <= 0) continue;
-            mbar_wait(BAR(BAR_T_FULL + acc), acc_par);
-            tc_fence_after();
-            float* Cb = p.C + t.c_z + (long long)t.ytap * p.c_tap_stride;
-            const float* addb = p.addend ? p.addend + t.c_z + (long long)t.ytap * p.c_tap_stride : nullptr;
-            const int grow0 = t.m0 + q * 32;
-            const int nrows = min(32, t.rows - q * 32);        // <= 0 for padding rows
-            const long long crow0 = (long long)grow0 * p.c_mul + p.c_off;
-            const long long dstep = (long long)p.c_mul * p.ldc, astep = (long long)p.c_mul * p.ld_add;
-            float* stage = sStage + q * (32 * 33);             // transposition buffer: coalesced 128-byte row segments
-#pragma unroll 1
-            for (int ch = 0; ch < GEMM_BN / 32; ++ch) {
-                const int col0 = ch * 32;
-                uint32_t r[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * GEMM_BN + col0, r);
-                tmem_ld_wait();
-                if (ch == GEMM_BN / 32 - 1) {                  // accumulator stage fully read: hand it back to the MMA thread
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) { if (crank == 0) mbar_arrive(BAR(BAR_T_EMPTY + acc)); else mbar_arrive_remote(BAR(BAR_T_EMPTY + acc), 0); }
-                }
-                if (nrows <= 0 || t.n0 + col0 >= p.N) continue;   // warp-uniform
-#pragma unroll
-                for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = __uint_as_float(r[j]);
-                __syncwarp();
-                const int gcol = t.n0 + col0 + lane;
-                if (gcol < p.N) {
-                    const float bv = p.bias ? __ldg(p.bias + gcol) : 0.f;
-                    float* dst = Cb + crow0 * p.ldc + gcol;
-                    if (p.atomic) {
-                        for (int rr = 0; rr < nrows; ++rr, dst += dstep) atomicAdd(dst, stage[rr * 33 + lane] * p.alpha + bv);
-                    } else if (addb) {
-                        // 16 independent addend loads in flight per lane: the loop is bound by their latency otherwise
-                        const float* add = addb + crow0 * p.ld_add + gcol;
-                        for (int r0 = 0; r0 < nrows; r0 += 16) {
-                            float av[16];
-#pragma unroll
-                            for (int e = 0; e < 16; ++e) av[e] = (r0 + e < nrows) ? __ldg(add + (long long)(r0 + e) * astep) : 0.f;
-#pragma unroll
-                            for (int e = 0; e < 16; ++e)
-                                if (r0 + e < nrows) dst[(long long)(r0 + e) * dstep] = stage[(r0 + e) * 33 + lane] * p.alpha + bv + av[e];
-                        }
-                    } else {
-#pragma unroll 8
-                        for (int rr = 0; rr < nrows; ++rr, dst += dstep) *dst = stage[rr * 33 + lane] * p.alpha + bv;
-                    }
-                }
-                __syncwarp();
-            }
-            if (++acc == N_ACC) { acc = 0; acc_par ^= 1; }
-        }
+        if (!copy_fed) epilogue(warp & 3, 0, 1, sStage + (warp & 3) * 512);
     } else {
       asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
       if (warp == NPW + 4) {
@@ -459,7 +489,7 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
                 w_t += clock64() - c0;
                 tc_fence_after();
                 const uint32_t d = tmem_base + acc * GEMM_BN;
-                for (int kb = 0; kb < t.KB; ++kb) {
+                for (int kb = t.kb0; kb < t.kb1; ++kb) {
                     c0 = clock64();
                     mbar_wait(BAR(BAR_FULL_A + as), a_par);
                     const long long c1 = clock64();
@@ -474,7 +504,7 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
                         const uint64_t dal = make_sdesc(a_lo + ks * a_step, a_lbo, 1024);
                         const uint64_t dbh = make_sdesc(b_hi + ks * b_step, b_lbo, 1024);
                         const uint64_t dbl = make_sdesc(b_lo + ks * b_step, b_lbo, 1024);
-                        umma2_bf16(d, dah, dbh, idesc, (kb | ks) != 0);
+                        umma2_bf16(d, dah, dbh, idesc, ((kb - t.kb0) | ks) != 0);
                         umma2_bf16(d, dah, dbl, idesc, 1);
                         umma2_bf16(d, dal, dbh, idesc, 1);
                     }
@@ -534,15 +564,15 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
                     continue;
                 }
                 const uint8_t* src = reinterpret_cast<const uint8_t*>(p.Bpacked) + (size_t)t.nb * t.KB * B_STAGE + crank * B_SLOT;
-                for (int kb = 0; kb < t.KB; ++kb) {
-                    if (p.a_tma) {                             // A tile: two boxes (hi / lo plane) of 64 channels x 128 steps
+                for (int kb = t.kb0; kb < t.kb1; ++kb) {
+                    if (p.a_tma) {                             // A tile: two boxes (hi / lo plane) of 64 channels x 128 rows
                         const int tap = kb / t.KBc, cb = kb - tap * t.KBc;
                         mbar_wait(BAR(BAR_EMPTY_A + as), a_par);
-                        const uint32_t bar = BAR((crank == 0 ? BAR_FULL_A : BAR_LAND_A) + as);
+                        const uint32_t bar = BAR(BAR_LAND_A + as);         // the fix-up warp forwards it to the leader's FULL_A
                         const uint32_t dst = smem_u32(sA + as * A_SLOT);
                         mbar_arrive_expect_tx(bar, A_SLOT);
-                        tma_load_3d(dst, &p.tmA_hi, t.k_begin + cb * GEMM_BK, t.t0 + p.A.off[tap], t.item, bar);
-                        tma_load_3d(dst + A_PLANE, &p.tmA_lo, t.k_begin + cb * GEMM_BK, t.t0 + p.A.off[tap], t.item, bar);
+                        tma_load_2d(dst, &p.tmA_hi, t.k_begin + cb * GEMM_BK, t.m0 + p.A.off[tap], bar);
+                        tma_load_2d(dst + A_PLANE, &p.tmA_lo, t.k_begin + cb * GEMM_BK, t.m0 + p.A.off[tap], bar);
                         if (++as == NA_SLOTS) { as = 0; a_par ^= 1; }
                     }
                     if (!packed) continue;
@@ -559,20 +589,44 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
         }
         __syncwarp();
       } else if (warp == NPW + 6) {
-        // ================================================================ partner: tell the leader a B stage has landed
-        if (lane == 0 && (packed || p.a_tma || p.r_tma) && crank == 1) {
+        // ================================================================ landing relay + item-boundary fix-up (whole warp)
+        // Copies that land in this CTA are announced to the leader's FULL barriers from here.  For the flat conv-style
+        // A tiles, rows whose tap-shifted source step falls outside their own batch item were fetched from the
+        // neighbouring item: they are conv padding and are zeroed here first (generic-proxy stores + proxy fence).
+        if ((packed || p.a_tma || p.r_tma) && (crank == 1 || p.a_tma)) {
             int slot = 0, par = 0, as = 0, a_par = 0;
             for (int u = pair; u < total; u += npairs) {
                 const Unit t = decode_unit(p, u, MP, nblocks, crank);
-                for (int kb = 0; kb < t.KB; ++kb) {
-                    if (p.a_tma || p.r_tma) {
+                int tmod[4];                                   // step within the item of this lane's 4 rows
+#pragma unroll
+                for (int j = 0; j < 4; ++j) tmod[j] = (t.m0 + lane + 32 * j) % p.A.L;
+                for (int kb = t.kb0; kb < t.kb1; ++kb) {
+                    if (p.a_tma) {
                         mbar_wait(BAR(BAR_LAND_A + as), a_par);
-                        mbar_arrive_remote(BAR(BAR_FULL_A + as), 0);
+                        const int off = p.A.off[kb / t.KBc];
+                        if (off != 0) {
+                            bool any = false;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const int ts = tmod[j] + off;
+                                if (ts < 0 || ts >= p.A.L) {
+                                    any = true;
+                                    uint4* h = reinterpret_cast<uint4*>(sA + as * A_SLOT + (lane + 32 * j) * 128);
+                                    uint4* l = reinterpret_cast<uint4*>(sA + as * A_SLOT + A_PLANE + (lane + 32 * j) * 128);
+#pragma unroll
+                                    for (int e = 0; e < 8; ++e) { h[e] = make_uint4(0u, 0u, 0u, 0u); l[e] = make_uint4(0u, 0u, 0u, 0u); }
+                                }
+                            }
+                            if (__any_sync(0xffffffffu, any)) { fence_proxy_async(); __syncwarp(); }
+                        }
+                        if (lane == 0) { if (crank == 0) mbar_arrive(BAR(BAR_FULL_A + as)); else mbar_arrive_remote(BAR(BAR_FULL_A + as), 0); }
+                        if (++as == NA_SLOTS) { as = 0; a_par ^= 1; }
+                    } else if (p.r_tma) {
+                        if (lane == 0) { mbar_wait(BAR(BAR_LAND_A + as), a_par); mbar_arrive_remote(BAR(BAR_FULL_A + as), 0); }
                         if (++as == NA_SLOTS) { as = 0; a_par ^= 1; }
                     }
-                    if (packed || p.r_tma) {
-                        mbar_wait(BAR(BAR_LAND_B + slot), par);
-                        mbar_arrive_remote(BAR(BAR_FULL_B + slot), 0);
+                    if ((packed || p.r_tma) && crank == 1) {
+                        if (lane == 0) { mbar_wait(BAR(BAR_LAND_B + slot), par); mbar_arrive_remote(BAR(BAR_FULL_B + slot), 0); }
                         if (++slot == NB_SLOTS) { slot = 0; par ^= 1; }
                     }
                 }

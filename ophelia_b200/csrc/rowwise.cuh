@@ -19,12 +19,12 @@ __device__ __forceinline__ float warp_sum(float v) {
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
 
 // counter-based dropout mask (recomputed in backward): keep iff u >= rate; kept values scaled by 1/(1-rate)
+// (32-bit avalanche hash of (seed, element index): a handful of integer instructions per element)
 __device__ __forceinline__ float drop_scale(unsigned long long seed, unsigned long long idx, float rate, float inv_keep) {
-    unsigned long long z = seed + idx * 0x9E3779B97F4A7C15ull;
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    z ^= z >> 31;
-    const float u = (float)(z >> 40) * (1.0f / 16777216.0f);
+    uint32_t h = (uint32_t)idx * 0x9E3779B1u + (uint32_t)seed;
+    h ^= ((uint32_t)(idx >> 32) * 0x85EBCA77u) ^ (uint32_t)(seed >> 32);
+    h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15; h *= 0x846CA68Bu; h ^= h >> 16;
+    const float u = (float)(h >> 8) * (1.0f / 16777216.0f);
     return u >= rate ? inv_keep : 0.f;
 }
 __device__ __forceinline__ unsigned long long eff_seed(unsigned long long seed, const long long* step) {
@@ -456,6 +456,13 @@ __device__ __forceinline__ void st_row_planes(unsigned short* __restrict__ hi, u
         *reinterpret_cast<uint2*>(lo + i * 128 + lane * 4) = ll;
     }
 }
+__device__ __forceinline__ void split4(const float4& v, uint2& hh, uint2& ll) {
+    const __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+    const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+    const __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2bfloat162_rn(v.z - f1.x, v.w - f1.y);
+    hh.x = *reinterpret_cast<const uint32_t*>(&h0); hh.y = *reinterpret_cast<const uint32_t*>(&h1);
+    ll.x = *reinterpret_cast<const uint32_t*>(&l0); ll.y = *reinterpret_cast<const uint32_t*>(&l1);
+}
 template <int VEC>
 __device__ __forceinline__ RowStats reg_stats(const float4 (&v)[VEC]) {
     float s = 0.f;
@@ -714,6 +721,151 @@ __global__ void __launch_bounds__(256) ln_act_bwd_vec_kernel(
     }
     float* const dst[3] = {norm ? dgamma : nullptr, norm ? dbeta : nullptr, dbias};
     flush_acc<VEC, 3>(acc, sacc, lane, dst);
+}
+
+}  // namespace oph
+
+// =================================================================================================
+// Backward of the highway tail, bandwidth-oriented layout: WPR warps share one row (256 channels per warp, two
+// float4 per lane), so the per-lane register accumulators of the six per-channel sums stay at 48 registers for every
+// width (C = 256 * WPR).  The loads of the next row are issued before the current row is processed (register
+// double buffer); gamma / beta vectors live in shared memory; the four per-row LN-backward sums are combined across
+// the warps of a row through shared memory and a named barrier.
+namespace oph {
+
+template <int WPR>
+__global__ void __launch_bounds__(256) hc_post_bwd_wide_kernel(
+        const float* __restrict__ dy, long long lddy, const float* __restrict__ z, long long ldz,
+        const float* __restrict__ x, long long ldx, const float* __restrict__ stats,
+        const float* __restrict__ g1, const float* __restrict__ b1, const float* __restrict__ g2,
+        const float* __restrict__ b2, unsigned short* __restrict__ dz_hi, unsigned short* __restrict__ dz_lo,
+        long long ldp, float* __restrict__ dxres, long long lddx,
+        float* __restrict__ dg1, float* __restrict__ db1, float* __restrict__ dg2, float* __restrict__ db2,
+        float* __restrict__ dbias, int rows, float drop_p, unsigned long long seed, const long long* step) {
+    constexpr int C = 256 * WPR;
+    constexpr int GROUPS = 8 / WPR;                      // rows in flight per block
+    extern __shared__ float smem_f[];
+    float* sacc = smem_f;                               // [6][C]
+    float* spar = smem_f + 6 * C;                       // [4][C]: g1, b1, g2, b2
+    float* sx = spar + 4 * C;                           // [2 parities][8 warps][4] partial row sums
+    for (int i = threadIdx.x; i < 6 * C; i += 256) sacc[i] = 0.f;
+    for (int i = threadIdx.x; i < C; i += 256) { spar[i] = g1[i]; spar[C + i] = b1[i]; spar[2 * C + i] = g2[i]; spar[3 * C + i] = b2[i]; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int grp = warp / WPR, part = warp % WPR;
+    const int cbase = part * 256 + lane * 4;            // first channel of this lane's float4 i is cbase + 128 * i
+    const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+    const float invC = 1.f / (float)C;
+    const unsigned long long sd = eff_seed(seed, step);
+    float acc[6][8];
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[k][i] = 0.f;
+
+    const long long stride = (long long)gridDim.x * GROUPS;
+    long long row = (long long)blockIdx.x * GROUPS + grp;
+    float4 z1[2], z2[2], xv[2], dv[2], st;
+    auto load_row = [&](long long r, float4 (&a)[2], float4 (&b)[2], float4 (&c)[2], float4 (&d)[2], float4& s4) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            a[i] = __ldg(reinterpret_cast<const float4*>(z + r * ldz + cbase + 128 * i));
+            b[i] = __ldg(reinterpret_cast<const float4*>(z + r * ldz + C + cbase + 128 * i));
+            c[i] = __ldg(reinterpret_cast<const float4*>(x + r * ldx + cbase + 128 * i));
+            d[i] = __ldg(reinterpret_cast<const float4*>(dy + r * lddy + cbase + 128 * i));
+        }
+        s4 = __ldg(reinterpret_cast<const float4*>(stats + r * 4));
+    };
+    if (row < rows) load_row(row, z1, z2, xv, dv, st);
+    int it = 0;
+    for (; row < rows; row += stride, ++it) {
+        float4 nz1[2], nz2[2], nxv[2], ndv[2], nst;
+        const bool more = row + stride < rows;
+        if (more) load_row(row + stride, nz1, nz2, nxv, ndv, nst);
+        const float m1 = st.x, r1 = st.y, m2 = st.z, r2 = st.w;
+        float a1 = 0.f, a2 = 0.f, c1 = 0.f, c2 = 0.f;
+        float4 e1v[2], e2v[2], xr[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            float4 G1 = *reinterpret_cast<const float4*>(spar + cbase + 128 * i);
+            float4 B1 = *reinterpret_cast<const float4*>(spar + C + cbase + 128 * i);
+            float4 G2 = *reinterpret_cast<const float4*>(spar + 2 * C + cbase + 128 * i);
+            float4 B2 = *reinterpret_cast<const float4*>(spar + 3 * C + cbase + 128 * i);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float xh1 = (OPH_F4(z1[i], e) - m1) * r1;
+                const float xh2 = (OPH_F4(z2[i], e) - m2) * r2;
+                const float u1 = xh1 * OPH_F4(G1, e) + OPH_F4(B1, e);
+                const float h = xh2 * OPH_F4(G2, e) + OPH_F4(B2, e);
+                const float g = sigmoidf_(u1);
+                float d_o = OPH_F4(dv[i], e);
+                if (drop_p > 0.f) d_o *= drop_scale(sd, (unsigned long long)row * C + cbase + 128 * i + e, drop_p, inv_keep);
+                OPH_F4(xr[i], e) = d_o * (1.f - g);
+                const float du1 = d_o * (h - OPH_F4(xv[i], e)) * g * (1.f - g);
+                const float du2 = d_o * g;
+                acc[0][i * 4 + e] += du1 * xh1; acc[1][i * 4 + e] += du1;
+                acc[2][i * 4 + e] += du2 * xh2; acc[3][i * 4 + e] += du2;
+                const float e1 = du1 * OPH_F4(G1, e), e2 = du2 * OPH_F4(G2, e);
+                a1 += e1; a2 += e1 * xh1; c1 += e2; c2 += e2 * xh2;
+                OPH_F4(e1v[i], e) = e1; OPH_F4(e2v[i], e) = e2;
+                OPH_F4(z1[i], e) = xh1; OPH_F4(z2[i], e) = xh2;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) *reinterpret_cast<float4*>(dxres + row * lddx + cbase + 128 * i) = xr[i];
+        a1 = warp_sum(a1); a2 = warp_sum(a2); c1 = warp_sum(c1); c2 = warp_sum(c2);
+        if (WPR > 1) {                                   // combine the partial sums of the warps sharing this row
+            float* my = sx + ((it & 1) * 8 + warp) * 4;
+            if (lane == 0) *reinterpret_cast<float4*>(my) = make_float4(a1, a2, c1, c2);
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(WPR * 32) : "memory");
+            a1 = a2 = c1 = c2 = 0.f;
+#pragma unroll
+            for (int w = 0; w < WPR; ++w) {
+                const float4 o = *reinterpret_cast<const float4*>(sx + ((it & 1) * 8 + grp * WPR + w) * 4);
+                a1 += o.x; a2 += o.y; c1 += o.z; c2 += o.w;
+            }
+        }
+        a1 *= invC; a2 *= invC; c1 *= invC; c2 *= invC;
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float d1 = r1 * (OPH_F4(e1v[i], e) - a1 - OPH_F4(z1[i], e) * a2);
+                const float d2 = r2 * (OPH_F4(e2v[i], e) - c1 - OPH_F4(z2[i], e) * c2);
+                OPH_F4(e1v[i], e) = d1; OPH_F4(e2v[i], e) = d2;
+                acc[4][i * 4 + e] += d1; acc[5][i * 4 + e] += d2;
+            }
+        {   // dz in the GEMMs' operand format: split-bf16 planes [rows][2C]
+            unsigned short* ph = dz_hi + row * ldp + cbase;
+            unsigned short* pl = dz_lo + row * ldp + cbase;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                uint2 hh, ll;
+                split4(e1v[i], hh, ll);
+                *reinterpret_cast<uint2*>(ph + 128 * i) = hh; *reinterpret_cast<uint2*>(pl + 128 * i) = ll;
+                split4(e2v[i], hh, ll);
+                *reinterpret_cast<uint2*>(ph + C + 128 * i) = hh; *reinterpret_cast<uint2*>(pl + C + 128 * i) = ll;
+            }
+        }
+        if (more) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) { z1[i] = nz1[i]; z2[i] = nz2[i]; xv[i] = nxv[i]; dv[i] = ndv[i]; }
+            st = nst;
+        }
+    }
+    // flush: per-lane sums -> shared (one atomic per warp and channel) -> global (one atomic per block and channel)
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) atomicAdd(&sacc[k * C + cbase + 128 * i + e], acc[k][i * 4 + e]);
+    __syncthreads();
+    float* const dst[6] = {dg1, db1, dg2, db2, dbias, dbias ? dbias + C : nullptr};
+    for (int idx = threadIdx.x; idx < 6 * C; idx += 256) {
+        float* d = dst[idx / C];
+        if (d) atomicAdd(d + (idx % C), sacc[idx]);
+    }
 }
 
 }  // namespace oph

@@ -48,10 +48,11 @@ class Session(object):
     def _evaluate(self, g, names, feeds):
         if "train_op" in names or "loss" in names or "loss_components" in names:
             assert g.training, "loss/train_op exist only on mode='train' graphs"
-            gs = int(g.store.global_step.item()) if "global_step" in names else None   # value before the step (tf semantics of fetching alongside train_op are unordered; the reference only logs it)
             comps = g.train_step().cpu().numpy()
+            # value after the step (fetching global_step alongside train_op is unordered in TF; the reference only logs it)
+            gs = int(g.store.global_step.item()) if "global_step" in names else None
             return {"train_op": None, "loss": float(comps[0]), "loss_components": [float(c) for c in comps],
-                    "global_step": gs if gs is None else gs + 1}
+                    "global_step": gs}
         if names == {"global_step"}:
             return {"global_step": int(g.store.global_step.item())}
         if isinstance(g, SSRNGraph):
