@@ -54,8 +54,14 @@ long long oph_launch_count(void);
  * (total cycles, cycles waiting for an accumulator stage, for A, for B, k-blocks). NULL disables. */
 int oph_gemm_debug_buffer(long long* dev_buf);
 /* diagnostics (results become garbage): 1 = operand producers skip loads/stores, 2 = weight loader skips copies,
- * 4 = unused, 8 = do not feed pre-split operands with TMA tensor copies (producer warps copy them instead) */
+ * 4 = CTA pairs do not rotate their k-block order, 8 = do not feed pre-split operands with TMA tensor copies (producer warps copy them instead),
+ * 16 = no remainder K-split of RED outputs, 32 = skip the item-boundary fix-up of flat A tiles */
 int oph_gemm_debug_flags(int flags);
+/* Execution context of the calling host thread (like cublasSetStream): with enable != 0 the weight-gradient GEMMs of
+ * oph_*_bwd are launched on `side` after an event fork behind the layer's row-wise backward kernel, so that they
+ * overlap the input-gradient chain on `stream`.  The caller joins `side` back (event / stream wait) before it reads
+ * the gradients and keeps x and dz alive until then.  enable == 0 restores in-order execution. */
+int oph_wgrad_stream(oph_stream_t side, int enable);
 int oph_profile_begin(void);
 int oph_profile_end(double* out);
 
@@ -66,6 +72,14 @@ int oph_profile_end(double* out);
 size_t oph_conv_pack_bytes(int k, int Cin, int Cout, int deconv, int backward);
 int oph_conv_pack(const float* w, int k, int Cin, int Cout, int deconv, void* packed_fwd, void* packed_bwd,
                   oph_stream_t stream);
+/* Batched form: build a plan on the HOST (array of opaque jobs, oph_pack_job_bytes() each; *njobs / *nblocks are
+ * running totals starting at 0), copy it to the device once, then oph_pack_run re-packs every kernel of the plan
+ * in ONE launch (called after each optimiser step: the reference re-reads its variables every step for free,
+ * architectures.py:128). */
+size_t oph_pack_job_bytes(void);
+int oph_pack_plan_add(void* plan_host, int capacity, int* njobs, long long* nblocks, const float* w, int k, int Cin,
+                      int Cout, int deconv, void* packed_fwd, void* packed_bwd);
+int oph_pack_run(const void* plan_dev, int njobs, long long nblocks, oph_stream_t stream);
 
 /* An activation [B*L rows][C]: an fp32 view and/or the same values as split-bf16 planes (hi = bf16(v),
  * lo = bf16(v - hi), row stride ldp elements, ldp % 8 == 0).  Planes are the operand format of the GEMM producers:

@@ -25,10 +25,14 @@ SIGNATURES = {
     "oph_launch_count": (LL, []),
     "oph_gemm_debug_buffer": (I, [P]),
     "oph_gemm_debug_flags": (I, [I]),
+    "oph_wgrad_stream": (I, [P, I]),
     "oph_profile_begin": (I, []),
     "oph_profile_end": (I, [P]),
     "oph_conv_pack_bytes": (SZ, [I, I, I, I, I]),
     "oph_conv_pack": (I, [P, I, I, I, I, P, P, P]),
+    "oph_pack_job_bytes": (SZ, []),
+    "oph_pack_plan_add": (I, [P, I, P, P, P, I, I, I, I, P, P]),
+    "oph_pack_run": (I, [P, I, LL, P]),
     "oph_conv1d_fwd": (I, [AP, P, P, P, P, P, LL, P, AP, P, LL, I, I, I, I, I, I, I, I, I, I, F, U64, P, P]),
     "oph_conv1d_bwd": (I, [P, LL, AP, P, LL, P, P, P, P, P, LL, P, LL, P, P, P, P,
                            I, I, I, I, I, I, I, I, I, I, F, U64, P, P]),

@@ -162,6 +162,17 @@ class Graph(object):
         assert not hp.update_weights, "hp.update_weights (partial fine-tuning) is outside the path"
         self.lr0 = hp.lr
 
+    # ---- side streams: independent chains (TextEnc || AudioEnc) and weight-gradient GEMMs overlap the main chain;
+    #      everything is joined back before the optimiser step, so callers (and CUDA-graph capture) see one stream
+    def _streams(self):
+        if not getattr(self.hp, "use_side_streams", True):
+            return None
+        st = self.__dict__.get("_side_streams")
+        if st is None:
+            st = tuple(torch.cuda.Stream(device=self.device) for _ in range(3))
+            self._side_streams = st
+        return st
+
     # ---- optimiser step shared by both models (architectures.py:110-128)
     def _apply_gradients(self):
         hp, st = self.hp, self.store
@@ -173,6 +184,7 @@ class Graph(object):
         ops.adam_clip(st.flat, st.m_flat, st.v_flat, st.grad_flat, st.lr_t, hp.beta1, hp.beta2, hp.epsilon, 1.0, scale)
         ops.step_inc(st.global_step)
         st.version += 1
+        st.repack_all()             # one launch refreshes every split-bf16 weight image for the next step
 
     # ---- whole-step CUDA graph: one launch replays the ~280 kernels of a training step (static shapes only)
     def capture_train_step(self, *example_inputs, warmup=2):
@@ -289,7 +301,22 @@ class SSRNGraph(Graph):
         comps = torch.empty(4, device=self.device, dtype=torch.float32)
         ops.loss_finalize(acc, comps, logits.shape[0] * logits.shape[1] * logits.shape[2], 1.0, w1, wbd, 0.0, w2,
                           False, squash)
-        tape.backward(dlogits)
+        side = self._streams()
+        if side is None:
+            tape.backward(dlogits)
+        else:
+            main = torch.cuda.current_stream(self.device)
+            s_w = side[1]
+            s_w.wait_stream(main)
+            ops.set_wgrad_stream(s_w)
+            try:
+                tape.backward(dlogits, release=False)
+            finally:
+                keep = ops.take_keepalive()
+                ops.set_wgrad_stream(None)
+            main.wait_stream(s_w)
+            tape.release()
+            del keep
         self._apply_gradients()
         return comps
 
@@ -310,7 +337,7 @@ class Text2MelGraph(Graph):
 
     # architectures.py:188-239
     def build_model(self, L, mels, training, K=None, V=None, prev_max_attentions=None, att_acc=None,
-                    want_alignments=True, tapes=None):
+                    want_alignments=True, tapes=None, text_stream=None):
         hp = self.hp
         mono = self.mode == 'synthesize'
         out = {}
@@ -320,11 +347,18 @@ class Text2MelGraph(Graph):
             return tape if tape is not None else _NullCtx()
         with use_store(self.store), variable_scope("Text2Mel"):
             # S = mels shifted one frame to the right (:191) is folded into AudioEnc C_1 (in_shift=1)
+            main = torch.cuda.current_stream(self.device)
+            forked = False
             if K is None:
-                with variable_scope("TextEnc"), on(t_text):
+                if text_stream is not None:                      # TextEnc and AudioEnc are independent chains
+                    text_stream.wait_stream(main)
+                    forked = True
+                with variable_scope("TextEnc"), on(t_text), (torch.cuda.stream(text_stream) if forked else _NullCtx()):
                     K, V = TextEnc(hp, L, training=training, speaker_codes=None, reuse=self.reuse)
             with variable_scope("AudioEnc"), on(t_aenc):
                 Q = AudioEnc(hp, mels, training=training, speaker_codes=None, reuse=self.reuse, in_shift=1)
+            if forked:
+                main.wait_stream(text_stream)
             with variable_scope("Attention"), on(t_dec):
                 R, alignments, max_attentions = Attention(
                     hp, Q, K, V, monotonic_attention=mono, prev_max_attentions=prev_max_attentions if mono else None,
@@ -373,7 +407,9 @@ class Text2MelGraph(Graph):
         st.grad_flat.zero_()
         acc = torch.zeros(4, dtype=torch.float64, device=self.device)
         tapes = (Tape(), Tape(), Tape())
-        out = self.build_model(L, mels, True, att_acc=acc[3:], want_alignments=False, tapes=tapes)
+        side = self._streams()
+        out = self.build_model(L, mels, True, att_acc=acc[3:], want_alignments=False, tapes=tapes,
+                               text_stream=side[0] if side else None)
         w1, wbd, watt, w2 = _loss_weights(hp, "t2m")
         squash = hp.squash_output_t2m
         logits = out["Y_logits"]
@@ -385,10 +421,36 @@ class Text2MelGraph(Graph):
         ops.loss_finalize(acc, comps, B * T * nm, n_att, w1, wbd, watt, w2, True, squash)
         # backward: AudioDec -> Attention -> (AudioEnc, TextEnc)
         t_text, t_aenc, t_dec = tapes
-        dRp = t_dec.backward(dlogits)
-        dQ, dKV = out["R"]._oph_attention_bwd(dRp, watt / n_att)
-        t_aenc.backward(dQ)
-        t_text.backward(dKV)
+        if side is None:
+            dRp = t_dec.backward(dlogits)
+            dQ, dKV = out["R"]._oph_attention_bwd(dRp, watt / n_att)
+            t_aenc.backward(dQ)
+            t_text.backward(dKV)
+        else:
+            # main: AudioDec -> Attention -> AudioEnc;  s_text: TextEnc;  s_w1 / s_w2: their weight-gradient GEMMs
+            main = torch.cuda.current_stream(self.device)
+            s_text, s_w1, s_w2 = side
+            s_w1.wait_stream(main)
+            keep = []
+            try:
+                ops.set_wgrad_stream(s_w1)
+                dRp = t_dec.backward(dlogits, release=False)
+                dQ, dKV = out["R"]._oph_attention_bwd(dRp, watt / n_att)
+                s_text.wait_stream(main)
+                s_w2.wait_stream(main)
+                with torch.cuda.stream(s_text):
+                    ops.set_wgrad_stream(s_w2)
+                    t_text.backward(dKV, release=False)
+                ops.set_wgrad_stream(s_w1)
+                t_aenc.backward(dQ, release=False)
+            finally:
+                keep.append(ops.take_keepalive())
+                ops.set_wgrad_stream(None)
+            for s_ in side:
+                main.wait_stream(s_)
+            for t in tapes:
+                t.release()
+            del keep, dKV, dQ, dRp
         self._apply_gradients()
         return comps
 

@@ -26,6 +26,25 @@ std::mutex g_prof_mu;
 bool g_prof_on = false;
 std::vector<ProfRec> g_prof;
 
+// Optional side stream for weight-gradient GEMMs (oph_wgrad_stream): they are off the critical path of the backward
+// chain, so they fork after the row-wise backward kernel of their layer and overlap the input-gradient chain.
+thread_local cudaStream_t g_wgrad_stream = nullptr;
+thread_local bool g_wgrad_fork = false;
+thread_local cudaEvent_t g_fork_ev[16];
+thread_local int g_fork_n = 0, g_fork_i = 0;
+
+cudaStream_t fork_wgrad(cudaStream_t main) {
+    if (!g_wgrad_fork || g_wgrad_stream == main) return main;
+    if (g_fork_n < 16) { cudaEventCreateWithFlags(&g_fork_ev[g_fork_n], cudaEventDisableTiming); ++g_fork_n; g_fork_i = g_fork_n - 1; }
+    else g_fork_i = (g_fork_i + 1) % 16;
+    cudaEvent_t ev = g_fork_ev[g_fork_i];
+    if (cudaEventRecord(ev, main) != cudaSuccess || cudaStreamWaitEvent(g_wgrad_stream, ev, 0) != cudaSuccess) {
+        cudaGetLastError();
+        return main;
+    }
+    return g_wgrad_stream;
+}
+
 int fail(int code, const char* fmt, const char* detail = "") {   // fmt contains exactly one %s
     snprintf(g_err, sizeof(g_err), fmt, detail);
     return code;
@@ -110,6 +129,19 @@ int launch_gemm(GemmArgs& a, int zdim, cudaStream_t st) {
         if (make_plane_tmap2d(&a.tmA_hi, a.A.hi, a.Kc, a.M, a.A.ld) && make_plane_tmap2d(&a.tmA_lo, a.A.lo, a.Kc, a.M, a.A.ld)) {
             a.a_tma = 1; a.items = a.M / a.A.L;
         }
+    }
+    if (a.b_mode == B_PACKED) {   // packed weight image as 128-byte rows: one 256-row box = one CTA's half of a stage
+        const size_t rows = (size_t)cdiv(a.N, GEMM_BN) * a.ntaps * cdiv(a.Kc, GEMM_BK) * (B_STAGE / 128);
+        EncodeTiledFn fn = encode_tiled_fn();
+        const cuuint64_t dims[2] = {64, (cuuint64_t)rows};
+        const cuuint64_t strides[1] = {128};
+        const cuuint32_t box[2] = {64, 256};
+        const cuuint32_t estr[2] = {1, 1};
+        if (!fn || (reinterpret_cast<uintptr_t>(a.Bpacked) & 127) ||
+            fn(&a.tmB_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(a.Bpacked), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return fail(OPH_ECUDA, "gemm: cannot encode the tensor map of the packed weight image%s");
     }
     a.dbg = g_gemm_dbg;
     a.dbg_flags = g_gemm_dbg_flags;
@@ -210,6 +242,49 @@ int pack_image(const float* w, int ntaps, const int* tap_idx, long long s_tap, l
     const long long total = (long long)(pack_image_bytes(ntaps, Cvalid, Nvalid) / B_STAGE) * 2048;
     pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p, total);
     return check_launch("pack_kernel");
+}
+
+// ---- batched packing: ONE launch re-packs every conv kernel of a model after the optimiser step
+struct PackJob { PackArgs a; long long total; long long first_block; };
+
+__global__ void pack_batch_kernel(const PackJob* __restrict__ jobs, int njobs) {
+    int lo = 0, hi = njobs - 1;                         // last job whose first block is <= blockIdx.x
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (jobs[mid].first_block <= (long long)blockIdx.x) lo = mid; else hi = mid - 1;
+    }
+    const PackJob& j = jobs[lo];
+    const PackArgs p = j.a;
+    const long long idx = ((long long)blockIdx.x - j.first_block) * blockDim.x + threadIdx.x;
+    if (idx >= j.total) return;
+    const int KBc = (p.Cvalid + GEMM_BK - 1) / GEMM_BK, KB = p.ntaps * KBc;
+    const int nl = (int)(idx & 255);
+    const int chunk = (int)((idx >> 8) & 7);
+    const long long rest = idx >> 11;
+    const int kb = (int)(rest % KB);
+    const int nb = (int)(rest / KB);
+    const int tap = kb / KBc, cb = kb - tap * KBc;
+    const int n = nb * GEMM_BN + nl;
+    const int c0 = cb * GEMM_BK + chunk * 8;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int c = c0 + e;
+        v[e] = (n < p.Nvalid && c < p.Cvalid) ? p.w[p.tap_idx[tap] * p.s_tap + c * p.s_c + n * p.s_n] : 0.f;
+    }
+    uint8_t* img = p.out + ((size_t)nb * KB + kb) * B_STAGE + (size_t)(nl >> 7) * B_SLOT;
+    const int nr = nl & 127;
+    store_split(img, img + B_PLANE, nr * 128 + ((chunk ^ (nr & 7)) << 4), v);
+}
+
+void plan_job(PackJob* j, const float* w, int ntaps, const int* tap_idx, long long s_tap, long long s_c, long long s_n,
+              int Cvalid, int Nvalid, void* out) {
+    j->a.w = w; j->a.ntaps = ntaps;
+    for (int i = 0; i < 3; ++i) j->a.tap_idx[i] = i < ntaps ? tap_idx[i] : 0;
+    j->a.s_tap = s_tap; j->a.s_c = s_c; j->a.s_n = s_n; j->a.Cvalid = Cvalid; j->a.Nvalid = Nvalid;
+    j->a.out = reinterpret_cast<uint8_t*>(out);
+    j->total = (long long)(pack_image_bytes(ntaps, Cvalid, Nvalid) / B_STAGE) * 2048;
+    j->first_block = 0;
 }
 
 // ------------------------------------------------------------------------------------------------ helpers
@@ -321,7 +396,13 @@ int oph_version(void) { return 100; }
 const char* oph_last_error(void) { return g_err; }
 long long oph_launch_count(void) { return g_launches.load(); }
 int oph_gemm_debug_buffer(long long* dev_buf) { g_gemm_dbg = dev_buf; return OPH_OK; }
-int oph_gemm_debug_flags(int flags) { g_gemm_dbg_flags = flags & 7; g_use_tma = !(flags & 8); g_use_split = !(flags & 16); return OPH_OK; }
+int oph_gemm_debug_flags(int flags) { g_gemm_dbg_flags = flags & 0x27; g_use_tma = !(flags & 8); g_use_split = !(flags & 16); return OPH_OK; }
+
+int oph_wgrad_stream(oph_stream_t side, int enable) {
+    g_wgrad_stream = S(side);
+    g_wgrad_fork = enable != 0;
+    return OPH_OK;
+}
 
 int oph_profile_begin(void) {
     std::lock_guard<std::mutex> lk(g_prof_mu);
@@ -376,6 +457,43 @@ int oph_conv_pack(const float* w, int k, int Cin, int Cout, int deconv, void* pa
     return OPH_OK;
 }
 
+size_t oph_pack_job_bytes(void) { return sizeof(PackJob); }
+
+// Appends the (up to 3) jobs of one kernel to a HOST plan; *njobs and *nblocks are running totals.
+int oph_pack_plan_add(void* plan_host, int capacity, int* njobs, long long* nblocks, const float* w, int k, int Cin,
+                      int Cout, int deconv, void* packed_fwd, void* packed_bwd) {
+    PackJob* plan = reinterpret_cast<PackJob*>(plan_host);
+    const int t012[3] = {0, 1, 2};
+    const long long s_tap = (long long)Cin * Cout;
+    PackJob tmp[3];
+    int n = 0;
+    if (!deconv) {
+        if (k < 1 || k > 3) return fail(OPH_EINVAL, "pack_plan_add: k must be 1..3%s");
+        if (packed_fwd) plan_job(&tmp[n++], w, k, t012, s_tap, Cout, 1, Cin, Cout, packed_fwd);
+        if (packed_bwd) plan_job(&tmp[n++], w, k, t012, s_tap, 1, Cout, Cout, Cin, packed_bwd);
+    } else {
+        if (packed_fwd) {
+            const int even[3] = {0, 2, 0}, odd[3] = {1, 0, 0};
+            plan_job(&tmp[n++], w, 2, even, s_tap, 1, Cin, Cin, Cout, packed_fwd);
+            plan_job(&tmp[n++], w, 1, odd, s_tap, 1, Cin, Cin, Cout, reinterpret_cast<uint8_t*>(packed_fwd) + pack_image_bytes(2, Cin, Cout));
+        }
+        if (packed_bwd) plan_job(&tmp[n++], w, 3, t012, s_tap, Cin, 1, Cout, Cin, packed_bwd);
+    }
+    if (*njobs + n > capacity) return fail(OPH_EINVAL, "pack_plan_add: plan capacity exceeded%s");
+    for (int i = 0; i < n; ++i) {
+        tmp[i].first_block = *nblocks;
+        *nblocks += (tmp[i].total + 255) / 256;
+        plan[(*njobs)++] = tmp[i];
+    }
+    return OPH_OK;
+}
+
+int oph_pack_run(const void* plan_dev, int njobs, long long nblocks, oph_stream_t stream) {
+    if (njobs <= 0 || nblocks <= 0) return OPH_OK;
+    pack_batch_kernel<<<(unsigned)nblocks, 256, 0, S(stream)>>>(reinterpret_cast<const PackJob*>(plan_dev), njobs);
+    return check_launch("pack_batch_kernel");
+}
+
 // ------------------------------------------------------------------------------------------------ conv1d
 static void set_operand(OperandMap& m, const oph_act* a) {
     m.ptr = a->f32; m.ld = a->ld; m.hi = m.lo = nullptr;
@@ -414,6 +532,7 @@ int oph_conv1d_bwd(const float* dy, long long lddy, const oph_act* x, const floa
     OperandMap dzm;
     OPH_TRY(launch_ln_act_bwd(dy, lddy, z, ldz, stats, gamma, beta, dz, lddz, dgamma, dbeta, dbias, (long long)B * L, Cout,
                               act, norm, drop_p, seed, step, &dzm, S(stream)));
+    cudaStream_t ws = dw ? fork_wgrad(S(stream)) : S(stream);
     int off[3];
     conv_offsets(k, rate, padding, in_shift, off);
     if (dx) {
@@ -428,7 +547,7 @@ int oph_conv1d_bwd(const float* dy, long long lddy, const oph_act* x, const floa
     if (dw) {
         const int zero[3] = {0, 0, 0};
         OperandMap xm; set_operand(xm, x);
-        OPH_TRY(launch_wgrad(xm, Cin, off, L, L, 1, dzm, Cout, zero, L, L, 1, B * L, k, dw, Cout, S(stream)));
+        OPH_TRY(launch_wgrad(xm, Cin, off, L, L, 1, dzm, Cout, zero, L, L, 1, B * L, k, dw, Cout, ws));
     }
     return OPH_OK;
 }
@@ -490,6 +609,7 @@ int oph_hc_bwd(const float* dy, long long lddy, const oph_act* x, const float* z
             (int)rows, C, norm, drop_p, seed, step);
     }
     OPH_TRY(check_launch("hc_post_bwd_kernel"));
+    cudaStream_t ws = dw ? fork_wgrad(S(stream)) : S(stream);
     int off[3];
     conv_offsets(k, rate, padding, 0, off);
     {
@@ -506,7 +626,7 @@ int oph_hc_bwd(const float* dy, long long lddy, const oph_act* x, const float* z
     if (dw) {
         const int zero[3] = {0, 0, 0};
         OperandMap xm; set_operand(xm, x);
-        OPH_TRY(launch_wgrad(xm, C, off, L, L, 1, dzm, 2 * C, zero, L, L, 1, B * L, k, dw, 2 * C, S(stream)));
+        OPH_TRY(launch_wgrad(xm, C, off, L, L, 1, dzm, 2 * C, zero, L, L, 1, B * L, k, dw, 2 * C, ws));
     }
     return OPH_OK;
 }
@@ -539,6 +659,7 @@ int oph_deconv_bwd(const float* dy, long long lddy, const oph_act* x, const floa
     OperandMap dzm;
     OPH_TRY(launch_ln_act_bwd(dy, lddy, z, ldz, stats, gamma, beta, dz, lddz, dgamma, dbeta, dbias, 2LL * B * L, C,
                               OPH_ACT_NONE, 1, drop_p, seed, step, &dzm, S(stream)));
+    cudaStream_t ws = dw ? fork_wgrad(S(stream)) : S(stream);
     if (dx) {   // dx[i] = W0^T dz[2i] + W1^T dz[2i+1] + W2^T dz[2i+2]
         GemmArgs g = blank();
         g.a_mode = A_KMAJOR; g.b_mode = B_PACKED;
@@ -551,7 +672,7 @@ int oph_deconv_bwd(const float* dy, long long lddy, const oph_act* x, const floa
     if (dw) {   // dW[j][co][ci]: j=0: dz[2i] x[i]; j=1: dz[2i+1] x[i]; j=2: dz[2i] x[i-1]
         const int a_off[3] = {0, 1, 0}, b_off[3] = {0, 0, -1};
         OperandMap xm; set_operand(xm, x);
-        OPH_TRY(launch_wgrad(dzm, C, a_off, L, 2 * L, 2, xm, C, b_off, L, L, 1, B * L, 3, dw, C, S(stream)));
+        OPH_TRY(launch_wgrad(dzm, C, a_off, L, 2 * L, 2, xm, C, b_off, L, L, 1, B * L, 3, dw, C, ws));
     }
     return OPH_OK;
 }

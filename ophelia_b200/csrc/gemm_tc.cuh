@@ -153,12 +153,11 @@ __device__ __forceinline__ bool map_row(const OperandMap& o, int r, int tap, lon
 }
 
 // barrier indices (same layout in both CTAs; FULL_* / T_EMPTY are only used in the leader, LAND_B only in the partner)
-constexpr int BAR_FULL_A = 0;                          // [NA_SLOTS] 2*NPW producer-warp arrivals (NPW per CTA)
+constexpr int BAR_FULL_A = 0;                          // [NA_SLOTS] leader: 2*NPW producer-warp arrivals, or 1 + copy bytes of both CTAs
 constexpr int BAR_EMPTY_A = BAR_FULL_A + NA_SLOTS;     // [NA_SLOTS] leader's commit, multicast to both CTAs
 constexpr int BAR_FULL_B = BAR_EMPTY_A + NA_SLOTS;     // [NB_SLOTS]
 constexpr int BAR_EMPTY_B = BAR_FULL_B + NB_SLOTS;     // [NB_SLOTS]
-constexpr int BAR_LAND_B = BAR_EMPTY_B + NB_SLOTS;     // [NB_SLOTS] partner: its bulk copy landed (relayed to the leader)
-constexpr int BAR_LAND_A = BAR_LAND_B + NB_SLOTS;      // [NA_SLOTS] partner: its TMA copy of A landed (relayed to the leader)
+constexpr int BAR_LAND_A = BAR_EMPTY_B + NB_SLOTS;     // [NA_SLOTS] local: an A tile that needs the item-boundary fix-up landed
 constexpr int BAR_T_FULL = BAR_LAND_A + NA_SLOTS;      // [N_ACC] accumulator stage complete (commit, multicast)
 constexpr int BAR_T_EMPTY = BAR_T_FULL + N_ACC;        // [N_ACC] accumulator stage drained by 4+4 epilogue warps
 constexpr int NUM_BARS = BAR_T_EMPTY + N_ACC;
@@ -169,6 +168,14 @@ struct Unit {               // one 256x256 output tile of one tap / z slice
     int rows;               // valid rows of this CTA's 128-row tile (<= 0: padding CTA)
     long long a_z, b_z, c_z;
 };
+
+// does the 128-row flat tile starting at row m0 contain rows whose tap-shifted step leaves their batch item?
+__device__ __forceinline__ bool needs_fix(int m0, int off, int L) {
+    if (off == 0) return false;
+    const int t0 = m0 % L;
+    if (t0 + GEMM_BM > L) return true;                 // the tile crosses an item boundary
+    return off < 0 ? t0 < -off : t0 + GEMM_BM > L - off;
+}
 
 __device__ __forceinline__ Unit decode_unit(const GemmArgs& p, int v, int MP, int nblocks, uint32_t crank) {
     Unit t;
@@ -226,17 +233,20 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
     // both operands arrive through the copy engines: the 16 producer warps have nothing to stage and drain the
     // accumulators instead (4 x more epilogue warps, the dedicated epilogue warps then idle)
     const bool copy_fed = (p.a_tma && packed) || p.r_tma;
+    const bool rotate = p.a_tma && packed && !(p.dbg_flags & 4);
+    const bool nofix = (p.dbg_flags & 32) != 0;        // diagnostics: skip the item-boundary fix-up (wrong results)
 
     if (tid == 0) {
         for (int i = 0; i < NA_SLOTS; ++i) {
-            mbar_init(BAR(BAR_FULL_A + i), (p.a_tma || p.r_tma) ? 2 : 2 * NPW);      // TMA: leader's expect_tx arrive + partner's relay
+            // copies: the leader's expect_tx arrive (+ for conv-style tiles one token per CTA: sent by its loader when
+            // the tile needs no fix-up, by its fix-up warp otherwise)
+            mbar_init(BAR(BAR_FULL_A + i), p.a_tma ? 3 : (p.r_tma ? 1 : 2 * NPW));
             mbar_init(BAR(BAR_EMPTY_A + i), 1);
             mbar_init(BAR(BAR_LAND_A + i), 1);
         }
         for (int i = 0; i < NB_SLOTS; ++i) {
-            mbar_init(BAR(BAR_FULL_B + i), (packed || p.r_tma) ? 2 : 2 * NPW);     // packed: leader's expect_tx arrive + partner's relay
+            mbar_init(BAR(BAR_FULL_B + i), (packed || p.r_tma) ? 1 : 2 * NPW);
             mbar_init(BAR(BAR_EMPTY_B + i), 1);
-            mbar_init(BAR(BAR_LAND_B + i), 1);
         }
         for (int i = 0; i < N_ACC; ++i) { mbar_init(BAR(BAR_T_FULL + i), 1); mbar_init(BAR(BAR_T_EMPTY + i), copy_fed ? 2 * EPI_WARPS : 8); }
         mbar_fence_init();
@@ -489,7 +499,8 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
                 w_t += clock64() - c0;
                 tc_fence_after();
                 const uint32_t d = tmem_base + acc * GEMM_BN;
-                for (int kb = t.kb0; kb < t.kb1; ++kb) {
+                const int nk = t.kb1 - t.kb0;
+                for (int j = 0; j < nk; ++j) {
                     c0 = clock64();
                     mbar_wait(BAR(BAR_FULL_A + as), a_par);
                     const long long c1 = clock64();
@@ -504,7 +515,7 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
                         const uint64_t dal = make_sdesc(a_lo + ks * a_step, a_lbo, 1024);
                         const uint64_t dbh = make_sdesc(b_hi + ks * b_step, b_lbo, 1024);
                         const uint64_t dbl = make_sdesc(b_lo + ks * b_step, b_lbo, 1024);
-                        umma2_bf16(d, dah, dbh, idesc, ((kb - t.kb0) | ks) != 0);
+                        umma2_bf16(d, dah, dbh, idesc, (j | ks) != 0);
                         umma2_bf16(d, dah, dbl, idesc, 1);
                         umma2_bf16(d, dal, dbh, idesc, 1);
                     }
@@ -525,11 +536,15 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
         }
         __syncwarp();
       } else if (warp == NPW + 5) {
-        // ================================================================ packed-weight loader (bulk copy engine)
+        // ================================================================ copy-engine loader (one thread per CTA)
+        // Both CTAs of the pair copy their halves with cta_group::2 tensor copies that signal the LEADER's FULL
+        // barrier directly; the leader's loader announces the bytes of both (arrive.expect_tx).
         if (lane == 0 && (packed || p.a_tma || p.r_tma)) {
             int slot = 0, par = 1, as = 0, a_par = 1;
             if (p.a_tma || p.r_tma) { tma_prefetch_desc(&p.tmA_hi); tma_prefetch_desc(&p.tmA_lo); }
-            if (p.r_tma) { tma_prefetch_desc(&p.tmB_hi); tma_prefetch_desc(&p.tmB_lo); }
+            if (p.r_tma || packed) tma_prefetch_desc(&p.tmB_hi);
+            if (p.r_tma) tma_prefetch_desc(&p.tmB_lo);
+            const uint32_t fullA0 = mapa_u32(BAR(BAR_FULL_A), 0), fullB0 = mapa_u32(BAR(BAR_FULL_B), 0);   // leader's barriers
             const int KBI = (p.A.L + GEMM_BK - 1) / GEMM_BK;       // 64-step blocks per batch item (r_tma)
             for (int u = pair; u < total; u += npairs) {
                 const Unit t = decode_unit(p, u, MP, nblocks, crank);
@@ -538,50 +553,67 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
                         const int g = t.k_begin + kb, item = g / KBI, tb = (g - item * KBI) * GEMM_BK;
                         {   // A: x^T tile = 64 steps x 128 channels [m0, m0+128) as two 64-channel boxes per plane
                             mbar_wait(BAR(BAR_EMPTY_A + as), a_par);
-                            const uint32_t bar = BAR((crank == 0 ? BAR_FULL_A : BAR_LAND_A) + as);
+                            const uint32_t bar = fullA0 + 8u * as;
                             const uint32_t dst = smem_u32(sA + as * A_SLOT);
-                            mbar_arrive_expect_tx(bar, A_SLOT);
+                            if (crank == 0) mbar_arrive_expect_tx(BAR(BAR_FULL_A + as), 2 * A_SLOT);
                             const int ta = tb + p.A.off[t.ytap];
-                            tma_load_3d(dst, &p.tmA_hi, t.m0, ta, item, bar);
-                            tma_load_3d(dst + 8192, &p.tmA_hi, t.m0 + 64, ta, item, bar);
-                            tma_load_3d(dst + A_PLANE, &p.tmA_lo, t.m0, ta, item, bar);
-                            tma_load_3d(dst + A_PLANE + 8192, &p.tmA_lo, t.m0 + 64, ta, item, bar);
+                            tma_load_3d_cg2(dst, &p.tmA_hi, t.m0, ta, item, bar);
+                            tma_load_3d_cg2(dst + 8192, &p.tmA_hi, t.m0 + 64, ta, item, bar);
+                            tma_load_3d_cg2(dst + A_PLANE, &p.tmA_lo, t.m0, ta, item, bar);
+                            tma_load_3d_cg2(dst + A_PLANE + 8192, &p.tmA_lo, t.m0 + 64, ta, item, bar);
                             if (++as == NA_SLOTS) { as = 0; a_par ^= 1; }
                         }
                         {   // B: this CTA's 128 of the 256 output columns
                             mbar_wait(BAR(BAR_EMPTY_B + slot), par);
-                            const uint32_t bar = BAR((crank == 0 ? BAR_FULL_B : BAR_LAND_B) + slot);
+                            const uint32_t bar = fullB0 + 8u * slot;
                             const uint32_t dst = smem_u32(sB + slot * B_SLOT);
-                            mbar_arrive_expect_tx(bar, B_SLOT);
+                            if (crank == 0) mbar_arrive_expect_tx(BAR(BAR_FULL_B + slot), 2 * B_SLOT);
                             const int tbb = tb + p.Bm.off[t.ytap], n = t.n0 + (int)crank * GEMM_BNC;
-                            tma_load_3d(dst, &p.tmB_hi, n, tbb, item, bar);
-                            tma_load_3d(dst + 8192, &p.tmB_hi, n + 64, tbb, item, bar);
-                            tma_load_3d(dst + B_PLANE, &p.tmB_lo, n, tbb, item, bar);
-                            tma_load_3d(dst + B_PLANE + 8192, &p.tmB_lo, n + 64, tbb, item, bar);
+                            tma_load_3d_cg2(dst, &p.tmB_hi, n, tbb, item, bar);
+                            tma_load_3d_cg2(dst + 8192, &p.tmB_hi, n + 64, tbb, item, bar);
+                            tma_load_3d_cg2(dst + B_PLANE, &p.tmB_lo, n, tbb, item, bar);
+                            tma_load_3d_cg2(dst + B_PLANE + 8192, &p.tmB_lo, n + 64, tbb, item, bar);
                             if (++slot == NB_SLOTS) { slot = 0; par ^= 1; }
                         }
                     }
                     continue;
                 }
-                const uint8_t* src = reinterpret_cast<const uint8_t*>(p.Bpacked) + (size_t)t.nb * t.KB * B_STAGE + crank * B_SLOT;
-                for (int kb = t.kb0; kb < t.kb1; ++kb) {
+                // packed image rows (128 bytes each) of this CTA's half of stage (nb, kb): ((nb*KB + kb)*2 + crank) * 256
+                const int brow0 = (t.nb * t.KB * 2 + (int)crank) * 256;
+                // CTA pairs walk the k-blocks of a unit from different starting points (rot): at any moment they ask the
+                // L2 for different weight stages instead of all hammering the same 64 KiB
+                const int nkb = t.kb1 - t.kb0, rot = rotate ? pair % nkb : 0;
+                for (int j = 0; j < nkb; ++j) {
+                    int kb = t.kb0 + j + rot; if (kb >= t.kb1) kb -= nkb;
                     if (p.a_tma) {                             // A tile: two boxes (hi / lo plane) of 64 channels x 128 rows
                         const int tap = kb / t.KBc, cb = kb - tap * t.KBc;
                         mbar_wait(BAR(BAR_EMPTY_A + as), a_par);
-                        const uint32_t bar = BAR(BAR_LAND_A + as);         // the fix-up warp forwards it to the leader's FULL_A
                         const uint32_t dst = smem_u32(sA + as * A_SLOT);
-                        mbar_arrive_expect_tx(bar, A_SLOT);
-                        tma_load_2d(dst, &p.tmA_hi, t.k_begin + cb * GEMM_BK, t.m0 + p.A.off[tap], bar);
-                        tma_load_2d(dst + A_PLANE, &p.tmA_lo, t.k_begin + cb * GEMM_BK, t.m0 + p.A.off[tap], bar);
+                        const int off = p.A.off[tap];
+                        const bool fix_me = !nofix && needs_fix(t.m0, off, p.A.L);
+                        if (crank == 0) {                      // bytes that will be signalled straight on FULL_A
+                            const bool fix_peer = !nofix && needs_fix(t.m0 + GEMM_BM, off, p.A.L);
+                            mbar_arrive_expect_tx(BAR(BAR_FULL_A + as), (fix_me ? 0 : A_SLOT) + (fix_peer ? 0 : A_SLOT));
+                        }
+                        if (fix_me) {                          // lands locally; the fix-up warp sends this CTA's token
+                            const uint32_t bar = BAR(BAR_LAND_A + as);
+                            mbar_arrive_expect_tx(bar, A_SLOT);
+                            tma_load_2d(dst, &p.tmA_hi, t.k_begin + cb * GEMM_BK, t.m0 + off, bar);
+                            tma_load_2d(dst + A_PLANE, &p.tmA_lo, t.k_begin + cb * GEMM_BK, t.m0 + off, bar);
+                        } else {
+                            const uint32_t bar = fullA0 + 8u * as;
+                            tma_load_2d_cg2(dst, &p.tmA_hi, t.k_begin + cb * GEMM_BK, t.m0 + off, bar);
+                            tma_load_2d_cg2(dst + A_PLANE, &p.tmA_lo, t.k_begin + cb * GEMM_BK, t.m0 + off, bar);
+                            if (crank == 0) mbar_arrive(BAR(BAR_FULL_A + as)); else mbar_arrive_remote(BAR(BAR_FULL_A + as), 0);
+                        }
                         if (++as == NA_SLOTS) { as = 0; a_par ^= 1; }
                     }
                     if (!packed) continue;
                     mbar_wait(BAR(BAR_EMPTY_B + slot), par);
-                    const uint32_t bar = BAR((crank == 0 ? BAR_FULL_B : BAR_LAND_B) + slot);
-                    if (p.dbg_flags & 2) { mbar_arrive(bar); }
+                    if (p.dbg_flags & 2) { if (crank == 0) mbar_arrive(BAR(BAR_FULL_B + slot)); }
                     else {
-                        mbar_arrive_expect_tx(bar, B_SLOT);
-                        bulk_g2s(smem_u32(sB + slot * B_SLOT), src + (size_t)kb * B_STAGE, B_SLOT, bar);
+                        if (crank == 0) mbar_arrive_expect_tx(BAR(BAR_FULL_B + slot), 2 * B_SLOT);
+                        tma_load_2d_cg2(smem_u32(sB + slot * B_SLOT), &p.tmB_hi, 0, brow0 + kb * 512, fullB0 + 8u * slot);
                     }
                     if (++slot == NB_SLOTS) { slot = 0; par ^= 1; }
                 }
@@ -589,46 +621,39 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
         }
         __syncwarp();
       } else if (warp == NPW + 6) {
-        // ================================================================ landing relay + item-boundary fix-up (whole warp)
-        // Copies that land in this CTA are announced to the leader's FULL barriers from here.  For the flat conv-style
-        // A tiles, rows whose tap-shifted source step falls outside their own batch item were fetched from the
-        // neighbouring item: they are conv padding and are zeroed here first (generic-proxy stores + proxy fence).
-        if ((packed || p.a_tma || p.r_tma) && (crank == 1 || p.a_tma)) {
-            int slot = 0, par = 0, as = 0, a_par = 0;
+        // ================================================================ item-boundary fix-up (whole warp, both CTAs)
+        // Flat conv-style A tiles: rows whose tap-shifted source step falls outside their own batch item were fetched
+        // from the neighbouring item.  They are conv padding: such tiles land on a local barrier, the rows are zeroed
+        // here (generic-proxy stores + proxy fence) and the bytes are then accounted on the leader's FULL barrier.
+        if (p.a_tma) {
+            int as = 0; uint32_t land_par = 0;
             for (int u = pair; u < total; u += npairs) {
                 const Unit t = decode_unit(p, u, MP, nblocks, crank);
                 int tmod[4];                                   // step within the item of this lane's 4 rows
 #pragma unroll
                 for (int j = 0; j < 4; ++j) tmod[j] = (t.m0 + lane + 32 * j) % p.A.L;
-                for (int kb = t.kb0; kb < t.kb1; ++kb) {
-                    if (p.a_tma) {
-                        mbar_wait(BAR(BAR_LAND_A + as), a_par);
-                        const int off = p.A.off[kb / t.KBc];
-                        if (off != 0) {
-                            bool any = false;
+                const int nkb = t.kb1 - t.kb0, rot = rotate ? pair % nkb : 0;
+                for (int j = 0; j < nkb; ++j) {
+                    int kb = t.kb0 + j + rot; if (kb >= t.kb1) kb -= nkb;
+                    const int off = p.A.off[kb / t.KBc];
+                    if (!nofix && needs_fix(t.m0, off, p.A.L)) {
+                        mbar_wait(BAR(BAR_LAND_A + as), (land_par >> as) & 1u);
+                        land_par ^= 1u << as;
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const int ts = tmod[j] + off;
-                                if (ts < 0 || ts >= p.A.L) {
-                                    any = true;
-                                    uint4* h = reinterpret_cast<uint4*>(sA + as * A_SLOT + (lane + 32 * j) * 128);
-                                    uint4* l = reinterpret_cast<uint4*>(sA + as * A_SLOT + A_PLANE + (lane + 32 * j) * 128);
+                        for (int r = 0; r < 4; ++r) {
+                            const int ts = tmod[r] + off;
+                            if (ts < 0 || ts >= p.A.L) {
+                                uint4* h = reinterpret_cast<uint4*>(sA + as * A_SLOT + (lane + 32 * r) * 128);
+                                uint4* l = reinterpret_cast<uint4*>(sA + as * A_SLOT + A_PLANE + (lane + 32 * r) * 128);
 #pragma unroll
-                                    for (int e = 0; e < 8; ++e) { h[e] = make_uint4(0u, 0u, 0u, 0u); l[e] = make_uint4(0u, 0u, 0u, 0u); }
-                                }
+                                for (int e = 0; e < 8; ++e) { h[e] = make_uint4(0u, 0u, 0u, 0u); l[e] = make_uint4(0u, 0u, 0u, 0u); }
                             }
-                            if (__any_sync(0xffffffffu, any)) { fence_proxy_async(); __syncwarp(); }
                         }
+                        fence_proxy_async();
+                        __syncwarp();
                         if (lane == 0) { if (crank == 0) mbar_arrive(BAR(BAR_FULL_A + as)); else mbar_arrive_remote(BAR(BAR_FULL_A + as), 0); }
-                        if (++as == NA_SLOTS) { as = 0; a_par ^= 1; }
-                    } else if (p.r_tma) {
-                        if (lane == 0) { mbar_wait(BAR(BAR_LAND_A + as), a_par); mbar_arrive_remote(BAR(BAR_FULL_A + as), 0); }
-                        if (++as == NA_SLOTS) { as = 0; a_par ^= 1; }
                     }
-                    if ((packed || p.r_tma) && crank == 1) {
-                        if (lane == 0) { mbar_wait(BAR(BAR_LAND_B + slot), par); mbar_arrive_remote(BAR(BAR_FULL_B + slot), 0); }
-                        if (++slot == NB_SLOTS) { slot = 0; par ^= 1; }
-                    }
+                    if (++as == NA_SLOTS) as = 0;
                 }
             }
         }

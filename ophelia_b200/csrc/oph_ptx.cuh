@@ -74,6 +74,31 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const void* tmap,
         "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
         ::"r"(dst_smem), "l"(tmap), "r"(c0), "r"(c1), "r"(bar) : "memory");
 }
+// CTA-pair forms (cta_group::2): the data lands in the executing CTA's shared memory, the transaction bytes are
+// signalled on an mbarrier that may live in the peer CTA (shared::cluster address, e.g. from mapa): both CTAs of a
+// pair report straight to the leader's FULL barrier, no relay hop.
+__device__ __forceinline__ void tma_load_2d_cg2(uint32_t dst_smem, const void* tmap, int c0, int c1, uint32_t bar_cluster) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst_smem), "l"(tmap), "r"(c0), "r"(c1), "r"(bar_cluster) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_cg2(uint32_t dst_smem, const void* tmap, int c0, int c1, int c2, uint32_t bar_cluster) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(dst_smem), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(bar_cluster) : "memory");
+}
+// shared::cluster address of `addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+// account `bytes` of transactions as complete on a (possibly remote) mbarrier: stands in for a copy that was
+// post-processed by threads before the consumer may see it
+__device__ __forceinline__ void mbar_complete_tx_cluster(uint32_t bar_cluster, uint32_t bytes) {
+    asm volatile("fence.acq_rel.cluster;" ::: "memory");
+    asm volatile("mbarrier.complete_tx.relaxed.cluster.shared::cluster.b64 [%0], %1;" ::"r"(bar_cluster), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }

@@ -28,11 +28,17 @@ class Tape(object):
     def __exit__(self, *exc):
         Tape.current = self._prev
 
-    def backward(self, grad):
+    def backward(self, grad, release=True):
+        """release=False keeps the closures (and the activations they hold) alive: needed while weight-gradient
+        GEMMs on a side stream may still read them; call release() after joining that stream."""
         for fn in reversed(self.steps):
             grad = fn(grad)
-        self.steps = []
+        if release:
+            self.steps = []
         return grad
+
+    def release(self):
+        self.steps = []
 
 
 def _record(fn):

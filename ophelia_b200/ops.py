@@ -16,6 +16,35 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+# Weight-gradient GEMMs on a side stream (oph_wgrad_stream): buffers they read (dz) are parked in `_keepalive` until
+# the caller has joined the side stream, so that the caching allocator cannot hand them to a later layer.
+_keepalive = None
+
+
+def set_wgrad_stream(stream):
+    """stream: torch.cuda.Stream or None (in-order).  Returns nothing; per host thread."""
+    global _keepalive
+    if stream is None:
+        _lib.call("oph_wgrad_stream", None, 0)
+        _keepalive = None
+    else:
+        _lib.call("oph_wgrad_stream", stream.cuda_stream, 1)
+        if _keepalive is None:
+            _keepalive = []
+
+
+def _park(*tensors):
+    if _keepalive is not None:
+        _keepalive.extend(t for t in tensors if t is not None)
+
+
+def take_keepalive():
+    """Hand the parked buffers to the caller (who drops them after joining the side stream)."""
+    global _keepalive
+    out, _keepalive = _keepalive, ([] if _keepalive is not None else None)
+    return out
+
+
 def _p(t):
     return None if t is None else t.data_ptr()
 
@@ -124,6 +153,7 @@ def conv1d_bwd(dy, x, saved, pk, gamma, beta, dw, dbias, dgamma, dbeta, rate=1, 
               _p(beta), _p(dz), dz.stride(1), _p(dx) if need_dx else None, dx.stride(1) if need_dx else 0, _p(dw),
               _p(dbias), _p(dgamma), _p(dbeta), B, L, cin, pk.cout, pk.k, rate, padding, in_shift, act,
               int(bool(norm)), float(drop_p), int(seed), _p(step), _stream())
+    _park(dz)
     return dx if need_dx else None
 
 
@@ -151,13 +181,14 @@ def hc_bwd(dy, x, saved, pk, g1, b1, g2, b2, dw, dbias, dg1, db1, dg2, db2, rate
     lddy = _rows(dy)[0]
     dev = x.device
     dz = torch.empty(B, L, 2 * C, device=dev, dtype=torch.float32)
-    dxres = torch.empty(B, L, C, device=dev, dtype=torch.float32)
     if dx is None:
         dx = torch.empty(B, L, C, device=dev, dtype=torch.float32)
+    # (dxres / ldxr of the C ABI are unused: the residual-path gradient is written straight into dx)
     _lib.call("oph_hc_bwd", _p(dy), lddy, _act(x), _p(z), z.stride(1), _p(stats), _p(pk.bwd), _p(g1), _p(b1),
-              _p(g2), _p(b2), _p(dz), dz.stride(1), _p(dxres), dxres.stride(1), _p(dx), dx.stride(1), _p(dw),
+              _p(g2), _p(b2), _p(dz), dz.stride(1), None, 0, _p(dx), dx.stride(1), _p(dw),
               _p(dbias), _p(dg1), _p(db1), _p(dg2), _p(db2), B, L, C, pk.k, rate, padding, int(bool(norm)),
               float(drop_p), int(seed), _p(step), _stream())
+    _park(dz)
     return dx
 
 
@@ -185,6 +216,7 @@ def deconv_bwd(dy, x, saved, pk, gamma, beta, dw, dbias, dgamma, dbeta, drop_p=0
     _lib.call("oph_deconv_bwd", _p(dy), lddy, _act(x), _p(z), z.stride(1), _p(stats), _p(pk.bwd), _p(gamma),
               _p(beta), _p(dz), dz.stride(1), _p(dx), dx.stride(1), _p(dw), _p(dbias), _p(dgamma), _p(dbeta),
               B, L, C, float(drop_p), int(seed), _p(step), _stream())
+    _park(dz)
     return dx
 
 

@@ -134,6 +134,7 @@ class VariableStore(object):
                 self.grads[name] = self.grad_flat[o:o + n].view(shape)
             self._host = OrderedDict()
             self.packed = {}
+            self._pack_plan = None
             self.version += 1
             if self.m_flat is not None:
                 self._alloc_opt()
@@ -146,6 +147,31 @@ class VariableStore(object):
         self.v_flat = torch.zeros_like(self.flat)
         self.global_step = torch.zeros(1, dtype=torch.int64, device=self.device)
         self.lr_t = torch.zeros(2, dtype=torch.float32, device=self.device)
+
+    # ---- packed conv kernels: one launch re-packs all of them after an optimiser step
+    def repack_all(self):
+        import ctypes
+        from . import _lib
+        if not self.packed:
+            return
+        key = tuple(self.packed)
+        plan = getattr(self, "_pack_plan", None)
+        if plan is None or plan[0] != key:
+            lib = _lib.load()
+            jb = int(lib.oph_pack_job_bytes())
+            cap = 3 * len(self.packed)
+            host = ctypes.create_string_buffer(cap * jb)
+            njobs, nblocks = ctypes.c_int(0), ctypes.c_longlong(0)
+            for pk in self.packed.values():
+                _lib.call("oph_pack_plan_add", ctypes.cast(host, ctypes.c_void_p), cap, ctypes.byref(njobs),
+                          ctypes.byref(nblocks), pk.w.data_ptr(), pk.k, pk.cin, pk.cout, int(pk.deconv),
+                          pk.fwd.data_ptr(), pk.bwd.data_ptr() if pk.bwd is not None else None)
+            dev = torch.frombuffer(bytearray(host.raw[:njobs.value * jb]), dtype=torch.uint8).to(self.device)
+            plan = (key, dev, njobs.value, nblocks.value)
+            self._pack_plan = plan
+        _lib.call("oph_pack_run", plan[1].data_ptr(), plan[2], plan[3], torch.cuda.current_stream().cuda_stream)
+        for pk in self.packed.values():
+            pk.version = self.version
 
     # ---- access
     def get(self, name):
