@@ -23,6 +23,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 METRIC = "Text2Mel train mel-frames/sec (B=32 per GPU, N=180, T=870)"
+METRIC_SSRN = "SSRN train coarse mel-frames/sec (B=32 per GPU, T=870 -> 3480 frames)"
 UNIT = "mel-frames/s"
 
 
@@ -117,7 +118,7 @@ def run_reference(args):
         return
     model = "t2m" if args.workload == "t2m_train" else "ssrn"
     value, dt, cores, sample = cpu_reference(args, model, args.ref_batch, max(1, args.steps), max(0, min(args.warmup, 1)))
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+    line = {"impl": "reference", "metric": METRIC if model == "t2m" else METRIC_SSRN, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, 1),
@@ -188,8 +189,12 @@ def run_ours(args):
     if rank == 0:
         clocks.start()
 
-    # ---- timed region 1: device-resident inputs
+    # ---- timed region 1: device-resident inputs, eager launches on ONE stream with CUDA events around every GEMM
+    #      launch (the per-kernel roofline numbers; side streams would make the event intervals overlap)
     import ctypes
+    hp.use_side_streams = False
+    for _ in range(2):
+        g.train_step_device(*dev_in)
     sync_all()
     launches0 = lib.oph_launch_count()
     lib.oph_profile_begin()
@@ -202,6 +207,7 @@ def run_ours(args):
     ms = e0.elapsed_time(e1) / args.steps
     prof = (ctypes.c_double * 15)()
     lib.oph_profile_end(prof)
+    hp.use_side_streams = True
     launches = (lib.oph_launch_count() - launches0) // args.steps
     last_loss = [float(c) for c in comps.cpu().numpy()]
 
@@ -253,13 +259,15 @@ def run_ours(args):
                             "tflops": (prof[i * 3 + 2] / (prof[i * 3 + 1] * 1e-3) / 1e12) if prof[i * 3 + 1] > 0 else 0.0}
                  for i in range(5) if prof[i * 3] > 0}
     line = {
-        "metric": METRIC, "value": frames_per_step / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "metric": METRIC if t2m else METRIC_SSRN, "value": frames_per_step / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
         "per_gpu": frames_per_step / world / (ms * 1e-3),
         "launch_mode": {"headline": "cuda_graph" if ms is ms_graph else "eager", "ms_per_step_eager": ms_eager,
                         "ms_per_step_cuda_graph": ms_graph,
-                        "note": "roofline/gemm_breakdown are CUDA-event timings of every GEMM launch in the eager steps"},
+                        "note": "roofline/gemm_breakdown are CUDA-event timings of every GEMM launch in the eager single-stream "
+                                "steps; the CUDA-graph steps run the same kernels with TextEnc and the weight-gradient GEMMs "
+                                "on side streams"},
         "e2e": {"value": frames_per_step / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": src.bytes_per_batch(), "d2h_bytes_per_step": 4 * len(last_loss) + 8},
         "gpu_launches": int(launches) * args.steps,
@@ -283,13 +291,70 @@ def run_ours(args):
         dist.barrier()
 
 
+def run_synth(args):
+    """BASELINE.json configs[3]: synthesize.py autoregressive inference, 10 sentences, max_N=150, max_T=200, monotonic
+    attention on, Griffin-Lim off: encode_text + AR loop + SSRN.  RTF = wall seconds / audio seconds."""
+    import numpy as np
+    import torch
+    import __graft_entry__
+    from ophelia_b200 import synthesize as syn
+    from ophelia_b200.architectures import SSRNGraph, Text2MelGraph
+    from ophelia_b200.configuration import default_hparams
+    from ophelia_b200.session import Session
+    from ophelia_b200.variables import VariableStore
+    __graft_entry__.build()
+    dev = torch.device("cuda", 0)
+    nsent, maxN, maxT = 10, 150, 200
+    hp = default_hparams(max_N=maxN, max_T=maxT, full_dim=args.full_dim, seed=0)
+    rng = np.random.default_rng(1234)
+    L = np.zeros((nsent, maxN), np.int32)
+    for i in range(nsent):
+        n = int(rng.integers(60, maxN - 1))
+        L[i, :n] = rng.integers(1, len(hp.vocab), n)
+    g1 = Text2MelGraph(hp, mode="synthesize", store=VariableStore(dev, seed=0), device=dev)
+    g2 = SSRNGraph(hp, mode="synthesize", store=VariableStore(dev, seed=1), device=dev)
+    sess = Session()
+    ends = syn.get_text_lengths(L)
+    sec_per_frame = hp.r * hp.hop_length / float(hp.sr)
+
+    def route(kind):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        K, V = syn.encode_text(hp, L, g1, sess)
+        if kind == "session":
+            Y, t_ends, _ = syn.synth_codedtext2mel(hp, K, V, ends, g1, sess)
+        else:
+            Y, t_ends, _ = syn.synth_codedtext2mel_device(hp, K, V, ends, g1, use_cuda_graph=(kind == "device_graph"))
+        t1 = time.perf_counter()
+        Z = syn.synth_mel2mag(hp, Y, g2, sess)
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        audio = sum(t_ends) * sec_per_frame
+        return {"wall_s": t2 - t0, "text2mel_s": t1 - t0, "ssrn_s": t2 - t1, "audio_s": audio, "rtf": (t2 - t0) / audio,
+                "frames": int(sum(t_ends)), "mag_shape": list(Z.shape)}
+    route("device_graph")                                # warm-up (packing, graph pools)
+    res = {k: route(k) for k in ("session", "device", "device_graph")}
+    best = res["device_graph"]
+    line = {"metric": "synthesis RTF (10 sentences, max_N=150, max_T=200, monotonic attention, Griffin-Lim off)",
+            "value": best["rtf"], "unit": "wall s per audio s", "n_gpus": 1, "steps": 1, "warmup": 1,
+            "ms_per_step": best["wall_s"] * 1e3, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic (random-init weights: attention never reaches the sentence end, so every "
+                                    "sentence runs all max_T frames)",
+            "config": {"workload": "encode_text + autoregressive Text2Mel loop (full graph re-run per frame, as "
+                                   "synthesize.py:150-230) + SSRN, B=10, max_N=150, max_T=200, F=%d" % args.full_dim},
+            "routes": res,
+            "e2e": {"value": res["session"]["rtf"], "unit": "wall s per audio s",
+                    "note": "Session.run route: numpy in/out every frame like the reference"}}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="t2m_train", choices=["t2m_train", "ssrn_train"])
+    ap.add_argument("--workload", default="t2m_train", choices=["t2m_train", "ssrn_train", "synth"])
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--N", type=int, default=180)
     ap.add_argument("--T", type=int, default=870)
@@ -300,6 +365,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "synth":
+        return run_synth(args)
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
                "--master-addr", "127.0.0.1", "--master-port", "29411", os.path.abspath(__file__)] + sys.argv[1:]

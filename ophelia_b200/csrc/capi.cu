@@ -18,6 +18,8 @@ namespace {
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
 int g_gemm_dbg_flags = 0;
+bool g_hcb_two = true;
+int g_hcb_depth = 0;               // ring depth of the highway-backward row kernel (tunable through oph_gemm_debug_flags bits 8..10)
 long long* g_gemm_dbg = nullptr;   // optional device buffer [74][8] for in-kernel wait-cycle counters
 
 // Optional per-launch timing of the GEMM core (bench.py roofline): CUDA events around every launch, by tag.
@@ -396,7 +398,12 @@ int oph_version(void) { return 100; }
 const char* oph_last_error(void) { return g_err; }
 long long oph_launch_count(void) { return g_launches.load(); }
 int oph_gemm_debug_buffer(long long* dev_buf) { g_gemm_dbg = dev_buf; return OPH_OK; }
-int oph_gemm_debug_flags(int flags) { g_gemm_dbg_flags = flags & 0x27; g_use_tma = !(flags & 8); g_use_split = !(flags & 16); return OPH_OK; }
+int oph_gemm_debug_flags(int flags) { g_gemm_dbg_flags = flags & 0x27; g_use_tma = !(flags & 8); g_use_split = !(flags & 16);
+    g_hcb_depth = (flags >> 8) & 7;                    // 0 = automatic
+    g_hcb_two = !(flags & 2048);
+    if (g_hcb_depth == 1) g_hcb_depth = 2;
+    if (g_hcb_depth > 4) g_hcb_depth = 4;
+    return OPH_OK; }
 
 int oph_wgrad_stream(oph_stream_t side, int enable) {
     g_wgrad_stream = S(side);
@@ -598,9 +605,20 @@ int oph_hc_bwd(const float* dy, long long lddy, const oph_act* x, const float* z
         unsigned short* h = const_cast<unsigned short*>(dzm.hi); unsigned short* l = const_cast<unsigned short*>(dzm.lo);
         const int wpr = C / 256, groups = 8 / wpr;
         long long gl = (rows + groups * 4 - 1) / (groups * 4);             // >= 4 rows per row group
-        const int grid = (int)(gl < 1 ? 1 : (gl > 148 ? 148 : gl));
-        const size_t sm2 = (10 * (size_t)C + 64) * sizeof(float);
-#define OPH_LAUNCH(W) hc_post_bwd_wide_kernel<W><<<grid, 256, sm2, S(stream)>>>(dy, lddy, z, ldz, x->f32, x->ld, stats, g1, b1, g2, b2, h, l, 2 * C, dx, lddx, dg1, db1, dg2, db2, dbias, (int)rows, drop_p, seed, step)
+        // two 8-warp blocks per SM; rows in flight per warp (ring slots): 3 where the shared memory of two blocks allows
+        const int gmax = g_hcb_two ? 296 : 148;
+        const int grid = (int)(gl < 1 ? 1 : (gl > gmax ? gmax : gl));
+        const int depth = g_hcb_depth ? g_hcb_depth : (C == 256 ? 3 : 2);
+        const size_t sm2 = (10 * (size_t)C + 64) * sizeof(float) + (size_t)8 * depth * HCB_SLOT;
+        static bool attr_done = false;
+        if (!attr_done) {
+            const int mx = 200 * 1024;
+            cudaFuncSetAttribute(hc_post_bwd_wide_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+            cudaFuncSetAttribute(hc_post_bwd_wide_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+            cudaFuncSetAttribute(hc_post_bwd_wide_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+            attr_done = true;
+        }
+#define OPH_LAUNCH(W) hc_post_bwd_wide_kernel<W><<<grid, 256, sm2, S(stream)>>>(dy, lddy, z, ldz, x->f32, x->ld, stats, g1, b1, g2, b2, h, l, 2 * C, dx, lddx, dg1, db1, dg2, db2, dbias, (int)rows, drop_p, seed, step, depth)
         if (C == 256) OPH_LAUNCH(1); else if (C == 512) OPH_LAUNCH(2); else OPH_LAUNCH(4);
 #undef OPH_LAUNCH
     } else {

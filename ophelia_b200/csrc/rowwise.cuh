@@ -728,10 +728,17 @@ __global__ void __launch_bounds__(256) ln_act_bwd_vec_kernel(
 // =================================================================================================
 // Backward of the highway tail, bandwidth-oriented layout: WPR warps share one row (256 channels per warp, two
 // float4 per lane), so the per-lane register accumulators of the six per-channel sums stay at 48 registers for every
-// width (C = 256 * WPR).  The loads of the next row are issued before the current row is processed (register
-// double buffer); gamma / beta vectors live in shared memory; the four per-row LN-backward sums are combined across
-// the warps of a row through shared memory and a named barrier.
+// width (C = 256 * WPR).  Each warp streams its rows through a private ring of `depth` shared-memory slots filled
+// with 16-byte async copies (LDGSTS), several rows ahead of the one being processed: one 8-warp block per SM keeps
+// >100 KB of loads in flight.  gamma / beta vectors live in shared memory; the four per-row LN-backward sums are
+// combined across the warps of a row through shared memory and a named barrier.
 namespace oph {
+
+constexpr int HCB_SLOT = 8 * 512 + 32;                  // 8 float4 per lane + the row's (mean, rstd) x 2
+
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
 
 template <int WPR>
 __global__ void __launch_bounds__(256) hc_post_bwd_wide_kernel(
@@ -741,13 +748,14 @@ __global__ void __launch_bounds__(256) hc_post_bwd_wide_kernel(
         const float* __restrict__ b2, unsigned short* __restrict__ dz_hi, unsigned short* __restrict__ dz_lo,
         long long ldp, float* __restrict__ dxres, long long lddx,
         float* __restrict__ dg1, float* __restrict__ db1, float* __restrict__ dg2, float* __restrict__ db2,
-        float* __restrict__ dbias, int rows, float drop_p, unsigned long long seed, const long long* step) {
+        float* __restrict__ dbias, int rows, float drop_p, unsigned long long seed, const long long* step, int depth) {
     constexpr int C = 256 * WPR;
     constexpr int GROUPS = 8 / WPR;                      // rows in flight per block
-    extern __shared__ float smem_f[];
+    extern __shared__ __align__(16) float smem_f[];
     float* sacc = smem_f;                               // [6][C]
     float* spar = smem_f + 6 * C;                       // [4][C]: g1, b1, g2, b2
     float* sx = spar + 4 * C;                           // [2 parities][8 warps][4] partial row sums
+    uint8_t* ring = reinterpret_cast<uint8_t*>(sx + 64);   // [8 warps][depth][HCB_SLOT]
     for (int i = threadIdx.x; i < 6 * C; i += 256) sacc[i] = 0.f;
     for (int i = threadIdx.x; i < C; i += 256) { spar[i] = g1[i]; spar[C + i] = b1[i]; spar[2 * C + i] = g2[i]; spar[3 * C + i] = b2[i]; }
     __syncthreads();
@@ -765,23 +773,47 @@ __global__ void __launch_bounds__(256) hc_post_bwd_wide_kernel(
 
     const long long stride = (long long)gridDim.x * GROUPS;
     long long row = (long long)blockIdx.x * GROUPS + grp;
-    float4 z1[2], z2[2], xv[2], dv[2], st;
-    auto load_row = [&](long long r, float4 (&a)[2], float4 (&b)[2], float4 (&c)[2], float4 (&d)[2], float4& s4) {
+    uint8_t* myring = ring + (size_t)warp * depth * HCB_SLOT;
+    const uint32_t ring_u32 = (uint32_t)__cvta_generic_to_shared(myring) + lane * 16;
+    auto issue = [&](long long r, int slot) {           // this lane's 9 x 16 bytes of row r -> ring slot
+        if (r < rows) {
+            const uint32_t d = ring_u32 + slot * HCB_SLOT;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                cp_async_16(d + (0 + i) * 512, z + r * ldz + cbase + 128 * i);
+                cp_async_16(d + (2 + i) * 512, z + r * ldz + C + cbase + 128 * i);
+                cp_async_16(d + (4 + i) * 512, x + r * ldx + cbase + 128 * i);
+                cp_async_16(d + (6 + i) * 512, dy + r * lddy + cbase + 128 * i);
+            }
+            if (lane == 0) cp_async_16(d + 8 * 512, stats + r * 4);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    for (int d = 0; d < depth - 1; ++d) issue(row + d * stride, d);
+    int it = 0, slot = 0;
+    for (; row < rows; row += stride, ++it) {
+        {
+            int ns = slot + depth - 1; if (ns >= depth) ns -= depth;
+            issue(row + (long long)(depth - 1) * stride, ns);
+        }
+        // all but the newest depth-1 groups are complete: the slot of this row has landed
+        if (depth == 2) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else if (depth == 3) asm volatile("cp.async.wait_group 2;" ::: "memory");
+        else if (depth == 4) asm volatile("cp.async.wait_group 3;" ::: "memory");
+        else if (depth == 5) asm volatile("cp.async.wait_group 4;" ::: "memory");
+        else asm volatile("cp.async.wait_group 5;" ::: "memory");
+        __syncwarp();                                    // lane 0's copy of the row statistics is read by every lane
+        const uint8_t* sl = myring + slot * HCB_SLOT + lane * 16;
+        float4 z1[2], z2[2], xv[2], dv[2];
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
-            a[i] = __ldg(reinterpret_cast<const float4*>(z + r * ldz + cbase + 128 * i));
-            b[i] = __ldg(reinterpret_cast<const float4*>(z + r * ldz + C + cbase + 128 * i));
-            c[i] = __ldg(reinterpret_cast<const float4*>(x + r * ldx + cbase + 128 * i));
-            d[i] = __ldg(reinterpret_cast<const float4*>(dy + r * lddy + cbase + 128 * i));
+            z1[i] = *reinterpret_cast<const float4*>(sl + (0 + i) * 512);
+            z2[i] = *reinterpret_cast<const float4*>(sl + (2 + i) * 512);
+            xv[i] = *reinterpret_cast<const float4*>(sl + (4 + i) * 512);
+            dv[i] = *reinterpret_cast<const float4*>(sl + (6 + i) * 512);
         }
-        s4 = __ldg(reinterpret_cast<const float4*>(stats + r * 4));
-    };
-    if (row < rows) load_row(row, z1, z2, xv, dv, st);
-    int it = 0;
-    for (; row < rows; row += stride, ++it) {
-        float4 nz1[2], nz2[2], nxv[2], ndv[2], nst;
-        const bool more = row + stride < rows;
-        if (more) load_row(row + stride, nz1, nz2, nxv, ndv, nst);
+        const float4 st = *reinterpret_cast<const float4*>(myring + slot * HCB_SLOT + 8 * 512);
+        if (++slot == depth) slot = 0;
         const float m1 = st.x, r1 = st.y, m2 = st.z, r2 = st.w;
         float a1 = 0.f, a2 = 0.f, c1 = 0.f, c2 = 0.f;
         float4 e1v[2], e2v[2], xr[2];
@@ -847,12 +879,8 @@ __global__ void __launch_bounds__(256) hc_post_bwd_wide_kernel(
                 *reinterpret_cast<uint2*>(ph + C + 128 * i) = hh; *reinterpret_cast<uint2*>(pl + C + 128 * i) = ll;
             }
         }
-        if (more) {
-#pragma unroll
-            for (int i = 0; i < 2; ++i) { z1[i] = nz1[i]; z2[i] = nz2[i]; xv[i] = nxv[i]; dv[i] = ndv[i]; }
-            st = nst;
-        }
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     // flush: per-lane sums -> shared (one atomic per warp and channel) -> global (one atomic per block and channel)
 #pragma unroll
     for (int k = 0; k < 6; ++k)

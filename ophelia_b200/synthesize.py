@@ -80,11 +80,13 @@ def synth_codedtext2mel(hp, K, V, ends, g, sess, speaker_data=None, duration_dat
     return (Y, t_ends.tolist(), alignments)
 
 
-def synth_codedtext2mel_device(hp, K, V, ends, g):
-    """Same loop with every tensor resident on the GPU; per frame only B int32 argmax values cross to the host."""
+def synth_codedtext2mel_device(hp, K, V, ends, g, use_cuda_graph=True):
+    """Same loop with every tensor resident on the GPU; per frame only B int32 argmax values cross to the host.
+    With use_cuda_graph the per-frame forward (AudioEnc + Attention + AudioDec over all max_T frames, ~55 kernels) is
+    captured once and replayed: Y and prev_max_attentions are static buffers that the loop updates in place."""
     dev = g.device
-    K = g._to_device(K, torch.float32)
-    V = g._to_device(V, torch.float32)
+    K = g._to_device(K, torch.float32).contiguous()
+    V = g._to_device(V, torch.float32).contiguous()
     B = K.shape[0]
     Y = torch.zeros(B, hp.max_T, hp.n_mels, device=dev, dtype=torch.float32)
     alignments = torch.zeros(B, hp.max_N, hp.max_T, device=dev, dtype=torch.float32)
@@ -92,11 +94,24 @@ def synth_codedtext2mel_device(hp, K, V, ends, g):
     ends = np.asarray(ends)
     endcounts = np.zeros(ends.shape, dtype=int)
     t_ends = np.ones(ends.shape, dtype=int) * hp.max_T
+
+    def forward():
+        return g.build_model(None, Y, False, K=K, V=V, prev_max_attentions=prev, want_alignments=True)
+    graph = None
+    if use_cuda_graph:
+        forward()                                       # warm-up outside the capture (lazy weight packing)
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = forward()
     for j in range(hp.max_T):
-        out = g.build_model(None, Y, False, K=K, V=V, prev_max_attentions=prev, want_alignments=True)
+        if graph is not None:
+            graph.replay()
+        else:
+            out = forward()
         Y[:, j, :].copy_(out["Y"][:, j, :])
         alignments[:, :, j].copy_(out["alignments"][:, :, j])
-        prev = out["max_attentions"][:, j].contiguous()
+        prev.copy_(out["max_attentions"][:, j])
         if _update_ends(hp, prev.cpu().numpy().astype(np.int64), ends, endcounts, t_ends, j):
             break
     return (Y.cpu().numpy(), t_ends.tolist(), alignments.cpu().numpy())

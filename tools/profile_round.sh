@@ -4,12 +4,12 @@
 set -u
 R=${1:-r01}
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/launches_${R}.csv \
-    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu_${R}.log 2>&1
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph > gpurun_out/bench_under_ncu_${R}.log 2>&1
 for op in hc_fwd hc_dgrad hc_bwd; do
   skip=3; [ $op = hc_bwd ] && skip=7
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16x3 -s $skip -c 1 -f \
       -o gpurun_out/${R}_gemm_${op} python tools/perf_layer.py --op $op --iters 2 > gpurun_out/ncu_${R}_${op}.log 2>&1
 done
-timeout 600 ncu --set full --clock-control none -k regex:hc_post_bwd_vec -s 2 -c 1 -f -o gpurun_out/${R}_hc_post_bwd \
+timeout 600 ncu --set full --clock-control none -k regex:hc_post_bwd_wide -s 2 -c 1 -f -o gpurun_out/${R}_hc_post_bwd \
     python tools/perf_layer.py --op hc_bwd --iters 2 > gpurun_out/ncu_${R}_post.log 2>&1
 ls -la gpurun_out/ | tail -8
