@@ -76,6 +76,8 @@ def load():
         fn.restype = res
         fn.argtypes = args
     _lib = lib
+    if os.environ.get("OPH_DEBUG_FLAGS"):            # diagnostics only (A/B timing of scheduling features)
+        lib.oph_gemm_debug_flags(int(os.environ["OPH_DEBUG_FLAGS"], 0))
     return lib
 
 

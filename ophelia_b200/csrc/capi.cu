@@ -47,6 +47,25 @@ cudaStream_t fork_wgrad(cudaStream_t main) {
     return g_wgrad_stream;
 }
 
+// Every kernel of the library is launched with programmatic stream serialization (PDL): a kernel's blocks may become
+// resident while its predecessor in the stream drains and run their prologue; `pdl_grid_sync()` at the top of each
+// kernel (griddepcontrol.wait) orders their first global-memory access after the predecessor's completion.
+bool g_use_pdl = false;   // measured on B200: no gain inside CUDA graphs (7.60 vs 7.57 ms per step), kept as an option
+struct launch_cfg {
+    dim3 grid, block; size_t smem; cudaStream_t st;
+    launch_cfg(dim3 g, dim3 b, size_t s, cudaStream_t stream) : grid(g), block(b), smem(s), st(stream) {}
+    template <typename... KA, typename... A>
+    void operator()(void (*kernel)(KA...), A&&... args) const {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = g_use_pdl ? 1 : 0;
+        cudaLaunchKernelEx(&cfg, kernel, static_cast<KA>(args)...);
+    }
+};
+
 int fail(int code, const char* fmt, const char* detail = "") {   // fmt contains exactly one %s
     snprintf(g_err, sizeof(g_err), fmt, detail);
     return code;
@@ -180,7 +199,7 @@ int launch_gemm(GemmArgs& a, int zdim, cudaStream_t st) {
             cudaEventRecord(rec.e0, st);
         }
     }
-    gemm_bf16x3_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(a);
+    launch_cfg(grid, GEMM_THREADS, GEMM_SMEM, st)(gemm_bf16x3_kernel, a);
     if (prof) {
         cudaEventRecord(rec.e1, st);
         std::lock_guard<std::mutex> lk(g_prof_mu);
@@ -207,6 +226,7 @@ struct PackArgs {
 };
 
 __global__ void pack_kernel(const PackArgs p, long long total) {
+    pdl_grid_sync();
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const int KBc = (p.Cvalid + GEMM_BK - 1) / GEMM_BK, KB = p.ntaps * KBc;
@@ -242,7 +262,7 @@ int pack_image(const float* w, int ntaps, const int* tap_idx, long long s_tap, l
     p.s_tap = s_tap; p.s_c = s_c; p.s_n = s_n; p.Cvalid = Cvalid; p.Nvalid = Nvalid;
     p.out = reinterpret_cast<uint8_t*>(out);
     const long long total = (long long)(pack_image_bytes(ntaps, Cvalid, Nvalid) / B_STAGE) * 2048;
-    pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p, total);
+    launch_cfg((unsigned)((total + 255) / 256), 256, 0, st)(pack_kernel, p, total);
     return check_launch("pack_kernel");
 }
 
@@ -250,6 +270,7 @@ int pack_image(const float* w, int ntaps, const int* tap_idx, long long s_tap, l
 struct PackJob { PackArgs a; long long total; long long first_block; };
 
 __global__ void pack_batch_kernel(const PackJob* __restrict__ jobs, int njobs) {
+    pdl_grid_sync();
     int lo = 0, hi = njobs - 1;                         // last job whose first block is <= blockIdx.x
     while (lo < hi) {
         const int mid = (lo + hi + 1) >> 1;
@@ -260,8 +281,11 @@ __global__ void pack_batch_kernel(const PackJob* __restrict__ jobs, int njobs) {
     const long long idx = ((long long)blockIdx.x - j.first_block) * blockDim.x + threadIdx.x;
     if (idx >= j.total) return;
     const int KBc = (p.Cvalid + GEMM_BK - 1) / GEMM_BK, KB = p.ntaps * KBc;
-    const int nl = (int)(idx & 255);
-    const int chunk = (int)((idx >> 8) & 7);
+    // thread -> (row nl of the 256-row stage, 8-channel chunk): the index that is contiguous in the SOURCE runs fastest,
+    // so that a warp reads whole 128-byte lines (s_c == 1: channels are contiguous; else rows are)
+    const bool chunk_fast = p.s_c == 1;
+    const int nl = chunk_fast ? (int)((idx >> 3) & 255) : (int)(idx & 255);
+    const int chunk = chunk_fast ? (int)(idx & 7) : (int)((idx >> 8) & 7);
     const long long rest = idx >> 11;
     const int kb = (int)(rest % KB);
     const int nb = (int)(rest / KB);
@@ -269,10 +293,16 @@ __global__ void pack_batch_kernel(const PackJob* __restrict__ jobs, int njobs) {
     const int n = nb * GEMM_BN + nl;
     const int c0 = cb * GEMM_BK + chunk * 8;
     float v[8];
+    const float* src = p.w + p.tap_idx[tap] * p.s_tap + (long long)c0 * p.s_c + (long long)n * p.s_n;
+    if (chunk_fast && n < p.Nvalid && c0 + 8 <= p.Cvalid && !((reinterpret_cast<uintptr_t>(src)) & 15)) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        const int c = c0 + e;
-        v[e] = (n < p.Nvalid && c < p.Cvalid) ? p.w[p.tap_idx[tap] * p.s_tap + c * p.s_c + n * p.s_n] : 0.f;
+        for (int e = 0; e < 8; ++e) {
+            const int c = c0 + e;
+            v[e] = (n < p.Nvalid && c < p.Cvalid) ? __ldg(src + (long long)e * p.s_c) : 0.f;
+        }
     }
     uint8_t* img = p.out + ((size_t)nb * KB + kb) * B_STAGE + (size_t)(nl >> 7) * B_SLOT;
     const int nr = nl & 127;
@@ -318,11 +348,11 @@ int launch_ln_act_fwd(const float* z, long long ldz, const float* gamma, const f
     if (yo->hi && !(vec_ok(C, ldz, ldy, y_sig ? ldys : 4) && !(yo->ldp & 7)))
         return fail(OPH_EINVAL, "split-bf16 output planes need C in {256,512,1024} and 16-byte aligned rows%s");
     if (vec_ok(C, ldz, ldy, y_sig ? ldys : 4)) {
-#define OPH_LAUNCH(V) ln_act_fwd_vec_kernel<V><<<grid, 256, 0, st>>>(z, ldz, gamma, beta, y, ldy, y_sig, ldys, yo->hi, yo->lo, yo->ldp, stats, (int)rows, act, norm, drop_p, seed, step)
+#define OPH_LAUNCH(V) launch_cfg(grid, 256, 0, st)(ln_act_fwd_vec_kernel<V>, z, ldz, gamma, beta, y, ldy, y_sig, ldys, yo->hi, yo->lo, yo->ldp, stats, (int)rows, act, norm, drop_p, seed, step)
         if (C == 256) OPH_LAUNCH(2); else if (C == 512) OPH_LAUNCH(4); else OPH_LAUNCH(8);
 #undef OPH_LAUNCH
     } else {
-        ln_act_fwd_kernel<<<grid, 256, 0, st>>>(z, ldz, gamma, beta, y, ldy, y_sig, ldys, stats, (int)rows, C, act, norm, drop_p, seed, step);
+        launch_cfg(grid, 256, 0, st)(ln_act_fwd_kernel, z, ldz, gamma, beta, y, ldy, y_sig, ldys, stats, (int)rows, C, act, norm, drop_p, seed, step);
     }
     return check_launch("ln_act_fwd_kernel");
 }
@@ -345,10 +375,10 @@ int launch_ln_act_bwd(const float* dy, long long lddy, const float* z, long long
         const int grid = bwd_grid(rows);
         dz_as_planes(dz, rows, C, dzmap);
         unsigned short* h = const_cast<unsigned short*>(dzmap->hi); unsigned short* l = const_cast<unsigned short*>(dzmap->lo);
-        if (C == 256) ln_act_bwd_vec_kernel<2><<<grid, 256, smem, st>>>(dy, lddy, z, ldz, stats, gamma, beta, nullptr, 0, h, l, C, dgamma, dbeta, dbias, (int)rows, act, norm, drop_p, seed, step);
-        else          ln_act_bwd_vec_kernel<4><<<grid, 256, smem, st>>>(dy, lddy, z, ldz, stats, gamma, beta, nullptr, 0, h, l, C, dgamma, dbeta, dbias, (int)rows, act, norm, drop_p, seed, step);
+        if (C == 256) launch_cfg(grid, 256, smem, st)(ln_act_bwd_vec_kernel<2>, dy, lddy, z, ldz, stats, gamma, beta, nullptr, 0, h, l, C, dgamma, dbeta, dbias, (int)rows, act, norm, drop_p, seed, step);
+        else          launch_cfg(grid, 256, smem, st)(ln_act_bwd_vec_kernel<4>, dy, lddy, z, ldz, stats, gamma, beta, nullptr, 0, h, l, C, dgamma, dbeta, dbias, (int)rows, act, norm, drop_p, seed, step);
     } else {
-        ln_act_bwd_kernel<<<rows_grid(rows, 8), 256, smem, st>>>(dy, lddy, z, ldz, stats, gamma, beta, dz, lddz, dgamma, dbeta, dbias, (int)rows, C, act, norm, drop_p, seed, step);
+        launch_cfg(rows_grid(rows, 8), 256, smem, st)(ln_act_bwd_kernel, dy, lddy, z, ldz, stats, gamma, beta, dz, lddz, dgamma, dbeta, dbias, (int)rows, C, act, norm, drop_p, seed, step);
     }
     return check_launch("ln_act_bwd_kernel");
 }
@@ -398,7 +428,7 @@ int oph_version(void) { return 100; }
 const char* oph_last_error(void) { return g_err; }
 long long oph_launch_count(void) { return g_launches.load(); }
 int oph_gemm_debug_buffer(long long* dev_buf) { g_gemm_dbg = dev_buf; return OPH_OK; }
-int oph_gemm_debug_flags(int flags) { g_gemm_dbg_flags = flags & 0x27; g_use_tma = !(flags & 8); g_use_split = !(flags & 16);
+int oph_gemm_debug_flags(int flags) { g_gemm_dbg_flags = flags & 0xA7; g_use_tma = !(flags & 8); g_use_split = !(flags & 16); g_use_pdl = (flags & 64) != 0;
     g_hcb_depth = (flags >> 8) & 7;                    // 0 = automatic
     g_hcb_two = !(flags & 2048);
     if (g_hcb_depth == 1) g_hcb_depth = 2;
@@ -497,7 +527,7 @@ int oph_pack_plan_add(void* plan_host, int capacity, int* njobs, long long* nblo
 
 int oph_pack_run(const void* plan_dev, int njobs, long long nblocks, oph_stream_t stream) {
     if (njobs <= 0 || nblocks <= 0) return OPH_OK;
-    pack_batch_kernel<<<(unsigned)nblocks, 256, 0, S(stream)>>>(reinterpret_cast<const PackJob*>(plan_dev), njobs);
+    launch_cfg((unsigned)nblocks, 256, 0, S(stream))(pack_batch_kernel, reinterpret_cast<const PackJob*>(plan_dev), njobs);
     return check_launch("pack_batch_kernel");
 }
 
@@ -579,11 +609,11 @@ int oph_hc_fwd(const oph_act* x, const void* packed_w, const float* bias, const 
     const bool vec = vec_ok(C, ldz, x->ld, y->ld);
     if (y->hi && !(vec && !(y->ldp & 7))) return fail(OPH_EINVAL, "hc_fwd: output planes need C in {256,512,1024}%s");
     if (vec) {
-#define OPH_LAUNCH(V) hc_post_fwd_vec_kernel<V><<<grid, 256, 0, S(stream)>>>(z, ldz, x->f32, x->ld, g1, b1, g2, b2, y->f32, y->ld, y->hi, y->lo, y->ldp, stats, (int)rows, norm, drop_p, seed, step)
+#define OPH_LAUNCH(V) launch_cfg(grid, 256, 0, S(stream))(hc_post_fwd_vec_kernel<V>, z, ldz, x->f32, x->ld, g1, b1, g2, b2, y->f32, y->ld, y->hi, y->lo, y->ldp, stats, (int)rows, norm, drop_p, seed, step)
         if (C == 256) OPH_LAUNCH(2); else if (C == 512) OPH_LAUNCH(4); else OPH_LAUNCH(8);
 #undef OPH_LAUNCH
     } else {
-        hc_post_fwd_kernel<<<grid, 256, 0, S(stream)>>>(z, ldz, x->f32, x->ld, g1, b1, g2, b2, y->f32, y->ld, stats, (int)rows, C, norm, drop_p, seed, step);
+        launch_cfg(grid, 256, 0, S(stream))(hc_post_fwd_kernel, z, ldz, x->f32, x->ld, g1, b1, g2, b2, y->f32, y->ld, stats, (int)rows, C, norm, drop_p, seed, step);
     }
     return check_launch("hc_post_fwd_kernel");
 }
@@ -618,11 +648,11 @@ int oph_hc_bwd(const float* dy, long long lddy, const oph_act* x, const float* z
             cudaFuncSetAttribute(hc_post_bwd_wide_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
             attr_done = true;
         }
-#define OPH_LAUNCH(W) hc_post_bwd_wide_kernel<W><<<grid, 256, sm2, S(stream)>>>(dy, lddy, z, ldz, x->f32, x->ld, stats, g1, b1, g2, b2, h, l, 2 * C, dx, lddx, dg1, db1, dg2, db2, dbias, (int)rows, drop_p, seed, step, depth)
+#define OPH_LAUNCH(W) launch_cfg(grid, 256, sm2, S(stream))(hc_post_bwd_wide_kernel<W>, dy, lddy, z, ldz, x->f32, x->ld, stats, g1, b1, g2, b2, h, l, 2 * C, dx, lddx, dg1, db1, dg2, db2, dbias, (int)rows, drop_p, seed, step, depth)
         if (C == 256) OPH_LAUNCH(1); else if (C == 512) OPH_LAUNCH(2); else OPH_LAUNCH(4);
 #undef OPH_LAUNCH
     } else {
-        hc_post_bwd_kernel<<<rows_grid(rows, 8), 256, smem, S(stream)>>>(
+        launch_cfg(rows_grid(rows, 8), 256, smem, S(stream))(hc_post_bwd_kernel, 
             dy, lddy, z, ldz, x->f32, x->ld, stats, g1, b1, g2, b2, dz, lddz, dx, lddx, dg1, db1, dg2, db2, dbias,
             (int)rows, C, norm, drop_p, seed, step);
     }
@@ -697,11 +727,11 @@ int oph_deconv_bwd(const float* dy, long long lddy, const oph_act* x, const floa
 
 // ------------------------------------------------------------------------------------------------ embedding
 int oph_embed_fwd(const int32_t* ids, const float* table, float* out, long long ldo, int rows, int E, oph_stream_t stream) {
-    embed_fwd_kernel<<<rows_grid(rows, 8), 256, 0, S(stream)>>>(ids, table, out, ldo, rows, E);
+    launch_cfg(rows_grid(rows, 8), 256, 0, S(stream))(embed_fwd_kernel, ids, table, out, ldo, rows, E);
     return check_launch("embed_fwd_kernel");
 }
 int oph_embed_bwd(const int32_t* ids, const float* dout, long long ldo, float* dtable, int rows, int E, oph_stream_t stream) {
-    embed_bwd_kernel<<<rows_grid(rows, 8), 256, 0, S(stream)>>>(ids, dout, ldo, dtable, rows, E);
+    launch_cfg(rows_grid(rows, 8), 256, 0, S(stream))(embed_bwd_kernel, ids, dout, ldo, dtable, rows, E);
     return check_launch("embed_bwd_kernel");
 }
 
@@ -721,7 +751,7 @@ int oph_attention_fwd(const float* Q, long long ldq, const float* K, long long l
         g.C = A; g.ldc = ldA; g.alpha = 1.0f / sqrtf((float)d);
         OPH_TRY(launch_gemm(g, B, S(stream)));
     }
-    softmax_fwd_kernel<<<rows_grid((long long)B * T, 8), 256, 0, S(stream)>>>(A, ldA, B, T, N, prev_max, win, align_t,
+    launch_cfg(rows_grid((long long)B * T, 8), 256, 0, S(stream))(softmax_fwd_kernel, A, ldA, B, T, N, prev_max, win, align_t,
                                                                             argmax, att_acc, maxN, maxT, g_);
     OPH_TRY(check_launch("softmax_fwd_kernel"));
     {   // R = A V
@@ -763,7 +793,7 @@ int oph_attention_bwd(const float* dR, long long lddr, const float* Q, long long
         g.C = dA; g.ldc = ldA;
         OPH_TRY(launch_gemm(g, B, S(stream)));
     }
-    softmax_bwd_kernel<<<rows_grid((long long)B * T, 8), 256, 0, S(stream)>>>(A, ldA, dA, ldA, B, T, N, att_coef, maxN, maxT, g_);
+    launch_cfg(rows_grid((long long)B * T, 8), 256, 0, S(stream))(softmax_bwd_kernel, A, ldA, dA, ldA, B, T, N, att_coef, maxN, maxT, g_);
     OPH_TRY(check_launch("softmax_bwd_kernel"));
     {   // dQ = dS K / sqrt(d) (+ direct path)
         GemmArgs g = blank();
@@ -796,27 +826,27 @@ int oph_attention_bwd(const float* dR, long long lddr, const float* Q, long long
 int oph_recon_loss(const float* logits, long long ldl, const float* target, long long ldt, float* dlogits,
                    long long ldd, long long rows, int C, int squash, float w_l1, float w_bd, float w_l2,
                    double* acc, oph_stream_t stream) {
-    recon_loss_kernel<<<rows_grid(rows, 8), 256, 0, S(stream)>>>(logits, ldl, target, ldt, dlogits, ldd, rows, C, squash,
+    launch_cfg(rows_grid(rows, 8), 256, 0, S(stream))(recon_loss_kernel, logits, ldl, target, ldt, dlogits, ldd, rows, C, squash,
                                                                 w_l1, w_bd, w_l2, acc);
     return check_launch("recon_loss_kernel");
 }
 int oph_loss_finalize(const double* acc, float* out, double n_recon, double n_att, float w_l1, float w_bd,
                       float w_att, float w_l2, int has_att, int squash, oph_stream_t stream) {
-    loss_finalize_kernel<<<1, 1, 0, S(stream)>>>(acc, out, n_recon, n_att, w_l1, w_bd, w_att, w_l2, has_att, squash);
+    launch_cfg(1, 1, 0, S(stream))(loss_finalize_kernel, acc, out, n_recon, n_att, w_l1, w_bd, w_att, w_l2, has_att, squash);
     return check_launch("loss_finalize_kernel");
 }
 int oph_adam_prepare(const long long* global_step, float* lr_t, float lr0, float beta1, float beta2, int decay_lr,
                      float warmup, oph_stream_t stream) {
-    adam_prepare_kernel<<<1, 1, 0, S(stream)>>>(global_step, lr_t, lr0, beta1, beta2, decay_lr, warmup);
+    launch_cfg(1, 1, 0, S(stream))(adam_prepare_kernel, global_step, lr_t, lr0, beta1, beta2, decay_lr, warmup);
     return check_launch("adam_prepare_kernel");
 }
 int oph_adam_clip(float* p, float* m, float* v, const float* g, long long n, const float* lr_t, float beta1,
                   float beta2, float eps, float clip, float grad_scale, oph_stream_t stream) {
-    adam_clip_kernel<<<148 * 4, 256, 0, S(stream)>>>(p, m, v, g, n, lr_t, beta1, beta2, eps, clip, grad_scale);
+    launch_cfg(148 * 4, 256, 0, S(stream))(adam_clip_kernel, p, m, v, g, n, lr_t, beta1, beta2, eps, clip, grad_scale);
     return check_launch("adam_clip_kernel");
 }
 int oph_step_inc(long long* global_step, oph_stream_t stream) {
-    step_inc_kernel<<<1, 1, 0, S(stream)>>>(global_step);
+    launch_cfg(1, 1, 0, S(stream))(step_inc_kernel, global_step);
     return check_launch("step_inc_kernel");
 }
 

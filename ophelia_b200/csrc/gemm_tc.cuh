@@ -234,7 +234,7 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
     // accumulators instead (4 x more epilogue warps, the dedicated epilogue warps then idle)
     const bool copy_fed = (p.a_tma && packed) || p.r_tma;
     const bool rotate = p.a_tma && packed && !(p.dbg_flags & 4);
-    const bool nofix = (p.dbg_flags & 32) != 0;        // diagnostics: skip the item-boundary fix-up (wrong results)
+    const bool nofix = (p.dbg_flags & (32 | 128)) != 0;        // diagnostics: skip the item-boundary fix-up (wrong results)
 
     if (tid == 0) {
         for (int i = 0; i < NA_SLOTS; ++i) {
@@ -257,6 +257,9 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // the prologue above overlapped the predecessor kernel's tail; its results are visible from here on
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
 
     // ================================================================ epilogue worker: TMEM -> global
@@ -590,6 +593,11 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
                         mbar_wait(BAR(BAR_EMPTY_A + as), a_par);
                         const uint32_t dst = smem_u32(sA + as * A_SLOT);
                         const int off = p.A.off[tap];
+                        if (p.dbg_flags & 128) {               // diagnostics: no A traffic at all
+                            if (crank == 0) { mbar_arrive(BAR(BAR_FULL_A + as)); mbar_arrive(BAR(BAR_FULL_A + as)); mbar_arrive(BAR(BAR_FULL_A + as)); }
+                            if (++as == NA_SLOTS) { as = 0; a_par ^= 1; }
+                            goto b_part;
+                        }
                         const bool fix_me = !nofix && needs_fix(t.m0, off, p.A.L);
                         if (crank == 0) {                      // bytes that will be signalled straight on FULL_A
                             const bool fix_peer = !nofix && needs_fix(t.m0 + GEMM_BM, off, p.A.L);
@@ -608,6 +616,7 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
                         }
                         if (++as == NA_SLOTS) { as = 0; a_par ^= 1; }
                     }
+                    b_part:
                     if (!packed) continue;
                     mbar_wait(BAR(BAR_EMPTY_B + slot), par);
                     if (p.dbg_flags & 2) { if (crank == 0) mbar_arrive(BAR(BAR_FULL_B + slot)); }

@@ -11,6 +11,13 @@ namespace oph {
 constexpr float LN_EPS = 1e-12f;                 // tf.contrib.layers.layer_norm (modules.py:65)
 constexpr float ATT_MASK_VALUE = -4294967295.0f; // -2**32+1 (networks.py:312)
 
+// Programmatic dependent launch: wait for the predecessor kernel of the stream (memory visible afterwards), then
+// allow the successor's blocks to become resident early.  A no-op for launches without the PDL attribute.
+__device__ __forceinline__ void pdl_grid_sync() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -51,6 +58,7 @@ __global__ void ln_act_fwd_kernel(const float* __restrict__ z, long long ldz, co
                                   float* __restrict__ y_sig, long long ldys, float* __restrict__ stats,
                                   int rows, int C, int act, int norm, float drop_p, unsigned long long seed,
                                   const long long* step) {
+    pdl_grid_sync();
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
     const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
@@ -77,6 +85,7 @@ __global__ void hc_post_fwd_kernel(const float* __restrict__ z, long long ldz, c
                                    const float* __restrict__ g2, const float* __restrict__ b2,
                                    float* __restrict__ y, long long ldy, float* __restrict__ stats,
                                    int rows, int C, int norm, float drop_p, unsigned long long seed, const long long* step) {
+    pdl_grid_sync();
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
     const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
@@ -111,6 +120,7 @@ __global__ void ln_act_bwd_kernel(const float* __restrict__ dy, long long lddy, 
                                   float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias,
                                   int rows, int C, int act, int norm, float drop_p, unsigned long long seed,
                                   const long long* step) {
+    pdl_grid_sync();
     extern __shared__ float sacc[];            // [3][C]: dgamma, dbeta, dbias
     for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) sacc[i] = 0.f;
     __syncthreads();
@@ -169,6 +179,7 @@ __global__ void hc_post_bwd_kernel(const float* __restrict__ dy, long long lddy,
                                    float* __restrict__ dg1, float* __restrict__ db1, float* __restrict__ dg2,
                                    float* __restrict__ db2, float* __restrict__ dbias,
                                    int rows, int C, int norm, float drop_p, unsigned long long seed, const long long* step) {
+    pdl_grid_sync();
     extern __shared__ float sacc[];            // [6][C]: dg1, db1, dg2, db2, dbias(H1), dbias(H2)
     for (int i = threadIdx.x; i < 6 * C; i += blockDim.x) sacc[i] = 0.f;
     __syncthreads();
@@ -242,6 +253,7 @@ __global__ void softmax_fwd_kernel(float* __restrict__ S, long long ldS, int B, 
                                    const int* __restrict__ prev_max, int win,
                                    float* __restrict__ align_t, int* __restrict__ argmax_out,
                                    double* __restrict__ att_acc, int maxN, int maxT, float g) {
+    pdl_grid_sync();
     const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
     const float inv_maxN = 1.f / (float)maxN, inv_maxT = 1.f / (float)maxT, inv_2g2 = 1.f / (2.f * g * g);
     float att_part = 0.f;
@@ -295,6 +307,7 @@ __global__ void softmax_fwd_kernel(float* __restrict__ S, long long ldS, int B, 
 // dA (in) -> dS (in place):  dS = A * (dA' - sum_n A*dA'),  dA' = dA + att_coef * W[n][t]
 __global__ void softmax_bwd_kernel(const float* __restrict__ A, long long ldA, float* __restrict__ dA, long long lddA,
                                    int B, int T, int N, float att_coef, int maxN, int maxT, float g) {
+    pdl_grid_sync();
     const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
     const float inv_maxN = 1.f / (float)maxN, inv_maxT = 1.f / (float)maxT, inv_2g2 = 1.f / (2.f * g * g);
     const long long rows = (long long)B * T;
@@ -318,6 +331,7 @@ __global__ void softmax_bwd_kernel(const float* __restrict__ A, long long ldA, f
 // modules.py:38-42: row 0 of the table reads as zeros and receives no gradient.
 __global__ void embed_fwd_kernel(const int* __restrict__ ids, const float* __restrict__ table, float* __restrict__ out,
                                  long long ldo, int rows, int E) {
+    pdl_grid_sync();
     const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
     for (long long row = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * wpb) {
         const int id = ids[row];
@@ -326,6 +340,7 @@ __global__ void embed_fwd_kernel(const int* __restrict__ ids, const float* __res
 }
 __global__ void embed_bwd_kernel(const int* __restrict__ ids, const float* __restrict__ dout, long long ldo,
                                  float* __restrict__ dtable, int rows, int E) {
+    pdl_grid_sync();
     const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
     for (long long row = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * wpb) {
         const int id = ids[row];
@@ -341,6 +356,7 @@ __global__ void recon_loss_kernel(const float* __restrict__ logits, long long ld
                                   long long ldt, float* __restrict__ dlogits, long long ldd,
                                   long long rows, int C, int squash, float w_l1, float w_bd, float w_l2,
                                   double* __restrict__ acc) {
+    pdl_grid_sync();
     const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
     const float inv_n = 1.f / ((float)rows * (float)C);
     float s1 = 0.f, sb = 0.f, s2 = 0.f;
@@ -375,6 +391,7 @@ __global__ void recon_loss_kernel(const float* __restrict__ logits, long long ld
 // loss_components (architectures.py:173, :352-355): out = [loss, L1, BD, (att,) L2]
 __global__ void loss_finalize_kernel(const double* __restrict__ acc, float* __restrict__ out, double n_recon, double n_att,
                                      float w_l1, float w_bd, float w_att, float w_l2, int has_att, int squash) {
+    pdl_grid_sync();
     const double l1 = acc[0] / n_recon, bd = squash ? acc[1] / n_recon : 0.0, l2 = acc[2] / n_recon;
     const double att = has_att ? acc[3] / n_att : 0.0;
     const double loss = w_l1 * l1 + w_bd * bd + w_att * att + w_l2 * l2;
@@ -386,18 +403,21 @@ __global__ void loss_finalize_kernel(const double* __restrict__ acc, float* __re
 // architectures.py:101-128 + utils.py:167-170: Noam lr on step+1, TF Adam bias correction folded into lr_t.
 __global__ void adam_prepare_kernel(const long long* __restrict__ global_step, float* __restrict__ lr_t, float lr0,
                                     float beta1, float beta2, int decay_lr, float warmup) {
+    pdl_grid_sync();
     const double t = (double)(*global_step + 1);
     double lr = lr0;
     if (decay_lr) lr = (double)lr0 * sqrt((double)warmup) * fmin(t * pow((double)warmup, -1.5), 1.0 / sqrt(t));
     lr_t[0] = (float)(lr * sqrt(1.0 - pow((double)beta2, t)) / (1.0 - pow((double)beta1, t)));
     lr_t[1] = (float)lr;
 }
-__global__ void step_inc_kernel(long long* global_step) { *global_step += 1; }
+__global__ void step_inc_kernel(long long* global_step) {
+    pdl_grid_sync(); *global_step += 1; }
 
 // clip_by_value(g*grad_scale, +-clip) -> m,v update -> theta -= lr_t * m / (sqrt(v) + eps)   (TF epsilon placement)
 __global__ void adam_clip_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
                                  const float* __restrict__ g, long long n, const float* __restrict__ lr_t,
                                  float beta1, float beta2, float eps, float clip, float grad_scale) {
+    pdl_grid_sync();
     const float lr = lr_t[0];
     const long long n4 = n >> 2;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
@@ -487,6 +507,7 @@ __global__ void __launch_bounds__(256) hc_post_fwd_vec_kernel(
         const float* __restrict__ b2, float* __restrict__ y, long long ldy, unsigned short* __restrict__ y_hi,
         unsigned short* __restrict__ y_lo, long long ldp, float* __restrict__ stats,
         int rows, int norm, float drop_p, unsigned long long seed, const long long* step) {
+    pdl_grid_sync();
     constexpr int C = 128 * VEC;
     const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
     const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
@@ -526,6 +547,7 @@ __global__ void __launch_bounds__(256) ln_act_fwd_vec_kernel(
         float* __restrict__ y, long long ldy, float* __restrict__ y_sig, long long ldys,
         unsigned short* __restrict__ y_hi, unsigned short* __restrict__ y_lo, long long ldp, float* __restrict__ stats,
         int rows, int act, int norm, float drop_p, unsigned long long seed, const long long* step) {
+    pdl_grid_sync();
     constexpr int C = 128 * VEC;
     const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
     const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
@@ -581,6 +603,7 @@ __global__ void __launch_bounds__(256) hc_post_bwd_vec_kernel(
         unsigned short* __restrict__ dz_lo, long long ldp, float* __restrict__ dxres, long long lddx,
         float* __restrict__ dg1, float* __restrict__ db1, float* __restrict__ dg2, float* __restrict__ db2,
         float* __restrict__ dbias, int rows, int norm, float drop_p, unsigned long long seed, const long long* step) {
+    pdl_grid_sync();
     constexpr int C = 128 * VEC;
     extern __shared__ float sacc[];            // [6][C]
     for (int i = threadIdx.x; i < 6 * C; i += blockDim.x) sacc[i] = 0.f;
@@ -666,6 +689,7 @@ __global__ void __launch_bounds__(256) ln_act_bwd_vec_kernel(
         long long ldp, float* __restrict__ dgamma, float* __restrict__ dbeta,
         float* __restrict__ dbias, int rows, int act, int norm, float drop_p, unsigned long long seed,
         const long long* step) {
+    pdl_grid_sync();
     constexpr int C = 128 * VEC;
     extern __shared__ float sacc[];            // [3][C]
     for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) sacc[i] = 0.f;
@@ -749,6 +773,7 @@ __global__ void __launch_bounds__(256) hc_post_bwd_wide_kernel(
         long long ldp, float* __restrict__ dxres, long long lddx,
         float* __restrict__ dg1, float* __restrict__ db1, float* __restrict__ dg2, float* __restrict__ db2,
         float* __restrict__ dbias, int rows, float drop_p, unsigned long long seed, const long long* step, int depth) {
+    pdl_grid_sync();
     constexpr int C = 256 * WPR;
     constexpr int GROUPS = 8 / WPR;                      // rows in flight per block
     extern __shared__ __align__(16) float smem_f[];

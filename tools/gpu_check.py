@@ -323,6 +323,60 @@ def case_loss_adam():
     report("global_step", abs(int(step.item()) - 3), 0)
 
 
+def case_pack_batch():
+    """One-launch re-pack (oph_pack_plan_add / oph_pack_run) must reproduce oph_conv_pack bit for bit."""
+    import ctypes
+    from ophelia_b200 import _lib
+    lib = _lib.load()
+    ws = [(torch.randn(3, 256, 512, device=dev), False), (torch.randn(1, 80, 256, device=dev), False),
+          (torch.randn(1, 513, 513, device=dev), False), (torch.randn(1, 3, 512, 512, device=dev), True)]
+    pks = [ops.PackedConv(w, deconv=d) for w, d in ws]
+    ref = [(pk.fwd.clone(), pk.bwd.clone()) for pk in pks]
+    for pk in pks:
+        pk.fwd.zero_(); pk.bwd.zero_()
+    jb = int(lib.oph_pack_job_bytes())
+    host = ctypes.create_string_buffer(3 * len(pks) * jb)
+    nj, nb = ctypes.c_int(0), ctypes.c_longlong(0)
+    for pk in pks:
+        _lib.call("oph_pack_plan_add", ctypes.cast(host, ctypes.c_void_p), 3 * len(pks), ctypes.byref(nj), ctypes.byref(nb),
+                  pk.w.data_ptr(), pk.k, pk.cin, pk.cout, int(pk.deconv), pk.fwd.data_ptr(), pk.bwd.data_ptr())
+    plan = torch.frombuffer(bytearray(host.raw[:nj.value * jb]), dtype=torch.uint8).to(dev)
+    _lib.call("oph_pack_run", plan.data_ptr(), nj.value, nb.value, torch.cuda.current_stream().cuda_stream)
+    bad = sum(int((pk.fwd != r[0]).sum()) + int((pk.bwd != r[1]).sum()) for pk, r in zip(pks, ref))
+    report("pack_run == conv_pack (mismatching bytes, %d jobs)" % nj.value, float(bad), 0)
+
+
+def case_dropout():
+    """Dropout (modules.py:141,205): element-wise keep-prob 1-rate, kept values scaled by 1/(1-rate), the backward
+    pass re-creates the same mask from (seed, global_step, element index)."""
+    B, L, C, rate = 4, 300, 256, 0.05
+    P = conv_params("h", 3, C, 2 * C, hc=True)
+    w = f32(P["h/conv1d/kernel"]); pk = ops.PackedConv(w)
+    prm = [f32(P[n]) for n in ("h/conv1d/bias", "h/H1/gamma", "h/H1/beta", "h/H2/gamma", "h/H2/beta")]
+    x = f32(rnd(B, L, C))
+    step = torch.full((1,), 7, dtype=torch.int64, device=dev)
+    y0, _ = ops.hc_fwd(x, pk, *prm, rate=3, padding=1, norm=True)
+    y1, saved = ops.hc_fwd(x, pk, *prm, rate=3, padding=1, norm=True, drop_p=rate, seed=1234, step=step, save=True)
+    y2, _ = ops.hc_fwd(x, pk, *prm, rate=3, padding=1, norm=True, drop_p=rate, seed=1234, step=step)
+    step2 = torch.full((1,), 8, dtype=torch.int64, device=dev)
+    y3, _ = ops.hc_fwd(x, pk, *prm, rate=3, padding=1, norm=True, drop_p=rate, seed=1234, step=step2)
+    keep = (y1 != 0)
+    frac = float(keep.float().mean())
+    report("dropout keep fraction (rate %.2f)" % rate, abs(frac - (1 - rate)), 4 * (rate * (1 - rate) / keep.numel()) ** 0.5 + 1e-4)
+    report("dropout scale 1/(1-rate)", maxerr(y1[keep], y0[keep] / (1 - rate)), 1e-5)
+    report("dropout mask repeatable for one step", float((y1 != y2).sum()), 0)
+    report("dropout mask changes with global_step (same fraction kept)", abs(float(((y3 != 0) == keep).float().mean()) - (1 - 2 * rate * (1 - rate))), 5e-3)
+    # backward uses the same mask: dx(dropout) == dx(no dropout, dy * mask / (1-rate))
+    dy = f32(rnd(B, L, C))
+    g = [torch.zeros_like(t) for t in [w] + prm]
+    dx1 = ops.hc_bwd(dy, x, saved, pk, *prm[1:], g[0], g[1], g[2], g[3], g[4], g[5], 3, 1, True, drop_p=rate, seed=1234, step=step)
+    g2 = [torch.zeros_like(t) for t in [w] + prm]
+    dym = (dy * keep.float() / (1 - rate)).contiguous()
+    dx0 = ops.hc_bwd(dym, x, saved, pk, *prm[1:], g2[0], g2[1], g2[2], g2[3], g2[4], g2[5], 3, 1, True)
+    report("dropout backward mask == forward mask (dx)", maxerr(dx1, dx0), 1e-5)
+    report("dropout backward mask == forward mask (dw)", maxerr(g[0], g2[0]), 1e-3)
+
+
 def perf():
     """First timing of the dominant layer shape (AudioEnc/AudioDec highway conv at B=32, T=870, C=256)."""
     for (B, L, C, k) in [(32, 870, 256, 3), (32, 180, 512, 3), (64, 870, 256, 3)]:
@@ -369,7 +423,7 @@ GROUPS = {
     "deconv": [case_deconv(2, 50, 512), case_deconv(1, 131, 256)],
     "attention": [case_attention(2, 200, 60, False), case_attention(2, 210, 180, True),
                   case_attention(3, 130, 47, False)],
-    "misc": [case_embed, case_loss_adam],
+    "misc": [case_embed, case_loss_adam, case_pack_batch, case_dropout],
 }
 
 
