@@ -153,17 +153,21 @@ int oph_embed_bwd(const int32_t* ids, const float* dout, long long ldo, float* d
  * forcibly-incremental window: keys outside [prev, prev+win) get -2^32+1 (networks.py:304-313).
  * align_t (nullable) = alignments [B][N][T]; argmax (nullable) int32 [B][T] (first maximum);
  * att_acc (nullable, device double) += sum A*W over n<maxN, t<maxT with the analytic guide (utils.py:155-161). */
-int oph_attention_fwd(const float* Q, long long ldq, const float* K, long long ldk, const float* V, long long ldv,
-                      float* A, long long ldA, float* R, long long ldr, float* align_t, int32_t* argmax,
-                      const int32_t* prev_max, int win, double* att_acc, int maxN, int maxT, float g, int B, int T,
-                      int N, int d, oph_stream_t stream);
-/* dR [B][T][lddr].  dA [B][T][ldA] scratch.  dq_addend (nullable) is added into dQ (the direct [R,Q] concat path).
- * att_coef = lw_att / (B*min(N,maxN)*min(T,maxT)) injects the guided-attention gradient. */
-int oph_attention_bwd(const float* dR, long long lddr, const float* Q, long long ldq, const float* K, long long ldk,
-                      const float* V, long long ldv, const float* A, long long ldA, float* dA, float* dQ,
-                      long long lddq, const float* dq_addend, long long ldqa, float* dK, long long lddk, float* dV,
-                      long long lddv, float att_coef, int maxN, int maxT, float g, int B, int T, int N, int d,
-                      oph_stream_t stream);
+/* Q, K, V, A (probabilities; f32 is written, planes are written when given) are activations per batch item.  When every
+ * operand carries split-bf16 planes (contiguous items: item z starts z*rows*ldp elements in), both products are fed by
+ * the copy engines; otherwise the producer warps convert the fp32 views. */
+int oph_attention_fwd(const oph_act* Q, const oph_act* K, const oph_act* V, const oph_act* A, float* R, long long ldr,
+                      float* align_t, int32_t* argmax, const int32_t* prev_max, int win, double* att_acc, int maxN,
+                      int maxT, float g, int B, int T, int N, int d, oph_stream_t stream);
+/* dR [B][T].  dA [B][T][ldA] scratch (f32 + optional planes for dS).  dq_addend (nullable) is added into dQ (the direct
+ * [R,Q] concat path).  att_coef = lw_att / (B*min(N,maxN)*min(T,maxT)) injects the guided-attention gradient. */
+int oph_attention_bwd(const oph_act* dR, const oph_act* Q, const oph_act* K, const oph_act* V, const oph_act* A,
+                      const oph_act* dA, float* dQ, long long lddq, const float* dq_addend, long long ldqa, float* dK,
+                      long long lddk, float* dV, long long lddv, float att_coef, int maxN, int maxT, float g, int B,
+                      int T, int N, int d, oph_stream_t stream);
+/* fp32 rows -> split-bf16 planes for operands that do not come out of a row-wise kernel of this library. */
+int oph_split_planes(const float* x, long long ldx, long long rows, int C, unsigned short* hi, unsigned short* lo,
+                     long long ldp, oph_stream_t stream);
 
 /* ---- losses (architectures.py:147-173, 245-355) ------------------------------------------------------------
  * acc: device double[4] zeroed by the caller: sum|Y-t|, sum BCE, sum (Y-t)^2, (attention sum).

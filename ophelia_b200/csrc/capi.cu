@@ -138,19 +138,47 @@ int launch_gemm(GemmArgs& a, int zdim, cudaStream_t st) {
     if (a.M <= 0 || a.N <= 0 || a.Kc <= 0) return fail(OPH_EINVAL, "gemm: empty problem%s");
     if ((a.A.ld & (a.A.hi ? 7 : 3)) || (a.b_mode != B_PACKED && (a.Bm.ld & (a.Bm.hi ? 7 : 3))))
         return fail(OPH_EINVAL, "gemm: row strides must be multiples of 4 (fp32) / 8 (bf16 planes)%s");
-    if ((a.A.hi && a.a_mode == A_KMAJOR && (a.Kc & 7)) || (a.A.hi && a.a_mode == A_MNMAJOR && (a.M & 7)) ||
-        (a.Bm.hi && a.b_mode == B_KMAJOR && (a.Kc & 7)) || (a.Bm.hi && a.b_mode == B_MNMAJOR && (a.N & 7)))
-        return fail(OPH_EINVAL, "gemm: plane operands need channel counts that are multiples of 8%s");
     if (a.ytaps < 1) a.ytaps = 1;
     a.zdim = zdim < 1 ? 1 : zdim;
-    // conv-style A already split into planes: feed it with TMA tensor copies (per-item tiles, padding = out-of-range)
-    a.a_tma = 0; if (!a.r_tma) a.items = 1;
+    // conv-style A already split into planes: feed it with TMA tensor copies (flat tiles, padding = out-of-range / fix-up)
+    a.a_tma = 0; a.b_tma = 0; if (!a.r_tma) a.items = 1;
     if (g_use_tma && a.a_mode == A_KMAJOR && a.A.hi && a.A.mul == 1 && a.A.L == a.A.Ls && a.z_mode == Z_NONE &&
         !(a.Kc & 63) && a.M % a.A.L == 0) {
         if (make_plane_tmap2d(&a.tmA_hi, a.A.hi, a.Kc, a.M, a.A.ld) && make_plane_tmap2d(&a.tmA_lo, a.A.lo, a.Kc, a.M, a.A.ld)) {
             a.a_tma = 1; a.items = a.M / a.A.L;
         }
     }
+    // batched activation x activation products (attention) with both operands as planes: every tile comes from the copy
+    // engines; the planes of item z start z * rows * ld elements after those of item 0 (contiguous items)
+    if (g_use_tma && a.z_mode == Z_BATCH && a.A.hi && a.Bm.hi && !a.r_tma && a.ytaps == 1 && a.ntaps == 1) {
+        if (a.a_mode == A_KMAJOR) {
+            bool ok = make_plane_tmap(&a.tmA_hi, a.A.hi, a.Kc, a.M, a.zdim, a.A.ld, GEMM_BM) &&
+                      make_plane_tmap(&a.tmA_lo, a.A.lo, a.Kc, a.M, a.zdim, a.A.ld, GEMM_BM);
+            if (ok && a.b_mode == B_KMAJOR) {
+                ok = make_plane_tmap(&a.tmB_hi, a.Bm.hi, a.Kc, a.N, a.zdim, a.Bm.ld, GEMM_BM) &&
+                     make_plane_tmap(&a.tmB_lo, a.Bm.lo, a.Kc, a.N, a.zdim, a.Bm.ld, GEMM_BM);
+                if (ok) { a.a_tma = 2; a.b_tma = 2; }
+            } else if (ok && a.b_mode == B_MNMAJOR) {
+                ok = make_plane_tmap(&a.tmB_hi, a.Bm.hi, a.N, a.Kc, a.zdim, a.Bm.ld, GEMM_BK) &&
+                     make_plane_tmap(&a.tmB_lo, a.Bm.lo, a.N, a.Kc, a.zdim, a.Bm.ld, GEMM_BK);
+                if (ok) { a.a_tma = 2; a.b_tma = 3; }
+            }
+        } else if (a.a_mode == A_MNMAJOR && a.b_mode == B_MNMAJOR) {
+            const int R = a.Kc;                                            // reduction steps per item
+            if (make_plane_tmap(&a.tmA_hi, a.A.hi, a.M, R, a.zdim, a.A.ld, GEMM_BK) && make_plane_tmap(&a.tmA_lo, a.A.lo, a.M, R, a.zdim, a.A.ld, GEMM_BK) &&
+                make_plane_tmap(&a.tmB_hi, a.Bm.hi, a.N, R, a.zdim, a.Bm.ld, GEMM_BK) && make_plane_tmap(&a.tmB_lo, a.Bm.lo, a.N, R, a.zdim, a.Bm.ld, GEMM_BK)) {
+                a.r_tma = 1; a.items = a.zdim; a.prof_k = R; a.Kc = cdiv(R, GEMM_BK);   // Kc now counts k-blocks
+                a.A.off[0] = a.Bm.off[0] = 0;
+            }
+        }
+    }
+    // operands that still go through the producer warps as planes are copied in 16-byte chunks
+    const bool a_prod = !a.a_tma && !a.r_tma, b_prod = a.b_mode != B_PACKED && !a.b_tma && !a.r_tma;
+    if ((a_prod && a.A.hi && a.a_mode == A_KMAJOR && (a.Kc & 7)) || (a_prod && a.A.hi && a.a_mode == A_MNMAJOR && (a.M & 7)) ||
+        (b_prod && a.Bm.hi && a.b_mode == B_KMAJOR && (a.Kc & 7)) || (b_prod && a.Bm.hi && a.b_mode == B_MNMAJOR && (a.N & 7)))
+        return fail(OPH_EINVAL, "gemm: plane operands need channel counts that are multiples of 8%s");
+    if ((a_prod && !a.A.hi && !a.A.ptr) || (b_prod && !a.Bm.hi && !a.Bm.ptr))
+        return fail(OPH_EINVAL, "gemm: an operand has neither an fp32 view nor usable planes%s");
     if (a.b_mode == B_PACKED) {   // packed weight image as 128-byte rows: one 256-row box = one CTA's half of a stage
         const size_t rows = (size_t)cdiv(a.N, GEMM_BN) * a.ntaps * cdiv(a.Kc, GEMM_BK) * (B_STAGE / 128);
         EncodeTiledFn fn = encode_tiled_fn();
@@ -736,72 +764,92 @@ int oph_embed_bwd(const int32_t* ids, const float* dout, long long ldo, float* d
 }
 
 // ------------------------------------------------------------------------------------------------ attention
-int oph_attention_fwd(const float* Q, long long ldq, const float* K, long long ldk, const float* V, long long ldv,
-                      float* A, long long ldA, float* R, long long ldr, float* align_t, int32_t* argmax,
-                      const int32_t* prev_max, int win, double* att_acc, int maxN, int maxT, float g_, int B, int T,
-                      int N, int d, oph_stream_t stream) {
+static bool planes_ready(const oph_act* a) { return a && a->hi && a->lo && !(a->ldp & 7) && !(reinterpret_cast<uintptr_t>(a->hi) & 15) && !(reinterpret_cast<uintptr_t>(a->lo) & 15); }
+// operand of a batched product: planes [items][rows][ldp] (contiguous items) when `planes`, else the fp32 view
+static void att_operand(OperandMap& m, const oph_act* a, bool planes, int rows) {
+    m.L = m.Ls = rows; m.mul = 1;
+    if (planes) { m.hi = a->hi; m.lo = a->lo; m.ld = a->ldp; m.ptr = nullptr; }
+    else { m.hi = m.lo = nullptr; m.ptr = a->f32; m.ld = a->ld; }
+}
+
+int oph_split_planes(const float* x, long long ldx, long long rows, int C, unsigned short* hi, unsigned short* lo,
+                     long long ldp, oph_stream_t stream) {
+    launch_cfg(rows_grid(rows, 8), 256, 0, S(stream))(split_planes_kernel, x, ldx, rows, C, hi, lo, ldp);
+    return check_launch("split_planes_kernel");
+}
+
+int oph_attention_fwd(const oph_act* Q, const oph_act* K, const oph_act* V, const oph_act* A, float* R, long long ldr,
+                      float* align_t, int32_t* argmax, const int32_t* prev_max, int win, double* att_acc, int maxN,
+                      int maxT, float g_, int B, int T, int N, int d, oph_stream_t stream) {
+    if (!Q || !K || !V || !A || !A->f32) return fail(OPH_EINVAL, "attention_fwd: missing operand%s");
+    const long long ldA = A->ld;
     if (ldA < N) return fail(OPH_EINVAL, "attention_fwd: ldA < N%s");
+    // all operands as split-bf16 planes: every tile of both products arrives through the copy engines
+    const bool fed = g_use_tma && planes_ready(Q) && planes_ready(K) && planes_ready(V) && planes_ready(A);
+    if (!fed && (!Q->f32 || !K->f32 || !V->f32)) return fail(OPH_EINVAL, "attention_fwd: operands need fp32 views or planes%s");
     {   // S = Q K^T / sqrt(d)
         GemmArgs g = blank();
         g.a_mode = A_KMAJOR; g.b_mode = B_KMAJOR;
-        g.A.ptr = Q; g.A.ld = ldq; g.A.L = T; g.A.Ls = T;
-        g.Bm.ptr = K; g.Bm.ld = ldk;
+        att_operand(g.A, Q, fed, T); att_operand(g.Bm, K, fed, N);
         g.M = T; g.N = N; g.Kc = d;
-        g.tag = OPH_TAG_ATTENTION; g.z_mode = Z_BATCH; g.a_zs = (long long)T * ldq; g.b_zs = (long long)N * ldk; g.c_zs = (long long)T * ldA;
-        g.C = A; g.ldc = ldA; g.alpha = 1.0f / sqrtf((float)d);
+        g.tag = OPH_TAG_ATTENTION; g.z_mode = Z_BATCH; g.a_zs = (long long)T * Q->ld; g.b_zs = (long long)N * K->ld; g.c_zs = (long long)T * ldA;
+        g.C = A->f32; g.ldc = ldA; g.alpha = 1.0f / sqrtf((float)d);
         OPH_TRY(launch_gemm(g, B, S(stream)));
     }
-    launch_cfg(rows_grid((long long)B * T, 8), 256, 0, S(stream))(softmax_fwd_kernel, A, ldA, B, T, N, prev_max, win, align_t,
-                                                                            argmax, att_acc, maxN, maxT, g_);
+    launch_cfg(rows_grid((long long)B * T, 8), 256, 0, S(stream))(softmax_fwd_kernel, A->f32, ldA, B, T, N, prev_max, win, align_t,
+                                                                 argmax, att_acc, maxN, maxT, g_, fed ? A->hi : nullptr,
+                                                                 fed ? A->lo : nullptr, A->ldp);
     OPH_TRY(check_launch("softmax_fwd_kernel"));
     {   // R = A V
         GemmArgs g = blank();
         g.a_mode = A_KMAJOR; g.b_mode = B_MNMAJOR;
-        g.A.ptr = A; g.A.ld = ldA; g.A.L = T; g.A.Ls = T;
-        g.Bm.ptr = V; g.Bm.ld = ldv; g.Bm.L = N; g.Bm.Ls = N;
+        att_operand(g.A, A, fed, T); att_operand(g.Bm, V, fed, N);
         g.M = T; g.N = d; g.Kc = N;
-        g.tag = OPH_TAG_ATTENTION; g.z_mode = Z_BATCH; g.a_zs = (long long)T * ldA; g.b_zs = (long long)N * ldv; g.c_zs = (long long)T * ldr;
+        g.tag = OPH_TAG_ATTENTION; g.z_mode = Z_BATCH; g.a_zs = (long long)T * ldA; g.b_zs = (long long)N * V->ld; g.c_zs = (long long)T * ldr;
         g.C = R; g.ldc = ldr;
         OPH_TRY(launch_gemm(g, B, S(stream)));
     }
     return OPH_OK;
 }
 
-int oph_attention_bwd(const float* dR, long long lddr, const float* Q, long long ldq, const float* K, long long ldk,
-                      const float* V, long long ldv, const float* A, long long ldA, float* dA, float* dQ,
-                      long long lddq, const float* dq_addend, long long ldqa, float* dK, long long lddk, float* dV,
-                      long long lddv, float att_coef, int maxN, int maxT, float g_, int B, int T, int N, int d,
-                      oph_stream_t stream) {
+int oph_attention_bwd(const oph_act* dR, const oph_act* Q, const oph_act* K, const oph_act* V, const oph_act* A,
+                      const oph_act* dA, float* dQ, long long lddq, const float* dq_addend, long long ldqa, float* dK,
+                      long long lddk, float* dV, long long lddv, float att_coef, int maxN, int maxT, float g_, int B,
+                      int T, int N, int d, oph_stream_t stream) {
+    if (!dR || !Q || !K || !V || !A || !dA || !A->f32 || !dA->f32) return fail(OPH_EINVAL, "attention_bwd: missing operand%s");
     const float scale = 1.0f / sqrtf((float)d);
+    const long long ldA = A->ld;
+    if (dA->ld != ldA) return fail(OPH_EINVAL, "attention_bwd: dA must share A's row stride%s");
+    const bool fed = g_use_tma && planes_ready(dR) && planes_ready(Q) && planes_ready(K) && planes_ready(V) &&
+                     planes_ready(A) && planes_ready(dA);
+    if (!fed && (!dR->f32 || !Q->f32 || !K->f32 || !V->f32)) return fail(OPH_EINVAL, "attention_bwd: operands need fp32 views or planes%s");
     {   // dV[n][:] = sum_t A[t][n] dR[t][:]
         GemmArgs g = blank();
         g.a_mode = A_MNMAJOR; g.b_mode = B_MNMAJOR;
-        g.A.ptr = A; g.A.ld = ldA; g.A.L = T; g.A.Ls = T;
-        g.Bm.ptr = dR; g.Bm.ld = lddr; g.Bm.L = T; g.Bm.Ls = T;
+        att_operand(g.A, A, fed, T); att_operand(g.Bm, dR, fed, T);
         g.M = N; g.N = d; g.Kc = T;
-        g.tag = OPH_TAG_ATTENTION; g.z_mode = Z_BATCH; g.a_zs = (long long)T * ldA; g.b_zs = (long long)T * lddr; g.c_zs = (long long)N * lddv;
+        g.tag = OPH_TAG_ATTENTION; g.z_mode = Z_BATCH; g.a_zs = (long long)T * ldA; g.b_zs = (long long)T * dR->ld; g.c_zs = (long long)N * lddv;
         g.C = dV; g.ldc = lddv;
         OPH_TRY(launch_gemm(g, B, S(stream)));
     }
     {   // dA = dR V^T
         GemmArgs g = blank();
         g.a_mode = A_KMAJOR; g.b_mode = B_KMAJOR;
-        g.A.ptr = dR; g.A.ld = lddr; g.A.L = T; g.A.Ls = T;
-        g.Bm.ptr = V; g.Bm.ld = ldv;
+        att_operand(g.A, dR, fed, T); att_operand(g.Bm, V, fed, N);
         g.M = T; g.N = N; g.Kc = d;
-        g.tag = OPH_TAG_ATTENTION; g.z_mode = Z_BATCH; g.a_zs = (long long)T * lddr; g.b_zs = (long long)N * ldv; g.c_zs = (long long)T * ldA;
-        g.C = dA; g.ldc = ldA;
+        g.tag = OPH_TAG_ATTENTION; g.z_mode = Z_BATCH; g.a_zs = (long long)T * dR->ld; g.b_zs = (long long)N * V->ld; g.c_zs = (long long)T * ldA;
+        g.C = dA->f32; g.ldc = ldA;
         OPH_TRY(launch_gemm(g, B, S(stream)));
     }
-    launch_cfg(rows_grid((long long)B * T, 8), 256, 0, S(stream))(softmax_bwd_kernel, A, ldA, dA, ldA, B, T, N, att_coef, maxN, maxT, g_);
+    launch_cfg(rows_grid((long long)B * T, 8), 256, 0, S(stream))(softmax_bwd_kernel, A->f32, ldA, dA->f32, ldA, B, T, N, att_coef, maxN,
+                                                                 maxT, g_, fed ? dA->hi : nullptr, fed ? dA->lo : nullptr, dA->ldp);
     OPH_TRY(check_launch("softmax_bwd_kernel"));
     {   // dQ = dS K / sqrt(d) (+ direct path)
         GemmArgs g = blank();
         g.a_mode = A_KMAJOR; g.b_mode = B_MNMAJOR;
-        g.A.ptr = dA; g.A.ld = ldA; g.A.L = T; g.A.Ls = T;
-        g.Bm.ptr = K; g.Bm.ld = ldk; g.Bm.L = N; g.Bm.Ls = N;
+        att_operand(g.A, dA, fed, T); att_operand(g.Bm, K, fed, N);
         g.M = T; g.N = d; g.Kc = N;
-        g.tag = OPH_TAG_ATTENTION; g.z_mode = Z_BATCH; g.a_zs = (long long)T * ldA; g.b_zs = (long long)N * ldk; g.c_zs = (long long)T * lddq;
+        g.tag = OPH_TAG_ATTENTION; g.z_mode = Z_BATCH; g.a_zs = (long long)T * ldA; g.b_zs = (long long)N * K->ld; g.c_zs = (long long)T * lddq;
         g.C = dQ; g.ldc = lddq; g.alpha = scale;
         if (dq_addend) {
             if ((long long)T * ldqa != g.c_zs || ldqa != lddq) return fail(OPH_EINVAL, "attention_bwd: dq_addend must share dQ's layout%s");
@@ -812,10 +860,9 @@ int oph_attention_bwd(const float* dR, long long lddr, const float* Q, long long
     {   // dK[n][:] = sum_t dS[t][n] Q[t][:] / sqrt(d)
         GemmArgs g = blank();
         g.a_mode = A_MNMAJOR; g.b_mode = B_MNMAJOR;
-        g.A.ptr = dA; g.A.ld = ldA; g.A.L = T; g.A.Ls = T;
-        g.Bm.ptr = Q; g.Bm.ld = ldq; g.Bm.L = T; g.Bm.Ls = T;
+        att_operand(g.A, dA, fed, T); att_operand(g.Bm, Q, fed, T);
         g.M = N; g.N = d; g.Kc = T;
-        g.tag = OPH_TAG_ATTENTION; g.z_mode = Z_BATCH; g.a_zs = (long long)T * ldA; g.b_zs = (long long)T * ldq; g.c_zs = (long long)N * lddk;
+        g.tag = OPH_TAG_ATTENTION; g.z_mode = Z_BATCH; g.a_zs = (long long)T * ldA; g.b_zs = (long long)T * Q->ld; g.c_zs = (long long)N * lddk;
         g.C = dK; g.ldc = lddk; g.alpha = scale;
         OPH_TRY(launch_gemm(g, B, S(stream)));
     }

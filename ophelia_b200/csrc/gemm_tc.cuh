@@ -59,8 +59,11 @@ struct GemmArgs {
     // fix-up warp before the MMA sees the stage.
     // Weight-gradient products with both operands pre-split (r_tma): the reduction runs over (item, 64-step block) pairs
     // so that tap shifts and item boundaries are out-of-range coordinates too; k_chunk then counts k-blocks.
-    int a_tma;             // 1: conv-style A tiles come from tmA_hi / tmA_lo, the producer warps do not touch A
-    int r_tma;             // 1: MN-major A and B tiles (64 steps x 128 channels each) come from tmA_* / tmB_*
+    int a_tma;             // K-major A tiles come from tmA_hi / tmA_lo: 1 = flat conv-style tiles (2-D map), 2 = tiles of
+                           //   batch item z (3-D map, Z_BATCH products such as the attention contractions)
+    int b_tma;             // activation B operand of item z from tmB_hi / tmB_lo: 2 = K-major rows, 3 = MN-major steps
+    int r_tma;             // 1: MN-major A and B tiles (64 steps x 128 channels each) come from tmA_* / tmB_*; the
+                           //   reduction runs over the steps of item z (Z_BATCH) or over (item, block) pairs (Z_SPLITK)
     int items;             // number of batch items (M = items * A.L)
     // remainder K-split (RED outputs only): work items >= split_from are split_s k-block slices of the remaining units,
     // so that the last round of the persistent CTA pairs is short instead of mostly idle
@@ -165,6 +168,7 @@ constexpr int NUM_BARS = BAR_T_EMPTY + N_ACC;
 struct Unit {               // one 256x256 output tile of one tap / z slice
     int m0, n0, nb, ytap, k_begin, k_end, KBc, KB;
     int kb0, kb1;           // k-block range of this work item (the whole unit unless it is a remainder slice)
+    int z;                  // batch item (Z_BATCH) or split-K slice
     int rows;               // valid rows of this CTA's 128-row tile (<= 0: padding CTA)
     long long a_z, b_z, c_z;
 };
@@ -188,6 +192,7 @@ __device__ __forceinline__ Unit decode_unit(const GemmArgs& p, int v, int MP, in
     t.nb = rest % nblocks; rest /= nblocks;
     t.ytap = rest % p.ytaps;
     const int z = rest / p.ytaps;
+    t.z = z;
     const int mt = mp * 2 + (int)crank;
     t.m0 = mt * GEMM_BM;                               // may lie beyond M for the padding CTA of the last pair
     t.rows = min(GEMM_BM, p.M - t.m0);
@@ -232,8 +237,8 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
     const bool a_k = p.a_mode == A_KMAJOR;
     // both operands arrive through the copy engines: the 16 producer warps have nothing to stage and drain the
     // accumulators instead (4 x more epilogue warps, the dedicated epilogue warps then idle)
-    const bool copy_fed = (p.a_tma && packed) || p.r_tma;
-    const bool rotate = p.a_tma && packed && !(p.dbg_flags & 4);
+    const bool copy_fed = (p.a_tma && (packed || p.b_tma)) || p.r_tma;
+    const bool rotate = p.a_tma == 1 && packed && !(p.dbg_flags & 4);
     const bool nofix = (p.dbg_flags & (32 | 128)) != 0;        // diagnostics: skip the item-boundary fix-up (wrong results)
 
     if (tid == 0) {
@@ -245,7 +250,7 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
             mbar_init(BAR(BAR_LAND_A + i), 1);
         }
         for (int i = 0; i < NB_SLOTS; ++i) {
-            mbar_init(BAR(BAR_FULL_B + i), (packed || p.r_tma) ? 1 : 2 * NPW);
+            mbar_init(BAR(BAR_FULL_B + i), (packed || p.r_tma || p.b_tma) ? 1 : 2 * NPW);
             mbar_init(BAR(BAR_EMPTY_B + i), 1);
         }
         for (int i = 0; i < N_ACC; ++i) { mbar_init(BAR(BAR_T_FULL + i), 1); mbar_init(BAR(BAR_T_EMPTY + i), copy_fed ? 2 * EPI_WARPS : 8); }
@@ -441,6 +446,7 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
                 }
             };
             // one k-block: (convert +) store the A tile held in registers, then B for activation x activation products
+            float wb[NCH][8];
             auto emit = [&](int kb, float (&v)[NCH][8]) {
                 if (!p.a_tma) {
                     mbar_wait(BAR(BAR_EMPTY_A + a_slot), a_par);
@@ -454,21 +460,21 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
                     if (lane == 0) { if (crank == 0) mbar_arrive(BAR(BAR_FULL_A + a_slot)); else mbar_arrive_remote(BAR(BAR_FULL_A + a_slot), 0); }
                     if (++a_slot == NA_SLOTS) { a_slot = 0; a_par ^= 1; }
                 }
-                if (!packed) {
-                    float w[NCH][8];
-                    load_b(kb, w);
+                if (!packed) {                                 // wb was loaded one k-block ahead
                     mbar_wait(BAR(BAR_EMPTY_B + b_slot), b_par);
                     uint8_t* hi = sB + b_slot * B_SLOT;
 #pragma unroll
-                    for (int i = 0; i < NCH; ++i) store_chunk(b_split, hi, hi + B_PLANE, off_b[i], w[i]);
+                    for (int i = 0; i < NCH; ++i) store_chunk(b_split, hi, hi + B_PLANE, off_b[i], wb[i]);
                     fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) { if (crank == 0) mbar_arrive(BAR(BAR_FULL_B + b_slot)); else mbar_arrive_remote(BAR(BAR_FULL_B + b_slot), 0); }
                     if (++b_slot == NB_SLOTS) { b_slot = 0; b_par ^= 1; }
+                    if (kb + 1 < t.KB) load_b(kb + 1, wb);
                 }
             };
             float v0[NCH][8], v1[NCH][8];
             load_a(v0);
+            if (!packed) load_b(0, wb);
             for (int kb = 0; kb < t.KB; kb += 2) {
                 if (kb + 1 < t.KB) load_a(v1);
                 emit(kb, v0);
@@ -545,42 +551,12 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
         if (lane == 0 && (packed || p.a_tma || p.r_tma)) {
             int slot = 0, par = 1, as = 0, a_par = 1;
             if (p.a_tma || p.r_tma) { tma_prefetch_desc(&p.tmA_hi); tma_prefetch_desc(&p.tmA_lo); }
-            if (p.r_tma || packed) tma_prefetch_desc(&p.tmB_hi);
-            if (p.r_tma) tma_prefetch_desc(&p.tmB_lo);
+            if (p.r_tma || packed || p.b_tma) tma_prefetch_desc(&p.tmB_hi);
+            if (p.r_tma || p.b_tma) tma_prefetch_desc(&p.tmB_lo);
             const uint32_t fullA0 = mapa_u32(BAR(BAR_FULL_A), 0), fullB0 = mapa_u32(BAR(BAR_FULL_B), 0);   // leader's barriers
-            const int KBI = (p.A.L + GEMM_BK - 1) / GEMM_BK;       // 64-step blocks per batch item (r_tma)
+            const int KBI = (p.A.L + GEMM_BK - 1) / GEMM_BK;       // 64-step blocks per batch item (r_tma, split-K)
             for (int u = pair; u < total; u += npairs) {
                 const Unit t = decode_unit(p, u, MP, nblocks, crank);
-                if (p.r_tma) {
-                    for (int kb = 0; kb < t.KB; ++kb) {
-                        const int g = t.k_begin + kb, item = g / KBI, tb = (g - item * KBI) * GEMM_BK;
-                        {   // A: x^T tile = 64 steps x 128 channels [m0, m0+128) as two 64-channel boxes per plane
-                            mbar_wait(BAR(BAR_EMPTY_A + as), a_par);
-                            const uint32_t bar = fullA0 + 8u * as;
-                            const uint32_t dst = smem_u32(sA + as * A_SLOT);
-                            if (crank == 0) mbar_arrive_expect_tx(BAR(BAR_FULL_A + as), 2 * A_SLOT);
-                            const int ta = tb + p.A.off[t.ytap];
-                            tma_load_3d_cg2(dst, &p.tmA_hi, t.m0, ta, item, bar);
-                            tma_load_3d_cg2(dst + 8192, &p.tmA_hi, t.m0 + 64, ta, item, bar);
-                            tma_load_3d_cg2(dst + A_PLANE, &p.tmA_lo, t.m0, ta, item, bar);
-                            tma_load_3d_cg2(dst + A_PLANE + 8192, &p.tmA_lo, t.m0 + 64, ta, item, bar);
-                            if (++as == NA_SLOTS) { as = 0; a_par ^= 1; }
-                        }
-                        {   // B: this CTA's 128 of the 256 output columns
-                            mbar_wait(BAR(BAR_EMPTY_B + slot), par);
-                            const uint32_t bar = fullB0 + 8u * slot;
-                            const uint32_t dst = smem_u32(sB + slot * B_SLOT);
-                            if (crank == 0) mbar_arrive_expect_tx(BAR(BAR_FULL_B + slot), 2 * B_SLOT);
-                            const int tbb = tb + p.Bm.off[t.ytap], n = t.n0 + (int)crank * GEMM_BNC;
-                            tma_load_3d_cg2(dst, &p.tmB_hi, n, tbb, item, bar);
-                            tma_load_3d_cg2(dst + 8192, &p.tmB_hi, n + 64, tbb, item, bar);
-                            tma_load_3d_cg2(dst + B_PLANE, &p.tmB_lo, n, tbb, item, bar);
-                            tma_load_3d_cg2(dst + B_PLANE + 8192, &p.tmB_lo, n + 64, tbb, item, bar);
-                            if (++slot == NB_SLOTS) { slot = 0; par ^= 1; }
-                        }
-                    }
-                    continue;
-                }
                 // packed image rows (128 bytes each) of this CTA's half of stage (nb, kb): ((nb*KB + kb)*2 + crank) * 256
                 const int brow0 = (t.nb * t.KB * 2 + (int)crank) * 256;
                 // CTA pairs walk the k-blocks of a unit from different starting points (rot): at any moment they ask the
@@ -588,43 +564,85 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
                 const int nkb = t.kb1 - t.kb0, rot = rotate ? pair % nkb : 0;
                 for (int j = 0; j < nkb; ++j) {
                     int kb = t.kb0 + j + rot; if (kb >= t.kb1) kb -= nkb;
-                    if (p.a_tma) {                             // A tile: two boxes (hi / lo plane) of 64 channels x 128 rows
+                    // steps [tb, tb + 64) of batch item `item`: the k-block of an MN-major (row-reduction) operand
+                    int item = t.z, tb = kb * GEMM_BK;
+                    if (p.z_mode != Z_BATCH) { const int g = t.k_begin + kb; item = g / KBI; tb = (g - item * KBI) * GEMM_BK; }
+                    // ------------------------------------------------ A
+                    if (p.r_tma) {         // x^T tile = 64 steps x 128 channels [m0, m0+128) as two 64-channel boxes per plane
+                        mbar_wait(BAR(BAR_EMPTY_A + as), a_par);
+                        const uint32_t bar = fullA0 + 8u * as;
+                        const uint32_t dst = smem_u32(sA + as * A_SLOT);
+                        if (crank == 0) mbar_arrive_expect_tx(BAR(BAR_FULL_A + as), 2 * A_SLOT);
+                        const int ta = tb + p.A.off[t.ytap];
+                        tma_load_3d_cg2(dst, &p.tmA_hi, t.m0, ta, item, bar);
+                        tma_load_3d_cg2(dst + 8192, &p.tmA_hi, t.m0 + 64, ta, item, bar);
+                        tma_load_3d_cg2(dst + A_PLANE, &p.tmA_lo, t.m0, ta, item, bar);
+                        tma_load_3d_cg2(dst + A_PLANE + 8192, &p.tmA_lo, t.m0 + 64, ta, item, bar);
+                        if (++as == NA_SLOTS) { as = 0; a_par ^= 1; }
+                    } else if (p.a_tma) {  // K-major tile: two boxes (hi / lo plane) of 64 channels x 128 rows
                         const int tap = kb / t.KBc, cb = kb - tap * t.KBc;
                         mbar_wait(BAR(BAR_EMPTY_A + as), a_par);
                         const uint32_t dst = smem_u32(sA + as * A_SLOT);
                         const int off = p.A.off[tap];
                         if (p.dbg_flags & 128) {               // diagnostics: no A traffic at all
                             if (crank == 0) { mbar_arrive(BAR(BAR_FULL_A + as)); mbar_arrive(BAR(BAR_FULL_A + as)); mbar_arrive(BAR(BAR_FULL_A + as)); }
-                            if (++as == NA_SLOTS) { as = 0; a_par ^= 1; }
-                            goto b_part;
-                        }
-                        const bool fix_me = !nofix && needs_fix(t.m0, off, p.A.L);
-                        if (crank == 0) {                      // bytes that will be signalled straight on FULL_A
-                            const bool fix_peer = !nofix && needs_fix(t.m0 + GEMM_BM, off, p.A.L);
-                            mbar_arrive_expect_tx(BAR(BAR_FULL_A + as), (fix_me ? 0 : A_SLOT) + (fix_peer ? 0 : A_SLOT));
-                        }
-                        if (fix_me) {                          // lands locally; the fix-up warp sends this CTA's token
-                            const uint32_t bar = BAR(BAR_LAND_A + as);
-                            mbar_arrive_expect_tx(bar, A_SLOT);
-                            tma_load_2d(dst, &p.tmA_hi, t.k_begin + cb * GEMM_BK, t.m0 + off, bar);
-                            tma_load_2d(dst + A_PLANE, &p.tmA_lo, t.k_begin + cb * GEMM_BK, t.m0 + off, bar);
                         } else {
-                            const uint32_t bar = fullA0 + 8u * as;
-                            tma_load_2d_cg2(dst, &p.tmA_hi, t.k_begin + cb * GEMM_BK, t.m0 + off, bar);
-                            tma_load_2d_cg2(dst + A_PLANE, &p.tmA_lo, t.k_begin + cb * GEMM_BK, t.m0 + off, bar);
-                            if (crank == 0) mbar_arrive(BAR(BAR_FULL_A + as)); else mbar_arrive_remote(BAR(BAR_FULL_A + as), 0);
+                            const bool flat = p.a_tma == 1;
+                            const bool fix_me = flat && !nofix && needs_fix(t.m0, off, p.A.L);
+                            if (crank == 0) {                  // bytes that will be signalled straight on FULL_A
+                                const bool fix_peer = flat && !nofix && needs_fix(t.m0 + GEMM_BM, off, p.A.L);
+                                mbar_arrive_expect_tx(BAR(BAR_FULL_A + as), (fix_me ? 0 : A_SLOT) + (fix_peer ? 0 : A_SLOT));
+                            }
+                            const int c0 = t.k_begin + cb * GEMM_BK;
+                            if (fix_me) {                      // lands locally; the fix-up warp sends this CTA's token
+                                const uint32_t bar = BAR(BAR_LAND_A + as);
+                                mbar_arrive_expect_tx(bar, A_SLOT);
+                                tma_load_2d(dst, &p.tmA_hi, c0, t.m0 + off, bar);
+                                tma_load_2d(dst + A_PLANE, &p.tmA_lo, c0, t.m0 + off, bar);
+                            } else {
+                                const uint32_t bar = fullA0 + 8u * as;
+                                if (flat) {
+                                    tma_load_2d_cg2(dst, &p.tmA_hi, c0, t.m0 + off, bar);
+                                    tma_load_2d_cg2(dst + A_PLANE, &p.tmA_lo, c0, t.m0 + off, bar);
+                                } else {
+                                    tma_load_3d_cg2(dst, &p.tmA_hi, c0, t.m0, t.z, bar);
+                                    tma_load_3d_cg2(dst + A_PLANE, &p.tmA_lo, c0, t.m0, t.z, bar);
+                                }
+                                if (crank == 0) mbar_arrive(BAR(BAR_FULL_A + as)); else mbar_arrive_remote(BAR(BAR_FULL_A + as), 0);
+                            }
                         }
                         if (++as == NA_SLOTS) { as = 0; a_par ^= 1; }
                     }
-                    b_part:
-                    if (!packed) continue;
-                    mbar_wait(BAR(BAR_EMPTY_B + slot), par);
-                    if (p.dbg_flags & 2) { if (crank == 0) mbar_arrive(BAR(BAR_FULL_B + slot)); }
-                    else {
+                    // ------------------------------------------------ B
+                    if (p.r_tma || p.b_tma == 3) {             // MN-major: 64 steps x this CTA's 128 of the 256 output columns
+                        mbar_wait(BAR(BAR_EMPTY_B + slot), par);
+                        const uint32_t bar = fullB0 + 8u * slot;
+                        const uint32_t dst = smem_u32(sB + slot * B_SLOT);
                         if (crank == 0) mbar_arrive_expect_tx(BAR(BAR_FULL_B + slot), 2 * B_SLOT);
-                        tma_load_2d_cg2(smem_u32(sB + slot * B_SLOT), &p.tmB_hi, 0, brow0 + kb * 512, fullB0 + 8u * slot);
+                        const int tbb = tb + (p.r_tma ? p.Bm.off[t.ytap] : 0), n = t.n0 + (int)crank * GEMM_BNC;
+                        tma_load_3d_cg2(dst, &p.tmB_hi, n, tbb, item, bar);
+                        tma_load_3d_cg2(dst + 8192, &p.tmB_hi, n + 64, tbb, item, bar);
+                        tma_load_3d_cg2(dst + B_PLANE, &p.tmB_lo, n, tbb, item, bar);
+                        tma_load_3d_cg2(dst + B_PLANE + 8192, &p.tmB_lo, n + 64, tbb, item, bar);
+                        if (++slot == NB_SLOTS) { slot = 0; par ^= 1; }
+                    } else if (p.b_tma == 2) {                 // K-major rows [n, n + 128) of item z, 64 channels
+                        mbar_wait(BAR(BAR_EMPTY_B + slot), par);
+                        const uint32_t bar = fullB0 + 8u * slot;
+                        const uint32_t dst = smem_u32(sB + slot * B_SLOT);
+                        if (crank == 0) mbar_arrive_expect_tx(BAR(BAR_FULL_B + slot), 2 * B_SLOT);
+                        const int n = t.n0 + (int)crank * GEMM_BNC, c0 = t.k_begin + kb * GEMM_BK;
+                        tma_load_3d_cg2(dst, &p.tmB_hi, c0, n, t.z, bar);
+                        tma_load_3d_cg2(dst + B_PLANE, &p.tmB_lo, c0, n, t.z, bar);
+                        if (++slot == NB_SLOTS) { slot = 0; par ^= 1; }
+                    } else if (packed) {
+                        mbar_wait(BAR(BAR_EMPTY_B + slot), par);
+                        if (p.dbg_flags & 2) { if (crank == 0) mbar_arrive(BAR(BAR_FULL_B + slot)); }
+                        else {
+                            if (crank == 0) mbar_arrive_expect_tx(BAR(BAR_FULL_B + slot), 2 * B_SLOT);
+                            tma_load_2d_cg2(smem_u32(sB + slot * B_SLOT), &p.tmB_hi, 0, brow0 + kb * 512, fullB0 + 8u * slot);
+                        }
+                        if (++slot == NB_SLOTS) { slot = 0; par ^= 1; }
                     }
-                    if (++slot == NB_SLOTS) { slot = 0; par ^= 1; }
                 }
             }
         }
@@ -634,7 +652,7 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
         // Flat conv-style A tiles: rows whose tap-shifted source step falls outside their own batch item were fetched
         // from the neighbouring item.  They are conv padding: such tiles land on a local barrier, the rows are zeroed
         // here (generic-proxy stores + proxy fence) and the bytes are then accounted on the leader's FULL barrier.
-        if (p.a_tma) {
+        if (p.a_tma == 1) {
             int as = 0; uint32_t land_par = 0;
             for (int u = pair; u < total; u += npairs) {
                 const Unit t = decode_unit(p, u, MP, nblocks, crank);

@@ -249,10 +249,25 @@ __device__ __forceinline__ float guide_w(int n, int t, float inv_maxN, float inv
 
 // in: S[b][t][0..N) scaled scores.  out: probabilities in place, optional transposed alignments [B][N][T],
 // argmax (first maximum), guided-attention partial sum  sum_{n<maxN,t<maxT} A*W  (architectures.py:258-270)
+__device__ __forceinline__ void split4(const float4& v, uint2& hh, uint2& ll) {
+    const __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+    const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+    const __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2bfloat162_rn(v.z - f1.x, v.w - f1.y);
+    hh.x = *reinterpret_cast<const uint32_t*>(&h0); hh.y = *reinterpret_cast<const uint32_t*>(&h1);
+    ll.x = *reinterpret_cast<const uint32_t*>(&l0); ll.y = *reinterpret_cast<const uint32_t*>(&l1);
+}
+__device__ __forceinline__ void st_split1(unsigned short* hi, unsigned short* lo, long long idx, float v) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+    hi[idx] = *reinterpret_cast<const unsigned short*>(&h);
+    lo[idx] = *reinterpret_cast<const unsigned short*>(&l);
+}
+
 __global__ void softmax_fwd_kernel(float* __restrict__ S, long long ldS, int B, int T, int N,
                                    const int* __restrict__ prev_max, int win,
                                    float* __restrict__ align_t, int* __restrict__ argmax_out,
-                                   double* __restrict__ att_acc, int maxN, int maxT, float g) {
+                                   double* __restrict__ att_acc, int maxN, int maxT, float g,
+                                   unsigned short* __restrict__ p_hi, unsigned short* __restrict__ p_lo, long long ldp) {
     pdl_grid_sync();
     const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
     const float inv_maxN = 1.f / (float)maxN, inv_maxT = 1.f / (float)maxT, inv_2g2 = 1.f / (2.f * g * g);
@@ -286,6 +301,7 @@ __global__ void softmax_fwd_kernel(float* __restrict__ S, long long ldS, int B, 
         for (int n = lane; n < N; n += 32) {
             const float a = sr[n] * inv;
             sr[n] = a;
+            if (p_hi) st_split1(p_hi, p_lo, row * ldp + n, a);      // operand planes of the A.V / A^T.dR products
             if (align_t) align_t[((long long)b * N + n) * T + t] = a;
             if (att_acc && n < maxN && t < maxT) att_part += a * guide_w(n, t, inv_maxN, inv_maxT, inv_2g2);
         }
@@ -306,7 +322,8 @@ __global__ void softmax_fwd_kernel(float* __restrict__ S, long long ldS, int B, 
 
 // dA (in) -> dS (in place):  dS = A * (dA' - sum_n A*dA'),  dA' = dA + att_coef * W[n][t]
 __global__ void softmax_bwd_kernel(const float* __restrict__ A, long long ldA, float* __restrict__ dA, long long lddA,
-                                   int B, int T, int N, float att_coef, int maxN, int maxT, float g) {
+                                   int B, int T, int N, float att_coef, int maxN, int maxT, float g,
+                                   unsigned short* __restrict__ ds_hi, unsigned short* __restrict__ ds_lo, long long ldp) {
     pdl_grid_sync();
     const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
     const float inv_maxN = 1.f / (float)maxN, inv_maxT = 1.f / (float)maxT, inv_2g2 = 1.f / (2.f * g * g);
@@ -323,7 +340,33 @@ __global__ void softmax_bwd_kernel(const float* __restrict__ A, long long ldA, f
             dot += ar[n] * d;
         }
         dot = warp_sum(dot);
-        for (int n = lane; n < N; n += 32) dr[n] = ar[n] * (dr[n] - dot);
+        for (int n = lane; n < N; n += 32) {
+            const float ds = ar[n] * (dr[n] - dot);
+            dr[n] = ds;
+            if (ds_hi) st_split1(ds_hi, ds_lo, row * ldp + n, ds);
+        }
+    }
+}
+
+// fp32 rows -> split-bf16 planes (hi = bf16(x), lo = bf16(x - hi)): operands that reach a GEMM from outside the
+// row-wise kernels (fed K / V at synthesis, the decoder-input gradient) get their copy-engine format here
+__global__ void split_planes_kernel(const float* __restrict__ x, long long ldx, long long rows, int C,
+                                    unsigned short* __restrict__ hi, unsigned short* __restrict__ lo, long long ldp) {
+    pdl_grid_sync();
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (long long row = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * wpb) {
+        const float* xr = x + row * ldx;
+        if (!(C & 3) && !(ldx & 3) && !(ldp & 3)) {
+            for (int c = lane * 4; c < C; c += 128) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(xr + c));
+                uint2 hh, ll;
+                split4(v, hh, ll);
+                *reinterpret_cast<uint2*>(hi + row * ldp + c) = hh;
+                *reinterpret_cast<uint2*>(lo + row * ldp + c) = ll;
+            }
+        } else {
+            for (int c = lane; c < C; c += 32) st_split1(hi, lo, row * ldp + c, xr[c]);
+        }
     }
 }
 
@@ -475,13 +518,6 @@ __device__ __forceinline__ void st_row_planes(unsigned short* __restrict__ hi, u
         *reinterpret_cast<uint2*>(hi + i * 128 + lane * 4) = hh;
         *reinterpret_cast<uint2*>(lo + i * 128 + lane * 4) = ll;
     }
-}
-__device__ __forceinline__ void split4(const float4& v, uint2& hh, uint2& ll) {
-    const __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
-    const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
-    const __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2bfloat162_rn(v.z - f1.x, v.w - f1.y);
-    hh.x = *reinterpret_cast<const uint32_t*>(&h0); hh.y = *reinterpret_cast<const uint32_t*>(&h1);
-    ll.x = *reinterpret_cast<const uint32_t*>(&l0); ll.y = *reinterpret_cast<const uint32_t*>(&l1);
 }
 template <int VEC>
 __device__ __forceinline__ RowStats reg_stats(const float4 (&v)[VEC]) {

@@ -178,7 +178,7 @@ def hc(inputs, filters=None, size=1, rate=1, padding="SAME", dropout_rate=0, use
     step = _step_ptr(store, training)
     rec = _recording(training)
     y, saved = ops.hc_fwd(inputs, pk, store.get(bn), g1, b1, g2, b2, rate, pad, norm, drop, seed, step, save=rec, y=out,
-                          planes=out is None)
+                          planes=True)
     if rec:
         def bwd(dy):
             gr = [store.grad(n) for n in names] if norm else [None] * 4

@@ -42,6 +42,10 @@ def TextEnc(hp, L, training=True, speaker_codes=None, reuse=None):
     d = tensor.shape[-1] // 2
     K, V = tensor[:, :, :d], tensor[:, :, d:]
     K._oph_kv = V._oph_kv = tensor
+    pl = getattr(tensor, "_oph_planes", None)
+    if pl is not None:                              # the attention products read K and V as split-bf16 planes
+        K._oph_planes = (pl[0][:, :, :d], pl[1][:, :, :d])
+        V._oph_planes = (pl[0][:, :, d:], pl[1][:, :, d:])
     return K, V
 
 

@@ -236,19 +236,50 @@ def embed_bwd(ids, dout, dtable):
 
 
 # ---------------------------------------------------------------------------------------------- attention
+def _pad8(c):
+    return (c + 7) // 8 * 8
+
+
+def ensure_planes(t):
+    """Attach split-bf16 planes (hi, lo) [B, L, pad8(C)] to a [B, L, C] activation that did not come out of a row-wise
+    kernel (fed K / V at synthesis, the decoder-input gradient): one oph_split_planes launch, cached on the tensor."""
+    pl = getattr(t, "_oph_planes", None)
+    if pl is not None:
+        return pl
+    ld, B, L, C = _rows(t)
+    ldp = _pad8(C)
+    hi = torch.empty(B, L, ldp, device=t.device, dtype=torch.bfloat16)
+    lo = torch.empty(B, L, ldp, device=t.device, dtype=torch.bfloat16)
+    _lib.call("oph_split_planes", _p(t), ld, B * L, C, _p(hi), _p(lo), ldp, _stream())
+    t._oph_planes = (hi[:, :, :C], lo[:, :, :C])
+    return t._oph_planes
+
+
+def _new_planes(t):
+    """Uninitialised planes for an fp32 [B, T, ld >= N] scratch whose logical width is t.shape[2]."""
+    B, L, C = t.shape
+    ldp = _pad8(C)
+    hi = torch.empty(B, L, ldp, device=t.device, dtype=torch.bfloat16)
+    lo = torch.empty(B, L, ldp, device=t.device, dtype=torch.bfloat16)
+    t._oph_planes = (hi[:, :, :C], lo[:, :, :C])
+
+
 def attention_fwd(Q, K, V, R=None, prev_max=None, win=3, want_alignments=False, want_argmax=True, att_acc=None,
                   maxN=1, maxT=1, g=0.2):
     ldq, B, T, d = _rows(Q)
     ldk, _, N, _ = _rows(K)
-    ldv = _rows(V)[0]
+    _rows(V)
     dev = Q.device
     ldA = _pad4(N)
-    A = torch.zeros(B, T, ldA, device=dev, dtype=torch.float32)
+    A = torch.zeros(B, T, ldA, device=dev, dtype=torch.float32)[:, :, :N]
     if R is None:
         R = torch.empty(B, T, d, device=dev, dtype=torch.float32)
     align = torch.empty(B, N, T, device=dev, dtype=torch.float32) if want_alignments else None
     argmax = torch.empty(B, T, device=dev, dtype=torch.int32) if want_argmax else None
-    _lib.call("oph_attention_fwd", _p(Q), ldq, _p(K), ldk, _p(V), ldv, _p(A), ldA, _p(R), R.stride(1), _p(align),
+    for t in (Q, K, V):
+        ensure_planes(t)
+    _new_planes(A)
+    _lib.call("oph_attention_fwd", _act(Q), _act(K), _act(V), _act(A), _p(R), R.stride(1), _p(align),
               _p(argmax), _p(prev_max), int(win), _p(att_acc), int(maxN), int(maxT), float(g), B, T, N, d, _stream())
     return R, A, align, argmax
 
@@ -256,10 +287,8 @@ def attention_fwd(Q, K, V, R=None, prev_max=None, win=3, want_alignments=False, 
 def attention_bwd(dR, Q, K, V, A, dq_addend=None, att_coef=0.0, maxN=1, maxT=1, g=0.2, dK=None, dV=None):
     ldq, B, T, d = _rows(Q)
     ldk, _, N, _ = _rows(K)
-    ldv = _rows(V)[0]
     dev = Q.device
-    ldA = A.stride(1)
-    dA = torch.zeros_like(A)
+    dA = torch.zeros(B, T, A.stride(1), device=dev, dtype=torch.float32)[:, :, :N]
     if dq_addend is not None:   # may be a strided view (second half of the [R,Q] gradient): mirror its layout
         _rows(dq_addend)
         dQ = torch.empty_strided(dq_addend.shape, dq_addend.stride(), device=dev, dtype=torch.float32)
@@ -269,7 +298,12 @@ def attention_bwd(dR, Q, K, V, A, dq_addend=None, att_coef=0.0, maxN=1, maxT=1, 
         dK = torch.empty(B, N, d, device=dev, dtype=torch.float32)
     if dV is None:
         dV = torch.empty(B, N, d, device=dev, dtype=torch.float32)
-    _lib.call("oph_attention_bwd", _p(dR), _rows(dR)[0], _p(Q), ldq, _p(K), ldk, _p(V), ldv, _p(A), ldA, _p(dA),
+    for t in (dR, Q, K, V):
+        ensure_planes(t)
+    if getattr(A, "_oph_planes", None) is None:
+        ensure_planes(A)
+    _new_planes(dA)
+    _lib.call("oph_attention_bwd", _act(dR), _act(Q), _act(K), _act(V), _act(A), _act(dA),
               _p(dQ), dQ.stride(1), _p(dq_addend), dq_addend.stride(1) if dq_addend is not None else 0,
               _p(dK), dK.stride(1), _p(dV), dV.stride(1), float(att_coef), int(maxN), int(maxT), float(g),
               B, T, N, d, _stream())

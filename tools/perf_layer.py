@@ -86,5 +86,5 @@ d = d[d[:, 0] > 0]
 if len(d):
     print("   last GEMM, per CTA pair (mean cycles): total %.0f  wait_acc %.0f  wait_A %.0f  wait_B %.0f  k-blocks %.0f  -> %.0f cyc/k-block (MMA needs 1536)" %
           (d[:, 0].mean(), d[:, 1].mean(), d[:, 2].mean(), d[:, 3].mean(), d[:, 4].mean(), (d[:, 0] / d[:, 4]).mean()))
-    print("   ns from kernel entry (mean / max over pairs): MMA loop end %.0f / %.0f, producers done %.0f / %.0f, after final cluster barrier %.0f / %.0f; clock %.2f GHz" %
+    sys.stdout.flush(); print("   ns from kernel entry (mean / max over pairs): MMA loop end %.0f / %.0f, producers done %.0f / %.0f, after final cluster barrier %.0f / %.0f; clock %.2f GHz" %
           (d[:, 5].mean(), d[:, 5].max(), d[:, 6].mean(), d[:, 6].max(), d[:, 7].mean(), d[:, 7].max(), (d[:, 0] / d[:, 5]).mean()))
