@@ -153,10 +153,12 @@ int oph_embed_bwd(const int32_t* ids, const float* dout, long long ldo, float* d
  * forcibly-incremental window: keys outside [prev, prev+win) get -2^32+1 (networks.py:304-313).
  * align_t (nullable) = alignments [B][N][T]; argmax (nullable) int32 [B][T] (first maximum);
  * att_acc (nullable, device double) += sum A*W over n<maxN, t<maxT with the analytic guide (utils.py:155-161). */
-/* Q, K, V, A (probabilities; f32 is written, planes are written when given) are activations per batch item.  When every
+/* Q, K, V, A (probabilities) and R (context vectors) are activations per batch item; for the outputs A and R the f32
+ * view is written and the planes too when given (R's by the epilogue of the A.V product, so that the decoder's first
+ * conv reads [R|Q] through the copy engines).  When every
  * operand carries split-bf16 planes (contiguous items: item z starts z*rows*ldp elements in), both products are fed by
  * the copy engines; otherwise the producer warps convert the fp32 views. */
-int oph_attention_fwd(const oph_act* Q, const oph_act* K, const oph_act* V, const oph_act* A, float* R, long long ldr,
+int oph_attention_fwd(const oph_act* Q, const oph_act* K, const oph_act* V, const oph_act* A, const oph_act* R,
                       float* align_t, int32_t* argmax, const int32_t* prev_max, int win, double* att_acc, int maxN,
                       int maxT, float g, int B, int T, int N, int d, oph_stream_t stream);
 /* dR [B][T].  dA [B][T][ldA] scratch (f32 + optional planes for dS).  dq_addend (nullable) is added into dQ (the direct

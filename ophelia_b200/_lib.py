@@ -43,7 +43,7 @@ SIGNATURES = {
     "oph_deconv_bwd": (I, [P, LL, AP, P, LL, P, P, P, P, P, LL, P, LL, P, P, P, P, I, I, I, F, U64, P, P]),
     "oph_embed_fwd": (I, [P, P, P, LL, I, I, P]),
     "oph_embed_bwd": (I, [P, P, LL, P, I, I, P]),
-    "oph_attention_fwd": (I, [AP, AP, AP, AP, P, LL, P, P, P, I, P, I, I, F, I, I, I, I, P]),
+    "oph_attention_fwd": (I, [AP, AP, AP, AP, AP, P, P, P, I, P, I, I, F, I, I, I, I, P]),
     "oph_attention_bwd": (I, [AP, AP, AP, AP, AP, AP, P, LL, P, LL, P, LL, P, LL, F, I, I, F, I, I, I, I, P]),
     "oph_split_planes": (I, [P, LL, LL, I, P, P, LL, P]),
     "oph_recon_loss": (I, [P, LL, P, LL, P, LL, LL, I, I, F, F, F, P, P]),

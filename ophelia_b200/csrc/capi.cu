@@ -1,8 +1,8 @@
 // C ABI of libophelia_sm100.so: composes the tcgen05 implicit-GEMM core with the row-wise kernels into the
 // reference's operators (modules.conv1d / hc / conv1d_transpose / embed, networks.Attention, losses, Adam).
 #include "../../include/ophelia_b200.h"
-#include "gemm_tc.cuh"
 #include "rowwise.cuh"
+#include "gemm_tc.cuh"
 
 #include <atomic>
 #include <cmath>
@@ -143,7 +143,7 @@ int launch_gemm(GemmArgs& a, int zdim, cudaStream_t st) {
     // conv-style A already split into planes: feed it with TMA tensor copies (flat tiles, padding = out-of-range / fix-up)
     a.a_tma = 0; a.b_tma = 0; if (!a.r_tma) a.items = 1;
     if (g_use_tma && a.a_mode == A_KMAJOR && a.A.hi && a.A.mul == 1 && a.A.L == a.A.Ls && a.z_mode == Z_NONE &&
-        !(a.Kc & 63) && a.M % a.A.L == 0) {
+        !(a.Kc & 7) && a.M % a.A.L == 0) {
         if (make_plane_tmap2d(&a.tmA_hi, a.A.hi, a.Kc, a.M, a.A.ld) && make_plane_tmap2d(&a.tmA_lo, a.A.lo, a.Kc, a.M, a.A.ld)) {
             a.a_tma = 1; a.items = a.M / a.A.L;
         }
@@ -426,7 +426,7 @@ int launch_wgrad(const OperandMap& a, int M, const int* a_off, int aL, int aLs, 
     g.r_tma = 0;
     const int items = aL > 0 ? R / aL : 0;
     if (g_use_tma && g.A.hi && g.Bm.hi && a_mul == 1 && b_mul == 1 && aL == aLs && bL == bLs && aL == bL && items * aL == R &&
-        !(M & 127) && !(N & 127) &&
+        !(M & 7) && !(N & 7) &&
         make_plane_tmap(&g.tmA_hi, g.A.hi, M, aL, items, g.A.ld, GEMM_BK) && make_plane_tmap(&g.tmA_lo, g.A.lo, M, aL, items, g.A.ld, GEMM_BK) &&
         make_plane_tmap(&g.tmB_hi, g.Bm.hi, N, bL, items, g.Bm.ld, GEMM_BK) && make_plane_tmap(&g.tmB_lo, g.Bm.lo, N, bL, items, g.Bm.ld, GEMM_BK)) {
         g.r_tma = 1; g.items = items;
@@ -778,10 +778,11 @@ int oph_split_planes(const float* x, long long ldx, long long rows, int C, unsig
     return check_launch("split_planes_kernel");
 }
 
-int oph_attention_fwd(const oph_act* Q, const oph_act* K, const oph_act* V, const oph_act* A, float* R, long long ldr,
+int oph_attention_fwd(const oph_act* Q, const oph_act* K, const oph_act* V, const oph_act* A, const oph_act* Ro,
                       float* align_t, int32_t* argmax, const int32_t* prev_max, int win, double* att_acc, int maxN,
                       int maxT, float g_, int B, int T, int N, int d, oph_stream_t stream) {
-    if (!Q || !K || !V || !A || !A->f32) return fail(OPH_EINVAL, "attention_fwd: missing operand%s");
+    if (!Q || !K || !V || !A || !A->f32 || !Ro || !Ro->f32) return fail(OPH_EINVAL, "attention_fwd: missing operand%s");
+    float* R = Ro->f32; const long long ldr = Ro->ld;
     const long long ldA = A->ld;
     if (ldA < N) return fail(OPH_EINVAL, "attention_fwd: ldA < N%s");
     // all operands as split-bf16 planes: every tile of both products arrives through the copy engines
@@ -807,6 +808,7 @@ int oph_attention_fwd(const oph_act* Q, const oph_act* K, const oph_act* V, cons
         g.M = T; g.N = d; g.Kc = N;
         g.tag = OPH_TAG_ATTENTION; g.z_mode = Z_BATCH; g.a_zs = (long long)T * ldA; g.b_zs = (long long)N * V->ld; g.c_zs = (long long)T * ldr;
         g.C = R; g.ldc = ldr;
+        if (planes_ready(Ro) && !(ldr & 3)) { g.Chi = Ro->hi; g.Clo = Ro->lo; g.ldcp = Ro->ldp; g.cp_zs = (long long)T * Ro->ldp; }
         OPH_TRY(launch_gemm(g, B, S(stream)));
     }
     return OPH_OK;

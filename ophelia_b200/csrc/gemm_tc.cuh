@@ -43,6 +43,9 @@ struct GemmArgs {
     long long c_tap_stride;
     float* C;
     long long ldc;
+    unsigned short* Chi;   // optional: the output also as split-bf16 planes (operand format of the next product);
+    unsigned short* Clo;   //   plain (non-atomic) 16-byte-aligned outputs only
+    long long ldcp, cp_zs; // plane row stride / z stride in elements
     int c_mul, c_off;      // output row = m*c_mul + c_off
     const float* bias;     // [N] or null
     const float* addend;   // [rows][ld_add] or null, indexed like C
@@ -326,6 +329,13 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
                                 o[0] += a.x; o[1] += a.y; o[2] += a.z; o[3] += a.w;
                             }
                             *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+                            if (p.Chi) {
+                                const long long pi = (long long)t.z * p.cp_zs + (crow0 + (long long)rr * p.c_mul) * p.ldcp + gcol;
+                                uint2 hh, ll;
+                                split4(make_float4(o[0], o[1], o[2], o[3]), hh, ll);
+                                *reinterpret_cast<uint2*>(p.Chi + pi) = hh;
+                                *reinterpret_cast<uint2*>(p.Clo + pi) = ll;
+                            }
                         }
                     } else {
 #pragma unroll

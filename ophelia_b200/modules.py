@@ -149,7 +149,7 @@ def conv1d(inputs, filters=None, size=1, rate=1, padding="SAME", dropout_rate=0,
 
 # ------------------------------------------------------------------------------------------------ highway conv
 def hc(inputs, filters=None, size=1, rate=1, padding="SAME", dropout_rate=0, use_bias=True, activation_fn=None,
-       training=True, scope="hc", reuse=None, normtype='layer', lcc=0, codes=None, *, out=None):
+       training=True, scope="hc", reuse=None, normtype='layer', lcc=0, codes=None, *, out=None, out_planes=None):
     """modules.py:148-207: conv to 2C, split, LN(H1), LN(H2), gate = sigmoid(H1), gate*H2 + (1-gate)*inputs."""
     assert use_bias and not lcc and activation_fn is None
     assert normtype in (None, 'layer')
@@ -178,7 +178,7 @@ def hc(inputs, filters=None, size=1, rate=1, padding="SAME", dropout_rate=0, use
     step = _step_ptr(store, training)
     rec = _recording(training)
     y, saved = ops.hc_fwd(inputs, pk, store.get(bn), g1, b1, g2, b2, rate, pad, norm, drop, seed, step, save=rec, y=out,
-                          planes=True)
+                          planes=True, y_planes=out_planes)
     if rec:
         def bwd(dy):
             gr = [store.grad(n) for n in names] if norm else [None] * 4

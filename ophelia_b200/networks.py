@@ -49,6 +49,16 @@ def TextEnc(hp, L, training=True, speaker_codes=None, reuse=None):
     return K, V
 
 
+def _new_rq(B, T, d, device):
+    """[R | Q] decoder-input buffer (networks.py:317-319) and its split-bf16 planes: Q's half is written by the last
+    AudioEnc layer, R's half by the epilogue of the attention A.V product."""
+    rq = torch.empty(B, T, 2 * d, device=device, dtype=torch.float32)
+    planes = (torch.empty(B, T, 2 * d, device=device, dtype=torch.bfloat16),
+              torch.empty(B, T, 2 * d, device=device, dtype=torch.bfloat16))
+    rq._oph_planes_buf = planes
+    return rq, planes
+
+
 def AudioEnc(hp, S, training=True, speaker_codes=None, reuse=None, *, in_shift=0):
     '''
     Args:
@@ -72,13 +82,14 @@ def AudioEnc(hp, S, training=True, speaker_codes=None, reuse=None, *, in_shift=0
                         training=training, scope="HC_{}".format(i), normtype=hp.norm, reuse=reuse); i += 1
     rq = None
     for n in range(2):
-        out = None
+        out = out_planes = None
         if n == 1 and getattr(hp, "concatenate_query", True):
             B, T, d = tensor.shape
-            rq = torch.empty(B, T, 2 * d, device=tensor.device, dtype=torch.float32)
+            rq, rq_planes = _new_rq(B, T, d, tensor.device)
             out = rq[:, :, d:]
+            out_planes = (rq_planes[0][:, :, d:], rq_planes[1][:, :, d:])
         tensor = hc(tensor, size=3, rate=3, padding="CAUSAL", dropout_rate=hp.dropout_rate, training=training,
-                    scope="HC_{}".format(i), normtype=hp.norm, reuse=reuse, out=out); i += 1
+                    scope="HC_{}".format(i), normtype=hp.norm, reuse=reuse, out=out, out_planes=out_planes); i += 1
     if rq is not None:
         tensor._oph_rq = rq
     return tensor
@@ -105,14 +116,20 @@ def Attention(hp, Q, K, V, monotonic_attention=False, prev_max_attentions=None, 
     concat = getattr(hp, "concatenate_query", True)
     rq = getattr(Q, "_oph_rq", None) if concat else None
     if concat and rq is None:                       # Q did not come from AudioEnc: build the [R, Q] buffer here
-        rq = torch.empty(B, T, 2 * d, device=Q.device, dtype=torch.float32)
+        rq, rq_planes = _new_rq(B, T, d, Q.device)
         rq[:, :, d:].copy_(Q)
         Q = rq[:, :, d:]
+        Q._oph_planes = ops.split_planes(Q, into=(rq_planes[0][:, :, d:], rq_planes[1][:, :, d:]))
     R_out = rq[:, :, :d] if concat else None
+    if concat:
+        hi, lo = rq._oph_planes_buf
+        R_out._oph_planes = (hi[:, :, :d], lo[:, :, :d])
     R, A, alignments, max_attentions = ops.attention_fwd(
         Q, K, V, R=R_out, prev_max=prev, win=hp.attention_win_size, want_alignments=want_alignments,
         att_acc=att_acc, maxN=hp.max_N, maxT=hp.max_T, g=hp.g)
     result = rq if concat else R
+    if concat:
+        rq._oph_planes = rq._oph_planes_buf         # both halves are written now: AudioDec's first conv reads planes
     if training and Tape.current is not None:
         kv = getattr(K, "_oph_kv", None)
 

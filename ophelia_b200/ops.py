@@ -66,22 +66,28 @@ def _pad4(c):
 PLANE_WIDTHS = (256, 512, 1024)      # channel counts for which the row-wise kernels can emit split-bf16 planes
 
 
-def _act(t, use_planes=True):
-    """oph_act for a [B, L, C] activation; planes ride along as `t._oph_planes = (hi, lo)` (bf16 [B, L, C])."""
+def _act(t, use_planes=True, planes=None):
+    """oph_act for a [B, L, C] activation; planes ride along as `t._oph_planes = (hi, lo)` (bf16 [B, L, C]) or are
+    passed explicitly."""
     a = _lib.Act()
     ld = _rows(t)[0]
     a.f32, a.ld = t.data_ptr(), ld
-    pl = getattr(t, "_oph_planes", None) if use_planes else None
+    pl = planes if planes is not None else (getattr(t, "_oph_planes", None) if use_planes else None)
     if pl is not None:
         a.hi, a.lo, a.ldp = pl[0].data_ptr(), pl[1].data_ptr(), pl[0].stride(1)
     return a
 
 
-def _out_act(y, want_planes):
-    """oph_act for an output; allocates (and attaches) the planes when the width supports them."""
+def _out_act(y, want_planes, given=None):
+    """oph_act for an output; allocates (and attaches) the planes when the width supports them, or uses `given`
+    (hi, lo) views (e.g. one half of a wider planes buffer)."""
     a = _lib.Act()
     a.f32, a.ld = y.data_ptr(), y.stride(1)
-    if want_planes and y.shape[2] in PLANE_WIDTHS:
+    if given is not None and y.shape[2] in PLANE_WIDTHS:
+        hi, lo = given
+        a.hi, a.lo, a.ldp = hi.data_ptr(), lo.data_ptr(), hi.stride(1)
+        y._oph_planes = (hi, lo)
+    elif want_planes and y.shape[2] in PLANE_WIDTHS:
         hi = torch.empty(y.shape, device=y.device, dtype=torch.bfloat16)
         lo = torch.empty(y.shape, device=y.device, dtype=torch.bfloat16)
         a.hi, a.lo, a.ldp = hi.data_ptr(), lo.data_ptr(), hi.stride(1)
@@ -134,22 +140,25 @@ def conv1d_fwd(x, pk, bias, gamma, beta, rate=1, padding=SAME, in_shift=0, act=A
         y = new_act(B, L, cout, dev)
     ysig = new_act(B, L, cout, dev) if want_sigmoid else None
     ya = _out_act(y, planes)
-    _lib.call("oph_conv1d_fwd", _act(x), _p(pk.fwd), _p(bias), _p(gamma), _p(beta), _p(z), z.stride(1), _p(stats),
+    xpl = getattr(x, "_oph_planes", None)
+    if xpl is None and cin % 8 == 0:       # inputs from outside the row-wise kernels (mels, embeddings): split once per call
+        xpl = split_planes(x)
+    _lib.call("oph_conv1d_fwd", _act(x, planes=xpl), _p(pk.fwd), _p(bias), _p(gamma), _p(beta), _p(z), z.stride(1), _p(stats),
               ya, _p(ysig), ysig.stride(1) if ysig is not None else 0, B, L, cin, cout, pk.k, rate,
               padding, in_shift, act, int(bool(norm)), float(drop_p), int(seed), _p(step), _stream())
-    return y, ysig, (z, stats)
+    return y, ysig, (z, stats, xpl)
 
 
 def conv1d_bwd(dy, x, saved, pk, gamma, beta, dw, dbias, dgamma, dbeta, rate=1, padding=SAME, in_shift=0,
                act=ACT_NONE, norm=True, drop_p=0.0, seed=0, step=None, need_dx=True, dx=None):
-    z, stats = saved
+    z, stats, xpl = saved
     ldx, B, L, cin = _rows(x)
     lddy = _rows(dy)[0]
     dev = x.device
     dz = new_act(B, L, pk.cout, dev)
     if need_dx and dx is None:
         dx = new_act(B, L, cin, dev)
-    _lib.call("oph_conv1d_bwd", _p(dy), lddy, _act(x), _p(z), z.stride(1), _p(stats), _p(pk.bwd), _p(gamma),
+    _lib.call("oph_conv1d_bwd", _p(dy), lddy, _act(x, planes=xpl), _p(z), z.stride(1), _p(stats), _p(pk.bwd), _p(gamma),
               _p(beta), _p(dz), dz.stride(1), _p(dx) if need_dx else None, dx.stride(1) if need_dx else 0, _p(dw),
               _p(dbias), _p(dgamma), _p(dbeta), B, L, cin, pk.cout, pk.k, rate, padding, in_shift, act,
               int(bool(norm)), float(drop_p), int(seed), _p(step), _stream())
@@ -159,7 +168,7 @@ def conv1d_bwd(dy, x, saved, pk, gamma, beta, dw, dbias, dgamma, dbeta, rate=1, 
 
 # ---------------------------------------------------------------------------------------------- highway conv
 def hc_fwd(x, pk, bias, g1, b1, g2, b2, rate=1, padding=SAME, norm=True, drop_p=0.0, seed=0, step=None,
-           save=False, y=None, planes=True):
+           save=False, y=None, planes=True, y_planes=None):
     ldx, B, L, C = _rows(x)
     assert pk.cin == C and pk.cout == 2 * C
     dev = x.device
@@ -167,7 +176,7 @@ def hc_fwd(x, pk, bias, g1, b1, g2, b2, rate=1, padding=SAME, norm=True, drop_p=
     stats = torch.empty(B * L, 4, device=dev, dtype=torch.float32) if (save and norm) else None
     if y is None:
         y = torch.empty(B, L, C, device=dev, dtype=torch.float32)
-    ya = _out_act(y, planes)
+    ya = _out_act(y, planes, y_planes)
     _lib.call("oph_hc_fwd", _act(x), _p(pk.fwd), _p(bias), _p(g1), _p(b1), _p(g2), _p(b2), _p(z), z.stride(1),
               _p(stats), ya, B, L, C, pk.k, rate, padding, int(bool(norm)), float(drop_p),
               int(seed), _p(step), _stream())
@@ -240,19 +249,31 @@ def _pad8(c):
     return (c + 7) // 8 * 8
 
 
-def ensure_planes(t):
-    """Attach split-bf16 planes (hi, lo) [B, L, pad8(C)] to a [B, L, C] activation that did not come out of a row-wise
-    kernel (fed K / V at synthesis, the decoder-input gradient): one oph_split_planes launch, cached on the tensor."""
-    pl = getattr(t, "_oph_planes", None)
-    if pl is not None:
-        return pl
+def split_planes(t, into=None):
+    """Split-bf16 planes (hi, lo) [B, L, pad8(C)] of a [B, L, C] activation that did not come out of a row-wise kernel
+    (mels, embeddings, fed K / V, the decoder-input gradient): one oph_split_planes launch.  `into` = (hi, lo) views to
+    fill instead of new buffers."""
     ld, B, L, C = _rows(t)
-    ldp = _pad8(C)
-    hi = torch.empty(B, L, ldp, device=t.device, dtype=torch.bfloat16)
-    lo = torch.empty(B, L, ldp, device=t.device, dtype=torch.bfloat16)
-    _lib.call("oph_split_planes", _p(t), ld, B * L, C, _p(hi), _p(lo), ldp, _stream())
-    t._oph_planes = (hi[:, :, :C], lo[:, :, :C])
-    return t._oph_planes
+    if into is None:
+        ldp = _pad8(C)
+        hi = torch.empty(B, L, ldp, device=t.device, dtype=torch.bfloat16)[:, :, :C]
+        lo = torch.empty(B, L, ldp, device=t.device, dtype=torch.bfloat16)[:, :, :C]
+    else:
+        hi, lo = into
+    assert hi.stride(1) == lo.stride(1) and hi.stride(2) == 1 and hi.stride(0) == L * hi.stride(1)
+    _lib.call("oph_split_planes", _p(t), ld, B * L, C, _p(hi), _p(lo), hi.stride(1), _stream())
+    return hi, lo
+
+
+def ensure_planes(t, cache=False):
+    """Planes of t: the ones attached by the producing kernel, else a fresh split.  cache=True attaches the result to the
+    tensor: only for tensors whose contents do not change afterwards (K / V inside the autoregressive loop)."""
+    pl = getattr(t, "_oph_planes", None)
+    if pl is None:
+        pl = split_planes(t)
+        if cache:
+            t._oph_planes = pl
+    return pl
 
 
 def _new_planes(t):
@@ -276,10 +297,10 @@ def attention_fwd(Q, K, V, R=None, prev_max=None, win=3, want_alignments=False, 
         R = torch.empty(B, T, d, device=dev, dtype=torch.float32)
     align = torch.empty(B, N, T, device=dev, dtype=torch.float32) if want_alignments else None
     argmax = torch.empty(B, T, device=dev, dtype=torch.int32) if want_argmax else None
-    for t in (Q, K, V):
-        ensure_planes(t)
     _new_planes(A)
-    _lib.call("oph_attention_fwd", _act(Q), _act(K), _act(V), _act(A), _p(R), R.stride(1), _p(align),
+    _rows(R)
+    pq, pk_, pv = ensure_planes(Q), ensure_planes(K), ensure_planes(V)      # locals keep fresh splits alive over the call
+    _lib.call("oph_attention_fwd", _act(Q, planes=pq), _act(K, planes=pk_), _act(V, planes=pv), _act(A), _act(R), _p(align),
               _p(argmax), _p(prev_max), int(win), _p(att_acc), int(maxN), int(maxT), float(g), B, T, N, d, _stream())
     return R, A, align, argmax
 
@@ -298,12 +319,10 @@ def attention_bwd(dR, Q, K, V, A, dq_addend=None, att_coef=0.0, maxN=1, maxT=1, 
         dK = torch.empty(B, N, d, device=dev, dtype=torch.float32)
     if dV is None:
         dV = torch.empty(B, N, d, device=dev, dtype=torch.float32)
-    for t in (dR, Q, K, V):
-        ensure_planes(t)
-    if getattr(A, "_oph_planes", None) is None:
-        ensure_planes(A)
     _new_planes(dA)
-    _lib.call("oph_attention_bwd", _act(dR), _act(Q), _act(K), _act(V), _act(A), _act(dA),
+    pr, pq, pk_, pv, pa = (ensure_planes(t) for t in (dR, Q, K, V, A))     # locals keep fresh splits alive over the call
+    _lib.call("oph_attention_bwd", _act(dR, planes=pr), _act(Q, planes=pq), _act(K, planes=pk_), _act(V, planes=pv),
+              _act(A, planes=pa), _act(dA),
               _p(dQ), dQ.stride(1), _p(dq_addend), dq_addend.stride(1) if dq_addend is not None else 0,
               _p(dK), dK.stride(1), _p(dV), dV.stride(1), float(att_coef), int(maxN), int(maxT), float(g),
               B, T, N, d, _stream())

@@ -88,6 +88,9 @@ def synth_codedtext2mel_device(hp, K, V, ends, g, use_cuda_graph=True):
     K = g._to_device(K, torch.float32).contiguous()
     V = g._to_device(V, torch.float32).contiguous()
     B = K.shape[0]
+    from . import ops
+    ops.ensure_planes(K, cache=True)                    # K, V stay constant over the loop: split them once
+    ops.ensure_planes(V, cache=True)
     Y = torch.zeros(B, hp.max_T, hp.n_mels, device=dev, dtype=torch.float32)
     alignments = torch.zeros(B, hp.max_N, hp.max_T, device=dev, dtype=torch.float32)
     prev = torch.zeros(B, device=dev, dtype=torch.int32)
