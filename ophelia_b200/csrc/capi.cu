@@ -18,6 +18,7 @@ namespace {
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
 int g_gemm_dbg_flags = 0;
+int g_gemm_dbg_flags_host = 0;     // all bits as passed to oph_gemm_debug_flags (host-side switches)
 bool g_hcb_two = true;
 int g_hcb_depth = 0;               // ring depth of the highway-backward row kernel (tunable through oph_gemm_debug_flags bits 8..10)
 long long* g_gemm_dbg = nullptr;   // optional device buffer [74][8] for in-kernel wait-cycle counters
@@ -199,8 +200,11 @@ int launch_gemm(GemmArgs& a, int zdim, cudaStream_t st) {
     // RED outputs fed by the copy engines: split the units of the last (partial) round into k-block slices so that it
     // costs a fraction of a round; s minimises rounds x (slice length + 1 k-block of per-item overhead)
     long long items = units;
-    a.split_from = (int)units; a.split_s = 1;
-    if (g_use_split && a.a_tma && a.b_mode == B_PACKED && a.atomic && !a.bias && a.z_mode == Z_NONE && a.ytaps == 1) {
+    a.split_from = (int)units; a.split_s = 1; a.split_red = 0;
+    const bool can_red = a.atomic && !a.bias;
+    // plain outputs the caller allows us to pre-zero (a.zero_bytes > 0): the slices of the remainder units RED into zeros
+    const bool can_zero = !a.atomic && a.zero_bytes > 0 && !a.addend && !a.Chi && a.c_mul == 1;
+    if (g_use_split && a.a_tma == 1 && a.b_mode == B_PACKED && (can_red || can_zero) && a.z_mode == Z_NONE && a.ytaps == 1) {
         const int P = GEMM_MAX_PAIRS, KB = a.ntaps * cdiv(a.Kc, GEMM_BK);
         const int rem = (int)(units % P);
         if (rem > 0) {
@@ -209,7 +213,14 @@ int launch_gemm(GemmArgs& a, int zdim, cudaStream_t st) {
                 const long long cost = (long long)cdiv(rem * sl, P) * (cdiv(KB, sl) + 1);
                 if (cost < best) { best = cost; best_s = sl; }
             }
-            if (best_s > 1) { a.split_from = (int)(units - rem); a.split_s = best_s; items = a.split_from + (long long)rem * best_s; }
+            const long long zero_cost = can_zero ? 2 + (long long)(a.zero_bytes / 4000000) : 0;   // ~k-block times of the memset
+            if (best_s > 1 && best + zero_cost + 4 <= (long long)KB + 1) {
+                if (can_zero) {
+                    if (cudaMemsetAsync(a.C, 0, a.zero_bytes, st) != cudaSuccess) return check_launch("cudaMemsetAsync(z)");
+                    a.split_red = 1;
+                }
+                a.split_from = (int)(units - rem); a.split_s = best_s; items = a.split_from + (long long)rem * best_s;
+            }
         }
     }
     const int pairs = (int)(items < GEMM_MAX_PAIRS ? items : GEMM_MAX_PAIRS);
@@ -456,7 +467,7 @@ int oph_version(void) { return 100; }
 const char* oph_last_error(void) { return g_err; }
 long long oph_launch_count(void) { return g_launches.load(); }
 int oph_gemm_debug_buffer(long long* dev_buf) { g_gemm_dbg = dev_buf; return OPH_OK; }
-int oph_gemm_debug_flags(int flags) { g_gemm_dbg_flags = flags & 0xA7; g_use_tma = !(flags & 8); g_use_split = !(flags & 16); g_use_pdl = (flags & 64) != 0;
+int oph_gemm_debug_flags(int flags) { g_gemm_dbg_flags_host = flags; g_gemm_dbg_flags = flags & 0xA7; g_use_tma = !(flags & 8); g_use_split = !(flags & 16); g_use_pdl = (flags & 64) != 0;
     g_hcb_depth = (flags >> 8) & 7;                    // 0 = automatic
     g_hcb_two = !(flags & 2048);
     if (g_hcb_depth == 1) g_hcb_depth = 2;
@@ -583,6 +594,7 @@ int oph_conv1d_fwd(const oph_act* x, const void* packed_w, const float* bias, co
     conv_offsets(k, rate, padding, in_shift, g.A.off);
     g.Bpacked = packed_w; g.M = B * L; g.N = Cout; g.Kc = Cin; g.ntaps = k;
     g.C = z; g.ldc = ldz; g.bias = bias; g.tag = OPH_TAG_CONV_FWD;
+    g.zero_bytes = (size_t)B * L * ldz * sizeof(float);
     OPH_TRY(launch_gemm(g, 1, S(stream)));
     return launch_ln_act_fwd(z, ldz, gamma, beta, y, y_sig, ldys, stats, (long long)B * L, Cout, act, norm, drop_p,
                              seed, step, S(stream));
@@ -631,12 +643,30 @@ int oph_hc_fwd(const oph_act* x, const void* packed_w, const float* bias, const 
     conv_offsets(k, rate, padding, 0, g.A.off);
     g.Bpacked = packed_w; g.M = B * L; g.N = 2 * C; g.Kc = C; g.ntaps = k;
     g.C = z; g.ldc = ldz; g.bias = bias; g.tag = OPH_TAG_CONV_FWD;
+    g.zero_bytes = (size_t)B * L * ldz * sizeof(float);        // z is ours to overwrite: remainder units may be K-split
     OPH_TRY(launch_gemm(g, 1, S(stream)));
     const long long rows = (long long)B * L;
     const int grid = rows_grid(rows, 8);
     const bool vec = vec_ok(C, ldz, x->ld, y->ld);
     if (y->hi && !(vec && !(y->ldp & 7))) return fail(OPH_EINVAL, "hc_fwd: output planes need C in {256,512,1024}%s");
-    if (vec) {
+    if (vec && norm && !(g_gemm_dbg_flags_host & 4096)) {
+        const int wpr = C / 256, groups = 8 / wpr;
+        const int depth = ((g_gemm_dbg_flags_host & 8192) || C > 256) ? 3 : 2;         // ring slots per warp
+        const int bps = depth == 3 ? 2 : 4;                                            // blocks of 8 warps per SM (shared memory)
+        long long gl = (rows + groups * 2 - 1) / (groups * 2);
+        const int gridw = (int)(gl < 1 ? 1 : (gl > 148 * bps ? 148 * bps : gl));
+        const size_t smw = (4 * (size_t)C + 64) * sizeof(float) + (size_t)8 * depth * HCF_SLOT;
+        static bool attr_done = false;
+        if (!attr_done) {
+            cudaFuncSetAttribute(hc_post_fwd_wide_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+            cudaFuncSetAttribute(hc_post_fwd_wide_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+            cudaFuncSetAttribute(hc_post_fwd_wide_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+            attr_done = true;
+        }
+#define OPH_LAUNCH(W) launch_cfg(gridw, 256, smw, S(stream))(hc_post_fwd_wide_kernel<W>, z, ldz, x->f32, x->ld, g1, b1, g2, b2, y->f32, y->ld, y->hi, y->lo, y->ldp, stats, (int)rows, drop_p, seed, step, depth)
+        if (C == 256) OPH_LAUNCH(1); else if (C == 512) OPH_LAUNCH(2); else OPH_LAUNCH(4);
+#undef OPH_LAUNCH
+    } else if (vec) {
 #define OPH_LAUNCH(V) launch_cfg(grid, 256, 0, S(stream))(hc_post_fwd_vec_kernel<V>, z, ldz, x->f32, x->ld, g1, b1, g2, b2, y->f32, y->ld, y->hi, y->lo, y->ldp, stats, (int)rows, norm, drop_p, seed, step)
         if (C == 256) OPH_LAUNCH(2); else if (C == 512) OPH_LAUNCH(4); else OPH_LAUNCH(8);
 #undef OPH_LAUNCH

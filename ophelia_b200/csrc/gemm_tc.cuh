@@ -71,6 +71,8 @@ struct GemmArgs {
     // remainder K-split (RED outputs only): work items >= split_from are split_s k-block slices of the remaining units,
     // so that the last round of the persistent CTA pairs is short instead of mostly idle
     int split_from, split_s;
+    size_t zero_bytes;     // host-side: > 0 if launch_gemm may memset C[0, zero_bytes) (the caller owns a dense output)
+    int split_red;         // 1: C was zeroed by the host and only the split work items accumulate with RED (plain outputs)
     alignas(64) CUtensorMap tmA_hi;
     alignas(64) CUtensorMap tmA_lo;
     alignas(64) CUtensorMap tmB_hi;
@@ -172,6 +174,7 @@ struct Unit {               // one 256x256 output tile of one tap / z slice
     int m0, n0, nb, ytap, k_begin, k_end, KBc, KB;
     int kb0, kb1;           // k-block range of this work item (the whole unit unless it is a remainder slice)
     int z;                  // batch item (Z_BATCH) or split-K slice
+    int sliced;             // 1: this work item is one k-block slice of a remainder unit
     int rows;               // valid rows of this CTA's 128-row tile (<= 0: padding CTA)
     long long a_z, b_z, c_z;
 };
@@ -187,7 +190,9 @@ __device__ __forceinline__ bool needs_fix(int m0, int off, int L) {
 __device__ __forceinline__ Unit decode_unit(const GemmArgs& p, int v, int MP, int nblocks, uint32_t crank) {
     Unit t;
     int u = v, slice = 0, nslices = 1;
+    t.sliced = 0;
     if (p.split_s > 1 && v >= p.split_from) {
+        t.sliced = 1;
         const int w = v - p.split_from;
         u = p.split_from + w / p.split_s; slice = w - (w / p.split_s) * p.split_s; nslices = p.split_s;
     }
@@ -289,6 +294,7 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
             const float* addb = p.addend ? p.addend + t.c_z + (long long)t.ytap * p.c_tap_stride : nullptr;
             const int grow0 = t.m0 + q * 32;
             const int nrows = min(32, t.rows - q * 32);        // <= 0 for padding rows
+            const bool atom = p.atomic || (p.split_red && t.sliced);
             const long long crow0 = (long long)grow0 * p.c_mul + p.c_off;
 #pragma unroll 1
             for (int cb = cg; cb < GEMM_BN / 16; cb += ncg) {
@@ -309,7 +315,7 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
                 __syncwarp();
                 const int gcol = t.n0 + col0 + c4 * 4;
                 float bv[4] = {0.f, 0.f, 0.f, 0.f};
-                if (p.bias) {
+                if (p.bias && t.kb0 == 0) {
 #pragma unroll
                     for (int e = 0; e < 4; ++e) if (gcol + e < p.N) bv[e] = __ldg(p.bias + gcol + e);
                 }
@@ -322,7 +328,7 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
                     float o[4] = {v.x * p.alpha + bv[0], v.y * p.alpha + bv[1], v.z * p.alpha + bv[2], v.w * p.alpha + bv[3]};
                     float* dst = Cb + (crow0 + (long long)rr * p.c_mul) * p.ldc + gcol;
                     if (full) {
-                        if (p.atomic) red_add_v4(dst, o[0], o[1], o[2], o[3]);
+                        if (atom) red_add_v4(dst, o[0], o[1], o[2], o[3]);
                         else {
                             if (addb) {
                                 const float4 a = __ldg(reinterpret_cast<const float4*>(addb + (crow0 + (long long)rr * p.c_mul) * p.ld_add + gcol));
@@ -341,7 +347,7 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             if (gcol + e >= p.N) break;
-                            if (p.atomic) atomicAdd(dst + e, o[e]);
+                            if (atom) atomicAdd(dst + e, o[e]);
                             else dst[e] = o[e] + (addb ? __ldg(addb + (crow0 + (long long)rr * p.c_mul) * p.ld_add + gcol + e) : 0.f);
                         }
                     }

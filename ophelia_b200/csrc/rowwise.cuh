@@ -958,3 +958,133 @@ __global__ void __launch_bounds__(256) hc_post_bwd_wide_kernel(
 }
 
 }  // namespace oph
+
+// =================================================================================================
+// Forward highway tail in the same streaming layout as hc_post_bwd_wide_kernel: WPR warps per row, gamma / beta in
+// shared memory (loaded once per block, not once per warp), rows prefetched through per-warp cp.async rings.  Row
+// moments: each warp takes the two-pass mean / M2 of its 256 channels, the warps of a row merge them exactly
+// (equal-sized groups: M2 = sum M2_w + 256 * sum (mean_w - mean)^2).
+namespace oph {
+
+constexpr int HCF_SLOT = 6 * 512;                       // z1, z2, x: two float4 per lane each
+
+template <int WPR>
+__global__ void __launch_bounds__(256) hc_post_fwd_wide_kernel(
+        const float* __restrict__ z, long long ldz, const float* __restrict__ x, long long ldx,
+        const float* __restrict__ g1, const float* __restrict__ b1, const float* __restrict__ g2,
+        const float* __restrict__ b2, float* __restrict__ y, long long ldy, unsigned short* __restrict__ y_hi,
+        unsigned short* __restrict__ y_lo, long long ldp, float* __restrict__ stats,
+        int rows, float drop_p, unsigned long long seed, const long long* step, int depth) {
+    pdl_grid_sync();
+    constexpr int C = 256 * WPR;
+    constexpr int GROUPS = 8 / WPR;
+    extern __shared__ __align__(16) float smem_f[];
+    float* spar = smem_f;                               // [4][C]: g1, b1, g2, b2
+    float* sx = spar + 4 * C;                           // [2 parities][8 warps][4] partial moments
+    uint8_t* ring = reinterpret_cast<uint8_t*>(sx + 64);
+    for (int i = threadIdx.x; i < C; i += 256) { spar[i] = g1[i]; spar[C + i] = b1[i]; spar[2 * C + i] = g2[i]; spar[3 * C + i] = b2[i]; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int grp = warp / WPR, part = warp % WPR;
+    const int cbase = part * 256 + lane * 4;
+    const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+    const unsigned long long sd = eff_seed(seed, step);
+    const long long stride = (long long)gridDim.x * GROUPS;
+    long long row = (long long)blockIdx.x * GROUPS + grp;
+    uint8_t* myring = ring + (size_t)warp * depth * HCF_SLOT;
+    const uint32_t ring_u32 = (uint32_t)__cvta_generic_to_shared(myring) + lane * 16;
+    auto issue = [&](long long r, int slot) {
+        if (r < rows) {
+            const uint32_t d = ring_u32 + slot * HCF_SLOT;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                cp_async_16(d + (0 + i) * 512, z + r * ldz + cbase + 128 * i);
+                cp_async_16(d + (2 + i) * 512, z + r * ldz + C + cbase + 128 * i);
+                cp_async_16(d + (4 + i) * 512, x + r * ldx + cbase + 128 * i);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    for (int d = 0; d < depth - 1; ++d) issue(row + d * stride, d);
+    int it = 0, slot = 0;
+    for (; row < rows; row += stride, ++it) {
+        {
+            int ns = slot + depth - 1; if (ns >= depth) ns -= depth;
+            issue(row + (long long)(depth - 1) * stride, ns);
+        }
+        if (depth == 2) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else if (depth == 3) asm volatile("cp.async.wait_group 2;" ::: "memory");
+        else asm volatile("cp.async.wait_group 3;" ::: "memory");
+        const uint8_t* sl = myring + slot * HCF_SLOT + lane * 16;
+        float4 z1[2], z2[2], xv[2], o[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            z1[i] = *reinterpret_cast<const float4*>(sl + (0 + i) * 512);
+            z2[i] = *reinterpret_cast<const float4*>(sl + (2 + i) * 512);
+            xv[i] = *reinterpret_cast<const float4*>(sl + (4 + i) * 512);
+        }
+        if (++slot == depth) slot = 0;
+        // two-pass moments of this warp's 256 channels
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) { s1 += (z1[i].x + z1[i].y) + (z1[i].z + z1[i].w); s2 += (z2[i].x + z2[i].y) + (z2[i].z + z2[i].w); }
+        float m1 = warp_sum(s1) * (1.f / 256.f), m2 = warp_sum(s2) * (1.f / 256.f);
+        float q1 = 0.f, q2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float a = OPH_F4(z1[i], e) - m1, b = OPH_F4(z2[i], e) - m2;
+                q1 += a * a; q2 += b * b;
+            }
+        q1 = warp_sum(q1); q2 = warp_sum(q2);
+        if (WPR > 1) {                                   // merge the equal-sized groups of the warps sharing this row
+            float* my = sx + ((it & 1) * 8 + warp) * 4;
+            if (lane == 0) *reinterpret_cast<float4*>(my) = make_float4(m1, q1, m2, q2);
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(WPR * 32) : "memory");
+            float mm1 = 0.f, mm2 = 0.f;
+            float4 ow[WPR];
+#pragma unroll
+            for (int w = 0; w < WPR; ++w) { ow[w] = *reinterpret_cast<const float4*>(sx + ((it & 1) * 8 + grp * WPR + w) * 4); mm1 += ow[w].x; mm2 += ow[w].z; }
+            mm1 *= (1.f / WPR); mm2 *= (1.f / WPR);
+            float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+            for (int w = 0; w < WPR; ++w) {
+                t1 += ow[w].y + 256.f * (ow[w].x - mm1) * (ow[w].x - mm1);
+                t2 += ow[w].w + 256.f * (ow[w].z - mm2) * (ow[w].z - mm2);
+            }
+            m1 = mm1; m2 = mm2; q1 = t1; q2 = t2;
+        }
+        const float r1 = rsqrtf(q1 * (1.f / (float)C) + LN_EPS), r2 = rsqrtf(q2 * (1.f / (float)C) + LN_EPS);
+        if (stats && lane == 0 && part == 0) *reinterpret_cast<float4*>(stats + row * 4) = make_float4(m1, r1, m2, r2);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            float4 G1 = *reinterpret_cast<const float4*>(spar + cbase + 128 * i);
+            float4 B1 = *reinterpret_cast<const float4*>(spar + C + cbase + 128 * i);
+            float4 G2 = *reinterpret_cast<const float4*>(spar + 2 * C + cbase + 128 * i);
+            float4 B2 = *reinterpret_cast<const float4*>(spar + 3 * C + cbase + 128 * i);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float u1 = (OPH_F4(z1[i], e) - m1) * r1 * OPH_F4(G1, e) + OPH_F4(B1, e);
+                const float u2 = (OPH_F4(z2[i], e) - m2) * r2 * OPH_F4(G2, e) + OPH_F4(B2, e);
+                const float g = sigmoidf_(u1);
+                float r = g * u2 + (1.f - g) * OPH_F4(xv[i], e);
+                if (drop_p > 0.f) r *= drop_scale(sd, (unsigned long long)row * C + cbase + 128 * i + e, drop_p, inv_keep);
+                OPH_F4(o[i], e) = r;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            *reinterpret_cast<float4*>(y + row * ldy + cbase + 128 * i) = o[i];
+            if (y_hi) {
+                uint2 hh, ll;
+                split4(o[i], hh, ll);
+                *reinterpret_cast<uint2*>(y_hi + row * ldp + cbase + 128 * i) = hh;
+                *reinterpret_cast<uint2*>(y_lo + row * ldp + cbase + 128 * i) = ll;
+            }
+        }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+}  // namespace oph
