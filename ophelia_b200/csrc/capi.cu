@@ -446,11 +446,15 @@ int launch_wgrad(const OperandMap& a, int M, const int* a_off, int aL, int aLs, 
     const int base = cdiv(cdiv(M, GEMM_BM), 2) * cdiv(N, GEMM_BN) * taps;     // work units before split-K
     const int kblocks = g.r_tma ? items * cdiv(aL, GEMM_BK) : cdiv(R, GEMM_BK);
     const int max_splits = cdiv(kblocks, 4);
-    int rounds = cdiv(base, GEMM_MAX_PAIRS);
-    if (rounds < 2 && base * max_splits >= 2 * GEMM_MAX_PAIRS) rounds = 2;
-    int splits = (rounds * GEMM_MAX_PAIRS) / base;
-    if (splits > max_splits) splits = max_splits;
-    if (splits < 1) splits = 1;
+    // fewest split-K slices whose work units fill whole rounds of the 74 CTA pairs to >= 92 % (else the best found);
+    // every slice costs one more RED pass over dW, so small counts win ties
+    int splits = 1; double best_eff = 0.0;
+    for (int sp = 1; sp <= max_splits && sp <= 64; ++sp) {
+        const long long u = (long long)base * sp;
+        const double eff = (double)u / (double)(cdiv((int)u, GEMM_MAX_PAIRS) * GEMM_MAX_PAIRS);
+        if (eff > best_eff + 1e-9) { best_eff = eff; splits = sp; }
+        if (eff >= 0.92 && u >= 2 * GEMM_MAX_PAIRS) break;
+    }
     const int kb_chunk = cdiv(kblocks, splits);
     splits = cdiv(kblocks, kb_chunk);
     if (g.r_tma) { g.k_chunk = kb_chunk; g.Kc = kblocks; g.prof_k = R; }       // units of k-blocks

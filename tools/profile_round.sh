@@ -1,6 +1,6 @@
 #!/bin/bash
-# Run ON THE GPU BOX (via gpurun): ncu launch list of the bench command + full captures of the dominant kernel.
-# Outputs land in gpurun_out/; summarise them afterwards with tools/ncu_summary.py into profiles/.
+# Run ON THE GPU BOX (via gpurun): ncu launch list of the bench command + full captures of the dominant kernels.
+# Outputs land in gpurun_out/; summarise them afterwards with tools/ncu_summary.py / tools/launch_shares.py into profiles/.
 set -u
 R=${1:-r01}
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/launches_${R}.csv \
@@ -10,6 +10,11 @@ for op in hc_fwd hc_dgrad hc_bwd; do
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16x3 -s $skip -c 1 -f \
       -o gpurun_out/${R}_gemm_${op} python tools/perf_layer.py --op $op --iters 2 > gpurun_out/ncu_${R}_${op}.log 2>&1
 done
-timeout 600 ncu --set full --clock-control none -k regex:hc_post_bwd_wide -s 2 -c 1 -f -o gpurun_out/${R}_hc_post_bwd \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:hc_post_bwd_wide -s 2 -c 1 -f -o gpurun_out/${R}_hc_post_bwd \
     python tools/perf_layer.py --op hc_bwd --iters 2 > gpurun_out/ncu_${R}_post.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:hc_post_fwd_wide -s 2 -c 1 -f -o gpurun_out/${R}_hc_post_fwd \
+    python tools/perf_layer.py --op hc_fwd --iters 2 > gpurun_out/ncu_${R}_postf.log 2>&1
+timeout 300 python tools/perf_layer.py --op attn_fwd --iters 2 > /dev/null 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16x3 -s 6 -c 1 -f -o gpurun_out/${R}_gemm_attn_qk \
+    python tools/perf_layer.py --op attn_fwd --iters 2 > gpurun_out/ncu_${R}_attn.log 2>&1
 ls -la gpurun_out/ | tail -8
