@@ -223,7 +223,9 @@ class Graph(object):
         if key in steps:
             return steps[key](*dev_inputs)
         seen[key] = seen.get(key, 0) + 1
-        if seen[key] > 2:
+        # every captured step keeps its own activation pool (GBs at the benchmark shape): with dynamically padded batches
+        # (data_load.py:534-541) only the hp.max_cuda_graphs most frequent shapes get one, the others run eagerly
+        if seen[key] > 2 and len(steps) < getattr(self.hp, "max_cuda_graphs", 4):
             steps[key] = self.capture_train_step(*dev_inputs, warmup=0)     # two eager calls already warmed everything
             return steps[key](*dev_inputs)
         return self.train_step_device(*dev_inputs)

@@ -144,7 +144,7 @@ int launch_gemm(GemmArgs& a, int zdim, cudaStream_t st) {
     // conv-style A already split into planes: feed it with TMA tensor copies (flat tiles, padding = out-of-range / fix-up)
     a.a_tma = 0; a.b_tma = 0; if (!a.r_tma) a.items = 1;
     if (g_use_tma && a.a_mode == A_KMAJOR && a.A.hi && a.A.mul == 1 && a.A.L == a.A.Ls && a.z_mode == Z_NONE &&
-        !(a.Kc & 7) && a.M % a.A.L == 0) {
+        a.M % a.A.L == 0) {
         if (make_plane_tmap2d(&a.tmA_hi, a.A.hi, a.Kc, a.M, a.A.ld) && make_plane_tmap2d(&a.tmA_lo, a.A.lo, a.Kc, a.M, a.A.ld)) {
             a.a_tma = 1; a.items = a.M / a.A.L;
         }
@@ -384,14 +384,13 @@ int launch_ln_act_fwd(const float* z, long long ldz, const float* gamma, const f
                       uint64_t seed, const long long* step, cudaStream_t st) {
     const int grid = rows_grid(rows, 8);
     float* y = yo->f32; const long long ldy = yo->ld;
-    if (yo->hi && !(vec_ok(C, ldz, ldy, y_sig ? ldys : 4) && !(yo->ldp & 7)))
-        return fail(OPH_EINVAL, "split-bf16 output planes need C in {256,512,1024} and 16-byte aligned rows%s");
+    if (yo->hi && (!yo->lo || (yo->ldp & 7))) return fail(OPH_EINVAL, "split-bf16 output planes need 16-byte aligned rows%s");
     if (vec_ok(C, ldz, ldy, y_sig ? ldys : 4)) {
 #define OPH_LAUNCH(V) launch_cfg(grid, 256, 0, st)(ln_act_fwd_vec_kernel<V>, z, ldz, gamma, beta, y, ldy, y_sig, ldys, yo->hi, yo->lo, yo->ldp, stats, (int)rows, act, norm, drop_p, seed, step)
         if (C == 256) OPH_LAUNCH(2); else if (C == 512) OPH_LAUNCH(4); else OPH_LAUNCH(8);
 #undef OPH_LAUNCH
     } else {
-        launch_cfg(grid, 256, 0, st)(ln_act_fwd_kernel, z, ldz, gamma, beta, y, ldy, y_sig, ldys, stats, (int)rows, C, act, norm, drop_p, seed, step);
+        launch_cfg(grid, 256, 0, st)(ln_act_fwd_kernel, z, ldz, gamma, beta, y, ldy, y_sig, ldys, yo->hi, yo->lo, yo->ldp, stats, (int)rows, C, act, norm, drop_p, seed, step);
     }
     return check_launch("ln_act_fwd_kernel");
 }
@@ -417,7 +416,14 @@ int launch_ln_act_bwd(const float* dy, long long lddy, const float* z, long long
         if (C == 256) launch_cfg(grid, 256, smem, st)(ln_act_bwd_vec_kernel<2>, dy, lddy, z, ldz, stats, gamma, beta, nullptr, 0, h, l, C, dgamma, dbeta, dbias, (int)rows, act, norm, drop_p, seed, step);
         else          launch_cfg(grid, 256, smem, st)(ln_act_bwd_vec_kernel<4>, dy, lddy, z, ldz, stats, gamma, beta, nullptr, 0, h, l, C, dgamma, dbeta, dbias, (int)rows, act, norm, drop_p, seed, step);
     } else {
-        launch_cfg(rows_grid(rows, 8), 256, smem, st)(ln_act_bwd_kernel, dy, lddy, z, ldz, stats, gamma, beta, dz, lddz, dgamma, dbeta, dbias, (int)rows, C, act, norm, drop_p, seed, step);
+        // other widths (80, 513, 1025, 1024): planes with rows padded to 8 elements when the caller's dz buffer holds them
+        const long long ldp = (C + 7) / 8 * 8;
+        unsigned short* h = nullptr; unsigned short* l = nullptr;
+        if (lddz >= ldp && !(reinterpret_cast<uintptr_t>(dz) & 15)) {
+            h = reinterpret_cast<unsigned short*>(dz); l = h + rows * ldp;
+            dzmap->hi = h; dzmap->lo = l; dzmap->ld = ldp; dzmap->ptr = nullptr;
+        }
+        launch_cfg(rows_grid(rows, 8), 256, smem, st)(ln_act_bwd_kernel, dy, lddy, z, ldz, stats, gamma, beta, dz, lddz, h, l, ldp, dgamma, dbeta, dbias, (int)rows, C, act, norm, drop_p, seed, step);
     }
     return check_launch("ln_act_bwd_kernel");
 }
@@ -437,7 +443,6 @@ int launch_wgrad(const OperandMap& a, int M, const int* a_off, int aL, int aLs, 
     g.r_tma = 0;
     const int items = aL > 0 ? R / aL : 0;
     if (g_use_tma && g.A.hi && g.Bm.hi && a_mul == 1 && b_mul == 1 && aL == aLs && bL == bLs && aL == bL && items * aL == R &&
-        !(M & 7) && !(N & 7) &&
         make_plane_tmap(&g.tmA_hi, g.A.hi, M, aL, items, g.A.ld, GEMM_BK) && make_plane_tmap(&g.tmA_lo, g.A.lo, M, aL, items, g.A.ld, GEMM_BK) &&
         make_plane_tmap(&g.tmB_hi, g.Bm.hi, N, bL, items, g.Bm.ld, GEMM_BK) && make_plane_tmap(&g.tmB_lo, g.Bm.lo, N, bL, items, g.Bm.ld, GEMM_BK)) {
         g.r_tma = 1; g.items = items;
@@ -591,7 +596,6 @@ int oph_conv1d_fwd(const oph_act* x, const void* packed_w, const float* bias, co
                    uint64_t seed, const long long* step, oph_stream_t stream) {
     if (k < 1 || k > 3) return fail(OPH_EINVAL, "conv1d_fwd: k must be 1..3%s");
     OPH_TRY(check_act(x, "conv1d_fwd x"));
-    if (x->hi && (Cin & 7)) return fail(OPH_EINVAL, "conv1d_fwd: planes need Cin % 8 == 0%s");
     GemmArgs g = blank();
     g.a_mode = A_KMAJOR; g.b_mode = B_PACKED;
     set_operand(g.A, x); g.A.L = L; g.A.Ls = L; g.A.mul = 1;

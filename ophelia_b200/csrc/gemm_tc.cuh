@@ -6,9 +6,11 @@
 // 256-column output tile (x one tap / batch item / split-K slice): each CTA of the pair owns 128 rows of the fp32
 // accumulator in its tensor memory and stages its own 128 rows of A plus HALF of every B stage; the MMA unit reads
 // the other half from the partner's shared memory.  The 512 TMEM columns hold TWO accumulator stages, so the
-// epilogue of unit i (dedicated warps) overlaps the main loop of unit i+1.  fp32 activations are split into
-// (hi, lo) bf16 planes by the producer warps on their way into SWIZZLE_128B shared-memory tiles; pre-packed weight
-// images arrive through the bulk-copy (TMA) engine.  One thread of the leader CTA issues every tcgen05.mma.
+// epilogue of unit i overlaps the main loop of unit i+1.  Operands normally arrive as TMA tensor copies of
+// split-bf16 planes (activations: written by the row-wise kernels; weights: pre-packed smem images) that signal the
+// leader CTA's barriers directly; fp32 operands without planes are split by 16 producer warps on their way into the
+// SWIZZLE_128B tiles.  One thread of the leader CTA issues every tcgen05.mma; when nothing needs producing, the
+// producer warps drain the accumulators (16-warp epilogue).
 #pragma once
 #include <cuda.h>
 #include "oph_ptx.cuh"

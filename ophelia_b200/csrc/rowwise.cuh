@@ -38,6 +38,20 @@ __device__ __forceinline__ unsigned long long eff_seed(unsigned long long seed, 
     return step ? seed + (unsigned long long)(*step) * 0xD1342543DE82EF95ull : seed;
 }
 
+__device__ __forceinline__ void split4(const float4& v, uint2& hh, uint2& ll) {
+    const __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+    const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+    const __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2bfloat162_rn(v.z - f1.x, v.w - f1.y);
+    hh.x = *reinterpret_cast<const uint32_t*>(&h0); hh.y = *reinterpret_cast<const uint32_t*>(&h1);
+    ll.x = *reinterpret_cast<const uint32_t*>(&l0); ll.y = *reinterpret_cast<const uint32_t*>(&l1);
+}
+__device__ __forceinline__ void st_split1(unsigned short* hi, unsigned short* lo, long long idx, float v) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+    hi[idx] = *reinterpret_cast<const unsigned short*>(&h);
+    lo[idx] = *reinterpret_cast<const unsigned short*>(&l);
+}
+
 struct RowStats { float mean, rstd; };
 
 // two-pass moments like tf.nn.moments: mean, then mean of squared deviations (biased)
@@ -55,7 +69,8 @@ __device__ __forceinline__ RowStats row_stats(const float* __restrict__ z, int C
 // conv1d tail (modules.py:137-141): y = dropout(act(LN(z)));  optional y_sig = sigmoid(LN(z)) (networks.py:430-433)
 __global__ void ln_act_fwd_kernel(const float* __restrict__ z, long long ldz, const float* __restrict__ gamma,
                                   const float* __restrict__ beta, float* __restrict__ y, long long ldy,
-                                  float* __restrict__ y_sig, long long ldys, float* __restrict__ stats,
+                                  float* __restrict__ y_sig, long long ldys, unsigned short* __restrict__ y_hi,
+                                  unsigned short* __restrict__ y_lo, long long ldp, float* __restrict__ stats,
                                   int rows, int C, int act, int norm, float drop_p, unsigned long long seed,
                                   const long long* step) {
     pdl_grid_sync();
@@ -75,6 +90,7 @@ __global__ void ln_act_fwd_kernel(const float* __restrict__ z, long long ldz, co
             float a = act == 1 ? fmaxf(u, 0.f) : u;
             if (drop_p > 0.f) a *= drop_scale(sd, (unsigned long long)row * C + c, drop_p, inv_keep);
             y[row * ldy + c] = a;
+            if (y_hi) st_split1(y_hi, y_lo, row * ldp + c, a);
         }
     }
 }
@@ -113,10 +129,12 @@ __global__ void hc_post_fwd_kernel(const float* __restrict__ z, long long ldz, c
     }
 }
 
-// backward of ln_act: dz (pre-LN conv output gradient); column sums dgamma/dbeta/dbias via shared atomics
+// backward of ln_act: dz (pre-LN conv output gradient); column sums dgamma/dbeta/dbias via shared atomics.
+// Two passes over the row, nothing staged in dz: the output may be fp32 or split-bf16 planes (dz_hi != NULL).
 __global__ void ln_act_bwd_kernel(const float* __restrict__ dy, long long lddy, const float* __restrict__ z, long long ldz,
                                   const float* __restrict__ stats, const float* __restrict__ gamma,
                                   const float* __restrict__ beta, float* __restrict__ dz, long long lddz,
+                                  unsigned short* __restrict__ dz_hi, unsigned short* __restrict__ dz_lo, long long ldp,
                                   float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias,
                                   int rows, int C, int act, int norm, float drop_p, unsigned long long seed,
                                   const long long* step) {
@@ -132,35 +150,35 @@ __global__ void ln_act_bwd_kernel(const float* __restrict__ dy, long long lddy, 
     for (long long row = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * wpb) {
         const float* zr = z + row * ldz;
         const float* dyr = dy + row * lddy;
-        float* dzr = dz + row * lddz;
         float mean = 0.f, rstd = 1.f;
         if (norm) { mean = stats[row * 2]; rstd = stats[row * 2 + 1]; }
-        float s1 = 0.f, s2 = 0.f;
-        for (int c = lane; c < C; c += 32) {
-            const float xh = norm ? (zr[c] - mean) * rstd : zr[c];
+        auto du_at = [&](int c, float& xh) {       // gradient w.r.t. the LN output u (after dropout / ReLU backward)
+            xh = norm ? (zr[c] - mean) * rstd : zr[c];
             const float u = norm ? xh * gamma[c] + beta[c] : xh;
             float du = dyr[c];
             if (drop_p > 0.f) du *= drop_scale(sd, (unsigned long long)row * C + c, drop_p, inv_keep);
             if (act == 1 && !(u > 0.f)) du = 0.f;
-            if (norm) {
+            return du;
+        };
+        float s1 = 0.f, s2 = 0.f;
+        if (norm) {
+            for (int c = lane; c < C; c += 32) {
+                float xh;
+                const float du = du_at(c, xh);
                 atomicAdd(&sacc[c], du * xh);
                 atomicAdd(&sacc[C + c], du);
                 const float dxh = du * gamma[c];
                 s1 += dxh; s2 += dxh * xh;
-                dzr[c] = dxh;                  // staged; finished below
-            } else {
-                dzr[c] = du;
-                atomicAdd(&sacc[2 * C + c], du);
             }
-        }
-        if (norm) {
             s1 = warp_sum(s1) * invC; s2 = warp_sum(s2) * invC;
-            for (int c = lane; c < C; c += 32) {
-                const float xh = (zr[c] - mean) * rstd;
-                const float d = rstd * (dzr[c] - s1 - xh * s2);
-                dzr[c] = d;
-                atomicAdd(&sacc[2 * C + c], d);
-            }
+        }
+        for (int c = lane; c < C; c += 32) {
+            float xh;
+            const float du = du_at(c, xh);
+            const float d = norm ? rstd * (du * gamma[c] - s1 - xh * s2) : du;
+            if (dz_hi) st_split1(dz_hi, dz_lo, row * ldp + c, d);
+            else dz[row * lddz + c] = d;
+            atomicAdd(&sacc[2 * C + c], d);
         }
     }
     __syncthreads();
@@ -249,20 +267,6 @@ __device__ __forceinline__ float guide_w(int n, int t, float inv_maxN, float inv
 
 // in: S[b][t][0..N) scaled scores.  out: probabilities in place, optional transposed alignments [B][N][T],
 // argmax (first maximum), guided-attention partial sum  sum_{n<maxN,t<maxT} A*W  (architectures.py:258-270)
-__device__ __forceinline__ void split4(const float4& v, uint2& hh, uint2& ll) {
-    const __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
-    const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
-    const __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2bfloat162_rn(v.z - f1.x, v.w - f1.y);
-    hh.x = *reinterpret_cast<const uint32_t*>(&h0); hh.y = *reinterpret_cast<const uint32_t*>(&h1);
-    ll.x = *reinterpret_cast<const uint32_t*>(&l0); ll.y = *reinterpret_cast<const uint32_t*>(&l1);
-}
-__device__ __forceinline__ void st_split1(unsigned short* hi, unsigned short* lo, long long idx, float v) {
-    const __nv_bfloat16 h = __float2bfloat16_rn(v);
-    const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
-    hi[idx] = *reinterpret_cast<const unsigned short*>(&h);
-    lo[idx] = *reinterpret_cast<const unsigned short*>(&l);
-}
-
 __global__ void softmax_fwd_kernel(float* __restrict__ S, long long ldS, int B, int T, int N,
                                    const int* __restrict__ prev_max, int win,
                                    float* __restrict__ align_t, int* __restrict__ argmax_out,
@@ -628,93 +632,6 @@ __device__ __forceinline__ void flush_acc(float (&acc)[NACC][VEC * 4], float* sa
         float* d = dst[idx / C];
         if (d) atomicAdd(d + (idx % C), sacc[idx]);
     }
-}
-
-template <int VEC>
-__global__ void __launch_bounds__(256) hc_post_bwd_vec_kernel(
-        const float* __restrict__ dy, long long lddy, const float* __restrict__ z, long long ldz,
-        const float* __restrict__ x, long long ldx, const float* __restrict__ stats,
-        const float* __restrict__ g1, const float* __restrict__ b1, const float* __restrict__ g2,
-        const float* __restrict__ b2, float* __restrict__ dz, long long lddz, unsigned short* __restrict__ dz_hi,
-        unsigned short* __restrict__ dz_lo, long long ldp, float* __restrict__ dxres, long long lddx,
-        float* __restrict__ dg1, float* __restrict__ db1, float* __restrict__ dg2, float* __restrict__ db2,
-        float* __restrict__ dbias, int rows, int norm, float drop_p, unsigned long long seed, const long long* step) {
-    pdl_grid_sync();
-    constexpr int C = 128 * VEC;
-    extern __shared__ float sacc[];            // [6][C]
-    for (int i = threadIdx.x; i < 6 * C; i += blockDim.x) sacc[i] = 0.f;
-    __syncthreads();
-    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-    const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-    const float invC = 1.f / (float)C;
-    const unsigned long long sd = eff_seed(seed, step);
-    float4 G1[VEC], B1[VEC], G2[VEC], B2[VEC];
-    if (norm) { ld_row<VEC>(g1, lane, G1); ld_row<VEC>(b1, lane, B1); ld_row<VEC>(g2, lane, G2); ld_row<VEC>(b2, lane, B2); }
-    float acc[6][VEC * 4];                     // dg1, db1, dg2, db2, dbias(H1), dbias(H2)
-#pragma unroll
-    for (int k = 0; k < 6; ++k)
-#pragma unroll
-        for (int i = 0; i < VEC * 4; ++i) acc[k][i] = 0.f;
-    for (long long row = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * wpb) {
-        float4 z1[VEC], z2[VEC], xv[VEC], dv[VEC];
-        ld_row<VEC>(z + row * ldz, lane, z1);
-        ld_row<VEC>(z + row * ldz + C, lane, z2);
-        ld_row<VEC>(x + row * ldx, lane, xv);
-        ld_row<VEC>(dy + row * lddy, lane, dv);
-        float m1 = 0.f, r1 = 1.f, m2 = 0.f, r2 = 1.f;
-        if (norm) { const float4 s = __ldg(reinterpret_cast<const float4*>(stats + row * 4)); m1 = s.x; r1 = s.y; m2 = s.z; r2 = s.w; }
-        float a1 = 0.f, a2 = 0.f, c1 = 0.f, c2 = 0.f;
-        float4 e1v[VEC], e2v[VEC], xr[VEC];
-#pragma unroll
-        for (int i = 0; i < VEC; ++i)
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const float xh1 = norm ? (OPH_F4(z1[i], e) - m1) * r1 : OPH_F4(z1[i], e);
-                const float xh2 = norm ? (OPH_F4(z2[i], e) - m2) * r2 : OPH_F4(z2[i], e);
-                const float u1 = norm ? xh1 * OPH_F4(G1[i], e) + OPH_F4(B1[i], e) : xh1;
-                const float h = norm ? xh2 * OPH_F4(G2[i], e) + OPH_F4(B2[i], e) : xh2;
-                const float g = sigmoidf_(u1);
-                float d_o = OPH_F4(dv[i], e);
-                if (drop_p > 0.f) d_o *= drop_scale(sd, (unsigned long long)row * C + i * 128 + lane * 4 + e, drop_p, inv_keep);
-                OPH_F4(xr[i], e) = d_o * (1.f - g);
-                const float du1 = d_o * (h - OPH_F4(xv[i], e)) * g * (1.f - g);
-                const float du2 = d_o * g;
-                if (norm) {
-                    acc[0][i * 4 + e] += du1 * xh1; acc[1][i * 4 + e] += du1;
-                    acc[2][i * 4 + e] += du2 * xh2; acc[3][i * 4 + e] += du2;
-                    const float e1 = du1 * OPH_F4(G1[i], e), e2 = du2 * OPH_F4(G2[i], e);
-                    a1 += e1; a2 += e1 * xh1; c1 += e2; c2 += e2 * xh2;
-                    OPH_F4(e1v[i], e) = e1; OPH_F4(e2v[i], e) = e2;
-                    OPH_F4(z1[i], e) = xh1; OPH_F4(z2[i], e) = xh2;     // keep x-hat for the second half
-                } else {
-                    OPH_F4(e1v[i], e) = du1; OPH_F4(e2v[i], e) = du2;
-                    acc[4][i * 4 + e] += du1; acc[5][i * 4 + e] += du2;
-                }
-            }
-        st_row<VEC>(dxres + row * lddx, lane, xr);
-        if (norm) {
-            a1 = warp_sum(a1) * invC; a2 = warp_sum(a2) * invC; c1 = warp_sum(c1) * invC; c2 = warp_sum(c2) * invC;
-#pragma unroll
-            for (int i = 0; i < VEC; ++i)
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float d1 = r1 * (OPH_F4(e1v[i], e) - a1 - OPH_F4(z1[i], e) * a2);
-                    const float d2 = r2 * (OPH_F4(e2v[i], e) - c1 - OPH_F4(z2[i], e) * c2);
-                    OPH_F4(e1v[i], e) = d1; OPH_F4(e2v[i], e) = d2;
-                    acc[4][i * 4 + e] += d1; acc[5][i * 4 + e] += d2;
-                }
-        }
-        if (dz_hi) {                           // the GEMMs are the only consumers of dz: write it in their operand format
-            st_row_planes<VEC>(dz_hi + row * ldp, dz_lo + row * ldp, lane, e1v);
-            st_row_planes<VEC>(dz_hi + row * ldp + C, dz_lo + row * ldp + C, lane, e2v);
-        } else {
-            st_row<VEC>(dz + row * lddz, lane, e1v);
-            st_row<VEC>(dz + row * lddz + C, lane, e2v);
-        }
-    }
-    float* const dst[6] = {norm ? dg1 : nullptr, norm ? db1 : nullptr, norm ? dg2 : nullptr, norm ? db2 : nullptr,
-                           dbias, dbias ? dbias + C : nullptr};
-    flush_acc<VEC, 6>(acc, sacc, lane, dst);
 }
 
 template <int VEC>

@@ -104,7 +104,7 @@ def normalize(inputs, scope="normalize", reuse=None, normtype='layer'):
 # ------------------------------------------------------------------------------------------------ conv1d
 def conv1d(inputs, filters=None, size=1, rate=1, padding="SAME", dropout_rate=0, use_bias=True, activation_fn=None,
            training=True, scope="conv1d", reuse=None, normtype='layer', lcc=0, codes=None,
-           *, out=None, in_shift=0, want_sigmoid=False):
+           *, out=None, in_shift=0, want_sigmoid=False, planes=True):
     """modules.py:91-146: conv (+bias) -> layer norm -> activation -> dropout (training only)."""
     assert use_bias and not lcc, "bias-free / learn_channel_contributions variants are outside the path"
     assert normtype in (None, 'layer'), "batch norm is unused by every shipped config"
@@ -133,7 +133,7 @@ def conv1d(inputs, filters=None, size=1, rate=1, padding="SAME", dropout_rate=0,
     step = _step_ptr(store, training)
     rec = _recording(training)
     y, ysig, saved = ops.conv1d_fwd(inputs, pk, store.get(bn), gamma, beta, rate, pad, in_shift, act, norm, drop, seed,
-                                    step, save=rec, y=out, want_sigmoid=want_sigmoid, planes=out is None)
+                                    step, save=rec, y=out, want_sigmoid=want_sigmoid, planes=planes and out is None)
     if rec:
         need_dx = not getattr(inputs, "_oph_no_grad", False)
 

@@ -168,7 +168,7 @@ def AudioDec(hp, R, training=True, speaker_codes=None, reuse=None):
     squash = hp.squash_output_t2m
     out = conv1d(tensor, filters=hp.n_mels, size=1, rate=1, padding="CAUSAL", dropout_rate=hp.dropout_rate,
                  training=training, scope="C_{}".format(i), normtype=hp.norm, reuse=reuse,
-                 want_sigmoid=squash); i += 1
+                 want_sigmoid=squash, planes=False); i += 1          # the logits feed no further product
     logits, Y = out if squash else (out, out)
     return logits, Y
 
@@ -211,6 +211,6 @@ def SSRN(hp, Y, training=True, speaker_codes=None, reuse=None):
                         scope="C_{}".format(i), normtype=hp.norm, reuse=reuse); i += 1
     squash = hp.squash_output_ssrn
     out = conv1d(tensor, size=1, rate=1, dropout_rate=hp.dropout_rate, training=training, scope="C_{}".format(i),
-                 normtype=hp.norm, reuse=reuse, want_sigmoid=squash)
+                 normtype=hp.norm, reuse=reuse, want_sigmoid=squash, planes=False)
     logits, Z = out if squash else (out, out)
     return logits, Z

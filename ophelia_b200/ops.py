@@ -63,7 +63,7 @@ def _pad4(c):
     return (c + 3) // 4 * 4
 
 
-PLANE_WIDTHS = (256, 512, 1024)      # channel counts for which the row-wise kernels can emit split-bf16 planes
+PLANE_WIDTHS = (256, 512, 1024)      # channel counts of the highway kernels (they always emit planes)
 
 
 def _act(t, use_planes=True, planes=None):
@@ -83,21 +83,27 @@ def _out_act(y, want_planes, given=None):
     (hi, lo) views (e.g. one half of a wider planes buffer)."""
     a = _lib.Act()
     a.f32, a.ld = y.data_ptr(), y.stride(1)
-    if given is not None and y.shape[2] in PLANE_WIDTHS:
+    if given is not None:
         hi, lo = given
         a.hi, a.lo, a.ldp = hi.data_ptr(), lo.data_ptr(), hi.stride(1)
         y._oph_planes = (hi, lo)
-    elif want_planes and y.shape[2] in PLANE_WIDTHS:
-        hi = torch.empty(y.shape, device=y.device, dtype=torch.bfloat16)
-        lo = torch.empty(y.shape, device=y.device, dtype=torch.bfloat16)
+    elif want_planes:                   # any width: plane rows are padded to 8 elements (16 bytes) for the tensor maps
+        B, L, C = y.shape
+        hi = torch.empty(B, L, _pad8(C), device=y.device, dtype=torch.bfloat16)[:, :, :C]
+        lo = torch.empty(B, L, _pad8(C), device=y.device, dtype=torch.bfloat16)[:, :, :C]
         a.hi, a.lo, a.ldp = hi.data_ptr(), lo.data_ptr(), hi.stride(1)
         y._oph_planes = (hi, lo)
     return a
 
 
+def _pad8(c):
+    return (c + 7) // 8 * 8
+
+
 def new_act(B, L, C, device):
-    """[B, L, C] view over a buffer whose row stride is padded to a multiple of 4 floats."""
-    ld = _pad4(C)
+    """[B, L, C] view over a buffer whose row stride is padded to a multiple of 8 floats (fp32 rows stay 16-byte
+    aligned, and the same bytes can hold the two bf16 planes of a gradient with 16-byte aligned rows)."""
+    ld = _pad8(C)
     if ld == C:
         return torch.empty(B, L, C, device=device, dtype=torch.float32)
     return torch.zeros(B, L, ld, device=device, dtype=torch.float32)[:, :, :C]
@@ -141,7 +147,7 @@ def conv1d_fwd(x, pk, bias, gamma, beta, rate=1, padding=SAME, in_shift=0, act=A
     ysig = new_act(B, L, cout, dev) if want_sigmoid else None
     ya = _out_act(y, planes)
     xpl = getattr(x, "_oph_planes", None)
-    if xpl is None and cin % 8 == 0:       # inputs from outside the row-wise kernels (mels, embeddings): split once per call
+    if xpl is None:                        # inputs from outside the row-wise kernels (mels, embeddings): split once per call
         xpl = split_planes(x)
     _lib.call("oph_conv1d_fwd", _act(x, planes=xpl), _p(pk.fwd), _p(bias), _p(gamma), _p(beta), _p(z), z.stride(1), _p(stats),
               ya, _p(ysig), ysig.stride(1) if ysig is not None else 0, B, L, cin, cout, pk.k, rate,
@@ -245,10 +251,6 @@ def embed_bwd(ids, dout, dtable):
 
 
 # ---------------------------------------------------------------------------------------------- attention
-def _pad8(c):
-    return (c + 7) // 8 * 8
-
-
 def split_planes(t, into=None):
     """Split-bf16 planes (hi, lo) [B, L, pad8(C)] of a [B, L, C] activation that did not come out of a row-wise kernel
     (mels, embeddings, fed K / V, the decoder-input gradient): one oph_split_planes launch.  `into` = (hi, lo) views to
