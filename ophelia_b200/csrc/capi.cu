@@ -203,7 +203,9 @@ int launch_gemm(GemmArgs& a, int zdim, cudaStream_t st) {
     a.split_from = (int)units; a.split_s = 1; a.split_red = 0;
     const bool can_red = a.atomic && !a.bias;
     // plain outputs the caller allows us to pre-zero (a.zero_bytes > 0): the slices of the remainder units RED into zeros
-    const bool can_zero = !a.atomic && a.zero_bytes > 0 && !a.addend && !a.Chi && a.c_mul == 1;
+    // (off by default, flag 16384: the arrival order of the REDs would make FORWARD results vary in the last bits from run
+    // to run, and with the side streams the idle SMs of a partial round are filled by other kernels anyway)
+    const bool can_zero = (g_gemm_dbg_flags_host & 16384) && !a.atomic && a.zero_bytes > 0 && !a.addend && !a.Chi && a.c_mul == 1;
     if (g_use_split && a.a_tma == 1 && a.b_mode == B_PACKED && (can_red || can_zero) && a.z_mode == Z_NONE && a.ytaps == 1) {
         const int P = GEMM_MAX_PAIRS, KB = a.ntaps * cdiv(a.Kc, GEMM_BK);
         const int rem = (int)(units % P);

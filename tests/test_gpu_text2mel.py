@@ -148,3 +148,33 @@ def test_side_streams_and_cuda_graph_match_single_stream():
     s1, s2 = g1.store.state_dict(), g2.store.state_dict()
     for name in s1:
         assert maxabs(s1[name], s2[name]) < 2e-5, name
+
+
+def test_full_size_properties_b32_n180_t870():
+    """BASELINE.json's training shape (B=32, N=180, T=870) is too large for the numpy oracle, so the forward pass is
+    checked there through properties the reference's graph has by construction: utterances do not interact
+    (architectures.py:188-239 has no cross-batch op; here tiles, taps and the boundary fix-up run across item
+    boundaries), AudioEnc / AudioDec are causal in time (networks.py:214-284, 360-435), attention rows are
+    distributions, and padded text positions embed to zero (modules.py:38-40)."""
+    from ophelia_b200.session import Session
+    B, N, T = 32, 180, 870
+    hp = make_hp(max_N=N, max_T=T)
+    P = oracle_params(hp, "t2m", seed=7)
+    b = synthetic_batch(hp, B, N, T, ragged=True)
+    g = _graph(hp, "generate_attention", P)
+    sess = Session()
+    Y, ali, Q = sess.run([g.Y, g.alignments, g.Q], {g.L: b["L"], g.mels: b["mels"]})
+    assert Y.shape == (B, T, 80) and np.isfinite(Y).all()
+    np.testing.assert_allclose(ali.sum(axis=1), 1.0, atol=2e-5)                    # softmax over the N keys
+    for i in (0, 17, 31):                                                            # one utterance at a time
+        Yi, ai = sess.run([g.Y, g.alignments], {g.L: b["L"][i:i + 1], g.mels: b["mels"][i:i + 1]})
+        # another batch size means another tile / split-K schedule, i.e. another summation order of the same fp32-grade
+        # arithmetic (differences at its 2e-5 noise level); leakage between utterances would show at the 1e-1 level
+        assert maxabs(Yi[0], Y[i]) < 1e-4 and maxabs(ai[0], ali[i]) < 2e-5
+    m2 = b["mels"].copy()
+    m2[:, 500:] = 1.0 - m2[:, 500:]                                                  # change the future only
+    Y2, Q2 = sess.run([g.Y, g.Q], {g.L: b["L"], g.mels: m2})
+    # frame t of the input feeds Q[t+1] onwards (one-frame shift, architectures.py:191)
+    # (same schedule in both runs and no atomics in the forward pass: bit-identical)
+    assert maxabs(Q2[:, :501], Q[:, :501]) == 0.0 and maxabs(Y2[:, :501], Y[:, :501]) == 0.0
+    assert maxabs(Y2[:, 501:], Y[:, 501:]) > 1e-3

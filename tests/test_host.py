@@ -116,3 +116,20 @@ def test_data_parallel_gradient_exchange_gloo():
         p.join(120)
         assert p.exitcode == 0
     assert sorted(out.get(timeout=5)[0] for _ in range(2)) == [0, 1]
+
+
+def test_end_of_sentence_bookkeeping_matches_reference_rule():
+    """synthesize.py:218-228: a sentence ends at the first frame whose attention argmax reaches its first padding
+    position (endcount_threshold = 1); the loop stops once every sentence has ended."""
+    from ophelia_b200.configuration import default_hparams
+    from ophelia_b200.synthesize import _update_ends, get_text_lengths
+    hp = default_hparams(max_N=8, max_T=6)
+    L = np.array([[3, 4, 5, 0, 0, 0, 0, 0], [1, 2, 3, 4, 5, 6, 0, 0]], np.int32)
+    ends = get_text_lengths(L)
+    assert ends.tolist() == [3, 6]
+    endcounts = np.zeros(2, dtype=int)
+    t_ends = np.ones(2, dtype=int) * hp.max_T
+    argmax_per_frame = [[0, 0], [1, 2], [3, 4], [3, 6], [3, 6]]      # sentence 0 reaches its end at frame 2, 1 at frame 3
+    stops = [_update_ends(hp, np.array(a), ends, endcounts, t_ends, j) for j, a in enumerate(argmax_per_frame)]
+    assert stops == [False, False, False, True, True]
+    assert t_ends.tolist() == [2, 3]
