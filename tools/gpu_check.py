@@ -430,7 +430,10 @@ GROUPS = {
 def main():
     print(torch.cuda.get_device_name(0), flush=True)
     t0 = time.time()
+    only = [a for a in sys.argv[1:] if not a.startswith("-")]       # optional group names
     for name, cases in GROUPS.items():
+        if only and name not in only:
+            continue
         for fn in cases:
             run(name, fn)
     print("checks took %.1fs" % (time.time() - t0), flush=True)
