@@ -205,7 +205,7 @@ def run_ours(args):
     e1.record()
     sync_all()
     ms = e0.elapsed_time(e1) / args.steps
-    prof = (ctypes.c_double * 15)()
+    prof = (ctypes.c_double * 21)()
     lib.oph_profile_end(prof)
     hp.use_side_streams = True
     launches = (lib.oph_launch_count() - launches0) // args.steps
@@ -255,9 +255,17 @@ def run_ours(args):
     names = ["other", "conv_fwd", "dgrad", "wgrad", "attention"]
     tot_n = sum(prof[i * 3] for i in range(5)); tot_ms = sum(prof[i * 3 + 1] for i in range(5)); tot_fl = sum(prof[i * 3 + 2] for i in range(5))
     achieved = tot_fl / (tot_ms * 1e-3) / 1e12 if tot_ms > 0 else 0.0
+    row_n, row_ms, row_by = prof[15] + prof[18], prof[16] + prof[19], prof[17] + prof[20]
+    row_gbs = row_by / (row_ms * 1e-3) / 1e9 if row_ms > 0 else 0.0
     breakdown = {names[i]: {"launches_per_step": prof[i * 3] / args.steps, "ms_per_step": prof[i * 3 + 1] / args.steps,
                             "tflops": (prof[i * 3 + 2] / (prof[i * 3 + 1] * 1e-3) / 1e12) if prof[i * 3 + 1] > 0 else 0.0}
                  for i in range(5) if prof[i * 3] > 0}
+    if "attention" in breakdown:       # the attention block is HBM-bound (AI 58-75 FLOP/B); report that fraction too
+        att_bytes = 3.0 * 4.0 * args.batch * (2.0 * args.T * 256 + 2.0 * args.N * 256)      # fwd + bwd, A never counted
+        att = breakdown["attention"]
+        att["algorithmic_gbs"] = att_bytes / (att["ms_per_step"] * 1e-3) / 1e9
+        att["frac_of_hbm_peak"] = att["algorithmic_gbs"] / pk["hbm"]
+        att["frac_of_tensor_peak"] = att["tflops"] / pk["tensor_sustained"]
     line = {
         "metric": METRIC if t2m else METRIC_SSRN, "value": frames_per_step / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -280,6 +288,12 @@ def run_ours(args):
                      "share_of_step": (tot_ms / args.steps) / ms_eager,
                      "note": "achieved counts ALGORITHMIC FLOPs once; the split-bf16 scheme issues 3 tensor passes per "
                              "FLOP, so the ceiling of this number is peak/3"},
+        "roofline_hbm": {"kernel": "row-wise LayerNorm / highway tails (hc_post_fwd/bwd_wide, ln_act_fwd/bwd)", "bound": "hbm",
+                         "achieved": row_gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": row_gbs / pk["hbm"], "traffic": None,
+                         "launches_per_step": row_n / args.steps, "ms_per_step": row_ms / args.steps,
+                         "forward_gbs": (prof[17] / (prof[16] * 1e-3) / 1e9) if prof[16] > 0 else 0.0,
+                         "backward_gbs": (prof[20] / (prof[19] * 1e-3) / 1e9) if prof[19] > 0 else 0.0,
+                         "note": "algorithmic bytes (fp32 in/out + operand planes) over CUDA-event time, eager single stream"},
         "gemm_breakdown": breakdown,
         "clocks": clk, "loss_components": last_loss, "global_step": int(gs),
     }

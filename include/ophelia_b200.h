@@ -42,13 +42,16 @@ const char* oph_last_error(void);
 /* ---- instrumentation used by bench.py ---------------------------------------------------------------------
  * oph_launch_count: kernels launched by this library so far (all streams).
  * oph_profile_begin/end: time every launch of the tcgen05 GEMM core with CUDA events on its own stream;
- * out is double[OPH_NUM_TAGS*3] = per tag (launches, summed milliseconds, summed algorithmic FLOPs). */
+ * oph_profile_begin/end also time the row-wise LayerNorm / highway kernels;
+ * out is double[OPH_NUM_TAGS*3] = per tag (launches, summed milliseconds, summed algorithmic FLOPs or bytes). */
 #define OPH_TAG_OTHER 0
 #define OPH_TAG_CONV_FWD 1
 #define OPH_TAG_DGRAD 2
 #define OPH_TAG_WGRAD 3
 #define OPH_TAG_ATTENTION 4
-#define OPH_NUM_TAGS 5
+#define OPH_TAG_ROW_FWD 5   /* LayerNorm / highway forward tails: third value = algorithmic BYTES */
+#define OPH_TAG_ROW_BWD 6
+#define OPH_NUM_TAGS 7
 long long oph_launch_count(void);
 /* diagnostics: device buffer long long[74][8]; every GEMM launch overwrites per CTA pair
  * (total cycles, cycles waiting for an accumulator stage, for A, for B, k-blocks). NULL disables. */

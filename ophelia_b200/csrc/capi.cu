@@ -67,6 +67,28 @@ struct launch_cfg {
     }
 };
 
+// CUDA events around one launch while profiling is on (oph_profile_begin/end); `work` = algorithmic FLOPs (GEMM tags) or
+// algorithmic bytes (row-wise tags)
+struct ProfScope {
+    ProfRec rec{}; bool on = false; cudaStream_t st;
+    ProfScope(int tag, double work, cudaStream_t stream) : st(stream) {
+        if (!g_prof_on) return;
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(st, &cs);
+        if (cs != cudaStreamCaptureStatusNone) return;
+        on = true;
+        cudaEventCreate(&rec.e0); cudaEventCreate(&rec.e1);
+        rec.tag = tag; rec.flops = work;
+        cudaEventRecord(rec.e0, st);
+    }
+    ~ProfScope() {
+        if (!on) return;
+        cudaEventRecord(rec.e1, st);
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        g_prof.push_back(rec);
+    }
+};
+
 int fail(int code, const char* fmt, const char* detail = "") {   // fmt contains exactly one %s
     snprintf(g_err, sizeof(g_err), fmt, detail);
     return code;
@@ -227,24 +249,9 @@ int launch_gemm(GemmArgs& a, int zdim, cudaStream_t st) {
     }
     const int pairs = (int)(items < GEMM_MAX_PAIRS ? items : GEMM_MAX_PAIRS);
     dim3 grid(2 * pairs);
-    ProfRec rec{};
-    bool prof = false;
-    if (g_prof_on) {
-        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-        cudaStreamIsCapturing(st, &cs);
-        if (cs == cudaStreamCaptureStatusNone) {
-            prof = true;
-            cudaEventCreate(&rec.e0); cudaEventCreate(&rec.e1);
-            rec.tag = a.tag;
-            rec.flops = 2.0 * a.M * a.N * (a.prof_k ? a.prof_k : a.Kc) * (a.a_mode == A_KMAJOR ? a.ntaps : a.ytaps) * (a.z_mode == Z_BATCH ? a.zdim : 1);
-            cudaEventRecord(rec.e0, st);
-        }
-    }
-    launch_cfg(grid, GEMM_THREADS, GEMM_SMEM, st)(gemm_bf16x3_kernel, a);
-    if (prof) {
-        cudaEventRecord(rec.e1, st);
-        std::lock_guard<std::mutex> lk(g_prof_mu);
-        g_prof.push_back(rec);
+    {
+        ProfScope ps(a.tag, 2.0 * a.M * a.N * (a.prof_k ? a.prof_k : a.Kc) * (a.a_mode == A_KMAJOR ? a.ntaps : a.ytaps) * (a.z_mode == Z_BATCH ? a.zdim : 1), st);
+        launch_cfg(grid, GEMM_THREADS, GEMM_SMEM, st)(gemm_bf16x3_kernel, a);
     }
     return check_launch("gemm_bf16x3_kernel");
 }
@@ -386,6 +393,7 @@ int launch_ln_act_fwd(const float* z, long long ldz, const float* gamma, const f
                       uint64_t seed, const long long* step, cudaStream_t st) {
     const int grid = rows_grid(rows, 8);
     float* y = yo->f32; const long long ldy = yo->ld;
+    ProfScope ps(OPH_TAG_ROW_FWD, (double)rows * C * (yo->hi ? 12.0 : 8.0), st);
     if (yo->hi && (!yo->lo || (yo->ldp & 7))) return fail(OPH_EINVAL, "split-bf16 output planes need 16-byte aligned rows%s");
     if (vec_ok(C, ldz, ldy, y_sig ? ldys : 4)) {
 #define OPH_LAUNCH(V) launch_cfg(grid, 256, 0, st)(ln_act_fwd_vec_kernel<V>, z, ldz, gamma, beta, y, ldy, y_sig, ldys, yo->hi, yo->lo, yo->ldp, stats, (int)rows, act, norm, drop_p, seed, step)
@@ -411,6 +419,7 @@ int launch_ln_act_bwd(const float* dy, long long lddy, const float* z, long long
                       const long long* step, OperandMap* dzmap, cudaStream_t st) {
     const size_t smem = 3 * (size_t)C * sizeof(float);
     dzmap->ptr = dz; dzmap->ld = lddz; dzmap->hi = dzmap->lo = nullptr;
+    ProfScope ps(OPH_TAG_ROW_BWD, (double)rows * C * 12.0, st);
     if (vec_ok(C, lddy, ldz, lddz) && C <= 512 && lddz >= C) {
         const int grid = bwd_grid(rows);
         dz_as_planes(dz, rows, C, dzmap);
@@ -499,7 +508,7 @@ int oph_profile_begin(void) {
     return OPH_OK;
 }
 
-// out[tag*3 + {0,1,2}] = launches, summed device milliseconds, summed algorithmic FLOPs; tags 0..OPH_NUM_TAGS-1
+// out[tag*3 + {0,1,2}] = launches, summed device milliseconds, summed algorithmic FLOPs (bytes for the row-wise tags)
 int oph_profile_end(double* out) {
     std::lock_guard<std::mutex> lk(g_prof_mu);
     g_prof_on = false;
@@ -659,6 +668,7 @@ int oph_hc_fwd(const oph_act* x, const void* packed_w, const float* bias, const 
     const int grid = rows_grid(rows, 8);
     const bool vec = vec_ok(C, ldz, x->ld, y->ld);
     if (y->hi && !(vec && !(y->ldp & 7))) return fail(OPH_EINVAL, "hc_fwd: output planes need C in {256,512,1024}%s");
+    ProfScope ps(OPH_TAG_ROW_FWD, (double)rows * C * (y->hi ? 20.0 : 16.0), S(stream));
     if (vec && norm && !(g_gemm_dbg_flags_host & 4096)) {
         const int wpr = C / 256, groups = 8 / wpr;
         const int depth = ((g_gemm_dbg_flags_host & 8192) || C > 256) ? 3 : 2;         // ring slots per warp
@@ -698,6 +708,8 @@ int oph_hc_bwd(const float* dy, long long lddy, const oph_act* x, const float* z
     const size_t smem = 6 * (size_t)C * sizeof(float);
     OperandMap dzm; dzm.ptr = dz; dzm.ld = lddz; dzm.hi = dzm.lo = nullptr;
     (void)dxres; (void)ldxr;
+    {
+    ProfScope ps(OPH_TAG_ROW_BWD, (double)rows * C * 28.0, S(stream));
     if (norm && vec_ok(C, lddy, ldz, x->ld, lddz, lddx) && lddz >= 2 * C) {
         dz_as_planes(dz, rows, 2 * C, &dzm);
         unsigned short* h = const_cast<unsigned short*>(dzm.hi); unsigned short* l = const_cast<unsigned short*>(dzm.lo);
@@ -723,6 +735,7 @@ int oph_hc_bwd(const float* dy, long long lddy, const oph_act* x, const float* z
         launch_cfg(rows_grid(rows, 8), 256, smem, S(stream))(hc_post_bwd_kernel, 
             dy, lddy, z, ldz, x->f32, x->ld, stats, g1, b1, g2, b2, dz, lddz, dx, lddx, dg1, db1, dg2, db2, dbias,
             (int)rows, C, norm, drop_p, seed, step);
+    }
     }
     OPH_TRY(check_launch("hc_post_bwd_kernel"));
     cudaStream_t ws = dw ? fork_wgrad(S(stream)) : S(stream);

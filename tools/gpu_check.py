@@ -259,7 +259,7 @@ def case_attention(B, T, N, mono):
         report(tag + " R'", maxerr(buf, Rref), 2e-4)
         report(tag + " alignments", maxerr(align, Aref), 1e-4)
         report(tag + " argmax(mismatches)", float((argmax.cpu().long() != mxref).sum()), 0)
-        report(tag + " att_loss", abs(float(acc[3]) / (B * N * T) - float(att)), 1e-6)
+        report(tag + " att_loss", abs(float(acc[3]) / (B * N * T) - float(att.detach())), 1e-6)
         dRg = f32(dRp)
         dKV = torch.zeros(B, N, 2 * d, device=dev)
         dQ, dK, dV = ops.attention_bwd(dRg[:, :, :d], Qg, Kg, Vg, A, dq_addend=dRg[:, :, d:],

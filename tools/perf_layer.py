@@ -72,7 +72,7 @@ for _ in range(a.iters):
     run()
 e1.record()
 torch.cuda.synchronize()
-prof = (ctypes.c_double * 15)()
+prof = (ctypes.c_double * 21)()
 lib.oph_profile_end(prof)
 ms = e0.elapsed_time(e1) / a.iters
 print("%s B%d L%d C%d k%d planes%d dbg%d: %.3f ms per call" % (a.op, B, L, C, k, a.planes, a.dbg, ms))
@@ -81,6 +81,10 @@ for i, n in enumerate(["other", "conv_fwd", "dgrad", "wgrad", "attention"]):
         print("   gemm[%s]: %d launches/call, %.3f ms each, %.1f TFLOP/s algorithmic" %
               (n, prof[3 * i] / a.iters, prof[3 * i + 1] / prof[3 * i], prof[3 * i + 2] / prof[3 * i + 1] / 1e9))
 
+for i, n in ((5, "row fwd"), (6, "row bwd")):
+    if prof[3 * i] > 0:
+        print("   %s: %d launches/call, %.3f ms each, %.0f GB/s algorithmic" %
+              (n, prof[3 * i] / a.iters, prof[3 * i + 1] / prof[3 * i], prof[3 * i + 2] / prof[3 * i + 1] / 1e6))
 d = dbg.cpu().double()
 d = d[d[:, 0] > 0]
 if len(d):
