@@ -174,10 +174,23 @@ class Graph(object):
         return st
 
     # ---- optimiser step shared by both models (architectures.py:110-128)
-    def _apply_gradients(self):
+    def _grad_buckets(self, bounds):
+        """Bucketed, overlapped all-reduce of the flat gradient buffer (data parallel runs only)."""
+        # (off by default: at 8 GPUs it measured 7.37 ms per step against 7.35 ms with the single collective)
+        if self.process_group is None or not getattr(self.hp, "overlap_allreduce", False):
+            return None
+        gb = self.__dict__.get("_buckets")
+        if gb is None:
+            from .parallel import GradBuckets
+            gb = self._buckets = GradBuckets(self.store, bounds, self.process_group)
+        return gb
+
+    def _apply_gradients(self, buckets=None):
         hp, st = self.hp, self.store
         scale = 1.0
-        if self.process_group is not None:
+        if buckets is not None:
+            scale = buckets.finish()                                       # the buckets not yet launched + join
+        elif self.process_group is not None:
             from .parallel import allreduce_gradients
             scale = allreduce_gradients(st.grad_flat, self.process_group)  # NCCL sum over NVLink; only collective
         ops.adam_prepare(st.global_step, st.lr_t, hp.lr, hp.beta1, hp.beta2, hp.decay_lr)
@@ -434,17 +447,28 @@ class Text2MelGraph(Graph):
             s_text, s_w1, s_w2 = side
             s_w1.wait_stream(main)
             keep = []
+            # data parallel: gradient buckets in flat-buffer order (TextEnc first half | second half | AudioEnc | AudioDec)
+            # are all-reduced on a communication stream as soon as their layers' backward kernels are enqueued
+            buckets = self._grad_buckets(["Text2Mel/TextEnc/", "Text2Mel/TextEnc/HC_10/", "Text2Mel/AudioEnc/",
+                                          "Text2Mel/AudioDec/"])
             try:
                 ops.set_wgrad_stream(s_w1)
                 dRp = t_dec.backward(dlogits, release=False)
+                if buckets:
+                    buckets.launch(3, after=(main, s_w1))
                 dQ, dKV = out["R"]._oph_attention_bwd(dRp, watt / n_att)
                 s_text.wait_stream(main)
                 s_w2.wait_stream(main)
                 with torch.cuda.stream(s_text):
                     ops.set_wgrad_stream(s_w2)
-                    t_text.backward(dKV, release=False)
+                    marks = {6: lambda: buckets.launch(1, after=(s_text, s_w2))} if buckets else None   # HC_15..HC_10 done
+                    t_text.backward(dKV, release=False, marks=marks)
+                    if buckets:
+                        buckets.launch(0, after=(s_text, s_w2))
                 ops.set_wgrad_stream(s_w1)
                 t_aenc.backward(dQ, release=False)
+                if buckets:
+                    buckets.launch(2, after=(main, s_w1))
             finally:
                 keep.append(ops.take_keepalive())
                 ops.set_wgrad_stream(None)
@@ -453,6 +477,8 @@ class Text2MelGraph(Graph):
             for t in tapes:
                 t.release()
             del keep, dKV, dQ, dRp
+            self._apply_gradients(buckets)
+            return comps
         self._apply_gradients()
         return comps
 

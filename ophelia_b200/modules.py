@@ -28,11 +28,15 @@ class Tape(object):
     def __exit__(self, *exc):
         Tape.current = self._prev
 
-    def backward(self, grad, release=True):
+    def backward(self, grad, release=True, marks=None):
         """release=False keeps the closures (and the activations they hold) alive: needed while weight-gradient
-        GEMMs on a side stream may still read them; call release() after joining that stream."""
-        for fn in reversed(self.steps):
+        GEMMs on a side stream may still read them; call release() after joining that stream.
+        marks = {n: callback}: callback() runs once the backward functions of the LAST n layers are enqueued (gradient
+        buckets of those layers can then be all-reduced while the earlier layers' backward still runs)."""
+        for k, fn in enumerate(reversed(self.steps), 1):
             grad = fn(grad)
+            if marks and k in marks:
+                marks[k]()
         if release:
             self.steps = []
         return grad

@@ -44,6 +44,58 @@ def allreduce_gradients(flat_grad, group=None):
     return 1.0 / dist.get_world_size(group)
 
 
+class GradBuckets(object):
+    """Contiguous slices of the flat gradient buffer that are all-reduced as soon as the backward pass has produced them
+    (on a communication stream, overlapping the rest of the backward pass) instead of in one collective at the end.
+
+    `bounds` = variable-name prefixes in flat-buffer (creation) order that START a new bucket, e.g.
+    ["Text2Mel/TextEnc/", "Text2Mel/TextEnc/HC_10/", "Text2Mel/AudioEnc/", "Text2Mel/AudioDec/"]; bucket i covers the
+    variables from its first match up to the first match of bucket i+1."""
+
+    def __init__(self, store, bounds, group=None):
+        names = list(store.offsets)
+        starts = []
+        for b in bounds:
+            first = next(n for n in names if n.startswith(b))
+            starts.append(store.offsets[first])
+        assert starts == sorted(starts) and starts[0] == 0, "bucket prefixes must follow the creation order from the start"
+        ends = starts[1:] + [store.numel]
+        self.slices = [store.grad_flat[a:b] for a, b in zip(starts, ends)]
+        self.group = group
+        self.works = []
+        self.done = [False] * len(self.slices)
+        cuda = store.grad_flat.is_cuda
+        self.comm = torch.cuda.Stream(device=store.grad_flat.device) if cuda else None
+
+    def launch(self, i, after=()):
+        """All-reduce bucket i once the streams in `after` have finished what is enqueued on them so far."""
+        if not dist.is_initialized() or self.done[i]:
+            return
+        self.done[i] = True
+        if self.comm is None:
+            self.works.append(dist.all_reduce(self.slices[i], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            return
+        for s_ in after:
+            self.comm.wait_stream(s_)
+        with torch.cuda.stream(self.comm):
+            self.works.append(dist.all_reduce(self.slices[i], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def finish(self):
+        """Launch whatever is left, make the current stream wait for every bucket; returns the 1/world scale."""
+        if not dist.is_initialized():
+            return 1.0
+        cur = torch.cuda.current_stream() if self.comm is not None else None
+        for i in range(len(self.slices)):
+            self.launch(i, after=(cur,) if cur is not None else ())
+        for w in self.works:
+            w.wait()
+        if self.comm is not None:
+            cur.wait_stream(self.comm)
+        self.works = []
+        self.done = [False] * len(self.slices)
+        return 1.0 / dist.get_world_size(self.group)
+
+
 def broadcast_parameters(store, group=None, src=0):
     """Make every replica start from rank `src`'s values (same seed gives this for free; explicit for restores)."""
     if dist.is_initialized():

@@ -100,6 +100,19 @@ def _dp_worker(rank, world, port, out):
     scale = allreduce_gradients(flat, dist.group.WORLD)
     got = (flat * scale).numpy()
     np.testing.assert_allclose(got, full["mel"].mean(axis=(0, 1)), rtol=1e-6)
+    # bucketed exchange: slices of the flat gradient buffer reduced one by one, in any launch order, cover it exactly once
+    from ophelia_b200.parallel import GradBuckets
+    from ophelia_b200.variables import VariableStore
+    st = VariableStore("cpu").declare_all([("a/w", (5, 3), "ones"), ("a/b", (3,), "zeros"), ("b/w", (7,), "ones"),
+                                           ("c/w", (2, 2), "ones")]).finalize(with_optimizer=True)
+    st.grad_flat.copy_(torch.arange(st.numel, dtype=torch.float32) * (rank + 1))
+    gb = GradBuckets(st, ["a/", "b/", "c/"], dist.group.WORLD)
+    assert sum(s_.numel() for s_ in gb.slices) == st.numel
+    gb.launch(2)
+    gb.launch(0)
+    scale = gb.finish()                      # launches bucket 1, waits for all three
+    assert scale == 0.5
+    np.testing.assert_allclose(st.grad_flat.numpy(), np.arange(st.numel, dtype=np.float32) * 3.0)
     out.put((rank, True))
     dist.destroy_process_group()
 
