@@ -94,7 +94,7 @@ constexpr int NA_SLOTS = 3;
 constexpr int NB_SLOTS = 3;
 constexpr int N_ACC = 2;                            // accumulator stages in tensor memory (2 x 256 columns)
 constexpr int NPW = 16;                             // producer warps
-constexpr int GEMM_THREADS = (NPW + 8) * 32;        // producers, then 4 epilogue warps, then MMA / bulk copy / relay / idle
+constexpr int GEMM_THREADS = (NPW + 8) * 32;        // 16 producer (or epilogue) warps, 4 epilogue warps, then MMA issuer / copy loader / fix-up / idle
 constexpr int EPI_WARPS = 16;                       // epilogue workers when both operands come from the copy engines
 constexpr int EPI_STAGE_BYTES = EPI_WARPS * 2048;   // per-warp [32 rows][16 columns] fp32 transposition buffers
 constexpr int GEMM_SMEM = NA_SLOTS * A_SLOT + NB_SLOTS * B_SLOT + EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
@@ -162,7 +162,7 @@ __device__ __forceinline__ bool map_row(const OperandMap& o, int r, int tap, lon
     return ts >= 0 && ts < o.Ls;
 }
 
-// barrier indices (same layout in both CTAs; FULL_* / T_EMPTY are only used in the leader, LAND_B only in the partner)
+// barrier indices (same layout in both CTAs; FULL_* / T_EMPTY are only used in the leader, LAND_A in either CTA)
 constexpr int BAR_FULL_A = 0;                          // [NA_SLOTS] leader: 2*NPW producer-warp arrivals, or 1 + copy bytes of both CTAs
 constexpr int BAR_EMPTY_A = BAR_FULL_A + NA_SLOTS;     // [NA_SLOTS] leader's commit, multicast to both CTAs
 constexpr int BAR_FULL_B = BAR_EMPTY_A + NA_SLOTS;     // [NB_SLOTS]

@@ -1,6 +1,8 @@
 // Row-wise (HBM-bound) kernels of the dc_tts path: layer-norm / activation / highway mix (+ their backward),
 // softmax with the monotonic window mask and guided-attention loss, embedding, losses, Adam.
-// One warp owns one [C]-row; reductions along channels are warp shuffles; loads are lane-contiguous.
+// Generic kernels: one warp owns one [C]-row, reductions along channels are warp shuffles, loads are lane-contiguous.
+// Hot shapes (C = 256 / 512 / 1024) use the vectorised / streaming variants further down (float4 per lane, rows
+// prefetched through per-warp cp.async rings, WPR warps per row).
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>

@@ -63,9 +63,6 @@ def _pad4(c):
     return (c + 3) // 4 * 4
 
 
-PLANE_WIDTHS = (256, 512, 1024)      # channel counts of the highway kernels (they always emit planes)
-
-
 def _act(t, use_planes=True, planes=None):
     """oph_act for a [B, L, C] activation; planes ride along as `t._oph_planes = (hi, lo)` (bf16 [B, L, C]) or are
     passed explicitly."""
