@@ -420,7 +420,24 @@ int launch_ln_act_bwd(const float* dy, long long lddy, const float* z, long long
     const size_t smem = 3 * (size_t)C * sizeof(float);
     dzmap->ptr = dz; dzmap->ld = lddz; dzmap->hi = dzmap->lo = nullptr;
     ProfScope ps(OPH_TAG_ROW_BWD, (double)rows * C * 12.0, st);
-    if (vec_ok(C, lddy, ldz, lddz) && C <= 512 && lddz >= C) {
+    if (norm && vec_ok(C, lddy, ldz, lddz) && lddz >= C && !(g_gemm_dbg_flags_host & 32768)) {
+        dz_as_planes(dz, rows, C, dzmap);
+        unsigned short* h = const_cast<unsigned short*>(dzmap->hi); unsigned short* l = const_cast<unsigned short*>(dzmap->lo);
+        const int wpr = C / 256, groups = 8 / wpr, depth = 3;
+        long long gl = (rows + groups * 4 - 1) / (groups * 4);
+        const int gridw = (int)(gl < 1 ? 1 : (gl > 296 ? 296 : gl));              // two 8-warp blocks per SM
+        const size_t smw = (5 * (size_t)C + 32) * sizeof(float) + (size_t)8 * depth * LNB_SLOT;
+        static bool attr_done = false;
+        if (!attr_done) {
+            cudaFuncSetAttribute(ln_act_bwd_wide_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+            cudaFuncSetAttribute(ln_act_bwd_wide_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+            cudaFuncSetAttribute(ln_act_bwd_wide_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+            attr_done = true;
+        }
+#define OPH_LAUNCH(W) launch_cfg(gridw, 256, smw, st)(ln_act_bwd_wide_kernel<W>, dy, lddy, z, ldz, stats, gamma, beta, h, l, C, dgamma, dbeta, dbias, (int)rows, act, drop_p, seed, step, depth)
+        if (C == 256) OPH_LAUNCH(1); else if (C == 512) OPH_LAUNCH(2); else OPH_LAUNCH(4);
+#undef OPH_LAUNCH
+    } else if (vec_ok(C, lddy, ldz, lddz) && C <= 512 && lddz >= C) {
         const int grid = bwd_grid(rows);
         dz_as_planes(dz, rows, C, dzmap);
         unsigned short* h = const_cast<unsigned short*>(dzmap->hi); unsigned short* l = const_cast<unsigned short*>(dzmap->lo);

@@ -25,7 +25,9 @@ __device__ __forceinline__ float warp_sum(float v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+// (fast reciprocal: 2 ulp, far below the 2e-5 noise of the split-bf16 products; the IEEE division costs ~8 instructions
+// per element in kernels that are issue-bound as much as memory-bound)
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 
 // counter-based dropout mask (recomputed in backward): keep iff u >= rate; kept values scaled by 1/(1-rate)
 // (32-bit avalanche hash of (seed, element index): a handful of integer instructions per element)
@@ -1004,6 +1006,141 @@ __global__ void __launch_bounds__(256) hc_post_fwd_wide_kernel(
         }
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+}  // namespace oph
+
+// =================================================================================================
+// Backward of the conv tail (LayerNorm + ReLU + dropout) in the streaming layout of hc_post_bwd_wide_kernel: WPR warps
+// per row, gamma / beta in shared memory, rows prefetched through per-warp cp.async rings, three per-channel sums
+// (dgamma, dbeta, dbias) in 24 registers per lane for every width C = 256 * WPR.
+namespace oph {
+
+constexpr int LNB_SLOT = 4 * 512 + 32;                  // z, dy: two float4 per lane each + (mean, rstd)
+
+template <int WPR>
+__global__ void __launch_bounds__(256) ln_act_bwd_wide_kernel(
+        const float* __restrict__ dy, long long lddy, const float* __restrict__ z, long long ldz,
+        const float* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
+        unsigned short* __restrict__ dz_hi, unsigned short* __restrict__ dz_lo, long long ldp,
+        float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias,
+        int rows, int act, float drop_p, unsigned long long seed, const long long* step, int depth) {
+    pdl_grid_sync();
+    constexpr int C = 256 * WPR;
+    constexpr int GROUPS = 8 / WPR;
+    extern __shared__ __align__(16) float smem_f[];
+    float* sacc = smem_f;                               // [3][C]
+    float* spar = smem_f + 3 * C;                       // [2][C]: gamma, beta
+    float* sx = spar + 2 * C;                           // [2 parities][8 warps][2] partial row sums
+    uint8_t* ring = reinterpret_cast<uint8_t*>(sx + 32);
+    for (int i = threadIdx.x; i < 3 * C; i += 256) sacc[i] = 0.f;
+    for (int i = threadIdx.x; i < C; i += 256) { spar[i] = gamma[i]; spar[C + i] = beta[i]; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int grp = warp / WPR, part = warp % WPR;
+    const int cbase = part * 256 + lane * 4;
+    const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+    const float invC = 1.f / (float)C;
+    const unsigned long long sd = eff_seed(seed, step);
+    float acc[3][8];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[k][i] = 0.f;
+    const long long stride = (long long)gridDim.x * GROUPS;
+    long long row = (long long)blockIdx.x * GROUPS + grp;
+    uint8_t* myring = ring + (size_t)warp * depth * LNB_SLOT;
+    const uint32_t ring_u32 = (uint32_t)__cvta_generic_to_shared(myring) + lane * 16;
+    auto issue = [&](long long r, int slot) {
+        if (r < rows) {
+            const uint32_t d = ring_u32 + slot * LNB_SLOT;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                cp_async_16(d + (0 + i) * 512, z + r * ldz + cbase + 128 * i);
+                cp_async_16(d + (2 + i) * 512, dy + r * lddy + cbase + 128 * i);
+            }
+            if (lane == 0) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d - lane * 16 + 4 * 512), "l"(stats + r * 2) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    for (int d = 0; d < depth - 1; ++d) issue(row + d * stride, d);
+    int it = 0, slot = 0;
+    for (; row < rows; row += stride, ++it) {
+        {
+            int ns = slot + depth - 1; if (ns >= depth) ns -= depth;
+            issue(row + (long long)(depth - 1) * stride, ns);
+        }
+        if (depth == 2) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else if (depth == 3) asm volatile("cp.async.wait_group 2;" ::: "memory");
+        else asm volatile("cp.async.wait_group 3;" ::: "memory");
+        __syncwarp();
+        const uint8_t* sl = myring + slot * LNB_SLOT + lane * 16;
+        float4 zv[2], dv[2], ev[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            zv[i] = *reinterpret_cast<const float4*>(sl + (0 + i) * 512);
+            dv[i] = *reinterpret_cast<const float4*>(sl + (2 + i) * 512);
+        }
+        const float2 st = *reinterpret_cast<const float2*>(myring + slot * LNB_SLOT + 4 * 512);
+        if (++slot == depth) slot = 0;
+        const float mean = st.x, rstd = st.y;
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            float4 G = *reinterpret_cast<const float4*>(spar + cbase + 128 * i);
+            float4 Bt = *reinterpret_cast<const float4*>(spar + C + cbase + 128 * i);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float xh = (OPH_F4(zv[i], e) - mean) * rstd;
+                const float u = xh * OPH_F4(G, e) + OPH_F4(Bt, e);
+                float du = OPH_F4(dv[i], e);
+                if (drop_p > 0.f) du *= drop_scale(sd, (unsigned long long)row * C + cbase + 128 * i + e, drop_p, inv_keep);
+                if (act == 1 && !(u > 0.f)) du = 0.f;
+                acc[0][i * 4 + e] += du * xh; acc[1][i * 4 + e] += du;
+                const float dxh = du * OPH_F4(G, e);
+                s1 += dxh; s2 += dxh * xh;
+                OPH_F4(ev[i], e) = dxh; OPH_F4(zv[i], e) = xh;
+            }
+        }
+        s1 = warp_sum(s1); s2 = warp_sum(s2);
+        if (WPR > 1) {
+            float* my = sx + ((it & 1) * 8 + warp) * 2;
+            if (lane == 0) *reinterpret_cast<float2*>(my) = make_float2(s1, s2);
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(WPR * 32) : "memory");
+            s1 = s2 = 0.f;
+#pragma unroll
+            for (int w = 0; w < WPR; ++w) {
+                const float2 o = *reinterpret_cast<const float2*>(sx + ((it & 1) * 8 + grp * WPR + w) * 2);
+                s1 += o.x; s2 += o.y;
+            }
+        }
+        s1 *= invC; s2 *= invC;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float d = rstd * (OPH_F4(ev[i], e) - s1 - OPH_F4(zv[i], e) * s2);
+                OPH_F4(ev[i], e) = d; acc[2][i * 4 + e] += d;
+            }
+            uint2 hh, ll;
+            split4(ev[i], hh, ll);
+            *reinterpret_cast<uint2*>(dz_hi + row * ldp + cbase + 128 * i) = hh;
+            *reinterpret_cast<uint2*>(dz_lo + row * ldp + cbase + 128 * i) = ll;
+        }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) atomicAdd(&sacc[k * C + cbase + 128 * i + e], acc[k][i * 4 + e]);
+    __syncthreads();
+    float* const dst[3] = {dgamma, dbeta, dbias};
+    for (int idx = threadIdx.x; idx < 3 * C; idx += 256) {
+        float* d = dst[idx / C];
+        if (d) atomicAdd(d + (idx % C), sacc[idx]);
+    }
 }
 
 }  // namespace oph

@@ -302,7 +302,7 @@ def case_loss_adam():
     out = torch.zeros(5, device=dev)
     ops.loss_finalize(acc, out, B * L * C, 1.0, 0.4, 0.5, 0.0, 0.1, True, True)
     report("recon_loss dlogits", maxerr(dl, logits.grad), 1e-8)
-    ref = torch.tensor([0.4 * l1 + 0.5 * bd + 0.1 * l2, l1, bd, 0.0, l2])
+    ref = torch.tensor([float(0.4 * l1 + 0.5 * bd + 0.1 * l2), float(l1), float(bd), 0.0, float(l2)])
     report("loss components", maxerr(out, ref), 2e-6)
     # adam
     n = 1003
@@ -416,7 +416,7 @@ GROUPS = {
     "conv1d": [case_conv1d(2, 200, 80, 256, 1, 1, in_shift=1), case_conv1d(2, 200, 256, 80, 0, 1),
                case_conv1d(2, 60, 128, 512, 1, 0), case_conv1d(1, 150, 1024, 513, 0, 0),
                case_conv1d(1, 150, 513, 513, 1, 0), case_conv1d(2, 100, 256, 256, 0, 1, norm=False),
-               case_conv1d(1, 37, 1025, 1025, 1, 0)],
+               case_conv1d(1, 37, 1025, 1025, 1, 0), case_conv1d(1, 150, 512, 1024, 1, 0)],
     "hc": [case_hc(*a) for a in [(2, 200, 256, 3, 1, 1), (2, 200, 256, 3, 27, 1), (2, 60, 512, 3, 9, 0),
                                  (2, 60, 512, 1, 1, 0), (1, 130, 1024, 3, 1, 0), (3, 129, 256, 3, 3, 0)]],
     "hc_planes": [case_hc_planes(2, 200, 256, 3, 3, 1), case_hc_planes(2, 70, 512, 3, 27, 0), case_hc_planes(1, 130, 1024, 3, 1, 0)],
