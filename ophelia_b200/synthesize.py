@@ -80,10 +80,12 @@ def synth_codedtext2mel(hp, K, V, ends, g, sess, speaker_data=None, duration_dat
     return (Y, t_ends.tolist(), alignments)
 
 
-def synth_codedtext2mel_device(hp, K, V, ends, g, use_cuda_graph=True):
-    """Same loop with every tensor resident on the GPU; per frame only B int32 argmax values cross to the host.
-    With use_cuda_graph the per-frame forward (AudioEnc + Attention + AudioDec over all max_T frames, ~55 kernels) is
-    captured once and replayed: Y and prev_max_attentions are static buffers that the loop updates in place."""
+def synth_codedtext2mel_device(hp, K, V, ends, g, use_cuda_graph=True, check_every=8):
+    """Same loop with every tensor resident on the GPU.  With use_cuda_graph the per-frame forward (AudioEnc + Attention +
+    AudioDec over all max_T frames, ~55 kernels) is captured once and replayed: Y and prev_max_attentions are static
+    buffers that the loop updates in place.  The attention argmax of every frame is kept on the device and read back
+    only every `check_every` frames for the reference's end-of-sentence test (synthesize.py:218-228); frames computed
+    past the stopping frame are cleared again, so the results equal the frame-by-frame loop's."""
     dev = g.device
     K = g._to_device(K, torch.float32).contiguous()
     V = g._to_device(V, torch.float32).contiguous()
@@ -94,6 +96,7 @@ def synth_codedtext2mel_device(hp, K, V, ends, g, use_cuda_graph=True):
     Y = torch.zeros(B, hp.max_T, hp.n_mels, device=dev, dtype=torch.float32)
     alignments = torch.zeros(B, hp.max_N, hp.max_T, device=dev, dtype=torch.float32)
     prev = torch.zeros(B, device=dev, dtype=torch.int32)
+    history = torch.zeros(hp.max_T, B, device=dev, dtype=torch.int32)      # argmax of frame j at frame j
     ends = np.asarray(ends)
     endcounts = np.zeros(ends.shape, dtype=int)
     t_ends = np.ones(ends.shape, dtype=int) * hp.max_T
@@ -107,6 +110,8 @@ def synth_codedtext2mel_device(hp, K, V, ends, g, use_cuda_graph=True):
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             out = forward()
+    checked = 0
+    stop_at = None
     for j in range(hp.max_T):
         if graph is not None:
             graph.replay()
@@ -115,8 +120,19 @@ def synth_codedtext2mel_device(hp, K, V, ends, g, use_cuda_graph=True):
         Y[:, j, :].copy_(out["Y"][:, j, :])
         alignments[:, :, j].copy_(out["alignments"][:, :, j])
         prev.copy_(out["max_attentions"][:, j])
-        if _update_ends(hp, prev.cpu().numpy().astype(np.int64), ends, endcounts, t_ends, j):
-            break
+        history[j].copy_(prev)
+        if (j + 1) % max(1, check_every) == 0 or j == hp.max_T - 1:
+            host = history[checked:j + 1].cpu().numpy().astype(np.int64)
+            for jj in range(checked, j + 1):
+                if _update_ends(hp, host[jj - checked], ends, endcounts, t_ends, jj):
+                    stop_at = jj
+                    break
+            checked = j + 1
+            if stop_at is not None:
+                break
+    if stop_at is not None and stop_at + 1 < hp.max_T:   # the reference never computed these frames
+        Y[:, stop_at + 1:, :].zero_()
+        alignments[:, :, stop_at + 1:].zero_()
     return (Y.cpu().numpy(), t_ends.tolist(), alignments.cpu().numpy())
 
 

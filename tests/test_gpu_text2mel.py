@@ -120,6 +120,15 @@ def test_autoregressive_loop_matches_oracle():
     assert maxabs(a1, ar) < 1e-4 and maxabs(a2, ar) < 1e-4
     Y3, t3 = syn.synth_text2mel(hp, b["L"], g, sess)
     assert t3 == tr and maxabs(Y3, Yr) < 1e-3
+    # early stop (synthesize.py:225-228): with the sentence ends at position 1 every sentence ends within a few frames;
+    # the device route checks only every 4th frame and must clear the frames it computed past the stopping frame
+    ends1 = np.ones_like(ends)
+    Yr, tr, ar = on.synth_codedtext2mel(hp, P, Kr, Vr, ends1)
+    assert max(tr) < hp.max_T - 1, tr
+    for kw in (dict(use_cuda_graph=True, check_every=4), dict(use_cuda_graph=False, check_every=1)):
+        Y4, t4, a4 = syn.synth_codedtext2mel_device(hp, K, V, ends1, g, **kw)
+        assert t4 == tr and maxabs(Y4, Yr) < 1e-3 and maxabs(a4, ar) < 1e-4
+        assert (Y4[:, max(tr) + 1:] == 0).all() and (a4[:, :, max(tr) + 1:] == 0).all()
 
 
 def test_side_streams_and_cuda_graph_match_single_stream():
