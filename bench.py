@@ -299,7 +299,8 @@ def run_ours(args):
         "clocks": clk, "loss_components": last_loss, "global_step": int(gs),
     }
     if world == 1 and not args.no_cpu_baseline:
-        v, dt, cores, sample = cpu_reference(args, "t2m" if t2m else "ssrn", args.ref_batch, 1, 1)
+        # ~10 s of host work: 20 timed steps of the port at batch `ref_batch` (one SSRN step is already ~10x a Text2Mel one)
+        v, dt, cores, sample = cpu_reference(args, "t2m" if t2m else "ssrn", args.ref_batch, 20 if t2m else 2, 1)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "s_per_step": dt}
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -374,7 +375,7 @@ def main():
     ap.add_argument("--N", type=int, default=180)
     ap.add_argument("--T", type=int, default=870)
     ap.add_argument("--full-dim", dest="full_dim", type=int, default=513)
-    ap.add_argument("--ref-batch", dest="ref_batch", type=int, default=2)
+    ap.add_argument("--ref-batch", dest="ref_batch", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="skip the CUDA-graph replay of the training step")
     ap.add_argument("--overlap", action="store_true",

@@ -147,5 +147,39 @@ def synth_mel2mag(hp, Y, g, sess, batchsize=128):
     return Z
 
 
+_MODEL_SCOPES = {'t2m': 'Text2Mel', 'ssrn': 'SSRN'}     # synthesize.py:303-306 (the babbler variant is outside the path)
+
+
+def restore_latest_model_parameters(sess, hp, model_type, graph=None):
+    """synthesize.py:302-316: restore the trainable variables of `model_type` from the latest TF checkpoint under
+    `hp.logdir + "-" + model_type` (read without TensorFlow, ophelia_b200/tf_checkpoint.py).  `graph` is the
+    Text2MelGraph / SSRNGraph whose variable store receives the values (the reference finds its variables through the
+    default TF graph).  Returns the epoch string of the checkpoint name."""
+    import sys
+    from . import tf_checkpoint
+    assert model_type in _MODEL_SCOPES, "model type %r is outside the path" % (model_type,)
+    savepath = hp.logdir + "-" + model_type
+    latest_checkpoint = tf_checkpoint.latest_checkpoint(savepath)
+    if latest_checkpoint is None:
+        sys.exit('No %s at %s?' % (model_type, savepath))
+    latest_epoch = latest_checkpoint.strip('/ ').split('/')[-1].replace('model_epoch_', '')
+    tf_checkpoint.restore(graph.store, latest_checkpoint, strict=True, with_optimizer=False)
+    print("Model of type %s restored from latest epoch %s" % (model_type, latest_epoch))
+    return latest_epoch
+
+
+def restore_archived_model_parameters(sess, hp, model_type, epoch_number, graph=None):
+    """synthesize.py:319-330: same from `<logdir>-<model_type>/archive/model_epoch_<n>`."""
+    import os
+    import sys
+    from . import tf_checkpoint
+    assert model_type in _MODEL_SCOPES, "model type %r is outside the path" % (model_type,)
+    desired_checkpoint = hp.logdir + "-" + model_type + "/archive/model_epoch_" + str(epoch_number)
+    if not os.path.isfile(desired_checkpoint + '.index'):
+        sys.exit('No %s at %s?' % (model_type, desired_checkpoint))
+    tf_checkpoint.restore(graph.store, desired_checkpoint, strict=True, with_optimizer=False)
+    print("Model of type %s restored from archived epoch %s" % (model_type, epoch_number))
+
+
 def split_batch(synth_batch, end_indices):
     return [predmel[:end_indices[i], :] for i, predmel in enumerate(synth_batch)]

@@ -146,3 +146,67 @@ def test_end_of_sentence_bookkeeping_matches_reference_rule():
     stops = [_update_ends(hp, np.array(a), ends, endcounts, t_ends, j) for j, a in enumerate(argmax_per_frame)]
     assert stops == [False, False, False, True, True]
     assert t_ends.tolist() == [2, 3]
+
+
+def test_tf_checkpoint_format_roundtrip(tmp_path):
+    """V2 checkpoint (tensor bundle) reader / writer: checksum known answers, wire-format known answer of one
+    BundleEntryProto, multi-block index round trip, corruption detection, restore into a VariableStore by name."""
+    from ophelia_b200 import tf_checkpoint as tfc
+    from ophelia_b200.variables import VariableStore
+    assert tfc.crc32c(b"123456789") == 0xE3069283                         # CRC-32C check value (RFC 3720)
+    assert tfc.crc32c(b"\x00" * 32) == 0x8a9136aa and tfc.crc32c(b"\xff" * 32) == 0x62a8ab43   # leveldb crc32c_test
+    assert tfc.masked_crc32c(b"foo") != tfc.crc32c(b"foo")
+    # dtype DT_FLOAT, shape [2,3], offset 0 (omitted), size 24, crc32c fixed32
+    assert tfc._encode_entry(1, (2, 3), 0, 24, 0x01020304) == bytes.fromhex("0801120812020802120208032818350403020100"[:-2])
+    rng = np.random.default_rng(0)
+    tensors = {"global_step": np.asarray(1234, np.int32)}
+    for i in range(300):                                                   # > one 4 KiB index block, shared key prefixes
+        shape = tuple(int(s) for s in rng.integers(1, 6, rng.integers(1, 4)))
+        tensors["Text2Mel/TextEnc/HC_%d/conv1d/kernel_%d" % (i % 16, i)] = rng.standard_normal(shape).astype(np.float32)
+    prefix = str(tmp_path / "model_gs_1k")
+    tfc.write_checkpoint(prefix, tensors)
+    entries = tfc.list_variables(prefix)
+    assert list(entries) == sorted(tensors, key=lambda n: n.encode())
+    back = tfc.read_checkpoint(prefix, verify_data=True)
+    assert set(back) == set(tensors)
+    for n, a in tensors.items():
+        assert back[n].dtype == a.dtype and back[n].shape == a.shape and np.array_equal(back[n], a), n
+    raw = bytearray(open(prefix + ".index", "rb").read())
+    raw[10] ^= 0x40
+    open(prefix + ".index", "wb").write(bytes(raw))
+    with pytest.raises(IOError):
+        tfc.list_variables(prefix)
+    # store -> checkpoint -> store, with Adam slots and global_step, found through the `checkpoint` state file
+    specs = [("SSRN/C_1/conv1d/kernel", (1, 4, 8), "kernel"), ("SSRN/C_1/conv1d/bias", (8,), "zeros"),
+             ("SSRN/C_1/normalize/beta", (8,), "zeros"), ("SSRN/C_1/normalize/gamma", (8,), "ones")]
+    st = VariableStore("cpu", seed=3).declare_all(specs).finalize(with_optimizer=True)
+    st.m_flat.copy_(torch.arange(st.numel, dtype=torch.float32))
+    st.v_flat.copy_(torch.arange(st.numel, dtype=torch.float32) * 2)
+    st.global_step.fill_(77)
+    tfc.save(st, str(tmp_path / "model_gs_77"))
+    assert tfc.latest_checkpoint(str(tmp_path)) == str(tmp_path / "model_gs_77")
+    st2 = VariableStore("cpu", seed=9).declare_all(specs).finalize(with_optimizer=True)
+    unused = tfc.restore(st2, tfc.latest_checkpoint(str(tmp_path)))
+    assert unused == [] and torch.equal(st2.flat, st.flat) and int(st2.global_step.item()) == 77
+    w = st.offsets["SSRN/C_1/conv1d/kernel"]
+    assert torch.equal(st2.m_flat[w:w + 32], st.m_flat[w:w + 32]) and torch.equal(st2.v_flat[w:w + 32], st.v_flat[w:w + 32])
+
+
+def test_restore_latest_model_parameters_follows_reference_convention(tmp_path):
+    """synthesize.py:302-316: `<logdir>-<model_type>/checkpoint` names the latest `model_epoch_N` prefix."""
+    from ophelia_b200 import tf_checkpoint as tfc
+    from ophelia_b200.configuration import default_hparams
+    from ophelia_b200.synthesize import restore_latest_model_parameters
+    from ophelia_b200.variables import VariableStore
+    specs = [("SSRN/C_1/conv1d/kernel", (1, 4, 8), "kernel"), ("SSRN/C_1/conv1d/bias", (8,), "zeros")]
+    src = VariableStore("cpu", seed=1).declare_all(specs).finalize()
+    hp = default_hparams(logdir=str(tmp_path / "train"))
+    os.makedirs(hp.logdir + "-ssrn")
+    tfc.save(src, os.path.join(hp.logdir + "-ssrn", "model_epoch_12"), with_optimizer=False)
+
+    class G(object):
+        store = VariableStore("cpu", seed=2).declare_all(specs).finalize()
+    assert restore_latest_model_parameters(None, hp, "ssrn", graph=G) == "12"
+    assert torch.equal(G.store.flat, src.flat)
+    with pytest.raises(SystemExit):
+        restore_latest_model_parameters(None, hp, "t2m", graph=G)        # no checkpoint directory for that model
