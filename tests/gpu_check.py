@@ -1,7 +1,7 @@
 """Bring-up check of every C-ABI entry on a real B200 against the fp64 torch oracle (test tooling).
 
 Prints one line per case (max-abs error vs fp64) and keeps going on failures so that a single gpurun call
-gives the whole picture.  `python tools/gpu_check.py [--perf]`.
+gives the whole picture.  `python tests/gpu_check.py [groups] [--perf]`.
 """
 import os
 import sys

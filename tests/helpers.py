@@ -30,7 +30,7 @@ def check_grads(ours, ref, strict_prefix, median_tol=1.5e-2, max_tol=5e-2, stric
 
     The 3-term split-bf16 GEMMs reproduce the fp32 forward pass to ~2e-5, so a handful of ReLU units whose
     pre-activation lies within 2e-5 of the kink take the other branch than in the fp64 oracle.  Each flip perturbs
-    every upstream gradient by ~sqrt(flips / units) in Frobenius norm.  Measured on B200 (tools/grad_table.py,
+    every upstream gradient by ~sqrt(flips / units) in Frobenius norm.  Measured on B200 (tests/grad_table.py,
     B=2, T=200): AudioDec C_11 (no ReLU between it and the loss) 1.4e-5, C_10 2.4e-4, C_9 2.7e-3, C_8 and
     everything upstream 4-6e-3 -- the error steps up exactly at the three ReLU layers and nowhere else.  The L1
     loss |Y - target| has the same kind of kink (sign flips where |Y - target| < 2e-5), so the tail is only tight

@@ -1,5 +1,5 @@
 """Forward + one training step of Text2Mel against the oracles over awkward shapes (tile / k-block / item boundaries).
-  python tools/shape_fuzz.py [n_random]"""
+  python tests/shape_fuzz.py [n_random]"""
 import os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -1,6 +1,6 @@
 """Per-operator parity of every C-ABI entry (forward and backward) against the fp64 torch oracle.
 
-The cases live in tools/gpu_check.py (also runnable stand-alone for bring-up); shapes cover non-multiples of the
+The cases live in tests/gpu_check.py (also runnable stand-alone for bring-up); shapes cover non-multiples of the
 128-row tile, N/K tails (80, 180, 513, 1025 channels), all dilation rates, causal/SAME, strided [R|Q] / [K|V]
 buffers, the monotonic window mask, split-K weight gradients and batched attention GEMMs."""
 import os
@@ -8,7 +8,7 @@ import sys
 
 import pytest
 
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 pytestmark = pytest.mark.gpu
 
