@@ -187,3 +187,33 @@ def test_full_size_properties_b32_n180_t870():
     # (same schedule in both runs and no atomics in the forward pass: bit-identical)
     assert maxabs(Q2[:, :501], Q[:, :501]) == 0.0 and maxabs(Y2[:, :501], Y[:, :501]) == 0.0
     assert maxabs(Y2[:, 501:], Y[:, 501:]) > 1e-3
+
+
+def test_session_train_loop_with_changing_batch_shapes():
+    """train.py:273 through Session.run with the dynamically padded batches of data_load.py:534-541: every batch has its
+    own (N_b, T_b).  Shapes seen three times get a CUDA graph, the others run eagerly, batches are prefetched one step
+    ahead; the loss trajectory must equal the one of a graph-free, prefetch-free run on the same batches."""
+    import copy
+    from ophelia_b200.session import Session
+    hp1 = make_hp(max_N=40, max_T=120, dropout_rate=0.0)
+    hp2 = copy.copy(hp1)
+    hp2.use_cuda_graph = False
+    hp2.use_side_streams = False
+    P = oracle_params(hp1, "t2m", seed=9)
+    shapes = [(3, 30, 100), (2, 40, 120), (3, 30, 100), (3, 30, 100), (2, 40, 120), (3, 30, 100), (2, 40, 120),
+              (3, 30, 100), (4, 17, 33), (2, 40, 120)]
+    batches = []
+    for i, (B, N, T) in enumerate(shapes):
+        b = synthetic_batch(hp1, B, N, T, seed=100 + i, ragged=True)
+        batches.append({"text": torch.tensor(b["L"]), "mel": torch.tensor(b["mels"])})
+    g1 = _graph(hp1, "train", P, data=iter(batches))
+    g2 = _graph(hp2, "train", P, data=None if False else iter([]))
+    sess = Session()
+    for i, b in enumerate(batches):
+        gs, comps, _ = sess.run([g1.global_step, g1.loss_components, g1.train_op])
+        ref = g2.train_step_device(b["text"].cuda(), b["mel"].cuda()).cpu().numpy()
+        assert gs == i + 1
+        np.testing.assert_allclose(np.asarray(comps), ref, rtol=2e-5, atol=1e-7)
+    assert len(g1._graph_steps) == 2                       # the two recurring shapes were captured, (4,17,33) was not
+    with pytest.raises(StopIteration):
+        sess.run([g1.global_step, g1.loss_components, g1.train_op])
