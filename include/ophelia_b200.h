@@ -61,7 +61,8 @@ int oph_gemm_debug_buffer(long long* dev_buf);
  * 16 = no remainder K-split of RED outputs, 32 = skip the item-boundary fix-up of flat A tiles,
  * 64 = launch WITH programmatic stream serialization (PDL; off by default: no measured gain), 128 = A copies skipped; bits 8..10: ring depth of the highway-backward row
  * kernel (0 = automatic), 2048 = one block per SM for it, 4096 = previous (warp-per-row) highway-forward row kernel,
- * 32768 = previous (warp-per-row) conv-tail backward kernel,
+ * 32768 = previous (warp-per-row) conv-tail backward kernel, 65536 = fuse the conv tail (LayerNorm / ReLU / dropout / planes) of layers with <= 256 output channels into the
+ * GEMM epilogue (off by default: no gain on the training step, slower on the small autoregressive step),
  * 16384 = remainder K-split also for plain conv outputs (memset + RED: forward results then depend on RED order) */
 int oph_gemm_debug_flags(int flags);
 /* Execution context of the calling host thread (like cublasSetStream): with enable != 0 the weight-gradient GEMMs of

@@ -74,6 +74,15 @@ struct GemmArgs {
     // so that the last round of the persistent CTA pairs is short instead of mostly idle
     int split_from, split_s;
     size_t zero_bytes;     // host-side: > 0 if launch_gemm may memset C[0, zero_bytes) (the caller owns a dense output)
+    // conv tail fused into the epilogue (outputs with at most 256 columns: one work unit holds whole rows):
+    // y = dropout(act(LN(z))), z = acc + bias; C (z, may be NULL at inference), ln_stats, ln_y, planes, ln_ysig
+    int ln_fuse;           // set by launch_gemm when the request (ln_gamma != NULL) can be honoured
+    const float* ln_gamma; const float* ln_beta;
+    float* ln_stats;       // [M][2] (mean, rstd) or NULL
+    float* ln_y; long long ln_ldy;
+    unsigned short* ln_yhi; unsigned short* ln_ylo; long long ln_ldp;
+    float* ln_ysig; long long ln_ldys;
+    int ln_act; float ln_drop; unsigned long long ln_seed; const long long* ln_step;
     int split_red;         // 1: C was zeroed by the host and only the split work items accumulate with RED (plain outputs)
     alignas(64) CUtensorMap tmA_hi;
     alignas(64) CUtensorMap tmA_lo;
@@ -360,12 +369,140 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
         }
     };
 
+
+    // ================================================================ epilogue worker with the conv tail fused in
+    // N <= 256: the 16 epilogue warps of a CTA hold complete rows between them (4 warps x 64 columns per 32-row lane
+    // quadrant, lane = row).  Two passes over tensor memory give the two-pass row moments of z = acc + bias (partial sums
+    // exchanged through the warps' staging buffers, one named barrier per quadrant), a third pass normalises, applies
+    // ReLU / dropout and writes z, y, the operand planes and the row statistics: no separate LayerNorm launch, no
+    // re-read of z.
+    auto epilogue_ln = [&](const int q, const int cg, float* stage) {
+        constexpr int ncg = EPI_WARPS / 4;
+        const int rsub = lane >> 2, c4 = lane & 3;
+        float* qstage = sStage + (q * 512);                     // staging buffer of warp (q, cg = 0); warp w's is at w * 512
+        const float inv_n = 1.f / (float)p.N;
+        const float inv_keep = p.ln_drop > 0.f ? 1.f / (1.f - p.ln_drop) : 1.f;
+        const unsigned long long sd = eff_seed(p.ln_seed, p.ln_step);
+        auto quad_sum = [&](float part) {                       // sum over the 4 warps that share this lane quadrant
+            stage[lane] = part;
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");
+            float tot = 0.f;
+#pragma unroll
+            for (int g = 0; g < ncg; ++g) tot += qstage[g * 4 * 512 + lane];
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");
+            return tot;
+        };
+        int acc = 0, acc_par = 0;
+        for (int u = pair; u < total; u += npairs) {
+            const Unit t = decode_unit(p, u, MP, nblocks, crank);
+            if (t.KB <= 0) continue;
+            mbar_wait(BAR(BAR_T_FULL + acc), acc_par);
+            tc_fence_after();
+            const int grow0 = t.m0 + q * 32;
+            const int nrows = min(32, t.rows - q * 32);        // <= 0 for padding rows
+            const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + acc * GEMM_BN;
+            // ---- pass 1 / 2: mean and centred second moment of this lane's row
+            float mean = 0.f, rstd = 1.f;
+#pragma unroll 1
+            for (int pass = 0; pass < 2; ++pass) {
+                float part = 0.f;
+#pragma unroll 1
+                for (int cb = cg; cb < GEMM_BN / 16; cb += ncg) {
+                    const int col0 = cb * 16;
+                    if (col0 >= p.N) break;
+                    uint32_t r[16];
+                    tmem_ld16(tbase + col0, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        if (col0 + j < p.N) {
+                            const float v = __uint_as_float(r[j]) * p.alpha + (p.bias ? __ldg(p.bias + col0 + j) : 0.f);
+                            part += pass == 0 ? v : (v - mean) * (v - mean);
+                        }
+                    }
+                }
+                const float tot = quad_sum(part);
+                if (pass == 0) mean = tot * inv_n; else rstd = rsqrtf(tot * inv_n + 1e-12f);
+            }
+            if (p.ln_stats && cg == 0 && lane < nrows) *reinterpret_cast<float2*>(p.ln_stats + (long long)(grow0 + lane) * 2) = make_float2(mean, rstd);
+            // ---- pass 3: transposed, 16-byte wide outputs
+#pragma unroll 1
+            for (int cb = cg; cb < GEMM_BN / 16; cb += ncg) {
+                const int col0 = cb * 16;
+                const bool live = nrows > 0 && col0 < p.N;
+                uint32_t r[16];
+                if (live) { tmem_ld16(tbase + col0, r); tmem_ld_wait(); }
+                if (cb + ncg >= GEMM_BN / 16) {                // last block of this warp: hand the accumulator stage back
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) { if (crank == 0) mbar_arrive(BAR(BAR_T_EMPTY + acc)); else mbar_arrive_remote(BAR(BAR_T_EMPTY + acc), 0); }
+                }
+                if (!live) continue;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    *reinterpret_cast<uint4*>(stage + lane * 16 + ((j ^ ((lane >> 1) & 3)) << 2)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+                __syncwarp();
+                const int gcol = col0 + c4 * 4;
+                float bv[4] = {0.f, 0.f, 0.f, 0.f}, gm[4] = {0.f, 0.f, 0.f, 0.f}, bt[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) if (gcol + e < p.N) {
+                    if (p.bias) bv[e] = __ldg(p.bias + gcol + e);
+                    gm[e] = __ldg(p.ln_gamma + gcol + e); bt[e] = __ldg(p.ln_beta + gcol + e);
+                }
+                const bool full = gcol + 4 <= p.N;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int rr = rsub + 8 * i;
+                    const float m_r = __shfl_sync(0xffffffffu, mean, rr), s_r = __shfl_sync(0xffffffffu, rstd, rr);
+                    if (rr >= nrows || gcol >= p.N) continue;
+                    const float4 v = *reinterpret_cast<const float4*>(stage + rr * 16 + ((c4 ^ ((rr >> 1) & 3)) << 2));
+                    const long long row = grow0 + rr;
+                    float zv[4] = {v.x * p.alpha + bv[0], v.y * p.alpha + bv[1], v.z * p.alpha + bv[2], v.w * p.alpha + bv[3]};
+                    float yv[4], sg[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float uu = (zv[e] - m_r) * s_r * gm[e] + bt[e];
+                        sg[e] = sigmoidf_(uu);
+                        float a = p.ln_act == 1 ? fmaxf(uu, 0.f) : uu;
+                        if (p.ln_drop > 0.f) a *= drop_scale(sd, (unsigned long long)row * p.N + gcol + e, p.ln_drop, inv_keep);
+                        yv[e] = a;
+                    }
+                    if (full) {
+                        if (p.C) *reinterpret_cast<float4*>(p.C + row * p.ldc + gcol) = make_float4(zv[0], zv[1], zv[2], zv[3]);
+                        *reinterpret_cast<float4*>(p.ln_y + row * p.ln_ldy + gcol) = make_float4(yv[0], yv[1], yv[2], yv[3]);
+                        if (p.ln_ysig) *reinterpret_cast<float4*>(p.ln_ysig + row * p.ln_ldys + gcol) = make_float4(sg[0], sg[1], sg[2], sg[3]);
+                        if (p.ln_yhi) {
+                            uint2 hh, ll;
+                            split4(make_float4(yv[0], yv[1], yv[2], yv[3]), hh, ll);
+                            *reinterpret_cast<uint2*>(p.ln_yhi + row * p.ln_ldp + gcol) = hh;
+                            *reinterpret_cast<uint2*>(p.ln_ylo + row * p.ln_ldp + gcol) = ll;
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            if (gcol + e >= p.N) break;
+                            if (p.C) p.C[row * p.ldc + gcol + e] = zv[e];
+                            p.ln_y[row * p.ln_ldy + gcol + e] = yv[e];
+                            if (p.ln_ysig) p.ln_ysig[row * p.ln_ldys + gcol + e] = sg[e];
+                            if (p.ln_yhi) st_split1(p.ln_yhi, p.ln_ylo, row * p.ln_ldp + gcol + e, yv[e]);
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            if (++acc == N_ACC) { acc = 0; acc_par ^= 1; }
+        }
+    };
+
     // Register budget per role (768 threads launch at 80 regs): producer warpgroups grow to 88, the epilogue
     // warpgroup shrinks to 72 and the MMA / copy warpgroup to 40 (512*88 + 128*72 + 128*40 <= 768*80: setmaxnreg can
     // only hand out what the CTA got at launch).
     if (warp < NPW) {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
-        if (copy_fed) epilogue(warp & 3, warp >> 2, EPI_WARPS / 4, sStage + warp * 512);
+        if (copy_fed) {
+            if (p.ln_fuse) epilogue_ln(warp & 3, warp >> 2, sStage + warp * 512);
+            else epilogue(warp & 3, warp >> 2, EPI_WARPS / 4, sStage + warp * 512);
+        }
         // ================================================================ producers (both CTAs)
         // Each thread owns NCH chunks (8 consecutive elements) of every operand tile.  Global loads run one k-block
         // ahead of the shared-memory stores (register double buffer); address arithmetic is hoisted out of the chunk

@@ -375,6 +375,21 @@ def case_dropout():
     dx0 = ops.hc_bwd(dym, x, saved, pk, *prm[1:], g2[0], g2[1], g2[2], g2[3], g2[4], g2[5], 3, 1, True)
     report("dropout backward mask == forward mask (dx)", maxerr(dx1, dx0), 1e-5)
     report("dropout backward mask == forward mask (dw)", maxerr(g[0], g2[0]), 1e-3)
+    # conv1d (tail fused into the GEMM epilogue for Cout <= 256): forward mask must be the one ln_act_bwd re-creates
+    Pc = conv_params("c", 1, C, C)
+    wc = f32(Pc["c/conv1d/kernel"]); pkc = ops.PackedConv(wc)
+    bc, gc, bec = f32(Pc["c/conv1d/bias"]), f32(Pc["c/normalize/gamma"]), f32(Pc["c/normalize/beta"])
+    c0, _, _ = ops.conv1d_fwd(x, pkc, bc, gc, bec, 1, 1, 0, 0, True)
+    c1, _, savedc = ops.conv1d_fwd(x, pkc, bc, gc, bec, 1, 1, 0, 0, True, drop_p=rate, seed=77, step=step, save=True)
+    keepc = (c1 != 0)
+    report("conv1d dropout keep fraction", abs(float(keepc.float().mean()) - (1 - rate)), 4 * (rate * (1 - rate) / keepc.numel()) ** 0.5 + 1e-4)
+    report("conv1d dropout scale", maxerr(c1[keepc], c0[keepc] / (1 - rate)), 1e-5)
+    gr = [torch.zeros_like(t) for t in (wc, bc, gc, bec)]
+    dxa = ops.conv1d_bwd(dy, x, savedc, pkc, gc, bec, gr[0], gr[1], gr[2], gr[3], 1, 1, 0, 0, True, drop_p=rate, seed=77, step=step)
+    gr2 = [torch.zeros_like(t) for t in (wc, bc, gc, bec)]
+    dymc = (dy * keepc.float() / (1 - rate)).contiguous()
+    dxb = ops.conv1d_bwd(dymc, x, savedc, pkc, gc, bec, gr2[0], gr2[1], gr2[2], gr2[3], 1, 1, 0, 0, True)
+    report("conv1d dropout backward mask == forward mask (dx)", maxerr(dxa, dxb), 1e-5)
 
 
 def perf():
