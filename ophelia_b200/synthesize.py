@@ -87,29 +87,48 @@ def synth_codedtext2mel_device(hp, K, V, ends, g, use_cuda_graph=True, check_eve
     only every `check_every` frames for the reference's end-of-sentence test (synthesize.py:218-228); frames computed
     past the stopping frame are cleared again, so the results equal the frame-by-frame loop's."""
     dev = g.device
-    K = g._to_device(K, torch.float32).contiguous()
-    V = g._to_device(V, torch.float32).contiguous()
-    B = K.shape[0]
     from . import ops
-    ops.ensure_planes(K, cache=True)                    # K, V stay constant over the loop: split them once
-    ops.ensure_planes(V, cache=True)
-    Y = torch.zeros(B, hp.max_T, hp.n_mels, device=dev, dtype=torch.float32)
+    K = g._to_device(K, torch.float32)
+    V = g._to_device(V, torch.float32)
+    B = K.shape[0]
+    # static buffers (and the captured step) are kept on the graph object per batch shape: synthesising many batches
+    # re-uses them instead of capturing again
+    cache = g.__dict__.setdefault("_ar_state", {})
+    key = (B, K.shape[1], K.shape[2], hp.max_T, bool(use_cuda_graph))
+    st = cache.get(key)
+    if st is not None and st["version"] != g.store.version:      # weights changed since the capture: packed images are stale
+        st = None
+    if st is None:
+        st = {"K": torch.empty(K.shape, device=dev, dtype=torch.float32), "V": torch.empty(V.shape, device=dev, dtype=torch.float32),
+              "Y": torch.zeros(B, hp.max_T, hp.n_mels, device=dev, dtype=torch.float32),
+              "prev": torch.zeros(B, device=dev, dtype=torch.int32), "graph": None, "out": None,
+              "version": g.store.version}
+        for n in ("K", "V"):                            # planes live next to the static buffers and are refreshed per call
+            st[n]._oph_planes = ops.split_planes(st[n])
+        cache[key] = st
+    Kb, Vb, Y, prev = st["K"], st["V"], st["Y"], st["prev"]
+    Kb.copy_(K)
+    Vb.copy_(V)
+    ops.split_planes(Kb, into=Kb._oph_planes)            # K, V stay constant over the loop: split them once per call
+    ops.split_planes(Vb, into=Vb._oph_planes)
+    Y.zero_()
+    prev.zero_()
     alignments = torch.zeros(B, hp.max_N, hp.max_T, device=dev, dtype=torch.float32)
-    prev = torch.zeros(B, device=dev, dtype=torch.int32)
     history = torch.zeros(hp.max_T, B, device=dev, dtype=torch.int32)      # argmax of frame j at frame j
     ends = np.asarray(ends)
     endcounts = np.zeros(ends.shape, dtype=int)
     t_ends = np.ones(ends.shape, dtype=int) * hp.max_T
 
     def forward():
-        return g.build_model(None, Y, False, K=K, V=V, prev_max_attentions=prev, want_alignments=True)
-    graph = None
-    if use_cuda_graph:
+        return g.build_model(None, Y, False, K=Kb, V=Vb, prev_max_attentions=prev, want_alignments=True)
+    graph, out = st["graph"], st["out"]
+    if use_cuda_graph and graph is None:
         forward()                                       # warm-up outside the capture (lazy weight packing)
         torch.cuda.synchronize(dev)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             out = forward()
+        st["graph"], st["out"] = graph, out
     checked = 0
     stop_at = None
     for j in range(hp.max_T):
