@@ -217,3 +217,33 @@ def test_session_train_loop_with_changing_batch_shapes():
     assert len(g1._graph_steps) == 2                       # the two recurring shapes were captured, (4,17,33) was not
     with pytest.raises(StopIteration):
         sess.run([g1.global_step, g1.loss_components, g1.train_op])
+
+
+def test_norm_none_configuration_matches_oracle():
+    """hp.norm = None (the reference's config/project/*.cfg): conv1d / hc run without layer norm (modules.py:47-75 returns
+    its input), no normalize variables exist; forward and two optimiser steps against the oracles."""
+    from ophelia_b200.session import Session
+    B, N, T = 2, 40, 150
+    hp = make_hp(max_N=N, max_T=T, dropout_rate=0.0, norm=None)
+    P = oracle_params(hp, "t2m", seed=11)
+    b = synthetic_batch(hp, B, N, T, ragged=True)
+    ref = on.text2mel_forward(hp, P, b["L"], b["mels"], "generate_attention")
+    from ophelia_b200.architectures import Text2MelGraph
+    from ophelia_b200.variables import VariableStore
+    store = VariableStore("cuda:0")
+    g = Text2MelGraph(hp, mode="generate_attention", store=store)
+    assert not any("normalize" in n or "/H1/" in n for n in store.specs)
+    store.load_state_dict(P, strict=False)
+    Y, ali = Session().run([g.Y, g.alignments], {g.L: b["L"], g.mels: b["mels"]})
+    assert maxabs(Y, ref["Y"]) < 1e-3 and maxabs(ali, ref["alignments"]) < 1e-4
+    Pt = ot.to_torch(P, torch.float64, requires_grad=True)
+    opt = ot.TFAdam(hp, Pt)
+    st2 = VariableStore("cuda:0")
+    gt = Text2MelGraph(hp, mode="train", store=st2, data=iter([]))
+    st2.load_state_dict(P, strict=False)
+    Ld, md = torch.tensor(b["L"]).cuda(), torch.tensor(b["mels"]).cuda()
+    for _ in range(2):
+        comps_ref, _ = ot.text2mel_train_step(hp, Pt, opt, torch.tensor(b["L"].astype(np.int64)),
+                                              torch.tensor(b["mels"], dtype=torch.float64))
+        comps = gt.train_step_device(Ld, md).cpu().numpy()
+        np.testing.assert_allclose(comps, comps_ref, rtol=5e-4, atol=1e-6)
