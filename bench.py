@@ -267,6 +267,7 @@ def run_ours(args):
         att["algorithmic_gbs"] = att_bytes / (att["ms_per_step"] * 1e-3) / 1e9
         att["frac_of_hbm_peak"] = att["algorithmic_gbs"] / pk["hbm"]
         att["frac_of_tensor_peak"] = att["tflops"] / pk["tensor_sustained"]
+    traffic = ncu_traffic(args) if t2m else {}
     line = {
         "metric": METRIC if t2m else METRIC_SSRN, "value": frames_per_step / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -283,14 +284,15 @@ def run_ours(args):
         "gpu_launches_per_step": int(launches),
         "roofline": {"kernel": "gemm_bf16x3_kernel (tcgen05 implicit GEMM: conv fwd / dgrad / wgrad / attention)",
                      "bound": "tensor", "achieved": achieved, "peak": pk["tensor_sustained"], "unit": "TFLOP/s",
-                     "frac": achieved / pk["tensor_sustained"], "traffic": None,
+                     "frac": achieved / pk["tensor_sustained"], "traffic": traffic.get("gemm"),
+                     "traffic_detail": traffic.get("detail"),
                      "peak_source": pk["src"] + " bf16 cuBLAS sustained",
                      "launches_per_step": tot_n / args.steps, "avg_launch_ms": tot_ms / max(tot_n, 1),
                      "share_of_step": (tot_ms / args.steps) / ms_eager,
                      "note": "achieved counts ALGORITHMIC FLOPs once; the split-bf16 scheme issues 3 tensor passes per "
                              "FLOP, so the ceiling of this number is peak/3"},
         "roofline_hbm": {"kernel": "row-wise LayerNorm / highway tails (hc_post_fwd/bwd_wide, ln_act_fwd/bwd)", "bound": "hbm",
-                         "achieved": row_gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": row_gbs / pk["hbm"], "traffic": None,
+                         "achieved": row_gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": row_gbs / pk["hbm"], "traffic": traffic.get("rowwise"),
                          "launches_per_step": row_n / args.steps, "ms_per_step": row_ms / args.steps,
                          "forward_gbs": (prof[17] / (prof[16] * 1e-3) / 1e9) if prof[16] > 0 else 0.0,
                          "backward_gbs": (prof[20] / (prof[19] * 1e-3) / 1e9) if prof[19] > 0 else 0.0,
@@ -305,6 +307,23 @@ def run_ours(args):
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
+
+
+def ncu_traffic(args):
+    """DRAM bytes per launch of the dominant kernels from the committed `ncu --set full` captures (profiles/r01_traffic.json).
+    The captures were taken at the headline shape (B=32, N=180, T=870): other shapes report null."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_traffic.json")
+    if (args.batch, args.N, args.T) != (32, 180, 870) or not os.path.isfile(path):
+        return {}
+    with open(path) as f:
+        cap = json.load(f)["captures"]
+    tot = lambda k: cap[k]["dram_read"] + cap[k]["dram_write"]
+    return {"gemm": tot("gemm_hc_fwd"), "rowwise": tot("hc_post_bwd"),
+            "detail": {"unit": "bytes per launch, one ncu --set full capture each (cold caches)", "file": "profiles/r01_traffic.json",
+                       "launches": {k: {"dram": tot(k), "algorithmic": v["algorithmic"], "launch": v["launch"]}
+                                    for k, v in cap.items()},
+                       "note": "roofline.traffic is the highway-conv forward GEMM (the most frequent launch); "
+                               "roofline_hbm.traffic is the highway-tail backward kernel"}}
 
 
 def run_synth(args):

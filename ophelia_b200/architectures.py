@@ -214,7 +214,7 @@ class Graph(object):
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize(self.device)
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
+        with ops.capture(graph):
             comps = self.train_step_device(*static)
 
         def step(*inputs):

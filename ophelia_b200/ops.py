@@ -4,6 +4,9 @@ torch is used for device memory and streams only; every arithmetic op below is o
 libophelia_sm100.so.  Activations are fp32 CUDA tensors `[B, time, C]` whose rows may be strided
 (`stride(-1) == 1`, `stride(0) == time * stride(1)`), which is how K/V, R/Q share buffers.
 """
+import contextlib
+import gc
+
 import torch
 
 from . import _lib
@@ -14,6 +17,24 @@ ACT_NONE, ACT_RELU = 0, 1
 
 def _stream():
     return torch.cuda.current_stream().cuda_stream
+
+
+@contextlib.contextmanager
+def capture(graph):
+    """`with torch.cuda.graph(graph)` that cannot be invalidated by Python's cyclic collector.  A dead reference cycle
+    may own device resources whose release is illegal while any capture is open (another captured step with its private
+    pool, e.g. the per-shape autoregressive step a discarded Graph object kept): collected in the middle of a capture
+    it turns every later launch into cudaErrorStreamCaptureInvalidated.  torch.cuda.graph no longer collects on entry,
+    so collect here and keep the collector off until the capture has ended."""
+    gc.collect()
+    was_enabled = gc.isenabled()
+    gc.disable()
+    try:
+        with torch.cuda.graph(graph):
+            yield graph
+    finally:
+        if was_enabled:
+            gc.enable()
 
 
 # Weight-gradient GEMMs on a side stream (oph_wgrad_stream): buffers they read (dz) are parked in `_keepalive` until

@@ -126,7 +126,7 @@ def synth_codedtext2mel_device(hp, K, V, ends, g, use_cuda_graph=True, check_eve
         forward()                                       # warm-up outside the capture (lazy weight packing)
         torch.cuda.synchronize(dev)
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
+        with ops.capture(graph):
             out = forward()
         st["graph"], st["out"] = graph, out
     checked = 0
