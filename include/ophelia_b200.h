@@ -101,6 +101,21 @@ typedef struct {
     long long ldp;
 } oph_act;
 
+/* Attention targets that come with the batch instead of the analytic global guide (hp.attention_guide_dir,
+ * architectures.py:57-58, 258-280; data_load.py:454-464): w[b][n][t] over the batch-padded [Ng][Tg] block (row stride ld,
+ * item stride item_stride, both in floats), `pad` outside that block (1.0 for the guided-attention loss, the value the
+ * reference pads the guides with at architectures.py:263; 0.0 for the MSE variant, :275).  mse != 0 selects
+ * sum (A - W)^2 (hp.attention_guide_fa) instead of sum |A * W|. */
+typedef struct {
+    const float* w;
+    long long item_stride;
+    long long ld;
+    int Ng;
+    int Tg;
+    float pad;
+    int mse;
+} oph_guide;
+
 /* ---- modules.conv1d (modules.py:91-146), hot-path uses are k=1 -------------------------------------------
  * y = dropout(act(LN(conv(x) + bias))).  z [B*L][ldz] receives the pre-LN conv output (saved for backward,
  * scratch otherwise), stats [B*L][2] = (mean, rstd) (nullable in inference), y_sig (nullable) = sigmoid(LN(..)).
@@ -158,7 +173,8 @@ int oph_embed_bwd(const int32_t* ids, const float* dout, long long ldo, float* d
  * the first half of the [R, Q] buffer, networks.py:317-319).  prev_max (nullable, int32 [B]) + win enable the
  * forcibly-incremental window: keys outside [prev, prev+win) get -2^32+1 (networks.py:304-313).
  * align_t (nullable) = alignments [B][N][T]; argmax (nullable) int32 [B][T] (first maximum);
- * att_acc (nullable, device double) += sum A*W over n<maxN, t<maxT with the analytic guide (utils.py:155-161). */
+ * att_acc (nullable, device double) += sum A*W over n<maxN, t<maxT with the analytic guide (utils.py:155-161), or with
+ * the batch's own targets when guide != NULL (see oph_guide). */
 /* Q, K, V, A (probabilities) and R (context vectors) are activations per batch item; for the outputs A and R the f32
  * view is written and the planes too when given (R's by the epilogue of the A.V product, so that the decoder's first
  * conv reads [R|Q] through the copy engines).  When every
@@ -166,13 +182,13 @@ int oph_embed_bwd(const int32_t* ids, const float* dout, long long ldo, float* d
  * the copy engines; otherwise the producer warps convert the fp32 views. */
 int oph_attention_fwd(const oph_act* Q, const oph_act* K, const oph_act* V, const oph_act* A, const oph_act* R,
                       float* align_t, int32_t* argmax, const int32_t* prev_max, int win, double* att_acc, int maxN,
-                      int maxT, float g, int B, int T, int N, int d, oph_stream_t stream);
+                      int maxT, float g, int B, int T, int N, int d, const oph_guide* guide, oph_stream_t stream);
 /* dR [B][T].  dA [B][T][ldA] scratch (f32 + optional planes for dS).  dq_addend (nullable) is added into dQ (the direct
  * [R,Q] concat path).  att_coef = lw_att / (B*min(N,maxN)*min(T,maxT)) injects the guided-attention gradient. */
 int oph_attention_bwd(const oph_act* dR, const oph_act* Q, const oph_act* K, const oph_act* V, const oph_act* A,
                       const oph_act* dA, float* dQ, long long lddq, const float* dq_addend, long long ldqa, float* dK,
                       long long lddk, float* dV, long long lddv, float att_coef, int maxN, int maxT, float g, int B,
-                      int T, int N, int d, oph_stream_t stream);
+                      int T, int N, int d, const oph_guide* guide, oph_stream_t stream);
 /* fp32 rows -> split-bf16 planes for operands that do not come out of a row-wise kernel of this library. */
 int oph_split_planes(const float* x, long long ldx, long long rows, int C, unsigned short* hi, unsigned short* lo,
                      long long ldp, oph_stream_t stream);

@@ -18,6 +18,14 @@ class Act(ctypes.Structure):
 
 AP = ctypes.POINTER(Act)
 
+
+class Guide(ctypes.Structure):
+    """`oph_guide`: per-utterance attention targets of the batch (include/ophelia_b200.h)."""
+    _fields_ = [("w", P), ("item_stride", LL), ("ld", LL), ("Ng", I), ("Tg", I), ("pad", F), ("mse", I)]
+
+
+GP = ctypes.POINTER(Guide)
+
 # name -> (restype, argtypes); must list every symbol of include/ophelia_b200.h
 SIGNATURES = {
     "oph_version": (I, []),
@@ -43,8 +51,8 @@ SIGNATURES = {
     "oph_deconv_bwd": (I, [P, LL, AP, P, LL, P, P, P, P, P, LL, P, LL, P, P, P, P, I, I, I, F, U64, P, P]),
     "oph_embed_fwd": (I, [P, P, P, LL, I, I, P]),
     "oph_embed_bwd": (I, [P, P, LL, P, I, I, P]),
-    "oph_attention_fwd": (I, [AP, AP, AP, AP, AP, P, P, P, I, P, I, I, F, I, I, I, I, P]),
-    "oph_attention_bwd": (I, [AP, AP, AP, AP, AP, AP, P, LL, P, LL, P, LL, P, LL, F, I, I, F, I, I, I, I, P]),
+    "oph_attention_fwd": (I, [AP, AP, AP, AP, AP, P, P, P, I, P, I, I, F, I, I, I, I, GP, P]),
+    "oph_attention_bwd": (I, [AP, AP, AP, AP, AP, AP, P, LL, P, LL, P, LL, P, LL, F, I, I, F, I, I, I, I, GP, P]),
     "oph_split_planes": (I, [P, LL, LL, I, P, P, LL, P]),
     "oph_recon_loss": (I, [P, LL, P, LL, P, LL, LL, I, I, F, F, F, P, P]),
     "oph_loss_finalize": (I, [P, P, D, D, F, F, F, F, I, I, P]),

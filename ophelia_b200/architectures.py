@@ -153,7 +153,16 @@ class Graph(object):
         if self.mode == 'train':
             if data is None:
                 data = getattr(self.hp, "batch_source", None)
-            assert data is not None, "training graphs need `data=` (iterator of host batches) or hp.batch_source"
+            if data is None:
+                # batchdict = get_batch(hp, self.get_batchsize())  (architectures.py:38-44): transcript + .npy features;
+                # data-parallel ranks take disjoint slices of the same shuffled stream
+                from .data_load import get_batch
+                need = self.batch_fields + (("attention_guide",) if self.hp.attention_guide_dir else ())
+                rank, world = 0, 1
+                if self.process_group is not None:
+                    import torch.distributed as dist
+                    rank, world = dist.get_rank(self.process_group), dist.get_world_size(self.process_group)
+                data = get_batch(self.hp, self.get_batchsize(), need=need, rank=rank, world=world)
             self.batch_source = iter(data)
             self.num_batch = getattr(data, "num_batch", getattr(self.hp, "num_batch", 1))
 
@@ -279,6 +288,7 @@ class Graph(object):
 class SSRNGraph(Graph):
     scope_name = "SSRN"
     node_names = ("mels", "mags", "Z_logits", "Z", "loss", "loss_components", "train_op", "global_step")
+    batch_fields = ("mel", "mag")
 
     def variable_specs(self, hp):
         return ssrn_variables(hp)
@@ -352,7 +362,7 @@ class Text2MelGraph(Graph):
 
     # architectures.py:188-239
     def build_model(self, L, mels, training, K=None, V=None, prev_max_attentions=None, att_acc=None,
-                    want_alignments=True, tapes=None, text_stream=None):
+                    want_alignments=True, tapes=None, text_stream=None, gts=None):
         hp = self.hp
         mono = self.mode == 'synthesize'
         out = {}
@@ -377,7 +387,7 @@ class Text2MelGraph(Graph):
             with variable_scope("Attention"), on(t_dec):
                 R, alignments, max_attentions = Attention(
                     hp, Q, K, V, monotonic_attention=mono, prev_max_attentions=prev_max_attentions if mono else None,
-                    training=training, att_acc=att_acc, want_alignments=want_alignments)
+                    training=training, att_acc=att_acc, want_alignments=want_alignments, gts=gts)
             with variable_scope("AudioDec"), on(t_dec):
                 Y_logits, Y = AudioDec(hp, R, training=training, speaker_codes=None, reuse=self.reuse)
         out.update(K=K, V=V, Q=Q, R=R, alignments=alignments, max_attentions=max_attentions, Y_logits=Y_logits, Y=Y)
@@ -403,20 +413,27 @@ class Text2MelGraph(Graph):
         out["mels"] = mels
         return out
 
-    def train_step(self, batch=None):
-        if batch is None:
-            L, mels = self._next_inputs((("text", torch.int32), ("mel", torch.float32)))
-        else:
-            L = self._to_device(batch["text"], torch.int32)
-            mels = self._to_device(batch["mel"], torch.float32)
-        return self._step_maybe_graphed(L, mels)
+    batch_fields = ("text", "mel")            # what a Text2Mel step needs from data_load.get_batch (no magnitudes)
 
-    def train_step_device(self, L, mels):
+    def train_step(self, batch=None):
+        fields = [("text", torch.int32), ("mel", torch.float32)]
+        if self.hp.attention_guide_dir:                      # self.gts = batchdict['attention_guide'] (architectures.py:57-58)
+            fields.append(("attention_guide", torch.float32))
+        if batch is None:
+            inputs = self._next_inputs(tuple(fields))
+        else:
+            inputs = tuple(self._to_device(batch[k], dt) for k, dt in fields)
+        return self._step_maybe_graphed(*inputs)
+
+    def train_step_device(self, L, mels, gts=None):
         """One `sess.run([global_step, loss_components, train_op])` with inputs already on the device.
-        Returns loss_components [loss, L1, BD, att, L2] as a device tensor (architectures.py:352-355)."""
+        Returns loss_components [loss, L1, BD, att, L2] as a device tensor (architectures.py:352-355).
+        gts: the batch's attention guides / forced-alignment targets [B, Ng, Tg] when hp.attention_guide_dir is set
+        (else the analytic global guide of utils.py:155-164)."""
         hp, st = self.hp, self.store
-        assert not hp.attention_guide_dir and not hp.attention_guide_fa, \
-            "per-utterance / MSE attention guides are outside the path (global analytic guide only)"
+        assert (gts is not None) == bool(hp.attention_guide_dir), \
+            "hp.attention_guide_dir set <=> batches carry 'attention_guide' (architectures.py:57-60)"
+        assert not hp.attention_guide_fa or gts is not None, "the MSE attention loss needs targets from hp.attention_guide_dir"
         assert hp.lw_cdp == 0.0 and hp.lw_ain == 0.0 and hp.lw_aout == 0.0
         mels._oph_no_grad = True
         st.grad_flat.zero_()
@@ -424,7 +441,7 @@ class Text2MelGraph(Graph):
         tapes = (Tape(), Tape(), Tape())
         side = self._streams()
         out = self.build_model(L, mels, True, att_acc=acc[3:], want_alignments=False, tapes=tapes,
-                               text_stream=side[0] if side else None)
+                               text_stream=side[0] if side else None, gts=gts)
         w1, wbd, watt, w2 = _loss_weights(hp, "t2m")
         squash = hp.squash_output_t2m
         logits = out["Y_logits"]

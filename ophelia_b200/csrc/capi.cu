@@ -859,10 +859,25 @@ int oph_split_planes(const float* x, long long ldx, long long rows, int C, unsig
     return check_launch("split_planes_kernel");
 }
 
+static int guide_tensor(GuideTensor& G, const oph_guide* guide, int N, int T) {
+    G = GuideTensor{nullptr, 0, 0, 0, 0, 1.f, 0};
+    if (!guide || !guide->w) return OPH_OK;
+    if (guide->Ng < 1 || guide->Tg < 1 || guide->ld < guide->Tg || guide->item_stride < (long long)guide->Ng * guide->ld)
+        return fail(OPH_EINVAL, "attention: malformed guide tensor (Ng, Tg >= 1, ld >= Tg, item_stride >= Ng * ld)%s");
+    // the MSE variant pads alignments and targets with zeros, so target mass outside the batch's [N, T] block would add a
+    // constant the kernels do not see (architectures.py:271-280): forced-alignment targets must fit the batch
+    if (guide->mse && (guide->Ng > N || guide->Tg > T))
+        return fail(OPH_EINVAL, "attention: forced-alignment targets larger than the batch's [N, T] block%s");
+    G = GuideTensor{guide->w, guide->item_stride, guide->ld, guide->Ng, guide->Tg, guide->pad, guide->mse ? 1 : 0};
+    return OPH_OK;
+}
+
 int oph_attention_fwd(const oph_act* Q, const oph_act* K, const oph_act* V, const oph_act* A, const oph_act* Ro,
                       float* align_t, int32_t* argmax, const int32_t* prev_max, int win, double* att_acc, int maxN,
-                      int maxT, float g_, int B, int T, int N, int d, oph_stream_t stream) {
+                      int maxT, float g_, int B, int T, int N, int d, const oph_guide* guide, oph_stream_t stream) {
     if (!Q || !K || !V || !A || !A->f32 || !Ro || !Ro->f32) return fail(OPH_EINVAL, "attention_fwd: missing operand%s");
+    GuideTensor G;
+    OPH_TRY(guide_tensor(G, guide, N, T));
     float* R = Ro->f32; const long long ldr = Ro->ld;
     const long long ldA = A->ld;
     if (ldA < N) return fail(OPH_EINVAL, "attention_fwd: ldA < N%s");
@@ -879,7 +894,7 @@ int oph_attention_fwd(const oph_act* Q, const oph_act* K, const oph_act* V, cons
         OPH_TRY(launch_gemm(g, B, S(stream)));
     }
     launch_cfg(rows_grid((long long)B * T, 8), 256, 0, S(stream))(softmax_fwd_kernel, A->f32, ldA, B, T, N, prev_max, win, align_t,
-                                                                 argmax, att_acc, maxN, maxT, g_, fed ? A->hi : nullptr,
+                                                                 argmax, att_acc, maxN, maxT, g_, G, fed ? A->hi : nullptr,
                                                                  fed ? A->lo : nullptr, A->ldp);
     OPH_TRY(check_launch("softmax_fwd_kernel"));
     {   // R = A V
@@ -898,8 +913,10 @@ int oph_attention_fwd(const oph_act* Q, const oph_act* K, const oph_act* V, cons
 int oph_attention_bwd(const oph_act* dR, const oph_act* Q, const oph_act* K, const oph_act* V, const oph_act* A,
                       const oph_act* dA, float* dQ, long long lddq, const float* dq_addend, long long ldqa, float* dK,
                       long long lddk, float* dV, long long lddv, float att_coef, int maxN, int maxT, float g_, int B,
-                      int T, int N, int d, oph_stream_t stream) {
+                      int T, int N, int d, const oph_guide* guide, oph_stream_t stream) {
     if (!dR || !Q || !K || !V || !A || !dA || !A->f32 || !dA->f32) return fail(OPH_EINVAL, "attention_bwd: missing operand%s");
+    GuideTensor G;
+    OPH_TRY(guide_tensor(G, guide, N, T));
     const float scale = 1.0f / sqrtf((float)d);
     const long long ldA = A->ld;
     if (dA->ld != ldA) return fail(OPH_EINVAL, "attention_bwd: dA must share A's row stride%s");
@@ -925,7 +942,7 @@ int oph_attention_bwd(const oph_act* dR, const oph_act* Q, const oph_act* K, con
         OPH_TRY(launch_gemm(g, B, S(stream)));
     }
     launch_cfg(rows_grid((long long)B * T, 8), 256, 0, S(stream))(softmax_bwd_kernel, A->f32, ldA, dA->f32, ldA, B, T, N, att_coef, maxN,
-                                                                 maxT, g_, fed ? dA->hi : nullptr, fed ? dA->lo : nullptr, dA->ldp);
+                                                                 maxT, g_, G, fed ? dA->hi : nullptr, fed ? dA->lo : nullptr, dA->ldp);
     OPH_TRY(check_launch("softmax_bwd_kernel"));
     {   // dQ = dS K / sqrt(d) (+ direct path)
         GemmArgs g = blank();

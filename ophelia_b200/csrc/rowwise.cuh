@@ -268,13 +268,21 @@ __device__ __forceinline__ float guide_w(int n, int t, float inv_maxN, float inv
     const float d = (float)t * inv_maxT - (float)n * inv_maxN;           // utils.py:155-161
     return 1.f - __expf(-d * d * inv_2g2);
 }
+// Per-utterance guides from the batch (hp.attention_guide_dir, architectures.py:57-58): gw[b][n][t] inside the
+// batch-padded [Ng, Tg] block, `pad` outside it (1.0 for the guided loss, 0.0 for the MSE variant; :263, :275).
+struct GuideTensor {
+    const float* w; long long item_stride; long long ld; int Ng, Tg; float pad; int mse;
+};
+__device__ __forceinline__ float guide_t(const GuideTensor& G, int b, int n, int t) {
+    return (n < G.Ng && t < G.Tg) ? __ldg(G.w + (long long)b * G.item_stride + (long long)n * G.ld + t) : G.pad;
+}
 
 // in: S[b][t][0..N) scaled scores.  out: probabilities in place, optional transposed alignments [B][N][T],
 // argmax (first maximum), guided-attention partial sum  sum_{n<maxN,t<maxT} A*W  (architectures.py:258-270)
 __global__ void softmax_fwd_kernel(float* __restrict__ S, long long ldS, int B, int T, int N,
                                    const int* __restrict__ prev_max, int win,
                                    float* __restrict__ align_t, int* __restrict__ argmax_out,
-                                   double* __restrict__ att_acc, int maxN, int maxT, float g,
+                                   double* __restrict__ att_acc, int maxN, int maxT, float g, GuideTensor G,
                                    unsigned short* __restrict__ p_hi, unsigned short* __restrict__ p_lo, long long ldp) {
     pdl_grid_sync();
     const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
@@ -311,7 +319,13 @@ __global__ void softmax_fwd_kernel(float* __restrict__ S, long long ldS, int B, 
             sr[n] = a;
             if (p_hi) st_split1(p_hi, p_lo, row * ldp + n, a);      // operand planes of the A.V / A^T.dR products
             if (align_t) align_t[((long long)b * N + n) * T + t] = a;
-            if (att_acc && n < maxN && t < maxT) att_part += a * guide_w(n, t, inv_maxN, inv_maxT, inv_2g2);
+            if (att_acc && n < maxN && t < maxT) {
+                if (!G.w) att_part += a * guide_w(n, t, inv_maxN, inv_maxT, inv_2g2);
+                else {
+                    const float w = guide_t(G, b, n, t);
+                    att_part += G.mse ? (a - w) * (a - w) : a * w;       // sum (A - W)^2  |  sum |A * W|  (A, W >= 0)
+                }
+            }
         }
         if (argmax_out && lane == 0) argmax_out[row] = arg;
     }
@@ -328,9 +342,9 @@ __global__ void softmax_fwd_kernel(float* __restrict__ S, long long ldS, int B, 
     }
 }
 
-// dA (in) -> dS (in place):  dS = A * (dA' - sum_n A*dA'),  dA' = dA + att_coef * W[n][t]
+// dA (in) -> dS (in place):  dS = A * (dA' - sum_n A*dA'),  dA' = dA + att_coef * W[n][t]   (MSE variant: + att_coef * 2 (A - W))
 __global__ void softmax_bwd_kernel(const float* __restrict__ A, long long ldA, float* __restrict__ dA, long long lddA,
-                                   int B, int T, int N, float att_coef, int maxN, int maxT, float g,
+                                   int B, int T, int N, float att_coef, int maxN, int maxT, float g, GuideTensor G,
                                    unsigned short* __restrict__ ds_hi, unsigned short* __restrict__ ds_lo, long long ldp) {
     pdl_grid_sync();
     const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
@@ -343,7 +357,13 @@ __global__ void softmax_bwd_kernel(const float* __restrict__ A, long long ldA, f
         float dot = 0.f;
         for (int n = lane; n < N; n += 32) {
             float d = dr[n];
-            if (att_coef != 0.f && n < maxN && t < maxT) d += att_coef * guide_w(n, t, inv_maxN, inv_maxT, inv_2g2);
+            if (att_coef != 0.f && n < maxN && t < maxT) {
+                if (!G.w) d += att_coef * guide_w(n, t, inv_maxN, inv_maxT, inv_2g2);
+                else {
+                    const float w = guide_t(G, b, n, t);
+                    d += att_coef * (G.mse ? 2.f * (ar[n] - w) : w);
+                }
+            }
             dr[n] = d;
             dot += ar[n] * d;
         }

@@ -96,7 +96,7 @@ def AudioEnc(hp, S, training=True, speaker_codes=None, reuse=None, *, in_shift=0
 
 
 def Attention(hp, Q, K, V, monotonic_attention=False, prev_max_attentions=None, *, training=False, att_acc=None,
-              want_alignments=True):
+              want_alignments=True, gts=None):
     '''
     Args:
       Q: Queries. (B, T/r, d)   K: Keys. (B, N, d)   V: Values. (B, N, d)
@@ -108,6 +108,9 @@ def Attention(hp, Q, K, V, monotonic_attention=False, prev_max_attentions=None, 
     B, T, d = Q.shape
     N = K.shape[1]
     prev = None
+    # gts: the batch's own attention targets [B, Ng, Tg] (hp.attention_guide_dir) for the loss terms that this block
+    # accumulates into att_acc; hp.attention_guide_fa selects the MSE variant (architectures.py:256-280)
+    mse = bool(getattr(hp, "attention_guide_fa", False)) and gts is not None
     if monotonic_attention:
         if getattr(hp, "turn_off_monotonic_for_synthesis", False):
             raise NotImplementedError("turn_off_monotonic_for_synthesis needs hp.text_lengths (outside the path)")
@@ -126,7 +129,7 @@ def Attention(hp, Q, K, V, monotonic_attention=False, prev_max_attentions=None, 
         R_out._oph_planes = (hi[:, :, :d], lo[:, :, :d])
     R, A, alignments, max_attentions = ops.attention_fwd(
         Q, K, V, R=R_out, prev_max=prev, win=hp.attention_win_size, want_alignments=want_alignments,
-        att_acc=att_acc, maxN=hp.max_N, maxT=hp.max_T, g=hp.g)
+        att_acc=att_acc, maxN=hp.max_N, maxT=hp.max_T, g=hp.g, gts=gts, mse=mse)
     result = rq if concat else R
     if concat:
         rq._oph_planes = rq._oph_planes_buf         # both halves are written now: AudioDec's first conv reads planes
@@ -138,7 +141,7 @@ def Attention(hp, Q, K, V, monotonic_attention=False, prev_max_attentions=None, 
             dR = dRp[:, :, :d] if concat else dRp
             dq_add = dRp[:, :, d:] if concat else None
             dQ, _dK, _dV = ops.attention_bwd(dR, Q, K, V, A, dq_addend=dq_add, att_coef=att_coef, maxN=hp.max_N,
-                                             maxT=hp.max_T, g=hp.g, dK=dKV[:, :, :d], dV=dKV[:, :, d:])
+                                             maxT=hp.max_T, g=hp.g, dK=dKV[:, :, :d], dV=dKV[:, :, d:], gts=gts, mse=mse)
             return dQ, dKV
         result._oph_attention_bwd = bwd
     return result, alignments, max_attentions

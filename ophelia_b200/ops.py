@@ -5,6 +5,7 @@ libophelia_sm100.so.  Activations are fp32 CUDA tensors `[B, time, C]` whose row
 (`stride(-1) == 1`, `stride(0) == time * stride(1)`), which is how K/V, R/Q share buffers.
 """
 import contextlib
+import ctypes
 import gc
 
 import torch
@@ -305,8 +306,18 @@ def _new_planes(t):
     t._oph_planes = (hi[:, :, :C], lo[:, :, :C])
 
 
+def _guide(gts, mse):
+    """`oph_guide` of the batch's own attention targets [B, Ng, Tg] (None -> analytic global guide).  Outside the block the
+    guided loss sees 1.0 and the MSE variant 0.0 (architectures.py:263, 275)."""
+    if gts is None:
+        return None
+    assert gts.is_cuda and gts.dtype == torch.float32 and gts.dim() == 3 and gts.stride(2) == 1
+    return ctypes.byref(_lib.Guide(gts.data_ptr(), gts.stride(0), gts.stride(1), gts.shape[1], gts.shape[2],
+                                   0.0 if mse else 1.0, int(bool(mse))))
+
+
 def attention_fwd(Q, K, V, R=None, prev_max=None, win=3, want_alignments=False, want_argmax=True, att_acc=None,
-                  maxN=1, maxT=1, g=0.2):
+                  maxN=1, maxT=1, g=0.2, gts=None, mse=False):
     ldq, B, T, d = _rows(Q)
     ldk, _, N, _ = _rows(K)
     _rows(V)
@@ -321,11 +332,13 @@ def attention_fwd(Q, K, V, R=None, prev_max=None, win=3, want_alignments=False, 
     _rows(R)
     pq, pk_, pv = ensure_planes(Q), ensure_planes(K), ensure_planes(V)      # locals keep fresh splits alive over the call
     _lib.call("oph_attention_fwd", _act(Q, planes=pq), _act(K, planes=pk_), _act(V, planes=pv), _act(A), _act(R), _p(align),
-              _p(argmax), _p(prev_max), int(win), _p(att_acc), int(maxN), int(maxT), float(g), B, T, N, d, _stream())
+              _p(argmax), _p(prev_max), int(win), _p(att_acc), int(maxN), int(maxT), float(g), B, T, N, d, _guide(gts, mse),
+              _stream())
     return R, A, align, argmax
 
 
-def attention_bwd(dR, Q, K, V, A, dq_addend=None, att_coef=0.0, maxN=1, maxT=1, g=0.2, dK=None, dV=None):
+def attention_bwd(dR, Q, K, V, A, dq_addend=None, att_coef=0.0, maxN=1, maxT=1, g=0.2, dK=None, dV=None, gts=None,
+                  mse=False):
     ldq, B, T, d = _rows(Q)
     ldk, _, N, _ = _rows(K)
     dev = Q.device
@@ -345,7 +358,7 @@ def attention_bwd(dR, Q, K, V, A, dq_addend=None, att_coef=0.0, maxN=1, maxT=1, 
               _act(A, planes=pa), _act(dA),
               _p(dQ), dQ.stride(1), _p(dq_addend), dq_addend.stride(1) if dq_addend is not None else 0,
               _p(dK), dK.stride(1), _p(dV), dV.stride(1), float(att_coef), int(maxN), int(maxT), float(g),
-              B, T, N, d, _stream())
+              B, T, N, d, _guide(gts, mse), _stream())
     return dQ, dK, dV
 
 

@@ -200,5 +200,35 @@ def restore_archived_model_parameters(sess, hp, model_type, epoch_number, graph=
     print("Model of type %s restored from archived epoch %s" % (model_type, epoch_number))
 
 
+def make_mel_batch(hp, fnames, oracle=True):
+    """synthesize.py:270-284: natural coarse mels of `fnames` (from hp.coarse_audio_dir when `oracle`, else the paths
+    themselves) zero-padded to [n, max_T, n_mels]; lengths in full-rate frames (r per coarse frame)."""
+    import os
+    import re
+    if oracle:
+        paths = [os.path.join(hp.coarse_audio_dir, re.sub(r'\.[^\.]+\Z', '', os.path.split(f)[1]) + '.npy') for f in fnames]
+    else:
+        paths = list(fnames)
+    batch = np.zeros((len(paths), hp.max_T, hp.n_mels), np.float32)
+    lengths = []
+    for i, path in enumerate(paths):
+        mel = np.load(path)
+        batch[i, :mel.shape[0], :] = mel
+        lengths.append(mel.shape[0] * hp.r)
+    return batch, lengths
+
+
+def list2batch(inlist, pad_length):
+    """synthesize.py:286-299: stack [len_i, dim] arrays into [n, pad_length (0 = longest), dim], zero padded."""
+    dim = inlist[0].shape[1]
+    if pad_length == 0:
+        pad_length = max(a.shape[0] for a in inlist)
+    batch = np.zeros((len(inlist), pad_length, dim), np.float32)
+    for i, array in enumerate(inlist):
+        assert array.shape[0] <= pad_length and array.shape[1] == dim
+        batch[i, :array.shape[0], :] = array
+    return batch
+
+
 def split_batch(synth_batch, end_indices):
     return [predmel[:end_indices[i], :] for i, predmel in enumerate(synth_batch)]

@@ -377,3 +377,59 @@ def save(store, prefix, with_optimizer=True):
     with open(os.path.join(os.path.dirname(os.path.abspath(prefix)), "checkpoint"), "w") as f:
         base = os.path.basename(prefix)
         f.write('model_checkpoint_path: "%s"\nall_model_checkpoint_paths: "%s"\n' % (base, base))
+
+
+def _read_state(directory):
+    """(latest, all paths) of the `checkpoint` state file (text-format CheckpointState proto), paths as written."""
+    state = os.path.join(directory, "checkpoint")
+    latest, paths = None, []
+    if os.path.exists(state):
+        with open(state) as f:
+            for line in f:
+                key, _, val = line.partition(":")
+                val = val.strip().strip('"')
+                if key.strip() == "model_checkpoint_path":
+                    latest = val
+                elif key.strip() == "all_model_checkpoint_paths":
+                    paths.append(val)
+    return latest, paths
+
+
+class Saver(object):
+    """The part of `tf.train.Saver` that train.py relies on through `tf.train.Supervisor` (train.py:190, 296-297):
+    `save(store, prefix)` writes `<prefix>.index` / `<prefix>.data-00000-of-00001`, keeps the `max_to_keep` (5) most
+    recent checkpoints of the directory, deletes older ones and maintains the `checkpoint` state file that
+    `latest_checkpoint` reads.  Checkpoints listed by an existing state file are adopted, so a resumed run keeps
+    rotating the files of the previous run."""
+
+    def __init__(self, max_to_keep=5):
+        self.max_to_keep = max_to_keep
+        self._dirs = {}
+
+    def _known(self, directory):
+        if directory not in self._dirs:
+            _, paths = _read_state(directory)
+            self._dirs[directory] = [p for p in paths
+                                     if os.path.exists((p if os.path.isabs(p) else os.path.join(directory, p)) + ".index")]
+        return self._dirs[directory]
+
+    def save(self, store, prefix, with_optimizer=True):
+        directory = os.path.dirname(os.path.abspath(prefix))
+        os.makedirs(directory, exist_ok=True)
+        known = self._known(directory)
+        save(store, prefix, with_optimizer=with_optimizer)          # (also writes a one-entry state file)
+        base = os.path.basename(prefix)
+        if base in known:
+            known.remove(base)
+        known.append(base)
+        while self.max_to_keep and len(known) > self.max_to_keep:
+            old = known.pop(0)
+            old = old if os.path.isabs(old) else os.path.join(directory, old)
+            for suffix in (".index", ".data-00000-of-00001", ".meta"):
+                if os.path.exists(old + suffix):
+                    os.remove(old + suffix)
+        with open(os.path.join(directory, "checkpoint"), "w") as f:
+            f.write('model_checkpoint_path: "%s"\n' % base)
+            for p in known:
+                f.write('all_model_checkpoint_paths: "%s"\n' % p)
+        return prefix

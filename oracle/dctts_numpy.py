@@ -261,9 +261,19 @@ def _loss_weights(hp, which):
     return hp.lw_mag, hp.lw_bd2, getattr(hp, "lw_ssrn_l2", 0.0)
 
 
-def text2mel_loss(hp, out, mels, guide=None):
-    """architectures.py:241-355, guided-attention branch (attention_guide_fa False, lw_cdp=ain=aout=0).
-    Returns loss_components [loss, L1, BD, att, L2]."""
+def _pad_crop(x, value, max_N, max_T):
+    """`tf.pad(x, [(0,0),(0,max_N),(0,max_T)], constant_values=value)[:, :max_N, :max_T]` (architectures.py:261-263)."""
+    B, n, t = x.shape
+    out = np.full((B, n + max_N, t + max_T), float(value))
+    out[:, :n, :t] = x
+    return out[:, :max_N, :max_T]
+
+
+def text2mel_loss(hp, out, mels, guide=None, gts=None):
+    """architectures.py:241-355 (lw_cdp=ain=aout=0).  Returns loss_components [loss, L1, BD, att, L2].
+    gts: the batch's per-utterance guides / forced-alignment targets [B, Ng, Tg] (hp.attention_guide_dir, :57-58), zero
+    padded within the batch like the reference's dynamic_pad queue; None = global guide (:60).  hp.attention_guide_fa
+    selects the MSE branch (:271-280)."""
     mels = np.asarray(mels, np.float64)
     Y, logits, A = out["Y"], out["Y_logits"], out["alignments"]
     loss_l2 = ((Y - mels) ** 2).mean()
@@ -277,7 +287,15 @@ def text2mel_loss(hp, out, mels, guide=None):
     Ap[:, :Nb, :Tb] = A
     Ap = Ap[:, :hp.max_N, :hp.max_T]
     mask = (Ap != -1).astype(np.float64)
-    loss_att = (np.abs(Ap * np.asarray(guide, np.float64)[None]) * mask).sum() / mask.sum()
+    if gts is not None and getattr(hp, "attention_guide_fa", False):            # :271-280
+        A0 = _pad_crop(A, 0.0, hp.max_N, hp.max_T)
+        G0 = _pad_crop(np.asarray(gts, np.float64), 0.0, hp.max_N, hp.max_T)
+        loss_att = ((A0 - G0) ** 2).sum() / mask.sum()
+    elif gts is not None:                                                        # :262-268 with :263's padding by 1.0
+        G1 = _pad_crop(np.asarray(gts, np.float64), 1.0, hp.max_N, hp.max_T)
+        loss_att = (np.abs(Ap * G1) * mask).sum() / mask.sum()
+    else:
+        loss_att = (np.abs(Ap * np.asarray(guide, np.float64)[None]) * mask).sum() / mask.sum()
     w1, wbd, watt, w2 = _loss_weights(hp, "t2m")
     loss = w1 * loss_mels + wbd * loss_bd1 + watt * loss_att + w2 * loss_l2
     return [loss, loss_mels, loss_bd1, loss_att, loss_l2]

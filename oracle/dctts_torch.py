@@ -195,7 +195,14 @@ def _lw(hp, which):
     return hp.lw_mag, hp.lw_bd2, getattr(hp, "lw_ssrn_l2", 0.0)
 
 
-def text2mel_loss(hp, out, mels):
+def _pad_crop(x, value, max_N, max_T):
+    """tf.pad(..., constant_values=value)[:, :max_N, :max_T] (architectures.py:261-263)."""
+    return F.pad(x, (0, max_T, 0, max_N), value=float(value))[:, :max_N, :max_T]
+
+
+def text2mel_loss(hp, out, mels, gts=None):
+    """gts: per-utterance guides / forced-alignment targets of the batch [B, Ng, Tg] (architectures.py:57-58), else
+    the global guide; hp.attention_guide_fa selects the MSE branch (:271-280)."""
     Y, logits, A = out["Y"], out["Y_logits"], out["alignments"]
     l2 = ((Y - mels) ** 2).mean()
     l1 = (Y - mels).abs().mean()
@@ -204,6 +211,14 @@ def text2mel_loss(hp, out, mels):
     Nb, Tb = min(A.shape[1], hp.max_N), min(A.shape[2], hp.max_T)
     Ac = A[:, :Nb, :Tb]
     att = (Ac * W[None, :Nb, :Tb]).abs().sum() / float(Ac.numel())
+    if gts is not None:
+        gts = torch.as_tensor(gts).to(Y.dtype)
+        mask = (_pad_crop(A, -1.0, hp.max_N, hp.max_T) != -1).to(Y.dtype)
+        if getattr(hp, "attention_guide_fa", False):
+            d = _pad_crop(A, 0.0, hp.max_N, hp.max_T) - _pad_crop(gts, 0.0, hp.max_N, hp.max_T)
+            att = (d * d).sum() / mask.sum()
+        else:
+            att = ((_pad_crop(A, -1.0, hp.max_N, hp.max_T) * _pad_crop(gts, 1.0, hp.max_N, hp.max_T)).abs() * mask).sum() / mask.sum()
     w1, wbd, watt, w2 = _lw(hp, "t2m")
     return [w1 * l1 + wbd * bd + watt * att + w2 * l2, l1, bd, att, l2]
 
@@ -246,12 +261,12 @@ class TFAdam(object):
         self.global_step += 1
 
 
-def text2mel_train_step(hp, P, opt, L, mels, gen=None):
+def text2mel_train_step(hp, P, opt, L, mels, gen=None, gts=None):
     """One `sess.run([global_step, loss_components, train_op])` (train.py:273)."""
     for p in P.values():
         p.grad = None
     out = text2mel_forward(hp, P, L, mels, "train", gen=gen)
-    comps = text2mel_loss(hp, out, mels)
+    comps = text2mel_loss(hp, out, mels, gts=gts)
     comps[0].backward()
     grads = {k: p.grad for k, p in P.items() if p.grad is not None}
     opt.step(grads)

@@ -44,3 +44,64 @@ def check_grads(ours, ref, strict_prefix, median_tol=1.5e-2, max_tol=5e-2, stric
     assert errs[0][0] < max_tol, errs[:5]
     assert float(np.median(vals)) < median_tol, (float(np.median(vals)), errs[:5])
     return errs
+
+
+def make_corpus(root, n_utts=14, n_valid=3, max_N=24, max_T=40, seed=0, guides=True, full_dim=513, **overrides):
+    """A tiny on-disk corpus in the reference's layout (transcript `name|raw|normalised|phones`, .npy features under
+    mels/ full_mels/ mags/ attention_guides/) plus a python-syntax config file like config/lj_test.cfg.
+    Returns (config path, hp)."""
+    import os
+    from ophelia_b200.configuration import load_config
+    from ophelia_b200.data_load import save_floats_as_8bit
+    from ophelia_b200.utils import get_attention_guide
+    rng = np.random.default_rng(seed)
+    root = str(root)
+    dirs = {k: os.path.join(root, "data", k) for k in ("mels", "full_mels", "mags", "attention_guides")}
+    for d in dirs.values():
+        os.makedirs(d, exist_ok=True)
+    phones = ['a', 'b', 'd', 'e', 'i', 'k', 'l', 'm', 'n', 'o', 's', 't']
+    vocab = ['<PADDING>', '<_END_>', '<_START_>'] + phones
+    r, n_mels = 4, 80
+    lines = []
+    for u in range(n_utts + 2):
+        name = ("VAL050-%04d" if u < n_valid else "TRN001-%04d") % u
+        n = int(rng.integers(max_N // 2, max_N - 2))
+        t = int(rng.integers(max_T // 2, max_T + 1))
+        if u == n_utts:
+            t = max_T + 5                                   # too many frames: skipped by load_data
+        if u == n_utts + 1:
+            n = max_N + 4                                   # too many symbols: skipped
+        seq = ['<_START_>'] + [phones[int(i)] for i in rng.integers(0, len(phones), n)] + ['<_END_>']
+        full_mel = rng.uniform(1e-8, 1.0, (t * r, n_mels)).astype(np.float32)
+        np.save(os.path.join(dirs["full_mels"], name + ".npy"), full_mel)
+        np.save(os.path.join(dirs["mels"], name + ".npy"), full_mel[::r])
+        np.save(os.path.join(dirs["mags"], name + ".npy"), rng.uniform(1e-8, 1.0, (t * r, full_dim)).astype(np.float32))
+        if len(seq) <= max_N and t <= max_T:
+            save_floats_as_8bit(get_attention_guide(len(seq), t, g=0.2), os.path.join(dirs["attention_guides"], name + ".npy"))
+        lines.append("%s|Raw text %d.|raw text %d.|%s" % (name, u, u, " ".join(seq)))
+    lines.insert(2, "")                                      # blank lines are ignored
+    lines.append("NOFEATS-0001|x|x|<_START_> a <_END_>")     # no feature files: skipped
+    with open(os.path.join(root, "transcript.csv"), "w") as f:
+        f.write("\n".join(lines) + "\n")
+    with open(os.path.join(root, "test_transcript.csv"), "w") as f:
+        f.write("\n".join(l for l in lines[:4] if l) + "\n")
+    cfg = dict(
+        voicedir=root, logdir=os.path.join(root, "train"), sampledir=os.path.join(root, "synth"),
+        coarse_audio_dir=dirs["mels"], full_mel_dir=dirs["full_mels"], full_audio_dir=dirs["mags"],
+        attention_guide_dir=dirs["attention_guides"] if guides else '',
+        transcript=os.path.join(root, "transcript.csv"), test_transcript=os.path.join(root, "test_transcript.csv"),
+        waveforms=os.path.join(root, "wav"), input_type='phones', vocab=vocab, max_N=max_N, max_T=max_T, multispeaker=[],
+        n_utts=0, random_reduction_on_the_fly=True, prepro=True, vocoder='griffin_lim', sr=22050, n_fft=(full_dim - 1) * 2,
+        hop_length=275, win_length=1102, full_dim=full_dim, n_mels=n_mels, power=1.5, n_iter=50, preemphasis=.97, max_db=100, ref_db=20, r=r,
+        dropout_rate=0.05, e=128, d=256, c=512, attention_win_size=3, g=0.2, norm='layer', lw_mel=0.3333, lw_bd1=0.3333,
+        lw_att=0.3333, lw_mag=0.5, lw_bd2=0.5, validpatt='VAL050-', validation_sentences_to_evaluate=32,
+        validation_sentences_to_synth_params=2, restart_from_savepath=[], lr=0.001, batchsize={'t2m': 4, 'ssrn': 4},
+        num_threads=0, validate_every_n_epochs=1, save_every_n_epochs=2, max_epochs=2, plot_attention_every_n_epochs=1,
+        num_sentences_to_plot_attention=2, bucket_data_by='text_length')
+    cfg.update(overrides)
+    path = os.path.join(root, "tiny.cfg")
+    with open(path, "w") as f:
+        f.write("config_name = 'tiny'\n")
+        for k, v in cfg.items():
+            f.write("%s = %r\n" % (k, v))
+    return path, load_config(path)

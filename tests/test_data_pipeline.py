@@ -1,0 +1,172 @@
+"""Host-side input pipeline, checkpoint rotation and validation measures (no GPU): the contracts of data_load.py,
+objective_measures.py and the Saver used by train.py, on a tiny on-disk corpus in the reference's layout."""
+import os
+
+import numpy as np
+import torch
+
+from helpers import make_corpus
+
+
+def test_load_data_filters_and_modes(tmp_path):
+    from ophelia_b200.data_load import load_data, load_vocab
+    cfg, hp = make_corpus(tmp_path)
+    train = load_data(hp, "train")
+    valid = load_data(hp, "validation")
+    synth = load_data(hp, "synthesis")
+    # 16 utterances with features: 3 held out by validpatt, 1 too long in frames, 1 too long in symbols
+    assert len(train['fpaths']) == 11 and len(valid['fpaths']) == 3
+    assert all('TRN001-' in f for f in train['fpaths']) and all('VAL050-' in f for f in valid['fpaths'])
+    assert len(train['audio_lengths']) == len(train['fpaths']) == len(train['text_lengths']) == len(train['texts'])
+    assert train['label_lengths'] == []
+    char2idx, idx2char = load_vocab(hp)
+    first = train['texts'][0]
+    assert first.dtype == np.int32 and idx2char[int(first[0])] == '<_START_>' and idx2char[int(first[-1])] == '<_END_>'
+    assert valid['texts'].shape == (3, hp.max_N) and valid['texts'].dtype == np.int32
+    assert synth['texts'].shape == (3, hp.max_N) and (synth['texts'][:, 0] == char2idx['<_START_>']).all()
+    hp.n_utts = 5
+    assert len(load_data(hp, "train")['fpaths']) == 5
+
+
+def test_text_normalize_letters():
+    from ophelia_b200.configuration import default_hparams
+    from ophelia_b200.data_load import text_normalize
+    hp = default_hparams(vocab="PE abcdefghijklmnopqrstuvwxyz'.?")
+    assert text_normalize(u"Café  au LAIT, 12!", hp) == "cafe au lait "
+
+
+def test_batches_follow_the_reference_contract(tmp_path):
+    from ophelia_b200.data_load import bucket_boundaries, get_batch, read_floats_from_8bit
+    cfg, hp = make_corpus(tmp_path, n_utts=40, n_valid=4)
+    src = get_batch(hp, 4, seed=1)
+    assert src.num_batch == len(src.fpaths) // 4
+    assert src.bounds == bucket_boundaries(src.text_lengths) == list(range(min(src.text_lengths) + 1, max(src.text_lengths) - 1, 20))
+    seen = set()
+    for _ in range(12):
+        b = next(src)
+        assert b['num_batch'] == src.num_batch and len(b['fname']) == 4
+        text, mel, mag, gts = b['text'], b['mel'], b['mag'], b['attention_guide']
+        assert text.dtype == torch.int32 and mel.dtype == mag.dtype == gts.dtype == torch.float32
+        assert mel.shape[0] == 4 and mel.shape[2] == hp.n_mels and mag.shape[2] == hp.full_dim
+        assert mag.shape[1] == hp.r * mel.shape[1]
+        lens = (text != 0).sum(1)
+        assert int(lens.max()) == text.shape[1]                       # dynamic padding: longest member sets the width
+        buckets = {int(np.searchsorted(src.bounds, int(n), side='right')) for n in lens}
+        assert len(buckets) == 1                                       # one batch = one length bucket
+        for i, fname in enumerate(b['fname']):
+            seen.add(fname)
+            base = fname.replace(".wav", ".npy")
+            full = np.load(os.path.join(hp.full_mel_dir, base))
+            t = full.shape[0] // hp.r
+            got = mel[i, :t].numpy()
+            starts = [s for s in range(hp.r) if np.array_equal(full[s::hp.r], got)]
+            assert len(starts) == 1 and (mel[i, t:] == 0).all()        # the random reduction offset (data_load.py:357-361)
+            s = starts[0]
+            fmag = np.load(os.path.join(hp.full_audio_dir, base))
+            assert np.array_equal(mag[i, :fmag.shape[0] - s].numpy(), fmag[s:])   # mag shifted by the same offset ...
+            assert (mag[i, fmag.shape[0] - s:] == 0).all()                        # ... and zero padded at the end (:377)
+            g = read_floats_from_8bit(os.path.join(hp.attention_guide_dir, base))
+            assert np.array_equal(gts[i, :g.shape[0], :g.shape[1]].numpy(), g)
+            assert g.shape[0] == int(lens[i]) and (gts[i, g.shape[0]:] == 0).all() and (gts[i, :, g.shape[1]:] == 0).all()
+    assert len(seen) > 20
+    # prepro route (stored coarse mels, offset 0) and a Text2Mel run that skips the magnitude files
+    hp.random_reduction_on_the_fly = False
+    b = next(get_batch(hp, 4, need=('text', 'mel'), seed=2))
+    assert 'mag' not in b
+    for i, fname in enumerate(b['fname']):
+        ref = np.load(os.path.join(hp.coarse_audio_dir, fname.replace(".wav", ".npy")))
+        assert np.array_equal(b['mel'][i, :ref.shape[0]].numpy(), ref)
+
+
+def test_loader_threads_and_rank_shards(tmp_path):
+    from ophelia_b200.data_load import get_batch
+    cfg, hp = make_corpus(tmp_path, n_utts=30, n_valid=2)
+    # every utterance appears exactly once per epoch, split between the ranks without overlap
+    a = get_batch(hp, 2, need=('text', 'mel'), seed=3, rank=0, world=2)
+    b = get_batch(hp, 2, need=('text', 'mel'), seed=3, rank=1, world=2)
+    n = len(a.fpaths)
+    ia = [a._next_index() for _ in range((n + 1) // 2)]
+    ib = [b._next_index() for _ in range(n // 2)]
+    assert sorted(ia + ib) == list(range(n))
+    # threaded loading yields the same kind of batches and shuts down cleanly
+    src = get_batch(hp, 4, need=('text', 'mel'), seed=4, num_threads=3)
+    names = []
+    for _ in range(10):
+        names.extend(next(src)['fname'])
+    src.close()
+    assert len(names) == 40 and len(set(names)) > 10
+    # a missing feature file surfaces as an exception in the consumer, not as a hang
+    src = get_batch(hp, 4, need=('text', 'mel'), seed=5, num_threads=2)
+    for f in os.listdir(hp.full_mel_dir):
+        os.remove(os.path.join(hp.full_mel_dir, f))
+    try:
+        for _ in range(200):
+            next(src)
+        raise AssertionError("expected a loader error")
+    except (IOError, OSError):
+        pass
+    finally:
+        src.close()
+
+
+def test_saver_keeps_five_and_resumes(tmp_path):
+    from ophelia_b200 import tf_checkpoint
+    from ophelia_b200.variables import VariableStore
+    store = VariableStore("cpu", seed=0)
+    store.declare("SSRN/C_1/conv1d/kernel", (1, 8, 16), "kernel")
+    store.declare("SSRN/C_1/conv1d/bias", (16,), "zeros")
+    store.finalize(with_optimizer=True)
+    logdir = str(tmp_path / "train-ssrn")
+    saver = tf_checkpoint.Saver(max_to_keep=5)
+    for epoch in range(4):
+        store.global_step.fill_(10 * epoch)
+        saver.save(store, logdir + "/model_epoch_%d" % epoch)
+    saver = tf_checkpoint.Saver(max_to_keep=5)                     # a resumed run adopts the files of the previous one
+    for epoch in range(4, 8):
+        store.vars["SSRN/C_1/conv1d/bias"].fill_(float(epoch))
+        store.global_step.fill_(10 * epoch)
+        saver.save(store, logdir + "/model_epoch_%d" % epoch)
+    kept = sorted(f for f in os.listdir(logdir) if f.endswith(".index"))
+    assert kept == ["model_epoch_%d.index" % e for e in range(3, 8)]
+    assert not os.path.exists(logdir + "/model_epoch_2.data-00000-of-00001")
+    latest = tf_checkpoint.latest_checkpoint(logdir)
+    assert latest.endswith("model_epoch_7")
+    state = open(os.path.join(logdir, "checkpoint")).read()
+    assert state.count("all_model_checkpoint_paths") == 5 and 'model_checkpoint_path: "model_epoch_7"' in state
+    other = VariableStore("cpu", seed=1)
+    other.declare("SSRN/C_1/conv1d/kernel", (1, 8, 16), "kernel")
+    other.declare("SSRN/C_1/conv1d/bias", (16,), "zeros")
+    other.finalize(with_optimizer=True)
+    tf_checkpoint.restore(other, latest)
+    assert int(other.global_step.item()) == 70 and float(other.vars["SSRN/C_1/conv1d/bias"][3]) == 7.0
+    assert torch.equal(other.vars["SSRN/C_1/conv1d/kernel"], store.vars["SSRN/C_1/conv1d/kernel"])
+
+
+def test_objective_measures():
+    from ophelia_b200 import objective_measures as om
+    rng = np.random.default_rng(0)
+    nat, syn = rng.normal(size=(17, 6)), rng.normal(size=(23, 6))
+    C = np.array([[om.logSpecDbDist(x, y) for y in syn] for x in nat])
+    np.testing.assert_allclose(om._cost_matrix(nat, syn), C, rtol=1e-10)
+    D = np.full(C.shape, np.inf)
+    for i in range(C.shape[0]):
+        for j in range(C.shape[1]):
+            prev = 0.0 if i == j == 0 else min(D[i - 1, j] if i else np.inf, D[i, j - 1] if j else np.inf,
+                                               D[i - 1, j - 1] if i and j else np.inf)
+            D[i, j] = C[i, j] + prev
+    assert abs(om.dtw_min_cost(C) - D[-1, -1]) < 1e-9
+    assert abs(om.compute_dtw_error([nat], [syn]) - D[-1, -1] / 17) < 1e-9
+    assert om.compute_dtw_error([nat], [nat]) < 1e-6                 # a sequence aligns with itself at no cost
+    # known answer: two frames that differ by 1 in one bin -> 10 / ln(10) * sqrt(2) dB
+    a = np.zeros((4, 3)); b = a.copy(); b[:, 1] = 1.0
+    assert abs(om.compute_simple_LSD([a], [b]) - 10.0 / np.log(10.0) * np.sqrt(2.0)) < 1e-12
+
+
+def test_validation_set_of_the_training_driver(tmp_path):
+    from ophelia_b200 import train as drv
+    cfg, hp = make_corpus(tmp_path)
+    names, inputs, reference, texts, mels = drv._validation_set(hp, 't2m')
+    assert len(names) == 3 and inputs.shape == (3, hp.max_N) and len(reference) == 3 and reference[0].shape[1] == hp.n_mels
+    names2, inputs2, reference2, _, _ = drv._validation_set(hp, 'ssrn')
+    assert list(names2) == list(names)                               # seeded shuffle (train.py:111-115)
+    assert inputs2.shape == (3, hp.max_T, hp.n_mels) and reference2[0].shape[1] == hp.full_dim

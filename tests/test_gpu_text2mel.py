@@ -101,6 +101,40 @@ def test_train_step_matches_oracle(shape, l1):
         assert maxabs(new[name], p.detach().numpy()) < 5e-6 + 0.2 * 3 * ot.noam(hp.lr, 2), name
 
 
+@pytest.mark.parametrize("fa,gshape", [(False, (3, 30, 80)), (False, (3, 37, 95)), (True, (3, 37, 90)), (True, (3, 31, 77))])
+def test_train_step_with_batch_guides_matches_oracle(fa, gshape):
+    """hp.attention_guide_dir: the attention targets come with the batch (architectures.py:57-58) -- per-utterance guides
+    padded with 1.0 (:263) or, with hp.attention_guide_fa, forced-alignment targets under an MSE loss (:271-280).
+    First with the attention term alone (its gradient reaches the encoders through Q and K only: tight bound on the
+    ReLU-free AudioEnc tail), then two optimiser steps with all terms."""
+    B, N, T = 3, 37, 90
+    rng = np.random.default_rng(3)
+    gts = rng.uniform(0.0, 1.0, gshape).astype(np.float32)
+    gts[1, gshape[1] - 5:, :] = 0.0                                   # dynamic_pad zeros of a shorter utterance
+    gts[1, :, gshape[2] - 9:] = 0.0
+    b = synthetic_batch(make_hp(), B, N, T, ragged=True)
+    L, mels = torch.tensor(b["L"].astype(np.int64)), torch.tensor(b["mels"], dtype=torch.float64)
+    Ld, md, gd = torch.tensor(b["L"]).cuda(), torch.tensor(b["mels"]).cuda(), torch.tensor(gts).cuda()
+    for att_only in (True, False):
+        hp = make_hp(max_N=N + 3, max_T=T + 2, dropout_rate=0.0, attention_guide_dir="from-the-batch", attention_guide_fa=fa)
+        if att_only:
+            hp.lw_mel, hp.lw_bd1, hp.lw_att, hp.lw_t2m_l2 = 0.0, 0.0, 1.0, 0.0
+        P = oracle_params(hp, "t2m", seed=4)
+        Pt = ot.to_torch(P, torch.float64, requires_grad=True)
+        opt = ot.TFAdam(hp, Pt)
+        g = _graph(hp, "train", P, data=iter([]))
+        for step in range(1 if att_only else 2):
+            comps_ref, grads_ref = ot.text2mel_train_step(hp, Pt, opt, L, mels, gts=gts)
+            comps = g.train_step_device(Ld, md, gd).cpu().numpy()
+            np.testing.assert_allclose(comps, comps_ref, rtol=2e-4, atol=1e-6)
+            if att_only:
+                sd = g.store.grads
+                check_grads({n: sd[n].cpu().numpy() for n in grads_ref}, grads_ref, "Text2Mel/AudioEnc/HC_13/")
+    # a batch without targets is refused when the configuration promises them, and the other way round
+    with pytest.raises(AssertionError):
+        g.train_step_device(Ld, md)
+
+
 def test_autoregressive_loop_matches_oracle():
     from ophelia_b200.session import Session
     from ophelia_b200 import synthesize as syn

@@ -1,0 +1,66 @@
+"""The training driver end to end on a tiny on-disk corpus (train.py:main_work flow): data_load batches with
+per-utterance attention guides -> Session.run training steps -> validation -> TF-format checkpoints -> resume ->
+synthesis from the restored checkpoint."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from helpers import make_corpus
+
+pytestmark = pytest.mark.gpu
+
+
+def test_text2mel_training_driver_end_to_end(tmp_path):
+    from ophelia_b200 import synthesize as syn
+    from ophelia_b200 import tf_checkpoint
+    from ophelia_b200 import train as drv
+    from ophelia_b200.architectures import Text2MelGraph
+    from ophelia_b200.session import Session
+    cfg, hp = make_corpus(tmp_path, n_utts=22, n_valid=3, max_epochs=6, save_every_n_epochs=2, decay_lr=False)
+    logdir = hp.logdir + "-t2m"
+    score = drv.train(hp, 't2m')
+    assert np.isfinite(score) and score > 0
+    kept = sorted(os.path.basename(f) for f in glob.glob(logdir + "/model_epoch_*.index"))
+    assert kept == ["model_epoch_%d.index" % e for e in range(2, 7)]                       # the 5 most recent of epochs 0..6
+    archived = sorted(os.path.basename(f) for f in glob.glob(logdir + "/archive/model_epoch_*.index"))
+    assert archived == ["model_epoch_%d.index" % e for e in (0, 2, 4, 6)]
+    for e in range(7):
+        files = os.listdir("%s/validation_epoch_%d" % (logdir, e))
+        assert len(files) == 2 and all(f.startswith("VAL050-") for f in files)
+    assert len(glob.glob(logdir + "/alignments/alignment_*_*.npy")) == 2 * 8                 # epochs -1..6, two sentences
+    ali = np.load(logdir + "/alignments/alignment_1_6.npy")
+    assert ali.shape == (hp.max_N, hp.max_T) and np.allclose(ali.sum(0), 1.0, atol=1e-4)
+    log = open(glob.glob(logdir + "/log_*.txt")[0]).read()
+    assert log.count("train epoch") == 7 and "Max epochs (6) reached" in log
+    # the training loss falls over the 7 epochs (mean total loss is the first number of each 'train epoch' line)
+    totals = [float(l.split(": ")[1].split()[0]) for l in log.splitlines() if "train epoch" in l]
+    assert totals[-1] < totals[0]
+    steps_per_epoch = 19 // 4
+    ck = tf_checkpoint.read_checkpoint(logdir + "/model_epoch_6", names=["global_step"])
+    assert int(np.asarray(ck["global_step"]).reshape(-1)[0]) == 7 * steps_per_epoch
+    # resume: the epoch counter and the optimiser state continue from the latest checkpoint (train.py:193-197)
+    hp.max_epochs = 7
+    drv.train(hp, 't2m')
+    ck = tf_checkpoint.read_checkpoint(logdir + "/model_epoch_7", names=["global_step"])
+    assert int(np.asarray(ck["global_step"]).reshape(-1)[0]) == 9 * steps_per_epoch          # epochs 6 and 7 ran again / anew
+    # synthesis from the checkpoint with the reference's restore call
+    g = Text2MelGraph(hp, mode="synthesize")
+    sess = Session()
+    assert syn.restore_latest_model_parameters(sess, hp, 't2m', graph=g) == '7'
+    from ophelia_b200.data_load import load_data
+    L = load_data(hp, mode="synthesis")['texts']
+    Y, lengths = syn.synth_text2mel(hp, L, g, sess)
+    assert Y.shape == (len(L), hp.max_T, hp.n_mels) and np.isfinite(Y).all()
+
+
+def test_ssrn_training_driver(tmp_path):
+    from ophelia_b200 import train as drv
+    cfg, hp = make_corpus(tmp_path, n_utts=14, n_valid=2, max_epochs=1, guides=False)
+    score = drv.train(hp, 'ssrn')
+    assert np.isfinite(score) and score > 0
+    logdir = hp.logdir + "-ssrn"
+    assert sorted(os.path.basename(f) for f in glob.glob(logdir + "/model_epoch_*.index")) == ["model_epoch_0.index", "model_epoch_1.index"]
+    pred = np.load(glob.glob(logdir + "/validation_epoch_1/*.npy")[0])
+    assert pred.shape[1] == hp.full_dim and pred.shape[0] % hp.r == 0
