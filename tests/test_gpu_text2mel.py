@@ -197,30 +197,34 @@ def test_capture_survives_dead_cycle_owning_another_captured_step():
     """A discarded Graph object is a reference cycle; the autoregressive route parks a captured step (with its private
     pool) on it.  If Python's cyclic collector frees that cycle while the next capture is open, the release invalidates
     the capture (cudaErrorStreamCaptureInvalidated at the next launch).  ops.capture collects first and keeps the
-    collector off; here the collector is made as eager as possible to show it."""
+    collector off while the capture is open; here the collector is off from the start, so the garbage survives until
+    ops.capture itself removes it -- before the capture begins."""
     import gc
+    import weakref
     from ophelia_b200 import synthesize as syn
     B, N, T = 2, 20, 32
     hp = make_hp(max_N=N, max_T=T, dropout_rate=0.0)
     P = oracle_params(hp, "t2m", seed=2)
     b = synthetic_batch(hp, B, N, T, ragged=False)
-    gs = _graph(hp, "synthesize", P)
-    enc = gs.encode_text({"L": b["L"]})
-    K, V = enc["K"].cpu().numpy(), enc["V"].cpu().numpy()
-    syn.synth_codedtext2mel_device(hp, K, V, [N + 1] * B, gs, use_cuda_graph=True)
-    assert gs._ar_state
-    gs._self = gs                                   # make sure it is garbage only the cyclic collector can free
-    del gs, enc
-    hp2 = make_hp(max_N=N, max_T=T, dropout_rate=0.0)
-    g = _graph(hp2, "train", P, data=iter([]))
     Ld, md = torch.tensor(b["L"]).cuda(), torch.tensor(b["mels"]).cuda()
-    old = gc.get_threshold()
-    gc.set_threshold(1, 1, 1)
+    gc.collect()
+    gc.disable()
     try:
-        step = g.capture_train_step(Ld, md, warmup=1)
+        gs = _graph(hp, "synthesize", P)
+        enc = gs.encode_text({"L": b["L"]})
+        K, V = enc["K"].cpu().numpy(), enc["V"].cpu().numpy()
+        syn.synth_codedtext2mel_device(hp, K, V, [N + 1] * B, gs, use_cuda_graph=True)
+        assert gs._ar_state
+        dead = weakref.ref(gs)
+        del gs, enc                                  # garbage that only the cyclic collector can free (Node <-> Graph)
+        g = _graph(make_hp(max_N=N, max_T=T, dropout_rate=0.0), "train", P, data=iter([]))
+        g.train_step_device(Ld, md)                  # lazy initialisation outside the capture
+        assert dead() is not None
+        step = g.capture_train_step(Ld, md, warmup=0)
+        assert dead() is None and not gc.isenabled()
         c = step(Ld, md).cpu().numpy()
     finally:
-        gc.set_threshold(*old)
+        gc.enable()
     assert np.isfinite(c).all()
 
 
