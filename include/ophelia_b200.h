@@ -38,6 +38,10 @@ typedef void* oph_stream_t; /* cudaStream_t */
 
 int oph_version(void);
 const char* oph_last_error(void);
+/* Host helper (no GPU work): CRC-32C of a byte range, continuing from `crc` (0 to start) -- the checksum of the TF-V2
+ * checkpoint format (tensor_bundle records and leveldb table blocks) that ophelia_b200/tf_checkpoint.py reads and writes
+ * in place of tf.train.Saver (train.py:296-297, synthesize.py:302-330). */
+unsigned int oph_crc32c(const void* data, unsigned long long n, unsigned int crc);
 
 /* ---- instrumentation used by bench.py ---------------------------------------------------------------------
  * oph_launch_count: kernels launched by this library so far (all streams).
@@ -171,7 +175,9 @@ int oph_embed_bwd(const int32_t* ids, const float* dout, long long ldo, float* d
 /* ---- networks.Attention (networks.py:286-325) --------------------------------------------------------------
  * A = softmax(Q K^T / sqrt(d)) [B][T][ldA] (ldA >= N), R = A V written with row stride ldr (so it can land in
  * the first half of the [R, Q] buffer, networks.py:317-319).  prev_max (nullable, int32 [B]) + win enable the
- * forcibly-incremental window: keys outside [prev, prev+win) get -2^32+1 (networks.py:304-313).
+ * forcibly-incremental window: keys outside [prev, prev+win) get -2^32+1 (networks.py:304-313); with win <= 0 prev_max
+ * holds a per-item key count instead and keys n >= prev_max[b] are masked (hp.turn_off_monotonic_for_synthesis,
+ * networks.py:307-309).
  * align_t (nullable) = alignments [B][N][T]; argmax (nullable) int32 [B][T] (first maximum);
  * att_acc (nullable, device double) += sum A*W over n<maxN, t<maxT with the analytic guide (utils.py:155-161), or with
  * the batch's own targets when guide != NULL (see oph_guide). */

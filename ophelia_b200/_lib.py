@@ -30,6 +30,7 @@ GP = ctypes.POINTER(Guide)
 SIGNATURES = {
     "oph_version": (I, []),
     "oph_last_error": (ctypes.c_char_p, []),
+    "oph_crc32c": (ctypes.c_uint, [P, ctypes.c_ulonglong, ctypes.c_uint]),
     "oph_launch_count": (LL, []),
     "oph_gemm_debug_buffer": (I, [P]),
     "oph_gemm_debug_flags": (I, [I]),

@@ -506,6 +506,39 @@ int launch_wgrad(const OperandMap& a, int M, const int* a_off, int aL, int aLs, 
 extern "C" {
 
 int oph_version(void) { return 100; }
+
+// Host-side CRC-32C (Castagnoli, slicing-by-8) for the checkpoint writer / reader: a Text2Mel checkpoint with Adam slots
+// is ~290 MB, which the pure-Python fallback of tf_checkpoint.py checksums at ~10 MB/s.
+unsigned int oph_crc32c(const void* data, unsigned long long n, unsigned int crc) {
+    static unsigned int T[8][256];
+    static std::atomic<bool> ready{false};
+    static std::mutex mu;
+    if (!ready.load(std::memory_order_acquire)) {
+        std::lock_guard<std::mutex> lk(mu);
+        if (!ready.load(std::memory_order_relaxed)) {
+            for (unsigned int i = 0; i < 256; ++i) {
+                unsigned int c = i;
+                for (int k = 0; k < 8; ++k) c = (c & 1) ? (c >> 1) ^ 0x82F63B78u : c >> 1;
+                T[0][i] = c;
+            }
+            for (int t = 1; t < 8; ++t)
+                for (unsigned int i = 0; i < 256; ++i) T[t][i] = (T[t - 1][i] >> 8) ^ T[0][T[t - 1][i] & 0xFF];
+            ready.store(true, std::memory_order_release);
+        }
+    }
+    const unsigned char* p = static_cast<const unsigned char*>(data);
+    unsigned int c = crc ^ 0xFFFFFFFFu;
+    while (n >= 8) {
+        unsigned long long w;
+        memcpy(&w, p, 8);                                   // (little-endian hosts only, like the rest of the format code)
+        w ^= c;
+        c = T[7][w & 0xFF] ^ T[6][(w >> 8) & 0xFF] ^ T[5][(w >> 16) & 0xFF] ^ T[4][(w >> 24) & 0xFF] ^
+            T[3][(w >> 32) & 0xFF] ^ T[2][(w >> 40) & 0xFF] ^ T[1][(w >> 48) & 0xFF] ^ T[0][(w >> 56) & 0xFF];
+        p += 8; n -= 8;
+    }
+    while (n--) c = T[0][(c ^ *p++) & 0xFF] ^ (c >> 8);
+    return c ^ 0xFFFFFFFFu;
+}
 const char* oph_last_error(void) { return g_err; }
 long long oph_launch_count(void) { return g_launches.load(); }
 int oph_gemm_debug_buffer(long long* dev_buf) { g_gemm_dbg = dev_buf; return OPH_OK; }

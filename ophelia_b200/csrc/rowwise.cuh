@@ -293,7 +293,10 @@ __global__ void softmax_fwd_kernel(float* __restrict__ S, long long ldS, int B, 
         const int b = (int)(row / T), t = (int)(row - (long long)b * T);
         float* sr = S + row * ldS;
         int lo = 0, hi = N;
-        if (prev_max) { lo = prev_max[b]; hi = lo + win; }        // allowed keys: lo <= n < hi (networks.py:304-306)
+        if (prev_max) {
+            if (win > 0) { lo = prev_max[b]; hi = lo + win; }     // allowed keys: lo <= n < hi (networks.py:304-306)
+            else hi = prev_max[b];                                // win <= 0: per-item key count, n < hi (networks.py:308-309)
+        }
         float mx = -INFINITY; int arg = 0x7fffffff;
         for (int n = lane; n < N; n += 32) {
             float v = sr[n];

@@ -5,6 +5,7 @@ padding modes follow the reference line by line; the speaker-embedding / Merlin-
 """
 import sys
 
+import numpy as np
 import torch
 
 from . import ops
@@ -112,10 +113,16 @@ def Attention(hp, Q, K, V, monotonic_attention=False, prev_max_attentions=None, 
     # accumulates into att_acc; hp.attention_guide_fa selects the MSE variant (architectures.py:256-280)
     mse = bool(getattr(hp, "attention_guide_fa", False)) and gts is not None
     if monotonic_attention:
-        if getattr(hp, "turn_off_monotonic_for_synthesis", False):
-            raise NotImplementedError("turn_off_monotonic_for_synthesis needs hp.text_lengths (outside the path)")
         assert N == hp.max_N and T == hp.max_T, "networks.py:304-311 builds the mask with hp.max_N / hp.max_T"
-        prev = prev_max_attentions.to(torch.int32).contiguous()
+        win = hp.attention_win_size
+        if getattr(hp, "turn_off_monotonic_for_synthesis", False):
+            # no window: only the keys past each sentence's end are masked (networks.py:307-309; synthesize.py:505-507
+            # sets hp.text_lengths = first padding position + 1 for the batch being synthesised)
+            assert len(hp.text_lengths) == B, "hp.text_lengths must describe the batch (synthesize.py:505-507)"
+            prev = torch.as_tensor(np.asarray(hp.text_lengths), dtype=torch.int32).to(Q.device)
+            win = 0
+        else:
+            prev = prev_max_attentions.to(torch.int32).contiguous()
     concat = getattr(hp, "concatenate_query", True)
     rq = getattr(Q, "_oph_rq", None) if concat else None
     if concat and rq is None:                       # Q did not come from AudioEnc: build the [R, Q] buffer here
@@ -128,7 +135,7 @@ def Attention(hp, Q, K, V, monotonic_attention=False, prev_max_attentions=None, 
         hi, lo = rq._oph_planes_buf
         R_out._oph_planes = (hi[:, :, :d], lo[:, :, :d])
     R, A, alignments, max_attentions = ops.attention_fwd(
-        Q, K, V, R=R_out, prev_max=prev, win=hp.attention_win_size, want_alignments=want_alignments,
+        Q, K, V, R=R_out, prev_max=prev, win=win if prev is not None else hp.attention_win_size, want_alignments=want_alignments,
         att_acc=att_acc, maxN=hp.max_N, maxT=hp.max_T, g=hp.g, gts=gts, mse=mse)
     result = rq if concat else R
     if concat:

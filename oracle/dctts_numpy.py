@@ -243,7 +243,8 @@ def text2mel_forward(hp, P, L, mels, mode="train", prev_max_attentions=None, K=N
     Q = AudioEnc(hp, P, S)
     mono = (mode == "synthesize")
     R, alignments, max_att = Attention(hp, Q, np.asarray(K, np.float64), np.asarray(V, np.float64),
-                                       monotonic_attention=mono, prev_max_attentions=prev_max_attentions)
+                                       monotonic_attention=mono, prev_max_attentions=prev_max_attentions,
+                                       text_lengths=getattr(hp, "text_lengths", None))
     logits, Y = AudioDec(hp, P, R)
     return dict(K=K, V=V, Q=Q, R=R, alignments=alignments, max_attentions=max_att, Y_logits=logits, Y=Y)
 

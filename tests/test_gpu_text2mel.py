@@ -67,6 +67,14 @@ def test_synthesis_mode_window_mask():
     assert maxabs(ali, ref["alignments"]) < 1e-4
     assert (ali[0, :3] == 0).all() and (ali[0, 6:] == 0).all()       # only keys [prev, prev+3) survive
     assert (mx == ref["max_attentions"]).mean() > 0.995
+    # hp.turn_off_monotonic_for_synthesis: no window, keys from each sentence's first padding position + 1 on are masked
+    # (networks.py:307-309 with hp.text_lengths set as in synthesize.py:505-507)
+    hp.turn_off_monotonic_for_synthesis = True
+    hp.text_lengths = np.array([50, 31]) + 1
+    ref = on.text2mel_forward(hp, P, b["L"], b["mels"], "synthesize", prev)
+    Y, ali = sess.run([g.Y, g.alignments], {g.K: K, g.V: V, g.mels: b["mels"], g.prev_max_attentions: prev})
+    assert maxabs(Y, ref["Y"]) < 1e-3 and maxabs(ali, ref["alignments"]) < 1e-4
+    assert (ali[0, 51:] == 0).all() and (ali[1, 32:] == 0).all() and (ali[1, :32] > 0).all()
 
 
 @pytest.mark.parametrize("shape,l1", [((2, 60, 200), True), ((3, 37, 131), True), ((3, 37, 131), False)])
