@@ -7,7 +7,9 @@ Two routes produce identical results:
     B argmax values back per frame for the reference's end-of-sentence test.
 Both re-run AudioEnc + Attention + AudioDec over all max_T frames every step, because the reference applies the
 monotonic window derived from the *latest* prev_max_attentions to every time row (networks.py:304-313).
-Vocoding (Griffin-Lim / WORLD) is outside the hot path.
+`synthesize()` / `main_work()` keep the reference's command line (`python -m ophelia_b200.synthesize -c CONFIG [-N n]
+[-t2m_epoch e] [-ssrn_epoch e] [-odir dir] ...`): restore both models, Text2Mel loop, SSRN, attention diagnostics,
+Griffin-Lim on the GPU (ophelia_b200/vocoder.py).  The WORLD vocoder and babbling are outside the path.
 """
 import numpy as np
 import torch
@@ -232,3 +234,132 @@ def list2batch(inlist, pad_length):
 
 def split_batch(synth_batch, end_indices):
     return [predmel[:end_indices[i], :] for i, predmel in enumerate(synth_batch)]
+
+
+# ---------------------------------------------------------------------------------------------- attention diagnostics
+def getCDP(A):
+    """calculate_CDP_Ain_Aout.py:18-25: coverage deviation penalty of a trimmed alignment [N, T] (0 = every input symbol
+    receives a total attention of exactly 1; trailing symbols without any attention are not counted)."""
+    att_per_input = np.trim_zeros(np.sum(A, axis=1), 'b')
+    return float(np.sum(np.log(1. + (1. - att_per_input) ** 2)) / len(att_per_input))
+
+
+def _mean_entropy(A):
+    """calculate_CDP_Ain_Aout.py:27-43: mean entropy of the rows of A, each renormalised to sum 1, in units of
+    log(row length)."""
+    A = np.asarray(A, np.float64)
+    norm = A.sum(axis=1, keepdims=True)
+    P = np.divide(A, norm, out=A.copy(), where=norm != 0.0)
+    plogp = np.where(P != 0.0, P * np.log(np.where(P != 0.0, P, 1.0)), 0.0)
+    return float(-plogp.sum() / A.shape[0] / np.log(A.shape[1]))
+
+
+def getAP(A):
+    """calculate_CDP_Ain_Aout.py:46-57: absent-mindedness penalties (APin, APout): attention dispersion per input symbol
+    and per output frame."""
+    num_input = len(np.trim_zeros(np.sum(A, axis=1), 'b'))
+    A = A[:num_input, :]
+    return _mean_entropy(A), _mean_entropy(np.transpose(A))
+
+
+# ---------------------------------------------------------------------------------------------- driver
+def synthesize(hp, speaker_id='', num_sentences=0, ncores=1, topoutdir='', t2m_epoch=-1, ssrn_epoch=-1, vocode=True):
+    """synthesize.py:442-632 for the attention-driven single-speaker configurations.  Writes `<base>.wav` (and
+    `<base>_alignment.npy` in place of the attention plot) under `<topoutdir or hp.sampledir>/t2m<e>_ssrn<e>/`.
+    Returns (outdir, bases, lengths).  `ncores` is accepted for command-line compatibility: Griffin-Lim runs on the GPU.
+    vocode=False stops after SSRN (BASELINE config 4: "Griffin-Lim off") and stores the magnitudes as .npy."""
+    import os
+    import re
+    import time
+    from . import vocoder
+    from .architectures import SSRNGraph, Text2MelGraph
+    from .data_load import load_data
+    from .session import Session
+    assert hp.vocoder in ['griffin_lim'], 'Other vocoders than griffin_lim are outside the path'
+    assert not speaker_id and not hp.multispeaker, "multi-speaker synthesis is outside the path"
+    dataset = load_data(hp, mode="synthesis")
+    fpaths, L = dataset['fpaths'], dataset['texts']
+    if num_sentences > 0:
+        assert num_sentences <= len(fpaths)
+        L = L[:num_sentences, :]
+        fpaths = fpaths[:num_sentences]
+    bases = [re.sub(r'\.[^\.]+\Z', '', os.path.split(f)[1]) for f in fpaths]
+    if hp.turn_off_monotonic_for_synthesis:
+        hp.text_lengths = get_text_lengths(L) + 1
+    g1 = Text2MelGraph(hp, mode="synthesize"); print("Graph 1 (t2m) loaded")
+    g2 = SSRNGraph(hp, mode="synthesize"); print("Graph 2 (ssrn) loaded")
+    with Session() as sess:
+        if t2m_epoch > -1:
+            restore_archived_model_parameters(sess, hp, 't2m', t2m_epoch, graph=g1)
+        else:
+            t2m_epoch = restore_latest_model_parameters(sess, hp, 't2m', graph=g1)
+        if ssrn_epoch > -1:
+            restore_archived_model_parameters(sess, hp, 'ssrn', ssrn_epoch, graph=g2)
+        else:
+            ssrn_epoch = restore_latest_model_parameters(sess, hp, 'ssrn', graph=g2)
+        t0 = time.time()
+        text_lengths = get_text_lengths(L)
+        K, V = encode_text(hp, L, g1, sess)
+        Y, lengths, alignments = synth_codedtext2mel_device(hp, K, V, text_lengths, g1)
+        print('Text2Mel generating... %.2f seconds' % (time.time() - t0))
+        t0 = time.time()
+        Z = synth_mel2mag(hp, Y, g2, sess)
+        print('Mel2Mag generating... %.2f seconds' % (time.time() - t0))
+        if np.isnan(Z).any():
+            Z = np.nan_to_num(Z)
+        outdir = os.path.join(topoutdir or hp.sampledir, 't2m%s_ssrn%s' % (t2m_epoch, ssrn_epoch))
+        os.makedirs(outdir, exist_ok=True)
+        print("File |  CDP | Ain")
+        for i in range(len(Z)):
+            trimmed_alignment = alignments[i, :text_lengths[i], :lengths[i]]
+            np.save(os.path.join(outdir, bases[i] + '_alignment.npy'), trimmed_alignment)
+            if trimmed_alignment.size:
+                APin, _APout = getAP(trimmed_alignment)
+                print("%s | %.2f | %.2f" % (bases[i], getCDP(trimmed_alignment), APin))
+        print("Generating wav files, will save to following dir: %s" % (outdir))
+        for i, mag in enumerate(Z):
+            mag = mag[:lengths[i] * hp.r, :]                       # trim to generated length
+            outfile = os.path.join(outdir, bases[i] + '.wav')
+            if vocode:
+                vocoder.synth_wave(hp, mag, outfile)
+            else:
+                np.save(outfile.replace('.wav', '.npy'), mag)
+    return outdir, bases, lengths
+
+
+def main_work():
+    import os
+    import re
+    from argparse import ArgumentParser
+    from .configuration import load_config
+    a = ArgumentParser()
+    a.add_argument('-c', dest='config', required=True, type=str)
+    a.add_argument('-speaker', default='', type=str)
+    a.add_argument('-N', dest='num_sentences', default=0, type=int)
+    a.add_argument('-ncores', type=int, default=1, help='accepted for compatibility: Griffin-Lim runs on the GPU')
+    a.add_argument('-odir', type=str, default='', help='Alternative place to put output samples')
+    a.add_argument('-t2m_epoch', default=-1, type=int, help='Default: use latest (-1)')
+    a.add_argument('-ssrn_epoch', default=-1, type=int, help='Default: use latest (-1)')
+    a.add_argument('-max_N', default=-1, type=int, help='Default: use max_N from config')
+    a.add_argument('-max_T', default=-1, type=int, help='Default: use max_T from config')
+    a.add_argument('-tr', default='', type=str, help='Default:use test_transcript from config')
+    opts = a.parse_args()
+    hp = load_config(opts.config)
+    if opts.max_N != -1:
+        hp.max_N = opts.max_N
+    if opts.max_T != -1:
+        hp.max_T = opts.max_T
+    if opts.tr != '':
+        hp.test_transcript = opts.tr
+    print("max_N=" + str(hp.max_N))
+    print("max_T=" + str(hp.max_T))
+    print("test_transcript=" + str(hp.test_transcript))
+    outdir = opts.odir
+    if outdir:
+        outdir = os.path.join(outdir, re.sub(r'\.[^\.]+\Z', '', os.path.split(opts.config)[1]))
+    synthesize(hp, speaker_id=opts.speaker, num_sentences=opts.num_sentences, ncores=opts.ncores, topoutdir=outdir,
+               t2m_epoch=opts.t2m_epoch, ssrn_epoch=opts.ssrn_epoch)
+
+
+if __name__ == "__main__":
+    main_work()

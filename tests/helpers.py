@@ -92,7 +92,7 @@ def make_corpus(root, n_utts=14, n_valid=3, max_N=24, max_T=40, seed=0, guides=T
         transcript=os.path.join(root, "transcript.csv"), test_transcript=os.path.join(root, "test_transcript.csv"),
         waveforms=os.path.join(root, "wav"), input_type='phones', vocab=vocab, max_N=max_N, max_T=max_T, multispeaker=[],
         n_utts=0, random_reduction_on_the_fly=True, prepro=True, vocoder='griffin_lim', sr=22050, n_fft=(full_dim - 1) * 2,
-        hop_length=275, win_length=1102, full_dim=full_dim, n_mels=n_mels, power=1.5, n_iter=50, preemphasis=.97, max_db=100, ref_db=20, r=r,
+        hop_length=275, win_length=(full_dim - 1) * 2, full_dim=full_dim, n_mels=n_mels, power=1.5, n_iter=50, preemphasis=.97, max_db=100, ref_db=20, r=r,
         dropout_rate=0.05, e=128, d=256, c=512, attention_win_size=3, g=0.2, norm='layer', lw_mel=0.3333, lw_bd1=0.3333,
         lw_att=0.3333, lw_mag=0.5, lw_bd2=0.5, validpatt='VAL050-', validation_sentences_to_evaluate=32,
         validation_sentences_to_synth_params=2, restart_from_savepath=[], lr=0.001, batchsize={'t2m': 4, 'ssrn': 4},

@@ -170,3 +170,17 @@ def test_validation_set_of_the_training_driver(tmp_path):
     names2, inputs2, reference2, _, _ = drv._validation_set(hp, 'ssrn')
     assert list(names2) == list(names)                               # seeded shuffle (train.py:111-115)
     assert inputs2.shape == (3, hp.max_T, hp.n_mels) and reference2[0].shape[1] == hp.full_dim
+
+
+def test_attention_diagnostics_known_answers():
+    """calculate_CDP_Ain_Aout.py: a one-to-one alignment has no coverage deviation and no dispersion; uniform attention
+    has maximal dispersion (1.0 after normalisation by log of the row length)."""
+    from ophelia_b200 import synthesize as syn
+    eye = np.eye(6)
+    assert syn.getCDP(eye) == 0.0 and syn.getAP(eye) == (0.0, 0.0)
+    uni = np.full((5, 8), 1.0 / 5)
+    apin, apout = syn.getAP(uni)
+    assert abs(apin - 1.0) < 1e-12 and abs(apout - 1.0) < 1e-12
+    assert abs(syn.getCDP(uni) - np.log(1.0 + (1.0 - 8.0 / 5) ** 2)) < 1e-12
+    padded = np.vstack([eye, np.zeros((3, 6))])                      # trailing symbols without attention are ignored
+    assert syn.getCDP(padded) == 0.0 and syn.getAP(padded) == (0.0, 0.0)

@@ -53,6 +53,17 @@ def test_text2mel_training_driver_end_to_end(tmp_path):
     L = load_data(hp, mode="synthesis")['texts']
     Y, lengths = syn.synth_text2mel(hp, L, g, sess)
     assert Y.shape == (len(L), hp.max_T, hp.n_mels) and np.isfinite(Y).all()
+    # the whole synthesis driver (synthesize.py:442-632): needs an SSRN checkpoint next to the Text2Mel one
+    hp.max_epochs = 0
+    drv.train(hp, 'ssrn')
+    outdir, bases, lengths2 = syn.synthesize(hp, num_sentences=2)
+    assert outdir.endswith("t2m7_ssrn0") and len(bases) == 2
+    from scipy.io import wavfile
+    for base, n in zip(bases, lengths2):
+        sr, pcm = wavfile.read(os.path.join(outdir, base + ".wav"))
+        assert sr == hp.sr and len(pcm) == hp.hop_length * (n * hp.r - 1) and np.abs(pcm).max() > 0
+        ali = np.load(os.path.join(outdir, base + "_alignment.npy"))
+        assert ali.shape[1] == n and np.allclose(ali.sum(0), 1.0, atol=1e-4)
 
 
 def test_ssrn_training_driver(tmp_path):
