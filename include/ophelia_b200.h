@@ -225,6 +225,40 @@ int oph_gemm_nt(const float* A, long long lda, const float* Bm, long long ldb, f
 int oph_gemm_tn(const float* A, long long lda, const float* Bm, long long ldb, float* C, long long ldc, int M,
                 int N, int R, int splits, oph_stream_t stream);
 
+/* ---- autoregressive frame step, incremental (synthesize.py:150-230) ---------------------------------------
+ * The reference recomputes AudioEnc + Attention + AudioDec over all max_T frames per generated frame and keeps row j.
+ * AudioEnc is causal and its input row t is final once frame t - 1 exists, so row j of a layer needs rows j, j - rate,
+ * j - 2 rate of the layer below only: every layer keeps its output history [B][T][ld] (item stride *_item floats) and
+ * conv_step / hc_step compute row j = *frame (device int, so one captured CUDA graph serves all frames) for all
+ * B <= 16 items.  fp32 FMA arithmetic, deterministic.
+ * w is the reference-layout kernel [k][Cin][Cout] (fp32, not packed).  gamma == NULL: no layer norm (hp.norm = None).
+ * scratch: device floats, at least oph_ar_scratch_floats().
+ *  conv_step: y[b][j] = act(LN(bias + sum_i W[i] x[b][j - in_shift - (k-1-i) rate]));  y_sig (nullable) = sigmoid(LN(..))
+ *  hc_step:   highway layer (modules.py:148-207) with [H1 | H2] = conv to 2C channels and the residual x[b][j]
+ *  window_gather / window_scatter: Attention cannot be cached -- the window mask of the latest prev_max_attentions
+ *             applies to every time row (networks.py:304-313), so R[t < j] changes when the window moves and AudioDec's
+ *             row j sees it through its causal reach.  oph_attention_fwd and the AudioDec layers are therefore run per
+ *             step over the W = reach + 1 rows [s, s + W), s = max(0, min(j - reach, T - W)): gather copies those rows
+ *             of the Q history into a static [B][W][ldw] buffer, scatter moves row j - s of the window results
+ *             (Yw [B][W][ldyw], align_w [B][N][W], argmax_w [B][W]) into frame j of Y [B][T][ldy], alignments
+ *             [B][N][T], prev [B] and history [T][B] (synthesize.py:204-209).
+ *  advance:   *frame += 1 */
+size_t oph_ar_scratch_floats(void);
+int oph_ar_conv_step(const float* x, long long x_item, long long ldx, const float* w, const float* bias,
+                     const float* gamma, const float* beta, float* y, long long y_item, long long ldy, float* y_sig,
+                     long long s_item, long long lds, float* scratch, int B, int Cin, int Cout, int k, int rate,
+                     int in_shift, int act, const int* frame, oph_stream_t stream);
+int oph_ar_hc_step(const float* x, long long x_item, long long ldx, const float* w, const float* bias, const float* g1,
+                   const float* b1, const float* g2, const float* b2, float* y, long long y_item, long long ldy,
+                   float* scratch, int B, int C, int k, int rate, const int* frame, oph_stream_t stream);
+int oph_ar_window_gather(const float* Q, long long q_item, long long ldq, float* Qw, long long w_item, long long ldw,
+                         int B, int d, int T, int W, int reach, const int* frame, oph_stream_t stream);
+int oph_ar_window_scatter(const float* Yw, long long yw_item, long long ldyw, float* Y, long long y_item, long long ldy,
+                          int n_mels, const float* align_w, float* align_t, const int32_t* argmax_w, int32_t* prev,
+                          int32_t* history, int B, int N, int T, int W, int reach, const int* frame,
+                          oph_stream_t stream);
+int oph_ar_advance(int32_t* frame, oph_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -60,6 +60,12 @@ SIGNATURES = {
     "oph_adam_prepare": (I, [P, P, F, F, F, I, F, P]),
     "oph_adam_clip": (I, [P, P, P, P, LL, P, F, F, F, F, F, P]),
     "oph_step_inc": (I, [P, P]),
+    "oph_ar_scratch_floats": (SZ, []),
+    "oph_ar_conv_step": (I, [P, LL, LL, P, P, P, P, P, LL, LL, P, LL, LL, P, I, I, I, I, I, I, I, P, P]),
+    "oph_ar_hc_step": (I, [P, LL, LL, P, P, P, P, P, P, P, LL, LL, P, I, I, I, I, P, P]),
+    "oph_ar_window_gather": (I, [P, LL, LL, P, LL, LL, I, I, I, I, I, P, P]),
+    "oph_ar_window_scatter": (I, [P, LL, LL, P, LL, LL, I, P, P, P, P, P, I, I, I, I, I, P, P]),
+    "oph_ar_advance": (I, [P, P]),
     "oph_gemm_nt": (I, [P, LL, P, LL, P, LL, P, I, I, I, I, F, I, LL, LL, LL, P]),
     "oph_gemm_tn": (I, [P, LL, P, LL, P, LL, I, I, I, I, P]),
 }

@@ -3,6 +3,7 @@
 #include "../../include/ophelia_b200.h"
 #include "rowwise.cuh"
 #include "gemm_tc.cuh"
+#include "arstep.cuh"
 
 #include <atomic>
 #include <cmath>
@@ -1028,6 +1029,73 @@ int oph_adam_clip(float* p, float* m, float* v, const float* g, long long n, con
 int oph_step_inc(long long* global_step, oph_stream_t stream) {
     launch_cfg(1, 1, 0, S(stream))(step_inc_kernel, global_step);
     return check_launch("step_inc_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------ incremental frame step
+#define OPH_AR_SCRATCH_FLOATS (32ll * AR_MAXB * 1024)
+size_t oph_ar_scratch_floats(void) { return (size_t)OPH_AR_SCRATCH_FLOATS; }
+
+// slices of the reduction over k * Cin: ~128 CTAs per layer, at most 256 and at least 16 products per slice
+static int ar_gemv(const float* x, long long x_item, long long ldx, const float* w, float* partial, int B, int Cin, int O,
+                   int k, int rate, int in_shift, const int* frame, int* KS_out, cudaStream_t st) {
+    if (B < 1 || B > AR_MAXB) return fail(OPH_EINVAL, "ar step: 1 <= B <= 16%s");
+    if (k < 1 || k > 3 || Cin < 1 || O < 1 || O > 2048) return fail(OPH_EINVAL, "ar step: unsupported layer shape%s");
+    const int K = k * Cin, tiles = cdiv(O, AR_COLS);
+    int KS = cdiv(128, tiles);
+    if (KS > cdiv(K, 16)) KS = cdiv(K, 16);
+    if (KS < cdiv(K, AR_KSLICE_MAX)) KS = cdiv(K, AR_KSLICE_MAX);
+    if (KS > 32) KS = 32;
+    int kslice = cdiv(cdiv(K, KS), 4) * 4;
+    if (kslice > AR_KSLICE_MAX) return fail(OPH_EINVAL, "ar step: k * Cin too large%s");
+    KS = cdiv(K, kslice);
+    if ((long long)KS * B * O > OPH_AR_SCRATCH_FLOATS) return fail(OPH_EINVAL, "ar step: scratch too small%s");
+    launch_cfg(dim3(tiles, KS), 256, 0, st)(ar_gemv_kernel, w, x, x_item, ldx, Cin, O, k, rate, in_shift, frame, B, partial, kslice);
+    *KS_out = KS;
+    return check_launch("ar_gemv_kernel");
+}
+
+int oph_ar_conv_step(const float* x, long long x_item, long long ldx, const float* w, const float* bias,
+                     const float* gamma, const float* beta, float* y, long long y_item, long long ldy, float* y_sig,
+                     long long s_item, long long lds, float* scratch, int B, int Cin, int Cout, int k, int rate,
+                     int in_shift, int act, const int* frame, oph_stream_t stream) {
+    int KS = 0;
+    OPH_TRY(ar_gemv(x, x_item, ldx, w, scratch, B, Cin, Cout, k, rate, in_shift, frame, &KS, S(stream)));
+    launch_cfg(B, 256, (size_t)Cout * sizeof(float), S(stream))(ar_tail_kernel, scratch, KS, bias, Cout, 0, gamma, beta,
+        (const float*)nullptr, (const float*)nullptr, act, (const float*)nullptr, 0ll, 0ll, y, y_item, ldy, y_sig, s_item, lds, frame, B);
+    return check_launch("ar_tail_kernel");
+}
+
+int oph_ar_hc_step(const float* x, long long x_item, long long ldx, const float* w, const float* bias, const float* g1,
+                   const float* b1, const float* g2, const float* b2, float* y, long long y_item, long long ldy,
+                   float* scratch, int B, int C, int k, int rate, const int* frame, oph_stream_t stream) {
+    int KS = 0;
+    if ((g1 == nullptr) != (g2 == nullptr)) return fail(OPH_EINVAL, "ar_hc_step: H1 and H2 are normalised together%s");
+    OPH_TRY(ar_gemv(x, x_item, ldx, w, scratch, B, C, 2 * C, k, rate, 0, frame, &KS, S(stream)));
+    launch_cfg(B, 256, (size_t)2 * C * sizeof(float), S(stream))(ar_tail_kernel, scratch, KS, bias, 2 * C, 1, g1, b1, g2, b2, 0,
+        x, x_item, ldx, y, y_item, ldy, (float*)nullptr, 0ll, 0ll, frame, B);
+    return check_launch("ar_tail_kernel");
+}
+
+int oph_ar_window_gather(const float* Q, long long q_item, long long ldq, float* Qw, long long w_item, long long ldw,
+                         int B, int d, int T, int W, int reach, const int* frame, oph_stream_t stream) {
+    if (B < 1 || W < 1 || W > T || reach < 0) return fail(OPH_EINVAL, "ar_window_gather: need 1 <= W <= T%s");
+    launch_cfg(dim3(W, B), 128, 0, S(stream))(ar_window_gather_kernel, Q, q_item, ldq, Qw, w_item, ldw, d, T, W, reach, frame);
+    return check_launch("ar_window_gather_kernel");
+}
+
+int oph_ar_window_scatter(const float* Yw, long long yw_item, long long ldyw, float* Y, long long y_item, long long ldy,
+                          int n_mels, const float* align_w, float* align_t, const int32_t* argmax_w, int32_t* prev,
+                          int32_t* history, int B, int N, int T, int W, int reach, const int* frame,
+                          oph_stream_t stream) {
+    if (B < 1 || W < 1 || W > T || reach < 0) return fail(OPH_EINVAL, "ar_window_scatter: need 1 <= W <= T%s");
+    launch_cfg(B, 256, 0, S(stream))(ar_window_scatter_kernel, Yw, yw_item, ldyw, Y, y_item, ldy, n_mels, align_w, align_t,
+                                     argmax_w, prev, history, B, N, T, W, reach, frame);
+    return check_launch("ar_window_scatter_kernel");
+}
+
+int oph_ar_advance(int32_t* frame, oph_stream_t stream) {
+    launch_cfg(1, 1, 0, S(stream))(ar_advance_kernel, frame);
+    return check_launch("ar_advance_kernel");
 }
 
 // ------------------------------------------------------------------------------------------------ raw GEMM (tests)

@@ -157,6 +157,163 @@ def synth_codedtext2mel_device(hp, K, V, ends, g, use_cuda_graph=True, check_eve
     return (Y.cpu().numpy(), t_ends.tolist(), alignments.cpu().numpy())
 
 
+def _frame_step_layers(hp):
+    """(scope, kind, k, rate, act) of the causal stacks in creation order (networks.py:214-284, 360-435)."""
+    enc = [("C_1", "conv", 1, 1, 1), ("C_2", "conv", 1, 1, 1), ("C_3", "conv", 1, 1, 0)]
+    enc += [("HC_%d" % (4 + i), "hc", 3, 3 ** (i % 4), 0) for i in range(8)]
+    enc += [("HC_12", "hc", 3, 3, 0), ("HC_13", "hc", 3, 3, 0)]
+    dec = [("C_1", "conv", 1, 1, 0)]
+    dec += [("HC_%d" % (2 + i), "hc", 3, 3 ** i, 0) for i in range(4)]
+    dec += [("HC_6", "hc", 3, 1, 0), ("HC_7", "hc", 3, 1, 0)]
+    dec += [("C_8", "conv", 1, 1, 1), ("C_9", "conv", 1, 1, 1), ("C_10", "conv", 1, 1, 1), ("C_11", "conv", 1, 1, 0)]
+    return enc, dec
+
+
+def decoder_reach(hp):
+    """Causal reach of AudioDec in frames: sum over its layers of (k - 1) * rate = 84 (networks.py:360-435)."""
+    return sum((k - 1) * rate for _scope, _kind, k, rate, _act in _frame_step_layers(hp)[1])
+
+
+def _window_hp(hp, W):
+    """networks.Attention asserts T == hp.max_T in synthesis mode (the reference tiles its mask over hp.max_T rows):
+    the windowed pass over W rows gets a copy of hp that says so."""
+    import copy
+    hp_w = copy.copy(hp)
+    hp_w.max_T = W
+    return hp_w
+
+
+def synth_codedtext2mel_incremental(hp, K, V, ends, g, use_cuda_graph=True, check_every=8):
+    """The same loop with the per-frame work cut to what can change (csrc/arstep.cuh; SURVEY 7, hard part 5):
+
+    * AudioEnc is causal and its input row t is final once frame t - 1 exists: every layer keeps its output history and
+      a frame step computes row j only (fp32 FMA kernels that stream the fp32 weights once per step);
+    * Attention cannot be cached -- the window mask of the latest prev_max_attentions is applied to every time row
+      (networks.py:304-313), so the context rows R[t < j] change whenever the window moves, and AudioDec's row j sees them
+      through its 84-frame causal reach.  Attention and AudioDec therefore run per step with the batch (tcgen05) kernels,
+      but over the rows [max(0, j - 84), j] only.
+
+    One captured CUDA graph is replayed per frame (the frame index lives on the device).  Results equal the full
+    re-computation up to fp32 rounding (tests/test_incremental_algorithm.py pins the algorithm against the oracle loop);
+    K, V, ends and the return value are those of `synth_codedtext2mel`."""
+    from . import _lib, ops
+    from .networks import Attention, AudioDec
+    from .variables import use_store, variable_scope
+    assert not hp.multispeaker and not hp.use_external_durations and not hp.merlin_label_dir
+    assert not getattr(hp, "turn_off_monotonic_for_synthesis", False), "windowless attention: use synth_codedtext2mel_device"
+    dev, st = g.device, g.store
+    K = g._to_device(K, torch.float32).contiguous()
+    V = g._to_device(V, torch.float32).contiguous()
+    B, N, d = K.shape
+    T, nm = hp.max_T, hp.n_mels
+    assert N == hp.max_N, "networks.py:304-311 builds the mask with hp.max_N"
+    assert B <= 16, "the frame-step kernels handle up to 16 sentences per call"
+    assert hp.norm in ('layer', None)
+    norm = hp.norm == 'layer'
+    reach = decoder_reach(hp)
+    W = min(T, reach + 1)
+    hp_w = _window_hp(hp, W)
+    enc_layers = _frame_step_layers(hp)[0]
+    cache = g.__dict__.setdefault("_ar_inc_state", {})
+    key = (B, N, d, T, bool(use_cuda_graph), st.flat.data_ptr())
+    state = cache.get(key)
+    if state is not None and state["version"] != st.version:    # the windowed decoder reads packed weight images
+        state = None
+    if state is None:
+        z = lambda *shape, dt=torch.float32: torch.zeros(*shape, device=dev, dtype=dt)
+        state = {"K": z(B, N, d), "V": z(B, N, d), "Y": z(B, T, nm), "ali": z(B, N, T), "prev": z(B, dt=torch.int32),
+                 "hist": z(T, B, dt=torch.int32), "frame": z(1, dt=torch.int32), "Qw": z(B, W, d),
+                 "scratch": z(int(_lib.load().oph_ar_scratch_floats())), "enc": [z(B, T, d) for _ in enc_layers],
+                 "graph": None, "version": st.version}
+        for n in ("K", "V"):
+            state[n]._oph_planes = ops.split_planes(state[n])
+        cache[key] = state
+    Kb, Vb, Y, ali, prev, hist, frame, Qw = (state[n] for n in ("K", "V", "Y", "ali", "prev", "hist", "frame", "Qw"))
+
+    def var(name):
+        return st.vars.get("Text2Mel/AudioEnc/" + name)
+
+    def enc_layer(spec, x, y, in_shift):
+        scope, kind, k, rate, act = spec
+        w, bias = var(scope + "/conv1d/kernel"), var(scope + "/conv1d/bias")
+        stream = torch.cuda.current_stream().cuda_stream
+        if kind == "hc":
+            C = x.shape[2]
+            assert tuple(w.shape) == (k, C, 2 * C) and y.shape[2] == C
+            g1, b1, g2, b2 = (var(scope + n) if norm else None for n in ("/H1/gamma", "/H1/beta", "/H2/gamma", "/H2/beta"))
+            _lib.call("oph_ar_hc_step", x.data_ptr(), x.stride(0), x.stride(1), w.data_ptr(), bias.data_ptr(),
+                      ops._p(g1), ops._p(b1), ops._p(g2), ops._p(b2), y.data_ptr(), y.stride(0), y.stride(1),
+                      state["scratch"].data_ptr(), B, C, k, rate, frame.data_ptr(), stream)
+        else:
+            cin, cout = x.shape[2], y.shape[2]
+            assert tuple(w.shape) == (k, cin, cout)
+            gamma, beta = (var(scope + n) if norm else None for n in ("/normalize/gamma", "/normalize/beta"))
+            _lib.call("oph_ar_conv_step", x.data_ptr(), x.stride(0), x.stride(1), w.data_ptr(), bias.data_ptr(),
+                      ops._p(gamma), ops._p(beta), y.data_ptr(), y.stride(0), y.stride(1), None, 0, 0,
+                      state["scratch"].data_ptr(), B, cin, cout, k, rate, in_shift, act, frame.data_ptr(), stream)
+
+    def step():
+        x = Y                                              # S = mels delayed by one frame (architectures.py:191)
+        for i, spec in enumerate(enc_layers):
+            enc_layer(spec, x, state["enc"][i], 1 if i == 0 else 0)
+            x = state["enc"][i]
+        stream = torch.cuda.current_stream().cuda_stream
+        _lib.call("oph_ar_window_gather", x.data_ptr(), x.stride(0), x.stride(1), Qw.data_ptr(), Qw.stride(0), Qw.stride(1),
+                  B, d, T, W, reach, frame.data_ptr(), stream)
+        with use_store(st), variable_scope("Text2Mel"):
+            with variable_scope("Attention"):
+                Rw, ali_w, max_w = Attention(hp_w, Qw, Kb, Vb, monotonic_attention=True, prev_max_attentions=prev,
+                                             training=False, want_alignments=True)
+            with variable_scope("AudioDec"):
+                _logits_w, Yw = AudioDec(hp, Rw, training=False, speaker_codes=None, reuse=g.reuse)
+        assert ali_w.is_contiguous() and max_w.is_contiguous() and max_w.dtype == torch.int32
+        _lib.call("oph_ar_window_scatter", Yw.data_ptr(), Yw.stride(0), Yw.stride(1), Y.data_ptr(), Y.stride(0), Y.stride(1),
+                  nm, ali_w.data_ptr(), ali.data_ptr(), max_w.data_ptr(), prev.data_ptr(), hist.data_ptr(), B, N, T, W,
+                  reach, frame.data_ptr(), stream)
+        _lib.call("oph_ar_advance", frame.data_ptr(), stream)
+
+    def reset():
+        Kb.copy_(K)
+        Vb.copy_(V)
+        ops.split_planes(Kb, into=Kb._oph_planes)
+        ops.split_planes(Vb, into=Vb._oph_planes)
+        for t in (Y, ali, prev, hist, frame, state["enc"][-1]):
+            t.zero_()
+    graph = state["graph"]
+    if use_cuda_graph and graph is None:
+        reset()
+        step()                                             # warm-up outside the capture (lazy weight packing)
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        with ops.capture(graph):
+            step()
+        state["graph"] = graph
+    reset()
+    ends = np.asarray(ends)
+    endcounts = np.zeros(ends.shape, dtype=int)
+    t_ends = np.ones(ends.shape, dtype=int) * T
+    checked, stop_at = 0, None
+    for j in range(T):
+        if graph is not None:
+            graph.replay()
+        else:
+            step()
+        if (j + 1) % max(1, check_every) == 0 or j == T - 1:
+            host = hist[checked:j + 1].cpu().numpy().astype(np.int64)
+            for jj in range(checked, j + 1):
+                if _update_ends(hp, host[jj - checked], ends, endcounts, t_ends, jj):
+                    stop_at = jj
+                    break
+            checked = j + 1
+            if stop_at is not None:
+                break
+    Yh, ah = Y.cpu().numpy(), ali.cpu().numpy()
+    if stop_at is not None and stop_at + 1 < T:           # the reference never computed these frames
+        Yh[:, stop_at + 1:, :] = 0
+        ah[:, :, stop_at + 1:] = 0
+    return (Yh, t_ends.tolist(), ah)
+
+
 def synth_mel2mag(hp, Y, g, sess, batchsize=128):
     """SSRN over the padded mel batch in chunks of <= batchsize utterances (synthesize.py:250-260)."""
     if batchsize > 0:

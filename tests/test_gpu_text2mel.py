@@ -162,6 +162,10 @@ def test_autoregressive_loop_matches_oracle():
     assert maxabs(a1, ar) < 1e-4 and maxabs(a2, ar) < 1e-4
     Y3, t3 = syn.synth_text2mel(hp, b["L"], g, sess)
     assert t3 == tr and maxabs(Y3, Yr) < 1e-3
+    # incremental route: cached AudioEnc rows (fp32 frame-step kernels), Attention / AudioDec over the decoder's reach
+    for kw in (dict(use_cuda_graph=True), dict(use_cuda_graph=False, check_every=1)):
+        Y5, t5, a5 = syn.synth_codedtext2mel_incremental(hp, K, V, ends, g, **kw)
+        assert t5 == tr and maxabs(Y5, Yr) < 1e-3 and maxabs(a5, ar) < 1e-4
     # early stop (synthesize.py:225-228): with the sentence ends at position 1 every sentence ends within a few frames;
     # the device route checks only every 4th frame and must clear the frames it computed past the stopping frame
     ends1 = np.ones_like(ends)
@@ -171,6 +175,31 @@ def test_autoregressive_loop_matches_oracle():
         Y4, t4, a4 = syn.synth_codedtext2mel_device(hp, K, V, ends1, g, **kw)
         assert t4 == tr and maxabs(Y4, Yr) < 1e-3 and maxabs(a4, ar) < 1e-4
         assert (Y4[:, max(tr) + 1:] == 0).all() and (a4[:, :, max(tr) + 1:] == 0).all()
+        Y6, t6, a6 = syn.synth_codedtext2mel_incremental(hp, K, V, ends1, g, **kw)
+        assert t6 == tr and maxabs(Y6, Yr) < 1e-3 and maxabs(a6, ar) < 1e-4
+        assert (Y6[:, max(tr) + 1:] == 0).all() and (a6[:, :, max(tr) + 1:] == 0).all()
+
+
+def test_incremental_route_beyond_the_decoder_reach():
+    """max_T = 120 > 85: the Attention / AudioDec window slides (rows [j - 84, j]) and the widest AudioEnc dilation
+    (2 * 27 frames back) reads real history.  The numpy oracle's O(T^2) loop is too slow here, so the reference is the
+    full re-computation route on the GPU, itself pinned to the oracle above; the two routes differ only by rounding
+    (fp32 FMA vs split-bf16 AudioEnc).  Replaying the cached graph is bit-reproducible."""
+    from ophelia_b200 import synthesize as syn
+    hp = make_hp(max_N=30, max_T=120)
+    P = oracle_params(hp, "t2m", seed=6)
+    b = synthetic_batch(hp, 2, 30, 120, text_len=24)
+    g = _graph(hp, "synthesize", P)
+    enc = g.encode_text({"L": b["L"]})
+    K, V = enc["K"].cpu().numpy(), enc["V"].cpu().numpy()
+    ends = np.array([hp.max_N + 1] * 2)                              # never reached: all 120 frames are generated
+    Yf, tf_, af = syn.synth_codedtext2mel_device(hp, K, V, ends, g)
+    Yi, ti, ai = syn.synth_codedtext2mel_incremental(hp, K, V, ends, g)
+    assert ti == tf_ == [120, 120] and maxabs(Yi, Yf) < 1e-3 and maxabs(ai, af) < 1e-4
+    assert np.abs(Yf[:, 100:]).max() > 0
+    assert len(set(af[0].argmax(0).tolist())) > 2                     # the attention window moved during the run
+    Y2, t2, a2 = syn.synth_codedtext2mel_incremental(hp, K, V, ends, g)
+    assert t2 == ti and np.array_equal(Y2, Yi) and np.array_equal(a2, ai)
 
 
 def test_side_streams_and_cuda_graph_match_single_stream():
