@@ -314,6 +314,15 @@ def synth_codedtext2mel_incremental(hp, K, V, ends, g, use_cuda_graph=True, chec
     return (Yh, t_ends.tolist(), ah)
 
 
+def synth_codedtext2mel_fast(hp, K, V, ends, g):
+    """The fastest device route that applies: incremental for up to 16 sentences with the attention window on, else the
+    CUDA-graph replay of the full re-computation.  Same results (up to fp32 rounding) and return value as
+    `synth_codedtext2mel`."""
+    if len(K) <= 16 and not getattr(hp, "turn_off_monotonic_for_synthesis", False):
+        return synth_codedtext2mel_incremental(hp, K, V, ends, g)
+    return synth_codedtext2mel_device(hp, K, V, ends, g)
+
+
 def synth_mel2mag(hp, Y, g, sess, batchsize=128):
     """SSRN over the padded mel batch in chunks of <= batchsize utterances (synthesize.py:250-260)."""
     if batchsize > 0:
@@ -457,7 +466,7 @@ def synthesize(hp, speaker_id='', num_sentences=0, ncores=1, topoutdir='', t2m_e
         t0 = time.time()
         text_lengths = get_text_lengths(L)
         K, V = encode_text(hp, L, g1, sess)
-        Y, lengths, alignments = synth_codedtext2mel_device(hp, K, V, text_lengths, g1)
+        Y, lengths, alignments = synth_codedtext2mel_fast(hp, K, V, text_lengths, g1)
         print('Text2Mel generating... %.2f seconds' % (time.time() - t0))
         t0 = time.time()
         Z = synth_mel2mag(hp, Y, g2, sess)

@@ -55,7 +55,7 @@ def compute_validation(hp, model_type, epoch, inputs, synth_graph, sess, speaker
     from .objective_measures import compute_dtw_error, compute_simple_LSD
     if model_type == 't2m':
         K, V = syn.encode_text(hp, inputs, synth_graph, sess)
-        pred, lengths, _ = syn.synth_codedtext2mel_device(hp, K, V, syn.get_text_lengths(inputs), synth_graph)
+        pred, lengths, _ = syn.synth_codedtext2mel_fast(hp, K, V, syn.get_text_lengths(inputs), synth_graph)
         predictions = syn.split_batch(pred, lengths)
         score = compute_dtw_error(validation_set_reference, predictions)
     elif model_type == 'ssrn':
