@@ -109,7 +109,7 @@ typedef struct {
  * architectures.py:57-58, 258-280; data_load.py:454-464): w[b][n][t] over the batch-padded [Ng][Tg] block (row stride ld,
  * item stride item_stride, both in floats), `pad` outside that block (1.0 for the guided-attention loss, the value the
  * reference pads the guides with at architectures.py:263; 0.0 for the MSE variant, :275).  mse != 0 selects
- * sum (A - W)^2 (hp.attention_guide_fa) instead of sum |A * W|. */
+ * sum (A - W)^2 (hp.attention_guide_fa) instead of sum |A * W|.  w == NULL keeps the analytic global guide. */
 typedef struct {
     const float* w;
     long long item_stride;
@@ -118,6 +118,10 @@ typedef struct {
     int Tg;
     float pad;
     int mse;
+    /* gradient inputs of the CDP / Ain / Aout terms (nullable, backward only; written by oph_attention_extra_fwd) */
+    const float* col_g;
+    const float* col_h;
+    float c_aout;
 } oph_guide;
 
 /* ---- modules.conv1d (modules.py:91-146), hot-path uses are k=1 -------------------------------------------
@@ -195,6 +199,18 @@ int oph_attention_bwd(const oph_act* dR, const oph_act* Q, const oph_act* K, con
                       const oph_act* dA, float* dQ, long long lddq, const float* dq_addend, long long ldqa, float* dK,
                       long long lddk, float* dV, long long lddv, float att_coef, int maxN, int maxT, float g, int B,
                       int T, int N, int d, const oph_guide* guide, oph_stream_t stream);
+/* "Confidence through attention" losses (hp.lw_cdp / lw_ain / lw_aout, architectures.py:283-321) over the alignments
+ * A [B][T][ldA] of a training batch: coverage deviation penalty and the two attention entropies.
+ * extra_fwd: acc3 (device double[3], zeroed by the caller) += (sum log(1 + (1 - s)^2), sum_t P log P summed over keys,
+ *   sum A log A);  col_g / col_h [B][N] receive the per-key factors of the gradient for oph_attention_bwd
+ *   (oph_guide.col_g / col_h), with c_cdp = lw_cdp / (B N), c_ain = -lw_ain / (B N log T); oph_guide.c_aout =
+ *   -lw_aout / (B T log N).
+ * extra_finalize: comps8[5..7] = CDP, Ain, Aout; add_to_total != 0 adds the weighted terms to comps8[0] (the legacy lw_*
+ *   pattern of architectures.py:333-349; the loss_weights dict pattern reports them without adding them). */
+int oph_attention_extra_fwd(const float* A, long long ldA, int B, int T, int N, float c_cdp, float c_ain, float* col_g,
+                            float* col_h, double* acc3, oph_stream_t stream);
+int oph_attention_extra_finalize(const double* acc3, float* comps8, int B, int T, int N, float w_cdp, float w_ain,
+                                 float w_aout, int add_to_total, oph_stream_t stream);
 /* fp32 rows -> split-bf16 planes for operands that do not come out of a row-wise kernel of this library. */
 int oph_split_planes(const float* x, long long ldx, long long rows, int C, unsigned short* hi, unsigned short* lo,
                      long long ldp, oph_stream_t stream);

@@ -21,7 +21,8 @@ AP = ctypes.POINTER(Act)
 
 class Guide(ctypes.Structure):
     """`oph_guide`: per-utterance attention targets of the batch (include/ophelia_b200.h)."""
-    _fields_ = [("w", P), ("item_stride", LL), ("ld", LL), ("Ng", I), ("Tg", I), ("pad", F), ("mse", I)]
+    _fields_ = [("w", P), ("item_stride", LL), ("ld", LL), ("Ng", I), ("Tg", I), ("pad", F), ("mse", I),
+                ("col_g", P), ("col_h", P), ("c_aout", F)]
 
 
 GP = ctypes.POINTER(Guide)
@@ -54,6 +55,8 @@ SIGNATURES = {
     "oph_embed_bwd": (I, [P, P, LL, P, I, I, P]),
     "oph_attention_fwd": (I, [AP, AP, AP, AP, AP, P, P, P, I, P, I, I, F, I, I, I, I, GP, P]),
     "oph_attention_bwd": (I, [AP, AP, AP, AP, AP, AP, P, LL, P, LL, P, LL, P, LL, F, I, I, F, I, I, I, I, GP, P]),
+    "oph_attention_extra_fwd": (I, [P, LL, I, I, I, F, F, P, P, P, P]),
+    "oph_attention_extra_finalize": (I, [P, P, I, I, I, F, F, F, I, P]),
     "oph_split_planes": (I, [P, LL, LL, I, P, P, LL, P]),
     "oph_recon_loss": (I, [P, LL, P, LL, P, LL, LL, I, I, F, F, F, P, P]),
     "oph_loss_finalize": (I, [P, P, D, D, F, F, F, F, I, I, P]),

@@ -362,7 +362,7 @@ class Text2MelGraph(Graph):
 
     # architectures.py:188-239
     def build_model(self, L, mels, training, K=None, V=None, prev_max_attentions=None, att_acc=None,
-                    want_alignments=True, tapes=None, text_stream=None, gts=None):
+                    want_alignments=True, tapes=None, text_stream=None, gts=None, extra=None):
         hp = self.hp
         mono = self.mode == 'synthesize'
         out = {}
@@ -387,7 +387,7 @@ class Text2MelGraph(Graph):
             with variable_scope("Attention"), on(t_dec):
                 R, alignments, max_attentions = Attention(
                     hp, Q, K, V, monotonic_attention=mono, prev_max_attentions=prev_max_attentions if mono else None,
-                    training=training, att_acc=att_acc, want_alignments=want_alignments, gts=gts)
+                    training=training, att_acc=att_acc, want_alignments=want_alignments, gts=gts, extra=extra)
             with variable_scope("AudioDec"), on(t_dec):
                 Y_logits, Y = AudioDec(hp, R, training=training, speaker_codes=None, reuse=self.reuse)
         out.update(K=K, V=V, Q=Q, R=R, alignments=alignments, max_attentions=max_attentions, Y_logits=Y_logits, Y=Y)
@@ -434,14 +434,21 @@ class Text2MelGraph(Graph):
         assert (gts is not None) == bool(hp.attention_guide_dir), \
             "hp.attention_guide_dir set <=> batches carry 'attention_guide' (architectures.py:57-60)"
         assert not hp.attention_guide_fa or gts is not None, "the MSE attention loss needs targets from hp.attention_guide_dir"
-        assert hp.lw_cdp == 0.0 and hp.lw_ain == 0.0 and hp.lw_aout == 0.0
         mels._oph_no_grad = True
         st.grad_flat.zero_()
         acc = torch.zeros(4, dtype=torch.float64, device=self.device)
+        # CDP / Ain / Aout (architectures.py:283-321): reported whenever one weight is non-zero, part of the total loss (and
+        # of the gradient) only under the legacy lw_* pattern (:333-349)
+        extra = None
+        if hp.lw_cdp != 0.0 or hp.lw_ain != 0.0 or hp.lw_aout != 0.0:
+            lw = getattr(hp, "loss_weights", None)
+            in_total = not (lw and "t2m" in lw)
+            extra = {"acc": torch.zeros(3, dtype=torch.float64, device=self.device), "in_total": in_total,
+                     "lw": (hp.lw_cdp, hp.lw_ain, hp.lw_aout) if in_total else (0.0, 0.0, 0.0)}
         tapes = (Tape(), Tape(), Tape())
         side = self._streams()
         out = self.build_model(L, mels, True, att_acc=acc[3:], want_alignments=False, tapes=tapes,
-                               text_stream=side[0] if side else None, gts=gts)
+                               text_stream=side[0] if side else None, gts=gts, extra=extra)
         w1, wbd, watt, w2 = _loss_weights(hp, "t2m")
         squash = hp.squash_output_t2m
         logits = out["Y_logits"]
@@ -449,8 +456,10 @@ class Text2MelGraph(Graph):
         N = L.shape[1]
         n_att = float(B * min(N, hp.max_N) * min(T, hp.max_T))        # mask_sum of architectures.py:266-268
         dlogits = ops.recon_loss(logits, mels, acc, squash, w1, wbd if squash else 0.0, w2)
-        comps = torch.empty(5, device=self.device, dtype=torch.float32)
+        comps = torch.empty(8 if extra else 5, device=self.device, dtype=torch.float32)
         ops.loss_finalize(acc, comps, B * T * nm, n_att, w1, wbd, watt, w2, True, squash)
+        if extra:       # loss_components = [loss, L1, BD, att, L2, CDP, Ain, Aout] (architectures.py:352-353)
+            ops.attention_extra_finalize(extra["acc"], comps, B, T, N, hp.lw_cdp, hp.lw_ain, hp.lw_aout, extra["in_total"])
         # backward: AudioDec -> Attention -> (AudioEnc, TextEnc)
         t_text, t_aenc, t_dec = tapes
         if side is None:

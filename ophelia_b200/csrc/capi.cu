@@ -894,15 +894,20 @@ int oph_split_planes(const float* x, long long ldx, long long rows, int C, unsig
 }
 
 static int guide_tensor(GuideTensor& G, const oph_guide* guide, int N, int T) {
-    G = GuideTensor{nullptr, 0, 0, 0, 0, 1.f, 0};
-    if (!guide || !guide->w) return OPH_OK;
+    G = GuideTensor{nullptr, 0, 0, 0, 0, 1.f, 0, nullptr, nullptr, 0.f};
+    if (!guide) return OPH_OK;
+    if ((guide->col_g == nullptr) != (guide->col_h == nullptr))
+        return fail(OPH_EINVAL, "attention: col_g and col_h come together (oph_attention_extra_fwd)%s");
+    G.col_g = guide->col_g; G.col_h = guide->col_h; G.c_aout = guide->c_aout;
+    if (!guide->w) return OPH_OK;
     if (guide->Ng < 1 || guide->Tg < 1 || guide->ld < guide->Tg || guide->item_stride < (long long)guide->Ng * guide->ld)
         return fail(OPH_EINVAL, "attention: malformed guide tensor (Ng, Tg >= 1, ld >= Tg, item_stride >= Ng * ld)%s");
     // the MSE variant pads alignments and targets with zeros, so target mass outside the batch's [N, T] block would add a
     // constant the kernels do not see (architectures.py:271-280): forced-alignment targets must fit the batch
     if (guide->mse && (guide->Ng > N || guide->Tg > T))
         return fail(OPH_EINVAL, "attention: forced-alignment targets larger than the batch's [N, T] block%s");
-    G = GuideTensor{guide->w, guide->item_stride, guide->ld, guide->Ng, guide->Tg, guide->pad, guide->mse ? 1 : 0};
+    G.w = guide->w; G.item_stride = guide->item_stride; G.ld = guide->ld; G.Ng = guide->Ng; G.Tg = guide->Tg;
+    G.pad = guide->pad; G.mse = guide->mse ? 1 : 0;
     return OPH_OK;
 }
 
@@ -942,6 +947,21 @@ int oph_attention_fwd(const oph_act* Q, const oph_act* K, const oph_act* V, cons
         OPH_TRY(launch_gemm(g, B, S(stream)));
     }
     return OPH_OK;
+}
+
+int oph_attention_extra_fwd(const float* A, long long ldA, int B, int T, int N, float c_cdp, float c_ain, float* col_g,
+                            float* col_h, double* acc3, oph_stream_t stream) {
+    if (!A || !col_g || !col_h || !acc3 || B < 1 || T < 1 || N < 1) return fail(OPH_EINVAL, "attention_extra_fwd: missing operand%s");
+    launch_cfg(dim3(cdiv(N, 32), B), 256, 0, S(stream))(att_extra_kernel, A, ldA, B, T, N, c_cdp, c_ain, col_g, col_h, acc3);
+    return check_launch("att_extra_kernel");
+}
+
+int oph_attention_extra_finalize(const double* acc3, float* comps8, int B, int T, int N, float w_cdp, float w_ain,
+                                 float w_aout, int add_to_total, oph_stream_t stream) {
+    if (T < 2 || N < 2) return fail(OPH_EINVAL, "attention_extra_finalize: the entropies are normalised by log T and log N%s");
+    launch_cfg(1, 1, 0, S(stream))(att_extra_finalize_kernel, acc3, comps8, (double)B * N, (double)B * T, log((double)T),
+                                   log((double)N), w_cdp, w_ain, w_aout, add_to_total);
+    return check_launch("att_extra_finalize_kernel");
 }
 
 int oph_attention_bwd(const oph_act* dR, const oph_act* Q, const oph_act* K, const oph_act* V, const oph_act* A,

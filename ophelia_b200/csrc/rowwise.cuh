@@ -272,6 +272,8 @@ __device__ __forceinline__ float guide_w(int n, int t, float inv_maxN, float inv
 // batch-padded [Ng, Tg] block, `pad` outside it (1.0 for the guided loss, 0.0 for the MSE variant; :263, :275).
 struct GuideTensor {
     const float* w; long long item_stride; long long ld; int Ng, Tg; float pad; int mse;
+    // gradient of the CDP / Ain / Aout terms (architectures.py:283-321):  dA[b][t][n] += col_g[b][n] + (col_h[b][n] + c_aout) * log A + c_aout
+    const float* col_g; const float* col_h; float c_aout;
 };
 __device__ __forceinline__ float guide_t(const GuideTensor& G, int b, int n, int t) {
     return (n < G.Ng && t < G.Tg) ? __ldg(G.w + (long long)b * G.item_stride + (long long)n * G.ld + t) : G.pad;
@@ -367,6 +369,11 @@ __global__ void softmax_bwd_kernel(const float* __restrict__ A, long long ldA, f
                     d += att_coef * (G.mse ? 2.f * (ar[n] - w) : w);
                 }
             }
+            if (G.col_g) {
+                const float a = ar[n];
+                if (a > 0.f) d += G.col_g[(long long)b * N + n] + (G.col_h[(long long)b * N + n] + G.c_aout) * __logf(a) + G.c_aout;
+                else d += G.col_g[(long long)b * N + n];
+            }
             dr[n] = d;
             dot += ar[n] * d;
         }
@@ -376,6 +383,69 @@ __global__ void softmax_bwd_kernel(const float* __restrict__ A, long long ldA, f
             dr[n] = ds;
             if (ds_hi) st_split1(ds_hi, ds_lo, row * ldp + n, ds);
         }
+    }
+}
+
+// "Confidence through attention" terms (architectures.py:283-321) over the alignments of the batch, A[b][t][n]:
+//   s[b][n] = sum_t A,  e[b][n] = sum_t A log A  (0 log 0 = 0)
+//   CDP  = sum_{b,n} log(1 + (1 - s)^2) / (B N)
+//   Ain  = - sum_{b,n} sum_t P log P / (B N log T),  P = A / s  ->  sum_t P log P = e / s - log s
+//   Aout = - sum_{b,t} sum_n A log A / (B T log N)   (rows of A already sum to one)  = - sum_{b,n} e / (B T log N)
+// One block per (b, 32 keys): lanes along n (coalesced), 8 warps stride over t.  Adds the three sums to acc3 and stores
+// the per-key factors of the gradient, d/dA[b][t][n] = col_g + col_h log A (+ the Aout part, which needs no statistics):
+//   col_g = c_cdp * (-2 (1 - s) / (1 + (1 - s)^2)) - c_ain * e / s^2,   col_h = c_ain / s      (zero where s == 0)
+__global__ void att_extra_kernel(const float* __restrict__ A, long long ldA, int B, int T, int N, float c_cdp, float c_ain,
+                                 float* __restrict__ col_g, float* __restrict__ col_h, double* __restrict__ acc3) {
+    pdl_grid_sync();
+    __shared__ float ss[8][32], se[8][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.y, n = blockIdx.x * 32 + lane;
+    float s = 0.f, e = 0.f;
+    if (n < N) {
+        const float* ap = A + (long long)b * T * ldA + n;
+        for (int t = warp; t < T; t += 8) {
+            const float a = ap[(long long)t * ldA];
+            s += a;
+            if (a > 0.f) e += a * __logf(a);
+        }
+    }
+    ss[warp][lane] = s; se[warp][lane] = e;
+    __syncthreads();
+    if (warp == 0) {
+        for (int w = 1; w < 8; ++w) { s += ss[w][lane]; e += se[w][lane]; }
+        float cdp = 0.f, ain = 0.f, aout = 0.f;
+        if (n < N) {
+            const float r = 1.f - s;
+            cdp = __logf(1.f + r * r);
+            float g = c_cdp * (-2.f * r / (1.f + r * r)), h = 0.f;
+            if (s > 0.f) {
+                ain = e / s - __logf(s);
+                g -= c_ain * e / (s * s);
+                h = c_ain / s;
+            }
+            aout = e;
+            col_g[(long long)b * N + n] = g;
+            col_h[(long long)b * N + n] = h;
+        }
+        cdp = warp_sum(cdp); ain = warp_sum(ain); aout = warp_sum(aout);
+        if (lane == 0) { atomicAdd(acc3, (double)cdp); atomicAdd(acc3 + 1, (double)ain); atomicAdd(acc3 + 2, (double)aout); }
+    }
+}
+
+// loss_components[5..7] = CDP, Ain, Aout; the weighted terms join the total only under the legacy lw_* pattern
+// (architectures.py:333-349: the loss_weights dict branch does not add them)
+__global__ void att_extra_finalize_kernel(const double* __restrict__ acc3, float* __restrict__ comps, double n_keys,
+                                          double n_frames, double logT, double logN, float w_cdp, float w_ain, float w_aout,
+                                          int add_to_total) {
+    pdl_grid_sync();
+    const double cdp = acc3[0] / n_keys, ain = -acc3[1] / n_keys / logT, aout = -acc3[2] / n_frames / logN;
+    comps[5] = (float)cdp; comps[6] = (float)ain; comps[7] = (float)aout;
+    if (add_to_total) {
+        double tot = comps[0];
+        if (w_cdp != 0.f) tot += w_cdp * cdp;
+        if (w_ain != 0.f) tot += w_ain * ain;
+        if (w_aout != 0.f) tot += w_aout * aout;
+        comps[0] = (float)tot;
     }
 }
 

@@ -97,7 +97,7 @@ def AudioEnc(hp, S, training=True, speaker_codes=None, reuse=None, *, in_shift=0
 
 
 def Attention(hp, Q, K, V, monotonic_attention=False, prev_max_attentions=None, *, training=False, att_acc=None,
-              want_alignments=True, gts=None):
+              want_alignments=True, gts=None, extra=None):
     '''
     Args:
       Q: Queries. (B, T/r, d)   K: Keys. (B, N, d)   V: Values. (B, N, d)
@@ -112,6 +112,8 @@ def Attention(hp, Q, K, V, monotonic_attention=False, prev_max_attentions=None, 
     # gts: the batch's own attention targets [B, Ng, Tg] (hp.attention_guide_dir) for the loss terms that this block
     # accumulates into att_acc; hp.attention_guide_fa selects the MSE variant (architectures.py:256-280)
     mse = bool(getattr(hp, "attention_guide_fa", False)) and gts is not None
+    # extra = {"acc": device double[3], "lw": (lw_cdp, lw_ain, lw_aout) as they enter the total loss}: the "confidence
+    # through attention" terms of architectures.py:283-321 (training only)
     if monotonic_attention:
         assert N == hp.max_N and T == hp.max_T, "networks.py:304-311 builds the mask with hp.max_N / hp.max_T"
         win = hp.attention_win_size
@@ -140,6 +142,12 @@ def Attention(hp, Q, K, V, monotonic_attention=False, prev_max_attentions=None, 
     result = rq if concat else R
     if concat:
         rq._oph_planes = rq._oph_planes_buf         # both halves are written now: AudioDec's first conv reads planes
+    extra_bwd = None
+    if extra is not None and training:
+        import math
+        lw_cdp, lw_ain, lw_aout = extra["lw"]
+        col_g, col_h = ops.attention_extra_fwd(A, lw_cdp / float(B * N), -lw_ain / (B * N * math.log(T)), extra["acc"])
+        extra_bwd = (col_g, col_h, -lw_aout / (B * T * math.log(N)))
     if training and Tape.current is not None:
         kv = getattr(K, "_oph_kv", None)
 
@@ -148,7 +156,8 @@ def Attention(hp, Q, K, V, monotonic_attention=False, prev_max_attentions=None, 
             dR = dRp[:, :, :d] if concat else dRp
             dq_add = dRp[:, :, d:] if concat else None
             dQ, _dK, _dV = ops.attention_bwd(dR, Q, K, V, A, dq_addend=dq_add, att_coef=att_coef, maxN=hp.max_N,
-                                             maxT=hp.max_T, g=hp.g, dK=dKV[:, :, :d], dV=dKV[:, :, d:], gts=gts, mse=mse)
+                                             maxT=hp.max_T, g=hp.g, dK=dKV[:, :, :d], dV=dKV[:, :, d:], gts=gts, mse=mse,
+                                             extra=extra_bwd)
             return dQ, dKV
         result._oph_attention_bwd = bwd
     return result, alignments, max_attentions

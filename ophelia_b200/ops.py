@@ -306,14 +306,38 @@ def _new_planes(t):
     t._oph_planes = (hi[:, :, :C], lo[:, :, :C])
 
 
-def _guide(gts, mse):
+def _guide(gts, mse, extra=None):
     """`oph_guide` of the batch's own attention targets [B, Ng, Tg] (None -> analytic global guide).  Outside the block the
-    guided loss sees 1.0 and the MSE variant 0.0 (architectures.py:263, 275)."""
-    if gts is None:
+    guided loss sees 1.0 and the MSE variant 0.0 (architectures.py:263, 275).  extra = (col_g, col_h, c_aout): gradient
+    inputs of the CDP / Ain / Aout terms from attention_extra_fwd (backward only)."""
+    if gts is None and extra is None:
         return None
-    assert gts.is_cuda and gts.dtype == torch.float32 and gts.dim() == 3 and gts.stride(2) == 1
-    return ctypes.byref(_lib.Guide(gts.data_ptr(), gts.stride(0), gts.stride(1), gts.shape[1], gts.shape[2],
-                                   0.0 if mse else 1.0, int(bool(mse))))
+    gd = _lib.Guide()
+    if gts is not None:
+        assert gts.is_cuda and gts.dtype == torch.float32 and gts.dim() == 3 and gts.stride(2) == 1
+        gd.w, gd.item_stride, gd.ld, gd.Ng, gd.Tg = gts.data_ptr(), gts.stride(0), gts.stride(1), gts.shape[1], gts.shape[2]
+        gd.pad, gd.mse = (0.0 if mse else 1.0), int(bool(mse))
+    if extra is not None:
+        col_g, col_h, c_aout = extra
+        gd.col_g, gd.col_h, gd.c_aout = col_g.data_ptr(), col_h.data_ptr(), float(c_aout)
+    return ctypes.byref(gd)
+
+
+def attention_extra_fwd(A, c_cdp, c_ain, acc3):
+    """CDP / Ain / Aout sums of the alignments A [B, T, N] into acc3 (device double[3]); returns the per-key gradient
+    factors (col_g, col_h) [B, N] for attention_bwd (architectures.py:283-321)."""
+    B, T, N = A.shape
+    assert A.stride(2) == 1 and A.stride(0) == T * A.stride(1)
+    col_g = torch.empty(B, N, device=A.device, dtype=torch.float32)
+    col_h = torch.empty(B, N, device=A.device, dtype=torch.float32)
+    _lib.call("oph_attention_extra_fwd", _p(A), A.stride(1), B, T, N, float(c_cdp), float(c_ain), _p(col_g), _p(col_h),
+              _p(acc3), _stream())
+    return col_g, col_h
+
+
+def attention_extra_finalize(acc3, comps8, B, T, N, w_cdp, w_ain, w_aout, add_to_total):
+    _lib.call("oph_attention_extra_finalize", _p(acc3), _p(comps8), B, T, N, float(w_cdp), float(w_ain), float(w_aout),
+              int(bool(add_to_total)), _stream())
 
 
 def attention_fwd(Q, K, V, R=None, prev_max=None, win=3, want_alignments=False, want_argmax=True, att_acc=None,
@@ -338,7 +362,7 @@ def attention_fwd(Q, K, V, R=None, prev_max=None, win=3, want_alignments=False, 
 
 
 def attention_bwd(dR, Q, K, V, A, dq_addend=None, att_coef=0.0, maxN=1, maxT=1, g=0.2, dK=None, dV=None, gts=None,
-                  mse=False):
+                  mse=False, extra=None):
     ldq, B, T, d = _rows(Q)
     ldk, _, N, _ = _rows(K)
     dev = Q.device
@@ -358,7 +382,7 @@ def attention_bwd(dR, Q, K, V, A, dq_addend=None, att_coef=0.0, maxN=1, maxT=1, 
               _act(A, planes=pa), _act(dA),
               _p(dQ), dQ.stride(1), _p(dq_addend), dq_addend.stride(1) if dq_addend is not None else 0,
               _p(dK), dK.stride(1), _p(dV), dV.stride(1), float(att_coef), int(maxN), int(maxT), float(g),
-              B, T, N, d, _guide(gts, mse), _stream())
+              B, T, N, d, _guide(gts, mse, extra), _stream())
     return dQ, dK, dV
 
 

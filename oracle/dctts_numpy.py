@@ -299,7 +299,34 @@ def text2mel_loss(hp, out, mels, guide=None, gts=None):
         loss_att = (np.abs(Ap * np.asarray(guide, np.float64)[None]) * mask).sum() / mask.sum()
     w1, wbd, watt, w2 = _loss_weights(hp, "t2m")
     loss = w1 * loss_mels + wbd * loss_bd1 + watt * loss_att + w2 * loss_l2
+    lw_cdp, lw_ain, lw_aout = (getattr(hp, n, 0.0) for n in ("lw_cdp", "lw_ain", "lw_aout"))
+    if lw_cdp != 0.0 or lw_ain != 0.0 or lw_aout != 0.0:                        # :283-321, :333-355
+        cdp, ain, aout = attention_confidence_terms(A)
+        lw = getattr(hp, "loss_weights", None)
+        if not (lw and "t2m" in lw):        # the loss_weights dict branch (:325-331) does not add these terms
+            loss = loss + (lw_cdp * cdp if lw_cdp != 0.0 else 0.0) + (lw_ain * ain if lw_ain != 0.0 else 0.0) \
+                + (lw_aout * aout if lw_aout != 0.0 else 0.0)
+        return [loss, loss_mels, loss_bd1, loss_att, loss_l2, cdp, ain, aout]
     return [loss, loss_mels, loss_bd1, loss_att, loss_l2]
+
+
+def _plogp(P):
+    return np.where(P != 0, P * np.log(np.where(P != 0, P, 1.0)), 0.0)
+
+
+def attention_confidence_terms(A):
+    """architectures.py:283-321 on alignments [B, N_b, T_b]: coverage deviation penalty and the entropies of the attention
+    per input symbol (Ain, normalised over frames) and per output frame (Aout, normalised over symbols)."""
+    B, N, T = A.shape
+    att_per_input = A.sum(2)
+    cdp = np.log(1.0 + (1.0 - att_per_input) ** 2).sum() / (B * N)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        Pin = A / A.sum(2, keepdims=True)
+    Pin = np.where(np.isnan(Pin), 0.0, Pin)                                     # :301
+    ain = -_plogp(Pin).sum() / (B * N) / np.log(T)
+    Pout = A / A.sum(1, keepdims=True)
+    aout = -_plogp(Pout).sum() / (B * T) / np.log(N)
+    return cdp, ain, aout
 
 
 def ssrn_loss(hp, logits, Z, mags):

@@ -220,7 +220,20 @@ def text2mel_loss(hp, out, mels, gts=None):
         else:
             att = ((_pad_crop(A, -1.0, hp.max_N, hp.max_T) * _pad_crop(gts, 1.0, hp.max_N, hp.max_T)).abs() * mask).sum() / mask.sum()
     w1, wbd, watt, w2 = _lw(hp, "t2m")
-    return [w1 * l1 + wbd * bd + watt * att + w2 * l2, l1, bd, att, l2]
+    loss = w1 * l1 + wbd * bd + watt * att + w2 * l2
+    lw_cdp, lw_ain, lw_aout = (getattr(hp, n, 0.0) for n in ("lw_cdp", "lw_ain", "lw_aout"))
+    if lw_cdp != 0.0 or lw_ain != 0.0 or lw_aout != 0.0:                        # architectures.py:283-321, 333-355
+        Bn, Nn, Tn = A.shape
+        s_in = A.sum(2)
+        cdp = torch.log(1.0 + (1.0 - s_in) ** 2).sum() / (Bn * Nn)
+        plogp = lambda P: torch.where(P != 0, P * torch.log(torch.where(P != 0, P, torch.ones_like(P))), torch.zeros_like(P))
+        ain = -plogp(A / s_in[:, :, None]).sum() / (Bn * Nn) / math.log(Tn)
+        aout = -plogp(A / A.sum(1, keepdim=True)).sum() / (Bn * Tn) / math.log(Nn)
+        lw = getattr(hp, "loss_weights", None)
+        if not (lw and "t2m" in lw):
+            loss = loss + lw_cdp * cdp + lw_ain * ain + lw_aout * aout
+        return [loss, l1, bd, att, l2, cdp, ain, aout]
+    return [loss, l1, bd, att, l2]
 
 
 def ssrn_loss(hp, logits, Z, mags):

@@ -143,6 +143,37 @@ def test_train_step_with_batch_guides_matches_oracle(fa, gshape):
         g.train_step_device(Ld, md)
 
 
+def test_train_step_with_confidence_losses_matches_oracle():
+    """hp.lw_cdp / lw_ain / lw_aout (architectures.py:283-321): coverage deviation penalty and the two attention entropies
+    as training losses.  Alone first (their gradient reaches the encoders through Q and K only: tight bound on the
+    ReLU-free AudioEnc tail), then with every term over two optimiser steps, then under the loss_weights dict pattern,
+    where the reference reports them but leaves them out of the total (:325-331)."""
+    B, N, T = 3, 37, 90
+    b = synthetic_batch(make_hp(), B, N, T, ragged=True)
+    L, mels = torch.tensor(b["L"].astype(np.int64)), torch.tensor(b["mels"], dtype=torch.float64)
+    Ld, md = torch.tensor(b["L"]).cuda(), torch.tensor(b["mels"]).cuda()
+    for case in ("alone", "all", "dict"):
+        hp = make_hp(max_N=N + 3, max_T=T + 2, dropout_rate=0.0, lw_cdp=0.3, lw_ain=0.4, lw_aout=0.2)
+        if case == "alone":
+            hp.lw_mel, hp.lw_bd1, hp.lw_att, hp.lw_t2m_l2 = 0.0, 0.0, 0.0, 0.0
+        if case == "dict":
+            hp.loss_weights = {"t2m": {"L1": 0.3, "binary_divergence": 0.3, "attention": 0.3, "L2": 0.1}}
+        P = oracle_params(hp, "t2m", seed=8)
+        Pt = ot.to_torch(P, torch.float64, requires_grad=True)
+        opt = ot.TFAdam(hp, Pt)
+        g = _graph(hp, "train", P, data=iter([]))
+        for step in range(1 if case == "alone" else 2):
+            comps_ref, grads_ref = ot.text2mel_train_step(hp, Pt, opt, L, mels)
+            comps = g.train_step_device(Ld, md).cpu().numpy()
+            assert len(comps) == len(comps_ref) == 8
+            np.testing.assert_allclose(comps, comps_ref, rtol=2e-4, atol=1e-6)
+            if case == "alone":
+                sd = g.store.grads
+                check_grads({n: sd[n].cpu().numpy() for n in grads_ref}, grads_ref, "Text2Mel/AudioEnc/HC_13/")
+        if case == "dict":
+            assert abs(comps[0] - (0.3 * comps[1] + 0.3 * comps[2] + 0.3 * comps[3] + 0.1 * comps[4])) < 1e-5
+
+
 def test_autoregressive_loop_matches_oracle():
     from ophelia_b200.session import Session
     from ophelia_b200 import synthesize as syn
