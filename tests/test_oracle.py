@@ -133,3 +133,33 @@ def test_autoregressive_loop_early_stop():
         last = t_ends[b] if t_ends[b] < 9 else 8
         steps = np.diff(am[b, :last + 1])
         assert (steps >= 0).all() and (steps <= 2).all()
+
+
+def test_confidence_terms_restatements_agree_and_match_the_diagnostic_script():
+    """architectures.py:283-321 (training losses) in both oracles, and -- for one utterance -- against the independent
+    restatement of calculate_CDP_Ain_Aout.py (the reference's own numpy diagnostic of the same quantities)."""
+    import torch
+    from helpers import make_hp, oracle_params
+    from ophelia_b200 import synthesize as syn
+    from oracle import dctts_numpy as on
+    from oracle import dctts_torch as ot
+    from oracle.params import synthetic_batch
+    hp = make_hp(max_N=24, max_T=40, dropout_rate=0.0, lw_cdp=0.2, lw_ain=0.3, lw_aout=0.1)
+    P = oracle_params(hp, "t2m", seed=1)
+    b = synthetic_batch(hp, 2, 20, 36)
+    out = on.text2mel_forward(hp, P, b["L"], b["mels"], "train")
+    c1 = on.text2mel_loss(hp, out, b["mels"])
+    Pt = ot.to_torch(P, torch.float64)
+    o2 = ot.text2mel_forward(hp, Pt, torch.tensor(b["L"].astype(np.int64)), torch.tensor(b["mels"], dtype=torch.float64), "train")
+    c2 = [float(c) for c in ot.text2mel_loss(hp, o2, torch.tensor(b["mels"], dtype=torch.float64))]
+    assert len(c1) == len(c2) == 8
+    np.testing.assert_allclose(c1, c2, rtol=1e-12)
+    assert abs(c1[0] - (hp.lw_mel * c1[1] + hp.lw_bd1 * c1[2] + hp.lw_att * c1[3] + 0.2 * c1[5] + 0.3 * c1[6] + 0.1 * c1[7])) < 1e-12
+    for i in range(2):
+        A = out["alignments"][i:i + 1]
+        cdp, ain, aout = on.attention_confidence_terms(A)
+        apin, apout = syn.getAP(A[0])
+        assert abs(cdp - syn.getCDP(A[0])) < 1e-12 and abs(ain - apin) < 1e-12 and abs(aout - apout) < 1e-12
+    hp.loss_weights = {"t2m": {"L1": 0.3, "binary_divergence": 0.3, "attention": 0.3, "L2": 0.1}}
+    c3 = on.text2mel_loss(hp, out, b["mels"])
+    assert len(c3) == 8 and abs(c3[0] - (0.3 * c3[1] + 0.3 * c3[2] + 0.3 * c3[3] + 0.1 * c3[4])) < 1e-12
