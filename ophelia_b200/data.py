@@ -1,6 +1,7 @@
 """Synthetic batches that reproduce the output contract of the reference's input pipeline
 (`data_load.py:302-544`: text int32 [B,N] zero-padded, mel fp32 [B,T,n_mels] in [1e-8,1] zero-padded,
-mag fp32 [B,T*r,full_dim]).  The real pipeline (transcripts, .npy features, bucketing) is out of scope."""
+mag fp32 [B,T*r,full_dim]) -- what bench.py and the parity tests feed.  The pipeline over real transcripts and .npy
+features is ophelia_b200/data_load.py."""
 import numpy as np
 import torch
 
