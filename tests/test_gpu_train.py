@@ -64,6 +64,18 @@ def test_text2mel_training_driver_end_to_end(tmp_path):
         assert sr == hp.sr and len(pcm) == hp.hop_length * (n * hp.r - 1) and np.abs(pcm).max() > 0
         ali = np.load(os.path.join(outdir, base + "_alignment.npy"))
         assert ali.shape[1] == n and np.allclose(ali.sum(0), 1.0, atol=1e-4)
+    # copy synthesis (copy_synth_SSRN_GL.py) and waveforms for the stored validation predictions
+    # (synthesise_validation_waveforms.py)
+    from ophelia_b200 import copy_synth
+    wavs = copy_synth.copy_synth_SSRN_GL(hp, str(tmp_path / "copy"))
+    assert len(wavs) == 3 and all(os.path.getsize(w) > 44 for w in wavs)
+    for w in wavs:
+        mel = np.load(os.path.join(hp.coarse_audio_dir, os.path.basename(w).replace(".wav", ".npy")))
+        assert len(wavfile.read(w)[1]) == hp.hop_length * (mel.shape[0] * hp.r - 1)
+    vw = copy_synth.synthesise_validation_waveforms(hp)
+    n_t2m = len(glob.glob(logdir + "/validation_epoch_*/*.mag.npy"))
+    n_ssrn = len(glob.glob(hp.logdir + "-ssrn/validation_epoch_*/*.npy"))
+    assert n_t2m == 2 * 8 and n_ssrn == 2 and len(vw) == n_t2m + n_ssrn and all(os.path.exists(w) for w in vw)
 
 
 def test_ssrn_training_driver(tmp_path):
