@@ -259,6 +259,26 @@ int oph_gemm_tn(const float* A, long long lda, const float* Bm, long long ldb, f
  *             (Yw [B][W][ldyw], align_w [B][N][W], argmax_w [B][W]) into frame j of Y [B][T][ldy], alignments
  *             [B][N][T], prev [B] and history [T][B] (synthesize.py:204-209).
  *  advance:   *frame += 1 */
+/* One layer of the AudioEnc frame step for oph_ar_encoder_step: the same quantities as the arguments of conv_step / hc_step
+ * (kind 0: conv1d with C = Cout output channels; kind 1: highway layer with C channels, w = [k][C][2C]; g2 / b2 for
+ * highway layers only; g1 == NULL: no layer norm). */
+typedef struct {
+    const float* w;
+    const float* bias;
+    const float* g1;
+    const float* b1;
+    const float* g2;
+    const float* b2;
+    const float* x;
+    float* y;
+    long long x_item, ldx, y_item, ldy;
+    int Cin, C, k, rate, kind, act, in_shift;
+} oph_ar_layer;
+/* The whole AudioEnc frame step in one launch: row j of an item depends on that item's histories only, so the layers of an
+ * item run back to back in one kernel; an item gets a thread-block cluster of 8 CTAs (CTA r owns 1/8 of every layer's
+ * output channels, LayerNorm moments through distributed shared memory, a cluster barrier between layers).  Same results
+ * as the per-layer calls up to the summation order.  Needs C / 8 (2 C / 8 for highway layers) in {32, 64, 128}. */
+int oph_ar_encoder_step(const oph_ar_layer* layers, int nlayers, int B, const int* frame, oph_stream_t stream);
 size_t oph_ar_scratch_floats(void);
 int oph_ar_conv_step(const float* x, long long x_item, long long ldx, const float* w, const float* bias,
                      const float* gamma, const float* beta, float* y, long long y_item, long long ldy, float* y_sig,

@@ -27,6 +27,13 @@ class Guide(ctypes.Structure):
 
 GP = ctypes.POINTER(Guide)
 
+
+class ArLayer(ctypes.Structure):
+    """`oph_ar_layer`: one AudioEnc layer of the fused frame step (include/ophelia_b200.h)."""
+    _fields_ = [("w", P), ("bias", P), ("g1", P), ("b1", P), ("g2", P), ("b2", P), ("x", P), ("y", P),
+                ("x_item", LL), ("ldx", LL), ("y_item", LL), ("ldy", LL),
+                ("Cin", I), ("C", I), ("k", I), ("rate", I), ("kind", I), ("act", I), ("in_shift", I)]
+
 # name -> (restype, argtypes); must list every symbol of include/ophelia_b200.h
 SIGNATURES = {
     "oph_version": (I, []),
@@ -63,6 +70,7 @@ SIGNATURES = {
     "oph_adam_prepare": (I, [P, P, F, F, F, I, F, P]),
     "oph_adam_clip": (I, [P, P, P, P, LL, P, F, F, F, F, F, P]),
     "oph_step_inc": (I, [P, P]),
+    "oph_ar_encoder_step": (I, [ctypes.POINTER(ArLayer), I, I, P, P]),
     "oph_ar_scratch_floats": (SZ, []),
     "oph_ar_conv_step": (I, [P, LL, LL, P, P, P, P, P, LL, LL, P, LL, LL, P, I, I, I, I, I, I, I, P, P]),
     "oph_ar_hc_step": (I, [P, LL, LL, P, P, P, P, P, P, P, LL, LL, P, I, I, I, I, P, P]),

@@ -17,6 +17,7 @@
 // All arithmetic is fp32 FMA (the tcgen05 path's split-bf16 products are an emulation of exactly this).
 #pragma once
 #include "rowwise.cuh"
+#include <cooperative_groups.h>
 
 namespace oph {
 
@@ -183,6 +184,109 @@ __global__ void ar_window_scatter_kernel(const float* __restrict__ Yw, long long
         const int a = argmax_w[(long long)b * W + r];
         prev[b] = a;
         history[(long long)j * B + b] = a;
+    }
+}
+
+// ---- the whole AudioEnc frame step in ONE launch ---------------------------------------------------------------
+// Row j of every AudioEnc layer depends on that item's own histories only, so the 13 layers of an item can run back to
+// back inside one kernel.  A single SM cannot stream the 16 MB of weights fast enough (~120 GB/s from L2), so an item is
+// given a thread-block CLUSTER of 8 CTAs: CTA r owns the output channels [r C/8, (r+1) C/8) of every layer (for a highway
+// layer the matching slices of H1 and H2), the LayerNorm moments are exchanged through distributed shared memory, and a
+// cluster barrier publishes row j of a layer (written to its history in HBM / L2) to the 7 peers before the next layer
+// stages it.  26 launches per frame become one.
+struct ArEncLayer {
+    const float* w; const float* bias; const float* g1; const float* b1; const float* g2; const float* b2;
+    const float* x; float* y;
+    long long x_item, ldx, y_item, ldy;
+    int Cin, C, k, rate, kind, act, in_shift;      // kind 0: conv1d (C = Cout), 1: highway (C channels, 2 C conv outputs)
+};
+constexpr int AR_ENC_MAX_LAYERS = 16;
+constexpr int AR_ENC_CLUSTER = 8;
+constexpr int AR_ENC_MAXK = 3072;
+struct ArEncArgs { ArEncLayer L[AR_ENC_MAX_LAYERS]; int nlayers; };
+
+__global__ void __cluster_dims__(AR_ENC_CLUSTER, 1, 1) __launch_bounds__(256)
+ar_encoder_kernel(const ArEncArgs a, const int* __restrict__ frame) {
+    namespace cg = cooperative_groups;
+    pdl_grid_sync();
+    cg::cluster_group cl = cg::this_cluster();
+    __shared__ float xs[AR_ENC_MAXK];
+    __shared__ float red[8][128];
+    __shared__ float zs[128];
+    __shared__ float part[2][2][2];                  // [layer parity][pass][H1 / H2]: this CTA's share of the moments
+    const int r = (int)cl.block_rank(), b = blockIdx.y, tid = threadIdx.x;
+    const int j = *frame;
+    for (int l = 0; l < a.nlayers; ++l) {
+        const ArEncLayer& Ly = a.L[l];
+        const int K = Ly.k * Ly.Cin, C = Ly.C, hc = Ly.kind, cpc = C / AR_ENC_CLUSTER;
+        const int ncols = hc ? 2 * cpc : cpc, O = hc ? 2 * C : C, nsub = 256 / ncols, ph = l & 1;
+        for (int idx = tid; idx < K; idx += 256) {
+            const int tap = idx / Ly.Cin, c = idx - tap * Ly.Cin;
+            const int t = j - Ly.in_shift - (Ly.k - 1 - tap) * Ly.rate;
+            // (row j of the layer below was written by the peer CTAs a moment ago: read through L2)
+            xs[idx] = t >= 0 ? __ldcg(Ly.x + (long long)b * Ly.x_item + (long long)t * Ly.ldx + c) : 0.f;
+        }
+        __syncthreads();
+        const int lc = tid % ncols, sub = tid / ncols;
+        // channel of this thread's column inside its group, and the conv output column it accumulates
+        const int ch = r * cpc + (lc < cpc ? lc : lc - cpc);
+        const int gcol = (hc && lc >= cpc) ? C + ch : ch;
+        {
+            float acc = 0.f;
+            const float* wp = Ly.w + gcol;
+            for (int kk = sub; kk < K; kk += nsub) acc = fmaf(__ldg(wp + (long long)kk * O), xs[kk], acc);
+            red[sub][lc] = acc;
+        }
+        __syncthreads();
+        if (tid < ncols) {
+            float s = Ly.bias ? Ly.bias[gcol] : 0.f;
+            for (int q = 0; q < nsub; ++q) s += red[q][tid];
+            zs[tid] = s;
+        }
+        __syncthreads();
+        const int grp = (hc && tid >= cpc) ? 1 : 0;   // which LayerNorm a column of this CTA belongs to
+        float u = tid < ncols ? zs[tid] : 0.f;
+        if (Ly.g1) {
+            if (tid < (hc ? 2 : 1)) {
+                float s = 0.f;
+                for (int c = 0; c < cpc; ++c) s += zs[tid * cpc + c];
+                part[ph][0][tid] = s;
+            }
+            cl.sync();
+            float mean = 0.f;
+            for (int rr = 0; rr < AR_ENC_CLUSTER; ++rr) mean += cl.map_shared_rank(&part[ph][0][0], rr)[grp];
+            mean /= (float)C;
+            if (tid < (hc ? 2 : 1)) {
+                float m2 = 0.f;
+                for (int rr = 0; rr < AR_ENC_CLUSTER; ++rr) m2 += cl.map_shared_rank(&part[ph][0][0], rr)[tid];
+                m2 /= (float)C;
+                float q = 0.f;
+                for (int c = 0; c < cpc; ++c) { const float d = zs[tid * cpc + c] - m2; q += d * d; }
+                part[ph][1][tid] = q;
+            }
+            cl.sync();
+            float var = 0.f;
+            for (int rr = 0; rr < AR_ENC_CLUSTER; ++rr) var += cl.map_shared_rank(&part[ph][1][0], rr)[grp];
+            const float rstd = rsqrtf(var / (float)C + LN_EPS);
+            if (tid < ncols) {
+                const float gam = grp ? Ly.g2[ch] : Ly.g1[ch], bet = grp ? Ly.b2[ch] : Ly.b1[ch];
+                u = (u - mean) * rstd * gam + bet;
+            }
+        }
+        float* yr = Ly.y + (long long)b * Ly.y_item + (long long)j * Ly.ldy;
+        if (!hc) {
+            if (tid < ncols) yr[ch] = Ly.act ? fmaxf(u, 0.f) : u;
+        } else {
+            __syncthreads();                          // every column has read zs
+            if (tid < ncols) zs[tid] = u;
+            __syncthreads();
+            if (tid < cpc) {
+                const float g = sigmoidf_(zs[tid]);
+                const float xres = xs[(Ly.k - 1) * Ly.Cin + ch];      // tap k - 1 is row j of the layer input
+                yr[ch] = g * zs[cpc + tid] + (1.f - g) * xres;
+            }
+        }
+        cl.sync();                                    // row j of this layer is visible to the cluster; xs / zs / red are free
     }
 }
 

@@ -1096,6 +1096,27 @@ int oph_ar_hc_step(const float* x, long long x_item, long long ldx, const float*
     return check_launch("ar_tail_kernel");
 }
 
+int oph_ar_encoder_step(const oph_ar_layer* layers, int nlayers, int B, const int* frame, oph_stream_t stream) {
+    if (!layers || nlayers < 1 || nlayers > AR_ENC_MAX_LAYERS || B < 1) return fail(OPH_EINVAL, "ar_encoder_step: 1..16 layers%s");
+    ArEncArgs a;
+    memset(&a, 0, sizeof(a));
+    a.nlayers = nlayers;
+    for (int i = 0; i < nlayers; ++i) {
+        const oph_ar_layer& s = layers[i];
+        const int cols = (s.kind ? 2 : 1) * (s.C / AR_ENC_CLUSTER);
+        if (s.C % AR_ENC_CLUSTER || (cols != 32 && cols != 64 && cols != 128) || s.k < 1 || s.k > 3 || s.Cin < 1 ||
+            s.k * s.Cin > AR_ENC_MAXK || (s.kind && s.Cin != s.C) || !s.w || !s.x || !s.y ||
+            ((s.g1 == nullptr) != (s.b1 == nullptr)) || (s.kind && ((s.g1 == nullptr) != (s.g2 == nullptr))))
+            return fail(OPH_EINVAL, "ar_encoder_step: unsupported layer shape (use the per-layer calls)%s");
+        ArEncLayer& d = a.L[i];
+        d.w = s.w; d.bias = s.bias; d.g1 = s.g1; d.b1 = s.b1; d.g2 = s.g2; d.b2 = s.b2; d.x = s.x; d.y = s.y;
+        d.x_item = s.x_item; d.ldx = s.ldx; d.y_item = s.y_item; d.ldy = s.ldy;
+        d.Cin = s.Cin; d.C = s.C; d.k = s.k; d.rate = s.rate; d.kind = s.kind; d.act = s.act; d.in_shift = s.in_shift;
+    }
+    launch_cfg(dim3(AR_ENC_CLUSTER, B), 256, 0, S(stream))(ar_encoder_kernel, a, frame);
+    return check_launch("ar_encoder_kernel");
+}
+
 int oph_ar_window_gather(const float* Q, long long q_item, long long ldq, float* Qw, long long w_item, long long ldw,
                          int B, int d, int T, int W, int reach, const int* frame, oph_stream_t stream) {
     if (B < 1 || W < 1 || W > T || reach < 0) return fail(OPH_EINVAL, "ar_window_gather: need 1 <= W <= T%s");

@@ -183,7 +183,7 @@ def _window_hp(hp, W):
     return hp_w
 
 
-def synth_codedtext2mel_incremental(hp, K, V, ends, g, use_cuda_graph=True, check_every=8):
+def synth_codedtext2mel_incremental(hp, K, V, ends, g, use_cuda_graph=True, check_every=8, fused_encoder=None):
     """The same loop with the per-frame work cut to what can change (csrc/arstep.cuh; SURVEY 7, hard part 5):
 
     * AudioEnc is causal and its input row t is final once frame t - 1 exists: every layer keeps its output history and
@@ -192,6 +192,9 @@ def synth_codedtext2mel_incremental(hp, K, V, ends, g, use_cuda_graph=True, chec
       (networks.py:304-313), so the context rows R[t < j] change whenever the window moves, and AudioDec's row j sees them
       through its 84-frame causal reach.  Attention and AudioDec therefore run per step with the batch (tcgen05) kernels,
       but over the rows [max(0, j - 84), j] only.
+
+    fused_encoder (default: whenever d is 256 or 512): the 13 AudioEnc layers of a frame step run in ONE launch, an
+    8-CTA thread-block cluster per sentence (oph_ar_encoder_step), instead of two launches per layer.
 
     One captured CUDA graph is replayed per frame (the frame index lives on the device).  Results equal the full
     re-computation up to fp32 rounding (tests/test_incremental_algorithm.py pins the algorithm against the oracle loop);
@@ -214,8 +217,10 @@ def synth_codedtext2mel_incremental(hp, K, V, ends, g, use_cuda_graph=True, chec
     W = min(T, reach + 1)
     hp_w = _window_hp(hp, W)
     enc_layers = _frame_step_layers(hp)[0]
+    if fused_encoder is None:
+        fused_encoder = d in (256, 512)
     cache = g.__dict__.setdefault("_ar_inc_state", {})
-    key = (B, N, d, T, bool(use_cuda_graph), st.flat.data_ptr())
+    key = (B, N, d, T, bool(use_cuda_graph), bool(fused_encoder), st.flat.data_ptr())
     state = cache.get(key)
     if state is not None and state["version"] != st.version:    # the windowed decoder reads packed weight images
         state = None
@@ -252,11 +257,36 @@ def synth_codedtext2mel_incremental(hp, K, V, ends, g, use_cuda_graph=True, chec
                       ops._p(gamma), ops._p(beta), y.data_ptr(), y.stride(0), y.stride(1), None, 0, 0,
                       state["scratch"].data_ptr(), B, cin, cout, k, rate, in_shift, act, frame.data_ptr(), stream)
 
+    def encoder_table():
+        """oph_ar_layer[13]: the static description of the AudioEnc frame step for the one-launch kernel."""
+        table = (_lib.ArLayer * len(enc_layers))()
+        x = Y
+        for i, (scope, kind, k, rate, act) in enumerate(enc_layers):
+            y = state["enc"][i]
+            e = table[i]
+            names = ("/H1/gamma", "/H1/beta", "/H2/gamma", "/H2/beta") if kind == "hc" else ("/normalize/gamma", "/normalize/beta")
+            params = [ops._p(var(scope + n)) if norm else None for n in names] + [None, None]
+            e.w, e.bias = var(scope + "/conv1d/kernel").data_ptr(), var(scope + "/conv1d/bias").data_ptr()
+            e.g1, e.b1, e.g2, e.b2 = params[:4]
+            e.x, e.y = x.data_ptr(), y.data_ptr()
+            e.x_item, e.ldx, e.y_item, e.ldy = x.stride(0), x.stride(1), y.stride(0), y.stride(1)
+            e.Cin, e.C, e.k, e.rate = x.shape[2], y.shape[2], k, rate
+            e.kind, e.act, e.in_shift = int(kind == "hc"), act, 1 if i == 0 else 0
+            x = y
+        return table
+
     def step():
         x = Y                                              # S = mels delayed by one frame (architectures.py:191)
-        for i, spec in enumerate(enc_layers):
-            enc_layer(spec, x, state["enc"][i], 1 if i == 0 else 0)
-            x = state["enc"][i]
+        if fused_encoder:
+            if "enc_table" not in state:
+                state["enc_table"] = encoder_table()
+            _lib.call("oph_ar_encoder_step", state["enc_table"], len(enc_layers), B, frame.data_ptr(),
+                      torch.cuda.current_stream().cuda_stream)
+            x = state["enc"][-1]
+        else:
+            for i, spec in enumerate(enc_layers):
+                enc_layer(spec, x, state["enc"][i], 1 if i == 0 else 0)
+                x = state["enc"][i]
         stream = torch.cuda.current_stream().cuda_stream
         _lib.call("oph_ar_window_gather", x.data_ptr(), x.stride(0), x.stride(1), Qw.data_ptr(), Qw.stride(0), Qw.stride(1),
                   B, d, T, W, reach, frame.data_ptr(), stream)
