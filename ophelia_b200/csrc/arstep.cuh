@@ -205,22 +205,29 @@ constexpr int AR_ENC_CLUSTER = 8;
 constexpr int AR_ENC_MAXK = 3072;
 struct ArEncArgs { ArEncLayer L[AR_ENC_MAX_LAYERS]; int nlayers; };
 
-__global__ void __cluster_dims__(AR_ENC_CLUSTER, 1, 1) __launch_bounds__(256)
+constexpr int AR_ENC_THREADS = 1024;
+
+__device__ __forceinline__ void ar_cluster_barrier() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+__global__ void __cluster_dims__(AR_ENC_CLUSTER, 1, 1) __launch_bounds__(AR_ENC_THREADS)
 ar_encoder_kernel(const ArEncArgs a, const int* __restrict__ frame) {
     namespace cg = cooperative_groups;
     pdl_grid_sync();
     cg::cluster_group cl = cg::this_cluster();
     __shared__ float xs[AR_ENC_MAXK];
-    __shared__ float red[8][128];
+    __shared__ float red[AR_ENC_THREADS];            // [k sub-slice][column]
     __shared__ float zs[128];
-    __shared__ float part[2][2][2];                  // [layer parity][pass][H1 / H2]: this CTA's share of the moments
+    __shared__ float2 part[2][2];                    // [layer parity][H1 / H2]: (mean, sum of squared deviations) of this CTA's columns
     const int r = (int)cl.block_rank(), b = blockIdx.y, tid = threadIdx.x;
     const int j = *frame;
     for (int l = 0; l < a.nlayers; ++l) {
         const ArEncLayer& Ly = a.L[l];
         const int K = Ly.k * Ly.Cin, C = Ly.C, hc = Ly.kind, cpc = C / AR_ENC_CLUSTER;
-        const int ncols = hc ? 2 * cpc : cpc, O = hc ? 2 * C : C, nsub = 256 / ncols, ph = l & 1;
-        for (int idx = tid; idx < K; idx += 256) {
+        const int ncols = hc ? 2 * cpc : cpc, O = hc ? 2 * C : C, nsub = AR_ENC_THREADS / ncols, ph = l & 1;
+        for (int idx = tid; idx < K; idx += AR_ENC_THREADS) {
             const int tap = idx / Ly.Cin, c = idx - tap * Ly.Cin;
             const int t = j - Ly.in_shift - (Ly.k - 1 - tap) * Ly.rate;
             // (row j of the layer below was written by the peer CTAs a moment ago: read through L2)
@@ -232,42 +239,49 @@ ar_encoder_kernel(const ArEncArgs a, const int* __restrict__ frame) {
         const int ch = r * cpc + (lc < cpc ? lc : lc - cpc);
         const int gcol = (hc && lc >= cpc) ? C + ch : ch;
         {
-            float acc = 0.f;
+            // four independent chains, four weight loads in flight per thread (the weights come from L2)
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
             const float* wp = Ly.w + gcol;
-            for (int kk = sub; kk < K; kk += nsub) acc = fmaf(__ldg(wp + (long long)kk * O), xs[kk], acc);
-            red[sub][lc] = acc;
+            int kk = sub;
+            for (; kk + 3 * nsub < K; kk += 4 * nsub) {
+                const float w0 = __ldg(wp + (long long)kk * O), w1 = __ldg(wp + (long long)(kk + nsub) * O);
+                const float w2 = __ldg(wp + (long long)(kk + 2 * nsub) * O), w3 = __ldg(wp + (long long)(kk + 3 * nsub) * O);
+                a0 = fmaf(w0, xs[kk], a0); a1 = fmaf(w1, xs[kk + nsub], a1);
+                a2 = fmaf(w2, xs[kk + 2 * nsub], a2); a3 = fmaf(w3, xs[kk + 3 * nsub], a3);
+            }
+            for (; kk < K; kk += nsub) a0 = fmaf(__ldg(wp + (long long)kk * O), xs[kk], a0);
+            red[sub * ncols + lc] = (a0 + a1) + (a2 + a3);
         }
         __syncthreads();
         if (tid < ncols) {
             float s = Ly.bias ? Ly.bias[gcol] : 0.f;
-            for (int q = 0; q < nsub; ++q) s += red[q][tid];
+            for (int q = 0; q < nsub; ++q) s += red[q * ncols + tid];
             zs[tid] = s;
         }
         __syncthreads();
-        const int grp = (hc && tid >= cpc) ? 1 : 0;   // which LayerNorm a column of this CTA belongs to
+        const int grp = (hc && lc >= cpc) ? 1 : 0;    // which LayerNorm a column of this CTA belongs to
         float u = tid < ncols ? zs[tid] : 0.f;
         if (Ly.g1) {
+            // moments of the C channels of a group from the 8 CTAs' (mean, M2) pairs (two passes locally, Chan's
+            // combination across the cluster: as accurate as two global passes, one exchange instead of two)
             if (tid < (hc ? 2 : 1)) {
-                float s = 0.f;
-                for (int c = 0; c < cpc; ++c) s += zs[tid * cpc + c];
-                part[ph][0][tid] = s;
-            }
-            cl.sync();
-            float mean = 0.f;
-            for (int rr = 0; rr < AR_ENC_CLUSTER; ++rr) mean += cl.map_shared_rank(&part[ph][0][0], rr)[grp];
-            mean /= (float)C;
-            if (tid < (hc ? 2 : 1)) {
-                float m2 = 0.f;
-                for (int rr = 0; rr < AR_ENC_CLUSTER; ++rr) m2 += cl.map_shared_rank(&part[ph][0][0], rr)[tid];
-                m2 /= (float)C;
+                float m = 0.f;
+                for (int c = 0; c < cpc; ++c) m += zs[tid * cpc + c];
+                m /= (float)cpc;
                 float q = 0.f;
-                for (int c = 0; c < cpc; ++c) { const float d = zs[tid * cpc + c] - m2; q += d * d; }
-                part[ph][1][tid] = q;
+                for (int c = 0; c < cpc; ++c) { const float d = zs[tid * cpc + c] - m; q += d * d; }
+                part[ph][tid] = make_float2(m, q);
             }
-            cl.sync();
-            float var = 0.f;
-            for (int rr = 0; rr < AR_ENC_CLUSTER; ++rr) var += cl.map_shared_rank(&part[ph][1][0], rr)[grp];
-            const float rstd = rsqrtf(var / (float)C + LN_EPS);
+            ar_cluster_barrier();
+            float2 pr[AR_ENC_CLUSTER];
+            float mean = 0.f;
+#pragma unroll
+            for (int rr = 0; rr < AR_ENC_CLUSTER; ++rr) { pr[rr] = cl.map_shared_rank(&part[ph][0], rr)[grp]; mean += pr[rr].x; }
+            mean *= 1.f / (float)AR_ENC_CLUSTER;
+            float m2 = 0.f;
+#pragma unroll
+            for (int rr = 0; rr < AR_ENC_CLUSTER; ++rr) { const float d = pr[rr].x - mean; m2 += pr[rr].y + (float)cpc * d * d; }
+            const float rstd = rsqrtf(m2 / (float)C + LN_EPS);
             if (tid < ncols) {
                 const float gam = grp ? Ly.g2[ch] : Ly.g1[ch], bet = grp ? Ly.b2[ch] : Ly.b1[ch];
                 u = (u - mean) * rstd * gam + bet;
@@ -277,7 +291,7 @@ ar_encoder_kernel(const ArEncArgs a, const int* __restrict__ frame) {
         if (!hc) {
             if (tid < ncols) yr[ch] = Ly.act ? fmaxf(u, 0.f) : u;
         } else {
-            __syncthreads();                          // every column has read zs
+            __syncthreads();                          // every column (and the moment threads) has read zs
             if (tid < ncols) zs[tid] = u;
             __syncthreads();
             if (tid < cpc) {
@@ -286,7 +300,7 @@ ar_encoder_kernel(const ArEncArgs a, const int* __restrict__ frame) {
                 yr[ch] = g * zs[cpc + tid] + (1.f - g) * xres;
             }
         }
-        cl.sync();                                    // row j of this layer is visible to the cluster; xs / zs / red are free
+        ar_cluster_barrier();                         // row j of this layer is visible to the cluster; xs / zs / red are free
     }
 }
 

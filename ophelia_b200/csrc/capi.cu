@@ -1113,7 +1113,7 @@ int oph_ar_encoder_step(const oph_ar_layer* layers, int nlayers, int B, const in
         d.x_item = s.x_item; d.ldx = s.ldx; d.y_item = s.y_item; d.ldy = s.ldy;
         d.Cin = s.Cin; d.C = s.C; d.k = s.k; d.rate = s.rate; d.kind = s.kind; d.act = s.act; d.in_shift = s.in_shift;
     }
-    launch_cfg(dim3(AR_ENC_CLUSTER, B), 256, 0, S(stream))(ar_encoder_kernel, a, frame);
+    launch_cfg(dim3(AR_ENC_CLUSTER, B), AR_ENC_THREADS, 0, S(stream))(ar_encoder_kernel, a, frame);
     return check_launch("ar_encoder_kernel");
 }
 

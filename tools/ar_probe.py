@@ -39,13 +39,20 @@ g1 = Text2MelGraph(hp, mode="synthesize", store=VariableStore(dev, seed=0), devi
 K, V = syn.encode_text(hp, L, g1, Session())
 ends = np.full(10, hp.max_N + 1)
 lib = _lib.load()
-for use_graph in ((True, False) if args.graph else (False,)):
-    for rep in range(2 if use_graph else 1):
+results = {}
+for use_graph, fused in (((True, False), (True, True), (False, False)) if args.graph else ((False, False),)):
+    for rep in range(3 if use_graph else 1):
         n0 = lib.oph_launch_count()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        Y, t_ends, _ = syn.synth_codedtext2mel_incremental(hp, K, V, ends, g1, use_cuda_graph=use_graph, check_every=8)
+        Y, t_ends, A = syn.synth_codedtext2mel_incremental(hp, K, V, ends, g1, use_cuda_graph=use_graph, check_every=8,
+                                                           fused_encoder=fused)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
-        print("cuda_graph=%s run %d: %.2f ms per frame, %d library launches" % (use_graph, rep, 1e3 * dt / args.frames,
-                                                                                lib.oph_launch_count() - n0))
+        print("cuda_graph=%s fused_encoder=%s run %d: %.3f ms per frame, %d library launches"
+              % (use_graph, fused, rep, 1e3 * dt / args.frames, lib.oph_launch_count() - n0), flush=True)
+    results[(use_graph, fused)] = (Y, t_ends, A)
+if (True, True) in results:
+    (Y0, t0_, A0), (Y1, t1_, A1) = results[(True, False)], results[(True, True)]
+    print("fused vs per-layer encoder: t_ends equal %s, max |dY| %.2e, max |dA| %.2e"
+          % (t0_ == t1_, float(np.abs(Y0 - Y1).max()), float(np.abs(A0 - A1).max())))
