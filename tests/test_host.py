@@ -210,3 +210,33 @@ def test_restore_latest_model_parameters_follows_reference_convention(tmp_path):
     assert torch.equal(G.store.flat, src.flat)
     with pytest.raises(SystemExit):
         restore_latest_model_parameters(None, hp, "t2m", graph=G)        # no checkpoint directory for that model
+
+
+def test_header_is_plain_c_and_struct_layouts_match_the_ctypes_mirrors(tmp_path):
+    """include/ophelia_b200.h must be bindable from C (cgo / JNI style hosts): compile a C99 probe against it with gcc and
+    compare sizeof / offsetof of every struct that crosses the boundary with the ctypes Structures of _lib.py."""
+    import ctypes
+    import subprocess
+    from ophelia_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    structs = {"oph_act": _lib.Act, "oph_guide": _lib.Guide, "oph_ar_layer": _lib.ArLayer}
+    lines = []
+    for cname, cls in structs.items():
+        fields = [f[0] for f in cls._fields_]
+        fmt = " ".join(["%zu"] * (len(fields) + 1))
+        args = ", ".join(["sizeof(%s)" % cname] + ["offsetof(%s, %s)" % (cname, f) for f in fields])
+        lines.append('    printf("%s %s\\n", %s);' % (cname, fmt, args))
+    src = tmp_path / "abi_probe.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "ophelia_b200.h"\nint main(void) {\n%s\n    return 0;\n}\n'
+                   % "\n".join(lines))
+    exe = str(tmp_path / "abi_probe")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(root, "include"), str(src), "-o", exe])
+    out = subprocess.check_output([exe]).decode().split("\n")
+    seen = {}
+    for line in out:
+        if line.strip():
+            name, *nums = line.split()
+            seen[name] = [int(n) for n in nums]
+    for cname, cls in structs.items():
+        expect = [ctypes.sizeof(cls)] + [getattr(cls, f[0]).offset for f in cls._fields_]
+        assert seen[cname] == expect, (cname, seen[cname], expect)
