@@ -184,3 +184,25 @@ def test_attention_diagnostics_known_answers():
     assert abs(syn.getCDP(uni) - np.log(1.0 + (1.0 - 8.0 / 5) ** 2)) < 1e-12
     padded = np.vstack([eye, np.zeros((3, 6))])                      # trailing symbols without attention are ignored
     assert syn.getCDP(padded) == 0.0 and syn.getAP(padded) == (0.0, 0.0)
+
+
+def test_prepare_attention_guides_writes_what_get_batch_reads(tmp_path):
+    """prepare_attention_guides.py: one 8-bit guide per training utterance, shaped [symbols, coarse frames], equal to the
+    analytic guide up to the 1/255 quantisation; get_batch then serves them."""
+    import shutil
+    from ophelia_b200.data_load import get_batch, load_data, read_floats_from_8bit
+    from ophelia_b200.prepare_attention_guides import prepare_attention_guides
+    from ophelia_b200.utils import get_attention_guide
+    cfg, hp = make_corpus(tmp_path)
+    shutil.rmtree(hp.attention_guide_dir)
+    written = prepare_attention_guides(hp, ncores=2)
+    data = load_data(hp)
+    assert len(written) == len(data['fpaths']) == 11
+    for fpath, n in zip(data['fpaths'], data['text_lengths']):
+        base = os.path.basename(fpath).replace(".wav", ".npy")
+        t = np.load(os.path.join(hp.coarse_audio_dir, base)).shape[0]
+        g = read_floats_from_8bit(os.path.join(hp.attention_guide_dir, base))
+        ref = get_attention_guide(n, t, g=hp.g)
+        assert g.shape == (n, t) and (g <= ref + 1e-7).all() and (ref - g).max() < 1.0 / 255 + 1e-6
+    b = next(get_batch(hp, 4, need=('text', 'mel'), seed=0))
+    assert b['attention_guide'].shape[0] == 4 and float(b['attention_guide'].max()) <= 1.0
