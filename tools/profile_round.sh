@@ -17,4 +17,8 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:hc_p
 timeout 300 python tools/perf_layer.py --op attn_fwd --iters 2 > /dev/null 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16x3 -s 6 -c 1 -f -o gpurun_out/${R}_gemm_attn_qk \
     python tools/perf_layer.py --op attn_fwd --iters 2 > gpurun_out/ncu_${R}_attn.log 2>&1
+# incremental autoregressive route: launch list of ~2 frame steps (eager) and per-frame timing of the graph replays
+timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 3400 -c 80 --csv \
+    --log-file gpurun_out/launches_ar_${R}.csv python tools/ar_probe.py --frames 120 > gpurun_out/ar_probe_ncu_${R}.log 2>&1
+timeout 120 python tools/ar_probe.py --graph > gpurun_out/ar_probe_${R}.log 2>&1
 ls -la gpurun_out/ | tail -8
