@@ -117,3 +117,19 @@ def test_incremental_frame_step_equals_full_recomputation():
     Yn, tn, an = incremental_loop(hp, P, K, V, np.array([99, 99]), synth, cache_decoder=True)
     Yr, tr, ar = on.synth_codedtext2mel(hp, P, K, V, np.array([99, 99]))
     assert maxabs(Yn[:, 0], Yr[:, 0]) < 1e-9 and maxabs(Yn, Yr) > 1e-2
+
+
+def test_cluster_moment_combination_equals_two_pass_layer_norm():
+    """ar_encoder_kernel: each of the 8 CTAs of a cluster owns C / 8 channels and contributes (mean, sum of squared
+    deviations) of its slice; mean = average of the slice means, M2 = sum M2_r + (C / 8) sum (mean_r - mean)^2 (Chan et
+    al.).  Same moments as the two global passes of tf.nn.moments, including for badly centred rows."""
+    rng = np.random.default_rng(0)
+    for C, offset in ((256, 0.0), (512, 300.0), (256, -1e4)):
+        z = rng.normal(size=(5, C)) * 3.0 + offset
+        parts = z.reshape(5, 8, C // 8)
+        m_r = parts.mean(-1)
+        M2_r = ((parts - m_r[..., None]) ** 2).sum(-1)
+        mean = m_r.mean(-1)
+        M2 = M2_r.sum(-1) + (C // 8) * ((m_r - mean[:, None]) ** 2).sum(-1)
+        np.testing.assert_allclose(mean, z.mean(-1), rtol=1e-12)
+        np.testing.assert_allclose(M2 / C, z.var(-1), rtol=1e-9)
