@@ -104,6 +104,30 @@ def _validation_set(hp, model_type):
     return valid_filenames, inputs, validation_mags, validation_text, validation_mels
 
 
+def initialise_from_existing(store, hp):
+    """train.py:209-223: `hp.initialise_weights_from_existing = [(scope, checkpoint prefix), ...]` overwrites the variables
+    under each scope (e.g. 'Text2Mel/AudioEnc', from a babbler or another voice) with the values of that checkpoint; scopes
+    that match nothing in this model are reported and skipped (a t2m run looking at an SSRN entry)."""
+    from . import tf_checkpoint
+    if not hp.initialise_weights_from_existing:
+        return []
+    loaded = []
+    info('=====Initialise some variables from existing model(s)=====')
+    for (scope, checkpoint) in hp.initialise_weights_from_existing:
+        names = store.names(scope)
+        info('----From existing model %s:----' % (checkpoint))
+        if names:
+            values = tf_checkpoint.read_checkpoint(checkpoint, names=names)
+            store.load_state_dict(values, strict=True)
+            for name in names:
+                info('   %s' % (name))
+            loaded.extend(names)
+        else:
+            info('   No variables!')
+        info('========================================================')
+    return loaded
+
+
 def _dist_env():
     """(rank, world, process group) when launched by torchrun, else (0, 1, None)."""
     if "WORLD_SIZE" not in os.environ or int(os.environ["WORLD_SIZE"]) == 1:
@@ -156,19 +180,7 @@ def train(hp, model_type, max_steps_per_epoch=None):
     os.makedirs(logdir + '/archive/', exist_ok=True)
 
     sess = Session()
-    if hp.initialise_weights_from_existing:                       # train.py:209-223
-        info('=====Initialise some variables from existing model(s)=====')
-        for (scope, checkpoint) in hp.initialise_weights_from_existing:
-            names = g.store.names(scope)
-            info('----From existing model %s:----' % (checkpoint))
-            if names:
-                values = tf_checkpoint.read_checkpoint(checkpoint, names=names)
-                g.store.load_state_dict(values, strict=True)
-                for name in names:
-                    info('   %s' % (name))
-            else:
-                info('   No variables!')
-            info('========================================================')
+    initialise_from_existing(g.store, hp)
     assert not getattr(hp, "restart_from_savepath", []), "hp.restart_from_savepath: restore with initialise_weights_from_existing"
     if world > 1:                                                 # one set of initial weights on every rank
         import torch.distributed as dist

@@ -206,3 +206,34 @@ def test_prepare_attention_guides_writes_what_get_batch_reads(tmp_path):
         assert g.shape == (n, t) and (g <= ref + 1e-7).all() and (ref - g).max() < 1.0 / 255 + 1e-6
     b = next(get_batch(hp, 4, need=('text', 'mel'), seed=0))
     assert b['attention_guide'].shape[0] == 4 and float(b['attention_guide'].max()) <= 1.0
+
+
+def test_initialise_weights_from_existing(tmp_path):
+    """train.py:209-223: variables under the listed scopes come from other checkpoints, everything else keeps its
+    initial value; a scope that matches nothing is skipped."""
+    from ophelia_b200 import tf_checkpoint
+    from ophelia_b200 import train as drv
+    from ophelia_b200.configuration import default_hparams
+    from ophelia_b200.variables import VariableStore
+
+    def store(seed):
+        st = VariableStore("cpu", seed=seed)
+        st.declare("Text2Mel/AudioEnc/C_1/conv1d/kernel", (1, 8, 16), "kernel")
+        st.declare("Text2Mel/AudioEnc/C_1/conv1d/bias", (16,), "zeros")
+        st.declare("Text2Mel/AudioDec/C_1/conv1d/kernel", (1, 16, 8), "kernel")
+        return st.finalize(with_optimizer=True)
+    donor, target = store(1), store(2)
+    donor.vars["Text2Mel/AudioEnc/C_1/conv1d/bias"].fill_(0.25)
+    prefix = str(tmp_path / "donor" / "model_epoch_3")
+    os.makedirs(os.path.dirname(prefix))
+    tf_checkpoint.save(donor, prefix)
+    before = target.state_dict()
+    hp = default_hparams(initialise_weights_from_existing=[("Text2Mel/AudioEnc", prefix), ("SSRN", prefix)])
+    loaded = drv.initialise_from_existing(target, hp)
+    assert sorted(loaded) == ["Text2Mel/AudioEnc/C_1/conv1d/bias", "Text2Mel/AudioEnc/C_1/conv1d/kernel"]
+    after, src = target.state_dict(), donor.state_dict()
+    for n in loaded:
+        assert np.array_equal(after[n], src[n])
+    n = "Text2Mel/AudioDec/C_1/conv1d/kernel"
+    assert np.array_equal(after[n], before[n]) and not np.array_equal(after[n], src[n])
+    assert drv.initialise_from_existing(target, default_hparams()) == []
