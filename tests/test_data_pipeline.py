@@ -237,3 +237,41 @@ def test_initialise_weights_from_existing(tmp_path):
     n = "Text2Mel/AudioDec/C_1/conv1d/kernel"
     assert np.array_equal(after[n], before[n]) and not np.array_equal(after[n], src[n])
     assert drv.initialise_from_existing(target, default_hparams()) == []
+
+
+def _graph_shard_worker(rank, world, port, cfg, out):
+    """One data-parallel rank: a training graph built without `data=` (architectures.py:38-44) must read its own slice of
+    the shuffled utterance stream.  The variable store lives on the CPU here: nothing is stepped."""
+    import torch.distributed as dist
+    from ophelia_b200.architectures import Text2MelGraph
+    from ophelia_b200.configuration import load_config
+    from ophelia_b200.variables import VariableStore
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    hp = load_config(cfg)
+    g = Text2MelGraph(hp, mode="train", store=VariableStore("cpu"), device="cpu", process_group=dist.group.WORLD)
+    src = g.batch_source
+    assert (src.rank, src.world) == (rank, world) and 'mag' not in src.need and src.with_guides
+    n = len(src.fpaths)
+    mine = [src._next_index() for _ in range(n // world)]            # this rank's share of the first epoch
+    batch = next(src)
+    assert set(batch) >= {"text", "mel", "attention_guide", "fname"} and "mag" not in batch
+    out.put((rank, mine, g.num_batch))
+    dist.destroy_process_group()
+
+
+def test_training_graphs_of_two_ranks_read_disjoint_shards(tmp_path):
+    import torch.multiprocessing as mp
+    cfg, hp = make_corpus(tmp_path, n_utts=26, n_valid=2)
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_graph_shard_worker, args=(r, 2, port, cfg, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    got = sorted(out.get(timeout=5) for _ in range(2))
+    (r0, idx0, nb0), (r1, idx1, nb1) = got
+    assert (r0, r1) == (0, 1) and nb0 == nb1 == 24 // 4
+    assert not set(idx0) & set(idx1) and len(set(idx0) | set(idx1)) == 24
