@@ -54,10 +54,13 @@ def deemphasis(wav, preemphasis):
 
 def spectrogram2wav(hp, mag, trim_output=False, device=None, dtype=torch.float32):
     """utils.py:69-96.  mag: normalised magnitudes [frames, 1 + n_fft // 2] in [0, 1] (SSRN output); returns float32
-    samples.  `device` defaults to the GPU when there is one."""
+    samples.  Runs on the GPU; there is no silent CPU fallback (tests pass device='cpu' explicitly to compare the same
+    code with the numpy restatement)."""
     assert not trim_output, "librosa.effects.trim is outside the path (the generation loop already stops at the sentence end)"
     if device is None:
-        device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
+        if not torch.cuda.is_available():
+            raise RuntimeError("spectrogram2wav: no CUDA device (pass device='cpu' explicitly for an offline check)")
+        device = torch.device("cuda")
     mag = torch.as_tensor(np.ascontiguousarray(mag), dtype=dtype).to(device).t()
     mag = torch.clamp(mag, 0, 1) * hp.max_db - hp.max_db + hp.ref_db          # de-normalise (dB)
     mag = torch.pow(10.0, mag * 0.05)                                          # to amplitude
