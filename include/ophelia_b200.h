@@ -55,7 +55,10 @@ unsigned int oph_crc32c(const void* data, unsigned long long n, unsigned int crc
 #define OPH_TAG_ATTENTION 4
 #define OPH_TAG_ROW_FWD 5   /* LayerNorm / highway forward tails: third value = algorithmic BYTES */
 #define OPH_TAG_ROW_BWD 6
-#define OPH_NUM_TAGS 7
+#define OPH_TAG_HC_FWD 7      /* the forward GEMM of a highway-conv layer (conv tag 1 = the other conv layers) */
+#define OPH_TAG_HC_ROW_FWD 8  /* the highway tail of oph_hc_fwd when it runs as its own launch: BYTES */
+#define OPH_TAG_AR_ENC 9      /* oph_ar_encoder_step: third value = fp32 weight BYTES streamed per launch */
+#define OPH_NUM_TAGS 10
 long long oph_launch_count(void);
 /* diagnostics: device buffer long long[74][8]; every GEMM launch overwrites per CTA pair
  * (total cycles, cycles waiting for an accumulator stage, for A, for B, k-blocks). NULL disables. */
@@ -143,6 +146,17 @@ int oph_conv1d_bwd(const float* dy, long long lddy, const oph_act* x, const floa
                    long long lddz, float* dx, long long lddx, float* dw, float* dbias, float* dgamma, float* dbeta,
                    int B, int L, int Cin, int Cout, int k, int rate, int padding, int in_shift, int act, int norm,
                    float drop_p, uint64_t seed, const long long* step, oph_stream_t stream);
+
+/* ---- modules.normalize (modules.py:47-75) on its own: layer norm over the channels (eps 1e-12, biased variance) --
+ * y = LN(x) * gamma + beta for `rows` rows of C channels; stats [rows][2] = (mean, rstd) (nullable; needed by bwd);
+ * y's planes are written when given.  Inside conv1d / hc / conv1d_transpose the same arithmetic is fused into the
+ * layer's tail; this entry point serves direct calls of the reference function. */
+int oph_normalize_fwd(const float* x, long long ldx, const float* gamma, const float* beta, const oph_act* y,
+                      float* stats, long long rows, int C, oph_stream_t stream);
+/* dx = gradient w.r.t. x (fp32, overwritten); dgamma / dbeta are ACCUMULATED into. */
+int oph_normalize_bwd(const float* dy, long long lddy, const float* x, long long ldx, const float* stats,
+                      const float* gamma, const float* beta, float* dx, long long lddx, float* dgamma, float* dbeta,
+                      long long rows, int C, oph_stream_t stream);
 
 /* ---- modules.hc (modules.py:148-207): highway conv, C -> 2C -> C ------------------------------------------
  * z [B*L][ldz] (>= 2C wide) pre-LN conv output; stats [B*L][4] = (mean1, rstd1, mean2, rstd2).

@@ -53,6 +53,8 @@ SIGNATURES = {
     "oph_conv1d_fwd": (I, [AP, P, P, P, P, P, LL, P, AP, P, LL, I, I, I, I, I, I, I, I, I, I, F, U64, P, P]),
     "oph_conv1d_bwd": (I, [P, LL, AP, P, LL, P, P, P, P, P, LL, P, LL, P, P, P, P,
                            I, I, I, I, I, I, I, I, I, I, F, U64, P, P]),
+    "oph_normalize_fwd": (I, [P, LL, P, P, AP, P, LL, I, P]),
+    "oph_normalize_bwd": (I, [P, LL, P, LL, P, P, P, P, LL, P, P, LL, I, P]),
     "oph_hc_fwd": (I, [AP, P, P, P, P, P, P, P, LL, P, AP, I, I, I, I, I, I, I, F, U64, P, P]),
     "oph_hc_bwd": (I, [P, LL, AP, P, LL, P, P, P, P, P, P, P, LL, P, LL, P, LL, P, P, P, P, P, P,
                        I, I, I, I, I, I, I, F, U64, P, P]),

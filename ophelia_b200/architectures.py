@@ -17,7 +17,7 @@ import torch
 from . import ops
 from .modules import Tape
 from .networks import SSRN, Attention, AudioDec, AudioEnc, TextEnc
-from .variables import VariableStore, use_store, variable_scope
+from .variables import VariableStore, mix_dropout_seed, use_store, variable_scope
 
 _default_stores = {}
 
@@ -92,6 +92,18 @@ def ssrn_variables(hp):
     return out
 
 
+def filter_variables_for_update(store, update_weights):
+    """architectures.py:436-443: the variables whose TF name (`<scope path>:0`) matches one of the patterns from its
+    start (tf.get_collection filters with re.match), in creation order, each once."""
+    import re
+    to_train = []
+    for pattern_string in update_weights:
+        for name in store.specs:
+            if re.match(pattern_string, name + ":0") and name not in to_train:
+                to_train.append(name)
+    return to_train
+
+
 class Node(object):
     """Symbolic handle standing in for a tf.Tensor / tf.placeholder / tf.Operation of the reference graph."""
     __slots__ = ("graph", "name")
@@ -137,6 +149,13 @@ class Graph(object):
                 store = VariableStore(self.device, seed=getattr(hp, "seed", 0))
                 _default_stores[key] = store
         self.store = store
+        if self.training:               # dropout masks: another hp.seed or another data-parallel rank, another sequence
+            rank = 0
+            if process_group is not None:
+                import torch.distributed as dist
+                rank = dist.get_rank(process_group)
+            store.dropout_seed = mix_dropout_seed(getattr(hp, "seed", 0), rank)
+            store.hp = hp               # the checkpoint writer stores Adam's beta powers next to the slots
         self.store.declare_all(self.variable_specs(hp))
         self.store.finalize(with_optimizer=self.training)
         for n in self.node_names:
@@ -167,9 +186,32 @@ class Graph(object):
             self.num_batch = getattr(data, "num_batch", getattr(self.hp, "num_batch", 1))
 
     def build_training_scheme(self):
+        """architectures.py:96-131.  hp.update_weights (a list of regular expressions matched against the variable names
+        like tf.get_collection(TRAINABLE_VARIABLES, pattern), :113-120 and :436-443) restricts the optimiser to the matching
+        variables: the others stay frozen, bit for bit, and global_step still advances.  The flat parameter buffer keeps
+        the variables in creation order, so the trainable set is a short list of contiguous ranges and the fused
+        clip + Adam kernel runs once per range."""
         hp = self.hp
-        assert not hp.update_weights, "hp.update_weights (partial fine-tuning) is outside the path"
         self.lr0 = hp.lr
+        self.train_ranges = None
+        if hp.update_weights:
+            train_variables = filter_variables_for_update(self.store, hp.update_weights)
+            print('Subset of trainable variables chosen for finetuning.')
+            print('Variables not in this list will remain frozen:')
+            for name in train_variables:
+                print(name + ":0")
+            chosen = set(train_variables)
+            ranges = []
+            for name, (shape, _k) in self.store.specs.items():
+                if name not in chosen:
+                    continue
+                o = self.store.offsets[name]
+                end = o + (int(np.prod(shape)) + 3) // 4 * 4
+                if ranges and ranges[-1][1] == o:
+                    ranges[-1][1] = end
+                else:
+                    ranges.append([o, end])
+            self.train_ranges = [tuple(r) for r in ranges]
 
     # ---- side streams: independent chains (TextEnc || AudioEnc) and weight-gradient GEMMs overlap the main chain;
     #      everything is joined back before the optimiser step, so callers (and CUDA-graph capture) see one stream
@@ -203,7 +245,12 @@ class Graph(object):
             from .parallel import allreduce_gradients
             scale = allreduce_gradients(st.grad_flat, self.process_group)  # NCCL sum over NVLink; only collective
         ops.adam_prepare(st.global_step, st.lr_t, hp.lr, hp.beta1, hp.beta2, hp.decay_lr)
-        ops.adam_clip(st.flat, st.m_flat, st.v_flat, st.grad_flat, st.lr_t, hp.beta1, hp.beta2, hp.epsilon, 1.0, scale)
+        if self.train_ranges is None:
+            ops.adam_clip(st.flat, st.m_flat, st.v_flat, st.grad_flat, st.lr_t, hp.beta1, hp.beta2, hp.epsilon, 1.0, scale)
+        else:                       # hp.update_weights: only the chosen variables move
+            for a, b in self.train_ranges:
+                ops.adam_clip(st.flat[a:b], st.m_flat[a:b], st.v_flat[a:b], st.grad_flat[a:b], st.lr_t, hp.beta1, hp.beta2,
+                              hp.epsilon, 1.0, scale)
         ops.step_inc(st.global_step)
         st.version += 1
         st.repack_all()             # one launch refreshes every split-bf16 weight image for the next step
@@ -260,7 +307,7 @@ class Graph(object):
         if getattr(self, "_copy_stream", None) is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
         with torch.cuda.stream(self._copy_stream):
-            dev = tuple(self._to_device(batch[k], dt) for k, dt in fields)
+            dev = tuple(self._to_device(batch[k], dt, ids=(k == "text")) for k, dt in fields)
             ev = torch.cuda.Event()
             ev.record(self._copy_stream)
         for t in dev:
@@ -278,7 +325,13 @@ class Graph(object):
             self._prefetched = None
         return dev
 
-    def _to_device(self, x, dtype):
+    def _to_device(self, x, dtype, ids=False):
+        if ids and not (isinstance(x, torch.Tensor) and x.is_cuda):
+            # symbol ids assembled on the host: the embedding kernels index the table without a bounds check
+            # (tf.nn.embedding_lookup raises on the CPU for ids outside the table)
+            hi = int(x.max()) if len(x) else 0
+            lo = int(x.min()) if len(x) else 0
+            assert 0 <= lo and hi < len(self.hp.vocab), "symbol id %d outside the vocabulary of %d" % (hi if hi >= len(self.hp.vocab) else lo, len(self.hp.vocab))
         if isinstance(x, torch.Tensor):
             return x.to(self.device, dtype, non_blocking=True)
         return torch.as_tensor(np.ascontiguousarray(x)).to(self.device, dtype, non_blocking=True)
@@ -362,7 +415,7 @@ class Text2MelGraph(Graph):
 
     # architectures.py:188-239
     def build_model(self, L, mels, training, K=None, V=None, prev_max_attentions=None, att_acc=None,
-                    want_alignments=True, tapes=None, text_stream=None, gts=None, extra=None):
+                    want_alignments=True, tapes=None, text_stream=None, gts=None, extra=None, text_lengths=None):
         hp = self.hp
         mono = self.mode == 'synthesize'
         out = {}
@@ -387,14 +440,15 @@ class Text2MelGraph(Graph):
             with variable_scope("Attention"), on(t_dec):
                 R, alignments, max_attentions = Attention(
                     hp, Q, K, V, monotonic_attention=mono, prev_max_attentions=prev_max_attentions if mono else None,
-                    training=training, att_acc=att_acc, want_alignments=want_alignments, gts=gts, extra=extra)
+                    training=training, att_acc=att_acc, want_alignments=want_alignments, gts=gts, extra=extra,
+                    text_lengths=text_lengths)
             with variable_scope("AudioDec"), on(t_dec):
                 Y_logits, Y = AudioDec(hp, R, training=training, speaker_codes=None, reuse=self.reuse)
         out.update(K=K, V=V, Q=Q, R=R, alignments=alignments, max_attentions=max_attentions, Y_logits=Y_logits, Y=Y)
         return out
 
     def encode_text(self, feeds):
-        L = self._to_device(feeds["L"], torch.int32)
+        L = self._to_device(feeds["L"], torch.int32, ids=True)
         with use_store(self.store), variable_scope("Text2Mel"), variable_scope("TextEnc"):
             K, V = TextEnc(self.hp, L, training=False, speaker_codes=None, reuse=self.reuse)
         return {"L": L, "K": K, "V": V}
@@ -406,7 +460,7 @@ class Text2MelGraph(Graph):
             K = self._to_device(feeds["K"], torch.float32)
             V = self._to_device(feeds["V"], torch.float32)
         else:
-            L = self._to_device(feeds["L"], torch.int32)
+            L = self._to_device(feeds["L"], torch.int32, ids=True)
         if self.mode == 'synthesize':
             prev = self._to_device(feeds["prev_max_attentions"], torch.int32)
         out = self.build_model(L, mels, False, K=K, V=V, prev_max_attentions=prev, want_alignments=want_alignments)
@@ -422,7 +476,7 @@ class Text2MelGraph(Graph):
         if batch is None:
             inputs = self._next_inputs(tuple(fields))
         else:
-            inputs = tuple(self._to_device(batch[k], dt) for k, dt in fields)
+            inputs = tuple(self._to_device(batch[k], dt, ids=(k == "text")) for k, dt in fields)
         return self._step_maybe_graphed(*inputs)
 
     def train_step_device(self, L, mels, gts=None):

@@ -710,6 +710,24 @@ int oph_conv1d_bwd(const float* dy, long long lddy, const oph_act* x, const floa
     return OPH_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ normalize
+// modules.normalize (modules.py:47-75) on its own: the conv tail without a conv in front of it.
+int oph_normalize_fwd(const float* x, long long ldx, const float* gamma, const float* beta, const oph_act* y, float* stats,
+                      long long rows, int C, oph_stream_t stream) {
+    if (!x || !gamma || !beta || !y || !y->f32 || rows < 1 || C < 1) return fail(OPH_EINVAL, "normalize_fwd: missing operand%s");
+    return launch_ln_act_fwd(x, ldx, gamma, beta, y, nullptr, 0, stats, rows, C, OPH_ACT_NONE, 1, 0.f, 0, nullptr, S(stream));
+}
+// dx (fp32) = dLN/dx . dy; dgamma / dbeta are accumulated into.  stats from the forward call.
+int oph_normalize_bwd(const float* dy, long long lddy, const float* x, long long ldx, const float* stats,
+                      const float* gamma, const float* beta, float* dx, long long lddx, float* dgamma, float* dbeta,
+                      long long rows, int C, oph_stream_t stream) {
+    if (!dy || !x || !stats || !gamma || !beta || !dx || !dgamma || !dbeta) return fail(OPH_EINVAL, "normalize_bwd: missing operand%s");
+    launch_cfg(rows_grid(rows, 8), 256, 3 * (size_t)C * sizeof(float), S(stream))(ln_act_bwd_kernel, dy, lddy, x, ldx, stats, gamma, beta,
+        dx, lddx, (unsigned short*)nullptr, (unsigned short*)nullptr, 0ll, dgamma, dbeta, (float*)nullptr, (int)rows, C, OPH_ACT_NONE, 1,
+        0.f, 0ull, (const long long*)nullptr);
+    return check_launch("ln_act_bwd_kernel");
+}
+
 // ------------------------------------------------------------------------------------------------ highway conv
 int oph_hc_fwd(const oph_act* x, const void* packed_w, const float* bias, const float* g1, const float* b1,
                const float* g2, const float* b2, float* z, long long ldz, float* stats, const oph_act* y, int B, int L,
@@ -723,14 +741,14 @@ int oph_hc_fwd(const oph_act* x, const void* packed_w, const float* bias, const 
     set_operand(g.A, x); g.A.L = L; g.A.Ls = L; g.A.mul = 1;
     conv_offsets(k, rate, padding, 0, g.A.off);
     g.Bpacked = packed_w; g.M = B * L; g.N = 2 * C; g.Kc = C; g.ntaps = k;
-    g.C = z; g.ldc = ldz; g.bias = bias; g.tag = OPH_TAG_CONV_FWD;
+    g.C = z; g.ldc = ldz; g.bias = bias; g.tag = OPH_TAG_HC_FWD;
     g.zero_bytes = (size_t)B * L * ldz * sizeof(float);        // z is ours to overwrite: remainder units may be K-split
     OPH_TRY(launch_gemm(g, 1, S(stream)));
     const long long rows = (long long)B * L;
     const int grid = rows_grid(rows, 8);
     const bool vec = vec_ok(C, ldz, x->ld, y->ld);
     if (y->hi && !(vec && !(y->ldp & 7))) return fail(OPH_EINVAL, "hc_fwd: output planes need C in {256,512,1024}%s");
-    ProfScope ps(OPH_TAG_ROW_FWD, (double)rows * C * (y->hi ? 20.0 : 16.0), S(stream));
+    ProfScope ps(OPH_TAG_HC_ROW_FWD, (double)rows * C * (y->hi ? 20.0 : 16.0), S(stream));
     if (vec && norm && !(g_gemm_dbg_flags_host & 4096)) {
         const int wpr = C / 256, groups = 8 / wpr;
         const int depth = ((g_gemm_dbg_flags_host & 8192) || C > 256) ? 3 : 2;         // ring slots per warp
@@ -1113,6 +1131,9 @@ int oph_ar_encoder_step(const oph_ar_layer* layers, int nlayers, int B, const in
         d.x_item = s.x_item; d.ldx = s.ldx; d.y_item = s.y_item; d.ldy = s.ldy;
         d.Cin = s.Cin; d.C = s.C; d.k = s.k; d.rate = s.rate; d.kind = s.kind; d.act = s.act; d.in_shift = s.in_shift;
     }
+    double wbytes = 0.0;
+    for (int i = 0; i < nlayers; ++i) wbytes += 4.0 * layers[i].k * layers[i].Cin * layers[i].C * (layers[i].kind ? 2 : 1);
+    ProfScope ps(OPH_TAG_AR_ENC, wbytes, S(stream));
     launch_cfg(dim3(AR_ENC_CLUSTER, B), AR_ENC_THREADS, 0, S(stream))(ar_encoder_kernel, a, frame);
     return check_launch("ar_encoder_kernel");
 }

@@ -100,9 +100,27 @@ def embed(inputs, vocab_size, num_units, zero_pad=True, scope="embedding", reuse
 
 
 def normalize(inputs, scope="normalize", reuse=None, normtype='layer'):
-    """modules.py:47-75 exists only fused into conv1d / hc / conv1d_transpose here (layer norm over channels,
-    eps 1e-12); a stand-alone call is not part of the hot path."""
-    raise NotImplementedError("normalize() is fused into conv1d/hc/conv1d_transpose on this path")
+    """modules.py:47-75: layer norm over the last axis (tf.contrib.layers.layer_norm: biased variance, eps 1e-12, gamma /
+    beta of shape [C] under `scope`), or the identity for normtype None.  Inside conv1d / hc / conv1d_transpose the same
+    arithmetic runs fused into the layer's tail; this is the stand-alone function (one launch)."""
+    assert normtype in (None, 'layer'), "batch norm is unused by every shipped config"
+    if normtype is None:
+        return inputs
+    store = get_store()
+    C = inputs.shape[-1]
+    with variable_scope(scope, reuse=reuse):
+        gn, ben = scoped("gamma"), scoped("beta")
+        store.declare(ben, (C,), "zeros")
+        store.declare(gn, (C,), "ones")
+    store.finalize()
+    gamma, beta = store.get(gn), store.get(ben)
+    rec = Tape.current is not None
+    y, stats = ops.normalize_fwd(inputs, gamma, beta, save=rec)
+    if rec:
+        def bwd(dy):
+            return ops.normalize_bwd(dy, inputs, stats, gamma, beta, store.grad(gn), store.grad(ben))
+        _record(bwd)
+    return y
 
 
 # ------------------------------------------------------------------------------------------------ conv1d
@@ -133,7 +151,7 @@ def conv1d(inputs, filters=None, size=1, rate=1, padding="SAME", dropout_rate=0,
     act = ops.ACT_RELU if activation_fn == relu else ops.ACT_NONE
     pad = _padding_code(padding)
     drop = float(dropout_rate) if training else 0.0
-    seed = layer_seed(kn)
+    seed = layer_seed(kn, store)
     step = _step_ptr(store, training)
     rec = _recording(training)
     y, ysig, saved = ops.conv1d_fwd(inputs, pk, store.get(bn), gamma, beta, rate, pad, in_shift, act, norm, drop, seed,
@@ -178,7 +196,7 @@ def hc(inputs, filters=None, size=1, rate=1, padding="SAME", dropout_rate=0, use
     g1, b1, g2, b2 = ([store.get(n) for n in names] if norm else [None] * 4)
     pad = _padding_code(padding)
     drop = float(dropout_rate) if training else 0.0
-    seed = layer_seed(kn)
+    seed = layer_seed(kn, store)
     step = _step_ptr(store, training)
     rec = _recording(training)
     y, saved = ops.hc_fwd(inputs, pk, store.get(bn), g1, b1, g2, b2, rate, pad, norm, drop, seed, step, save=rec, y=out,
@@ -214,7 +232,7 @@ def conv1d_transpose(inputs, filters=None, size=3, stride=2, padding='same', dro
     pk = _packed(store, kn, deconv=True)
     gamma, beta = store.get(gn), store.get(ben)
     drop = float(dropout_rate) if training else 0.0
-    seed = layer_seed(kn)
+    seed = layer_seed(kn, store)
     step = _step_ptr(store, training)
     rec = _recording(training)
     y, saved = ops.deconv_fwd(inputs, pk, store.get(bn), gamma, beta, drop, seed, step, save=rec)

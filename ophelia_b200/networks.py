@@ -97,7 +97,7 @@ def AudioEnc(hp, S, training=True, speaker_codes=None, reuse=None, *, in_shift=0
 
 
 def Attention(hp, Q, K, V, monotonic_attention=False, prev_max_attentions=None, *, training=False, att_acc=None,
-              want_alignments=True, gts=None, extra=None):
+              want_alignments=True, gts=None, extra=None, text_lengths=None):
     '''
     Args:
       Q: Queries. (B, T/r, d)   K: Keys. (B, N, d)   V: Values. (B, N, d)
@@ -120,8 +120,15 @@ def Attention(hp, Q, K, V, monotonic_attention=False, prev_max_attentions=None, 
         if getattr(hp, "turn_off_monotonic_for_synthesis", False):
             # no window: only the keys past each sentence's end are masked (networks.py:307-309; synthesize.py:505-507
             # sets hp.text_lengths = first padding position + 1 for the batch being synthesised)
-            assert len(hp.text_lengths) == B, "hp.text_lengths must describe the batch (synthesize.py:505-507)"
-            prev = torch.as_tensor(np.asarray(hp.text_lengths), dtype=torch.int32).to(Q.device)
+            # text_lengths: the same numbers already on the device (int32 [B]); callers that capture this forward pass
+            # into a CUDA graph keep them in a static buffer they refresh per batch (an upload here would be illegal
+            # inside the capture and would freeze the first batch's lengths into the graph)
+            if text_lengths is not None:
+                assert text_lengths.dtype == torch.int32 and text_lengths.is_cuda and text_lengths.numel() == B
+                prev = text_lengths
+            else:
+                assert len(hp.text_lengths) == B, "hp.text_lengths must describe the batch (synthesize.py:505-507)"
+                prev = torch.as_tensor(np.asarray(hp.text_lengths), dtype=torch.int32).to(Q.device)
             win = 0
         else:
             prev = prev_max_attentions.to(torch.int32).contiguous()

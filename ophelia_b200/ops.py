@@ -191,6 +191,24 @@ def conv1d_bwd(dy, x, saved, pk, gamma, beta, dw, dbias, dgamma, dbeta, rate=1, 
     return dx if need_dx else None
 
 
+# ---------------------------------------------------------------------------------------------- normalize
+def normalize_fwd(x, gamma, beta, save=False, planes=False):
+    ldx, B, L, C = _rows(x)
+    y = new_act(B, L, C, x.device)
+    stats = torch.empty(B * L, 2, device=x.device, dtype=torch.float32) if save else None
+    _lib.call("oph_normalize_fwd", _p(x), ldx, _p(gamma), _p(beta), _out_act(y, planes), _p(stats), B * L, C, _stream())
+    return y, stats
+
+
+def normalize_bwd(dy, x, stats, gamma, beta, dgamma, dbeta):
+    ldx, B, L, C = _rows(x)
+    lddy = _rows(dy)[0]
+    dx = new_act(B, L, C, x.device)
+    _lib.call("oph_normalize_bwd", _p(dy), lddy, _p(x), ldx, _p(stats), _p(gamma), _p(beta), _p(dx), dx.stride(1),
+              _p(dgamma), _p(dbeta), B * L, C, _stream())
+    return dx
+
+
 # ---------------------------------------------------------------------------------------------- highway conv
 def hc_fwd(x, pk, bias, g1, b1, g2, b2, rate=1, padding=SAME, norm=True, drop_p=0.0, seed=0, step=None,
            save=False, y=None, planes=True, y_planes=None):
@@ -389,8 +407,13 @@ def attention_bwd(dR, Q, K, V, A, dq_addend=None, att_coef=0.0, maxN=1, maxT=1, 
 # ---------------------------------------------------------------------------------------------- losses / optimiser
 def recon_loss(logits, target, acc, squash, w_l1, w_bd, w_l2, want_grad=True):
     ldl, B, L, C = _rows(logits)
+    # the kernel pairs row r of the logits with row r of the target: a target of another length (features not padded
+    # to r * T, a truncated .npy) would pair rows of different utterances -- TF raises a shape error here, so do we
+    assert tuple(target.shape) == tuple(logits.shape), \
+        "target %s does not match the predictions %s" % (tuple(target.shape), tuple(logits.shape))
+    assert target.is_cuda and target.dtype == torch.float32 and target.stride(2) == 1
+    assert B == 1 or target.stride(0) == L * target.stride(1), "target rows must be uniformly strided"
     ldt = target.stride(1)
-    assert target.stride(2) == 1 and target.dtype == torch.float32
     dl = new_act(B, L, C, logits.device) if want_grad else None
     _lib.call("oph_recon_loss", _p(logits), ldl, _p(target), ldt, _p(dl), dl.stride(1) if want_grad else 0,
               B * L, C, int(bool(squash)), float(w_l1), float(w_bd), float(w_l2), _p(acc), _stream())

@@ -96,7 +96,7 @@ def synth_codedtext2mel_device(hp, K, V, ends, g, use_cuda_graph=True, check_eve
     # static buffers (and the captured step) are kept on the graph object per batch shape: synthesising many batches
     # re-uses them instead of capturing again
     cache = g.__dict__.setdefault("_ar_state", {})
-    key = (B, K.shape[1], K.shape[2], hp.max_T, bool(use_cuda_graph))
+    key = (B, K.shape[1], K.shape[2], hp.max_T, bool(use_cuda_graph), bool(getattr(hp, "turn_off_monotonic_for_synthesis", False)))
     st = cache.get(key)
     if st is not None and st["version"] != g.store.version:      # weights changed since the capture: packed images are stale
         st = None
@@ -121,8 +121,18 @@ def synth_codedtext2mel_device(hp, K, V, ends, g, use_cuda_graph=True, check_eve
     endcounts = np.zeros(ends.shape, dtype=int)
     t_ends = np.ones(ends.shape, dtype=int) * hp.max_T
 
+    # windowless synthesis (networks.py:307-309): the per-sentence key counts live in a static device buffer that is
+    # refreshed here, outside any capture, so a replayed graph masks with THIS batch's lengths
+    tl = None
+    if getattr(hp, "turn_off_monotonic_for_synthesis", False):
+        assert len(hp.text_lengths) == B, "hp.text_lengths must describe the batch (synthesize.py:505-507)"
+        if "tl" not in st:
+            st["tl"] = torch.zeros(B, device=dev, dtype=torch.int32)
+        tl = st["tl"]
+        tl.copy_(torch.as_tensor(np.asarray(hp.text_lengths), dtype=torch.int32))
+
     def forward():
-        return g.build_model(None, Y, False, K=Kb, V=Vb, prev_max_attentions=prev, want_alignments=True)
+        return g.build_model(None, Y, False, K=Kb, V=Vb, prev_max_attentions=prev, want_alignments=True, text_lengths=tl)
     graph, out = st["graph"], st["out"]
     if use_cuda_graph and graph is None:
         forward()                                       # warm-up outside the capture (lazy weight packing)
@@ -485,7 +495,13 @@ def synthesize(hp, speaker_id='', num_sentences=0, ncores=1, topoutdir='', t2m_e
     if hp.turn_off_monotonic_for_synthesis:
         hp.text_lengths = get_text_lengths(L) + 1
     g1 = Text2MelGraph(hp, mode="synthesize"); print("Graph 1 (t2m) loaded")
-    g2 = SSRNGraph(hp, mode="synthesize"); print("Graph 2 (ssrn) loaded")
+    # synthesize.py:513-533: a Text2Mel trained without layer norm is paired with an SSRN that has it
+    hp2 = hp
+    if hp.norm is None:
+        import copy
+        hp2 = copy.copy(hp)
+        hp2.norm = 'layer'
+    g2 = SSRNGraph(hp2, mode="synthesize"); print("Graph 2 (ssrn) loaded")
     with Session() as sess:
         if t2m_epoch > -1:
             restore_archived_model_parameters(sess, hp, 't2m', t2m_epoch, graph=g1)

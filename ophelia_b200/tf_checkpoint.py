@@ -4,7 +4,8 @@ The reference restores its voices with `tf.train.Saver().restore(sess, tf.train.
 (`synthesize.py:302-316`, `train.py:196-207`): a `<prefix>.index` file (a LevelDB-format sorted table that maps
 variable names to BundleEntryProto records) plus `<prefix>.data-00000-of-00001` (raw little-endian tensor bytes).
 The variable names and kernel layouts of `VariableStore` are the reference's, so a checkpoint written by the
-reference loads by name, and a checkpoint written here can be restored by the reference.
+reference loads by name, and a checkpoint written here can be restored by the reference (synthesize.py's restore by
+scope as well as train.py's Supervisor, which wants every global variable: Adam slots, beta powers, global_step).
 
 Formats restated from their public definitions (nothing of this can be executed against TensorFlow in this image,
 so it is pinned by round trips and by the byte-level known answers in tests/test_host.py only):
@@ -314,7 +315,11 @@ def write_checkpoint(prefix, tensors, block_size=4096):
     """Write {name: array} as a one-shard V2 checkpoint that `tf.train.Saver().restore` accepts."""
     names = sorted(tensors, key=lambda n: n.encode())
     items, offset = [], 0
-    with open(prefix + ".data-00000-of-00001", "wb") as df:
+    # both files are written under temporary names and moved into place at the end: an interrupted save never leaves a
+    # half-written checkpoint under the name the `checkpoint` state file points to
+    final_data, final_index = prefix + ".data-00000-of-00001", prefix + ".index"
+    tmp_data, tmp_index = final_data + ".tmp%d" % os.getpid(), final_index + ".tmp%d" % os.getpid()
+    with open(tmp_data, "wb") as df:
         for n in names:
             a = np.asarray(tensors[n], order="C")               # (ascontiguousarray would turn scalars into shape [1])
             code = _DTYPE_CODES.get(a.dtype)
@@ -326,7 +331,7 @@ def write_checkpoint(prefix, tensors, block_size=4096):
             offset += len(raw)
     header = bytes([0x08, 0x01, 0x1A, 0x02, 0x08, 0x01])       # num_shards = 1, (little endian), version { producer: 1 }
     items = [(b"", header)] + items
-    with open(prefix + ".index", "wb") as f:
+    with open(tmp_index, "wb") as f:
         index, cur, cur_bytes = [], [], 0
         for k, v in items:
             cur.append((k, v))
@@ -342,6 +347,8 @@ def write_checkpoint(prefix, tensors, block_size=4096):
         footer += b"\x00" * (40 - len(footer))
         footer += struct.pack("<Q", _MAGIC)
         f.write(bytes(footer))
+    os.replace(tmp_data, final_data)
+    os.replace(tmp_index, final_index)
 
 
 def latest_checkpoint(directory):
@@ -386,6 +393,8 @@ def restore(store, prefix, strict=True, with_optimizer=True):
         if "global_step" in ck:
             store.global_step.fill_(int(np.asarray(ck["global_step"]).reshape(-1)[0]))
             used.add("global_step")
+        # Adam's beta powers are functions of global_step here (adam_prepare_kernel recomputes them every step)
+        used.update(n for n in ("beta1_power", "beta2_power") if n in ck)
     return [n for n in ck if n not in used]
 
 
@@ -398,7 +407,14 @@ def save(store, prefix, with_optimizer=True):
             shape = store.specs[n][0]
             tensors["%s/Adam" % n] = store.m_flat[o:o + cnt].detach().cpu().numpy().reshape(shape).copy()
             tensors["%s/Adam_1" % n] = store.v_flat[o:o + cnt].detach().cpu().numpy().reshape(shape).copy()
-        tensors["global_step"] = np.asarray(int(store.global_step.item()), dtype=np.int32)
+        step = int(store.global_step.item())
+        tensors["global_step"] = np.asarray(step, dtype=np.int32)
+        # tf.train.AdamOptimizer's non-slot variables: train.py resumes through tf.train.Supervisor, which restores ALL
+        # global variables and fails with NotFound without them.  After t updates they hold beta^(t+1).
+        hp = getattr(store, "hp", None)
+        b1, b2 = (getattr(hp, "beta1", 0.9), getattr(hp, "beta2", 0.999)) if hp is not None else (0.9, 0.999)
+        tensors["beta1_power"] = np.asarray(b1 ** (step + 1), dtype=np.float32)
+        tensors["beta2_power"] = np.asarray(b2 ** (step + 1), dtype=np.float32)
     write_checkpoint(prefix, tensors)
     with open(os.path.join(os.path.dirname(os.path.abspath(prefix)), "checkpoint"), "w") as f:
         base = os.path.basename(prefix)

@@ -93,6 +93,7 @@ class VariableStore(object):
         self.flat = self.grad_flat = self.m_flat = self.v_flat = None
         self.version = 0               # bumped whenever values change (packed weight images re-pack lazily)
         self.packed = {}
+        self.dropout_seed = mix_dropout_seed(seed, 0)
 
     # ---- declaration
     def declare(self, name, shape, kind):
@@ -210,6 +211,12 @@ class VariableStore(object):
             self.load_state_dict({k: z[k] for k in z.files}, strict=strict)
 
 
-def layer_seed(name):
-    """Stable per-layer dropout seed."""
-    return zlib.crc32(name.encode()) * 2654435761 % (1 << 62)
+def layer_seed(name, store=None):
+    """Per-layer dropout seed: stable per layer name, offset by the store's `dropout_seed` (hp.seed and the data-parallel
+    rank mixed by the Graph constructor) so that runs with another seed and the replicas of one run draw different masks;
+    the kernels add global_step on top."""
+    return (zlib.crc32(name.encode()) * 2654435761 + (getattr(store, "dropout_seed", 0) if store is not None else 0)) % (1 << 62)
+
+
+def mix_dropout_seed(seed, rank):
+    return (int(seed) * 0x9E3779B97F4A7C15 + int(rank) * 0xBF58476D1CE4E5B9) % (1 << 62)

@@ -295,3 +295,78 @@ def ssrn_train_step(hp, P, opt, mels, mags, gen=None):
     grads = {k: p.grad for k, p in P.items() if p.grad is not None}
     opt.step(grads)
     return [float(c.detach()) for c in comps], grads
+
+
+def synth_codedtext2mel(hp, P, K, V, ends, truncate=True, return_margin=False):
+    """synthesize.py:150-230: the autoregressive loop that re-runs the whole graph per frame (`sess.run([g.Y,
+    g.max_attentions, g.alignments], {g.K, g.V, g.mels, g.prev_max_attentions})`, :181-183), keeps row j of its outputs
+    (:204-209), counts sentence ends (`endcount_threshold=1`, :163-165, :218-223) and stops when every sentence ended
+    (:225-228).  Returns (Y [B,max_T,n_mels], t_ends, alignments [B,max_N,max_T]) like the reference.
+
+    truncate=True feeds only rows 0..j of the mel buffer at step j.  The reference feeds all max_T rows but uses row j
+    only; AudioEnc / AudioDec are causal, LayerNorm and the attention softmax act per row, and the window mask depends on
+    N only (networks.py:304-313), so rows > j cannot influence row j: the truncated run is the same function (checked
+    against truncate=False and against the numpy loop in tests/test_oracle.py) at half the cost, which is what lets the
+    BASELINE synthesis shape (10 x N=150 x T=200) run in a test.
+    return_margin=True also returns the smallest gap between the best and the second best score inside the attention
+    window over all (sentence, frame) decisions that were used: a parity test can then tell a near-tie from a bug."""
+    K, V = torch.as_tensor(K), torch.as_tensor(V)
+    dt = K.dtype
+    B, N = K.shape[0], K.shape[1]
+    assert N == hp.max_N
+    T = hp.max_T
+    Y = torch.zeros(B, T, hp.n_mels, dtype=dt)
+    alignments = torch.zeros(B, N, T, dtype=dt)
+    prev = torch.zeros(B, dtype=torch.long)
+    ends = np.asarray(ends)
+    endcounts = np.zeros(ends.shape, dtype=int)
+    t_ends = np.ones(ends.shape, dtype=int) * T
+    margin = float("inf")
+    n_idx = torch.arange(N)[None, :]
+    with torch.no_grad():
+        for j in range(T):
+            rows = j + 1 if truncate else T
+            mels = Y[:, :rows]
+            S = torch.cat([torch.zeros_like(mels[:, :1]), mels[:, :-1]], 1)              # architectures.py:191
+            Q = AudioEnc(hp, P, S)
+            A = torch.matmul(Q, K.transpose(1, 2)) * (1.0 / math.sqrt(float(hp.d)))      # networks.py:300
+            pv = prev.reshape(B, 1)
+            key_masks = n_idx < pv                                                       # :304-306
+            reverse = torch.flip(n_idx < (hp.max_N - hp.attention_win_size - pv), dims=[1])
+            masks = (key_masks | reverse)[:, None, :].expand_as(A)
+            A = torch.where(masks, torch.full_like(A, MASK_VALUE), A)
+            if return_margin:
+                top2 = torch.topk(A[:, j], 2, dim=-1).values
+                margin = min(margin, float((top2[:, 0] - top2[:, 1]).min()))
+            A = torch.softmax(A, -1)
+            mx = A.argmax(-1)
+            R = torch.matmul(A, V)
+            if getattr(hp, "concatenate_query", True):
+                R = torch.cat([R, Q], -1)
+            _, Yj = AudioDec(hp, P, R)
+            Y[:, j] = Yj[:, j]
+            alignments[:, :, j] = A[:, j]
+            prev = mx[:, j]
+            endcounts += (prev.numpy() >= ends)
+            for i in range(B):
+                if t_ends[i] == T and endcounts[i] >= 1:
+                    t_ends[i] = j
+            if (t_ends < T).all():
+                break
+    out = (Y.numpy(), t_ends.tolist(), alignments.numpy())
+    return out + (margin,) if return_margin else out
+
+
+def advancing_keys(K, c=8.0, seed=0, period=8):
+    """Synthetic "diagonal bias" for synthesis tests with random-init weights (SURVEY 8(d), C4 parity variant): with such
+    weights the attention argmax never leaves the first window, so no sentence ever ends.  Adding c * (n mod period) * u
+    (u a fixed random unit vector, n the key position) to the keys makes the best key inside the window
+    [prev, prev + win) the last one whenever Q[t].u > 0 and the first one otherwise (the middle one where the window
+    straddles a wrap of n mod period): the attention advances at a sentence- and frame-dependent pace and reaches the
+    sentence ends in the middle of the run, while the scores stay of order c * period.  numpy [B, N, d] in and out."""
+    K = np.asarray(K)
+    rng = np.random.default_rng(seed)
+    u = rng.standard_normal(K.shape[-1])
+    u /= np.linalg.norm(u)
+    n = (np.arange(K.shape[1]) % period).astype(np.float64)[None, :, None]
+    return (K + c * n * u[None, None, :]).astype(K.dtype)

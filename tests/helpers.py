@@ -105,3 +105,26 @@ def make_corpus(root, n_utts=14, n_valid=3, max_N=24, max_T=40, seed=0, guides=T
         for k, v in cfg.items():
             f.write("%s = %r\n" % (k, v))
     return path, load_config(path)
+
+
+def argmax_mismatches(ours, ref_argmax, ref_scores, tie_gap=1e-5):
+    """`max_attentions` parity (exact): indices must equal the oracle's except where the oracle's
+    own top-2 gap along the key axis is below `tie_gap` (a near-tie that fp32-grade arithmetic may legitimately resolve
+    the other way).  ref_scores [..., N] are the oracle's attention rows; returns (number of unexplained mismatches,
+    number of near-ties skipped)."""
+    ours, ref_argmax = np.asarray(ours), np.asarray(ref_argmax)
+    s = np.sort(np.asarray(ref_scores, np.float64), axis=-1)
+    near_tie = (s[..., -1] - s[..., -2]) < tie_gap
+    bad = (ours != ref_argmax) & ~near_tie
+    return int(bad.sum()), int(((ours != ref_argmax) & near_tie).sum())
+
+
+def network_grad_errors(ours, ref, prefixes):
+    """Frobenius-norm relative error of the gradient of each network (all variables under a prefix taken together)."""
+    out = {}
+    for p in prefixes:
+        names = [n for n in ref if n.startswith(p)]
+        num = sum(float(((np.asarray(ours[n], np.float64) - np.asarray(ref[n], np.float64)) ** 2).sum()) for n in names)
+        den = sum(float((np.asarray(ref[n], np.float64) ** 2).sum()) for n in names)
+        out[p] = (num / max(den, 1e-300)) ** 0.5
+    return out

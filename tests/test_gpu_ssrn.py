@@ -35,6 +35,25 @@ def test_forward_matches_oracle(full_dim, T):
     assert maxabs(Zg, Z) < 1e-3
 
 
+@pytest.mark.parametrize("full_dim", [513, 1025])
+def test_forward_matches_oracle_at_baseline_length(full_dim):
+    """BASELINE.json configs[2] length (T=870 -> 3480 frames) with B=2 against the fp64 torch oracle: 6960 output rows,
+    so the 1024-channel highway layers (HC_11/12) and the odd-width output layers run several rounds of work units per
+    launch (networks.py:437-537)."""
+    from ophelia_b200.session import Session
+    T = 870
+    hp = make_hp(full_dim=full_dim)
+    P = oracle_params(hp, "ssrn", seed=8)
+    b = synthetic_batch(hp, 2, 8, T, seed=13)
+    with torch.no_grad():
+        logits, Z = ot.SSRN(hp, ot.to_torch(P, torch.float64), torch.tensor(b["mels"], dtype=torch.float64))
+    g = _graph(hp, "synthesize", P)
+    Zg, Lg = Session().run([g.Z, g.Z_logits], {g.mels: b["mels"]})
+    assert Zg.shape == (2, 4 * T, full_dim)
+    assert maxabs(Zg, Z.numpy()) < 1e-3, maxabs(Zg, Z.numpy())
+    assert maxabs(Lg, logits.numpy()) < 5e-3, maxabs(Lg, logits.numpy())
+
+
 def test_forward_matches_golden_fixture():
     from ophelia_b200.session import Session
     z = np.load(os.path.join(os.path.dirname(__file__), "golden", "ssrn_small.npz"))

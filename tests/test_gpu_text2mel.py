@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import check_grads, make_hp, maxabs, oracle_params
+from helpers import argmax_mismatches, check_grads, make_hp, maxabs, network_grad_errors, oracle_params
 from oracle import dctts_numpy as on
 from oracle import dctts_torch as ot
 from oracle.params import synthetic_batch
@@ -34,7 +34,9 @@ def test_forward_matches_oracle_c1():
     assert maxabs(K, ref["K"]) < 1e-3 and maxabs(V, ref["V"]) < 1e-3
     assert maxabs(Y, ref["Y"]) < 1e-3            # north-star tolerance: mels within 1e-3 max-abs
     assert maxabs(ali, ref["alignments"]) < 1e-4
-    assert (mx == ref["max_attentions"]).mean() > 0.995      # exact except near-ties
+    # exact, except where the oracle's own top-2 gap is below 1e-5
+    bad, ties = argmax_mismatches(mx, ref["max_attentions"], np.swapaxes(ref["alignments"], 1, 2))
+    assert bad == 0, (bad, ties)
 
 
 def test_forward_matches_golden_fixture():
@@ -66,7 +68,8 @@ def test_synthesis_mode_window_mask():
     assert maxabs(Y, ref["Y"]) < 1e-3
     assert maxabs(ali, ref["alignments"]) < 1e-4
     assert (ali[0, :3] == 0).all() and (ali[0, 6:] == 0).all()       # only keys [prev, prev+3) survive
-    assert (mx == ref["max_attentions"]).mean() > 0.995
+    bad, ties = argmax_mismatches(mx, ref["max_attentions"], np.swapaxes(ref["alignments"], 1, 2))
+    assert bad == 0, (bad, ties)
     # hp.turn_off_monotonic_for_synthesis: no window, keys from each sentence's first padding position + 1 on are masked
     # (networks.py:307-309 with hp.text_lengths set as in synthesize.py:505-507)
     hp.turn_off_monotonic_for_synthesis = True
@@ -211,6 +214,71 @@ def test_autoregressive_loop_matches_oracle():
         assert (Y6[:, max(tr) + 1:] == 0).all() and (a6[:, :, max(tr) + 1:] == 0).all()
 
 
+def test_windowless_synthesis_on_the_captured_device_route():
+    """hp.turn_off_monotonic_for_synthesis through synth_codedtext2mel_device with a CUDA graph (what the synthesize()
+    driver uses for this configuration): the per-sentence key counts of networks.py:307-309 must come from the batch
+    being synthesised -- also when a second batch of the same shape replays the captured graph."""
+    from ophelia_b200 import synthesize as syn
+    from ophelia_b200.session import Session
+    hp = make_hp(max_N=24, max_T=12)
+    hp.turn_off_monotonic_for_synthesis = True
+    P = oracle_params(hp, "t2m", seed=4)
+    g = _graph(hp, "synthesize", P)
+    sess = Session()
+    for text_len in (9, 17):                        # same shapes, different sentence lengths
+        b = synthetic_batch(hp, 3, 24, 12, text_len=text_len, seed=text_len)
+        hp.text_lengths = syn.get_text_lengths(b["L"]) + 1
+        K, V = syn.encode_text(hp, b["L"], g, sess)
+        ends = np.array([hp.max_N + 1] * 3)
+        Yr, tr, ar = syn.synth_codedtext2mel(hp, K, V, ends, g, sess)          # eager Session route (pinned to the oracle
+        Yd, td, ad = syn.synth_codedtext2mel_device(hp, K, V, ends, g, use_cuda_graph=True)   # in test_synthesis_mode_window_mask)
+        assert td == tr and maxabs(Yd, Yr) < 1e-5 and maxabs(ad, ar) < 1e-6
+        assert (ad[:, text_len + 2:, :] == 0).all() and (ad[:, :text_len + 1, :] > 0).all()
+    assert len(g._ar_state) == 1                    # the second batch replayed the first batch's graph
+
+
+def test_synthesis_at_baseline_shape_with_advancing_attention():
+    """BASELINE.json configs[3] (10 sentences, max_N=150, max_T=200, window on) against the fp64 torch oracle loop
+    (synthesize.py:150-230), every route.  Random-init weights never move the attention, so the keys carry the synthetic
+    diagonal bias of oracle.dctts_torch.advancing_keys (SURVEY 8(d), C4 parity variant): the argmax walks through the
+    sentences at different paces, six sentences end in the middle of the run (t_ends between 72 and 194), four run all 200
+    frames.  Each frame's argmax feeds the next frame's window, so one wrong decision would derail everything after it:
+    the oracle reports its smallest top-2 score gap (1.8e-4 here), an order above the score error of the GPU path."""
+    from ophelia_b200 import synthesize as syn
+    from ophelia_b200.session import Session
+    B, N, T = 10, 150, 200
+    hp = make_hp(max_N=N, max_T=T)
+    P = oracle_params(hp, "t2m", seed=3)
+    rng = np.random.default_rng(1234)
+    L = np.zeros((B, N), np.int32)
+    for i in range(B):
+        n = int(rng.integers(40, N - 1))
+        L[i, :n] = rng.integers(1, len(hp.vocab), n)
+    ends = syn.get_text_lengths(L)
+    Pt = ot.to_torch(P, torch.float64)
+    with torch.no_grad():
+        Kt, Vt = ot.TextEnc(hp, Pt, L)
+    K64 = ot.advancing_keys(Kt.numpy(), c=8.0, seed=0)
+    Yr, tr, ar, margin = ot.synth_codedtext2mel(hp, Pt, torch.tensor(K64), Vt, ends, return_margin=True)
+    assert margin > 1e-4, margin
+    assert sum(t < T for t in tr) >= 4 and sum(t == T for t in tr) >= 2, tr        # early ends and full-length sentences
+    K, V = K64.astype(np.float32), Vt.numpy().astype(np.float32)
+    g = _graph(hp, "synthesize", P)
+    routes = {
+        "session": lambda: syn.synth_codedtext2mel(hp, K, V, ends, g, Session()),
+        "device": lambda: syn.synth_codedtext2mel_device(hp, K, V, ends, g, use_cuda_graph=False),
+        "device_graph": lambda: syn.synth_codedtext2mel_device(hp, K, V, ends, g, use_cuda_graph=True),
+        "incremental": lambda: syn.synth_codedtext2mel_incremental(hp, K, V, ends, g),
+        "incremental_layers": lambda: syn.synth_codedtext2mel_incremental(hp, K, V, ends, g, fused_encoder=False),
+    }
+    for name, run in routes.items():
+        Y, t, a = run()
+        assert t == tr, (name, t, tr)
+        assert maxabs(Y, Yr) < 1e-3, (name, maxabs(Y, Yr))
+        assert maxabs(a, ar) < 1e-4, (name, maxabs(a, ar))
+        assert (a.argmax(1) == ar.argmax(1))[a.max(1) > 0].all(), name                # the whole attention path
+
+
 def test_incremental_route_beyond_the_decoder_reach():
     """max_T = 120 > 85: the Attention / AudioDec window slides (rows [j - 84, j]) and the widest AudioEnc dilation
     (2 * 27 frames back) reads real history.  The numpy oracle's O(T^2) loop is too slow here, so the reference is the
@@ -299,9 +367,57 @@ def test_capture_survives_dead_cycle_owning_another_captured_step():
     assert np.isfinite(c).all()
 
 
+def test_full_size_matches_oracle_b32_n180_t870():
+    """BASELINE.json configs[1] at its own size (B=32, N=180, T=870) against the fp64 torch oracle: forward outputs of the
+    un-masked graph (mels <= 1e-3, attention <= 1e-4, max_attentions exact except the oracle's near-ties), then one
+    dropout-free optimiser step (loss components rel 2e-4, gradient of every network in Frobenius norm).  At this size
+    the persistent GEMM runs several rounds per launch and reuses both accumulator stages, the remainder K-split and the
+    split-K weight gradients see their production schedules (architectures.py:188-362, train.py:273)."""
+    from ophelia_b200.session import Session
+    B, N, T = 32, 180, 870
+    hp = make_hp(max_N=N, max_T=T, dropout_rate=0.0)
+    P = oracle_params(hp, "t2m", seed=7)
+    b = synthetic_batch(hp, B, N, T, ragged=True)
+    Pt = ot.to_torch(P, torch.float64, requires_grad=True)
+    opt = ot.TFAdam(hp, Pt)
+    Lt, mt = torch.tensor(b["L"].astype(np.int64)), torch.tensor(b["mels"], dtype=torch.float64)
+    out = ot.text2mel_forward(hp, Pt, Lt, mt, "train")
+    comps_t = ot.text2mel_loss(hp, out, mt)
+    comps_t[0].backward()
+    grads_ref = {k: p.grad.numpy() for k, p in Pt.items() if p.grad is not None}
+    comps_ref = [float(c.detach()) for c in comps_t]
+    ref = {k: v.detach().numpy() for k, v in out.items()}
+    # forward (generate_attention mode = the training graph without dropout, no window mask)
+    store = None
+    g = _graph(hp, "generate_attention", P)
+    Y, ali, mx, K, V = Session().run([g.Y, g.alignments, g.max_attentions, g.K, g.V], {g.L: b["L"], g.mels: b["mels"]})
+    assert maxabs(K, ref["K"]) < 1e-3 and maxabs(V, ref["V"]) < 1e-3
+    assert maxabs(Y, ref["Y"]) < 1e-3, maxabs(Y, ref["Y"])
+    assert maxabs(ali, ref["alignments"]) < 1e-4, maxabs(ali, ref["alignments"])
+    bad, ties = argmax_mismatches(mx, ref["max_attentions"], np.swapaxes(ref["alignments"], 1, 2))
+    assert bad == 0, (bad, ties)
+    del g
+    # one optimiser step
+    gt = _graph(hp, "train", P, data=iter([]))
+    comps = gt.train_step_device(torch.tensor(b["L"]).cuda(), torch.tensor(b["mels"]).cuda()).cpu().numpy()
+    np.testing.assert_allclose(comps, comps_ref, rtol=2e-4, atol=1e-6)
+    sd = gt.store.grads
+    ours = {n: sd[n].cpu().numpy() for n in grads_ref}
+    nets = network_grad_errors(ours, grads_ref, ["Text2Mel/TextEnc/", "Text2Mel/AudioEnc/", "Text2Mel/AudioDec/",
+                                                 "Text2Mel/AudioDec/C_11/"])
+    # ReLU / |.| kinks flip for a few units at the 2e-5 forward noise level (helpers.check_grads); at this batch size
+    # their share is far smaller than at B=2
+    assert nets["Text2Mel/AudioDec/C_11/"] < 1e-2, nets
+    assert max(nets.values()) < 2e-2, nets
+    check_grads(ours, grads_ref, "Text2Mel/AudioDec/C_11/", strict_tol=1e-2)
+    opt.step({k: torch.tensor(v) for k, v in grads_ref.items()})
+    new = gt.store.state_dict()
+    for name, p in Pt.items():
+        assert maxabs(new[name], p.detach().numpy()) < 5e-6 + 0.2 * ot.noam(hp.lr, 0), name
+
+
 def test_full_size_properties_b32_n180_t870():
-    """BASELINE.json's training shape (B=32, N=180, T=870) is too large for the numpy oracle, so the forward pass is
-    checked there through properties the reference's graph has by construction: utterances do not interact
+    """The same shape through properties the reference's graph has by construction: utterances do not interact
     (architectures.py:188-239 has no cross-batch op; here tiles, taps and the boundary fix-up run across item
     boundaries), AudioEnc / AudioDec are causal in time (networks.py:214-284, 360-435), attention rows are
     distributions, and padded text positions embed to zero (modules.py:38-40)."""
@@ -327,6 +443,45 @@ def test_full_size_properties_b32_n180_t870():
     # (same schedule in both runs and no atomics in the forward pass: bit-identical)
     assert maxabs(Q2[:, :501], Q[:, :501]) == 0.0 and maxabs(Y2[:, :501], Y[:, :501]) == 0.0
     assert maxabs(Y2[:, 501:], Y[:, 501:]) > 1e-3
+
+
+def test_update_weights_freezes_everything_else():
+    """hp.update_weights (architectures.py:113-120, 436-443): only variables whose name matches one of the patterns are
+    given to the optimiser.  Two steps against the oracle restricted to the same variables; every other variable (and its
+    Adam slots) must stay bit-identical while global_step still advances."""
+    from ophelia_b200.architectures import filter_variables_for_update
+    B, N, T = 2, 30, 70
+    hp = make_hp(max_N=N, max_T=T, dropout_rate=0.0)
+    hp.update_weights = ["Text2Mel/AudioDec", "Text2Mel/TextEnc/HC_1[45]/"]
+    P = oracle_params(hp, "t2m", seed=12)
+    b = synthetic_batch(hp, B, N, T, ragged=True)
+    g = _graph(hp, "train", P, data=iter([]))
+    chosen = filter_variables_for_update(g.store, hp.update_weights)
+    assert chosen and all(n.startswith("Text2Mel/AudioDec/") or "/TextEnc/HC_14/" in n or "/TextEnc/HC_15/" in n for n in chosen)
+    assert len(g.train_ranges) == 2                              # two contiguous runs of the flat buffer
+    Pt = ot.to_torch(P, torch.float64, requires_grad=True)
+    opt = ot.TFAdam(hp, Pt)
+    Ld, md = torch.tensor(b["L"]).cuda(), torch.tensor(b["mels"]).cuda()
+    before = g.store.state_dict()
+    for _ in range(2):
+        for p in Pt.values():
+            p.grad = None
+        out = ot.text2mel_forward(hp, Pt, torch.tensor(b["L"].astype(np.int64)), torch.tensor(b["mels"], dtype=torch.float64), "train")
+        comps_t = ot.text2mel_loss(hp, out, torch.tensor(b["mels"], dtype=torch.float64))
+        comps_t[0].backward()
+        opt.step({k: Pt[k].grad for k in chosen})               # compute_gradients(loss, var_list=train_variables)
+        comps = g.train_step_device(Ld, md).cpu().numpy()
+        np.testing.assert_allclose(comps, [float(c.detach()) for c in comps_t], rtol=3e-4, atol=1e-6)
+    after = g.store.state_dict()
+    assert int(g.store.global_step.item()) == 2
+    for name in after:
+        if name in chosen:
+            assert maxabs(after[name], Pt[name].detach().numpy()) < 5e-6 + 0.2 * 2 * ot.noam(hp.lr, 1), name
+            assert maxabs(after[name], before[name]) > 0, name
+        else:
+            assert np.array_equal(after[name], before[name]), name
+            o, cnt = g.store.offsets[name], after[name].size
+            assert float(g.store.m_flat[o:o + cnt].abs().max()) == 0.0 and float(g.store.v_flat[o:o + cnt].abs().max()) == 0.0
 
 
 def test_session_train_loop_with_changing_batch_shapes():

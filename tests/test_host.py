@@ -185,6 +185,11 @@ def test_tf_checkpoint_format_roundtrip(tmp_path):
     st.global_step.fill_(77)
     tfc.save(st, str(tmp_path / "model_gs_77"))
     assert tfc.latest_checkpoint(str(tmp_path)) == str(tmp_path / "model_gs_77")
+    ck = tfc.read_checkpoint(str(tmp_path / "model_gs_77"))
+    # tf.train.AdamOptimizer's non-slot variables, which train.py's Supervisor restore expects: beta^(t+1) after t updates
+    assert ck["beta1_power"].shape == () and abs(float(ck["beta1_power"]) - 0.9 ** 78) < 1e-9
+    assert abs(float(ck["beta2_power"]) - 0.999 ** 78) < 1e-7
+    assert not [f for f in os.listdir(str(tmp_path)) if ".tmp" in f]          # temporary files were moved into place
     st2 = VariableStore("cpu", seed=9).declare_all(specs).finalize(with_optimizer=True)
     unused = tfc.restore(st2, tfc.latest_checkpoint(str(tmp_path)))
     assert unused == [] and torch.equal(st2.flat, st.flat) and int(st2.global_step.item()) == 77

@@ -163,3 +163,26 @@ def test_confidence_terms_restatements_agree_and_match_the_diagnostic_script():
     hp.loss_weights = {"t2m": {"L1": 0.3, "binary_divergence": 0.3, "attention": 0.3, "L2": 0.1}}
     c3 = on.text2mel_loss(hp, out, b["mels"])
     assert len(c3) == 8 and abs(c3[0] - (0.3 * c3[1] + 0.3 * c3[2] + 0.3 * c3[3] + 0.1 * c3[4])) < 1e-12
+
+
+def test_torch_autoregressive_loop_equals_numpy_loop_and_truncation_is_exact():
+    """oracle.dctts_torch.synth_codedtext2mel (the loop the GPU routes are checked against at BASELINE's synthesis shape)
+    equals the numpy restatement of synthesize.py:150-230, and feeding rows 0..j only (truncate=True) is the same function
+    as feeding all max_T rows: the networks are causal and every other op acts per row.  With the synthetic diagonal bias
+    on the keys the attention advances and sentences end at different frames."""
+    hp = HP(max_N=26, max_T=30)
+    P = init_params(text2mel_specs(hp), 3, perturb=True)
+    b = synthetic_batch(hp, 3, 26, 30, text_len=9)
+    K, V = on.TextEnc(hp, P, b["L"])
+    K = ot.advancing_keys(K, c=8.0, seed=1)
+    ends = np.array([6, 9, 27])
+    Yn, tn, an = on.synth_codedtext2mel(hp, P, K, V, ends)
+    Pt = ot.to_torch(P, torch.float64)
+    Y1, t1, a1, margin = ot.synth_codedtext2mel(hp, Pt, K, V, ends, truncate=True, return_margin=True)
+    Y2, t2, a2 = ot.synth_codedtext2mel(hp, Pt, K, V, ends, truncate=False)
+    assert t1 == t2 == tn and margin > 1e-6
+    assert min(tn) < hp.max_T - 1 and max(tn) == hp.max_T, tn      # early ends and a sentence that never ends
+    assert np.abs(Y1 - Yn).max() < 1e-10 and np.abs(a1 - an).max() < 1e-10
+    assert np.abs(Y1 - Y2).max() < 1e-12 and np.abs(a1 - a2).max() < 1e-12
+    path = an[0].argmax(0)
+    assert len(set(path.tolist())) > 3                              # the window moved
