@@ -70,7 +70,10 @@ int oph_gemm_debug_buffer(long long* dev_buf);
  * kernel (0 = automatic), 2048 = one block per SM for it, 4096 = previous (warp-per-row) highway-forward row kernel,
  * 32768 = previous (warp-per-row) conv-tail backward kernel, 65536 = fuse the conv tail (LayerNorm / ReLU / dropout / planes) of layers with <= 256 output channels into the
  * GEMM epilogue (off by default: no gain on the training step, slower on the small autoregressive step),
- * 16384 = remainder K-split also for plain conv outputs (memset + RED: forward results then depend on RED order) */
+ * 16384 = remainder K-split also for plain conv outputs (memset + RED: forward results then depend on RED order),
+ * 131072 = highway tail of oph_hc_fwd always as its own launch (default: inside the conv launch when the row tiles fill whole
+ * rounds of the 74 CTA pairs, the last one to >= 70 %), 262144 = also fuse the full rounds when the last round is emptier
+ * (the rest of the rows then gets plain work units + a partial tail launch) */
 int oph_gemm_debug_flags(int flags);
 /* Execution context of the calling host thread (like cublasSetStream): with enable != 0 the weight-gradient GEMMs of
  * oph_*_bwd are launched on `side` after an event fork behind the layer's row-wise backward kernel, so that they
@@ -160,7 +163,10 @@ int oph_normalize_bwd(const float* dy, long long lddy, const float* x, long long
 
 /* ---- modules.hc (modules.py:148-207): highway conv, C -> 2C -> C ------------------------------------------
  * z [B*L][ldz] (>= 2C wide) pre-LN conv output; stats [B*L][4] = (mean1, rstd1, mean2, rstd2).
- * x needs its fp32 view (highway residual); its planes, when present, feed the GEMM. */
+ * x needs its fp32 view (highway residual); its planes, when present, feed the GEMM.
+ * One launch when C is 256 / 512 / 1024, x carries planes and the row tiles fill the CTA pairs (see flag 131072): the
+ * conv's epilogue warps then apply LN(H1), LN(H2), the sigmoid gate, the highway mix and dropout to their rows while the
+ * tensor pipe is on the next row tile.  Otherwise two launches (conv, then the streaming tail kernel). */
 int oph_hc_fwd(const oph_act* x, const void* packed_w, const float* bias, const float* g1, const float* b1,
                const float* g2, const float* b2, float* z, long long ldz, float* stats, const oph_act* y, int B, int L,
                int C, int k, int rate, int padding, int norm, float drop_p, uint64_t seed, const long long* step,

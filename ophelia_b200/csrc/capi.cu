@@ -152,6 +152,7 @@ bool make_plane_tmap2d(CUtensorMap* out, const unsigned short* base, int C, long
 bool g_use_tma = true;
 bool g_use_split = true;
 bool g_use_ln_fuse = false;  // measured: 7.02 vs 7.04 ms per training step, but 0.71 vs 0.61 ms per autoregressive frame step
+bool g_use_hc_fuse = true;   // highway tail in the epilogue phase of the conv GEMM (oph_gemm_debug_flags bit 131072 turns it off)
 
 int launch_gemm(GemmArgs& a, int zdim, cudaStream_t st) {
     static bool attr_done = false;
@@ -224,6 +225,9 @@ int launch_gemm(GemmArgs& a, int zdim, cudaStream_t st) {
     a.ln_fuse = (a.ln_gamma && a.ln_y && g_use_ln_fuse && a.a_tma == 1 && a.b_mode == B_PACKED && a.N <= GEMM_BN && !a.atomic &&
                  !a.addend && !a.Chi && a.c_mul == 1 && a.c_off == 0 && a.z_mode == Z_NONE && a.ytaps == 1 &&
                  !(a.ldc & 3) && !(a.ln_ldy & 3) && !(a.ln_ldys & 3) && !(a.ln_ldp & 3)) ? 1 : 0;
+    // highway tail in the same launch: only for copy-fed conv products whose epilogue runs on the 16 producer warps
+    if (a.hc_fused && !(a.a_tma == 1 && a.b_mode == B_PACKED && a.z_mode == Z_NONE && a.ytaps == 1 && !a.atomic && !a.addend &&
+                        !a.Chi && a.c_mul == 1 && a.c_off == 0 && !a.ln_fuse)) a.hc_fused = 0;
     const long long units = (long long)cdiv(cdiv(a.M, GEMM_BM), 2) * cdiv(a.N, GEMM_BN) * a.ytaps * a.zdim;
     // RED outputs fed by the copy engines: split the units of the last (partial) round into k-block slices so that it
     // costs a fraction of a round; s minimises rounds x (slice length + 1 k-block of per-item overhead)
@@ -234,7 +238,7 @@ int launch_gemm(GemmArgs& a, int zdim, cudaStream_t st) {
     // (off by default, flag 16384: the arrival order of the REDs would make FORWARD results vary in the last bits from run
     // to run, and with the side streams the idle SMs of a partial round are filled by other kernels anyway)
     const bool can_zero = (g_gemm_dbg_flags_host & 16384) && !a.atomic && a.zero_bytes > 0 && !a.addend && !a.Chi && a.c_mul == 1;
-    if (g_use_split && a.a_tma == 1 && a.b_mode == B_PACKED && (can_red || can_zero) && a.z_mode == Z_NONE && a.ytaps == 1) {
+    if (g_use_split && !a.hc_fused && a.a_tma == 1 && a.b_mode == B_PACKED && (can_red || can_zero) && a.z_mode == Z_NONE && a.ytaps == 1) {
         const int P = GEMM_MAX_PAIRS, KB = a.ntaps * cdiv(a.Kc, GEMM_BK);
         const int rem = (int)(units % P);
         if (rem > 0) {
@@ -253,7 +257,11 @@ int launch_gemm(GemmArgs& a, int zdim, cudaStream_t st) {
             }
         }
     }
-    const int pairs = (int)(items < GEMM_MAX_PAIRS ? items : GEMM_MAX_PAIRS);
+    int pairs = (int)(items < GEMM_MAX_PAIRS ? items : GEMM_MAX_PAIRS);
+    if (a.hc_fused) {                                   // super-units: one per row-tile pair
+        const int mp = cdiv(cdiv(a.M, GEMM_BM), 2);
+        pairs = mp < GEMM_MAX_PAIRS ? mp : GEMM_MAX_PAIRS;
+    }
     dim3 grid(2 * pairs);
     {
         ProfScope ps(a.tag, 2.0 * a.M * a.N * (a.prof_k ? a.prof_k : a.Kc) * (a.a_mode == A_KMAJOR ? a.ntaps : a.ytaps) * (a.z_mode == Z_BATCH ? a.zdim : 1), st);
@@ -543,7 +551,7 @@ unsigned int oph_crc32c(const void* data, unsigned long long n, unsigned int crc
 const char* oph_last_error(void) { return g_err; }
 long long oph_launch_count(void) { return g_launches.load(); }
 int oph_gemm_debug_buffer(long long* dev_buf) { g_gemm_dbg = dev_buf; return OPH_OK; }
-int oph_gemm_debug_flags(int flags) { g_gemm_dbg_flags_host = flags; g_gemm_dbg_flags = flags & 0xA7; g_use_tma = !(flags & 8); g_use_split = !(flags & 16); g_use_pdl = (flags & 64) != 0; g_use_ln_fuse = (flags & 65536) != 0;
+int oph_gemm_debug_flags(int flags) { g_gemm_dbg_flags_host = flags; g_gemm_dbg_flags = flags & 0xA7; g_use_tma = !(flags & 8); g_use_split = !(flags & 16); g_use_pdl = (flags & 64) != 0; g_use_ln_fuse = (flags & 65536) != 0; g_use_hc_fuse = !(flags & 131072);
     g_hcb_depth = (flags >> 8) & 7;                    // 0 = automatic
     g_hcb_two = !(flags & 2048);
     if (g_hcb_depth == 1) g_hcb_depth = 2;
@@ -743,11 +751,41 @@ int oph_hc_fwd(const oph_act* x, const void* packed_w, const float* bias, const 
     g.Bpacked = packed_w; g.M = B * L; g.N = 2 * C; g.Kc = C; g.ntaps = k;
     g.C = z; g.ldc = ldz; g.bias = bias; g.tag = OPH_TAG_HC_FWD;
     g.zero_bytes = (size_t)B * L * ldz * sizeof(float);        // z is ours to overwrite: remainder units may be K-split
-    OPH_TRY(launch_gemm(g, 1, S(stream)));
-    const long long rows = (long long)B * L;
-    const int grid = rows_grid(rows, 8);
+    const long long all_rows = (long long)B * L;
     const bool vec = vec_ok(C, ldz, x->ld, y->ld);
     if (y->hi && !(vec && !(y->ldp & 7))) return fail(OPH_EINVAL, "hc_fwd: output planes need C in {256,512,1024}%s");
+    // Highway tail in the same launch (gemm_tc.cuh, hc_fused): row-tile pairs run as super-units whose epilogue warps finish
+    // the rows.  A super-unit pins all column blocks of a row tile to one CTA pair, so the schedule is only as good as
+    // (row tiles) / (74 pairs) rounds up: used when the last round is full or at least 70 % full.  Otherwise (e.g. 109 row
+    // tiles at B=32, T=870: 74 + 35) the tail stays its own launch -- measured on B200, fusing the 74 and leaving the 35 to
+    // plain units + a partial tail launch gives the same step time (7.02 vs 6.97 ms) and a slower conv launch.  The kernel
+    // supports that mixed schedule (flag 262144 selects it) and the tests cover it.
+    long long done_rows = 0;
+    if (g_use_hc_fuse && vec && norm && y->f32 && !(y->hi && (y->ldp & 3)) && !(g_gemm_dbg_flags_host & 4096)) {
+        const int MP = cdiv(cdiv((int)all_rows, GEMM_BM), 2), P = GEMM_MAX_PAIRS;
+        const int full = (MP / P) * P, rem = MP - full;
+        const int F = (rem == 0 || rem * 10 >= P * 7) ? MP : ((g_gemm_dbg_flags_host & 262144) ? full : 0);
+        if (F > 0) {
+            g.hc_fused = F; g.hc_C = C;
+            g.hc_x = x->f32; g.hc_ldx = x->ld; g.hc_g1 = g1; g.hc_b1 = b1; g.hc_g2 = g2; g.hc_b2 = b2;
+            g.hc_y = y->f32; g.hc_ldy = y->ld; g.hc_yhi = y->hi; g.hc_ylo = y->lo; g.hc_ldp = y->ldp;
+            g.hc_stats = stats; g.hc_drop = drop_p; g.hc_seed = seed; g.hc_step = step;
+        }
+    }
+    OPH_TRY(launch_gemm(g, 1, S(stream)));
+    if (g.hc_fused) done_rows = (long long)g.hc_fused * 2 * GEMM_BM < all_rows ? (long long)g.hc_fused * 2 * GEMM_BM : all_rows;
+    if (done_rows >= all_rows) return OPH_OK;
+    // the rows the GEMM launch did not finish: offset every row-indexed pointer
+    const long long rows = all_rows - done_rows;
+    z += done_rows * ldz;
+    if (stats) stats += done_rows * 4;
+    oph_act xr = *x, yr = *y;
+    xr.f32 += done_rows * x->ld;
+    yr.f32 += done_rows * y->ld;
+    if (yr.hi) { yr.hi += done_rows * y->ldp; yr.lo += done_rows * y->ldp; }
+    x = &xr; y = &yr;
+    const unsigned long long row_base = (unsigned long long)done_rows;
+    const int grid = rows_grid(rows, 8);
     ProfScope ps(OPH_TAG_HC_ROW_FWD, (double)rows * C * (y->hi ? 20.0 : 16.0), S(stream));
     if (vec && norm && !(g_gemm_dbg_flags_host & 4096)) {
         const int wpr = C / 256, groups = 8 / wpr;
@@ -763,7 +801,7 @@ int oph_hc_fwd(const oph_act* x, const void* packed_w, const float* bias, const 
             cudaFuncSetAttribute(hc_post_fwd_wide_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
             attr_done = true;
         }
-#define OPH_LAUNCH(W) launch_cfg(gridw, 256, smw, S(stream))(hc_post_fwd_wide_kernel<W>, z, ldz, x->f32, x->ld, g1, b1, g2, b2, y->f32, y->ld, y->hi, y->lo, y->ldp, stats, (int)rows, drop_p, seed, step, depth)
+#define OPH_LAUNCH(W) launch_cfg(gridw, 256, smw, S(stream))(hc_post_fwd_wide_kernel<W>, z, ldz, x->f32, x->ld, g1, b1, g2, b2, y->f32, y->ld, y->hi, y->lo, y->ldp, stats, (int)rows, drop_p, seed, step, depth, (long long)row_base)
         if (C == 256) OPH_LAUNCH(1); else if (C == 512) OPH_LAUNCH(2); else OPH_LAUNCH(4);
 #undef OPH_LAUNCH
     } else if (vec) {

@@ -84,6 +84,18 @@ struct GemmArgs {
     float* ln_ysig; long long ln_ldys;
     int ln_act; float ln_drop; unsigned long long ln_seed; const long long* ln_step;
     int split_red;         // 1: C was zeroed by the host and only the split work items accumulate with RED (plain outputs)
+    // Highway tail fused into the same launch (modules.hc, N = 2C): the first hc_fused row-tile pairs (256 rows each) are
+    // SUPER-UNITS -- a CTA pair runs all column blocks of such a tile back to back, its epilogue warps write z as usual and,
+    // after the last block, finish their CTA's 128 rows from the just-written z (L2 hits): LN(H1), LN(H2), sigmoid gate,
+    // highway mix with x, dropout -> y, operand planes, row statistics.  Row tiles >= hc_fused stay plain units (the host
+    // launches the stand-alone tail kernel for their rows).
+    int hc_fused, hc_C;
+    const float* hc_x; long long hc_ldx;
+    const float* hc_g1; const float* hc_b1; const float* hc_g2; const float* hc_b2;
+    float* hc_y; long long hc_ldy;
+    unsigned short* hc_yhi; unsigned short* hc_ylo; long long hc_ldp;
+    float* hc_stats;       // [M][4] (mean1, rstd1, mean2, rstd2) or NULL
+    float hc_drop; unsigned long long hc_seed; const long long* hc_step;
     alignas(64) CUtensorMap tmA_hi;
     alignas(64) CUtensorMap tmA_lo;
     alignas(64) CUtensorMap tmB_hi;
@@ -230,6 +242,124 @@ __device__ __forceinline__ Unit decode_unit(const GemmArgs& p, int v, int MP, in
     return t;
 }
 
+// The it-th work item of CTA pair `pair` as a unit index for decode_unit, or -1 past the end.  Plain launches walk the
+// units round-robin.  With a fused highway tail the first hc_fused row-tile pairs are super-units (all column blocks of a
+// row tile consecutively on one pair), the other row tiles follow as plain units.
+__device__ __forceinline__ int item_unit(const GemmArgs& p, int it, int pair, int npairs, int MP, int nblocks, int total) {
+    if (!p.hc_fused) { const int u = pair + it * npairs; return u < total ? u : -1; }
+    const int F = p.hc_fused;
+    const int nsup = F > pair ? (F - pair + npairs - 1) / npairs : 0;
+    if (it < nsup * nblocks) return (it % nblocks) * MP + pair + (it / nblocks) * npairs;
+    const int r = pair + (it - nsup * nblocks) * npairs, W = MP - F;
+    if (W <= 0 || r >= W * nblocks) return -1;
+    return (r / W) * MP + F + r % W;
+}
+// is item `it` of this pair the last column block of a fused super-unit?
+__device__ __forceinline__ bool item_closes_tile(const GemmArgs& p, int it, int pair, int npairs, int nblocks) {
+    if (!p.hc_fused) return false;
+    const int nsup = p.hc_fused > pair ? (p.hc_fused - pair + npairs - 1) / npairs : 0;
+    return it < nsup * nblocks && (it % nblocks) == nblocks - 1;
+}
+
+__device__ __forceinline__ float4 ld_cg4(const float* p) {
+    float4 v;
+    asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
+// Highway tail over `nrows` rows of one CTA (the 16 epilogue warps, 512 threads), same arithmetic in the same order as
+// hc_post_fwd_wide_kernel: WPR warps share a row (256 channels per warp, two float4 per lane), per-warp two-pass moments
+// merged exactly across the warps of a row.  z rows are read back with ld.global.cg (they were written by other warps of
+// this CTA just before the CTA-wide barrier); sm = the epilogue staging area, free during this phase.
+template <int WPR>
+__device__ __forceinline__ void hc_tail_rows(const GemmArgs& p, float* sm, int warp, int lane, long long row0, int nrows,
+                                             const float* zrow0) {
+    constexpr int C = 256 * WPR;
+    constexpr int GROUPS = 16 / WPR;
+    float* spar = sm;                                   // [4][C]: g1, b1, g2, b2
+    float* sx = sm + 4 * C;                             // [2 parities][16 warps][4] partial moments
+    for (int i = warp * 32 + lane; i < C; i += 512) {
+        spar[i] = __ldg(p.hc_g1 + i); spar[C + i] = __ldg(p.hc_b1 + i);
+        spar[2 * C + i] = __ldg(p.hc_g2 + i); spar[3 * C + i] = __ldg(p.hc_b2 + i);
+    }
+    asm volatile("bar.sync 13, 512;" ::: "memory");
+    const int grp = warp / WPR, part = warp % WPR;
+    const int cbase = part * 256 + lane * 4;
+    const float inv_keep = p.hc_drop > 0.f ? 1.f / (1.f - p.hc_drop) : 1.f;
+    const unsigned long long sd = eff_seed(p.hc_seed, p.hc_step);
+    int it = 0;
+    for (int r = grp; r < nrows; r += GROUPS, ++it) {
+        const long long row = row0 + r;
+        const float* zr = zrow0 + (long long)r * p.ldc;
+        float4 z1[2], z2[2], xv[2], o[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            z1[i] = ld_cg4(zr + cbase + 128 * i);
+            z2[i] = ld_cg4(zr + C + cbase + 128 * i);
+            xv[i] = __ldg(reinterpret_cast<const float4*>(p.hc_x + row * p.hc_ldx + cbase + 128 * i));
+        }
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) { s1 += (z1[i].x + z1[i].y) + (z1[i].z + z1[i].w); s2 += (z2[i].x + z2[i].y) + (z2[i].z + z2[i].w); }
+        float m1 = warp_sum(s1) * (1.f / 256.f), m2 = warp_sum(s2) * (1.f / 256.f);
+        float q1 = 0.f, q2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float a = OPH_F4(z1[i], e) - m1, b = OPH_F4(z2[i], e) - m2;
+                q1 += a * a; q2 += b * b;
+            }
+        q1 = warp_sum(q1); q2 = warp_sum(q2);
+        if (WPR > 1) {
+            float* my = sx + ((it & 1) * 16 + warp) * 4;
+            if (lane == 0) *reinterpret_cast<float4*>(my) = make_float4(m1, q1, m2, q2);
+            asm volatile("bar.sync %0, %1;" ::"r"(5 + grp), "r"(WPR * 32) : "memory");
+            float mm1 = 0.f, mm2 = 0.f;
+            float4 ow[WPR];
+#pragma unroll
+            for (int w = 0; w < WPR; ++w) { ow[w] = *reinterpret_cast<const float4*>(sx + ((it & 1) * 16 + grp * WPR + w) * 4); mm1 += ow[w].x; mm2 += ow[w].z; }
+            mm1 *= (1.f / WPR); mm2 *= (1.f / WPR);
+            float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+            for (int w = 0; w < WPR; ++w) {
+                t1 += ow[w].y + 256.f * (ow[w].x - mm1) * (ow[w].x - mm1);
+                t2 += ow[w].w + 256.f * (ow[w].z - mm2) * (ow[w].z - mm2);
+            }
+            m1 = mm1; m2 = mm2; q1 = t1; q2 = t2;
+        }
+        const float r1 = rsqrtf(q1 * (1.f / (float)C) + LN_EPS), r2 = rsqrtf(q2 * (1.f / (float)C) + LN_EPS);
+        if (p.hc_stats && lane == 0 && part == 0) *reinterpret_cast<float4*>(p.hc_stats + row * 4) = make_float4(m1, r1, m2, r2);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            float4 G1 = *reinterpret_cast<const float4*>(spar + cbase + 128 * i);
+            float4 B1 = *reinterpret_cast<const float4*>(spar + C + cbase + 128 * i);
+            float4 G2 = *reinterpret_cast<const float4*>(spar + 2 * C + cbase + 128 * i);
+            float4 B2 = *reinterpret_cast<const float4*>(spar + 3 * C + cbase + 128 * i);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float u1 = (OPH_F4(z1[i], e) - m1) * r1 * OPH_F4(G1, e) + OPH_F4(B1, e);
+                const float u2 = (OPH_F4(z2[i], e) - m2) * r2 * OPH_F4(G2, e) + OPH_F4(B2, e);
+                const float g = sigmoidf_(u1);
+                float v = g * u2 + (1.f - g) * OPH_F4(xv[i], e);
+                if (p.hc_drop > 0.f) v *= drop_scale(sd, (unsigned long long)row * C + cbase + 128 * i + e, p.hc_drop, inv_keep);
+                OPH_F4(o[i], e) = v;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            *reinterpret_cast<float4*>(p.hc_y + row * p.hc_ldy + cbase + 128 * i) = o[i];
+            if (p.hc_yhi) {
+                uint2 hh, ll;
+                split4(o[i], hh, ll);
+                *reinterpret_cast<uint2*>(p.hc_yhi + row * p.hc_ldp + cbase + 128 * i) = hh;
+                *reinterpret_cast<uint2*>(p.hc_ylo + row * p.hc_ldp + cbase + 128 * i) = ll;
+            }
+        }
+    }
+    asm volatile("bar.sync 13, 512;" ::: "memory");        // the staging area goes back to the plain epilogue
+}
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
     extern __shared__ uint8_t smem_raw[];
@@ -296,7 +426,9 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
         const bool vec_ok = !(p.ldc & 3) && !(reinterpret_cast<uintptr_t>(p.C) & 15) && !(p.c_zs & 3) && !(p.c_tap_stride & 3) &&
                             (!p.addend || (!(p.ld_add & 3) && !(reinterpret_cast<uintptr_t>(p.addend) & 15)));
         int acc = 0, acc_par = 0;
-        for (int u = pair; u < total; u += npairs) {
+        for (int it_ = 0;; ++it_) {
+            const int u = item_unit(p, it_, pair, npairs, MP, nblocks, total);
+            if (u < 0) break;
             const Unit t = decode_unit(p, u, MP, nblocks, crank);
             if (t.KB <= 0) continue;
             mbar_wait(BAR(BAR_T_FULL + acc), acc_par);
@@ -366,6 +498,16 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
                 __syncwarp();
             }
             if (++acc == N_ACC) { acc = 0; acc_par ^= 1; }
+            if (item_closes_tile(p, it_, pair, npairs, nblocks)) {
+                // every column block of this CTA's 128 rows is in z now (written by the 16 epilogue warps of this CTA):
+                // make it visible CTA-wide, then finish the rows -- the MMA warp is already busy with the next row tile
+                asm volatile("bar.sync 13, 512;" ::: "memory");
+                const float* z0 = p.C + (long long)t.m0 * p.ldc;
+                const int wq = (cg << 2) | q;                  // 0..15, any bijection of the 16 warps
+                if (p.hc_C == 256) hc_tail_rows<1>(p, sStage, wq, lane, t.m0, t.rows, z0);
+                else if (p.hc_C == 512) hc_tail_rows<2>(p, sStage, wq, lane, t.m0, t.rows, z0);
+                else hc_tail_rows<4>(p, sStage, wq, lane, t.m0, t.rows, z0);
+            }
         }
     };
 
@@ -393,7 +535,9 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
             return tot;
         };
         int acc = 0, acc_par = 0;
-        for (int u = pair; u < total; u += npairs) {
+        for (int it_ = 0;; ++it_) {
+            const int u = item_unit(p, it_, pair, npairs, MP, nblocks, total);
+            if (u < 0) break;
             const Unit t = decode_unit(p, u, MP, nblocks, crank);
             if (t.KB <= 0) continue;
             mbar_wait(BAR(BAR_T_FULL + acc), acc_par);
@@ -655,7 +799,9 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
             const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
             int as = 0, a_par = 0, bs = 0, b_par = 0, acc = 0, acc_par = 1;
             long long w_t = 0, w_a = 0, w_b = 0, t_begin = clock64(), nkb = 0;
-            for (int u = pair; u < total; u += npairs) {
+            for (int it_ = 0;; ++it_) {
+                const int u = item_unit(p, it_, pair, npairs, MP, nblocks, total);
+                if (u < 0) break;
                 const Unit t = decode_unit(p, u, MP, nblocks, crank);
                 if (t.KB <= 0) continue;
                 long long c0 = clock64();
@@ -710,7 +856,9 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
             if (p.r_tma || p.b_tma) tma_prefetch_desc(&p.tmB_lo);
             const uint32_t fullA0 = mapa_u32(BAR(BAR_FULL_A), 0), fullB0 = mapa_u32(BAR(BAR_FULL_B), 0);   // leader's barriers
             const int KBI = (p.A.L + GEMM_BK - 1) / GEMM_BK;       // 64-step blocks per batch item (r_tma, split-K)
-            for (int u = pair; u < total; u += npairs) {
+            for (int it_ = 0;; ++it_) {
+                const int u = item_unit(p, it_, pair, npairs, MP, nblocks, total);
+                if (u < 0) break;
                 const Unit t = decode_unit(p, u, MP, nblocks, crank);
                 // packed image rows (128 bytes each) of this CTA's half of stage (nb, kb): ((nb*KB + kb)*2 + crank) * 256
                 const int brow0 = (t.nb * t.KB * 2 + (int)crank) * 256;
@@ -809,7 +957,9 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
         // here (generic-proxy stores + proxy fence) and the bytes are then accounted on the leader's FULL barrier.
         if (p.a_tma == 1) {
             int as = 0; uint32_t land_par = 0;
-            for (int u = pair; u < total; u += npairs) {
+            for (int it_ = 0;; ++it_) {
+                const int u = item_unit(p, it_, pair, npairs, MP, nblocks, total);
+                if (u < 0) break;
                 const Unit t = decode_unit(p, u, MP, nblocks, crank);
                 int tmod[4];                                   // step within the item of this lane's 4 rows
 #pragma unroll

@@ -988,7 +988,8 @@ __global__ void __launch_bounds__(256) hc_post_fwd_wide_kernel(
         const float* __restrict__ g1, const float* __restrict__ b1, const float* __restrict__ g2,
         const float* __restrict__ b2, float* __restrict__ y, long long ldy, unsigned short* __restrict__ y_hi,
         unsigned short* __restrict__ y_lo, long long ldp, float* __restrict__ stats,
-        int rows, float drop_p, unsigned long long seed, const long long* step, int depth) {
+        int rows, float drop_p, unsigned long long seed, const long long* step, int depth, long long row_base) {
+    // row_base: index of row 0 within the layer's activation (the dropout mask is a function of the absolute element index)
     pdl_grid_sync();
     constexpr int C = 256 * WPR;
     constexpr int GROUPS = 8 / WPR;
@@ -1083,7 +1084,7 @@ __global__ void __launch_bounds__(256) hc_post_fwd_wide_kernel(
                 const float u2 = (OPH_F4(z2[i], e) - m2) * r2 * OPH_F4(G2, e) + OPH_F4(B2, e);
                 const float g = sigmoidf_(u1);
                 float r = g * u2 + (1.f - g) * OPH_F4(xv[i], e);
-                if (drop_p > 0.f) r *= drop_scale(sd, (unsigned long long)row * C + cbase + 128 * i + e, drop_p, inv_keep);
+                if (drop_p > 0.f) r *= drop_scale(sd, (unsigned long long)(row_base + row) * C + cbase + 128 * i + e, drop_p, inv_keep);
                 OPH_F4(o[i], e) = r;
             }
         }

@@ -82,3 +82,54 @@ def test_standalone_normalize_matches_oracle(C):
     assert err(dx, x64.grad) < 5e-5 * float(x64.grad.abs().max())  + 1e-6
     assert err(store.grad("n/gamma"), gamma.grad) < 1e-4 * float(gamma.grad.abs().max())
     assert err(store.grad("n/beta"), beta.grad) < 1e-4 * float(beta.grad.abs().max())
+
+
+@pytest.mark.parametrize("C,rows,k,rate,causal,drop", [
+    (256, 27840, 3, 3, True, 0.05),      # BASELINE shape: 109 row-tile pairs = 74 fused + 35 plain (two launches)
+    (256, 74 * 256, 3, 27, False, 0.0),  # exactly one round of super-units, everything fused (one launch)
+    (256, 60 * 256 + 37, 1, 1, True, 0.05),   # partial round that still fuses, ragged last tile
+    (512, 19000, 3, 9, False, 0.05),     # 4 column blocks per super-unit, two warps per row in the tail
+    (1024, 14000, 3, 1, False, 0.0),     # 8 column blocks, four warps per row
+])
+def test_fused_highway_tail_equals_separate_tail(C, rows, k, rate, causal, drop):
+    """modules.hc with the highway tail inside the conv launch (the super-unit schedule of gemm_tc.cuh) against the same
+    layer with the tail as its own launch (oph_gemm_debug_flags bit 131072; that path is pinned to the oracle by the `hc`
+    group above and by the network tests): same arithmetic in the same order, so y, its operand planes, z and the row
+    statistics must be bit-identical -- at sizes where whole rounds of CTA pairs run super-units."""
+    import torch
+    from ophelia_b200 import _lib, ops
+    lib = _lib.load()
+    torch.manual_seed(C + rows)
+    dev = "cuda:0"
+    B, L = (32, rows // 32) if rows % 32 == 0 else (1, rows)
+    x = torch.randn(B, L, C, device=dev)
+    x._oph_planes = ops.split_planes(x)
+    w = torch.randn(k, C, 2 * C, device=dev) * (2.6 / (k * C)) ** 0.5
+    pk = ops.PackedConv(w)
+    bias = 0.1 * torch.randn(2 * C, device=dev)
+    g1, g2 = (1.0 + 0.2 * torch.randn(C, device=dev) for _ in range(2))
+    b1, b2 = (0.2 * torch.randn(C, device=dev) for _ in range(2))
+    step = torch.tensor([3], dtype=torch.int64, device=dev)
+
+    def run():
+        n0 = lib.oph_launch_count()
+        y, (z, stats) = ops.hc_fwd(x, pk, bias, g1, b1, g2, b2, rate, ops.CAUSAL if causal else ops.SAME, True, drop, 1234,
+                                   step, save=True)
+        torch.cuda.synchronize()
+        return y, y._oph_planes, z, stats, lib.oph_launch_count() - n0
+    # (flag 4: every CTA pair walks the k-blocks in the same order -- the two schedules give a row tile to different
+    # pairs, and the default per-pair rotation of the k-block order would change the summation order of z)
+    lib.oph_gemm_debug_flags(4 | 262144)          # (262144: the mixed schedule for a sparsely filled last round as well)
+    try:
+        y1, p1, z1, s1, n_fused = run()
+        lib.oph_gemm_debug_flags(131072 | 4)
+        y0, p0, z0, s0, n_sep = run()
+    finally:
+        lib.oph_gemm_debug_flags(0)
+    assert n_sep == 2
+    full_rounds_only = (-(-rows // 256)) % 74 == 0 or ((-(-rows // 256)) % 74) * 10 >= 74 * 7
+    assert n_fused == (1 if full_rounds_only else 2), n_fused
+    assert torch.equal(z1, z0) and torch.equal(s1, s0)
+    assert torch.equal(y1, y0), float((y1 - y0).abs().max())
+    assert torch.equal(p1[0], p0[0]) and torch.equal(p1[1], p0[1])
+    assert torch.isfinite(y1).all() and float(y1.abs().max()) > 0

@@ -72,16 +72,16 @@ for _ in range(a.iters):
     run()
 e1.record()
 torch.cuda.synchronize()
-prof = (ctypes.c_double * 21)()
+prof = (ctypes.c_double * 30)()
 lib.oph_profile_end(prof)
 ms = e0.elapsed_time(e1) / a.iters
 print("%s B%d L%d C%d k%d planes%d dbg%d: %.3f ms per call" % (a.op, B, L, C, k, a.planes, a.dbg, ms))
-for i, n in enumerate(["other", "conv_fwd", "dgrad", "wgrad", "attention"]):
+for i, n in ((0, "other"), (1, "conv_fwd"), (2, "dgrad"), (3, "wgrad"), (4, "attention"), (7, "hc_fwd")):
     if prof[3 * i] > 0:
         print("   gemm[%s]: %d launches/call, %.3f ms each, %.1f TFLOP/s algorithmic" %
               (n, prof[3 * i] / a.iters, prof[3 * i + 1] / prof[3 * i], prof[3 * i + 2] / prof[3 * i + 1] / 1e9))
 
-for i, n in ((5, "row fwd"), (6, "row bwd")):
+for i, n in ((5, "row fwd"), (6, "row bwd"), (8, "hc row fwd")):
     if prof[3 * i] > 0:
         print("   %s: %d launches/call, %.3f ms each, %.0f GB/s algorithmic" %
               (n, prof[3 * i] / a.iters, prof[3 * i + 1] / prof[3 * i], prof[3 * i + 2] / prof[3 * i + 1] / 1e6))
