@@ -105,8 +105,22 @@ def load():
         fn.argtypes = args
     _lib = lib
     if os.environ.get("OPH_DEBUG_FLAGS"):            # diagnostics only (A/B timing of scheduling features)
-        lib.oph_gemm_debug_flags(int(os.environ["OPH_DEBUG_FLAGS"], 0))
+        set_debug_flags(int(os.environ["OPH_DEBUG_FLAGS"], 0))
     return lib
+
+
+_debug_flags = 0
+
+
+def set_debug_flags(flags):
+    """oph_gemm_debug_flags, remembered on the host (a few wrappers size their buffers by the path the flags select)."""
+    global _debug_flags
+    _debug_flags = int(flags)
+    load().oph_gemm_debug_flags(_debug_flags)
+
+
+def debug_flags():
+    return _debug_flags
 
 
 def call(name, *args):

@@ -4,6 +4,7 @@
 #include "rowwise.cuh"
 #include "gemm_tc.cuh"
 #include "arstep.cuh"
+#include "attn_fused.cuh"
 
 #include <atomic>
 #include <cmath>
@@ -152,6 +153,7 @@ bool make_plane_tmap2d(CUtensorMap* out, const unsigned short* base, int C, long
 bool g_use_tma = true;
 bool g_use_split = true;
 bool g_use_ln_fuse = false;  // measured: 7.02 vs 7.04 ms per training step, but 0.71 vs 0.61 ms per autoregressive frame step
+bool g_use_attn_fuse = true; // networks.Attention forward as one kernel (oph_gemm_debug_flags bit 524288 turns it off)
 bool g_use_hc_fuse = true;   // highway tail in the epilogue phase of the conv GEMM (oph_gemm_debug_flags bit 131072 turns it off)
 
 int launch_gemm(GemmArgs& a, int zdim, cudaStream_t st) {
@@ -551,7 +553,7 @@ unsigned int oph_crc32c(const void* data, unsigned long long n, unsigned int crc
 const char* oph_last_error(void) { return g_err; }
 long long oph_launch_count(void) { return g_launches.load(); }
 int oph_gemm_debug_buffer(long long* dev_buf) { g_gemm_dbg = dev_buf; return OPH_OK; }
-int oph_gemm_debug_flags(int flags) { g_gemm_dbg_flags_host = flags; g_gemm_dbg_flags = flags & 0xA7; g_use_tma = !(flags & 8); g_use_split = !(flags & 16); g_use_pdl = (flags & 64) != 0; g_use_ln_fuse = (flags & 65536) != 0; g_use_hc_fuse = !(flags & 131072);
+int oph_gemm_debug_flags(int flags) { g_gemm_dbg_flags_host = flags; g_gemm_dbg_flags = flags & 0xA7; g_use_tma = !(flags & 8); g_use_split = !(flags & 16); g_use_pdl = (flags & 64) != 0; g_use_ln_fuse = (flags & 65536) != 0; g_use_hc_fuse = !(flags & 131072); g_use_attn_fuse = !(flags & 524288);
     g_hcb_depth = (flags >> 8) & 7;                    // 0 = automatic
     g_hcb_two = !(flags & 2048);
     if (g_hcb_depth == 1) g_hcb_depth = 2;
@@ -970,15 +972,43 @@ static int guide_tensor(GuideTensor& G, const oph_guide* guide, int N, int T) {
 int oph_attention_fwd(const oph_act* Q, const oph_act* K, const oph_act* V, const oph_act* A, const oph_act* Ro,
                       float* align_t, int32_t* argmax, const int32_t* prev_max, int win, double* att_acc, int maxN,
                       int maxT, float g_, int B, int T, int N, int d, const oph_guide* guide, oph_stream_t stream) {
-    if (!Q || !K || !V || !A || !A->f32 || !Ro || !Ro->f32) return fail(OPH_EINVAL, "attention_fwd: missing operand%s");
+    if (!Q || !K || !V || !A || !Ro || !Ro->f32) return fail(OPH_EINVAL, "attention_fwd: missing operand%s");
     GuideTensor G;
     OPH_TRY(guide_tensor(G, guide, N, T));
     float* R = Ro->f32; const long long ldr = Ro->ld;
     const long long ldA = A->ld;
-    if (ldA < N) return fail(OPH_EINVAL, "attention_fwd: ldA < N%s");
+    if (A->f32 && ldA < N) return fail(OPH_EINVAL, "attention_fwd: ldA < N%s");
     // all operands as split-bf16 planes: every tile of both products arrives through the copy engines
     const bool fed = g_use_tma && planes_ready(Q) && planes_ready(K) && planes_ready(V) && planes_ready(A);
     if (!fed && (!Q->f32 || !K->f32 || !V->f32)) return fail(OPH_EINVAL, "attention_fwd: operands need fp32 views or planes%s");
+    // One kernel for the whole block (attn_fused.cuh) when Q, K, V come as planes and the shape is the dc_tts one
+    if (g_use_attn_fuse && g_use_tma && planes_ready(Q) && planes_ready(K) && planes_ready(V) && d == 256 && N >= 1 && N <= 256 &&
+        !(A->hi && !planes_ready(A)) && !(Ro->hi && !planes_ready(Ro)) && !(ldr & 3)) {
+        AttnArgs a;
+        memset(&a, 0, sizeof(a));
+        a.B = B; a.T = T; a.N = N; a.d = d;
+        a.Npad = cdiv(N, 16) * 16; a.nblk = cdiv(a.Npad, 64); a.vslots = a.nblk <= 3 ? 2 : 1;
+        a.scale = 1.0f / sqrtf((float)d);
+        a.prev_max = prev_max; a.win = win;
+        a.A = A->f32; a.ldA = ldA; a.Ahi = A->hi; a.Alo = A->lo; a.ldAp = A->ldp;
+        a.align_t = align_t; a.argmax = argmax; a.att_acc = att_acc; a.maxN = maxN; a.maxT = maxT; a.g = g_; a.G = G;
+        a.R = R; a.ldr = ldr; a.Rhi = Ro->hi; a.Rlo = Ro->lo; a.ldrp = Ro->ldp;
+        if (make_plane_tmap(&a.tmQ_hi, Q->hi, d, T, B, Q->ldp, ATT_BM) && make_plane_tmap(&a.tmQ_lo, Q->lo, d, T, B, Q->ldp, ATT_BM) &&
+            make_plane_tmap(&a.tmK_hi, K->hi, d, N, B, K->ldp, a.Npad) && make_plane_tmap(&a.tmK_lo, K->lo, d, N, B, K->ldp, a.Npad) &&
+            make_plane_tmap(&a.tmV_hi, V->hi, d, N, B, V->ldp, 64) && make_plane_tmap(&a.tmV_lo, V->lo, d, N, B, V->ldp, 64)) {
+            static bool attr_done = false;
+            if (!attr_done) {
+                if (cudaFuncSetAttribute(attn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM) != cudaSuccess)
+                    return check_launch("cudaFuncSetAttribute(attn_fused)");
+                attr_done = true;
+            }
+            const int units = B * cdiv(T, ATT_BM);
+            ProfScope ps(OPH_TAG_ATTENTION, 4.0 * B * T * (double)N * d, S(stream));
+            launch_cfg(units < 148 ? units : 148, ATT_THREADS, ATT_SMEM, S(stream))(attn_fused_kernel, a);
+            return check_launch("attn_fused_kernel");
+        }
+    }
+    if (!A->f32) return fail(OPH_EINVAL, "attention_fwd: this shape runs as three launches and needs A (fp32 [B][T][ldA]) as scratch%s");
     {   // S = Q K^T / sqrt(d)
         GemmArgs g = blank();
         g.a_mode = A_KMAJOR; g.b_mode = B_KMAJOR;

@@ -145,7 +145,8 @@ def Attention(hp, Q, K, V, monotonic_attention=False, prev_max_attentions=None, 
         R_out._oph_planes = (hi[:, :, :d], lo[:, :, :d])
     R, A, alignments, max_attentions = ops.attention_fwd(
         Q, K, V, R=R_out, prev_max=prev, win=win if prev is not None else hp.attention_win_size, want_alignments=want_alignments,
-        att_acc=att_acc, maxN=hp.max_N, maxT=hp.max_T, g=hp.g, gts=gts, mse=mse)
+        att_acc=att_acc, maxN=hp.max_N, maxT=hp.max_T, g=hp.g, gts=gts, mse=mse,
+        need_A=bool(training and Tape.current is not None))
     result = rq if concat else R
     if concat:
         rq._oph_planes = rq._oph_planes_buf         # both halves are written now: AudioDec's first conv reads planes

@@ -359,21 +359,28 @@ def attention_extra_finalize(acc3, comps8, B, T, N, w_cdp, w_ain, w_aout, add_to
 
 
 def attention_fwd(Q, K, V, R=None, prev_max=None, win=3, want_alignments=False, want_argmax=True, att_acc=None,
-                  maxN=1, maxT=1, g=0.2, gts=None, mse=False):
+                  maxN=1, maxT=1, g=0.2, gts=None, mse=False, need_A=True):
+    """need_A=False (inference): the probabilities [B, T, N] are not wanted as such (the transposed `alignments` are a
+    separate output).  The one-kernel attention (d == 256, N <= 256) then keeps them on chip; the three-launch path needs
+    the buffer as scratch either way."""
     ldq, B, T, d = _rows(Q)
     ldk, _, N, _ = _rows(K)
     _rows(V)
     dev = Q.device
     ldA = _pad4(N)
-    A = torch.zeros(B, T, ldA, device=dev, dtype=torch.float32)[:, :, :N]
     if R is None:
         R = torch.empty(B, T, d, device=dev, dtype=torch.float32)
     align = torch.empty(B, N, T, device=dev, dtype=torch.float32) if want_alignments else None
     argmax = torch.empty(B, T, device=dev, dtype=torch.int32) if want_argmax else None
-    _new_planes(A)
     _rows(R)
     pq, pk_, pv = ensure_planes(Q), ensure_planes(K), ensure_planes(V)      # locals keep fresh splits alive over the call
-    _lib.call("oph_attention_fwd", _act(Q, planes=pq), _act(K, planes=pk_), _act(V, planes=pv), _act(A), _act(R), _p(align),
+    if need_A or not (d == 256 and N <= 256) or _lib.debug_flags() & (524288 | 8):
+        A = torch.zeros(B, T, ldA, device=dev, dtype=torch.float32)[:, :, :N]
+        _new_planes(A)
+        Aa = _act(A)
+    else:
+        A, Aa = None, _lib.Act()
+    _lib.call("oph_attention_fwd", _act(Q, planes=pq), _act(K, planes=pk_), _act(V, planes=pv), Aa, _act(R), _p(align),
               _p(argmax), _p(prev_max), int(win), _p(att_acc), int(maxN), int(maxT), float(g), B, T, N, d, _guide(gts, mse),
               _stream())
     return R, A, align, argmax

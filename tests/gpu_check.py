@@ -437,7 +437,8 @@ GROUPS = {
     "hc_planes": [case_hc_planes(2, 200, 256, 3, 3, 1), case_hc_planes(2, 70, 512, 3, 27, 0), case_hc_planes(1, 130, 1024, 3, 1, 0)],
     "deconv": [case_deconv(2, 50, 512), case_deconv(1, 131, 256)],
     "attention": [case_attention(2, 200, 60, False), case_attention(2, 210, 180, True),
-                  case_attention(3, 130, 47, False)],
+                  case_attention(3, 130, 47, False), case_attention(2, 300, 256, True), case_attention(1, 129, 130, False),
+                  case_attention(4, 85, 150, True), case_attention(3, 870, 180, False)],
     "misc": [case_embed, case_loss_adam, case_pack_batch, case_dropout],
 }
 

@@ -133,3 +133,49 @@ def test_fused_highway_tail_equals_separate_tail(C, rows, k, rate, causal, drop)
     assert torch.equal(y1, y0), float((y1 - y0).abs().max())
     assert torch.equal(p1[0], p0[0]) and torch.equal(p1[1], p0[1])
     assert torch.isfinite(y1).all() and float(y1.abs().max()) > 0
+
+
+@pytest.mark.parametrize("B,T,N,mono", [(32, 870, 180, False), (10, 85, 150, True), (3, 200, 256, True), (2, 131, 17, False)])
+def test_fused_attention_equals_three_launch_path(B, T, N, mono):
+    """networks.Attention forward as one kernel (S and P stay in tensor / shared memory) against the three-launch path
+    (two GEMM launches + the softmax kernel, oph_gemm_debug_flags bit 524288), which the `attention` group pins to the
+    oracle: the scores come out of the same MMA sequence, so the argmax must agree exactly, the probabilities, the context
+    vectors and the loss sum up to the summation order of the softmax; and it really is one launch."""
+    import torch
+    from ophelia_b200 import _lib, ops
+    lib = _lib.load()
+    torch.manual_seed(B * T + N)
+    dev, d = "cuda:0", 256
+    buf = torch.zeros(B, T, 2 * d, device=dev)
+    Q = buf[:, :, d:]
+    Q.copy_(torch.randn(B, T, d, device=dev))
+    KV = torch.randn(B, N, 2 * d, device=dev)
+    K, V = KV[:, :, :d], KV[:, :, d:]
+    prev = torch.randint(0, max(1, N - 2), (B,), dtype=torch.int32, device=dev) if mono else None
+
+    def run(need_A):
+        acc = torch.zeros(1, device=dev, dtype=torch.float64)
+        R = torch.zeros(B, T, d, device=dev)
+        n0 = lib.oph_launch_count()
+        R, A, align, argmax = ops.attention_fwd(Q, K, V, R=R, prev_max=prev, win=3, want_alignments=True, att_acc=acc,
+                                                maxN=N, maxT=T, g=0.2, need_A=need_A)
+        torch.cuda.synchronize()
+        return R, A, align, argmax, float(acc[0]), lib.oph_launch_count() - n0
+    R1, A1, al1, am1, acc1, n1 = run(True)
+    R2, A2, al2, am2, acc2, n2 = run(False)          # inference form: the probabilities stay on chip
+    _lib.set_debug_flags(524288)
+    try:
+        R0, A0, al0, am0, acc0, n0 = run(True)
+    finally:
+        _lib.set_debug_flags(0)
+    # launches: Q / K / V planes are split by ensure_planes (3 small launches) in both modes
+    assert n0 - n1 == 2 and n2 == n1 and A2 is None
+    assert torch.equal(am1, am0) and torch.equal(am2, am0)
+    assert float((al1 - al0).abs().max()) < 2e-6 and float((A1 - A0).abs().max()) < 2e-6
+    assert torch.equal(al1.transpose(1, 2), A1)
+    assert float((R1 - R0).abs().max()) < 2e-5 * max(1.0, float(R0.abs().max()))
+    assert torch.equal(R2, R1) and torch.equal(al2, al1)
+    assert abs(acc1 - acc0) < 1e-5 * max(1.0, abs(acc0))
+    pl1, pl0 = A1._oph_planes, A0._oph_planes
+    assert float((pl1[0].float() + pl1[1].float() - A1).abs().max()) < 1e-5
+    assert float((pl0[0].float() + pl0[1].float() - A0).abs().max()) < 1e-5

@@ -59,7 +59,7 @@ def run():
 
 dbg = torch.zeros(74, 8, dtype=torch.int64, device=dev)
 _lib.call("oph_gemm_debug_buffer", dbg.data_ptr())
-_lib.call("oph_gemm_debug_flags", a.dbg)
+_lib.set_debug_flags(a.dbg)
 for _ in range(a.warmup):
     run()
 torch.cuda.synchronize()
