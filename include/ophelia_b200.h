@@ -219,6 +219,10 @@ int oph_attention_bwd(const oph_act* dR, const oph_act* Q, const oph_act* K, con
                       const oph_act* dA, float* dQ, long long lddq, const float* dq_addend, long long ldqa, float* dK,
                       long long lddk, float* dV, long long lddv, float att_coef, int maxN, int maxT, float g, int B,
                       int T, int N, int d, const oph_guide* guide, oph_stream_t stream);
+/* networks.FixedAttention (networks.py:327-358) takes its alignments A [B][T][ldA] from outside (external durations) but
+ * reports the same guided-attention term: att_acc += sum A*W over n < maxN, t < maxT (guide as in oph_attention_fwd). */
+int oph_attention_guide_sum(const float* A, long long ldA, int B, int T, int N, double* att_acc, int maxN, int maxT, float g,
+                            const oph_guide* guide, oph_stream_t stream);
 /* "Confidence through attention" losses (hp.lw_cdp / lw_ain / lw_aout, architectures.py:283-321) over the alignments
  * A [B][T][ldA] of a training batch: coverage deviation penalty and the two attention entropies.
  * extra_fwd: acc3 (device double[3], zeroed by the caller) += (sum log(1 + (1 - s)^2), sum_t P log P summed over keys,

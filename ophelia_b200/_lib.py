@@ -64,6 +64,7 @@ SIGNATURES = {
     "oph_embed_bwd": (I, [P, P, LL, P, I, I, P]),
     "oph_attention_fwd": (I, [AP, AP, AP, AP, AP, P, P, P, I, P, I, I, F, I, I, I, I, GP, P]),
     "oph_attention_bwd": (I, [AP, AP, AP, AP, AP, AP, P, LL, P, LL, P, LL, P, LL, F, I, I, F, I, I, I, I, GP, P]),
+    "oph_attention_guide_sum": (I, [P, LL, I, I, I, P, I, I, F, GP, P]),
     "oph_attention_extra_fwd": (I, [P, LL, I, I, I, F, F, P, P, P, P]),
     "oph_attention_extra_finalize": (I, [P, P, I, I, I, F, F, F, I, P]),
     "oph_split_planes": (I, [P, LL, LL, I, P, P, LL, P]),

@@ -16,7 +16,7 @@ import torch
 
 from . import ops
 from .modules import Tape
-from .networks import SSRN, Attention, AudioDec, AudioEnc, TextEnc
+from .networks import SSRN, Attention, AudioDec, AudioEnc, FixedAttention, LinearTransformLabels, MerlinTextEnc, TextEnc
 from .variables import VariableStore, mix_dropout_seed, use_store, variable_scope
 
 _default_stores = {}
@@ -41,31 +41,76 @@ def _hc_specs(out, prefix, name, k, c, norm=True):
             out.append((s + "/%s/gamma" % h, (c,), "ones"))
 
 
-def text2mel_variables(hp):
+def _speaker_embed(out, prefix, i, hp):
+    out.append(("%s/embed_%d/lookup_table" % (prefix, i), (hp.nspeakers, hp.speaker_embedding_size), "embed"))
+
+
+def _text_encoder_body_specs(out, p, i, cin, hp, ms, nrm):
+    """C (relu), C, 10 k=3 highway layers, [speaker embedding + C], 2 k=1 highway layers (networks.py:146-209)."""
+    d = hp.d
+    _conv_specs(out, p, "C_%d" % i, 1, cin, 2 * d, nrm); i += 1
+    _conv_specs(out, p, "C_%d" % i, 1, 2 * d, 2 * d, nrm); i += 1
+    for _ in range(10):
+        _hc_specs(out, p, "HC_%d" % i, 3, 2 * d, nrm); i += 1
+    if 'text_encoder_towards_end' in ms:
+        _speaker_embed(out, p, i, hp); i += 1
+        _conv_specs(out, p, "C_%d" % i, 1, 2 * d + hp.speaker_embedding_size, 2 * d, nrm); i += 1
+    for _ in range(2):
+        _hc_specs(out, p, "HC_%d" % i, 1, 2 * d, nrm); i += 1
+
+
+def text2mel_variables(hp, with_text_encoder=True, with_audio=True):
     """Creation-ordered variable inventory of `Text2MelGraph` (TF names; 209 variables / 23 974 512 values for
-    the LJ configs, cf. the structural known answers at train.py:194)."""
+    the LJ configs, cf. the structural known answers at train.py:194).  The layer counter of every network also counts
+    the speaker embeddings of hp.multispeaker, like the reference's `i` (networks.py:133-144 etc.)."""
     V, e, d, nm, nrm = len(hp.vocab), hp.e, hp.d, hp.n_mels, hp.norm == 'layer'
-    out = [("Text2Mel/TextEnc/embed_1/lookup_table", (V, e), "embed")]
-    p = "Text2Mel/TextEnc"
-    _conv_specs(out, p, "C_2", 1, e, 2 * d, nrm)
-    _conv_specs(out, p, "C_3", 1, 2 * d, 2 * d, nrm)
-    for i in range(4, 14):
-        _hc_specs(out, p, "HC_%d" % i, 3, 2 * d, nrm)
-    for i in range(14, 16):
-        _hc_specs(out, p, "HC_%d" % i, 1, 2 * d, nrm)
+    ms = getattr(hp, "multispeaker", [])
+    S = getattr(hp, "speaker_embedding_size", 0)
+    out = []
+    enc = hp.text_encoder_type if with_text_encoder else 'none'
+    if enc == 'DCTTS_standard':
+        p = "Text2Mel/TextEnc"
+        out.append((p + "/embed_1/lookup_table", (V, e), "embed"))
+        i, cin = 2, e
+        if 'text_encoder_input' in ms:
+            _speaker_embed(out, p, i, hp); i += 1; cin += S
+        _text_encoder_body_specs(out, p, i, cin, hp, ms, nrm)
+    elif enc == 'MerlinTextEnc':
+        p = "Text2Mel/MerlinTextEnc"
+        _conv_specs(out, p, "C_1", 1, hp.merlin_lab_dim, e, nrm)           # LinearTransformLabels(out_dim=hp.e, i=1)
+        i, cin = 2, e
+        if hp.MerlinTextEncWithPhoneEmbedding:
+            out.append(("%s/embed_%d/lookup_table" % (p, i), (V, e), "embed")); i += 1; cin += e
+        if 'text_encoder_input' in ms:
+            _speaker_embed(out, p, i, hp); i += 1; cin += S
+        _text_encoder_body_specs(out, p, i, cin, hp, ms, nrm)
+    elif enc == 'minimal_feedforward':                                   # K = V = LinearTransformLabels (architectures.py:197-200)
+        _conv_specs(out, "Text2Mel", "C_1", 1, hp.merlin_lab_dim, d, nrm)
+    else:
+        assert enc == 'none', enc                                         # K = V = the labels themselves
+    if not with_audio:
+        return out
     p = "Text2Mel/AudioEnc"
     _conv_specs(out, p, "C_1", 1, nm, d, nrm)
-    _conv_specs(out, p, "C_2", 1, d, d, nrm)
-    _conv_specs(out, p, "C_3", 1, d, d, nrm)
-    for i in range(4, 14):
-        _hc_specs(out, p, "HC_%d" % i, 3, d, nrm)
+    i = 2
+    if 'audio_encoder_input' in ms:
+        _speaker_embed(out, p, i, hp); i += 1
+        _conv_specs(out, p, "C_%d" % i, 1, d + S, d, nrm); i += 1
+    for _ in range(2):
+        _conv_specs(out, p, "C_%d" % i, 1, d, d, nrm); i += 1
+    for _ in range(10):
+        _hc_specs(out, p, "HC_%d" % i, 3, d, nrm); i += 1
     p = "Text2Mel/AudioDec"
     _conv_specs(out, p, "C_1", 1, 2 * d if hp.concatenate_query else d, d, nrm)
-    for i in range(2, 8):
-        _hc_specs(out, p, "HC_%d" % i, 3, d, nrm)
-    for i in range(8, 11):
-        _conv_specs(out, p, "C_%d" % i, 1, d, d, nrm)
-    _conv_specs(out, p, "C_11", 1, d, nm, nrm)
+    i = 2
+    if 'audio_decoder_input' in ms:
+        _speaker_embed(out, p, i, hp); i += 1
+        _conv_specs(out, p, "C_%d" % i, 1, d + S, d, nrm); i += 1
+    for _ in range(6):
+        _hc_specs(out, p, "HC_%d" % i, 3, d, nrm); i += 1
+    for _ in range(3):
+        _conv_specs(out, p, "C_%d" % i, 1, d, d, nrm); i += 1
+    _conv_specs(out, p, "C_%d" % i, 1, d, nm, nrm)
     return out
 
 
@@ -73,6 +118,9 @@ def ssrn_variables(hp):
     c, nm, F, nrm = hp.c, hp.n_mels, hp.full_dim, hp.norm == 'layer'
     out, p, i = [], "SSRN", 1
     _conv_specs(out, p, "C_%d" % i, 1, nm, c, nrm); i += 1
+    if 'ssrn_input' in getattr(hp, "multispeaker", []):                  # networks.py:457-465
+        _speaker_embed(out, p, i, hp); i += 1
+        _conv_specs(out, p, "C_%d" % i, 1, c + hp.speaker_embedding_size, c, nrm); i += 1
     for _ in range(2):
         _hc_specs(out, p, "HC_%d" % i, 3, c, nrm); i += 1
     for _ in range({4: 2, 8: 3}[hp.r]):
@@ -340,7 +388,7 @@ class Graph(object):
 # ====================================================================================================== SSRN
 class SSRNGraph(Graph):
     scope_name = "SSRN"
-    node_names = ("mels", "mags", "Z_logits", "Z", "loss", "loss_components", "train_op", "global_step")
+    node_names = ("mels", "mags", "speakers", "Z_logits", "Z", "loss", "loss_components", "train_op", "global_step")
     batch_fields = ("mel", "mag")
 
     def variable_specs(self, hp):
@@ -349,30 +397,34 @@ class SSRNGraph(Graph):
     def get_batchsize(self):
         return self.hp.batchsize['ssrn']
 
-    def build_model(self, mels, training):
+    def build_model(self, mels, training, speakers=None):
         with use_store(self.store), variable_scope("SSRN"):
-            return SSRN(self.hp, mels, training=training, speaker_codes=None, reuse=self.reuse)
+            return SSRN(self.hp, mels, training=training, speaker_codes=speakers, reuse=self.reuse)
 
     def forward(self, feeds):
         mels = self._to_device(feeds["mels"], torch.float32)
-        logits, Z = self.build_model(mels, False)
+        speakers = self._to_device(feeds["speakers"], torch.int32) if self.hp.multispeaker else None
+        logits, Z = self.build_model(mels, False, speakers)
         return {"mels": mels, "Z_logits": logits, "Z": Z}
 
     def train_step(self, batch=None):
+        fields = [("mel", torch.float32), ("mag", torch.float32)]
+        if self.hp.multispeaker:
+            fields.append(("speaker", torch.int32))
         if batch is None:
-            mels, mags = self._next_inputs((("mel", torch.float32), ("mag", torch.float32)))
+            inputs = self._next_inputs(tuple(fields))
         else:
-            mels = self._to_device(batch["mel"], torch.float32)
-            mags = self._to_device(batch["mag"], torch.float32)
-        return self._step_maybe_graphed(mels, mags)
+            inputs = tuple(self._to_device(batch[k], dt) for k, dt in fields)
+        return self._step_maybe_graphed(*inputs)
 
-    def train_step_device(self, mels, mags):
+    def train_step_device(self, mels, mags, speakers=None):
         hp, st = self.hp, self.store
+        assert (speakers is not None) == bool(hp.multispeaker), "hp.multispeaker <=> batches carry 'speaker'"
         mels._oph_no_grad = True
         st.grad_flat.zero_()
         acc = torch.zeros(4, dtype=torch.float64, device=self.device)
         with Tape() as tape:
-            logits, Z = self.build_model(mels, True)
+            logits, Z = self.build_model(mels, True, speakers)
         w1, wbd, _, w2 = _loss_weights(hp, "ssrn")
         squash = hp.squash_output_ssrn
         dlogits = ops.recon_loss(logits, mags, acc, squash, w1, wbd if squash else 0.0, w2)
@@ -402,20 +454,52 @@ class SSRNGraph(Graph):
 # ====================================================================================================== Text2Mel
 class Text2MelGraph(Graph):
     scope_name = "Text2Mel"
-    node_names = ("L", "mels", "prev_max_attentions", "K", "V", "Q", "R", "alignments", "max_attentions",
-                  "Y_logits", "Y", "loss", "loss_components", "train_op", "global_step")
+    node_names = ("L", "mels", "prev_max_attentions", "speakers", "durations", "merlin_label", "K", "V", "Q", "R",
+                  "alignments", "max_attentions", "Y_logits", "Y", "loss", "loss_components", "train_op", "global_step")
 
     def variable_specs(self, hp):
-        assert hp.text_encoder_type == 'DCTTS_standard' and hp.history_type == 'DCTTS_standard' \
-            and not hp.use_external_durations, "label-input / fixed-attention variants are outside the path"
+        assert hp.text_encoder_type in ('DCTTS_standard', 'none', 'minimal_feedforward', 'MerlinTextEnc'), hp.text_encoder_type
+        assert hp.history_type == 'DCTTS_standard', "position-in-phone histories (architectures.py:211-212) are not built"
+        assert hp.text_encoder_type == 'DCTTS_standard' or hp.merlin_label_dir, "label encoders need hp.merlin_label_dir"
         return text2mel_variables(hp)
+
+    def extra_fields(self):
+        """Batch fields beyond text and mel that this configuration reads (architectures.py:46-65)."""
+        hp, f = self.hp, []
+        if hp.attention_guide_dir:
+            f.append(("attention_guide", torch.float32))
+        if hp.multispeaker:
+            f.append(("speaker", torch.int32))
+        if hp.use_external_durations:
+            f.append(("duration", torch.float32))
+        if hp.merlin_label_dir:
+            f.append(("merlin_label", torch.float32))
+        return f
+
+    def text_encoder(self, L, training, speakers=None, merlin_label=None):
+        """The four text encoder types of architectures.py:192-206 -> K, V."""
+        hp = self.hp
+        enc = hp.text_encoder_type
+        if enc == 'none':
+            assert merlin_label.shape[-1] == hp.d, "text_encoder_type 'none' feeds the labels to the attention as they are"
+            K = V = merlin_label
+        elif enc == 'minimal_feedforward':
+            K = V = LinearTransformLabels(hp, merlin_label, training=training, reuse=self.reuse)
+        elif enc == 'MerlinTextEnc':
+            with variable_scope("MerlinTextEnc"):
+                K, V = MerlinTextEnc(hp, L, merlin_label, training=training, speaker_codes=speakers, reuse=self.reuse)
+        else:
+            with variable_scope("TextEnc"):
+                K, V = TextEnc(hp, L, training=training, speaker_codes=speakers, reuse=self.reuse)
+        return K, V
 
     def get_batchsize(self):
         return self.hp.batchsize['t2m']
 
     # architectures.py:188-239
     def build_model(self, L, mels, training, K=None, V=None, prev_max_attentions=None, att_acc=None,
-                    want_alignments=True, tapes=None, text_stream=None, gts=None, extra=None, text_lengths=None):
+                    want_alignments=True, tapes=None, text_stream=None, gts=None, extra=None, text_lengths=None,
+                    speakers=None, durations=None, merlin_label=None):
         hp = self.hp
         mono = self.mode == 'synthesize'
         out = {}
@@ -431,26 +515,41 @@ class Text2MelGraph(Graph):
                 if text_stream is not None:                      # TextEnc and AudioEnc are independent chains
                     text_stream.wait_stream(main)
                     forked = True
-                with variable_scope("TextEnc"), on(t_text), (torch.cuda.stream(text_stream) if forked else _NullCtx()):
-                    K, V = TextEnc(hp, L, training=training, speaker_codes=None, reuse=self.reuse)
+                with on(t_text), (torch.cuda.stream(text_stream) if forked else _NullCtx()):
+                    K, V = self.text_encoder(L, training, speakers, merlin_label)
             with variable_scope("AudioEnc"), on(t_aenc):
-                Q = AudioEnc(hp, mels, training=training, speaker_codes=None, reuse=self.reuse, in_shift=1)
+                Q = AudioEnc(hp, mels, training=training, speaker_codes=speakers, reuse=self.reuse, in_shift=1)
             if forked:
                 main.wait_stream(text_stream)
             with variable_scope("Attention"), on(t_dec):
-                R, alignments, max_attentions = Attention(
-                    hp, Q, K, V, monotonic_attention=mono, prev_max_attentions=prev_max_attentions if mono else None,
-                    training=training, att_acc=att_acc, want_alignments=want_alignments, gts=gts, extra=extra,
-                    text_lengths=text_lengths)
+                if hp.use_external_durations:                    # architectures.py:222-223
+                    R, alignments, max_attentions = FixedAttention(hp, durations, Q, V, training=training, att_acc=att_acc,
+                                                                   gts=gts)
+                else:
+                    R, alignments, max_attentions = Attention(
+                        hp, Q, K, V, monotonic_attention=mono, prev_max_attentions=prev_max_attentions if mono else None,
+                        training=training, att_acc=att_acc, want_alignments=want_alignments, gts=gts, extra=extra,
+                        text_lengths=text_lengths)
             with variable_scope("AudioDec"), on(t_dec):
-                Y_logits, Y = AudioDec(hp, R, training=training, speaker_codes=None, reuse=self.reuse)
+                Y_logits, Y = AudioDec(hp, R, training=training, speaker_codes=speakers, reuse=self.reuse)
         out.update(K=K, V=V, Q=Q, R=R, alignments=alignments, max_attentions=max_attentions, Y_logits=Y_logits, Y=Y)
         return out
 
+    def _variant_feeds(self, feeds):
+        """Device copies of the placeholders of architectures.py:69-93 that this configuration has."""
+        hp = self.hp
+        speakers = self._to_device(feeds["speakers"], torch.int32) if hp.multispeaker and "speakers" in feeds else None
+        durations = self._to_device(feeds["durations"], torch.float32) if hp.use_external_durations else None
+        labels = self._to_device(feeds["merlin_label"], torch.float32) if hp.merlin_label_dir and "merlin_label" in feeds else None
+        return speakers, durations, labels
+
     def encode_text(self, feeds):
-        L = self._to_device(feeds["L"], torch.int32, ids=True)
-        with use_store(self.store), variable_scope("Text2Mel"), variable_scope("TextEnc"):
-            K, V = TextEnc(self.hp, L, training=False, speaker_codes=None, reuse=self.reuse)
+        hp = self.hp
+        L = self._to_device(feeds["L"], torch.int32, ids=True) if "L" in feeds else None
+        speakers = self._to_device(feeds["speakers"], torch.int32) if hp.multispeaker and "speakers" in feeds else None
+        labels = self._to_device(feeds["merlin_label"], torch.float32) if "merlin_label" in feeds else None
+        with use_store(self.store), variable_scope("Text2Mel"):
+            K, V = self.text_encoder(L, False, speakers, labels)
         return {"L": L, "K": K, "V": V}
 
     def forward(self, feeds, want_alignments=True):
@@ -459,32 +558,48 @@ class Text2MelGraph(Graph):
         if "K" in feeds:
             K = self._to_device(feeds["K"], torch.float32)
             V = self._to_device(feeds["V"], torch.float32)
-        else:
+        elif "L" in feeds:
             L = self._to_device(feeds["L"], torch.int32, ids=True)
-        if self.mode == 'synthesize':
+        if self.mode == 'synthesize' and not self.hp.use_external_durations:
             prev = self._to_device(feeds["prev_max_attentions"], torch.int32)
-        out = self.build_model(L, mels, False, K=K, V=V, prev_max_attentions=prev, want_alignments=want_alignments)
+        speakers, durations, labels = self._variant_feeds(feeds)
+        out = self.build_model(L, mels, False, K=K, V=V, prev_max_attentions=prev, want_alignments=want_alignments,
+                               speakers=speakers, durations=durations, merlin_label=labels)
         out["mels"] = mels
         return out
 
     batch_fields = ("text", "mel")            # what a Text2Mel step needs from data_load.get_batch (no magnitudes)
 
+    def _text_grad(self, dKV):
+        """Gradient of the text encoder's output from [dK | dV].  TextEnc / MerlinTextEnc end in tf.split, so it is dKV as
+        it stands; with K = V = one tensor (text_encoder_type 'minimal_feedforward', architectures.py:197-200) the two
+        halves add up (a [B, N, d] sum outside the kernels: this variant's only extra arithmetic)."""
+        if self.hp.text_encoder_type == 'minimal_feedforward':
+            d = dKV.shape[-1] // 2
+            return (dKV[:, :, :d] + dKV[:, :, d:]).contiguous()
+        return dKV
+
     def train_step(self, batch=None):
-        fields = [("text", torch.int32), ("mel", torch.float32)]
-        if self.hp.attention_guide_dir:                      # self.gts = batchdict['attention_guide'] (architectures.py:57-58)
-            fields.append(("attention_guide", torch.float32))
+        fields = [("text", torch.int32), ("mel", torch.float32)] + self.extra_fields()
         if batch is None:
             inputs = self._next_inputs(tuple(fields))
         else:
             inputs = tuple(self._to_device(batch[k], dt, ids=(k == "text")) for k, dt in fields)
         return self._step_maybe_graphed(*inputs)
 
-    def train_step_device(self, L, mels, gts=None):
+    def train_step_device(self, L, mels, *extras, gts=None):
         """One `sess.run([global_step, loss_components, train_op])` with inputs already on the device.
         Returns loss_components [loss, L1, BD, att, L2] as a device tensor (architectures.py:352-355).
         gts: the batch's attention guides / forced-alignment targets [B, Ng, Tg] when hp.attention_guide_dir is set
         (else the analytic global guide of utils.py:155-164)."""
         hp, st = self.hp, self.store
+        # positional extras follow extra_fields(): attention_guide, speaker, duration, merlin_label
+        named = dict(zip([k for k, _ in self.extra_fields()], extras))
+        assert len(extras) == len(named), "inputs after (L, mels) must be exactly the fields of extra_fields()"
+        gts = named.get("attention_guide", gts)
+        speakers, durations, merlin_label = named.get("speaker"), named.get("duration"), named.get("merlin_label")
+        if merlin_label is not None:
+            merlin_label._oph_no_grad = True
         assert (gts is not None) == bool(hp.attention_guide_dir), \
             "hp.attention_guide_dir set <=> batches carry 'attention_guide' (architectures.py:57-60)"
         assert not hp.attention_guide_fa or gts is not None, "the MSE attention loss needs targets from hp.attention_guide_dir"
@@ -502,12 +617,13 @@ class Text2MelGraph(Graph):
         tapes = (Tape(), Tape(), Tape())
         side = self._streams()
         out = self.build_model(L, mels, True, att_acc=acc[3:], want_alignments=False, tapes=tapes,
-                               text_stream=side[0] if side else None, gts=gts, extra=extra)
+                               text_stream=side[0] if side else None, gts=gts, extra=extra, speakers=speakers,
+                               durations=durations, merlin_label=merlin_label)
         w1, wbd, watt, w2 = _loss_weights(hp, "t2m")
         squash = hp.squash_output_t2m
         logits = out["Y_logits"]
         B, T, nm = logits.shape
-        N = L.shape[1]
+        N = out["K"].shape[1]
         n_att = float(B * min(N, hp.max_N) * min(T, hp.max_T))        # mask_sum of architectures.py:266-268
         dlogits = ops.recon_loss(logits, mels, acc, squash, w1, wbd if squash else 0.0, w2)
         comps = torch.empty(8 if extra else 5, device=self.device, dtype=torch.float32)
@@ -520,7 +636,7 @@ class Text2MelGraph(Graph):
             dRp = t_dec.backward(dlogits)
             dQ, dKV = out["R"]._oph_attention_bwd(dRp, watt / n_att)
             t_aenc.backward(dQ)
-            t_text.backward(dKV)
+            t_text.backward(self._text_grad(dKV))
         else:
             # main: AudioDec -> Attention -> AudioEnc;  s_text: TextEnc;  s_w1 / s_w2: their weight-gradient GEMMs
             main = torch.cuda.current_stream(self.device)
@@ -542,7 +658,7 @@ class Text2MelGraph(Graph):
                 with torch.cuda.stream(s_text):
                     ops.set_wgrad_stream(s_w2)
                     marks = {6: lambda: buckets.launch(1, after=(s_text, s_w2))} if buckets else None   # HC_15..HC_10 done
-                    t_text.backward(dKV, release=False, marks=marks)
+                    t_text.backward(self._text_grad(dKV), release=False, marks=marks)
                     if buckets:
                         buckets.launch(0, after=(s_text, s_w2))
                 ops.set_wgrad_stream(s_w1)
@@ -561,6 +677,97 @@ class Text2MelGraph(Graph):
             return comps
         self._apply_gradients()
         return comps
+
+
+class TextEncGraph(Text2MelGraph):
+    """architectures.py:367-376: partial graph for deployment, the text encoder only (K, V from L)."""
+    node_names = ("L", "speakers", "merlin_label", "K", "V")
+
+    def variable_specs(self, hp):
+        return text2mel_variables(hp, with_audio=False)
+
+    def forward(self, feeds, want_alignments=True):
+        return self.encode_text(feeds)
+
+
+class BabblerGraph(Graph):
+    """architectures.py:380-432: AudioEnc + AudioDec predicting the next frame from the audio history alone, with all-zero
+    text encoder outputs in place of the attention context (semi-supervised pre-training, Chung et al. 2018).  Scope names
+    are those of the full Text2Mel model so that its weights can initialise one."""
+    scope_name = "Text2Mel"
+    node_names = ("mels", "Q", "R", "Y_logits", "Y", "loss", "loss_components", "train_op", "global_step")
+    batch_fields = ("mel",)
+
+    def variable_specs(self, hp):
+        assert not hp.multispeaker, "the babbler's AudioEnc takes no speaker codes (architectures.py:402)"
+        assert hp.concatenate_query, "R = concat(zeros, Q)"
+        return text2mel_variables(hp, with_text_encoder=False)
+
+    def get_batchsize(self):
+        return self.hp.batchsize.get('babbler', 32)
+
+    def build_model(self, mels, training, tapes=None):
+        hp = self.hp
+        t_aenc, t_dec = tapes if tapes else (None, None)
+        on = lambda tape: tape if tape is not None else _NullCtx()     # noqa: E731
+        with use_store(self.store), variable_scope("Text2Mel"):
+            with variable_scope("AudioEnc"), on(t_aenc):
+                Q = AudioEnc(hp, mels, training=training, reuse=self.reuse, in_shift=1)
+            rq = Q._oph_rq                                              # [R | Q]: Q already sits in the second half
+            d = Q.shape[-1]
+            rq[:, :, :d].zero_()                                        # dummy_R_prime = tf.zeros_like(self.Q)
+            hi, lo = rq._oph_planes_buf
+            hi[:, :, :d].zero_(); lo[:, :, :d].zero_()
+            rq._oph_planes = rq._oph_planes_buf
+            with variable_scope("AudioDec"), on(t_dec):
+                Y_logits, Y = AudioDec(hp, rq, training=training, speaker_codes=None, reuse=self.reuse)
+        return {"Q": Q, "R": rq, "Y_logits": Y_logits, "Y": Y}
+
+    def forward(self, feeds, want_alignments=False):
+        mels = self._to_device(feeds["mels"], torch.float32)
+        out = self.build_model(mels, False)
+        out["mels"] = mels
+        return out
+
+    def train_step(self, batch=None):
+        fields = (("mel", torch.float32),)
+        inputs = self._next_inputs(fields) if batch is None else tuple(self._to_device(batch[k], dt) for k, dt in fields)
+        return self._step_maybe_graphed(*inputs)
+
+    def train_step_device(self, mels):
+        """loss_components = [loss, L1, BD] with hp.loss_weights['babbler'] (architectures.py:412-424)."""
+        hp, st = self.hp, self.store
+        mels._oph_no_grad = True
+        st.grad_flat.zero_()
+        acc = torch.zeros(4, dtype=torch.float64, device=self.device)
+        tapes = (Tape(), Tape())
+        out = self.build_model(mels, True, tapes=tapes)
+        w = hp.loss_weights['babbler']
+        logits = out["Y_logits"]
+        B, T, nm = logits.shape
+        dlogits = ops.recon_loss(logits, mels, acc, True, w['L1'], w['binary_divergence'], 0.0)
+        comps = torch.empty(4, device=self.device, dtype=torch.float32)
+        ops.loss_finalize(acc, comps, B * T * nm, 1.0, w['L1'], w['binary_divergence'], 0.0, 0.0, False, True)
+        t_aenc, t_dec = tapes
+        d = out["Q"].shape[-1]
+        side = self._streams()
+        main = torch.cuda.current_stream(self.device)
+        if side is not None:
+            side[1].wait_stream(main)
+            ops.set_wgrad_stream(side[1])
+        try:
+            dRp = t_dec.backward(dlogits, release=False)
+            t_aenc.backward(dRp[:, :, d:], release=False)               # the zero half of R has no producer
+        finally:
+            keep = ops.take_keepalive() if side is not None else None
+            ops.set_wgrad_stream(None)
+        if side is not None:
+            main.wait_stream(side[1])
+        for t in tapes:
+            t.release()
+        del keep
+        self._apply_gradients()
+        return comps[:3]
 
 
 class _NullCtx(object):

@@ -1035,6 +1035,15 @@ int oph_attention_fwd(const oph_act* Q, const oph_act* K, const oph_act* V, cons
     return OPH_OK;
 }
 
+int oph_attention_guide_sum(const float* A, long long ldA, int B, int T, int N, double* att_acc, int maxN, int maxT, float g_,
+                            const oph_guide* guide, oph_stream_t stream) {
+    if (!A || !att_acc || B < 1 || T < 1 || N < 1 || ldA < N) return fail(OPH_EINVAL, "attention_guide_sum: missing operand%s");
+    GuideTensor G;
+    OPH_TRY(guide_tensor(G, guide, N, T));
+    launch_cfg(rows_grid((long long)B * T, 8), 256, 0, S(stream))(guide_sum_kernel, A, ldA, B, T, N, att_acc, maxN, maxT, g_, G);
+    return check_launch("guide_sum_kernel");
+}
+
 int oph_attention_extra_fwd(const float* A, long long ldA, int B, int T, int N, float c_cdp, float c_ain, float* col_g,
                             float* col_h, double* acc3, oph_stream_t stream) {
     if (!A || !col_g || !col_h || !acc3 || B < 1 || T < 1 || N < 1) return fail(OPH_EINVAL, "attention_extra_fwd: missing operand%s");

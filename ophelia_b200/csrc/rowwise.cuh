@@ -347,6 +347,39 @@ __global__ void softmax_fwd_kernel(float* __restrict__ S, long long ldS, int B, 
     }
 }
 
+// The guided-attention sum of softmax_fwd_kernel for alignments that were not computed here (FixedAttention,
+// networks.py:327-358: the externally supplied duration matrix is reported through the same loss term):
+// att_acc += sum_{n < maxN, t < maxT} A*W  (or (A - W)^2 for the MSE variant)
+__global__ void guide_sum_kernel(const float* __restrict__ A, long long ldA, int B, int T, int N, double* __restrict__ att_acc,
+                                 int maxN, int maxT, float g, GuideTensor G) {
+    pdl_grid_sync();
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    const float inv_maxN = 1.f / (float)maxN, inv_maxT = 1.f / (float)maxT, inv_2g2 = 1.f / (2.f * g * g);
+    float part = 0.f;
+    const long long rows = (long long)B * T;
+    for (long long row = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * wpb) {
+        const int b = (int)(row / T), t = (int)(row - (long long)b * T);
+        if (t >= maxT) continue;
+        for (int n = lane; n < N && n < maxN; n += 32) {
+            const float a = A[row * ldA + n];
+            if (!G.w) part += a * guide_w(n, t, inv_maxN, inv_maxT, inv_2g2);
+            else {
+                const float w = guide_t(G, b, n, t);
+                part += G.mse ? (a - w) * (a - w) : a * w;
+            }
+        }
+    }
+    __shared__ float red[32];
+    part = warp_sum(part);
+    if (lane == 0) red[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = threadIdx.x < wpb ? red[threadIdx.x] : 0.f;
+        v = warp_sum(v);
+        if (threadIdx.x == 0) atomicAdd(att_acc, (double)v);
+    }
+}
+
 // dA (in) -> dS (in place):  dS = A * (dA' - sum_n A*dA'),  dA' = dA + att_coef * W[n][t]   (MSE variant: + att_coef * 2 (A - W))
 __global__ void softmax_bwd_kernel(const float* __restrict__ A, long long ldA, float* __restrict__ dA, long long lddA,
                                    int B, int T, int N, float att_coef, int maxN, int maxT, float g, GuideTensor G,

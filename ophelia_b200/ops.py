@@ -341,6 +341,14 @@ def _guide(gts, mse, extra=None):
     return ctypes.byref(gd)
 
 
+def attention_guide_sum(A, att_acc, maxN, maxT, g, gts=None, mse=False):
+    """att_acc += the guided-attention sum over externally supplied alignments A [B, T, N] (FixedAttention)."""
+    B, T, N = A.shape
+    assert A.is_cuda and A.dtype == torch.float32 and A.stride(2) == 1 and (B == 1 or A.stride(0) == T * A.stride(1))
+    _lib.call("oph_attention_guide_sum", _p(A), A.stride(1), B, T, N, _p(att_acc), int(maxN), int(maxT), float(g),
+              _guide(gts, mse), _stream())
+
+
 def attention_extra_fwd(A, c_cdp, c_ain, acc3):
     """CDP / Ain / Aout sums of the alignments A [B, T, N] into acc3 (device double[3]); returns the per-key gradient
     factors (col_g, col_h) [B, N] for attention_bwd (architectures.py:283-321)."""

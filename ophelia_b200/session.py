@@ -5,7 +5,7 @@ keep their call sites.  Arrays cross the boundary as numpy, like `tf.Session.run
 import numpy as np
 import torch
 
-from .architectures import Node, SSRNGraph, Text2MelGraph
+from .architectures import BabblerGraph, Node, SSRNGraph, Text2MelGraph
 
 
 class Session(object):
@@ -55,7 +55,7 @@ class Session(object):
                     "global_step": gs}
         if names == {"global_step"}:
             return {"global_step": int(g.store.global_step.item())}
-        if isinstance(g, SSRNGraph):
+        if isinstance(g, (SSRNGraph, BabblerGraph)):
             out = g.forward(feeds)
         elif isinstance(g, Text2MelGraph):
             if names <= {"K", "V"} and "K" not in feeds:

@@ -20,10 +20,20 @@ def get_text_lengths(L):
     return np.array([int(np.where(L[i, :] == 0)[0][0]) for i in range(len(L))])
 
 
+def _variant_feeds(hp, g, feeddict, speaker_data=None, duration_data=None, labels=None):
+    """The optional placeholders of synthesize.py:83-92 / 173-178."""
+    if hp.multispeaker:
+        feeddict[g.speakers] = speaker_data
+    if hp.use_external_durations and duration_data is not None:
+        feeddict[g.durations] = duration_data
+    if hp.merlin_label_dir and labels is not None:
+        feeddict[g.merlin_label] = labels
+    return feeddict
+
+
 def encode_text(hp, L, g, sess, speaker_data=None, labels=None):
-    """One TextEnc pass -> (K, V) (synthesize.py:232-240)."""
-    assert not hp.multispeaker and not hp.merlin_label_dir
-    K, V = sess.run([g.K, g.V], {g.L: L})
+    """One text encoder pass -> (K, V) (synthesize.py:232-240)."""
+    K, V = sess.run([g.K, g.V], _variant_feeds(hp, g, {g.L: L}, speaker_data, None, labels))
     return (K, V)
 
 
@@ -39,14 +49,14 @@ def _update_ends(hp, max_att_j, ends, endcounts, t_ends, j, endcount_threshold=1
 
 def synth_text2mel(hp, L, g, sess, speaker_data=None, duration_data=None, labels=None, position_in_phone_data=None):
     """Route that re-runs TextEnc every frame (synthesize.py:62-132).  Returns (Y, t_ends)."""
-    assert not hp.multispeaker and not hp.use_external_durations and not hp.merlin_label_dir
     B = len(L)
     Y = np.zeros((B, hp.max_T, hp.n_mels), np.float32)
     prev_max_attentions = np.zeros((B,), np.int32)
     ends = get_text_lengths(L)
     endcounts = np.zeros(ends.shape, dtype=int)
     t_ends = np.ones(ends.shape, dtype=int) * hp.max_T
-    feeddict = {g.L: L, g.mels: Y, g.prev_max_attentions: prev_max_attentions}
+    feeddict = _variant_feeds(hp, g, {g.L: L, g.mels: Y, g.prev_max_attentions: prev_max_attentions}, speaker_data,
+                              duration_data, labels)
     for j in range(hp.max_T):
         _Y, _max_attentions, _alignments = sess.run([g.Y, g.max_attentions, g.alignments], feeddict)
         Y[:, j, :] = _Y[:, j, :]
@@ -60,8 +70,8 @@ def synth_text2mel(hp, L, g, sess, speaker_data=None, duration_data=None, labels
 
 def synth_codedtext2mel(hp, K, V, ends, g, sess, speaker_data=None, duration_data=None, labels=None,
                         position_in_phone_data=None):
-    """Route with K, V encoded once and fed (synthesize.py:150-230).  Returns (Y, t_ends, alignments)."""
-    assert not hp.multispeaker and not hp.use_external_durations and not hp.merlin_label_dir
+    """Route with K, V encoded once and fed (synthesize.py:150-230).  Returns (Y, t_ends, alignments).  With external
+    durations the sentence ends are known in advance (`t_ends = duration_data.sum(axis=(1,2))`, :168-169)."""
     B = len(K)
     Y = np.zeros((B, hp.max_T, hp.n_mels), np.float32)
     alignments = np.zeros((len(ends), hp.max_N, hp.max_T), np.float32)
@@ -69,7 +79,10 @@ def synth_codedtext2mel(hp, K, V, ends, g, sess, speaker_data=None, duration_dat
     ends = np.asarray(ends)
     endcounts = np.zeros(ends.shape, dtype=int)
     t_ends = np.ones(ends.shape, dtype=int) * hp.max_T
-    feeddict = {g.K: K, g.V: V, g.mels: Y, g.prev_max_attentions: prev_max_attentions}
+    if hp.use_external_durations:
+        t_ends = np.asarray(duration_data).sum(axis=(1, 2)).astype(int)
+    feeddict = _variant_feeds(hp, g, {g.K: K, g.V: V, g.mels: Y, g.prev_max_attentions: prev_max_attentions}, speaker_data,
+                              duration_data, labels)
     for j in range(hp.max_T):
         _Y, _max_attentions, _alignments = sess.run([g.Y, g.max_attentions, g.alignments], feeddict)
         Y[:, j, :] = _Y[:, j, :]
@@ -77,9 +90,50 @@ def synth_codedtext2mel(hp, K, V, ends, g, sess, speaker_data=None, duration_dat
         prev_max_attentions = _max_attentions[:, j]
         feeddict[g.mels] = Y
         feeddict[g.prev_max_attentions] = prev_max_attentions
-        if _update_ends(hp, _max_attentions[:, j], ends, endcounts, t_ends, j):
+        if hp.use_external_durations:                        # synthesize.py:211-215
+            if j >= t_ends.max():
+                break
+        elif _update_ends(hp, _max_attentions[:, j], ends, endcounts, t_ends, j):
             break
     return (Y, t_ends.tolist(), alignments)
+
+
+def synth_babble(hp, g, sess, seed=False, nsamples=16):
+    """synthesize.py:134-148: let a BabblerGraph continue from silence, frame by frame.  Returns Y [nsamples, max_T, n_mels]."""
+    assert not seed, 'TODO: implement seeding babbler'
+    Y = np.zeros((nsamples, hp.max_T, hp.n_mels), np.float32)
+    for j in range(hp.max_T):
+        _Y, = sess.run([g.Y], {g.mels: Y})
+        Y[:, j, :] = _Y[:, j, :]
+    return Y
+
+
+def babble(hp, num_sentences=0, vocode=True):
+    """synthesize.py:333-364: babbler + SSRN (+ Griffin-Lim) from the latest checkpoints; returns the output directory."""
+    import os
+    from . import vocoder
+    from .architectures import BabblerGraph, SSRNGraph
+    from .session import Session
+    if num_sentences == 0:
+        num_sentences = 4
+    g1 = BabblerGraph(hp, mode="synthesize"); print("Babbler graph loaded")
+    g2 = SSRNGraph(hp, mode="synthesize"); print("SSRN graph loaded")
+    with Session() as sess:
+        babbler_epoch = restore_latest_model_parameters(sess, hp, 'babbler', graph=g1)
+        ssrn_epoch = restore_latest_model_parameters(sess, hp, 'ssrn', graph=g2)
+        Y = synth_babble(hp, g1, sess, seed=False, nsamples=num_sentences)
+        Z = synth_mel2mag(hp, Y, g2, sess)
+        if np.isnan(Z).any():
+            Z = np.nan_to_num(Z)
+        outdir = os.path.join(hp.voicedir, 'synth_babble', '%s_%s' % (babbler_epoch, ssrn_epoch))
+        os.makedirs(outdir, exist_ok=True)
+        for i, mag in enumerate(Z):
+            if vocode:
+                wav = vocoder.spectrogram2wav(hp, mag)
+                vocoder.write_wav(outdir + "/{:03d}.wav".format(i), wav, hp.sr)
+            else:
+                np.save(outdir + "/{:03d}.npy".format(i), mag)
+    return outdir
 
 
 def synth_codedtext2mel_device(hp, K, V, ends, g, use_cuda_graph=True, check_every=8):
@@ -376,7 +430,7 @@ def synth_mel2mag(hp, Y, g, sess, batchsize=128):
     return Z
 
 
-_MODEL_SCOPES = {'t2m': 'Text2Mel', 'ssrn': 'SSRN'}     # synthesize.py:303-306 (the babbler variant is outside the path)
+_MODEL_SCOPES = {'t2m': 'Text2Mel', 'ssrn': 'SSRN', 'babbler': 'Text2Mel'}     # synthesize.py:303-306
 
 
 def restore_latest_model_parameters(sess, hp, model_type, graph=None):
