@@ -73,7 +73,9 @@ int oph_gemm_debug_buffer(long long* dev_buf);
  * 16384 = remainder K-split also for plain conv outputs (memset + RED: forward results then depend on RED order),
  * 131072 = highway tail of oph_hc_fwd always as its own launch (default: inside the conv launch when the row tiles fill whole
  * rounds of the 74 CTA pairs, the last one to >= 70 %), 262144 = also fuse the full rounds when the last round is emptier
- * (the rest of the rows then gets plain work units + a partial tail launch) */
+ * (the rest of the rows then gets plain work units + a partial tail launch), 524288 = networks.Attention forward as three
+ * launches (two GEMMs + the softmax kernel) instead of the one-kernel form, 1048576 = scalar conv-tail kernels for channel
+ * counts other than 256 / 512 / 1024 (default: the 16-byte kernels over padded rows) */
 int oph_gemm_debug_flags(int flags);
 /* Execution context of the calling host thread (like cublasSetStream): with enable != 0 the weight-gradient GEMMs of
  * oph_*_bwd are launched on `side` after an event fork behind the layer's row-wise backward kernel, so that they

@@ -415,6 +415,13 @@ int launch_ln_act_fwd(const float* z, long long ldz, const float* gamma, const f
 #define OPH_LAUNCH(V) launch_cfg(grid, 256, 0, st)(ln_act_fwd_vec_kernel<V>, z, ldz, gamma, beta, y, ldy, y_sig, ldys, yo->hi, yo->lo, yo->ldp, stats, (int)rows, act, norm, drop_p, seed, step)
         if (C == 256) OPH_LAUNCH(2); else if (C == 512) OPH_LAUNCH(4); else OPH_LAUNCH(8);
 #undef OPH_LAUNCH
+    } else if (!((ldz | ldy | (y_sig ? ldys : 4) | (yo->hi ? yo->ldp : 4)) & 3) && C <= 1280 && !(g_gemm_dbg_flags_host & 1048576)) {
+        // other widths (80, 513, 1025): 16-byte accesses over the padded rows, elements >= C masked
+        const int nv = (C + 3) / 4;
+        const size_t sm = (2 * (size_t)((C + 3) & ~3) + 32) * sizeof(float);
+#define OPH_LAUNCH(V, W) launch_cfg(rows_grid(rows, 8 / W), 256, sm, st)(ln_act_fwd_any_kernel<V, W>, z, ldz, gamma, beta, y, ldy, y_sig, ldys, yo->hi, yo->lo, yo->ldp, stats, (int)rows, C, act, norm, drop_p, seed, step)
+        if (nv <= 32) OPH_LAUNCH(1, 1); else if (nv <= 160) OPH_LAUNCH(5, 1); else OPH_LAUNCH(5, 2);
+#undef OPH_LAUNCH
     } else {
         launch_cfg(grid, 256, 0, st)(ln_act_fwd_kernel, z, ldz, gamma, beta, y, ldy, y_sig, ldys, yo->hi, yo->lo, yo->ldp, stats, (int)rows, C, act, norm, drop_p, seed, step);
     }
@@ -467,7 +474,18 @@ int launch_ln_act_bwd(const float* dy, long long lddy, const float* z, long long
             h = reinterpret_cast<unsigned short*>(dz); l = h + rows * ldp;
             dzmap->hi = h; dzmap->lo = l; dzmap->ld = ldp; dzmap->ptr = nullptr;
         }
-        launch_cfg(rows_grid(rows, 8), 256, smem, st)(ln_act_bwd_kernel, dy, lddy, z, ldz, stats, gamma, beta, dz, lddz, h, l, ldp, dgamma, dbeta, dbias, (int)rows, C, act, norm, drop_p, seed, step);
+        if (!((lddy | ldz | lddz) & 3) && C <= 1280 && !(g_gemm_dbg_flags_host & 1048576)) {
+            const int nv = (C + 3) / 4;
+            const size_t sm = (2 * (size_t)((C + 3) & ~3) + 32) * sizeof(float);
+            const int wpr = nv > 160 ? 2 : 1;
+            long long gl = (rows + (8 / wpr) * 8 - 1) / ((8 / wpr) * 8);                  // >= 8 rows per row group
+            const int gridb = (int)(gl < 1 ? 1 : (gl > 148 * 3 ? 148 * 3 : gl));
+#define OPH_LAUNCH(V, W) launch_cfg(gridb, 256, sm, st)(ln_act_bwd_any_kernel<V, W>, dy, lddy, z, ldz, stats, gamma, beta, dz, lddz, h, l, ldp, dgamma, dbeta, dbias, (int)rows, C, act, norm, drop_p, seed, step)
+            if (nv <= 32) OPH_LAUNCH(1, 1); else if (nv <= 160) OPH_LAUNCH(5, 1); else OPH_LAUNCH(5, 2);
+#undef OPH_LAUNCH
+        } else {
+            launch_cfg(rows_grid(rows, 8), 256, smem, st)(ln_act_bwd_kernel, dy, lddy, z, ldz, stats, gamma, beta, dz, lddz, h, l, ldp, dgamma, dbeta, dbias, (int)rows, C, act, norm, drop_p, seed, step);
+        }
     }
     return check_launch("ln_act_bwd_kernel");
 }

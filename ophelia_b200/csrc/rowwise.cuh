@@ -1271,3 +1271,236 @@ __global__ void __launch_bounds__(256) ln_act_bwd_wide_kernel(
 }
 
 }  // namespace oph
+
+// =================================================================================================
+// Conv tails for channel counts that are not 256 / 512 / 1024 (80 mel bins, 513 / 1025 magnitude bins: the output layers
+// of AudioDec and SSRN, which run on the largest activations of the model).  Same arithmetic as ln_act_fwd / bwd_kernel,
+// but 16-byte accesses: rows are padded to a multiple of 4 floats, a group of WPR warps owns a row, lane l of part p holds
+// the float4s (i * WPR + p) * 32 + l of it in registers (i < MAXV), elements >= C are masked out of every sum.  Each lane
+// always sees the same channels, so the per-channel sums of the backward pass stay in registers until the end.
+namespace oph {
+
+template <int MAXV, int WPR>
+__global__ void __launch_bounds__(256) ln_act_fwd_any_kernel(
+        const float* __restrict__ z, long long ldz, const float* __restrict__ gamma, const float* __restrict__ beta,
+        float* __restrict__ y, long long ldy, float* __restrict__ y_sig, long long ldys,
+        unsigned short* __restrict__ y_hi, unsigned short* __restrict__ y_lo, long long ldp, float* __restrict__ stats,
+        int rows, int C, int act, int norm, float drop_p, unsigned long long seed, const long long* step) {
+    pdl_grid_sync();
+    constexpr int GROUPS = 8 / WPR;
+    extern __shared__ __align__(16) float smem_f[];
+    const int Cp = (C + 3) & ~3;
+    float* spar = smem_f;                               // [2][Cp]: gamma, beta (zero beyond C)
+    float* sx = smem_f + 2 * Cp;                        // [2 parities][8 warps][2]
+    for (int i = threadIdx.x; i < Cp; i += 256) { spar[i] = (norm && i < C) ? gamma[i] : 0.f; spar[Cp + i] = (norm && i < C) ? beta[i] : 0.f; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int grp = warp / WPR, part = warp % WPR;
+    const int nv = Cp >> 2;
+    const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+    const float invC = 1.f / (float)C;
+    const unsigned long long sd = eff_seed(seed, step);
+    int it = 0;
+    for (long long row = (long long)blockIdx.x * GROUPS + grp; row < rows; row += (long long)gridDim.x * GROUPS, ++it) {
+        float4 v[MAXV];
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            const int j = (i * WPR + part) * 32 + lane;
+            v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j < nv) {
+                v[i] = __ldg(reinterpret_cast<const float4*>(z + row * ldz) + j);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) if (j * 4 + e >= C) OPH_F4(v[i], e) = 0.f;
+                s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+            }
+        }
+        float mean = 0.f, rstd = 1.f;
+        if (norm) {
+            s = warp_sum(s);
+            if (WPR > 1) {
+                float* my = sx + ((it & 1) * 8 + warp) * 2;
+                if (lane == 0) my[0] = s;
+                asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(WPR * 32) : "memory");
+                s = 0.f;
+#pragma unroll
+                for (int w = 0; w < WPR; ++w) s += sx[((it & 1) * 8 + grp * WPR + w) * 2];
+            }
+            mean = s * invC;
+            float q = 0.f;
+#pragma unroll
+            for (int i = 0; i < MAXV; ++i) {
+                const int j = (i * WPR + part) * 32 + lane;
+                if (j < nv) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) if (j * 4 + e < C) { const float d = OPH_F4(v[i], e) - mean; q += d * d; }
+                }
+            }
+            q = warp_sum(q);
+            if (WPR > 1) {
+                float* my = sx + ((it & 1) * 8 + warp) * 2;
+                if (lane == 0) my[1] = q;
+                asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(WPR * 32) : "memory");
+                q = 0.f;
+#pragma unroll
+                for (int w = 0; w < WPR; ++w) q += sx[((it & 1) * 8 + grp * WPR + w) * 2 + 1];
+            }
+            rstd = rsqrtf(q * invC + LN_EPS);
+        }
+        if (stats && lane == 0 && part == 0) *reinterpret_cast<float2*>(stats + row * 2) = make_float2(mean, rstd);
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            const int j = (i * WPR + part) * 32 + lane;
+            if (j >= nv) continue;
+            const int c0 = j * 4;
+            const float4 G = *reinterpret_cast<const float4*>(spar + c0), Bt = *reinterpret_cast<const float4*>(spar + Cp + c0);
+            float4 o, sg;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float u = OPH_F4(v[i], e);
+                if (norm) u = (u - mean) * rstd * reinterpret_cast<const float*>(&G)[e] + reinterpret_cast<const float*>(&Bt)[e];
+                OPH_F4(sg, e) = sigmoidf_(u);
+                float a = act == 1 ? fmaxf(u, 0.f) : u;
+                if (drop_p > 0.f) a *= drop_scale(sd, (unsigned long long)row * C + c0 + e, drop_p, inv_keep);
+                OPH_F4(o, e) = a;
+            }
+            if (c0 + 4 <= C) {
+                *reinterpret_cast<float4*>(y + row * ldy + c0) = o;
+                if (y_sig) *reinterpret_cast<float4*>(y_sig + row * ldys + c0) = sg;
+                if (y_hi) {
+                    uint2 hh, ll;
+                    split4(o, hh, ll);
+                    *reinterpret_cast<uint2*>(y_hi + row * ldp + c0) = hh;
+                    *reinterpret_cast<uint2*>(y_lo + row * ldp + c0) = ll;
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    if (c0 + e >= C) break;
+                    y[row * ldy + c0 + e] = OPH_F4(o, e);
+                    if (y_sig) y_sig[row * ldys + c0 + e] = OPH_F4(sg, e);
+                    if (y_hi) st_split1(y_hi, y_lo, row * ldp + c0 + e, OPH_F4(o, e));
+                }
+            }
+        }
+    }
+}
+
+// backward: dz as split-bf16 planes [rows][ldp] (or fp32 when dz_hi == NULL), dgamma / dbeta / dbias accumulated into
+template <int MAXV, int WPR>
+__global__ void __launch_bounds__(256, 2) ln_act_bwd_any_kernel(
+        const float* __restrict__ dy, long long lddy, const float* __restrict__ z, long long ldz,
+        const float* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
+        float* __restrict__ dz, long long lddz, unsigned short* __restrict__ dz_hi, unsigned short* __restrict__ dz_lo,
+        long long ldp, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias,
+        int rows, int C, int act, int norm, float drop_p, unsigned long long seed, const long long* step) {
+    pdl_grid_sync();
+    constexpr int GROUPS = 8 / WPR;
+    extern __shared__ __align__(16) float smem_f[];
+    const int Cp = (C + 3) & ~3;
+    float* spar = smem_f;                               // [2][Cp]
+    float* sx = smem_f + 2 * Cp;                        // [2 parities][8 warps][2]
+    for (int i = threadIdx.x; i < Cp; i += 256) { spar[i] = (norm && i < C) ? gamma[i] : 0.f; spar[Cp + i] = (norm && i < C) ? beta[i] : 0.f; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int grp = warp / WPR, part = warp % WPR;
+    const int nv = Cp >> 2;
+    const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+    const float invC = 1.f / (float)C;
+    const unsigned long long sd = eff_seed(seed, step);
+    float acc[3][MAXV * 4];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int i = 0; i < MAXV * 4; ++i) acc[k][i] = 0.f;
+    int it = 0;
+    for (long long row = (long long)blockIdx.x * GROUPS + grp; row < rows; row += (long long)gridDim.x * GROUPS, ++it) {
+        float mean = 0.f, rstd = 1.f;
+        if (norm) { const float2 st = __ldg(reinterpret_cast<const float2*>(stats + row * 2)); mean = st.x; rstd = st.y; }
+        float4 xh[MAXV], ev[MAXV];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            const int j = (i * WPR + part) * 32 + lane;
+            xh[i] = ev[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j >= nv) continue;
+            const int c0 = j * 4;
+            const float4 zv = __ldg(reinterpret_cast<const float4*>(z + row * ldz) + j);
+            const float4 dv = __ldg(reinterpret_cast<const float4*>(dy + row * lddy) + j);
+            const float4 G = *reinterpret_cast<const float4*>(spar + c0), Bt = *reinterpret_cast<const float4*>(spar + Cp + c0);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                if (c0 + e >= C) continue;
+                const float zz = reinterpret_cast<const float*>(&zv)[e];
+                const float x_ = norm ? (zz - mean) * rstd : zz;
+                const float u = norm ? x_ * reinterpret_cast<const float*>(&G)[e] + reinterpret_cast<const float*>(&Bt)[e] : x_;
+                float du = reinterpret_cast<const float*>(&dv)[e];
+                if (drop_p > 0.f) du *= drop_scale(sd, (unsigned long long)row * C + c0 + e, drop_p, inv_keep);
+                if (act == 1 && !(u > 0.f)) du = 0.f;
+                if (norm) {
+                    acc[0][i * 4 + e] += du * x_; acc[1][i * 4 + e] += du;
+                    const float dxh = du * reinterpret_cast<const float*>(&G)[e];
+                    s1 += dxh; s2 += dxh * x_;
+                    OPH_F4(ev[i], e) = dxh; OPH_F4(xh[i], e) = x_;
+                } else {
+                    OPH_F4(ev[i], e) = du; acc[2][i * 4 + e] += du;
+                }
+            }
+        }
+        if (norm) {
+            s1 = warp_sum(s1); s2 = warp_sum(s2);
+            if (WPR > 1) {
+                float* my = sx + ((it & 1) * 8 + warp) * 2;
+                if (lane == 0) *reinterpret_cast<float2*>(my) = make_float2(s1, s2);
+                asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(WPR * 32) : "memory");
+                s1 = s2 = 0.f;
+#pragma unroll
+                for (int w = 0; w < WPR; ++w) {
+                    const float2 o = *reinterpret_cast<const float2*>(sx + ((it & 1) * 8 + grp * WPR + w) * 2);
+                    s1 += o.x; s2 += o.y;
+                }
+            }
+            s1 *= invC; s2 *= invC;
+        }
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            const int j = (i * WPR + part) * 32 + lane;
+            if (j >= nv) continue;
+            const int c0 = j * 4;
+            if (norm) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    if (c0 + e >= C) continue;
+                    const float d = rstd * (OPH_F4(ev[i], e) - s1 - OPH_F4(xh[i], e) * s2);
+                    OPH_F4(ev[i], e) = d; acc[2][i * 4 + e] += d;
+                }
+            }
+            if (dz_hi) {                                 // plane rows are padded to 8 elements: whole float4s fit
+                uint2 hh, ll;
+                split4(ev[i], hh, ll);
+                *reinterpret_cast<uint2*>(dz_hi + row * ldp + c0) = hh;
+                *reinterpret_cast<uint2*>(dz_lo + row * ldp + c0) = ll;
+            } else if (c0 + 4 <= C) {
+                *reinterpret_cast<float4*>(dz + row * lddz + c0) = ev[i];
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) if (c0 + e < C) dz[row * lddz + c0 + e] = OPH_F4(ev[i], e);
+            }
+        }
+    }
+    // flush: one global atomic per lane and channel (few, long-lived blocks)
+    float* const dst[3] = {norm ? dgamma : nullptr, norm ? dbeta : nullptr, dbias};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        if (!dst[k]) continue;
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            const int j = (i * WPR + part) * 32 + lane;
+            if (j >= nv) continue;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) if (j * 4 + e < C) atomicAdd(dst[k] + j * 4 + e, acc[k][i * 4 + e]);
+        }
+    }
+}
+
+}  // namespace oph

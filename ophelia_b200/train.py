@@ -96,7 +96,7 @@ def _validation_set(hp, model_type):
     valid_filenames = np.array(valid_filenames)[v_indices]
     validation_text = validation_text[v_indices, :]
     validation_mels = None
-    if model_type == 't2m':
+    if model_type in ('t2m', 'babbler'):       # (the babbler's validation score is the reference's dummy 0.0, train.py:49-50)
         validation_mels = [np.load(hp.coarse_audio_dir + os.path.sep + _basename(f) + '.npy') for f in valid_filenames]
         return valid_filenames, validation_text, validation_mels, validation_text, validation_mels
     validation_mags = [np.load(hp.full_audio_dir + os.path.sep + _basename(f) + '.npy') for f in valid_filenames]
@@ -144,9 +144,9 @@ def train(hp, model_type, max_steps_per_epoch=None):
     """The body of train.py:main_work for an already loaded configuration.  Returns the last validation score."""
     import torch
     from . import tf_checkpoint
-    from .architectures import SSRNGraph, Text2MelGraph
+    from .architectures import BabblerGraph, SSRNGraph, Text2MelGraph
     from .session import Session
-    assert model_type in ('t2m', 'ssrn'), "model type %r is outside the path" % (model_type,)
+    assert model_type in ('t2m', 'ssrn', 'babbler'), "unknown model type %r" % (model_type,)
     hp.turn_off_monotonic_for_synthesis = False                   # train.py:94
     logdir = hp.logdir + "-" + model_type
     rank, world, group = _dist_env()
@@ -163,7 +163,7 @@ def train(hp, model_type, max_steps_per_epoch=None):
         for i in range(n_plot):
             attention_mels[i, :validation_mels[i].shape[0], :] = validation_mels[i]
 
-    AppropriateGraph = {'t2m': Text2MelGraph, 'ssrn': SSRNGraph}[model_type]
+    AppropriateGraph = {'t2m': Text2MelGraph, 'ssrn': SSRNGraph, 'babbler': BabblerGraph}[model_type]    # train.py:185
     g = AppropriateGraph(hp, process_group=group); info("Training graph loaded")
     synth_graph = AppropriateGraph(hp, mode='synthesize', reuse=True); info("Synthesis graph loaded")
     attention_graph = AppropriateGraph(hp, mode='generate_attention', reuse=True); info("Atttention generating graph loaded")
@@ -237,7 +237,7 @@ def main_work():
     from .configuration import load_config
     a = ArgumentParser()
     a.add_argument('-c', dest='config', required=True, type=str)
-    a.add_argument('-m', dest='model_type', required=True, choices=['t2m', 'ssrn'])
+    a.add_argument('-m', dest='model_type', required=True, choices=['t2m', 'ssrn', 'babbler'])
     opts = a.parse_args()
     hp = load_config(opts.config)
     train(hp, opts.model_type)
