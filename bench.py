@@ -547,8 +547,7 @@ def ncu_traffic(args):
     with open(path) as f:
         cap = json.load(f)["captures"]
     tot = lambda k: cap[k]["dram_read"] + cap[k]["dram_write"]      # noqa: E731
-    gemm_key = "gemm_hc_fused_fwd" if "gemm_hc_fused_fwd" in cap else "gemm_hc_fwd"
-    return {"gemm": tot(gemm_key), "rowwise": tot("hc_post_bwd") if "hc_post_bwd" in cap else None,
+    return {"gemm": tot("gemm_hc_fwd"), "rowwise": tot("hc_post_bwd") if "hc_post_bwd" in cap else None,
             "detail": {"unit": "bytes per launch, one ncu --set full capture each (cold caches)", "file": "profiles/" + cands[-1],
                        "launches": {k: {"dram": tot(k), "algorithmic": v["algorithmic"], "launch": v["launch"]}
                                     for k, v in cap.items()},
