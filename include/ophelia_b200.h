@@ -182,6 +182,21 @@ int oph_hc_bwd(const float* dy, long long lddy, const oph_act* x, const float* z
                int rate, int padding, int norm, float drop_p, uint64_t seed, const long long* step,
                oph_stream_t stream);
 
+/* ---- modules.learn_channel_contributions (modules.py:78-88): per-speaker channel gates ---------------------------------
+ * gate[b][c] = sigmoid(table[codes[b]][c]) with the zero-padded embedding table [ncodes][C] (code 0 reads as zeros -> 0.5).
+ * Behind a conv1d layer (modules.py:141-144): lcc_fwd scales its output y0 (out may alias nothing; out_sig = sigmoid(out),
+ * nullable); lcc_bwd gives dy0 = gate * dy and fills scratch [B*L][C] with the per-element table gradients, which
+ * lcc_reduce sums over time into dtable (accumulated into; the zero-pad row gets nothing).
+ * Inside a highway layer the gate multiplies LN(H2) before the mix (modules.py:200-201): oph_lcc_context arms the NEXT
+ * oph_hc_fwd / oph_hc_bwd call of this host thread with (table, codes, scratch); oph_hc_bwd then fills scratch for
+ * lcc_reduce.  Gated highway layers run the generic (one warp per row) tail kernels as separate launches. */
+int oph_lcc_context(const float* table, const int32_t* codes, float* scratch);
+int oph_lcc_fwd(const float* y0, long long ld0, const float* table, const int32_t* codes, const oph_act* out, float* out_sig,
+                long long lds, int B, int L, int C, oph_stream_t stream);
+int oph_lcc_bwd(const float* dy, long long lddy, const float* y0, long long ld0, const float* table, const int32_t* codes,
+                float* dy0, long long ldd0, float* scratch, int B, int L, int C, oph_stream_t stream);
+int oph_lcc_reduce(const float* scratch, const int32_t* codes, float* dtable, int B, int L, int C, oph_stream_t stream);
+
 /* ---- modules.conv1d_transpose (modules.py:209-258): stride-2, k=3, always layer-normed ---------------------
  * out[2i] = W0.x[i] + W2.x[i-1], out[2i+1] = W1.x[i]; y is [B][2L][C].  z [B*2L][ldz], stats [B*2L][2]. */
 int oph_deconv_fwd(const oph_act* x, const void* packed_w, const float* bias, const float* gamma, const float* beta,

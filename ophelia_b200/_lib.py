@@ -58,6 +58,10 @@ SIGNATURES = {
     "oph_hc_fwd": (I, [AP, P, P, P, P, P, P, P, LL, P, AP, I, I, I, I, I, I, I, F, U64, P, P]),
     "oph_hc_bwd": (I, [P, LL, AP, P, LL, P, P, P, P, P, P, P, LL, P, LL, P, LL, P, P, P, P, P, P,
                        I, I, I, I, I, I, I, F, U64, P, P]),
+    "oph_lcc_context": (I, [P, P, P]),
+    "oph_lcc_fwd": (I, [P, LL, P, P, AP, P, LL, I, I, I, P]),
+    "oph_lcc_bwd": (I, [P, LL, P, LL, P, P, P, LL, P, I, I, I, P]),
+    "oph_lcc_reduce": (I, [P, P, P, I, I, I, P]),
     "oph_deconv_fwd": (I, [AP, P, P, P, P, P, LL, P, AP, I, I, I, F, U64, P, P]),
     "oph_deconv_bwd": (I, [P, LL, AP, P, LL, P, P, P, P, P, LL, P, LL, P, P, P, P, I, I, I, F, U64, P, P]),
     "oph_embed_fwd": (I, [P, P, P, LL, I, I, P]),

@@ -22,16 +22,18 @@ from .variables import VariableStore, mix_dropout_seed, use_store, variable_scop
 _default_stores = {}
 
 
-def _conv_specs(out, prefix, name, k, cin, cout, norm=True):
+def _conv_specs(out, prefix, name, k, cin, cout, norm=True, lcc=0):
     s = "%s/%s" % (prefix, name)
     out.append((s + "/conv1d/kernel", (k, cin, cout), "kernel"))
     out.append((s + "/conv1d/bias", (cout,), "zeros"))
     if norm:
         out.append((s + "/normalize/beta", (cout,), "zeros"))
         out.append((s + "/normalize/gamma", (cout,), "ones"))
+    if lcc:                                     # learn_channel_contributions: embed(codes, lcc, cout, scope="lcc_embed")
+        out.append((s + "/lcc_embed/lookup_table", (lcc, cout), "embed"))
 
 
-def _hc_specs(out, prefix, name, k, c, norm=True):
+def _hc_specs(out, prefix, name, k, c, norm=True, lcc=0):
     s = "%s/%s" % (prefix, name)
     out.append((s + "/conv1d/kernel", (k, c, 2 * c), "kernel"))
     out.append((s + "/conv1d/bias", (2 * c,), "zeros"))
@@ -39,6 +41,8 @@ def _hc_specs(out, prefix, name, k, c, norm=True):
         for h in ("H1", "H2"):
             out.append((s + "/%s/beta" % h, (c,), "zeros"))
             out.append((s + "/%s/gamma" % h, (c,), "ones"))
+    if lcc:
+        out.append((s + "/lcc_embed/lookup_table", (lcc, c), "embed"))
 
 
 def _speaker_embed(out, prefix, i, hp):
@@ -48,15 +52,16 @@ def _speaker_embed(out, prefix, i, hp):
 def _text_encoder_body_specs(out, p, i, cin, hp, ms, nrm):
     """C (relu), C, 10 k=3 highway layers, [speaker embedding + C], 2 k=1 highway layers (networks.py:146-209)."""
     d = hp.d
-    _conv_specs(out, p, "C_%d" % i, 1, cin, 2 * d, nrm); i += 1
-    _conv_specs(out, p, "C_%d" % i, 1, 2 * d, 2 * d, nrm); i += 1
+    lcc = hp.nspeakers if 'learn_channel_contributions' in ms else 0
+    _conv_specs(out, p, "C_%d" % i, 1, cin, 2 * d, nrm, lcc); i += 1
+    _conv_specs(out, p, "C_%d" % i, 1, 2 * d, 2 * d, nrm, lcc); i += 1
     for _ in range(10):
-        _hc_specs(out, p, "HC_%d" % i, 3, 2 * d, nrm); i += 1
+        _hc_specs(out, p, "HC_%d" % i, 3, 2 * d, nrm, lcc); i += 1
     if 'text_encoder_towards_end' in ms:
         _speaker_embed(out, p, i, hp); i += 1
         _conv_specs(out, p, "C_%d" % i, 1, 2 * d + hp.speaker_embedding_size, 2 * d, nrm); i += 1
     for _ in range(2):
-        _hc_specs(out, p, "HC_%d" % i, 1, 2 * d, nrm); i += 1
+        _hc_specs(out, p, "HC_%d" % i, 1, 2 * d, nrm, lcc); i += 1
 
 
 def text2mel_variables(hp, with_text_encoder=True, with_audio=True):
@@ -90,16 +95,17 @@ def text2mel_variables(hp, with_text_encoder=True, with_audio=True):
         assert enc == 'none', enc                                         # K = V = the labels themselves
     if not with_audio:
         return out
+    lcc = hp.nspeakers if 'learn_channel_contributions' in ms else 0
     p = "Text2Mel/AudioEnc"
-    _conv_specs(out, p, "C_1", 1, nm, d, nrm)
+    _conv_specs(out, p, "C_1", 1, nm, d, nrm, lcc)
     i = 2
     if 'audio_encoder_input' in ms:
         _speaker_embed(out, p, i, hp); i += 1
         _conv_specs(out, p, "C_%d" % i, 1, d + S, d, nrm); i += 1
     for _ in range(2):
-        _conv_specs(out, p, "C_%d" % i, 1, d, d, nrm); i += 1
+        _conv_specs(out, p, "C_%d" % i, 1, d, d, nrm, lcc); i += 1
     for _ in range(10):
-        _hc_specs(out, p, "HC_%d" % i, 3, d, nrm); i += 1
+        _hc_specs(out, p, "HC_%d" % i, 3, d, nrm, lcc); i += 1
     p = "Text2Mel/AudioDec"
     _conv_specs(out, p, "C_1", 1, 2 * d if hp.concatenate_query else d, d, nrm)
     i = 2
@@ -107,10 +113,10 @@ def text2mel_variables(hp, with_text_encoder=True, with_audio=True):
         _speaker_embed(out, p, i, hp); i += 1
         _conv_specs(out, p, "C_%d" % i, 1, d + S, d, nrm); i += 1
     for _ in range(6):
-        _hc_specs(out, p, "HC_%d" % i, 3, d, nrm); i += 1
+        _hc_specs(out, p, "HC_%d" % i, 3, d, nrm, lcc); i += 1
     for _ in range(3):
-        _conv_specs(out, p, "C_%d" % i, 1, d, d, nrm); i += 1
-    _conv_specs(out, p, "C_%d" % i, 1, d, nm, nrm)
+        _conv_specs(out, p, "C_%d" % i, 1, d, d, nrm, lcc); i += 1
+    _conv_specs(out, p, "C_%d" % i, 1, d, nm, nrm, lcc)
     return out
 
 

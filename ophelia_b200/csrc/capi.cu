@@ -38,6 +38,15 @@ thread_local bool g_wgrad_fork = false;
 thread_local cudaEvent_t g_fork_ev[16];
 thread_local int g_fork_n = 0, g_fork_i = 0;
 
+// Per-speaker channel gates for the NEXT oph_hc_fwd / oph_hc_bwd call of this host thread (oph_lcc_context); consumed by it.
+thread_local LccGate g_lcc = {nullptr, nullptr, 0, nullptr};
+LccGate take_lcc(int L) {
+    LccGate r = g_lcc;
+    r.L = L;
+    g_lcc = LccGate{nullptr, nullptr, 0, nullptr};
+    return r;
+}
+
 cudaStream_t fork_wgrad(cudaStream_t main) {
     if (!g_wgrad_fork || g_wgrad_stream == main) return main;
     if (g_fork_n < 16) { cudaEventCreateWithFlags(&g_fork_ev[g_fork_n], cudaEventDisableTiming); ++g_fork_n; g_fork_i = g_fork_n - 1; }
@@ -772,8 +781,10 @@ int oph_hc_fwd(const oph_act* x, const void* packed_w, const float* bias, const 
     g.C = z; g.ldc = ldz; g.bias = bias; g.tag = OPH_TAG_HC_FWD;
     g.zero_bytes = (size_t)B * L * ldz * sizeof(float);        // z is ours to overwrite: remainder units may be K-split
     const long long all_rows = (long long)B * L;
-    const bool vec = vec_ok(C, ldz, x->ld, y->ld);
-    if (y->hi && !(vec && !(y->ldp & 7))) return fail(OPH_EINVAL, "hc_fwd: output planes need C in {256,512,1024}%s");
+    const LccGate lcc = take_lcc(L);                            // per-speaker gates on H2 (modules.py:200-201): generic tail kernel
+    const bool vec = vec_ok(C, ldz, x->ld, y->ld) && !lcc.table;
+    if (y->hi && (y->ldp & 7)) return fail(OPH_EINVAL, "hc_fwd: plane rows must be 16-byte aligned%s");
+    if (y->hi && !vec && !lcc.table) return fail(OPH_EINVAL, "hc_fwd: output planes need C in {256,512,1024}%s");
     // Highway tail in the same launch (gemm_tc.cuh, hc_fused): row-tile pairs run as super-units whose epilogue warps finish
     // the rows.  A super-unit pins all column blocks of a row tile to one CTA pair, so the schedule is only as good as
     // (row tiles) / (74 pairs) rounds up: used when the last round is full or at least 70 % full.  Otherwise (e.g. 109 row
@@ -781,7 +792,7 @@ int oph_hc_fwd(const oph_act* x, const void* packed_w, const float* bias, const 
     // plain units + a partial tail launch gives the same step time (7.02 vs 6.97 ms) and a slower conv launch.  The kernel
     // supports that mixed schedule (flag 262144 selects it) and the tests cover it.
     long long done_rows = 0;
-    if (g_use_hc_fuse && vec && norm && y->f32 && !(y->hi && (y->ldp & 3)) && !(g_gemm_dbg_flags_host & 4096)) {
+    if (g_use_hc_fuse && vec && norm && !lcc.table && y->f32 && !(y->hi && (y->ldp & 3)) && !(g_gemm_dbg_flags_host & 4096)) {
         const int MP = cdiv(cdiv((int)all_rows, GEMM_BM), 2), P = GEMM_MAX_PAIRS;
         const int full = (MP / P) * P, rem = MP - full;
         const int F = (rem == 0 || rem * 10 >= P * 7) ? MP : ((g_gemm_dbg_flags_host & 262144) ? full : 0);
@@ -829,7 +840,8 @@ int oph_hc_fwd(const oph_act* x, const void* packed_w, const float* bias, const 
         if (C == 256) OPH_LAUNCH(2); else if (C == 512) OPH_LAUNCH(4); else OPH_LAUNCH(8);
 #undef OPH_LAUNCH
     } else {
-        launch_cfg(grid, 256, 0, S(stream))(hc_post_fwd_kernel, z, ldz, x->f32, x->ld, g1, b1, g2, b2, y->f32, y->ld, stats, (int)rows, C, norm, drop_p, seed, step);
+        launch_cfg(grid, 256, 0, S(stream))(hc_post_fwd_kernel, z, ldz, x->f32, x->ld, g1, b1, g2, b2, y->f32, y->ld, stats, (int)rows, C, norm, drop_p, seed, step,
+                                                lcc, y->hi, y->lo, y->ldp);
     }
     return check_launch("hc_post_fwd_kernel");
 }
@@ -846,9 +858,11 @@ int oph_hc_bwd(const float* dy, long long lddy, const oph_act* x, const float* z
     const size_t smem = 6 * (size_t)C * sizeof(float);
     OperandMap dzm; dzm.ptr = dz; dzm.ld = lddz; dzm.hi = dzm.lo = nullptr;
     (void)dxres; (void)ldxr;
+    const LccGate lcc = take_lcc(L);
+    if (lcc.table && !lcc.scratch) return fail(OPH_EINVAL, "hc_bwd: the channel gates need a [B*L][C] scratch (oph_lcc_context)%s");
     {
     ProfScope ps(OPH_TAG_ROW_BWD, (double)rows * C * 28.0, S(stream));
-    if (norm && vec_ok(C, lddy, ldz, x->ld, lddz, lddx) && lddz >= 2 * C) {
+    if (!lcc.table && norm && vec_ok(C, lddy, ldz, x->ld, lddz, lddx) && lddz >= 2 * C) {
         dz_as_planes(dz, rows, 2 * C, &dzm);
         unsigned short* h = const_cast<unsigned short*>(dzm.hi); unsigned short* l = const_cast<unsigned short*>(dzm.lo);
         const int wpr = C / 256, groups = 8 / wpr;
@@ -872,7 +886,7 @@ int oph_hc_bwd(const float* dy, long long lddy, const oph_act* x, const float* z
     } else {
         launch_cfg(rows_grid(rows, 8), 256, smem, S(stream))(hc_post_bwd_kernel, 
             dy, lddy, z, ldz, x->f32, x->ld, stats, g1, b1, g2, b2, dz, lddz, dx, lddx, dg1, db1, dg2, db2, dbias,
-            (int)rows, C, norm, drop_p, seed, step);
+            (int)rows, C, norm, drop_p, seed, step, lcc);
     }
     }
     OPH_TRY(check_launch("hc_post_bwd_kernel"));
@@ -896,6 +910,32 @@ int oph_hc_bwd(const float* dy, long long lddy, const oph_act* x, const float* z
         OPH_TRY(launch_wgrad(xm, C, off, L, L, 1, dzm, 2 * C, zero, L, L, 1, B * L, k, dw, 2 * C, ws));
     }
     return OPH_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ channel gates
+int oph_lcc_context(const float* table, const int32_t* codes, float* scratch) {
+    g_lcc = LccGate{table, codes, 0, scratch};
+    return OPH_OK;
+}
+int oph_lcc_fwd(const float* y0, long long ld0, const float* table, const int32_t* codes, const oph_act* out, float* out_sig,
+                long long lds, int B, int L, int C, oph_stream_t stream) {
+    if (!y0 || !table || !codes || !out || !out->f32) return fail(OPH_EINVAL, "lcc_fwd: missing operand%s");
+    const LccGate g = {table, codes, L, nullptr};
+    launch_cfg(rows_grid((long long)B * L, 8), 256, 0, S(stream))(lcc_fwd_kernel, y0, ld0, g, out->f32, out->ld, out_sig, lds,
+                                                                 out->hi, out->lo, out->ldp, (long long)B * L, C);
+    return check_launch("lcc_fwd_kernel");
+}
+int oph_lcc_bwd(const float* dy, long long lddy, const float* y0, long long ld0, const float* table, const int32_t* codes,
+                float* dy0, long long ldd0, float* scratch, int B, int L, int C, oph_stream_t stream) {
+    if (!dy || !y0 || !table || !codes || !dy0 || !scratch) return fail(OPH_EINVAL, "lcc_bwd: missing operand%s");
+    const LccGate g = {table, codes, L, scratch};
+    launch_cfg(rows_grid((long long)B * L, 8), 256, 0, S(stream))(lcc_bwd_kernel, dy, lddy, y0, ld0, g, dy0, ldd0, (long long)B * L, C);
+    return check_launch("lcc_bwd_kernel");
+}
+int oph_lcc_reduce(const float* scratch, const int32_t* codes, float* dtable, int B, int L, int C, oph_stream_t stream) {
+    if (!scratch || !codes || !dtable) return fail(OPH_EINVAL, "lcc_reduce: missing operand%s");
+    launch_cfg(dim3(cdiv(C, 32), B), 256, 0, S(stream))(lcc_reduce_kernel, scratch, codes, dtable, L, C);
+    return check_launch("lcc_reduce_kernel");
 }
 
 // ------------------------------------------------------------------------------------------------ transposed conv

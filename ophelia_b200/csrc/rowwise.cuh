@@ -100,11 +100,20 @@ __global__ void ln_act_fwd_kernel(const float* __restrict__ z, long long ldz, co
 }
 
 // highway tail (modules.py:194-205): z = [H1 | H2]; g = sigmoid(LN1(H1)); h = LN2(H2); y = dropout(g*h + (1-g)*x)
+// Per-speaker channel gates (modules.learn_channel_contributions, modules.py:78-88): gate[b][c] = sigmoid(table[code_b][c])
+// with the zero-padded embedding (code 0 reads as zeros -> 0.5); L = rows per batch item.  table == NULL: no gates.
+struct LccGate { const float* table; const int* codes; int L; float* scratch; };
+__device__ __forceinline__ float lcc_gate(const LccGate& g, long long row, int c, int C) {
+    const int code = g.codes[row / g.L];
+    return code == 0 ? 0.5f : sigmoidf_(__ldg(g.table + (long long)code * C + c));
+}
+
 __global__ void hc_post_fwd_kernel(const float* __restrict__ z, long long ldz, const float* __restrict__ x, long long ldx,
                                    const float* __restrict__ g1, const float* __restrict__ b1,
                                    const float* __restrict__ g2, const float* __restrict__ b2,
                                    float* __restrict__ y, long long ldy, float* __restrict__ stats,
-                                   int rows, int C, int norm, float drop_p, unsigned long long seed, const long long* step) {
+                                   int rows, int C, int norm, float drop_p, unsigned long long seed, const long long* step,
+                                   LccGate lcc, unsigned short* __restrict__ y_hi, unsigned short* __restrict__ y_lo, long long ldp) {
     pdl_grid_sync();
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
@@ -126,9 +135,11 @@ __global__ void hc_post_fwd_kernel(const float* __restrict__ z, long long ldz, c
                 u2 = (u2 - s2.mean) * s2.rstd * g2[c] + b2[c];
             }
             const float g = sigmoidf_(u1);
+            if (lcc.table) u2 *= lcc_gate(lcc, row, c, C);              // LCC on the transformation connection only (modules.py:200-201)
             float o = g * u2 + (1.f - g) * xr[c];
             if (drop_p > 0.f) o *= drop_scale(sd, (unsigned long long)row * C + c, drop_p, inv_keep);
             y[row * ldy + c] = o;
+            if (y_hi) st_split1(y_hi, y_lo, row * ldp + c, o);
         }
     }
 }
@@ -200,7 +211,8 @@ __global__ void hc_post_bwd_kernel(const float* __restrict__ dy, long long lddy,
                                    float* __restrict__ dz, long long lddz, float* __restrict__ dxres, long long lddx,
                                    float* __restrict__ dg1, float* __restrict__ db1, float* __restrict__ dg2,
                                    float* __restrict__ db2, float* __restrict__ dbias,
-                                   int rows, int C, int norm, float drop_p, unsigned long long seed, const long long* step) {
+                                   int rows, int C, int norm, float drop_p, unsigned long long seed, const long long* step,
+                                   LccGate lcc) {
     pdl_grid_sync();
     extern __shared__ float sacc[];            // [6][C]: dg1, db1, dg2, db2, dbias(H1), dbias(H2)
     for (int i = threadIdx.x; i < 6 * C; i += blockDim.x) sacc[i] = 0.f;
@@ -229,8 +241,13 @@ __global__ void hc_post_bwd_kernel(const float* __restrict__ dy, long long lddy,
             float d_o = dyr[c];
             if (drop_p > 0.f) d_o *= drop_scale(sd, (unsigned long long)row * C + c, drop_p, inv_keep);
             dxres[row * lddx + c] = d_o * (1.f - g);
-            const float du1 = d_o * (h - xr[c]) * g * (1.f - g);
-            const float du2 = d_o * g;
+            float gl = 1.f;
+            if (lcc.table) {           // out = g * (gl * h) + (1 - g) * x;  d out / d table = d_o * g * h * gl (1 - gl), summed over time
+                gl = lcc_gate(lcc, row, c, C);
+                lcc.scratch[row * C + c] = d_o * g * h * gl * (1.f - gl);
+            }
+            const float du1 = d_o * (gl * h - xr[c]) * g * (1.f - g);
+            const float du2 = d_o * g * gl;
             if (norm) {
                 atomicAdd(&sacc[c], du1 * xh1); atomicAdd(&sacc[C + c], du1);
                 atomicAdd(&sacc[2 * C + c], du2 * xh2); atomicAdd(&sacc[3 * C + c], du2);
@@ -1500,6 +1517,59 @@ __global__ void __launch_bounds__(256, 2) ln_act_bwd_any_kernel(
 #pragma unroll
             for (int e = 0; e < 4; ++e) if (j * 4 + e < C) atomicAdd(dst[k] + j * 4 + e, acc[k][i * 4 + e]);
         }
+    }
+}
+
+}  // namespace oph
+
+
+// =================================================================================================
+// Per-speaker channel gates behind a conv1d layer (modules.py:141-144): out = gate[b][c] * y0, gate = sigmoid(embed(code_b)).
+namespace oph {
+
+__global__ void lcc_fwd_kernel(const float* __restrict__ y0, long long ld0, LccGate lcc, float* __restrict__ out, long long ldo,
+                               float* __restrict__ out_sig, long long lds, unsigned short* __restrict__ o_hi,
+                               unsigned short* __restrict__ o_lo, long long ldp, long long rows, int C) {
+    pdl_grid_sync();
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (long long row = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * wpb) {
+        for (int c = lane; c < C; c += 32) {
+            const float v = y0[row * ld0 + c] * lcc_gate(lcc, row, c, C);
+            out[row * ldo + c] = v;
+            if (out_sig) out_sig[row * lds + c] = sigmoidf_(v);
+            if (o_hi) st_split1(o_hi, o_lo, row * ldp + c, v);
+        }
+    }
+}
+// dy0 = gate * dy;  scratch = dy * y0 * gate (1 - gate)  (summed over time per item by lcc_reduce_kernel)
+__global__ void lcc_bwd_kernel(const float* __restrict__ dy, long long lddy, const float* __restrict__ y0, long long ld0,
+                               LccGate lcc, float* __restrict__ dy0, long long ldd0, long long rows, int C) {
+    pdl_grid_sync();
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (long long row = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * wpb) {
+        for (int c = lane; c < C; c += 32) {
+            const float gl = lcc_gate(lcc, row, c, C), d = dy[row * lddy + c];
+            dy0[row * ldd0 + c] = d * gl;
+            lcc.scratch[row * C + c] = d * y0[row * ld0 + c] * gl * (1.f - gl);
+        }
+    }
+}
+// dtable[code_b][c] += sum_t scratch[b][t][c]   (block = (32 channels, item b); the zero-pad row 0 gets no gradient)
+__global__ void lcc_reduce_kernel(const float* __restrict__ scratch, const int* __restrict__ codes, float* __restrict__ dtable,
+                                  int L, int C) {
+    pdl_grid_sync();
+    __shared__ float ss[8][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.y, c = blockIdx.x * 32 + lane;
+    const int code = codes[b];
+    float s = 0.f;
+    if (c < C && code != 0)
+        for (int t = warp; t < L; t += 8) s += scratch[((long long)b * L + t) * C + c];
+    ss[warp][lane] = s;
+    __syncthreads();
+    if (warp == 0 && c < C && code != 0) {
+        for (int w = 1; w < 8; ++w) s += ss[w][lane];
+        atomicAdd(dtable + (long long)code * C + c, s);
     }
 }
 

@@ -46,16 +46,41 @@ def save_floats_as_8bit(data, fname):
 
 
 def _check_path_scope(hp):
-    assert not hp.multispeaker, "multi-speaker inputs are outside the path"
-    assert not hp.use_external_durations and not hp.merlin_label_dir, "duration / label inputs are outside the path"
     assert 'position_in_phone' not in hp.history_type, "position-in-phone history is outside the path"
+    assert not getattr(hp, "select_central", False), "hp.select_central (a subset of the Merlin label columns) is not built"
 
 
 def load_vocab(hp):
-    """data_load.py:43-53 without the speaker-dependent phone sets."""
-    char2idx = {char: idx for idx, char in enumerate(hp.vocab)}
-    idx2char = {idx: char for idx, char in enumerate(hp.vocab)}
+    """data_load.py:40-52: the symbol table; with 'speaker_dependent_phones' every phone exists once per speaker
+    (`<phone>_<speaker>`, speakers from hp.speaker_list[1:], index 0 stays the padding symbol)."""
+    vocab = hp.vocab
+    if 'speaker_dependent_phones' in hp.multispeaker:
+        vocab = [hp.vocab[0]]
+        for speaker in hp.speaker_list[1:]:
+            for phone in hp.vocab[1:]:
+                vocab.append('%s_%s' % (phone, speaker))
+    char2idx = {char: idx for idx, char in enumerate(vocab)}
+    idx2char = {idx: char for idx, char in enumerate(vocab)}
     return char2idx, idx2char
+
+
+def durations_to_hard_attention_matrix(durations):
+    """utils.py:197-219: durations per symbol (full-rate frames) -> selection matrix [sum(durations), n_symbols] with a one
+    where frame t belongs to symbol n (symbols of duration 0 get an empty column)."""
+    durations = np.asarray(durations)
+    A = np.zeros((int(durations.sum()), len(durations)), dtype=np.float32)
+    start = 0
+    for i, dur in enumerate(durations):
+        A[start:start + dur, i] = 1.0
+        start += dur
+    return A
+
+
+def end_pad_for_reduction_shape_sync(data, hp):
+    """utils.py:190-194: zero rows up to a multiple of the reduction factor."""
+    nframe = data.shape[0]
+    num_paddings = hp.r - (nframe % hp.r) if nframe % hp.r != 0 else 0
+    return np.pad(data, [[0, num_paddings], [0, 0]], mode="constant")
 
 
 def text_normalize(text, hp):
@@ -69,6 +94,8 @@ def text_normalize(text, hp):
 def phones_normalize(text, char2idx, speaker_code=''):
     """data_load.py:64-72: whitespace-separated phone symbols, every one of which must be in the phone set."""
     phones = re.split(r'\s+', text.strip(' \n'))
+    if speaker_code:                                    # speaker-dependent phones (data_load.py:66-67)
+        phones = ['%s_%s' % (phone, speaker_code) for phone in phones]
     for phone in phones:
         if phone not in char2idx:
             print(text)
@@ -89,6 +116,10 @@ def load_data(hp, mode="train"):
     transcript = hp.transcript if mode in ("train", "validation") else hp.test_transcript
     have_features = mode in ("train", "validation") and os.path.exists(hp.coarse_audio_dir)
     fpaths, text_lengths, texts, audio_lengths = [], [], [], []
+    speakers, durations, label_lengths = [], [], []
+    # speakers come from the transcript's fifth field in training / validation; at synthesis the user names one (data_load.py:79-80)
+    get_speaker_codes = bool(hp.multispeaker) and mode != 'synthesis'
+    speaker2ix = dict(zip(hp.speaker_list, range(len(hp.speaker_list)))) if hp.multispeaker else {}
     n_missing = n_long_audio = n_long_text = 0
     with codecs.open(transcript, 'r', 'utf-8') as f:
         lines = f.readlines()
@@ -115,10 +146,15 @@ def load_data(hp, mode="train"):
                 continue
             if mode == "validation" and hp.validpatt not in fname:
                 continue
+        speaker = None
+        if get_speaker_codes:                                          # data_load.py:143-148
+            assert len(fields) >= 5, fields
+            speaker = fields[4]
         if norm_text is None:
             symbols = []
         elif hp.input_type == 'phones':
-            symbols = [char2idx[p] for p in phones_normalize(fields[3], char2idx)]     # end markers are in the phones
+            speaker_code = speaker if ('speaker_dependent_phones' in hp.multispeaker and speaker) else ''
+            symbols = [char2idx[p] for p in phones_normalize(fields[3], char2idx, speaker_code)]   # end markers are in the phones
         elif hp.input_type == 'letters':
             symbols = [char2idx[ch] for ch in text_normalize(norm_text, hp) + "E"]     # E: end of sentence
         else:
@@ -129,6 +165,23 @@ def load_data(hp, mode="train"):
         texts.append(np.array(symbols, np.int32))
         fpaths.append(os.path.join(hp.waveforms, fname + ".wav"))
         text_lengths.append(len(symbols))
+        if get_speaker_codes:
+            speakers.append(np.array(speaker2ix[speaker], np.int32))
+        label_length = None
+        if hp.merlin_label_dir:                                        # only the shape here, the data later (data_load.py:176-178)
+            label_length = np.load("{}/{}".format(hp.merlin_label_dir, fname + ".npy"), mmap_mode='r').shape[0]
+            label_lengths.append(label_length)
+        if hp.use_external_durations:                                  # sixth field: frames per symbol (data_load.py:181-193)
+            assert len(fields) >= 6, fields
+            duration_data = np.array([int(v) for v in re.split(r'\s+', fields[5].strip(' '))], np.int32)
+            if hp.merlin_label_dir:
+                duration_data = duration_data[duration_data > 0]      # merlin labels contain no skipped items
+                assert len(duration_data) == label_length, (len(duration_data), label_length, fname)
+            else:
+                assert len(duration_data) == len(symbols), (len(duration_data), len(symbols), fname)
+            if nframes:
+                assert duration_data.sum() == nframes * hp.r, (duration_data.sum(), nframes * hp.r)
+            durations.append(duration_data)
         if nframes is not None:
             # (the reference appends this before the validation-pattern and max_N filters, data_load.py:131, which leaves
             # `audio_lengths` misaligned with `fpaths` whenever those filters drop something; kept aligned here)
@@ -146,17 +199,29 @@ def load_data(hp, mode="train"):
         logging.info('Take first %s (n_utts) sentences for training' % (hp.n_utts))
         fpaths, text_lengths, texts = fpaths[:hp.n_utts], text_lengths[:hp.n_utts], texts[:hp.n_utts]
         audio_lengths = audio_lengths[:hp.n_utts]
+        speakers, durations, label_lengths = speakers[:hp.n_utts], durations[:hp.n_utts], label_lengths[:hp.n_utts]
     if mode in ('validation', 'synthesis'):
         stacked = np.zeros((len(texts), hp.max_N), np.int32)
         for i, text in enumerate(texts):
             stacked[i, :len(text)] = text
         texts = stacked
-    return {'texts': texts, 'fpaths': fpaths, 'text_lengths': text_lengths, 'audio_lengths': audio_lengths,
-            'label_lengths': []}
+        if hp.use_external_durations:                                  # data_load.py:243-251
+            stacked_durations = np.zeros((len(texts), hp.max_T, hp.max_N), np.int32)
+            for i, dur in enumerate(durations):
+                dm = end_pad_for_reduction_shape_sync(durations_to_hard_attention_matrix(dur), hp)[0::hp.r, :]
+                stacked_durations[i, :dm.shape[0], :dm.shape[1]] = dm
+            durations = stacked_durations
+    dataset = {'texts': texts, 'fpaths': fpaths, 'text_lengths': text_lengths, 'audio_lengths': audio_lengths,
+               'label_lengths': label_lengths}
+    if get_speaker_codes:
+        dataset['speakers'] = speakers
+    if hp.use_external_durations:
+        dataset['durations'] = durations
+    return dataset
 
 
 # ------------------------------------------------------------------------------------------------ feature loading
-def load_features(hp, fpath, rng, need=('mel', 'mag')):
+def load_features(hp, fpath, rng, need=('mel', 'mag'), want_start=False):
     """One utterance's `(fname, mel, mag)` (data_load.py:346-383,439-452).
 
     `random_reduction_on_the_fly`: the coarse mel is every r-th frame of the full-rate mel starting at a random offset
@@ -166,6 +231,7 @@ def load_features(hp, fpath, rng, need=('mel', 'mag')):
     reference reads and discards."""
     base = _stem(fpath) + ".npy"
     mel = mag = None
+    start = 0
     if getattr(hp, "random_reduction_on_the_fly", False):
         assert os.path.isdir(hp.full_mel_dir)
         start = int(rng.integers(0, hp.r))
@@ -181,7 +247,16 @@ def load_features(hp, fpath, rng, need=('mel', 'mag')):
             mel = np.load(os.path.join(hp.coarse_audio_dir, base)).astype(np.float32, copy=False)
         if 'mag' in need:
             mag = np.load(os.path.join(hp.full_audio_dir, base)).astype(np.float32, copy=False)
+    if want_start:
+        return os.path.basename(fpath), mel, mag, start
     return os.path.basename(fpath), mel, mag
+
+
+def load_merlin_label(hp, fpath):
+    """data_load.py:466-478: linguistic label vectors [n_symbols, hp.merlin_lab_dim] of one utterance."""
+    label = np.float32(np.load("{}/{}".format(hp.merlin_label_dir, _stem(fpath) + ".npy")))
+    assert label.shape[1] == hp.merlin_lab_dim, (label.shape, hp.merlin_lab_dim)
+    return label
 
 
 def load_attention_guide(hp, fpath):
@@ -211,6 +286,9 @@ class BatchSource(object):
         dataset = dataset if dataset is not None else load_data(hp)
         self.fpaths, self.texts = dataset['fpaths'], dataset['texts']
         self.text_lengths, self.audio_lengths = dataset['text_lengths'], dataset['audio_lengths']
+        self.speakers, self.durations = dataset.get('speakers'), dataset.get('durations')
+        self.label_lengths = dataset.get('label_lengths') or []
+        assert not hp.multispeaker or self.speakers is not None, "hp.multispeaker needs the speaker field of the transcript"
         assert len(self.fpaths) >= self.batchsize, "fewer utterances (%d) than one batch" % len(self.fpaths)
         self.num_batch = len(self.fpaths) // self.batchsize                # data_load.py:311
         self.need = tuple(need)
@@ -219,8 +297,8 @@ class BatchSource(object):
         if by == 'audio_length':
             assert len(self.audio_lengths) == len(self.fpaths), "bucketing by audio length needs the coarse mel files"
             self.lengths = list(self.audio_lengths)
-        elif by == 'text_length':
-            self.lengths = list(self.text_lengths)
+        elif by == 'text_length':                                          # label lengths when labels are the text (data_load.py:521-524)
+            self.lengths = list(self.label_lengths) if hp.merlin_label_dir else list(self.text_lengths)
         else:
             sys.exit('hp.bucket_data_by must be one of "audio_length", "text_length"')
         self.bounds = bucket_boundaries(self.lengths)
@@ -253,10 +331,18 @@ class BatchSource(object):
         return self._pending.pop()
 
     def _load(self, i, rng):
-        fname, mel, mag = load_features(self.hp, self.fpaths[i], rng, self.need)
+        hp = self.hp
+        fname, mel, mag, start = load_features(hp, self.fpaths[i], rng, self.need, want_start=True)
         ex = {'text': self.texts[i], 'mel': mel, 'mag': mag, 'fname': fname, 'length': self.lengths[i]}
         if self.with_guides:
-            ex['attention_guide'] = load_attention_guide(self.hp, self.fpaths[i])
+            ex['attention_guide'] = load_attention_guide(hp, self.fpaths[i])
+        if hp.multispeaker:
+            ex['speaker'] = int(self.speakers[i])
+        if hp.use_external_durations:      # hard attention matrix at the coarse frame rate, same random offset as the mels
+            dm = end_pad_for_reduction_shape_sync(durations_to_hard_attention_matrix(self.durations[i]), hp)
+            ex['duration'] = dm[start::hp.r, :]                           # data_load.py:381-383
+        if hp.merlin_label_dir:
+            ex['merlin_label'] = load_merlin_label(hp, self.fpaths[i])
         return ex
 
     def _feed(self):
@@ -325,6 +411,27 @@ class BatchSource(object):
                 a = it['attention_guide']
                 gts[b, :a.shape[0], :a.shape[1]] = torch.from_numpy(np.ascontiguousarray(a))
             out['attention_guide'] = gts
+        if self.hp.multispeaker:                                           # [B, 1] like the reference's speaker codes
+            out['speaker'] = torch.tensor([[it['speaker']] for it in items], dtype=torch.int32)
+        if self.hp.use_external_durations:                                 # [B, T_b, N_b] zero padded like the mels / texts
+            tt = max(it['duration'].shape[0] for it in items)
+            if 'mel' in out:
+                tt = max(tt, out['mel'].shape[1])
+            n = max(it['duration'].shape[1] for it in items)
+            if 'text' in out and not self.hp.merlin_label_dir:
+                n = max(n, out['text'].shape[1])
+            dur = self._host((B, tt, n), torch.float32)
+            for b, it in enumerate(items):
+                a = it['duration']
+                dur[b, :a.shape[0], :a.shape[1]] = torch.from_numpy(np.ascontiguousarray(a))
+            out['duration'] = dur
+        if self.hp.merlin_label_dir:
+            n = max(it['merlin_label'].shape[0] for it in items)
+            lab = self._host((B, n, self.hp.merlin_lab_dim), torch.float32)
+            for b, it in enumerate(items):
+                a = it['merlin_label']
+                lab[b, :a.shape[0]] = torch.from_numpy(a)
+            out['merlin_label'] = lab
         out['num_batch'] = self.num_batch
         return out
 

@@ -127,8 +127,9 @@ def normalize(inputs, scope="normalize", reuse=None, normtype='layer'):
 def conv1d(inputs, filters=None, size=1, rate=1, padding="SAME", dropout_rate=0, use_bias=True, activation_fn=None,
            training=True, scope="conv1d", reuse=None, normtype='layer', lcc=0, codes=None,
            *, out=None, in_shift=0, want_sigmoid=False, planes=True):
-    """modules.py:91-146: conv (+bias) -> layer norm -> activation -> dropout (training only)."""
-    assert use_bias and not lcc, "bias-free / learn_channel_contributions variants are outside the path"
+    """modules.py:91-146: conv (+bias) -> layer norm -> activation -> dropout (training only) -> optional per-speaker
+    channel gates (lcc = number of speaker codes, codes int [B, 1]; modules.py:78-88, 141-144)."""
+    assert use_bias, "the bias-free variant is unused by the path"
     assert normtype in (None, 'layer'), "batch norm is unused by every shipped config"
     assert activation_fn in (None, relu)
     store = get_store()
@@ -143,6 +144,9 @@ def conv1d(inputs, filters=None, size=1, rate=1, padding="SAME", dropout_rate=0,
         if normtype == 'layer':
             store.declare(ben, (filters,), "zeros")
             store.declare(gn, (filters,), "ones")
+        ln_ = scoped("lcc_embed/lookup_table")
+        if lcc:
+            store.declare(ln_, (lcc, filters), "embed")
     store.finalize()
     norm = normtype == 'layer'
     pk = _packed(store, kn)
@@ -154,12 +158,21 @@ def conv1d(inputs, filters=None, size=1, rate=1, padding="SAME", dropout_rate=0,
     seed = layer_seed(kn, store)
     step = _step_ptr(store, training)
     rec = _recording(training)
+    gated = bool(lcc)
     y, ysig, saved = ops.conv1d_fwd(inputs, pk, store.get(bn), gamma, beta, rate, pad, in_shift, act, norm, drop, seed,
-                                    step, save=rec, y=out, want_sigmoid=want_sigmoid, planes=planes and out is None)
+                                    step, save=rec, y=None if gated else out, want_sigmoid=want_sigmoid and not gated,
+                                    planes=planes and out is None and not gated)
+    y0 = y
+    if gated:
+        assert out is None and codes is not None
+        cds = codes.to(torch.int32).reshape(-1).contiguous()
+        y, ysig = ops.lcc_fwd(y0, store.get(ln_), cds, want_sigmoid=want_sigmoid, planes=planes)
     if rec:
         need_dx = not getattr(inputs, "_oph_no_grad", False)
 
         def bwd(dy):
+            if gated:
+                dy = ops.lcc_bwd(dy, y0, store.get(ln_), cds, store.grad(ln_))
             return ops.conv1d_bwd(dy, inputs, saved, _packed(store, kn), gamma, beta, store.grad(kn), store.grad(bn),
                                   store.grad(gn) if norm else None, store.grad(ben) if norm else None, rate, pad,
                                   in_shift, act, norm, drop, seed, step, need_dx=need_dx)
@@ -173,7 +186,7 @@ def conv1d(inputs, filters=None, size=1, rate=1, padding="SAME", dropout_rate=0,
 def hc(inputs, filters=None, size=1, rate=1, padding="SAME", dropout_rate=0, use_bias=True, activation_fn=None,
        training=True, scope="hc", reuse=None, normtype='layer', lcc=0, codes=None, *, out=None, out_planes=None):
     """modules.py:148-207: conv to 2C, split, LN(H1), LN(H2), gate = sigmoid(H1), gate*H2 + (1-gate)*inputs."""
-    assert use_bias and not lcc and activation_fn is None
+    assert use_bias and activation_fn is None
     assert normtype in (None, 'layer')
     store = get_store()
     C = inputs.shape[-1]
@@ -190,7 +203,14 @@ def hc(inputs, filters=None, size=1, rate=1, padding="SAME", dropout_rate=0, use
             store.declare(names[0], (C,), "ones")
             store.declare(names[3], (C,), "zeros")
             store.declare(names[2], (C,), "ones")
+        ln_ = scoped("lcc_embed/lookup_table")
+        if lcc:
+            store.declare(ln_, (lcc, C), "embed")
     store.finalize()
+    gate = None
+    if lcc:                 # per-speaker gates on the transformation connection (modules.py:200-201)
+        assert codes is not None
+        gate = (store.get(ln_), codes.to(torch.int32).reshape(-1).contiguous())
     norm = normtype == 'layer'
     pk = _packed(store, kn)
     g1, b1, g2, b2 = ([store.get(n) for n in names] if norm else [None] * 4)
@@ -200,12 +220,13 @@ def hc(inputs, filters=None, size=1, rate=1, padding="SAME", dropout_rate=0, use
     step = _step_ptr(store, training)
     rec = _recording(training)
     y, saved = ops.hc_fwd(inputs, pk, store.get(bn), g1, b1, g2, b2, rate, pad, norm, drop, seed, step, save=rec, y=out,
-                          planes=True, y_planes=out_planes)
+                          planes=True, y_planes=out_planes, lcc=gate)
     if rec:
         def bwd(dy):
             gr = [store.grad(n) for n in names] if norm else [None] * 4
             return ops.hc_bwd(dy, inputs, saved, _packed(store, kn), g1, b1, g2, b2, store.grad(kn), store.grad(bn),
-                              gr[0], gr[1], gr[2], gr[3], rate, pad, norm, drop, seed, step)
+                              gr[0], gr[1], gr[2], gr[3], rate, pad, norm, drop, seed, step, lcc=gate,
+                              dtable=store.grad(ln_) if gate else None)
         _record(bwd)
     return y
 

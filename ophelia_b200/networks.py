@@ -2,7 +2,7 @@
 TextEnc, MerlinTextEnc, LinearTransformLabels, AudioEnc, Attention, FixedAttention, AudioDec, SSRN.  Layer order, scope
 names (= checkpoint variable prefixes) and padding modes follow the reference line by line, including the
 speaker-embedding branches of `hp.multispeaker` (text_encoder_input, text_encoder_towards_end, audio_encoder_input,
-audio_decoder_input, ssrn_input).  Not built: the per-speaker channel gates (`learn_channel_contributions`).
+audio_decoder_input, ssrn_input) and the per-speaker channel gates (`learn_channel_contributions`).
 """
 import sys
 
@@ -14,16 +14,19 @@ from .modules import Tape, _record, conv1d, conv1d_transpose, embed, hc, relu
 
 
 SPEAKER_POSITIONS = ('text_encoder_input', 'text_encoder_towards_end', 'audio_decoder_input', 'ssrn_input',
-                     'audio_encoder_input', 'speaker_dependent_phones')      # architectures.py:49-52 minus the LCC gates
+                     'audio_encoder_input', 'learn_channel_contributions', 'speaker_dependent_phones')   # architectures.py:49-52
 
 
 def _check_speakers(hp, speaker_codes):
     ms = getattr(hp, "multispeaker", [])
-    assert 'learn_channel_contributions' not in ms, \
-        "per-speaker channel gates (modules.py:78-88) are not built on the B200 path"
     for position in ms:
         assert position in SPEAKER_POSITIONS, position
     return ms
+
+
+def _lcc(hp):
+    """`lcc = hp.nspeakers` when 'learn_channel_contributions' is in hp.multispeaker, else 0 (networks.py:22-24 etc.)."""
+    return hp.nspeakers if 'learn_channel_contributions' in getattr(hp, "multispeaker", []) else 0
 
 
 def _with_speaker_reps(hp, tensor, speaker_codes, i, reuse):
@@ -69,17 +72,18 @@ def _split_kv(tensor):
 def _text_encoder_body(hp, tensor, i, training, speaker_codes, reuse, ms):
     """The part TextEnc and MerlinTextEnc share (networks.py:146-211 == 52-118): C (relu), C, 8 + 2 highway layers,
     the optional speaker embedding towards the end, two k=1 highway layers, split into K | V."""
+    lcc = _lcc(hp)
     tensor = conv1d(tensor, filters=2 * hp.d, size=1, rate=1, dropout_rate=hp.dropout_rate, activation_fn=relu,
-                    training=training, scope="C_{}".format(i), normtype=hp.norm, reuse=reuse); i += 1
+                    training=training, scope="C_{}".format(i), normtype=hp.norm, reuse=reuse, lcc=lcc, codes=speaker_codes); i += 1
     tensor = conv1d(tensor, size=1, rate=1, dropout_rate=hp.dropout_rate, training=training,
-                    scope="C_{}".format(i), normtype=hp.norm, reuse=reuse); i += 1
+                    scope="C_{}".format(i), normtype=hp.norm, reuse=reuse, lcc=lcc, codes=speaker_codes); i += 1
     for _ in range(2):
         for j in range(4):
             tensor = hc(tensor, size=3, rate=3 ** j, dropout_rate=hp.dropout_rate, activation_fn=None,
-                        training=training, scope="HC_{}".format(i), normtype=hp.norm, reuse=reuse); i += 1
+                        training=training, scope="HC_{}".format(i), normtype=hp.norm, reuse=reuse, lcc=lcc, codes=speaker_codes); i += 1
     for _ in range(2):
         tensor = hc(tensor, size=3, rate=1, dropout_rate=hp.dropout_rate, activation_fn=None, training=training,
-                    scope="HC_{}".format(i), normtype=hp.norm, reuse=reuse); i += 1
+                    scope="HC_{}".format(i), normtype=hp.norm, reuse=reuse, lcc=lcc, codes=speaker_codes); i += 1
     if 'text_encoder_towards_end' in ms:
         tensor = _with_speaker_reps(hp, tensor, speaker_codes, i, reuse); i += 1
         # extra 1x1 conv to squash hidden + embedding -> desired size (2*hp.d)
@@ -87,7 +91,7 @@ def _text_encoder_body(hp, tensor, i, training, speaker_codes, reuse, ms):
                         training=training, scope="C_{}".format(i), normtype=hp.norm, reuse=reuse); i += 1
     for _ in range(2):
         tensor = hc(tensor, size=1, rate=1, dropout_rate=hp.dropout_rate, activation_fn=None, training=training,
-                    scope="HC_{}".format(i), normtype=hp.norm, reuse=reuse); i += 1
+                    scope="HC_{}".format(i), normtype=hp.norm, reuse=reuse, lcc=lcc, codes=speaker_codes); i += 1
     return _split_kv(tensor)
 
 
@@ -177,22 +181,23 @@ def AudioEnc(hp, S, training=True, speaker_codes=None, reuse=None, *, in_shift=0
       Q: Queries. (B, T/r, d) -- written straight into the second half of the [R, Q] decoder input buffer
     '''
     ms = _check_speakers(hp, speaker_codes)
+    lcc = _lcc(hp)
     i = 1
     tensor = conv1d(S, filters=hp.d, size=1, rate=1, padding="CAUSAL", dropout_rate=hp.dropout_rate,
                     activation_fn=relu, training=training, scope="C_{}".format(i), normtype=hp.norm, reuse=reuse,
-                    in_shift=in_shift); i += 1
+                    lcc=lcc, codes=speaker_codes, in_shift=in_shift); i += 1
     if 'audio_encoder_input' in ms:                              # networks.py:237-245
         tensor = _with_speaker_reps(hp, tensor, speaker_codes, i, reuse); i += 1
         tensor = conv1d(tensor, filters=hp.d, size=1, rate=1, dropout_rate=hp.dropout_rate, training=training,
                         scope="C_{}".format(i), normtype=hp.norm, reuse=reuse); i += 1
     tensor = conv1d(tensor, size=1, rate=1, padding="CAUSAL", dropout_rate=hp.dropout_rate, activation_fn=relu,
-                    training=training, scope="C_{}".format(i), normtype=hp.norm, reuse=reuse); i += 1
+                    training=training, scope="C_{}".format(i), normtype=hp.norm, reuse=reuse, lcc=lcc, codes=speaker_codes); i += 1
     tensor = conv1d(tensor, size=1, rate=1, padding="CAUSAL", dropout_rate=hp.dropout_rate, training=training,
-                    scope="C_{}".format(i), normtype=hp.norm, reuse=reuse); i += 1
+                    scope="C_{}".format(i), normtype=hp.norm, reuse=reuse, lcc=lcc, codes=speaker_codes); i += 1
     for _ in range(2):
         for j in range(4):
             tensor = hc(tensor, size=3, rate=3 ** j, padding="CAUSAL", dropout_rate=hp.dropout_rate,
-                        training=training, scope="HC_{}".format(i), normtype=hp.norm, reuse=reuse); i += 1
+                        training=training, scope="HC_{}".format(i), normtype=hp.norm, reuse=reuse, lcc=lcc, codes=speaker_codes); i += 1
     rq = None
     for n in range(2):
         out = out_planes = None
@@ -202,7 +207,7 @@ def AudioEnc(hp, S, training=True, speaker_codes=None, reuse=None, *, in_shift=0
             out = rq[:, :, d:]
             out_planes = (rq_planes[0][:, :, d:], rq_planes[1][:, :, d:])
         tensor = hc(tensor, size=3, rate=3, padding="CAUSAL", dropout_rate=hp.dropout_rate, training=training,
-                    scope="HC_{}".format(i), normtype=hp.norm, reuse=reuse, out=out, out_planes=out_planes); i += 1
+                    scope="HC_{}".format(i), normtype=hp.norm, reuse=reuse, lcc=lcc, codes=speaker_codes, out=out, out_planes=out_planes); i += 1
     if rq is not None:
         tensor._oph_rq = rq
     return tensor
@@ -336,6 +341,7 @@ def AudioDec(hp, R, training=True, speaker_codes=None, reuse=None):
       logits, Y: Melspectrogram predictions. (B, T/r, n_mels)
     '''
     ms = _check_speakers(hp, speaker_codes)
+    lcc = _lcc(hp)
     i = 1
     tensor = conv1d(R, filters=hp.d, size=1, rate=1, padding="CAUSAL", dropout_rate=hp.dropout_rate,
                     training=training, scope="C_{}".format(i), normtype=hp.norm, reuse=reuse); i += 1
@@ -345,17 +351,17 @@ def AudioDec(hp, R, training=True, speaker_codes=None, reuse=None):
                         scope="C_{}".format(i), normtype=hp.norm, reuse=reuse); i += 1
     for j in range(4):
         tensor = hc(tensor, size=3, rate=3 ** j, padding="CAUSAL", dropout_rate=hp.dropout_rate, training=training,
-                    scope="HC_{}".format(i), normtype=hp.norm, reuse=reuse); i += 1
+                    scope="HC_{}".format(i), normtype=hp.norm, reuse=reuse, lcc=lcc, codes=speaker_codes); i += 1
     for _ in range(2):
         tensor = hc(tensor, size=3, rate=1, padding="CAUSAL", dropout_rate=hp.dropout_rate, training=training,
-                    scope="HC_{}".format(i), normtype=hp.norm, reuse=reuse); i += 1
+                    scope="HC_{}".format(i), normtype=hp.norm, reuse=reuse, lcc=lcc, codes=speaker_codes); i += 1
     for _ in range(3):
         tensor = conv1d(tensor, size=1, rate=1, padding="CAUSAL", dropout_rate=hp.dropout_rate, activation_fn=relu,
-                        training=training, scope="C_{}".format(i), normtype=hp.norm, reuse=reuse); i += 1
+                        training=training, scope="C_{}".format(i), normtype=hp.norm, reuse=reuse, lcc=lcc, codes=speaker_codes); i += 1
     # mel_hats
     squash = hp.squash_output_t2m
     out = conv1d(tensor, filters=hp.n_mels, size=1, rate=1, padding="CAUSAL", dropout_rate=hp.dropout_rate,
-                 training=training, scope="C_{}".format(i), normtype=hp.norm, reuse=reuse,
+                 training=training, scope="C_{}".format(i), normtype=hp.norm, reuse=reuse, lcc=lcc, codes=speaker_codes,
                  want_sigmoid=squash, planes=False); i += 1          # the logits feed no further product
     logits, Y = out if squash else (out, out)
     return logits, Y

@@ -211,8 +211,11 @@ def normalize_bwd(dy, x, stats, gamma, beta, dgamma, dbeta):
 
 # ---------------------------------------------------------------------------------------------- highway conv
 def hc_fwd(x, pk, bias, g1, b1, g2, b2, rate=1, padding=SAME, norm=True, drop_p=0.0, seed=0, step=None,
-           save=False, y=None, planes=True, y_planes=None):
+           save=False, y=None, planes=True, y_planes=None, lcc=None):
+    """lcc = (table [ncodes, C], codes int32 [B]): per-speaker gates on LN(H2) (modules.py:200-201)."""
     ldx, B, L, C = _rows(x)
+    if lcc is not None:
+        _lib.call("oph_lcc_context", _p(lcc[0]), _p(lcc[1]), None)
     assert pk.cin == C and pk.cout == 2 * C
     dev = x.device
     z = torch.empty(B, L, 2 * C, device=dev, dtype=torch.float32)
@@ -227,9 +230,13 @@ def hc_fwd(x, pk, bias, g1, b1, g2, b2, rate=1, padding=SAME, norm=True, drop_p=
 
 
 def hc_bwd(dy, x, saved, pk, g1, b1, g2, b2, dw, dbias, dg1, db1, dg2, db2, rate=1, padding=SAME, norm=True,
-           drop_p=0.0, seed=0, step=None, dx=None):
+           drop_p=0.0, seed=0, step=None, dx=None, lcc=None, dtable=None):
     z, stats = saved
     ldx, B, L, C = _rows(x)
+    scratch = None
+    if lcc is not None:
+        scratch = torch.empty(B * L, C, device=x.device, dtype=torch.float32)
+        _lib.call("oph_lcc_context", _p(lcc[0]), _p(lcc[1]), _p(scratch))
     lddy = _rows(dy)[0]
     dev = x.device
     dz = torch.empty(B, L, 2 * C, device=dev, dtype=torch.float32)
@@ -240,8 +247,32 @@ def hc_bwd(dy, x, saved, pk, g1, b1, g2, b2, dw, dbias, dg1, db1, dg2, db2, rate
               _p(g2), _p(b2), _p(dz), dz.stride(1), None, 0, _p(dx), dx.stride(1), _p(dw),
               _p(dbias), _p(dg1), _p(db1), _p(dg2), _p(db2), B, L, C, pk.k, rate, padding, int(bool(norm)),
               float(drop_p), int(seed), _p(step), _stream())
+    if lcc is not None:
+        _lib.call("oph_lcc_reduce", _p(scratch), _p(lcc[1]), _p(dtable), B, L, C, _stream())
     _park(dz)
     return dx
+
+
+# ---------------------------------------------------------------------------------------------- channel gates
+def lcc_fwd(y0, table, codes, want_sigmoid=False, planes=True):
+    """modules.learn_channel_contributions behind a conv1d layer: out = sigmoid(embed(codes)) * y0."""
+    ld0, B, L, C = _rows(y0)
+    out = new_act(B, L, C, y0.device)
+    sig = new_act(B, L, C, y0.device) if want_sigmoid else None
+    _lib.call("oph_lcc_fwd", _p(y0), ld0, _p(table), _p(codes), _out_act(out, planes), _p(sig),
+              sig.stride(1) if sig is not None else 0, B, L, C, _stream())
+    return out, sig
+
+
+def lcc_bwd(dy, y0, table, codes, dtable):
+    ld0, B, L, C = _rows(y0)
+    lddy = _rows(dy)[0]
+    dy0 = new_act(B, L, C, y0.device)
+    scratch = torch.empty(B * L, C, device=y0.device, dtype=torch.float32)
+    _lib.call("oph_lcc_bwd", _p(dy), lddy, _p(y0), ld0, _p(table), _p(codes), _p(dy0), dy0.stride(1), _p(scratch), B, L, C,
+              _stream())
+    _lib.call("oph_lcc_reduce", _p(scratch), _p(codes), _p(dtable), B, L, C, _stream())
+    return dy0
 
 
 # ---------------------------------------------------------------------------------------------- transposed conv

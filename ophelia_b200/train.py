@@ -54,8 +54,15 @@ def compute_validation(hp, model_type, epoch, inputs, synth_graph, sess, speaker
     from . import synthesize as syn
     from .objective_measures import compute_dtw_error, compute_simple_LSD
     if model_type == 't2m':
-        K, V = syn.encode_text(hp, inputs, synth_graph, sess)
-        pred, lengths, _ = syn.synth_codedtext2mel_fast(hp, K, V, syn.get_text_lengths(inputs), synth_graph)
+        if hp.multispeaker or hp.use_external_durations or hp.merlin_label_dir:
+            # the variant inputs travel through the Session surface like in the reference (train.py:39)
+            pred, lengths = syn.synth_text2mel(hp, inputs, synth_graph, sess, speaker_data=speaker_codes,
+                                               duration_data=duration_data, labels=validation_labels)
+            if hp.use_external_durations:
+                lengths = [int(t) for t in np.asarray(duration_data).sum(axis=(1, 2))]
+        else:
+            K, V = syn.encode_text(hp, inputs, synth_graph, sess)
+            pred, lengths, _ = syn.synth_codedtext2mel_fast(hp, K, V, syn.get_text_lengths(inputs), synth_graph)
         predictions = syn.split_batch(pred, lengths)
         score = compute_dtw_error(validation_set_reference, predictions)
     elif model_type == 'ssrn':
@@ -84,7 +91,7 @@ def get_and_plot_alignments(hp, epoch, attention_graph, sess, attention_inputs, 
 
 
 def _validation_set(hp, model_type):
-    """train.py:102-177: (filenames, inputs, reference, texts, mels) of the held-out sentences."""
+    """train.py:102-177: (filenames, inputs, reference, texts, mels, variant inputs) of the held-out sentences."""
     from .data_load import load_data
     from .synthesize import make_mel_batch
     dataset = load_data(hp, mode="validation")
@@ -95,13 +102,26 @@ def _validation_set(hp, model_type):
     v_indices = v_indices[:min(hp.validation_sentences_to_evaluate, len(valid_filenames))]
     valid_filenames = np.array(valid_filenames)[v_indices]
     validation_text = validation_text[v_indices, :]
+    # speaker codes / duration matrices / label vectors of the same sentences (train.py:113-150)
+    extras = {"speaker_codes": None, "duration_data": None, "validation_labels": None}
+    if hp.multispeaker:
+        extras["speaker_codes"] = np.array(dataset['speakers'], np.int32)[v_indices].reshape(-1, 1)
+    if hp.use_external_durations:
+        extras["duration_data"] = np.asarray(dataset['durations'], np.float32)[v_indices]
+    if hp.merlin_label_dir:
+        from .data_load import load_merlin_label
+        labels = np.zeros((len(valid_filenames), hp.max_N, hp.merlin_lab_dim), np.float32)
+        for i, f in enumerate(valid_filenames):
+            lab = load_merlin_label(hp, f)
+            labels[i, :lab.shape[0]] = lab
+        extras["validation_labels"] = labels
     validation_mels = None
     if model_type in ('t2m', 'babbler'):       # (the babbler's validation score is the reference's dummy 0.0, train.py:49-50)
         validation_mels = [np.load(hp.coarse_audio_dir + os.path.sep + _basename(f) + '.npy') for f in valid_filenames]
-        return valid_filenames, validation_text, validation_mels, validation_text, validation_mels
+        return valid_filenames, validation_text, validation_mels, validation_text, validation_mels, extras
     validation_mags = [np.load(hp.full_audio_dir + os.path.sep + _basename(f) + '.npy') for f in valid_filenames]
     inputs, _lengths = make_mel_batch(hp, valid_filenames)
-    return valid_filenames, inputs, validation_mags, validation_text, validation_mels
+    return valid_filenames, inputs, validation_mags, validation_text, validation_mels, extras
 
 
 def initialise_from_existing(store, hp):
@@ -154,7 +174,7 @@ def train(hp, model_type, max_steps_per_epoch=None):
     if chief:
         logger_setup(logdir)
         info('Command line: %s' % (" ".join(sys.argv)))
-    valid_filenames, validation_inputs, validation_reference, validation_text, validation_mels = _validation_set(hp, model_type)
+    valid_filenames, validation_inputs, validation_reference, validation_text, validation_mels, vx = _validation_set(hp, model_type)
     plot_attention = bool(hp.plot_attention_every_n_epochs) and model_type == 't2m' and hp.num_sentences_to_plot_attention > 0
     if plot_attention:                                            # train.py:160-171
         n_plot = hp.num_sentences_to_plot_attention
@@ -193,8 +213,9 @@ def train(hp, model_type, max_steps_per_epoch=None):
     if chief:
         if plot_attention and epoch == 0:
             get_and_plot_alignments(hp, epoch - 1, attention_graph, sess, attention_inputs, attention_mels, logdir + "/alignments")
-        current_score = compute_validation(hp, model_type, epoch, validation_inputs, synth_graph, sess, None, valid_filenames,
-                                           validation_reference)
+        current_score = compute_validation(hp, model_type, epoch, validation_inputs, synth_graph, sess, vx["speaker_codes"],
+                                           valid_filenames, validation_reference, duration_data=vx["duration_data"],
+                                           validation_labels=vx["validation_labels"])
         info('validation epoch {0}: {1:0.3f}'.format(epoch, current_score))
 
     steps_per_epoch = g.num_batch // world if world > 1 else g.num_batch
@@ -213,8 +234,9 @@ def train(hp, model_type, max_steps_per_epoch=None):
 
         if chief:
             if hp.validate_every_n_epochs and epoch % hp.validate_every_n_epochs == 0:
-                current_score = compute_validation(hp, model_type, epoch, validation_inputs, synth_graph, sess, None,
-                                                   valid_filenames, validation_reference)
+                current_score = compute_validation(hp, model_type, epoch, validation_inputs, synth_graph, sess, vx["speaker_codes"],
+                                                   valid_filenames, validation_reference, duration_data=vx["duration_data"],
+                                                   validation_labels=vx["validation_labels"])
                 info('validation epoch {0:0}: {1:0.3f}'.format(epoch, current_score))
             if plot_attention and epoch % hp.plot_attention_every_n_epochs == 0:
                 get_and_plot_alignments(hp, epoch, attention_graph, sess, attention_inputs, attention_mels, logdir + "/alignments")

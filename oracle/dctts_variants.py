@@ -1,6 +1,7 @@
 """torch-CPU restatement of the research variants that hang off the same operator surface (TEST INFRASTRUCTURE ONLY;
 PARITY UNPINNED like the rest of oracle/): speaker embeddings at the five positions of hp.multispeaker, MerlinTextEnc /
-LinearTransformLabels / the label-only text encoders, FixedAttention with external durations, BabblerGraph.
+LinearTransformLabels / the label-only text encoders, FixedAttention with external durations, BabblerGraph, and the
+per-speaker channel gates of modules.learn_channel_contributions (modules.py:78-88, 141-144, 200-201).
 Cites networks.py:15-119 (MerlinTextEnc), :121-212 (TextEnc), :214-284 (AudioEnc), :327-358 (FixedAttention),
 :360-435 (AudioDec), :437-537 (SSRN), :540-560 (LinearTransformLabels), architectures.py:183-239, 380-432.
 The layer counter `i` of every network is advanced exactly like the reference's (speaker embeddings consume an index)."""
@@ -21,19 +22,52 @@ def speaker_cat(hp, P, t, scope, speaker_codes):
     return torch.cat([t, ot.embed(P, ids, scope)], -1)
 
 
+def _lcc(hp):
+    return 'learn_channel_contributions' in _ms(hp)
+
+
+def lcc_gate(P, scope, codes):
+    """modules.learn_channel_contributions (modules.py:78-88): sigmoid(embed(codes [B, 1], scope="lcc_embed")) -> [B, 1, C]."""
+    ids = torch.as_tensor(codes, dtype=torch.long).reshape(-1, 1)
+    return torch.sigmoid(ot.embed(P, ids, scope + "/lcc_embed"))
+
+
+def conv1d(hp, P, x, scope, codes=None, gated=False, act=None, **kw):
+    """modules.conv1d with the optional channel gates after dropout (modules.py:141-144)."""
+    t = ot.conv1d(P, x, scope, act=act, **kw)
+    if gated and _lcc(hp):
+        t = lcc_gate(P, scope, codes) * t
+    return t
+
+
+def hc(hp, P, x, scope, size, rate, codes=None, gated=True, padding="SAME", normtype="layer", dropout_rate=0.0, training=False,
+       gen=None):
+    """modules.hc with the channel gates on the transformation connection H2 only (modules.py:194-205)."""
+    if not (gated and _lcc(hp)):
+        return ot.hc(P, x, scope, size, rate, padding=padding, normtype=normtype, dropout_rate=dropout_rate, training=training,
+                     gen=gen)
+    t = ot._conv(x, P[scope + "/conv1d/kernel"], P[scope + "/conv1d/bias"], rate, padding)
+    H1, H2 = t.chunk(2, -1)
+    H1 = torch.sigmoid(ot.layer_norm(P, H1, scope + "/H1", normtype))
+    H2 = ot.layer_norm(P, H2, scope + "/H2", normtype)
+    H2 = lcc_gate(P, scope, codes) * H2
+    return ot._drop(H1 * H2 + (1.0 - H1) * x, dropout_rate, training, gen)
+
+
 def _text_body(hp, P, t, i, prefix, speaker_codes, kw):
-    t = ot.conv1d(P, t, "%s/C_%d" % (prefix, i), act="relu", **kw); i += 1
-    t = ot.conv1d(P, t, "%s/C_%d" % (prefix, i), **kw); i += 1
+    c = speaker_codes
+    t = conv1d(hp, P, t, "%s/C_%d" % (prefix, i), c, True, act="relu", **kw); i += 1
+    t = conv1d(hp, P, t, "%s/C_%d" % (prefix, i), c, True, **kw); i += 1
     for _ in range(2):
         for j in range(4):
-            t = ot.hc(P, t, "%s/HC_%d" % (prefix, i), 3, 3 ** j, **kw); i += 1
+            t = hc(hp, P, t, "%s/HC_%d" % (prefix, i), 3, 3 ** j, c, **kw); i += 1
     for _ in range(2):
-        t = ot.hc(P, t, "%s/HC_%d" % (prefix, i), 3, 1, **kw); i += 1
+        t = hc(hp, P, t, "%s/HC_%d" % (prefix, i), 3, 1, c, **kw); i += 1
     if 'text_encoder_towards_end' in _ms(hp):
         t = speaker_cat(hp, P, t, "%s/embed_%d" % (prefix, i), speaker_codes); i += 1
         t = ot.conv1d(P, t, "%s/C_%d" % (prefix, i), act="relu", **kw); i += 1
     for _ in range(2):
-        t = ot.hc(P, t, "%s/HC_%d" % (prefix, i), 1, 1, **kw); i += 1
+        t = hc(hp, P, t, "%s/HC_%d" % (prefix, i), 1, 1, c, **kw); i += 1
     return t.chunk(2, -1)
 
 
@@ -64,18 +98,18 @@ def MerlinTextEnc(hp, P, L, labels, speaker_codes=None, training=False, gen=None
 
 def AudioEnc(hp, P, S, speaker_codes=None, training=False, gen=None, prefix="Text2Mel/AudioEnc"):
     kw = dict(padding="CAUSAL", normtype=hp.norm, dropout_rate=hp.dropout_rate, training=training, gen=gen)
-    i = 1
-    t = ot.conv1d(P, S, "%s/C_%d" % (prefix, i), act="relu", **kw); i += 1
+    i, c = 1, speaker_codes
+    t = conv1d(hp, P, S, "%s/C_%d" % (prefix, i), c, True, act="relu", **kw); i += 1
     if 'audio_encoder_input' in _ms(hp):
         t = speaker_cat(hp, P, t, "%s/embed_%d" % (prefix, i), speaker_codes); i += 1
         t = ot.conv1d(P, t, "%s/C_%d" % (prefix, i), **dict(kw, padding="SAME")); i += 1
-    t = ot.conv1d(P, t, "%s/C_%d" % (prefix, i), act="relu", **kw); i += 1
-    t = ot.conv1d(P, t, "%s/C_%d" % (prefix, i), **kw); i += 1
+    t = conv1d(hp, P, t, "%s/C_%d" % (prefix, i), c, True, act="relu", **kw); i += 1
+    t = conv1d(hp, P, t, "%s/C_%d" % (prefix, i), c, True, **kw); i += 1
     for _ in range(2):
         for j in range(4):
-            t = ot.hc(P, t, "%s/HC_%d" % (prefix, i), 3, 3 ** j, **kw); i += 1
+            t = hc(hp, P, t, "%s/HC_%d" % (prefix, i), 3, 3 ** j, c, **kw); i += 1
     for _ in range(2):
-        t = ot.hc(P, t, "%s/HC_%d" % (prefix, i), 3, 3, **kw); i += 1
+        t = hc(hp, P, t, "%s/HC_%d" % (prefix, i), 3, 3, c, **kw); i += 1
     return t
 
 
@@ -94,13 +128,14 @@ def AudioDec(hp, P, R, speaker_codes=None, training=False, gen=None, prefix="Tex
     if 'audio_decoder_input' in _ms(hp):
         t = speaker_cat(hp, P, t, "%s/embed_%d" % (prefix, i), speaker_codes); i += 1
         t = ot.conv1d(P, t, "%s/C_%d" % (prefix, i), **dict(kw, padding="SAME")); i += 1
+    c = speaker_codes
     for j in range(4):
-        t = ot.hc(P, t, "%s/HC_%d" % (prefix, i), 3, 3 ** j, **kw); i += 1
+        t = hc(hp, P, t, "%s/HC_%d" % (prefix, i), 3, 3 ** j, c, **kw); i += 1
     for _ in range(2):
-        t = ot.hc(P, t, "%s/HC_%d" % (prefix, i), 3, 1, **kw); i += 1
+        t = hc(hp, P, t, "%s/HC_%d" % (prefix, i), 3, 1, c, **kw); i += 1
     for _ in range(3):
-        t = ot.conv1d(P, t, "%s/C_%d" % (prefix, i), act="relu", **kw); i += 1
-    logits = ot.conv1d(P, t, "%s/C_%d" % (prefix, i), **kw)
+        t = conv1d(hp, P, t, "%s/C_%d" % (prefix, i), c, True, act="relu", **kw); i += 1
+    logits = conv1d(hp, P, t, "%s/C_%d" % (prefix, i), c, True, **kw)
     Y = torch.sigmoid(logits) if getattr(hp, "squash_output_t2m", True) else logits
     return logits, Y
 

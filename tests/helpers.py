@@ -46,7 +46,8 @@ def check_grads(ours, ref, strict_prefix, median_tol=1.5e-2, max_tol=5e-2, stric
     return errs
 
 
-def make_corpus(root, n_utts=14, n_valid=3, max_N=24, max_T=40, seed=0, guides=True, full_dim=513, **overrides):
+def make_corpus(root, n_utts=14, n_valid=3, max_N=24, max_T=40, seed=0, guides=True, full_dim=513, variant_fields=False,
+                **overrides):
     """A tiny on-disk corpus in the reference's layout (transcript `name|raw|normalised|phones`, .npy features under
     mels/ full_mels/ mags/ attention_guides/) plus a python-syntax config file like config/lj_test.cfg.
     Returns (config path, hp)."""
@@ -78,7 +79,14 @@ def make_corpus(root, n_utts=14, n_valid=3, max_N=24, max_T=40, seed=0, guides=T
         np.save(os.path.join(dirs["mags"], name + ".npy"), rng.uniform(1e-8, 1.0, (t * r, full_dim)).astype(np.float32))
         if len(seq) <= max_N and t <= max_T:
             save_floats_as_8bit(get_attention_guide(len(seq), t, g=0.2), os.path.join(dirs["attention_guides"], name + ".npy"))
-        lines.append("%s|Raw text %d.|raw text %d.|%s" % (name, u, u, " ".join(seq)))
+        line = "%s|Raw text %d.|raw text %d.|%s" % (name, u, u, " ".join(seq))
+        if variant_fields:      # fifth field: speaker; sixth: frames per symbol at the full rate (README: multispeaker / durations)
+            cuts = np.sort(rng.choice(np.arange(1, t * r), len(seq) - 1, replace=False))
+            durs = np.diff(np.concatenate([[0], cuts, [t * r]]))
+            line += "|%s|%s" % (["spk_a", "spk_b", "spk_c"][u % 3], " ".join(str(int(d)) for d in durs))
+            os.makedirs(os.path.join(root, "data", "labels"), exist_ok=True)
+            np.save(os.path.join(root, "data", "labels", name + ".npy"), rng.uniform(0, 1, (len(seq), 12)).astype(np.float32))
+        lines.append(line)
     lines.insert(2, "")                                      # blank lines are ignored
     lines.append("NOFEATS-0001|x|x|<_START_> a <_END_>")     # no feature files: skipped
     with open(os.path.join(root, "transcript.csv"), "w") as f:

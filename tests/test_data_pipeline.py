@@ -165,9 +165,9 @@ def test_objective_measures():
 def test_validation_set_of_the_training_driver(tmp_path):
     from ophelia_b200 import train as drv
     cfg, hp = make_corpus(tmp_path)
-    names, inputs, reference, texts, mels = drv._validation_set(hp, 't2m')
+    names, inputs, reference, texts, mels, _ = drv._validation_set(hp, 't2m')
     assert len(names) == 3 and inputs.shape == (3, hp.max_N) and len(reference) == 3 and reference[0].shape[1] == hp.n_mels
-    names2, inputs2, reference2, _, _ = drv._validation_set(hp, 'ssrn')
+    names2, inputs2, reference2, _, _, _ = drv._validation_set(hp, 'ssrn')
     assert list(names2) == list(names)                               # seeded shuffle (train.py:111-115)
     assert inputs2.shape == (3, hp.max_T, hp.n_mels) and reference2[0].shape[1] == hp.full_dim
 
@@ -275,3 +275,41 @@ def test_training_graphs_of_two_ranks_read_disjoint_shards(tmp_path):
     (r0, idx0, nb0), (r1, idx1, nb1) = got
     assert (r0, r1) == (0, 1) and nb0 == nb1 == 24 // 4
     assert not set(idx0) & set(idx1) and len(set(idx0) | set(idx1)) == 24
+
+
+def test_variant_fields_speakers_durations_labels(tmp_path):
+    """The transcript's speaker and duration fields and the Merlin label files (data_load.py:143-193, 243-251, 381-383,
+    466-478): speaker codes through hp.speaker_list, durations as hard attention matrices at the coarse frame rate with
+    the utterance's own random reduction offset, labels padded per batch; speaker-dependent phone sets."""
+    from helpers import make_corpus
+    from ophelia_b200 import data_load as dl
+    cfg, hp = make_corpus(tmp_path, n_utts=16, n_valid=3, variant_fields=True, guides=False,
+                          multispeaker=['text_encoder_input'], speaker_list=['<PADDING>', 'spk_a', 'spk_b', 'spk_c'],
+                          nspeakers=4, speaker_embedding_size=8, use_external_durations=True,
+                          merlin_label_dir=str(tmp_path / "data" / "labels"), merlin_lab_dim=12,
+                          text_encoder_type='MerlinTextEnc', bucket_data_by='audio_length')
+    data = dl.load_data(hp, mode="train")
+    n = len(data['fpaths'])
+    assert len(data['speakers']) == n and len(data['durations']) == n and len(data['label_lengths']) == n
+    assert set(int(s) for s in data['speakers']) == {1, 2, 3}
+    for dur, tl, al in zip(data['durations'], data['text_lengths'], data['audio_lengths']):
+        assert len(dur) == tl and dur.sum() == al * hp.r
+    src = dl.BatchSource(hp, 4, dataset=data, need=('text', 'mel'), seed=3, num_threads=0, pin=False)
+    batch = next(src)
+    B, T = batch['mel'].shape[:2]
+    assert batch['speaker'].shape == (B, 1) and batch['speaker'].dtype == torch.int32
+    assert batch['duration'].shape[:2] == (B, T) and batch['merlin_label'].shape[0] == B and batch['merlin_label'].shape[2] == 12
+    D = batch['duration'].numpy()
+    for b in range(B):
+        tlen = int((batch['mel'][b].abs().sum(-1) > 0).sum())
+        assert np.all(D[b, :tlen].sum(-1) == 1.0) and np.all(D[b, tlen:].sum() == 0.0)       # one symbol per real frame
+        path = D[b, :tlen].argmax(-1)
+        assert np.all(np.diff(path) >= 0)                                                     # monotonic
+    # validation mode stacks the duration matrices at offset 0 (data_load.py:243-251)
+    val = dl.load_data(hp, mode="validation")
+    assert val['durations'].shape == (len(val['fpaths']), hp.max_T, hp.max_N)
+    assert np.all(val['durations'].sum(-1) <= 1)
+    # speaker-dependent phones: one copy of the phone set per speaker
+    hp.multispeaker = ['speaker_dependent_phones']
+    c2i, _ = dl.load_vocab(hp)
+    assert len(c2i) == 1 + 3 * (len(hp.vocab) - 1) and 'a_spk_b' in c2i

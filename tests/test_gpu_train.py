@@ -87,3 +87,24 @@ def test_ssrn_training_driver(tmp_path):
     assert sorted(os.path.basename(f) for f in glob.glob(logdir + "/model_epoch_*.index")) == ["model_epoch_0.index", "model_epoch_1.index"]
     pred = np.load(glob.glob(logdir + "/validation_epoch_1/*.npy")[0])
     assert pred.shape[1] == hp.full_dim and pred.shape[0] % hp.r == 0
+
+
+def test_multispeaker_duration_label_training_driver(tmp_path):
+    """The training driver over a corpus whose transcript carries speakers and durations and whose symbols have Merlin label
+    vectors: get_batch feeds 'speaker' / 'duration' / 'merlin_label', the graph runs MerlinTextEnc + speaker embeddings +
+    channel gates + FixedAttention, validation feeds the same inputs through the Session surface (train.py:37-41, 113-150)."""
+    from ophelia_b200 import train as drv
+    cfg, hp = make_corpus(tmp_path, n_utts=20, n_valid=3, max_epochs=1, guides=False, variant_fields=True,
+                          multispeaker=['text_encoder_input', 'audio_decoder_input', 'learn_channel_contributions'],
+                          speaker_list=['<PADDING>', 'spk_a', 'spk_b', 'spk_c'], nspeakers=4, speaker_embedding_size=8,
+                          use_external_durations=True, merlin_label_dir=str(tmp_path / "data" / "labels"), merlin_lab_dim=12,
+                          text_encoder_type='MerlinTextEnc', plot_attention_every_n_epochs=0)
+    score = drv.train(hp, 't2m')
+    assert np.isfinite(score) and score > 0
+    logdir = hp.logdir + "-t2m"
+    from ophelia_b200 import tf_checkpoint
+    names = tf_checkpoint.list_variables(logdir + "/model_epoch_1")
+    assert any("MerlinTextEnc/embed_2/lookup_table" in n for n in names)            # speaker table at the text encoder input
+    assert any("/lcc_embed/lookup_table" in n for n in names)
+    log = open(glob.glob(logdir + "/log_*.txt")[0]).read()
+    assert log.count("train epoch") == 2

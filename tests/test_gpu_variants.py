@@ -78,6 +78,48 @@ def test_multispeaker_text2mel_matches_oracle(positions):
                 assert np.abs(gr[[0, 3]]).max() == 0.0 and np.abs(gr[[1, 2, 4]]).max() > 0, n
 
 
+def test_learn_channel_contributions_matches_oracle():
+    """'learn_channel_contributions' in hp.multispeaker (modules.py:78-88): a sigmoid gate per (speaker, channel) behind the
+    conv1d layers and on the transformation connection of the highway layers of TextEnc / AudioEnc / AudioDec, including the
+    mel logits.  Forward, two optimiser steps and the gradients of the gate tables against the fp64 restatement."""
+    from ophelia_b200.architectures import text2mel_variables
+    from ophelia_b200.session import Session
+    B, N, T = 3, 24, 50
+    hp = make_hp(max_N=N, max_T=T, dropout_rate=0.0, multispeaker=['learn_channel_contributions'], nspeakers=4,
+                 speaker_embedding_size=16)
+    specs = text2mel_variables(hp)
+    assert sum("/lcc_embed/" in n for n, _, _ in specs) == 14 + 13 + 10           # TextEnc C,C,12 HC; AudioEnc 3 C, 10 HC; AudioDec 6 HC, 4 C
+    P = _params(specs, 27)
+    for n in P:                                   # gates away from the trivial 0.5
+        if "/lcc_embed/" in n:
+            P[n] = (P[n] * 8).astype(np.float32)
+    b = synthetic_batch(hp, B, N, T, ragged=True)
+    speakers = np.array([[2], [0], [3]], np.int32)         # code 0 = the zero-pad row: gate 0.5, no gradient
+    Pt = ot.to_torch(P, torch.float64, requires_grad=True)
+    opt = ot.TFAdam(hp, Pt)
+    Lt, mt = _t(b["L"], torch.long), _t(b["mels"])
+    with torch.no_grad():
+        ref = ov.text2mel_forward(hp, Pt, Lt, mt, "generate_attention", speakers=speakers)
+    g = _t2m(hp, "generate_attention", P)
+    Y, ali = Session().run([g.Y, g.alignments], {g.L: b["L"], g.mels: b["mels"], g.speakers: speakers})
+    assert maxabs(Y, ref["Y"].numpy()) < 1e-3 and maxabs(ali, ref["alignments"].numpy()) < 1e-4
+    gt = _t2m(hp, "train", P, data=iter([]))
+    Ld, md, sd = torch.tensor(b["L"]).cuda(), torch.tensor(b["mels"]).cuda(), torch.tensor(speakers).cuda()
+    for step in range(2):
+        comps_ref, grads_ref = ov.text2mel_train_step(hp, Pt, opt, Lt, mt, speakers=speakers)
+        comps = gt.train_step_device(Ld, md, sd).cpu().numpy()
+        np.testing.assert_allclose(comps, comps_ref, rtol=3e-4, atol=1e-6)
+        if step == 0:
+            ours = {n: gt.store.grads[n].cpu().numpy() for n in grads_ref}
+            tables = [n for n in grads_ref if "/lcc_embed/" in n]
+            assert len(tables) == 37
+            for n in tables:
+                assert np.abs(ours[n][[0, 1]]).max() == 0.0, n                    # pad row and the absent speaker
+            nets = network_grad_errors(ours, {n: grads_ref[n].numpy() for n in tables},
+                                       ["Text2Mel/TextEnc/", "Text2Mel/AudioEnc/", "Text2Mel/AudioDec/"])
+            assert max(nets.values()) < 5e-2, nets
+
+
 def test_multispeaker_ssrn_matches_oracle():
     from ophelia_b200.architectures import SSRNGraph, ssrn_variables
     from ophelia_b200.variables import VariableStore
