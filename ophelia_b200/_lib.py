@@ -6,7 +6,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libophelia_sm100.so")
+LIB_PATH = os.environ.get("OPH_LIB_PATH") or os.path.join(_HERE, "libophelia_sm100.so")      # (override: A/B of two builds)
 
 P, LL, I, F, D, U64, SZ = (ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_float, ctypes.c_double,
                           ctypes.c_uint64, ctypes.c_size_t)
@@ -105,6 +105,8 @@ def load():
                            "(the CUDA path has no CPU fallback)" % LIB_PATH)
     lib = ctypes.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
+        if not hasattr(lib, name) and os.environ.get("OPH_LIB_PATH"):
+            continue                                    # an older build under A/B comparison lacks the newer entry points
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args

@@ -168,7 +168,8 @@ bool g_use_hc_fuse = true;   // highway tail in the epilogue phase of the conv G
 int launch_gemm(GemmArgs& a, int zdim, cudaStream_t st) {
     static bool attr_done = false;
     if (!attr_done) {
-        if (cudaFuncSetAttribute(gemm_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM) != cudaSuccess)
+        if (cudaFuncSetAttribute(gemm_bf16x3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM) != cudaSuccess ||
+            cudaFuncSetAttribute(gemm_bf16x3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM) != cudaSuccess)
             return check_launch("cudaFuncSetAttribute(gemm)");
         attr_done = true;
     }
@@ -276,7 +277,8 @@ int launch_gemm(GemmArgs& a, int zdim, cudaStream_t st) {
     dim3 grid(2 * pairs);
     {
         ProfScope ps(a.tag, 2.0 * a.M * a.N * (a.prof_k ? a.prof_k : a.Kc) * (a.a_mode == A_KMAJOR ? a.ntaps : a.ytaps) * (a.z_mode == Z_BATCH ? a.zdim : 1), st);
-        launch_cfg(grid, GEMM_THREADS, GEMM_SMEM, st)(gemm_bf16x3_kernel, a);
+        if (a.hc_fused) launch_cfg(grid, GEMM_THREADS, GEMM_SMEM, st)(gemm_bf16x3_kernel<true>, a);
+        else launch_cfg(grid, GEMM_THREADS, GEMM_SMEM, st)(gemm_bf16x3_kernel<false>, a);
     }
     return check_launch("gemm_bf16x3_kernel");
 }

@@ -245,8 +245,9 @@ __device__ __forceinline__ Unit decode_unit(const GemmArgs& p, int v, int MP, in
 // The it-th work item of CTA pair `pair` as a unit index for decode_unit, or -1 past the end.  Plain launches walk the
 // units round-robin.  With a fused highway tail the first hc_fused row-tile pairs are super-units (all column blocks of a
 // row tile consecutively on one pair), the other row tiles follow as plain units.
+template <bool HC>
 __device__ __forceinline__ int item_unit(const GemmArgs& p, int it, int pair, int npairs, int MP, int nblocks, int total) {
-    if (!p.hc_fused) { const int u = pair + it * npairs; return u < total ? u : -1; }
+    if (!HC || !p.hc_fused) { const int u = pair + it * npairs; return u < total ? u : -1; }
     const int F = p.hc_fused;
     const int nsup = F > pair ? (F - pair + npairs - 1) / npairs : 0;
     if (it < nsup * nblocks) return (it % nblocks) * MP + pair + (it / nblocks) * npairs;
@@ -255,8 +256,9 @@ __device__ __forceinline__ int item_unit(const GemmArgs& p, int it, int pair, in
     return (r / W) * MP + F + r % W;
 }
 // is item `it` of this pair the last column block of a fused super-unit?
+template <bool HC>
 __device__ __forceinline__ bool item_closes_tile(const GemmArgs& p, int it, int pair, int npairs, int nblocks) {
-    if (!p.hc_fused) return false;
+    if (!HC || !p.hc_fused) return false;
     const int nsup = p.hc_fused > pair ? (p.hc_fused - pair + npairs - 1) / npairs : 0;
     return it < nsup * nblocks && (it % nblocks) == nblocks - 1;
 }
@@ -360,6 +362,8 @@ __device__ __forceinline__ void hc_tail_rows(const GemmArgs& p, float* sm, int w
     asm volatile("bar.sync 13, 512;" ::: "memory");        // the staging area goes back to the plain epilogue
 }
 
+// HC = true: the instantiation that can run the highway tail (hc_fused); the plain one carries none of that code
+template <bool HC>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
     extern __shared__ uint8_t smem_raw[];
@@ -427,7 +431,7 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
                             (!p.addend || (!(p.ld_add & 3) && !(reinterpret_cast<uintptr_t>(p.addend) & 15)));
         int acc = 0, acc_par = 0;
         for (int it_ = 0;; ++it_) {
-            const int u = item_unit(p, it_, pair, npairs, MP, nblocks, total);
+            const int u = item_unit<HC>(p, it_, pair, npairs, MP, nblocks, total);
             if (u < 0) break;
             const Unit t = decode_unit(p, u, MP, nblocks, crank);
             if (t.KB <= 0) continue;
@@ -498,7 +502,7 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
                 __syncwarp();
             }
             if (++acc == N_ACC) { acc = 0; acc_par ^= 1; }
-            if (item_closes_tile(p, it_, pair, npairs, nblocks)) {
+            if (item_closes_tile<HC>(p, it_, pair, npairs, nblocks)) {
                 // every column block of this CTA's 128 rows is in z now (written by the 16 epilogue warps of this CTA):
                 // make it visible CTA-wide, then finish the rows -- the MMA warp is already busy with the next row tile
                 asm volatile("bar.sync 13, 512;" ::: "memory");
@@ -536,7 +540,7 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
         };
         int acc = 0, acc_par = 0;
         for (int it_ = 0;; ++it_) {
-            const int u = item_unit(p, it_, pair, npairs, MP, nblocks, total);
+            const int u = item_unit<HC>(p, it_, pair, npairs, MP, nblocks, total);
             if (u < 0) break;
             const Unit t = decode_unit(p, u, MP, nblocks, crank);
             if (t.KB <= 0) continue;
@@ -800,7 +804,7 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
             int as = 0, a_par = 0, bs = 0, b_par = 0, acc = 0, acc_par = 1;
             long long w_t = 0, w_a = 0, w_b = 0, t_begin = clock64(), nkb = 0;
             for (int it_ = 0;; ++it_) {
-                const int u = item_unit(p, it_, pair, npairs, MP, nblocks, total);
+                const int u = item_unit<HC>(p, it_, pair, npairs, MP, nblocks, total);
                 if (u < 0) break;
                 const Unit t = decode_unit(p, u, MP, nblocks, crank);
                 if (t.KB <= 0) continue;
@@ -857,7 +861,7 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
             const uint32_t fullA0 = mapa_u32(BAR(BAR_FULL_A), 0), fullB0 = mapa_u32(BAR(BAR_FULL_B), 0);   // leader's barriers
             const int KBI = (p.A.L + GEMM_BK - 1) / GEMM_BK;       // 64-step blocks per batch item (r_tma, split-K)
             for (int it_ = 0;; ++it_) {
-                const int u = item_unit(p, it_, pair, npairs, MP, nblocks, total);
+                const int u = item_unit<HC>(p, it_, pair, npairs, MP, nblocks, total);
                 if (u < 0) break;
                 const Unit t = decode_unit(p, u, MP, nblocks, crank);
                 // packed image rows (128 bytes each) of this CTA's half of stage (nb, kb): ((nb*KB + kb)*2 + crank) * 256
@@ -958,7 +962,7 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
         if (p.a_tma == 1) {
             int as = 0; uint32_t land_par = 0;
             for (int it_ = 0;; ++it_) {
-                const int u = item_unit(p, it_, pair, npairs, MP, nblocks, total);
+                const int u = item_unit<HC>(p, it_, pair, npairs, MP, nblocks, total);
                 if (u < 0) break;
                 const Unit t = decode_unit(p, u, MP, nblocks, crank);
                 int tmod[4];                                   // step within the item of this lane's 4 rows
