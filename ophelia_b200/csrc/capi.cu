@@ -9,6 +9,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -26,7 +27,7 @@ int g_hcb_depth = 0;               // ring depth of the highway-backward row ker
 long long* g_gemm_dbg = nullptr;   // optional device buffer [74][8] for in-kernel wait-cycle counters
 
 // Optional per-launch timing of the GEMM core (bench.py roofline): CUDA events around every launch, by tag.
-struct ProfRec { cudaEvent_t e0, e1; int tag; double flops; };
+struct ProfRec { cudaEvent_t e0, e1; int tag; double flops; char desc[112]; };
 std::mutex g_prof_mu;
 bool g_prof_on = false;
 std::vector<ProfRec> g_prof;
@@ -82,8 +83,9 @@ struct launch_cfg {
 // algorithmic bytes (row-wise tags)
 struct ProfScope {
     ProfRec rec{}; bool on = false; cudaStream_t st;
-    ProfScope(int tag, double work, cudaStream_t stream) : st(stream) {
+    ProfScope(int tag, double work, cudaStream_t stream, const char* desc = "") : st(stream) {
         if (!g_prof_on) return;
+        snprintf(rec.desc, sizeof(rec.desc), "%s", desc);
         cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
         cudaStreamIsCapturing(st, &cs);
         if (cs != cudaStreamCaptureStatusNone) return;
@@ -276,7 +278,11 @@ int launch_gemm(GemmArgs& a, int zdim, cudaStream_t st) {
     }
     dim3 grid(2 * pairs);
     {
-        ProfScope ps(a.tag, 2.0 * a.M * a.N * (a.prof_k ? a.prof_k : a.Kc) * (a.a_mode == A_KMAJOR ? a.ntaps : a.ytaps) * (a.z_mode == Z_BATCH ? a.zdim : 1), st);
+        char desc[112] = "";
+        if (g_prof_on)
+            snprintf(desc, sizeof(desc), "M=%d N=%d K=%d taps=%d ytaps=%d z=%d units=%lld items=%lld pairs=%d split=%d atma=%d btma=%d rtma=%d hc=%d", a.M, a.N,
+                     a.prof_k ? a.prof_k : a.Kc, a.ntaps, a.ytaps, a.zdim, units, items, pairs, a.split_s, a.a_tma, a.b_tma, a.r_tma, a.hc_fused);
+        ProfScope ps(a.tag, 2.0 * a.M * a.N * (a.prof_k ? a.prof_k : a.Kc) * (a.a_mode == A_KMAJOR ? a.ntaps : a.ytaps) * (a.z_mode == Z_BATCH ? a.zdim : 1), st, desc);
         if (a.hc_fused) launch_cfg(grid, GEMM_THREADS, GEMM_SMEM, st)(gemm_bf16x3_kernel<true>, a);
         else launch_cfg(grid, GEMM_THREADS, GEMM_SMEM, st)(gemm_bf16x3_kernel<false>, a);
     }
@@ -420,7 +426,8 @@ int launch_ln_act_fwd(const float* z, long long ldz, const float* gamma, const f
                       uint64_t seed, const long long* step, cudaStream_t st) {
     const int grid = rows_grid(rows, 8);
     float* y = yo->f32; const long long ldy = yo->ld;
-    ProfScope ps(OPH_TAG_ROW_FWD, (double)rows * C * (yo->hi ? 12.0 : 8.0), st);
+    char pdesc[64] = ""; if (g_prof_on) snprintf(pdesc, sizeof(pdesc), "ln_fwd rows=%lld C=%d", (long long)rows, C);
+    ProfScope ps(OPH_TAG_ROW_FWD, (double)rows * C * (yo->hi ? 12.0 : 8.0), st, pdesc);
     if (yo->hi && (!yo->lo || (yo->ldp & 7))) return fail(OPH_EINVAL, "split-bf16 output planes need 16-byte aligned rows%s");
     if (vec_ok(C, ldz, ldy, y_sig ? ldys : 4)) {
 #define OPH_LAUNCH(V) launch_cfg(grid, 256, 0, st)(ln_act_fwd_vec_kernel<V>, z, ldz, gamma, beta, y, ldy, y_sig, ldys, yo->hi, yo->lo, yo->ldp, stats, (int)rows, act, norm, drop_p, seed, step)
@@ -453,7 +460,8 @@ int launch_ln_act_bwd(const float* dy, long long lddy, const float* z, long long
                       const long long* step, OperandMap* dzmap, cudaStream_t st) {
     const size_t smem = 3 * (size_t)C * sizeof(float);
     dzmap->ptr = dz; dzmap->ld = lddz; dzmap->hi = dzmap->lo = nullptr;
-    ProfScope ps(OPH_TAG_ROW_BWD, (double)rows * C * 12.0, st);
+    char pdesc[64] = ""; if (g_prof_on) snprintf(pdesc, sizeof(pdesc), "ln_bwd rows=%lld C=%d", (long long)rows, C);
+    ProfScope ps(OPH_TAG_ROW_BWD, (double)rows * C * 12.0, st, pdesc);
     if (norm && vec_ok(C, lddy, ldz, lddz) && lddz >= C && !(g_gemm_dbg_flags_host & 32768)) {
         dz_as_planes(dz, rows, C, dzmap);
         unsigned short* h = const_cast<unsigned short*>(dzmap->hi); unsigned short* l = const_cast<unsigned short*>(dzmap->lo);
@@ -608,14 +616,20 @@ int oph_profile_end(double* out) {
     std::lock_guard<std::mutex> lk(g_prof_mu);
     g_prof_on = false;
     for (int i = 0; i < OPH_NUM_TAGS * 3; ++i) out[i] = 0.0;
+    // OPH_PROF_DUMP=<path>: one line per launch (tag, ms, algorithmic work, shape) for tools/launch_table.py
+    const char* dump = getenv("OPH_PROF_DUMP");
+    FILE* df = dump && *dump ? fopen(dump, "a") : nullptr;
+    if (df) fprintf(df, "# begin %zu launches\n", g_prof.size());
     for (auto& r : g_prof) {
         if (cudaEventSynchronize(r.e1) != cudaSuccess) return check_launch("profile_end");
         float ms = 0.f;
         cudaEventElapsedTime(&ms, r.e0, r.e1);
         const int t = (r.tag >= 0 && r.tag < OPH_NUM_TAGS) ? r.tag : 0;
         out[t * 3] += 1.0; out[t * 3 + 1] += ms; out[t * 3 + 2] += r.flops;
+        if (df) fprintf(df, "%d %.3f %.6g %s\n", r.tag, ms * 1e3, r.flops, r.desc);
         cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
     }
+    if (df) fclose(df);
     g_prof.clear();
     return OPH_OK;
 }
@@ -819,7 +833,8 @@ int oph_hc_fwd(const oph_act* x, const void* packed_w, const float* bias, const 
     x = &xr; y = &yr;
     const unsigned long long row_base = (unsigned long long)done_rows;
     const int grid = rows_grid(rows, 8);
-    ProfScope ps(OPH_TAG_HC_ROW_FWD, (double)rows * C * (y->hi ? 20.0 : 16.0), S(stream));
+    char pdesc[64] = ""; if (g_prof_on) snprintf(pdesc, sizeof(pdesc), "hc_tail_fwd rows=%lld C=%d", (long long)rows, C);
+    ProfScope ps(OPH_TAG_HC_ROW_FWD, (double)rows * C * (y->hi ? 20.0 : 16.0), S(stream), pdesc);
     if (vec && norm && !(g_gemm_dbg_flags_host & 4096)) {
         const int wpr = C / 256, groups = 8 / wpr;
         const int depth = ((g_gemm_dbg_flags_host & 8192) || C > 256) ? 3 : 2;         // ring slots per warp
@@ -863,7 +878,8 @@ int oph_hc_bwd(const float* dy, long long lddy, const oph_act* x, const float* z
     const LccGate lcc = take_lcc(L);
     if (lcc.table && !lcc.scratch) return fail(OPH_EINVAL, "hc_bwd: the channel gates need a [B*L][C] scratch (oph_lcc_context)%s");
     {
-    ProfScope ps(OPH_TAG_ROW_BWD, (double)rows * C * 28.0, S(stream));
+    char pdesc[64] = ""; if (g_prof_on) snprintf(pdesc, sizeof(pdesc), "hc_tail_bwd rows=%lld C=%d", (long long)rows, C);
+    ProfScope ps(OPH_TAG_ROW_BWD, (double)rows * C * 28.0, S(stream), pdesc);
     if (!lcc.table && norm && vec_ok(C, lddy, ldz, x->ld, lddz, lddx) && lddz >= 2 * C) {
         dz_as_planes(dz, rows, 2 * C, &dzm);
         unsigned short* h = const_cast<unsigned short*>(dzm.hi); unsigned short* l = const_cast<unsigned short*>(dzm.lo);
