@@ -60,9 +60,13 @@ unsigned int oph_crc32c(const void* data, unsigned long long n, unsigned int crc
 #define OPH_TAG_AR_ENC 9      /* oph_ar_encoder_step: third value = fp32 weight BYTES streamed per launch */
 #define OPH_NUM_TAGS 10
 long long oph_launch_count(void);
-/* diagnostics: device buffer long long[74][8]; every GEMM launch overwrites per CTA pair
+/* diagnostics: device buffer long long[74][16]; every GEMM launch overwrites per CTA pair
  * (total cycles, cycles waiting for an accumulator stage, for A, for B, k-blocks). NULL disables. */
 int oph_gemm_debug_buffer(long long* dev_buf);
+/* diagnostics: a ring of `slots` such buffers; every GEMM launch (also inside a stream capture) takes the next slot, so one
+ * replay of a captured step leaves the in-kernel time stamps of all its GEMM launches; _desc = shape of the launch in a slot */
+int oph_gemm_debug_ring(long long* dev_buf, int slots);
+int oph_gemm_debug_ring_desc(int slot, char* out, int cap);
 /* diagnostics (results become garbage): 1 = operand producers skip loads/stores, 2 = weight loader skips copies,
  * 4 = CTA pairs do not rotate their k-block order, 8 = do not feed pre-split operands with TMA tensor copies (producer warps copy them instead),
  * 16 = no remainder K-split of RED outputs, 32 = skip the item-boundary fix-up of flat A tiles,
@@ -82,6 +86,8 @@ int oph_gemm_debug_flags(int flags);
  * overlap the input-gradient chain on `stream`.  The caller joins `side` back (event / stream wait) before it reads
  * the gradients and keeps x and dz alive until then.  enable == 0 restores in-order execution. */
 int oph_wgrad_stream(oph_stream_t side, int enable);
+/* diagnostics: cudaDeviceSetCacheConfig (0 = none, 1 = prefer shared, 2 = prefer L1, 3 = equal) for the calling thread's device */
+int oph_cache_config(int mode);
 int oph_profile_begin(void);
 int oph_profile_end(double* out);
 

@@ -41,8 +41,11 @@ SIGNATURES = {
     "oph_crc32c": (ctypes.c_uint, [P, ctypes.c_ulonglong, ctypes.c_uint]),
     "oph_launch_count": (LL, []),
     "oph_gemm_debug_buffer": (I, [P]),
+    "oph_gemm_debug_ring": (I, [P, I]),
+    "oph_gemm_debug_ring_desc": (I, [I, P, I]),
     "oph_gemm_debug_flags": (I, [I]),
     "oph_wgrad_stream": (I, [P, I]),
+    "oph_cache_config": (I, [I]),
     "oph_profile_begin": (I, []),
     "oph_profile_end": (I, [P]),
     "oph_conv_pack_bytes": (SZ, [I, I, I, I, I]),

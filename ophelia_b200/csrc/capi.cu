@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <string>
 #include <vector>
 
 using namespace oph;
@@ -24,7 +25,9 @@ int g_gemm_dbg_flags = 0;
 int g_gemm_dbg_flags_host = 0;     // all bits as passed to oph_gemm_debug_flags (host-side switches)
 bool g_hcb_two = true;
 int g_hcb_depth = 0;               // ring depth of the highway-backward row kernel (tunable through oph_gemm_debug_flags bits 8..10)
-long long* g_gemm_dbg = nullptr;   // optional device buffer [74][8] for in-kernel wait-cycle counters
+long long* g_gemm_dbg = nullptr;   // optional device buffer [74][16] for in-kernel wait-cycle counters
+int g_dbg_slots = 0, g_dbg_next = 0;   // > 0: g_gemm_dbg is a ring of [slots][74][16]; every launch takes the next slot
+std::vector<std::string> g_dbg_desc;   // shape of the launch that owns each slot
 
 // Optional per-launch timing of the GEMM core (bench.py roofline): CUDA events around every launch, by tag.
 struct ProfRec { cudaEvent_t e0, e1; int tag; double flops; char desc[112]; };
@@ -233,6 +236,8 @@ int launch_gemm(GemmArgs& a, int zdim, cudaStream_t st) {
             return fail(OPH_ECUDA, "gemm: cannot encode the tensor map of the packed weight image%s");
     }
     a.dbg = g_gemm_dbg;
+    int dbg_slot = -1;
+    if (g_gemm_dbg && g_dbg_slots > 0) { dbg_slot = g_dbg_next++ % g_dbg_slots; a.dbg = g_gemm_dbg + (size_t)dbg_slot * GEMM_MAX_PAIRS * 16; }
     a.dbg_flags = g_gemm_dbg_flags;
     // persistent CTA pairs: work units = (pair of 128-row tiles) x (256-column block) x tap x z slice
     // conv tail in the epilogue: whole rows in one work unit (N <= 256), both operands from the copy engines
@@ -277,11 +282,18 @@ int launch_gemm(GemmArgs& a, int zdim, cudaStream_t st) {
         pairs = mp < GEMM_MAX_PAIRS ? mp : GEMM_MAX_PAIRS;
     }
     dim3 grid(2 * pairs);
+    {   // the launch constants the kernel divides by (same formulas as in the kernel)
+        const int KBc = cdiv(a.Kc, GEMM_BK);
+        a.fd_MP = make_fastdiv(cdiv(cdiv(a.M, GEMM_BM), 2)); a.fd_nb = make_fastdiv(cdiv(a.N, GEMM_BN)); a.fd_yt = make_fastdiv(a.ytaps);
+        a.fd_ss = make_fastdiv(a.split_s); a.fd_L = make_fastdiv(a.A.L); a.fd_KBc = make_fastdiv(KBc);
+        a.fd_KB = make_fastdiv((a.a_mode == A_KMAJOR ? a.ntaps : 1) * KBc); a.fd_KBI = make_fastdiv(cdiv(a.A.L, GEMM_BK));
+    }
     {
         char desc[112] = "";
-        if (g_prof_on)
+        if (g_prof_on || dbg_slot >= 0)
             snprintf(desc, sizeof(desc), "M=%d N=%d K=%d taps=%d ytaps=%d z=%d units=%lld items=%lld pairs=%d split=%d atma=%d btma=%d rtma=%d hc=%d", a.M, a.N,
                      a.prof_k ? a.prof_k : a.Kc, a.ntaps, a.ytaps, a.zdim, units, items, pairs, a.split_s, a.a_tma, a.b_tma, a.r_tma, a.hc_fused);
+        if (dbg_slot >= 0) { if ((int)g_dbg_desc.size() <= dbg_slot) g_dbg_desc.resize(dbg_slot + 1); g_dbg_desc[dbg_slot] = std::string("tag=") + std::to_string(a.tag) + " " + desc; }
         ProfScope ps(a.tag, 2.0 * a.M * a.N * (a.prof_k ? a.prof_k : a.Kc) * (a.a_mode == A_KMAJOR ? a.ntaps : a.ytaps) * (a.z_mode == Z_BATCH ? a.zdim : 1), st, desc);
         if (a.hc_fused) launch_cfg(grid, GEMM_THREADS, GEMM_SMEM, st)(gemm_bf16x3_kernel<true>, a);
         else launch_cfg(grid, GEMM_THREADS, GEMM_SMEM, st)(gemm_bf16x3_kernel<false>, a);
@@ -350,44 +362,65 @@ int pack_image(const float* w, int ntaps, const int* tap_idx, long long s_tap, l
 // ---- batched packing: ONE launch re-packs every conv kernel of a model after the optimiser step
 struct PackJob { PackArgs a; long long total; long long first_block; };
 
-__global__ void pack_batch_kernel(const PackJob* __restrict__ jobs, int njobs) {
+__global__ void __launch_bounds__(256) pack_batch_kernel(const PackJob* __restrict__ jobs, int njobs) {
     pdl_grid_sync();
-    int lo = 0, hi = njobs - 1;                         // last job whose first block is <= blockIdx.x
-    while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (jobs[mid].first_block <= (long long)blockIdx.x) lo = mid; else hi = mid - 1;
+    // one block = one stage (256 image rows x 64 channels = 2048 (row, 8-channel chunk) items, 8 per thread): the job
+    // lookup and the stage decode are paid once per block
+    __shared__ uint4 s_t[2][2][32][8];                  // [buffer][hi / lo][row][chunk]
+    int jl = 0, jh = njobs - 1;                         // last job whose first block is <= blockIdx.x
+    while (jl < jh) {
+        const int mid = (jl + jh + 1) >> 1;
+        if (jobs[mid].first_block <= (long long)blockIdx.x) jl = mid; else jh = mid - 1;
     }
-    const PackJob& j = jobs[lo];
+    const PackJob& j = jobs[jl];
     const PackArgs p = j.a;
-    const long long idx = ((long long)blockIdx.x - j.first_block) * blockDim.x + threadIdx.x;
-    if (idx >= j.total) return;
+    const int stage = (int)((long long)blockIdx.x - j.first_block);
+    if ((long long)stage * 2048 >= j.total) return;
     const int KBc = (p.Cvalid + GEMM_BK - 1) / GEMM_BK, KB = p.ntaps * KBc;
-    // thread -> (row nl of the 256-row stage, 8-channel chunk): the index that is contiguous in the SOURCE runs fastest,
-    // so that a warp reads whole 128-byte lines (s_c == 1: channels are contiguous; else rows are)
-    const bool chunk_fast = p.s_c == 1;
-    const int nl = chunk_fast ? (int)((idx >> 3) & 255) : (int)(idx & 255);
-    const int chunk = chunk_fast ? (int)(idx & 7) : (int)((idx >> 8) & 7);
-    const long long rest = idx >> 11;
-    const int kb = (int)(rest % KB);
-    const int nb = (int)(rest / KB);
+    const int nb = stage / KB, kb = stage - nb * KB;
     const int tap = kb / KBc, cb = kb - tap * KBc;
-    const int n = nb * GEMM_BN + nl;
-    const int c0 = cb * GEMM_BK + chunk * 8;
-    float v[8];
-    const float* src = p.w + p.tap_idx[tap] * p.s_tap + (long long)c0 * p.s_c + (long long)n * p.s_n;
-    if (chunk_fast && n < p.Nvalid && c0 + 8 <= p.Cvalid && !((reinterpret_cast<uintptr_t>(src)) & 15)) {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-    } else {
+    const float* wsrc = p.w + p.tap_idx[tap] * p.s_tap;
+    uint8_t* stage_img = p.out + (size_t)stage * B_STAGE;
+    // s_c == 1 (channels contiguous in the source): 8 lanes read one row's 64 channels and write one whole 128-byte image
+    // row.  Otherwise rows are contiguous in the source: per pass the block takes 32 rows x 64 channels, lanes run along
+    // the rows for the loads (whole 128-byte lines per channel) and the (hi, lo) chunks are transposed through shared
+    // memory so that the stores cover whole image rows as well.
+    const bool chunk_fast = p.s_c == 1;
+    const int tid = threadIdx.x;
+#pragma unroll 2
+    for (int pass = 0; pass < 8; ++pass) {
+        const int nl = chunk_fast ? pass * 32 + (tid >> 3) : pass * 32 + (tid & 31);
+        const int chunk = chunk_fast ? (tid & 7) : (tid >> 5);
+        const int n = nb * GEMM_BN + nl;
+        const int c0 = cb * GEMM_BK + chunk * 8;
+        float v[8];
+        const float* src = wsrc + (long long)c0 * p.s_c + (long long)n * p.s_n;
+        if (chunk_fast && n < p.Nvalid && c0 + 8 <= p.Cvalid && !((reinterpret_cast<uintptr_t>(src)) & 15)) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        } else {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const int c = c0 + e;
-            v[e] = (n < p.Nvalid && c < p.Cvalid) ? __ldg(src + (long long)e * p.s_c) : 0.f;
+            for (int e = 0; e < 8; ++e) {
+                const int c = c0 + e;
+                v[e] = (n < p.Nvalid && c < p.Cvalid) ? __ldg(src + (long long)e * p.s_c) : 0.f;
+            }
+        }
+        uint8_t* img = stage_img + (size_t)(nl >> 7) * B_SLOT;      // [CTA 0: hi | lo][CTA 1: hi | lo], 128 rows each
+        if (chunk_fast) {
+            const int nr = nl & 127;
+            store_split(img, img + B_PLANE, nr * 128 + ((chunk ^ (nr & 7)) << 4), v);
+        } else {
+            uint4 vh, vl;
+            split8(v, vh, vl);
+            s_t[pass & 1][0][tid & 31][chunk] = vh; s_t[pass & 1][1][tid & 31][chunk] = vl;
+            __syncthreads();                            // (two buffers: the next pass may start writing the other one)
+            const int r2 = tid >> 3, ch2 = tid & 7;
+            const int nr = ((pass * 32) & 127) | r2;
+            const uint32_t off = nr * 128 + ((ch2 ^ (nr & 7)) << 4);
+            *reinterpret_cast<uint4*>(img + off) = s_t[pass & 1][0][r2][ch2];
+            *reinterpret_cast<uint4*>(img + B_PLANE + off) = s_t[pass & 1][1][r2][ch2];
         }
     }
-    uint8_t* img = p.out + ((size_t)nb * KB + kb) * B_STAGE + (size_t)(nl >> 7) * B_SLOT;
-    const int nr = nl & 127;
-    store_split(img, img + B_PLANE, nr * 128 + ((chunk ^ (nr & 7)) << 4), v);
 }
 
 void plan_job(PackJob* j, const float* w, int ntaps, const int* tap_idx, long long s_tap, long long s_c, long long s_n,
@@ -495,7 +528,7 @@ int launch_ln_act_bwd(const float* dy, long long lddy, const float* z, long long
         }
         if (!((lddy | ldz | lddz) & 3) && C <= 1280 && !(g_gemm_dbg_flags_host & 1048576)) {
             const int nv = (C + 3) / 4;
-            const size_t sm = (2 * (size_t)((C + 3) & ~3) + 32) * sizeof(float);
+            const size_t sm = (5 * (size_t)((C + 3) & ~3) + 32) * sizeof(float);      // gamma, beta, partial moments, 3 column sums
             const int wpr = nv > 160 ? 2 : 1;
             long long gl = (rows + (8 / wpr) * 8 - 1) / ((8 / wpr) * 8);                  // >= 8 rows per row group
             const int gridb = (int)(gl < 1 ? 1 : (gl > 148 * 3 ? 148 * 3 : gl));
@@ -589,7 +622,13 @@ unsigned int oph_crc32c(const void* data, unsigned long long n, unsigned int crc
 }
 const char* oph_last_error(void) { return g_err; }
 long long oph_launch_count(void) { return g_launches.load(); }
-int oph_gemm_debug_buffer(long long* dev_buf) { g_gemm_dbg = dev_buf; return OPH_OK; }
+int oph_gemm_debug_buffer(long long* dev_buf) { g_gemm_dbg = dev_buf; g_dbg_slots = 0; return OPH_OK; }
+int oph_gemm_debug_ring(long long* dev_buf, int slots) { g_gemm_dbg = dev_buf; g_dbg_slots = dev_buf ? slots : 0; g_dbg_next = 0; g_dbg_desc.clear(); return OPH_OK; }
+int oph_gemm_debug_ring_desc(int slot, char* out, int cap) {
+    if (slot < 0 || slot >= (int)g_dbg_desc.size() || cap < 1) return OPH_EINVAL;
+    snprintf(out, (size_t)cap, "%s", g_dbg_desc[slot].c_str());
+    return OPH_OK;
+}
 int oph_gemm_debug_flags(int flags) { g_gemm_dbg_flags_host = flags; g_gemm_dbg_flags = flags & 0xA7; g_use_tma = !(flags & 8); g_use_split = !(flags & 16); g_use_pdl = (flags & 64) != 0; g_use_ln_fuse = (flags & 65536) != 0; g_use_hc_fuse = !(flags & 131072); g_use_attn_fuse = !(flags & 524288);
     g_hcb_depth = (flags >> 8) & 7;                    // 0 = automatic
     g_hcb_two = !(flags & 2048);
@@ -600,6 +639,12 @@ int oph_gemm_debug_flags(int flags) { g_gemm_dbg_flags_host = flags; g_gemm_dbg_
 int oph_wgrad_stream(oph_stream_t side, int enable) {
     g_wgrad_stream = S(side);
     g_wgrad_fork = enable != 0;
+    return OPH_OK;
+}
+
+int oph_cache_config(int mode) {
+    const cudaFuncCache m = mode == 1 ? cudaFuncCachePreferShared : mode == 2 ? cudaFuncCachePreferL1 : mode == 3 ? cudaFuncCachePreferEqual : cudaFuncCachePreferNone;
+    if (cudaDeviceSetCacheConfig(m) != cudaSuccess) return check_launch("cudaDeviceSetCacheConfig");
     return OPH_OK;
 }
 
@@ -687,7 +732,7 @@ int oph_pack_plan_add(void* plan_host, int capacity, int* njobs, long long* nblo
     if (*njobs + n > capacity) return fail(OPH_EINVAL, "pack_plan_add: plan capacity exceeded%s");
     for (int i = 0; i < n; ++i) {
         tmp[i].first_block = *nblocks;
-        *nblocks += (tmp[i].total + 255) / 256;
+        *nblocks += tmp[i].total / 2048;                 // one block per stage
         plan[(*njobs)++] = tmp[i];
     }
     return OPH_OK;

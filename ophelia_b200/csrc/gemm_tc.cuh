@@ -21,6 +21,21 @@ enum { A_KMAJOR = 0, A_MNMAJOR = 1 };
 enum { B_PACKED = 0, B_KMAJOR = 1, B_MNMAJOR = 2 };
 enum { Z_NONE = 0, Z_BATCH = 1, Z_SPLITK = 2 };
 
+// Division by a launch constant as multiply-high + shift (valid for 0 <= n < 2^31): the unit decode of every role sits on
+// the start-up path of a launch, and the emulated integer division is ~100+ dependent cycles a piece.
+struct FastDiv { uint32_t mul, shr; };     // mul == 0: divisor 1
+inline FastDiv make_fastdiv(int d) {
+    FastDiv f{0u, 0u};
+    if (d <= 1) return f;
+    int lg = 0;
+    while ((1ll << lg) < d) ++lg;                      // ceil(log2 d)
+    const unsigned p = 31u + (unsigned)lg;
+    f.mul = (uint32_t)(((1ull << p) + (unsigned)d - 1ull) / (unsigned)d);
+    f.shr = p - 32u;
+    return f;
+}
+__device__ __forceinline__ int fdiv(int n, FastDiv f) { return f.mul ? (int)(__umulhi((uint32_t)n, f.mul) >> f.shr) : n; }
+
 struct OperandMap {        // logical row r -> (item b, step t) = divmod(r, L);  source step ts = t*mul + off[tap]
     const float* ptr;      // valid iff 0 <= ts < Ls;  source row = b*Ls + ts
     const unsigned short* hi;   // optional pre-split operand: bf16 planes hi / lo with the same [row][ld] indexing
@@ -96,6 +111,9 @@ struct GemmArgs {
     unsigned short* hc_yhi; unsigned short* hc_ylo; long long hc_ldp;
     float* hc_stats;       // [M][4] (mean1, rstd1, mean2, rstd2) or NULL
     float hc_drop; unsigned long long hc_seed; const long long* hc_step;
+    // launch constants as fast divisors: row-tile pairs, column blocks, grid taps, slices per remainder unit, steps per item
+    // (A.L), k-blocks per tap, k-blocks per unit, 64-step blocks per item
+    FastDiv fd_MP, fd_nb, fd_yt, fd_ss, fd_L, fd_KBc, fd_KB, fd_KBI;
     alignas(64) CUtensorMap tmA_hi;
     alignas(64) CUtensorMap tmA_lo;
     alignas(64) CUtensorMap tmB_hi;
@@ -203,9 +221,9 @@ struct Unit {               // one 256x256 output tile of one tap / z slice
 };
 
 // does the 128-row flat tile starting at row m0 contain rows whose tap-shifted step leaves their batch item?
-__device__ __forceinline__ bool needs_fix(int m0, int off, int L) {
+__device__ __forceinline__ bool needs_fix(int m0, int off, int L, FastDiv fdL) {
     if (off == 0) return false;
-    const int t0 = m0 % L;
+    const int t0 = m0 - fdiv(m0, fdL) * L;
     if (t0 + GEMM_BM > L) return true;                 // the tile crosses an item boundary
     return off < 0 ? t0 < -off : t0 + GEMM_BM > L - off;
 }
@@ -216,13 +234,15 @@ __device__ __forceinline__ Unit decode_unit(const GemmArgs& p, int v, int MP, in
     t.sliced = 0;
     if (p.split_s > 1 && v >= p.split_from) {
         t.sliced = 1;
-        const int w = v - p.split_from;
-        u = p.split_from + w / p.split_s; slice = w - (w / p.split_s) * p.split_s; nslices = p.split_s;
+        const int w = v - p.split_from, wq = fdiv(w, p.fd_ss);
+        u = p.split_from + wq; slice = w - wq * p.split_s; nslices = p.split_s;
     }
-    const int mp = u % MP; int rest = u / MP;
-    t.nb = rest % nblocks; rest /= nblocks;
-    t.ytap = rest % p.ytaps;
-    const int z = rest / p.ytaps;
+    int rest = fdiv(u, p.fd_MP);
+    const int mp = u - rest * MP;
+    const int r1 = fdiv(rest, p.fd_nb);
+    t.nb = rest - r1 * nblocks;
+    const int z = fdiv(r1, p.fd_yt);
+    t.ytap = r1 - z * p.ytaps;
     t.z = z;
     const int mt = mp * 2 + (int)crank;
     t.m0 = mt * GEMM_BM;                               // may lie beyond M for the padding CTA of the last pair
@@ -237,8 +257,8 @@ __device__ __forceinline__ Unit decode_unit(const GemmArgs& p, int v, int MP, in
         t.KBc = (t.k_end - t.k_begin + GEMM_BK - 1) / GEMM_BK;
         t.KB = ((p.a_mode == A_KMAJOR) ? p.ntaps : 1) * t.KBc;
     }
-    t.kb0 = (int)((long long)slice * t.KB / nslices);
-    t.kb1 = (int)((long long)(slice + 1) * t.KB / nslices);
+    if (nslices == 1) { t.kb0 = 0; t.kb1 = t.KB; }
+    else { t.kb0 = fdiv(slice * t.KB, p.fd_ss); t.kb1 = fdiv((slice + 1) * t.KB, p.fd_ss); }
     return t;
 }
 
@@ -250,7 +270,7 @@ __device__ __forceinline__ int item_unit(const GemmArgs& p, int it, int pair, in
     if (!HC || !p.hc_fused) { const int u = pair + it * npairs; return u < total ? u : -1; }
     const int F = p.hc_fused;
     const int nsup = F > pair ? (F - pair + npairs - 1) / npairs : 0;
-    if (it < nsup * nblocks) return (it % nblocks) * MP + pair + (it / nblocks) * npairs;
+    if (it < nsup * nblocks) { const int q = fdiv(it, p.fd_nb); return (it - q * nblocks) * MP + pair + q * npairs; }
     const int r = pair + (it - nsup * nblocks) * npairs, W = MP - F;
     if (W <= 0 || r >= W * nblocks) return -1;
     return (r / W) * MP + F + r % W;
@@ -260,7 +280,7 @@ template <bool HC>
 __device__ __forceinline__ bool item_closes_tile(const GemmArgs& p, int it, int pair, int npairs, int nblocks) {
     if (!HC || !p.hc_fused) return false;
     const int nsup = p.hc_fused > pair ? (p.hc_fused - pair + npairs - 1) / npairs : 0;
-    return it < nsup * nblocks && (it % nblocks) == nblocks - 1;
+    return it < nsup * nblocks && (it - fdiv(it, p.fd_nb) * nblocks) == nblocks - 1;
 }
 
 __device__ __forceinline__ float4 ld_cg4(const float* p) {
@@ -394,6 +414,11 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
     const bool rotate = p.a_tma == 1 && packed && !(p.dbg_flags & 4);
     const bool nofix = (p.dbg_flags & (32 | 128)) != 0;        // diagnostics: skip the item-boundary fix-up (wrong results)
 
+    if (warp == NPW + 5 && lane == 0) {                // the copy-engine loader's descriptors: fetched while the prologue runs
+        if (p.a_tma || p.r_tma) { tma_prefetch_desc(&p.tmA_hi); tma_prefetch_desc(&p.tmA_lo); }
+        if (p.r_tma || packed || p.b_tma) tma_prefetch_desc(&p.tmB_hi);
+        if (p.r_tma || p.b_tma) tma_prefetch_desc(&p.tmB_lo);
+    }
     if (tid == 0) {
         for (int i = 0; i < NA_SLOTS; ++i) {
             // copies: the leader's expect_tx arrive (+ for conv-style tiles one token per CTA: sent by its loader when
@@ -418,6 +443,10 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
     // the prologue above overlapped the predecessor kernel's tail; its results are visible from here on
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (p.dbg && crank == 0 && tid == 0) {
+        unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        p.dbg[pair * 16 + 9] = (long long)(gt - gt_start);      // ns from kernel entry to the end of the prologue
+    }
 
 
     // ================================================================ epilogue worker: TMEM -> global
@@ -437,6 +466,10 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
             if (t.KB <= 0) continue;
             mbar_wait(BAR(BAR_T_FULL + acc), acc_par);
             tc_fence_after();
+            if (p.dbg && it_ == 0 && crank == 0 && q == 0 && cg == 0 && lane == 0) {
+                unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+                p.dbg[pair * 16 + 11] = (long long)(gt - gt_start);     // ns until the first accumulator stage was complete
+            }
             float* Cb = p.C + t.c_z + (long long)t.ytap * p.c_tap_stride;
             const float* addb = p.addend ? p.addend + t.c_z + (long long)t.ytap * p.c_tap_stride : nullptr;
             const int grow0 = t.m0 + q * 32;
@@ -512,6 +545,10 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
                 else if (p.hc_C == 512) hc_tail_rows<2>(p, sStage, wq, lane, t.m0, t.rows, z0);
                 else hc_tail_rows<4>(p, sStage, wq, lane, t.m0, t.rows, z0);
             }
+        }
+        if (p.dbg && crank == 0 && q == 0 && cg == 0 && lane == 0) {
+            unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+            p.dbg[pair * 16 + 12] = (long long)(gt - gt_start);         // ns until this warp had drained its last unit
         }
     };
 
@@ -818,9 +855,17 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
                     c0 = clock64();
                     mbar_wait(BAR(BAR_FULL_A + as), a_par);
                     const long long c1 = clock64();
+                    if (p.dbg && nkb == 0) {
+                        unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+                        p.dbg[pair * 16 + 15] = (long long)(gt - gt_start);     // ns until the first A tile had landed
+                    }
                     mbar_wait(BAR(BAR_FULL_B + bs), b_par);
                     w_a += c1 - c0; w_b += clock64() - c1; ++nkb;
                     tc_fence_after();
+                    if (p.dbg && nkb == 1) {
+                        unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+                        p.dbg[pair * 16 + 10] = (long long)(gt - gt_start);     // ns until the first operands had landed
+                    }
                     const uint32_t a_hi = sA_addr + as * A_SLOT, a_lo = a_hi + A_PLANE;
                     const uint32_t b_hi = sB_addr + bs * B_SLOT, b_lo = b_hi + B_PLANE;
 #pragma unroll
@@ -842,7 +887,7 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
                 if (++acc == N_ACC) { acc = 0; acc_par ^= 1; }
             }
             if (p.dbg) {
-                long long* o = p.dbg + pair * 8;
+                long long* o = p.dbg + pair * 16;
                 unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
                 o[0] = clock64() - t_begin; o[1] = w_t; o[2] = w_a; o[3] = w_b; o[4] = nkb;
                 o[5] = (long long)(gt - gt_start);      // ns from kernel entry to the end of the MMA issue loop
@@ -855,9 +900,6 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
         // barrier directly; the leader's loader announces the bytes of both (arrive.expect_tx).
         if (lane == 0 && (packed || p.a_tma || p.r_tma)) {
             int slot = 0, par = 1, as = 0, a_par = 1;
-            if (p.a_tma || p.r_tma) { tma_prefetch_desc(&p.tmA_hi); tma_prefetch_desc(&p.tmA_lo); }
-            if (p.r_tma || packed || p.b_tma) tma_prefetch_desc(&p.tmB_hi);
-            if (p.r_tma || p.b_tma) tma_prefetch_desc(&p.tmB_lo);
             const uint32_t fullA0 = mapa_u32(BAR(BAR_FULL_A), 0), fullB0 = mapa_u32(BAR(BAR_FULL_B), 0);   // leader's barriers
             const int KBI = (p.A.L + GEMM_BK - 1) / GEMM_BK;       // 64-step blocks per batch item (r_tma, split-K)
             for (int it_ = 0;; ++it_) {
@@ -868,12 +910,16 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
                 const int brow0 = (t.nb * t.KB * 2 + (int)crank) * 256;
                 // CTA pairs walk the k-blocks of a unit from different starting points (rot): at any moment they ask the
                 // L2 for different weight stages instead of all hammering the same 64 KiB
-                const int nkb = t.kb1 - t.kb0, rot = rotate ? pair % nkb : 0;
+                const int nkb = t.kb1 - t.kb0, rot = !rotate ? 0 : (nkb == t.KB ? pair - fdiv(pair, p.fd_KB) * nkb : pair % nkb);
                 for (int j = 0; j < nkb; ++j) {
                     int kb = t.kb0 + j + rot; if (kb >= t.kb1) kb -= nkb;
                     // steps [tb, tb + 64) of batch item `item`: the k-block of an MN-major (row-reduction) operand
                     int item = t.z, tb = kb * GEMM_BK;
-                    if (p.z_mode != Z_BATCH) { const int g = t.k_begin + kb; item = g / KBI; tb = (g - item * KBI) * GEMM_BK; }
+                    if (p.dbg && crank == 0 && it_ == 0 && j == 0) {
+                        unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+                        p.dbg[pair * 16 + 14] = (long long)(gt - gt_start);     // ns until the loader issues its first copy
+                    }
+                    if (p.z_mode != Z_BATCH) { const int g = t.k_begin + kb; item = fdiv(g, p.fd_KBI); tb = (g - item * KBI) * GEMM_BK; }
                     // ------------------------------------------------ A
                     if (p.r_tma) {         // x^T tile = 64 steps x 128 channels [m0, m0+128) as two 64-channel boxes per plane
                         mbar_wait(BAR(BAR_EMPTY_A + as), a_par);
@@ -887,7 +933,7 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
                         tma_load_3d_cg2(dst + A_PLANE + 8192, &p.tmA_lo, t.m0 + 64, ta, item, bar);
                         if (++as == NA_SLOTS) { as = 0; a_par ^= 1; }
                     } else if (p.a_tma) {  // K-major tile: two boxes (hi / lo plane) of 64 channels x 128 rows
-                        const int tap = kb / t.KBc, cb = kb - tap * t.KBc;
+                        const int tap = fdiv(kb, p.fd_KBc), cb = kb - tap * t.KBc;
                         mbar_wait(BAR(BAR_EMPTY_A + as), a_par);
                         const uint32_t dst = smem_u32(sA + as * A_SLOT);
                         const int off = p.A.off[tap];
@@ -895,9 +941,9 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
                             if (crank == 0) { mbar_arrive(BAR(BAR_FULL_A + as)); mbar_arrive(BAR(BAR_FULL_A + as)); mbar_arrive(BAR(BAR_FULL_A + as)); }
                         } else {
                             const bool flat = p.a_tma == 1;
-                            const bool fix_me = flat && !nofix && needs_fix(t.m0, off, p.A.L);
+                            const bool fix_me = flat && !nofix && needs_fix(t.m0, off, p.A.L, p.fd_L);
                             if (crank == 0) {                  // bytes that will be signalled straight on FULL_A
-                                const bool fix_peer = flat && !nofix && needs_fix(t.m0 + GEMM_BM, off, p.A.L);
+                                const bool fix_peer = flat && !nofix && needs_fix(t.m0 + GEMM_BM, off, p.A.L, p.fd_L);
                                 mbar_arrive_expect_tx(BAR(BAR_FULL_A + as), (fix_me ? 0 : A_SLOT) + (fix_peer ? 0 : A_SLOT));
                             }
                             const int c0 = t.k_begin + cb * GEMM_BK;
@@ -967,12 +1013,12 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
                 const Unit t = decode_unit(p, u, MP, nblocks, crank);
                 int tmod[4];                                   // step within the item of this lane's 4 rows
 #pragma unroll
-                for (int j = 0; j < 4; ++j) tmod[j] = (t.m0 + lane + 32 * j) % p.A.L;
-                const int nkb = t.kb1 - t.kb0, rot = rotate ? pair % nkb : 0;
+                for (int j = 0; j < 4; ++j) { const int r = t.m0 + lane + 32 * j; tmod[j] = r - fdiv(r, p.fd_L) * p.A.L; }
+                const int nkb = t.kb1 - t.kb0, rot = !rotate ? 0 : (nkb == t.KB ? pair - fdiv(pair, p.fd_KB) * nkb : pair % nkb);
                 for (int j = 0; j < nkb; ++j) {
                     int kb = t.kb0 + j + rot; if (kb >= t.kb1) kb -= nkb;
-                    const int off = p.A.off[kb / t.KBc];
-                    if (!nofix && needs_fix(t.m0, off, p.A.L)) {
+                    const int off = p.A.off[fdiv(kb, p.fd_KBc)];
+                    if (!nofix && needs_fix(t.m0, off, p.A.L, p.fd_L)) {
                         mbar_wait(BAR(BAR_LAND_A + as), (land_par >> as) & 1u);
                         land_par ^= 1u << as;
 #pragma unroll
@@ -1000,12 +1046,14 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
     tc_fence_before();
     if (p.dbg && crank == 0 && tid == 256) {           // an epilogue-free producer thread: time until its role loop ended
         unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-        p.dbg[pair * 8 + 6] = (long long)(gt - gt_start);
+        p.dbg[pair * 16 + 6] = (long long)(gt - gt_start);
     }
     cluster_sync_all();                                // the partner's smem/barriers stay alive until both are done
     if (p.dbg && crank == 0 && tid == 0) {
         unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-        p.dbg[pair * 8 + 7] = (long long)(gt - gt_start);      // ns from kernel entry to after the final cluster barrier
+        p.dbg[pair * 16 + 7] = (long long)(gt - gt_start);     // ns from kernel entry to after the final cluster barrier
+        p.dbg[pair * 16 + 8] = (long long)gt_start;            // absolute entry / exit times: launch skew between the pairs
+        p.dbg[pair * 16 + 13] = (long long)gt;
     }
     if (warp == NPW + 4) tmem_dealloc2<N_ACC * GEMM_BN>(tmem_base);
 }

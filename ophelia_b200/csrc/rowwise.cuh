@@ -1505,18 +1505,27 @@ __global__ void __launch_bounds__(256, 2) ln_act_bwd_any_kernel(
             }
         }
     }
-    // flush: one global atomic per lane and channel (few, long-lived blocks)
-    float* const dst[3] = {norm ? dgamma : nullptr, norm ? dbeta : nullptr, dbias};
+    // flush: per-block sums in shared memory first, then one global atomic per channel and block (a global atomic per
+    // lane made the 80-channel output layer's backward 87 us long: 835 k atomics on 240 addresses)
+    float* sacc = smem_f + 2 * Cp + 32;                 // [3][Cp]
+    for (int i = threadIdx.x; i < 3 * Cp; i += 256) sacc[i] = 0.f;
+    __syncthreads();
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        if (!dst[k]) continue;
+        if (k < 2 && !norm) continue;
 #pragma unroll
         for (int i = 0; i < MAXV; ++i) {
             const int j = (i * WPR + part) * 32 + lane;
             if (j >= nv) continue;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) if (j * 4 + e < C) atomicAdd(dst[k] + j * 4 + e, acc[k][i * 4 + e]);
+            for (int e = 0; e < 4; ++e) atomicAdd(&sacc[k * Cp + j * 4 + e], acc[k][i * 4 + e]);
         }
+    }
+    __syncthreads();
+    float* const dst[3] = {norm ? dgamma : nullptr, norm ? dbeta : nullptr, dbias};
+    for (int idx = threadIdx.x; idx < 3 * Cp; idx += 256) {
+        const int k = idx / Cp, c = idx - k * Cp;
+        if (dst[k] && c < C) atomicAdd(dst[k] + c, sacc[idx]);
     }
 }
 
