@@ -60,7 +60,7 @@ unsigned int oph_crc32c(const void* data, unsigned long long n, unsigned int crc
 #define OPH_TAG_AR_ENC 9      /* oph_ar_encoder_step: third value = fp32 weight BYTES streamed per launch */
 #define OPH_NUM_TAGS 10
 long long oph_launch_count(void);
-/* diagnostics: device buffer long long[74][16]; every GEMM launch overwrites per CTA pair
+/* diagnostics: device buffer long long[74][24]; every GEMM launch overwrites per CTA pair
  * (total cycles, cycles waiting for an accumulator stage, for A, for B, k-blocks). NULL disables. */
 int oph_gemm_debug_buffer(long long* dev_buf);
 /* diagnostics: a ring of `slots` such buffers; every GEMM launch (also inside a stream capture) takes the next slot, so one

@@ -25,8 +25,8 @@ int g_gemm_dbg_flags = 0;
 int g_gemm_dbg_flags_host = 0;     // all bits as passed to oph_gemm_debug_flags (host-side switches)
 bool g_hcb_two = true;
 int g_hcb_depth = 0;               // ring depth of the highway-backward row kernel (tunable through oph_gemm_debug_flags bits 8..10)
-long long* g_gemm_dbg = nullptr;   // optional device buffer [74][16] for in-kernel wait-cycle counters
-int g_dbg_slots = 0, g_dbg_next = 0;   // > 0: g_gemm_dbg is a ring of [slots][74][16]; every launch takes the next slot
+long long* g_gemm_dbg = nullptr;   // optional device buffer [74][24] for in-kernel wait-cycle counters
+int g_dbg_slots = 0, g_dbg_next = 0;   // > 0: g_gemm_dbg is a ring of [slots][74][24]; every launch takes the next slot
 std::vector<std::string> g_dbg_desc;   // shape of the launch that owns each slot
 
 // Optional per-launch timing of the GEMM core (bench.py roofline): CUDA events around every launch, by tag.
@@ -237,7 +237,7 @@ int launch_gemm(GemmArgs& a, int zdim, cudaStream_t st) {
     }
     a.dbg = g_gemm_dbg;
     int dbg_slot = -1;
-    if (g_gemm_dbg && g_dbg_slots > 0) { dbg_slot = g_dbg_next++ % g_dbg_slots; a.dbg = g_gemm_dbg + (size_t)dbg_slot * GEMM_MAX_PAIRS * 16; }
+    if (g_gemm_dbg && g_dbg_slots > 0) { dbg_slot = g_dbg_next++ % g_dbg_slots; a.dbg = g_gemm_dbg + (size_t)dbg_slot * GEMM_MAX_PAIRS * DBG_STRIDE; }
     a.dbg_flags = g_gemm_dbg_flags;
     // persistent CTA pairs: work units = (pair of 128-row tiles) x (256-column block) x tap x z slice
     // conv tail in the epilogue: whole rows in one work unit (N <= 256), both operands from the copy engines

@@ -137,7 +137,8 @@ constexpr int GEMM_THREADS = (NPW + 8) * 32;        // 16 producer (or epilogue)
 constexpr int EPI_WARPS = 16;                       // epilogue workers when both operands come from the copy engines
 constexpr int EPI_STAGE_BYTES = EPI_WARPS * 2048;   // per-warp [32 rows][16 columns] fp32 transposition buffers
 constexpr int GEMM_SMEM = NA_SLOTS * A_SLOT + NB_SLOTS * B_SLOT + EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-constexpr int GEMM_MAX_PAIRS = 74;                  // 148 SMs
+constexpr int GEMM_MAX_PAIRS = 74;
+constexpr int DBG_STRIDE = 24;                       // long long slots per CTA pair in the diagnostics buffer                  // 148 SMs
 
 __device__ __forceinline__ void load8(const float* src, bool row_ok, int first, int limit, float (&v)[8]) {
     if (row_ok && first + 8 <= limit) {
@@ -434,8 +435,12 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
         for (int i = 0; i < N_ACC; ++i) { mbar_init(BAR(BAR_T_FULL + i), 1); mbar_init(BAR(BAR_T_EMPTY + i), copy_fed ? 2 * EPI_WARPS : 8); }
         mbar_fence_init();
         fence_proxy_async();
+        if (p.dbg && crank == 0) { unsigned long long gt_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_)); p.dbg[pair * DBG_STRIDE + 17] = (long long)(gt_ - gt_start); }
     }
-    if (warp == NPW + 4) tmem_alloc2<N_ACC * GEMM_BN>(smem_u32(tmem_slot));
+    if (warp == NPW + 4) {
+        tmem_alloc2<N_ACC * GEMM_BN>(smem_u32(tmem_slot));
+        if (p.dbg && crank == 0 && lane == 0) { unsigned long long gt_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_)); p.dbg[pair * DBG_STRIDE + 16] = (long long)(gt_ - gt_start); }
+    }
     tc_fence_before();
     cluster_sync_all();
     tc_fence_after();
@@ -445,7 +450,7 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (p.dbg && crank == 0 && tid == 0) {
         unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-        p.dbg[pair * 16 + 9] = (long long)(gt - gt_start);      // ns from kernel entry to the end of the prologue
+        p.dbg[pair * DBG_STRIDE + 9] = (long long)(gt - gt_start);      // ns from kernel entry to the end of the prologue
     }
 
 
@@ -468,7 +473,7 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
             tc_fence_after();
             if (p.dbg && it_ == 0 && crank == 0 && q == 0 && cg == 0 && lane == 0) {
                 unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-                p.dbg[pair * 16 + 11] = (long long)(gt - gt_start);     // ns until the first accumulator stage was complete
+                p.dbg[pair * DBG_STRIDE + 11] = (long long)(gt - gt_start);     // ns until the first accumulator stage was complete
             }
             float* Cb = p.C + t.c_z + (long long)t.ytap * p.c_tap_stride;
             const float* addb = p.addend ? p.addend + t.c_z + (long long)t.ytap * p.c_tap_stride : nullptr;
@@ -548,7 +553,7 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
         }
         if (p.dbg && crank == 0 && q == 0 && cg == 0 && lane == 0) {
             unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-            p.dbg[pair * 16 + 12] = (long long)(gt - gt_start);         // ns until this warp had drained its last unit
+            p.dbg[pair * DBG_STRIDE + 12] = (long long)(gt - gt_start);         // ns until this warp had drained its last unit
         }
     };
 
@@ -682,7 +687,226 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
     // Register budget per role (768 threads launch at 80 regs): producer warpgroups grow to 88, the epilogue
     // warpgroup shrinks to 72 and the MMA / copy warpgroup to 40 (512*88 + 128*72 + 128*40 <= 768*80: setmaxnreg can
     // only hand out what the CTA got at launch).
-    if (warp < NPW) {
+    // (the MMA / copy / fix-up roles come first in the code: they sit on the start-up path of every launch, and straight-line
+    //  code after the prologue is what the instruction fetch already has in flight)
+    if (warp >= NPW + 4) {
+      if (p.dbg && crank == 0 && warp == NPW + 5 && lane == 0) { unsigned long long gt_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_)); p.dbg[pair * DBG_STRIDE + 18] = (long long)(gt_ - gt_start); }
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+      if (warp == NPW + 5) {
+        // ================================================================ copy-engine loader (one thread per CTA)
+        // Both CTAs of the pair copy their halves with cta_group::2 tensor copies that signal the LEADER's FULL
+        // barrier directly; the leader's loader announces the bytes of both (arrive.expect_tx).
+        if (lane == 0 && (packed || p.a_tma || p.r_tma)) {
+            if (p.dbg && crank == 0) { unsigned long long gt_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_)); p.dbg[pair * DBG_STRIDE + 19] = (long long)(gt_ - gt_start); }
+            int slot = 0, par = 1, as = 0, a_par = 1;
+            const uint32_t fullA0 = mapa_u32(BAR(BAR_FULL_A), 0), fullB0 = mapa_u32(BAR(BAR_FULL_B), 0);   // leader's barriers
+            const int KBI = (p.A.L + GEMM_BK - 1) / GEMM_BK;       // 64-step blocks per batch item (r_tma, split-K)
+            for (int it_ = 0;; ++it_) {
+                const int u = item_unit<HC>(p, it_, pair, npairs, MP, nblocks, total);
+                if (u < 0) break;
+                const Unit t = decode_unit(p, u, MP, nblocks, crank);
+                if (p.dbg && crank == 0 && it_ == 0) { unsigned long long gt_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_)); p.dbg[pair * DBG_STRIDE + 20] = (long long)(gt_ - gt_start); }
+                // packed image rows (128 bytes each) of this CTA's half of stage (nb, kb): ((nb*KB + kb)*2 + crank) * 256
+                const int brow0 = (t.nb * t.KB * 2 + (int)crank) * 256;
+                // CTA pairs walk the k-blocks of a unit from different starting points (rot): at any moment they ask the
+                // L2 for different weight stages instead of all hammering the same 64 KiB
+                const int nkb = t.kb1 - t.kb0, rot = !rotate ? 0 : (nkb == t.KB ? pair - fdiv(pair, p.fd_KB) * nkb : pair % nkb);
+                for (int j = 0; j < nkb; ++j) {
+                    int kb = t.kb0 + j + rot; if (kb >= t.kb1) kb -= nkb;
+                    // steps [tb, tb + 64) of batch item `item`: the k-block of an MN-major (row-reduction) operand
+                    int item = t.z, tb = kb * GEMM_BK;
+                    if (p.dbg && crank == 0 && it_ == 0 && j == 0) {
+                        unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+                        p.dbg[pair * DBG_STRIDE + 14] = (long long)(gt - gt_start);     // ns until the loader issues its first copy
+                    }
+                    if (p.z_mode != Z_BATCH) { const int g = t.k_begin + kb; item = fdiv(g, p.fd_KBI); tb = (g - item * KBI) * GEMM_BK; }
+                    // ------------------------------------------------ A
+                    if (p.r_tma) {         // x^T tile = 64 steps x 128 channels [m0, m0+128) as two 64-channel boxes per plane
+                        mbar_wait(BAR(BAR_EMPTY_A + as), a_par);
+                        const uint32_t bar = fullA0 + 8u * as;
+                        const uint32_t dst = smem_u32(sA + as * A_SLOT);
+                        if (crank == 0) mbar_arrive_expect_tx(BAR(BAR_FULL_A + as), 2 * A_SLOT);
+                        const int ta = tb + p.A.off[t.ytap];
+                        tma_load_3d_cg2(dst, &p.tmA_hi, t.m0, ta, item, bar);
+                        tma_load_3d_cg2(dst + 8192, &p.tmA_hi, t.m0 + 64, ta, item, bar);
+                        tma_load_3d_cg2(dst + A_PLANE, &p.tmA_lo, t.m0, ta, item, bar);
+                        tma_load_3d_cg2(dst + A_PLANE + 8192, &p.tmA_lo, t.m0 + 64, ta, item, bar);
+                        if (++as == NA_SLOTS) { as = 0; a_par ^= 1; }
+                    } else if (p.a_tma) {  // K-major tile: two boxes (hi / lo plane) of 64 channels x 128 rows
+                        const int tap = fdiv(kb, p.fd_KBc), cb = kb - tap * t.KBc;
+                        mbar_wait(BAR(BAR_EMPTY_A + as), a_par);
+                        const uint32_t dst = smem_u32(sA + as * A_SLOT);
+                        const int off = p.A.off[tap];
+                        if (p.dbg_flags & 128) {               // diagnostics: no A traffic at all
+                            if (crank == 0) { mbar_arrive(BAR(BAR_FULL_A + as)); mbar_arrive(BAR(BAR_FULL_A + as)); mbar_arrive(BAR(BAR_FULL_A + as)); }
+                        } else {
+                            const bool flat = p.a_tma == 1;
+                            const bool fix_me = flat && !nofix && needs_fix(t.m0, off, p.A.L, p.fd_L);
+                            if (crank == 0) {                  // bytes that will be signalled straight on FULL_A
+                                const bool fix_peer = flat && !nofix && needs_fix(t.m0 + GEMM_BM, off, p.A.L, p.fd_L);
+                                mbar_arrive_expect_tx(BAR(BAR_FULL_A + as), (fix_me ? 0 : A_SLOT) + (fix_peer ? 0 : A_SLOT));
+                            }
+                            const int c0 = t.k_begin + cb * GEMM_BK;
+                            if (fix_me) {                      // lands locally; the fix-up warp sends this CTA's token
+                                const uint32_t bar = BAR(BAR_LAND_A + as);
+                                mbar_arrive_expect_tx(bar, A_SLOT);
+                                tma_load_2d(dst, &p.tmA_hi, c0, t.m0 + off, bar);
+                                tma_load_2d(dst + A_PLANE, &p.tmA_lo, c0, t.m0 + off, bar);
+                            } else {
+                                const uint32_t bar = fullA0 + 8u * as;
+                                if (flat) {
+                                    tma_load_2d_cg2(dst, &p.tmA_hi, c0, t.m0 + off, bar);
+                                    tma_load_2d_cg2(dst + A_PLANE, &p.tmA_lo, c0, t.m0 + off, bar);
+                                } else {
+                                    tma_load_3d_cg2(dst, &p.tmA_hi, c0, t.m0, t.z, bar);
+                                    tma_load_3d_cg2(dst + A_PLANE, &p.tmA_lo, c0, t.m0, t.z, bar);
+                                }
+                                if (crank == 0) mbar_arrive(BAR(BAR_FULL_A + as)); else mbar_arrive_remote(BAR(BAR_FULL_A + as), 0);
+                            }
+                        }
+                        if (++as == NA_SLOTS) { as = 0; a_par ^= 1; }
+                    }
+                    // ------------------------------------------------ B
+                    if (p.r_tma || p.b_tma == 3) {             // MN-major: 64 steps x this CTA's 128 of the 256 output columns
+                        mbar_wait(BAR(BAR_EMPTY_B + slot), par);
+                        const uint32_t bar = fullB0 + 8u * slot;
+                        const uint32_t dst = smem_u32(sB + slot * B_SLOT);
+                        if (crank == 0) mbar_arrive_expect_tx(BAR(BAR_FULL_B + slot), 2 * B_SLOT);
+                        const int tbb = tb + (p.r_tma ? p.Bm.off[t.ytap] : 0), n = t.n0 + (int)crank * GEMM_BNC;
+                        tma_load_3d_cg2(dst, &p.tmB_hi, n, tbb, item, bar);
+                        tma_load_3d_cg2(dst + 8192, &p.tmB_hi, n + 64, tbb, item, bar);
+                        tma_load_3d_cg2(dst + B_PLANE, &p.tmB_lo, n, tbb, item, bar);
+                        tma_load_3d_cg2(dst + B_PLANE + 8192, &p.tmB_lo, n + 64, tbb, item, bar);
+                        if (++slot == NB_SLOTS) { slot = 0; par ^= 1; }
+                    } else if (p.b_tma == 2) {                 // K-major rows [n, n + 128) of item z, 64 channels
+                        mbar_wait(BAR(BAR_EMPTY_B + slot), par);
+                        const uint32_t bar = fullB0 + 8u * slot;
+                        const uint32_t dst = smem_u32(sB + slot * B_SLOT);
+                        if (crank == 0) mbar_arrive_expect_tx(BAR(BAR_FULL_B + slot), 2 * B_SLOT);
+                        const int n = t.n0 + (int)crank * GEMM_BNC, c0 = t.k_begin + kb * GEMM_BK;
+                        tma_load_3d_cg2(dst, &p.tmB_hi, c0, n, t.z, bar);
+                        tma_load_3d_cg2(dst + B_PLANE, &p.tmB_lo, c0, n, t.z, bar);
+                        if (++slot == NB_SLOTS) { slot = 0; par ^= 1; }
+                    } else if (packed) {
+                        mbar_wait(BAR(BAR_EMPTY_B + slot), par);
+                        if (p.dbg_flags & 2) { if (crank == 0) mbar_arrive(BAR(BAR_FULL_B + slot)); }
+                        else {
+                            if (crank == 0) mbar_arrive_expect_tx(BAR(BAR_FULL_B + slot), 2 * B_SLOT);
+                            tma_load_2d_cg2(smem_u32(sB + slot * B_SLOT), &p.tmB_hi, 0, brow0 + kb * 512, fullB0 + 8u * slot);
+                        }
+                        if (++slot == NB_SLOTS) { slot = 0; par ^= 1; }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+      } else if (warp == NPW + 6) {
+        // ================================================================ item-boundary fix-up (whole warp, both CTAs)
+        // Flat conv-style A tiles: rows whose tap-shifted source step falls outside their own batch item were fetched
+        // from the neighbouring item.  They are conv padding: such tiles land on a local barrier, the rows are zeroed
+        // here (generic-proxy stores + proxy fence) and the bytes are then accounted on the leader's FULL barrier.
+        if (p.a_tma == 1) {
+            int as = 0; uint32_t land_par = 0;
+            for (int it_ = 0;; ++it_) {
+                const int u = item_unit<HC>(p, it_, pair, npairs, MP, nblocks, total);
+                if (u < 0) break;
+                const Unit t = decode_unit(p, u, MP, nblocks, crank);
+                int tmod[4];                                   // step within the item of this lane's 4 rows
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { const int r = t.m0 + lane + 32 * j; tmod[j] = r - fdiv(r, p.fd_L) * p.A.L; }
+                const int nkb = t.kb1 - t.kb0, rot = !rotate ? 0 : (nkb == t.KB ? pair - fdiv(pair, p.fd_KB) * nkb : pair % nkb);
+                for (int j = 0; j < nkb; ++j) {
+                    int kb = t.kb0 + j + rot; if (kb >= t.kb1) kb -= nkb;
+                    const int off = p.A.off[fdiv(kb, p.fd_KBc)];
+                    if (!nofix && needs_fix(t.m0, off, p.A.L, p.fd_L)) {
+                        mbar_wait(BAR(BAR_LAND_A + as), (land_par >> as) & 1u);
+                        land_par ^= 1u << as;
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            const int ts = tmod[r] + off;
+                            if (ts < 0 || ts >= p.A.L) {
+                                uint4* h = reinterpret_cast<uint4*>(sA + as * A_SLOT + (lane + 32 * r) * 128);
+                                uint4* l = reinterpret_cast<uint4*>(sA + as * A_SLOT + A_PLANE + (lane + 32 * r) * 128);
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) { h[e] = make_uint4(0u, 0u, 0u, 0u); l[e] = make_uint4(0u, 0u, 0u, 0u); }
+                            }
+                        }
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) { if (crank == 0) mbar_arrive(BAR(BAR_FULL_A + as)); else mbar_arrive_remote(BAR(BAR_FULL_A + as), 0); }
+                    }
+                    if (++as == NA_SLOTS) as = 0;
+                }
+            }
+        }
+        __syncwarp();
+      } else if (warp == NPW + 4) {
+        // ================================================================ MMA issuer: one thread of the leader CTA
+        if (lane == 0 && crank == 0) {
+            const uint32_t idesc = make_idesc_bf16(2 * GEMM_BM, GEMM_BN, p.a_mode == A_MNMAJOR, p.b_mode == B_MNMAJOR);
+            const uint32_t a_step = (p.a_mode == A_MNMAJOR) ? 2048u : 32u;
+            const uint32_t a_lbo = (p.a_mode == A_MNMAJOR) ? 8192u : 16u;
+            const uint32_t b_step = (p.b_mode == B_MNMAJOR) ? 2048u : 32u;
+            const uint32_t b_lbo = (p.b_mode == B_MNMAJOR) ? 8192u : 16u;
+            const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
+            int as = 0, a_par = 0, bs = 0, b_par = 0, acc = 0, acc_par = 1;
+            long long w_t = 0, w_a = 0, w_b = 0, t_begin = clock64(), nkb = 0;
+            for (int it_ = 0;; ++it_) {
+                const int u = item_unit<HC>(p, it_, pair, npairs, MP, nblocks, total);
+                if (u < 0) break;
+                const Unit t = decode_unit(p, u, MP, nblocks, crank);
+                if (t.KB <= 0) continue;
+                long long c0 = clock64();
+                mbar_wait(BAR(BAR_T_EMPTY + acc), acc_par);    // epilogue of the unit that last used this stage is done
+                w_t += clock64() - c0;
+                tc_fence_after();
+                const uint32_t d = tmem_base + acc * GEMM_BN;
+                const int nk = t.kb1 - t.kb0;
+                for (int j = 0; j < nk; ++j) {
+                    c0 = clock64();
+                    mbar_wait(BAR(BAR_FULL_A + as), a_par);
+                    const long long c1 = clock64();
+                    if (p.dbg && nkb == 0) {
+                        unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+                        p.dbg[pair * DBG_STRIDE + 15] = (long long)(gt - gt_start);     // ns until the first A tile had landed
+                    }
+                    mbar_wait(BAR(BAR_FULL_B + bs), b_par);
+                    w_a += c1 - c0; w_b += clock64() - c1; ++nkb;
+                    tc_fence_after();
+                    if (p.dbg && nkb == 1) {
+                        unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+                        p.dbg[pair * DBG_STRIDE + 10] = (long long)(gt - gt_start);     // ns until the first operands had landed
+                    }
+                    const uint32_t a_hi = sA_addr + as * A_SLOT, a_lo = a_hi + A_PLANE;
+                    const uint32_t b_hi = sB_addr + bs * B_SLOT, b_lo = b_hi + B_PLANE;
+#pragma unroll
+                    for (int ks = 0; ks < GEMM_BK / 16; ++ks) {
+                        const uint64_t dah = make_sdesc(a_hi + ks * a_step, a_lbo, 1024);
+                        const uint64_t dal = make_sdesc(a_lo + ks * a_step, a_lbo, 1024);
+                        const uint64_t dbh = make_sdesc(b_hi + ks * b_step, b_lbo, 1024);
+                        const uint64_t dbl = make_sdesc(b_lo + ks * b_step, b_lbo, 1024);
+                        umma2_bf16(d, dah, dbh, idesc, (j | ks) != 0);
+                        umma2_bf16(d, dah, dbl, idesc, 1);
+                        umma2_bf16(d, dal, dbh, idesc, 1);
+                    }
+                    umma2_commit_mcast(BAR(BAR_EMPTY_B + bs), 3);   // frees the B slot in both CTAs
+                    umma2_commit_mcast(BAR(BAR_EMPTY_A + as), 3);   // frees the A slot in both CTAs
+                    if (++bs == NB_SLOTS) { bs = 0; b_par ^= 1; }
+                    if (++as == NA_SLOTS) { as = 0; a_par ^= 1; }
+                }
+                umma2_commit_mcast(BAR(BAR_T_FULL + acc), 3);       // accumulators of both CTAs complete
+                if (++acc == N_ACC) { acc = 0; acc_par ^= 1; }
+            }
+            if (p.dbg) {
+                long long* o = p.dbg + pair * DBG_STRIDE;
+                unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+                o[0] = clock64() - t_begin; o[1] = w_t; o[2] = w_a; o[3] = w_b; o[4] = nkb;
+                o[5] = (long long)(gt - gt_start);      // ns from kernel entry to the end of the MMA issue loop
+            }
+        }
+        __syncwarp();
+      }
+    } else if (warp < NPW) {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
         if (copy_fed) {
             if (p.ln_fuse) epilogue_ln(warp & 3, warp >> 2, sStage + warp * 512);
@@ -824,236 +1048,22 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
                 }
             }
         }
-    } else if (warp < NPW + 4) {
+    } else {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
         if (!copy_fed) epilogue(warp & 3, 0, 1, sStage + (warp & 3) * 512);
-    } else {
-      asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-      if (warp == NPW + 4) {
-        // ================================================================ MMA issuer: one thread of the leader CTA
-        if (lane == 0 && crank == 0) {
-            const uint32_t idesc = make_idesc_bf16(2 * GEMM_BM, GEMM_BN, p.a_mode == A_MNMAJOR, p.b_mode == B_MNMAJOR);
-            const uint32_t a_step = (p.a_mode == A_MNMAJOR) ? 2048u : 32u;
-            const uint32_t a_lbo = (p.a_mode == A_MNMAJOR) ? 8192u : 16u;
-            const uint32_t b_step = (p.b_mode == B_MNMAJOR) ? 2048u : 32u;
-            const uint32_t b_lbo = (p.b_mode == B_MNMAJOR) ? 8192u : 16u;
-            const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
-            int as = 0, a_par = 0, bs = 0, b_par = 0, acc = 0, acc_par = 1;
-            long long w_t = 0, w_a = 0, w_b = 0, t_begin = clock64(), nkb = 0;
-            for (int it_ = 0;; ++it_) {
-                const int u = item_unit<HC>(p, it_, pair, npairs, MP, nblocks, total);
-                if (u < 0) break;
-                const Unit t = decode_unit(p, u, MP, nblocks, crank);
-                if (t.KB <= 0) continue;
-                long long c0 = clock64();
-                mbar_wait(BAR(BAR_T_EMPTY + acc), acc_par);    // epilogue of the unit that last used this stage is done
-                w_t += clock64() - c0;
-                tc_fence_after();
-                const uint32_t d = tmem_base + acc * GEMM_BN;
-                const int nk = t.kb1 - t.kb0;
-                for (int j = 0; j < nk; ++j) {
-                    c0 = clock64();
-                    mbar_wait(BAR(BAR_FULL_A + as), a_par);
-                    const long long c1 = clock64();
-                    if (p.dbg && nkb == 0) {
-                        unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-                        p.dbg[pair * 16 + 15] = (long long)(gt - gt_start);     // ns until the first A tile had landed
-                    }
-                    mbar_wait(BAR(BAR_FULL_B + bs), b_par);
-                    w_a += c1 - c0; w_b += clock64() - c1; ++nkb;
-                    tc_fence_after();
-                    if (p.dbg && nkb == 1) {
-                        unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-                        p.dbg[pair * 16 + 10] = (long long)(gt - gt_start);     // ns until the first operands had landed
-                    }
-                    const uint32_t a_hi = sA_addr + as * A_SLOT, a_lo = a_hi + A_PLANE;
-                    const uint32_t b_hi = sB_addr + bs * B_SLOT, b_lo = b_hi + B_PLANE;
-#pragma unroll
-                    for (int ks = 0; ks < GEMM_BK / 16; ++ks) {
-                        const uint64_t dah = make_sdesc(a_hi + ks * a_step, a_lbo, 1024);
-                        const uint64_t dal = make_sdesc(a_lo + ks * a_step, a_lbo, 1024);
-                        const uint64_t dbh = make_sdesc(b_hi + ks * b_step, b_lbo, 1024);
-                        const uint64_t dbl = make_sdesc(b_lo + ks * b_step, b_lbo, 1024);
-                        umma2_bf16(d, dah, dbh, idesc, (j | ks) != 0);
-                        umma2_bf16(d, dah, dbl, idesc, 1);
-                        umma2_bf16(d, dal, dbh, idesc, 1);
-                    }
-                    umma2_commit_mcast(BAR(BAR_EMPTY_B + bs), 3);   // frees the B slot in both CTAs
-                    umma2_commit_mcast(BAR(BAR_EMPTY_A + as), 3);   // frees the A slot in both CTAs
-                    if (++bs == NB_SLOTS) { bs = 0; b_par ^= 1; }
-                    if (++as == NA_SLOTS) { as = 0; a_par ^= 1; }
-                }
-                umma2_commit_mcast(BAR(BAR_T_FULL + acc), 3);       // accumulators of both CTAs complete
-                if (++acc == N_ACC) { acc = 0; acc_par ^= 1; }
-            }
-            if (p.dbg) {
-                long long* o = p.dbg + pair * 16;
-                unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-                o[0] = clock64() - t_begin; o[1] = w_t; o[2] = w_a; o[3] = w_b; o[4] = nkb;
-                o[5] = (long long)(gt - gt_start);      // ns from kernel entry to the end of the MMA issue loop
-            }
-        }
-        __syncwarp();
-      } else if (warp == NPW + 5) {
-        // ================================================================ copy-engine loader (one thread per CTA)
-        // Both CTAs of the pair copy their halves with cta_group::2 tensor copies that signal the LEADER's FULL
-        // barrier directly; the leader's loader announces the bytes of both (arrive.expect_tx).
-        if (lane == 0 && (packed || p.a_tma || p.r_tma)) {
-            int slot = 0, par = 1, as = 0, a_par = 1;
-            const uint32_t fullA0 = mapa_u32(BAR(BAR_FULL_A), 0), fullB0 = mapa_u32(BAR(BAR_FULL_B), 0);   // leader's barriers
-            const int KBI = (p.A.L + GEMM_BK - 1) / GEMM_BK;       // 64-step blocks per batch item (r_tma, split-K)
-            for (int it_ = 0;; ++it_) {
-                const int u = item_unit<HC>(p, it_, pair, npairs, MP, nblocks, total);
-                if (u < 0) break;
-                const Unit t = decode_unit(p, u, MP, nblocks, crank);
-                // packed image rows (128 bytes each) of this CTA's half of stage (nb, kb): ((nb*KB + kb)*2 + crank) * 256
-                const int brow0 = (t.nb * t.KB * 2 + (int)crank) * 256;
-                // CTA pairs walk the k-blocks of a unit from different starting points (rot): at any moment they ask the
-                // L2 for different weight stages instead of all hammering the same 64 KiB
-                const int nkb = t.kb1 - t.kb0, rot = !rotate ? 0 : (nkb == t.KB ? pair - fdiv(pair, p.fd_KB) * nkb : pair % nkb);
-                for (int j = 0; j < nkb; ++j) {
-                    int kb = t.kb0 + j + rot; if (kb >= t.kb1) kb -= nkb;
-                    // steps [tb, tb + 64) of batch item `item`: the k-block of an MN-major (row-reduction) operand
-                    int item = t.z, tb = kb * GEMM_BK;
-                    if (p.dbg && crank == 0 && it_ == 0 && j == 0) {
-                        unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-                        p.dbg[pair * 16 + 14] = (long long)(gt - gt_start);     // ns until the loader issues its first copy
-                    }
-                    if (p.z_mode != Z_BATCH) { const int g = t.k_begin + kb; item = fdiv(g, p.fd_KBI); tb = (g - item * KBI) * GEMM_BK; }
-                    // ------------------------------------------------ A
-                    if (p.r_tma) {         // x^T tile = 64 steps x 128 channels [m0, m0+128) as two 64-channel boxes per plane
-                        mbar_wait(BAR(BAR_EMPTY_A + as), a_par);
-                        const uint32_t bar = fullA0 + 8u * as;
-                        const uint32_t dst = smem_u32(sA + as * A_SLOT);
-                        if (crank == 0) mbar_arrive_expect_tx(BAR(BAR_FULL_A + as), 2 * A_SLOT);
-                        const int ta = tb + p.A.off[t.ytap];
-                        tma_load_3d_cg2(dst, &p.tmA_hi, t.m0, ta, item, bar);
-                        tma_load_3d_cg2(dst + 8192, &p.tmA_hi, t.m0 + 64, ta, item, bar);
-                        tma_load_3d_cg2(dst + A_PLANE, &p.tmA_lo, t.m0, ta, item, bar);
-                        tma_load_3d_cg2(dst + A_PLANE + 8192, &p.tmA_lo, t.m0 + 64, ta, item, bar);
-                        if (++as == NA_SLOTS) { as = 0; a_par ^= 1; }
-                    } else if (p.a_tma) {  // K-major tile: two boxes (hi / lo plane) of 64 channels x 128 rows
-                        const int tap = fdiv(kb, p.fd_KBc), cb = kb - tap * t.KBc;
-                        mbar_wait(BAR(BAR_EMPTY_A + as), a_par);
-                        const uint32_t dst = smem_u32(sA + as * A_SLOT);
-                        const int off = p.A.off[tap];
-                        if (p.dbg_flags & 128) {               // diagnostics: no A traffic at all
-                            if (crank == 0) { mbar_arrive(BAR(BAR_FULL_A + as)); mbar_arrive(BAR(BAR_FULL_A + as)); mbar_arrive(BAR(BAR_FULL_A + as)); }
-                        } else {
-                            const bool flat = p.a_tma == 1;
-                            const bool fix_me = flat && !nofix && needs_fix(t.m0, off, p.A.L, p.fd_L);
-                            if (crank == 0) {                  // bytes that will be signalled straight on FULL_A
-                                const bool fix_peer = flat && !nofix && needs_fix(t.m0 + GEMM_BM, off, p.A.L, p.fd_L);
-                                mbar_arrive_expect_tx(BAR(BAR_FULL_A + as), (fix_me ? 0 : A_SLOT) + (fix_peer ? 0 : A_SLOT));
-                            }
-                            const int c0 = t.k_begin + cb * GEMM_BK;
-                            if (fix_me) {                      // lands locally; the fix-up warp sends this CTA's token
-                                const uint32_t bar = BAR(BAR_LAND_A + as);
-                                mbar_arrive_expect_tx(bar, A_SLOT);
-                                tma_load_2d(dst, &p.tmA_hi, c0, t.m0 + off, bar);
-                                tma_load_2d(dst + A_PLANE, &p.tmA_lo, c0, t.m0 + off, bar);
-                            } else {
-                                const uint32_t bar = fullA0 + 8u * as;
-                                if (flat) {
-                                    tma_load_2d_cg2(dst, &p.tmA_hi, c0, t.m0 + off, bar);
-                                    tma_load_2d_cg2(dst + A_PLANE, &p.tmA_lo, c0, t.m0 + off, bar);
-                                } else {
-                                    tma_load_3d_cg2(dst, &p.tmA_hi, c0, t.m0, t.z, bar);
-                                    tma_load_3d_cg2(dst + A_PLANE, &p.tmA_lo, c0, t.m0, t.z, bar);
-                                }
-                                if (crank == 0) mbar_arrive(BAR(BAR_FULL_A + as)); else mbar_arrive_remote(BAR(BAR_FULL_A + as), 0);
-                            }
-                        }
-                        if (++as == NA_SLOTS) { as = 0; a_par ^= 1; }
-                    }
-                    // ------------------------------------------------ B
-                    if (p.r_tma || p.b_tma == 3) {             // MN-major: 64 steps x this CTA's 128 of the 256 output columns
-                        mbar_wait(BAR(BAR_EMPTY_B + slot), par);
-                        const uint32_t bar = fullB0 + 8u * slot;
-                        const uint32_t dst = smem_u32(sB + slot * B_SLOT);
-                        if (crank == 0) mbar_arrive_expect_tx(BAR(BAR_FULL_B + slot), 2 * B_SLOT);
-                        const int tbb = tb + (p.r_tma ? p.Bm.off[t.ytap] : 0), n = t.n0 + (int)crank * GEMM_BNC;
-                        tma_load_3d_cg2(dst, &p.tmB_hi, n, tbb, item, bar);
-                        tma_load_3d_cg2(dst + 8192, &p.tmB_hi, n + 64, tbb, item, bar);
-                        tma_load_3d_cg2(dst + B_PLANE, &p.tmB_lo, n, tbb, item, bar);
-                        tma_load_3d_cg2(dst + B_PLANE + 8192, &p.tmB_lo, n + 64, tbb, item, bar);
-                        if (++slot == NB_SLOTS) { slot = 0; par ^= 1; }
-                    } else if (p.b_tma == 2) {                 // K-major rows [n, n + 128) of item z, 64 channels
-                        mbar_wait(BAR(BAR_EMPTY_B + slot), par);
-                        const uint32_t bar = fullB0 + 8u * slot;
-                        const uint32_t dst = smem_u32(sB + slot * B_SLOT);
-                        if (crank == 0) mbar_arrive_expect_tx(BAR(BAR_FULL_B + slot), 2 * B_SLOT);
-                        const int n = t.n0 + (int)crank * GEMM_BNC, c0 = t.k_begin + kb * GEMM_BK;
-                        tma_load_3d_cg2(dst, &p.tmB_hi, c0, n, t.z, bar);
-                        tma_load_3d_cg2(dst + B_PLANE, &p.tmB_lo, c0, n, t.z, bar);
-                        if (++slot == NB_SLOTS) { slot = 0; par ^= 1; }
-                    } else if (packed) {
-                        mbar_wait(BAR(BAR_EMPTY_B + slot), par);
-                        if (p.dbg_flags & 2) { if (crank == 0) mbar_arrive(BAR(BAR_FULL_B + slot)); }
-                        else {
-                            if (crank == 0) mbar_arrive_expect_tx(BAR(BAR_FULL_B + slot), 2 * B_SLOT);
-                            tma_load_2d_cg2(smem_u32(sB + slot * B_SLOT), &p.tmB_hi, 0, brow0 + kb * 512, fullB0 + 8u * slot);
-                        }
-                        if (++slot == NB_SLOTS) { slot = 0; par ^= 1; }
-                    }
-                }
-            }
-        }
-        __syncwarp();
-      } else if (warp == NPW + 6) {
-        // ================================================================ item-boundary fix-up (whole warp, both CTAs)
-        // Flat conv-style A tiles: rows whose tap-shifted source step falls outside their own batch item were fetched
-        // from the neighbouring item.  They are conv padding: such tiles land on a local barrier, the rows are zeroed
-        // here (generic-proxy stores + proxy fence) and the bytes are then accounted on the leader's FULL barrier.
-        if (p.a_tma == 1) {
-            int as = 0; uint32_t land_par = 0;
-            for (int it_ = 0;; ++it_) {
-                const int u = item_unit<HC>(p, it_, pair, npairs, MP, nblocks, total);
-                if (u < 0) break;
-                const Unit t = decode_unit(p, u, MP, nblocks, crank);
-                int tmod[4];                                   // step within the item of this lane's 4 rows
-#pragma unroll
-                for (int j = 0; j < 4; ++j) { const int r = t.m0 + lane + 32 * j; tmod[j] = r - fdiv(r, p.fd_L) * p.A.L; }
-                const int nkb = t.kb1 - t.kb0, rot = !rotate ? 0 : (nkb == t.KB ? pair - fdiv(pair, p.fd_KB) * nkb : pair % nkb);
-                for (int j = 0; j < nkb; ++j) {
-                    int kb = t.kb0 + j + rot; if (kb >= t.kb1) kb -= nkb;
-                    const int off = p.A.off[fdiv(kb, p.fd_KBc)];
-                    if (!nofix && needs_fix(t.m0, off, p.A.L, p.fd_L)) {
-                        mbar_wait(BAR(BAR_LAND_A + as), (land_par >> as) & 1u);
-                        land_par ^= 1u << as;
-#pragma unroll
-                        for (int r = 0; r < 4; ++r) {
-                            const int ts = tmod[r] + off;
-                            if (ts < 0 || ts >= p.A.L) {
-                                uint4* h = reinterpret_cast<uint4*>(sA + as * A_SLOT + (lane + 32 * r) * 128);
-                                uint4* l = reinterpret_cast<uint4*>(sA + as * A_SLOT + A_PLANE + (lane + 32 * r) * 128);
-#pragma unroll
-                                for (int e = 0; e < 8; ++e) { h[e] = make_uint4(0u, 0u, 0u, 0u); l[e] = make_uint4(0u, 0u, 0u, 0u); }
-                            }
-                        }
-                        fence_proxy_async();
-                        __syncwarp();
-                        if (lane == 0) { if (crank == 0) mbar_arrive(BAR(BAR_FULL_A + as)); else mbar_arrive_remote(BAR(BAR_FULL_A + as), 0); }
-                    }
-                    if (++as == NA_SLOTS) as = 0;
-                }
-            }
-        }
-        __syncwarp();
-      }
     }
 
     tc_fence_before();
     if (p.dbg && crank == 0 && tid == 256) {           // an epilogue-free producer thread: time until its role loop ended
         unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-        p.dbg[pair * 16 + 6] = (long long)(gt - gt_start);
+        p.dbg[pair * DBG_STRIDE + 6] = (long long)(gt - gt_start);
     }
     cluster_sync_all();                                // the partner's smem/barriers stay alive until both are done
     if (p.dbg && crank == 0 && tid == 0) {
         unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-        p.dbg[pair * 16 + 7] = (long long)(gt - gt_start);     // ns from kernel entry to after the final cluster barrier
-        p.dbg[pair * 16 + 8] = (long long)gt_start;            // absolute entry / exit times: launch skew between the pairs
-        p.dbg[pair * 16 + 13] = (long long)gt;
+        p.dbg[pair * DBG_STRIDE + 7] = (long long)(gt - gt_start);     // ns from kernel entry to after the final cluster barrier
+        p.dbg[pair * DBG_STRIDE + 8] = (long long)gt_start;            // absolute entry / exit times: launch skew between the pairs
+        p.dbg[pair * DBG_STRIDE + 13] = (long long)gt;
     }
     if (warp == NPW + 4) tmem_dealloc2<N_ACC * GEMM_BN>(tmem_base);
 }

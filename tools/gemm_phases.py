@@ -22,7 +22,7 @@ dev = torch.device("cuda:0")
 torch.manual_seed(0)
 if a.flags:
     _lib.set_debug_flags(a.flags)
-dbg = torch.zeros(74, 16, dtype=torch.int64, device=dev)
+dbg = torch.zeros(74, 24, dtype=torch.int64, device=dev)
 
 
 def planes(B, L, C):

@@ -45,7 +45,7 @@ def main():
         g.train_step_device(*dev_in)
     torch.cuda.synchronize()
     SLOTS = 512
-    ring = torch.zeros(SLOTS, 74, 16, dtype=torch.int64, device=dev)
+    ring = torch.zeros(SLOTS, 74, 24, dtype=torch.int64, device=dev)
     if args.eager:
         hp.use_side_streams = False
         g.train_step_device(*dev_in)
@@ -83,12 +83,12 @@ def main():
     out = os.path.join(ROOT, "gpurun_out", args.out)
     tot_busy = tot_mma = tot_start = tot_tail = 0.0
     with open(out, "w") as f:
-        f.write("# start_us span_us pairs | ns mean(max): copy1 A1 ops1 acc1 mma_end epi_end exit | skew_max | desc\n")
+        f.write("# start_us span_us pairs | ns mean(max): bar_init tmem_alloc prologue_end pre_setmaxnreg loader_in decoded | copy1 A1 ops1 acc1 mma_end epi_end exit | skew_max | desc\n")
         for t0, s, x, desc in rows:
             span = x[:, 13].max() - t0
             skew = x[:, 8] - t0
             m = lambda c: "%5.1f(%5.1f)" % (x[:, c].mean() / 1e3, x[:, c].max() / 1e3)  # noqa: E731
-            f.write("%8.1f %6.1f %3d | %s %s %s %s %s %s %s | %5.1f | %s\n" % ((t0 - T0) / 1e3, span / 1e3, len(x), m(14), m(15), m(10), m(11),
+            f.write("%8.1f %6.1f %3d | %s %s %s %s %s %s | %s %s %s %s %s %s %s | %5.1f | %s\n" % ((t0 - T0) / 1e3, span / 1e3, len(x), m(17), m(16), m(9), m(18), m(19), m(20), m(14), m(15), m(10), m(11),
                                                                            m(5), m(12), m(7), skew.max() / 1e3, desc))
             busy = float((x[:, 13] - x[:, 8]).sum())
             tot_busy += busy

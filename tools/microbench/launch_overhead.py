@@ -22,7 +22,7 @@ def raw():
     _lib.call("oph_gemm_nt", A.data_ptr(), 256, Bm.data_ptr(), 256, C.data_ptr(), 256, None, 256, 256, 256, 1, 1.0, 1, 0, 0, 0, torch.cuda.current_stream().cuda_stream)
 print("raw tiny gemm (no allocs): %.1f us" % timeit(raw))
 
-dbg = torch.zeros(74, 16, dtype=torch.int64, device=dev)
+dbg = torch.zeros(74, 24, dtype=torch.int64, device=dev)
 _lib.call("oph_gemm_debug_buffer", dbg.data_ptr())
 raw(); torch.cuda.synchronize()
 print("with timers: %.1f us" % timeit(raw))

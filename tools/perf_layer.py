@@ -57,7 +57,7 @@ def run():
         ops.attention_fwd(Q, K, V)
 
 
-dbg = torch.zeros(74, 16, dtype=torch.int64, device=dev)
+dbg = torch.zeros(74, 24, dtype=torch.int64, device=dev)
 _lib.call("oph_gemm_debug_buffer", dbg.data_ptr())
 _lib.set_debug_flags(a.dbg)
 for _ in range(a.warmup):
