@@ -296,6 +296,9 @@ class Graph(object):
         if buckets is not None:
             scale = buckets.finish()                                       # the buckets not yet launched + join
         elif self.process_group is not None:
+            nchunks = int(getattr(hp, "allreduce_chunks", 1))     # > 1: sliced exchange overlapping Adam (no gain measured)
+            if nchunks > 1 and st.grad_flat.is_cuda and self.train_ranges is None:
+                return self._apply_gradients_pipelined(nchunks)
             from .parallel import allreduce_gradients
             scale = allreduce_gradients(st.grad_flat, self.process_group)  # NCCL sum over NVLink; only collective
         ops.adam_prepare(st.global_step, st.lr_t, hp.lr, hp.beta1, hp.beta2, hp.decay_lr)
@@ -308,6 +311,40 @@ class Graph(object):
         ops.step_inc(st.global_step)
         st.version += 1
         st.repack_all()             # one launch refreshes every split-bf16 weight image for the next step
+
+    def _apply_gradients_pipelined(self, nchunks):
+        """Data parallel: the flat gradient is exchanged in `nchunks` contiguous slices on a communication stream and the
+        fused clip + Adam kernel of slice i runs on the main stream while slice i+1 is still being reduced -- the backward
+        pass is over at this point, so the collective and the optimiser share the SMs without starving a GEMM (DESIGN
+        section 6).  Same arithmetic as the one-collective form: sum over ranks, then (1/world) inside the Adam kernel."""
+        import torch.distributed as dist
+        hp, st = self.hp, self.store
+        pg = self.process_group
+        scale = 1.0 / dist.get_world_size(pg)
+        main = torch.cuda.current_stream(self.device)
+        comm = self.__dict__.get("_comm_stream")
+        if comm is None:
+            comm = self._comm_stream = torch.cuda.Stream(device=self.device)
+        n = st.numel
+        cuts = [0] + [min(n, ((n * i // nchunks) + 1023) // 1024 * 1024) for i in range(1, nchunks)] + [n]
+        chunks = [(a, b) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
+        comm.wait_stream(main)
+        events = []
+        with torch.cuda.stream(comm):
+            for a, b in chunks:
+                w = dist.all_reduce(st.grad_flat[a:b], op=dist.ReduceOp.SUM, group=pg, async_op=True)
+                w.wait()                                   # stream-level wait: `comm` follows NCCL's own stream
+                ev = torch.cuda.Event()
+                ev.record(comm)
+                events.append(ev)
+        ops.adam_prepare(st.global_step, st.lr_t, hp.lr, hp.beta1, hp.beta2, hp.decay_lr)
+        for (a, b), ev in zip(chunks, events):
+            main.wait_event(ev)
+            ops.adam_clip(st.flat[a:b], st.m_flat[a:b], st.v_flat[a:b], st.grad_flat[a:b], st.lr_t, hp.beta1, hp.beta2,
+                          hp.epsilon, 1.0, scale)
+        ops.step_inc(st.global_step)
+        st.version += 1
+        st.repack_all()
 
     # ---- whole-step CUDA graph: one launch replays the ~280 kernels of a training step (static shapes only)
     def capture_train_step(self, *example_inputs, warmup=2):
@@ -369,15 +406,26 @@ class Graph(object):
         self._prefetched = (dev, ev)
 
     def _next_inputs(self, fields):
+        """The prefetched device inputs of this step.  The caller launches the step and THEN calls `_prefetch_next`, so that
+        the host work of assembling batch i+1 and its H2D copy overlap step i instead of delaying its launch."""
         if getattr(self, "_prefetched", None) is None:
             self._prefetch(fields)
         dev, ev = self._prefetched
+        self._prefetched = None
         torch.cuda.current_stream(self.device).wait_event(ev)
+        return dev
+
+    def _launch_then_prefetch(self, inputs, fields):
+        out = self._step_maybe_graphed(*inputs)
+        if fields is not None:
+            self._prefetch_next(fields)
+        return out
+
+    def _prefetch_next(self, fields):
         try:
             self._prefetch(fields)
         except StopIteration:
             self._prefetched = None
-        return dev
 
     def _to_device(self, x, dtype, ids=False):
         if ids and not (isinstance(x, torch.Tensor) and x.is_cuda):
@@ -421,7 +469,7 @@ class SSRNGraph(Graph):
             inputs = self._next_inputs(tuple(fields))
         else:
             inputs = tuple(self._to_device(batch[k], dt) for k, dt in fields)
-        return self._step_maybe_graphed(*inputs)
+        return self._launch_then_prefetch(inputs, tuple(fields) if batch is None else None)
 
     def train_step_device(self, mels, mags, speakers=None):
         hp, st = self.hp, self.store
@@ -591,7 +639,7 @@ class Text2MelGraph(Graph):
             inputs = self._next_inputs(tuple(fields))
         else:
             inputs = tuple(self._to_device(batch[k], dt, ids=(k == "text")) for k, dt in fields)
-        return self._step_maybe_graphed(*inputs)
+        return self._launch_then_prefetch(inputs, tuple(fields) if batch is None else None)
 
     def train_step_device(self, L, mels, *extras, gts=None):
         """One `sess.run([global_step, loss_components, train_op])` with inputs already on the device.
@@ -738,7 +786,7 @@ class BabblerGraph(Graph):
     def train_step(self, batch=None):
         fields = (("mel", torch.float32),)
         inputs = self._next_inputs(fields) if batch is None else tuple(self._to_device(batch[k], dt) for k, dt in fields)
-        return self._step_maybe_graphed(*inputs)
+        return self._launch_then_prefetch(inputs, fields if batch is None else None)
 
     def train_step_device(self, mels):
         """loss_components = [loss, L1, BD] with hp.loss_weights['babbler'] (architectures.py:412-424)."""

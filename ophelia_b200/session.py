@@ -48,9 +48,24 @@ class Session(object):
     def _evaluate(self, g, names, feeds):
         if "train_op" in names or "loss" in names or "loss_components" in names:
             assert g.training, "loss/train_op exist only on mode='train' graphs"
-            comps = g.train_step().cpu().numpy()
-            # value after the step (fetching global_step alongside train_op is unordered in TF; the reference only logs it)
-            gs = int(g.store.global_step.item()) if "global_step" in names else None
+            comps_d = g.train_step()
+            # loss components and global_step come back through pinned buffers with ONE stream synchronisation (two blocking
+            # reads cost two round trips during which the device idles).  global_step: value after the step (fetching it
+            # alongside train_op is unordered in TF; the reference only logs it)
+            if not comps_d.is_cuda:
+                comps = comps_d.numpy()
+                gs = int(g.store.global_step.item()) if "global_step" in names else None
+                return {"train_op": None, "loss": float(comps[0]), "loss_components": [float(c) for c in comps], "global_step": gs}
+            pin = g.__dict__.get("_host_out")
+            if pin is None or pin[0].numel() < comps_d.numel():
+                pin = g.__dict__["_host_out"] = (torch.empty(16, dtype=torch.float32).pin_memory(),
+                                                 torch.empty(1, dtype=g.store.global_step.dtype).pin_memory())
+            pin[0][:comps_d.numel()].copy_(comps_d, non_blocking=True)
+            if "global_step" in names:
+                pin[1].copy_(g.store.global_step.reshape(1), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            comps = pin[0][:comps_d.numel()].numpy().copy()
+            gs = int(pin[1][0]) if "global_step" in names else None
             return {"train_op": None, "loss": float(comps[0]), "loss_components": [float(c) for c in comps],
                     "global_step": gs}
         if names == {"global_step"}:
