@@ -658,7 +658,18 @@ class Text2MelGraph(Graph):
             "hp.attention_guide_dir set <=> batches carry 'attention_guide' (architectures.py:57-60)"
         assert not hp.attention_guide_fa or gts is not None, "the MSE attention loss needs targets from hp.attention_guide_dir"
         mels._oph_no_grad = True
-        st.grad_flat.zero_()
+        side = self._streams()
+        zero_ev = None
+        if side is None:
+            st.grad_flat.zero_()
+        else:
+            # nothing touches the gradient buffer before the backward pass: its 96 MB memset rides a side stream under the
+            # forward pass instead of in front of it
+            side[1].wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side[1]):
+                st.grad_flat.zero_()
+                zero_ev = torch.cuda.Event()
+                zero_ev.record(side[1])
         acc = torch.zeros(4, dtype=torch.float64, device=self.device)
         # CDP / Ain / Aout (architectures.py:283-321): reported whenever one weight is non-zero, part of the total loss (and
         # of the gradient) only under the legacy lw_* pattern (:333-349)
@@ -669,7 +680,6 @@ class Text2MelGraph(Graph):
             extra = {"acc": torch.zeros(3, dtype=torch.float64, device=self.device), "in_total": in_total,
                      "lw": (hp.lw_cdp, hp.lw_ain, hp.lw_aout) if in_total else (0.0, 0.0, 0.0)}
         tapes = (Tape(), Tape(), Tape())
-        side = self._streams()
         out = self.build_model(L, mels, True, att_acc=acc[3:], want_alignments=False, tapes=tapes,
                                text_stream=side[0] if side else None, gts=gts, extra=extra, speakers=speakers,
                                durations=durations, merlin_label=merlin_label)
@@ -695,6 +705,7 @@ class Text2MelGraph(Graph):
             # main: AudioDec -> Attention -> AudioEnc;  s_text: TextEnc;  s_w1 / s_w2: their weight-gradient GEMMs
             main = torch.cuda.current_stream(self.device)
             s_text, s_w1, s_w2 = side
+            main.wait_event(zero_ev)                     # the zeroed gradient buffer (every other stream forks from main below)
             s_w1.wait_stream(main)
             keep = []
             # data parallel: gradient buckets in flat-buffer order (TextEnc first half | second half | AudioEnc | AudioDec)

@@ -865,7 +865,7 @@ __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src) {
 }
 
 template <int WPR>
-__global__ void __launch_bounds__(256) hc_post_bwd_wide_kernel(
+__global__ void __launch_bounds__(256, 2) hc_post_bwd_wide_kernel(
         const float* __restrict__ dy, long long lddy, const float* __restrict__ z, long long ldz,
         const float* __restrict__ x, long long ldx, const float* __restrict__ stats,
         const float* __restrict__ g1, const float* __restrict__ b1, const float* __restrict__ g2,
