@@ -79,8 +79,15 @@ int oph_gemm_debug_ring_desc(int slot, char* out, int cap);
  * rounds of the 74 CTA pairs, the last one to >= 70 %), 262144 = also fuse the full rounds when the last round is emptier
  * (the rest of the rows then gets plain work units + a partial tail launch), 524288 = networks.Attention forward as three
  * launches (two GEMMs + the softmax kernel) instead of the one-kernel form, 1048576 = scalar conv-tail kernels for channel
- * counts other than 256 / 512 / 1024 (default: the 16-byte kernels over padded rows) */
+ * counts other than 256 / 512 / 1024 (default: the 16-byte kernels over padded rows), 4194304 = two instead of three blocks per SM
+ * for the conv-tail backward kernel */
 int oph_gemm_debug_flags(int flags);
+/* Every in-kernel barrier wait is bounded and traps instead of hanging the GPU; before it traps the waiting thread leaves a
+ * record (block, warp = role, barrier, parity) in mapped host memory.  Returns 1 if such a record exists; out[4] = raw
+ * words, text = decoded sentence.  The same sentence is appended to oph_last_error() of the call that sees the failure. */
+int oph_last_trap(unsigned long long* out, char* text, int cap);
+/* diagnostics: records a fake wait and traps (kills the CUDA context of the calling process): self-test of the record */
+int oph_debug_trap_selftest(oph_stream_t stream);
 /* Execution context of the calling host thread (like cublasSetStream): with enable != 0 the weight-gradient GEMMs of
  * oph_*_bwd are launched on `side` after an event fork behind the layer's row-wise backward kernel, so that they
  * overlap the input-gradient chain on `stream`.  The caller joins `side` back (event / stream wait) before it reads

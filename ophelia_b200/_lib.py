@@ -44,6 +44,8 @@ SIGNATURES = {
     "oph_gemm_debug_ring": (I, [P, I]),
     "oph_gemm_debug_ring_desc": (I, [I, P, I]),
     "oph_gemm_debug_flags": (I, [I]),
+    "oph_last_trap": (I, [P, P, I]),
+    "oph_debug_trap_selftest": (I, [P]),
     "oph_wgrad_stream": (I, [P, I]),
     "oph_cache_config": (I, [I]),
     "oph_profile_begin": (I, []),

@@ -12,6 +12,8 @@ Execution is eager on CUDA; one training step = forward (tape), fused losses, ex
 clip + TF-Adam, all in kernels of libophelia_sm100.so.
 """
 import numpy as np
+import os
+
 import torch
 
 from . import ops
@@ -274,7 +276,8 @@ class Graph(object):
             return None
         st = self.__dict__.get("_side_streams")
         if st is None:
-            st = tuple(torch.cuda.Stream(device=self.device) for _ in range(3))
+            prio = int(os.environ.get("OPH_SIDE_PRIORITY", "0"))       # diagnostics: priority of the side streams
+            st = tuple(torch.cuda.Stream(device=self.device, priority=prio) for _ in range(3))
             self._side_streams = st
         return st
 

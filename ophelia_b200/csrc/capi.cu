@@ -109,11 +109,52 @@ int fail(int code, const char* fmt, const char* detail = "") {   // fmt contains
     snprintf(g_err, sizeof(g_err), fmt, detail);
     return code;
 }
+// ---- trap record of the bounded barrier waits (oph_ptx.cuh): 4 words of mapped pinned host memory per process
+unsigned long long* g_trap_host = nullptr;
+bool g_trap_armed[64] = {};
+void ensure_trap_record() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || g_trap_armed[dev]) return;
+    g_trap_armed[dev] = true;
+    if (!g_trap_host) {
+        if (cudaHostAlloc(reinterpret_cast<void**>(&g_trap_host), 4 * sizeof(unsigned long long), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
+            g_trap_host = nullptr; cudaGetLastError(); return;
+        }
+        memset(g_trap_host, 0, 4 * sizeof(unsigned long long));
+    }
+    unsigned long long* d = nullptr;
+    if (cudaHostGetDevicePointer(reinterpret_cast<void**>(&d), g_trap_host, 0) != cudaSuccess ||
+        cudaMemcpyToSymbol(g_oph_trap_rec, &d, sizeof(d)) != cudaSuccess) cudaGetLastError();
+}
+// "block 17 of 148, warp 20 (GEMM role: MMA issuer) waited on barrier 3 (FULL_B[0]) for parity 1"
+int describe_trap(char* out, size_t cap) {
+    if (!g_trap_host || g_trap_host[0] != OPH_TRAP_MAGIC) return 0;
+    const unsigned block = (unsigned)(g_trap_host[1] >> 32), thread = (unsigned)g_trap_host[1];
+    const unsigned bar = (unsigned)(g_trap_host[2] >> 32), parity = (unsigned)g_trap_host[2];
+    const unsigned grid = (unsigned)(g_trap_host[3] >> 32), bdim = (unsigned)g_trap_host[3];
+    const unsigned warp = thread >> 5, idx = (bar & 1023u) >> 3;
+    const char* role = "";
+    char name[48] = "";
+    if (bdim == (unsigned)GEMM_THREADS) {          // gemm_bf16x3_kernel: role by warp, barrier by its index in the block
+        role = warp < (unsigned)NPW ? " (GEMM: producer / epilogue warp)" : warp < (unsigned)NPW + 4 ? " (GEMM: epilogue warp)" :
+               warp == (unsigned)NPW + 4 ? " (GEMM: MMA issuer)" : warp == (unsigned)NPW + 5 ? " (GEMM: copy-engine loader)" :
+               warp == (unsigned)NPW + 6 ? " (GEMM: item-boundary fix-up)" : " (GEMM)";
+        static const struct { int first, n; const char* nm; } tab[] = {
+            {BAR_FULL_A, NA_SLOTS, "FULL_A"}, {BAR_EMPTY_A, NA_SLOTS, "EMPTY_A"}, {BAR_FULL_B, NB_SLOTS, "FULL_B"},
+            {BAR_EMPTY_B, NB_SLOTS, "EMPTY_B"}, {BAR_LAND_A, NA_SLOTS, "LAND_A"}, {BAR_T_FULL, N_ACC, "T_FULL"}, {BAR_T_EMPTY, N_ACC, "T_EMPTY"}};
+        for (const auto& t : tab)
+            if ((int)idx >= t.first && (int)idx < t.first + t.n) snprintf(name, sizeof(name), " = %s[%d]", t.nm, (int)idx - t.first);
+    }
+    return snprintf(out, cap, "; a bounded barrier wait trapped: block %u of %u, warp %u%s waited on the mbarrier at shared address 0x%x (index %u%s) for parity %u",
+                    block, grid, warp, role, bar, idx, name, parity);
+}
+
 int check_launch(const char* what) {
     g_launches.fetch_add(1, std::memory_order_relaxed);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
-        snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+        int n = snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+        if (n > 0 && n < (int)sizeof(g_err)) describe_trap(g_err + n, sizeof(g_err) - n);
         return OPH_ECUDA;
     }
     return OPH_OK;
@@ -171,6 +212,7 @@ bool g_use_attn_fuse = true; // networks.Attention forward as one kernel (oph_ge
 bool g_use_hc_fuse = true;   // highway tail in the epilogue phase of the conv GEMM (oph_gemm_debug_flags bit 131072 turns it off)
 
 int launch_gemm(GemmArgs& a, int zdim, cudaStream_t st) {
+    ensure_trap_record();
     static bool attr_done = false;
     if (!attr_done) {
         if (cudaFuncSetAttribute(gemm_bf16x3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM) != cudaSuccess ||
@@ -256,13 +298,18 @@ int launch_gemm(GemmArgs& a, int zdim, cudaStream_t st) {
     // plain outputs the caller allows us to pre-zero (a.zero_bytes > 0): the slices of the remainder units RED into zeros
     // (off by default, flag 16384: the arrival order of the REDs would make FORWARD results vary in the last bits from run
     // to run, and with the side streams the idle SMs of a partial round are filled by other kernels anyway)
-    const bool can_zero = (g_gemm_dbg_flags_host & 16384) && !a.atomic && a.zero_bytes > 0 && !a.addend && !a.Chi && a.c_mul == 1;
+    // Launches that fill at most half of the CTA pairs (the windowed Attention / AudioDec pass of the incremental
+    // autoregressive route: 4-8 units) are always split, but into TWO slices only: 0 + a + b does not depend on the arrival
+    // order of the two REDs, so these results stay bit-reproducible.
+    const bool small = units * 2 <= GEMM_MAX_PAIRS;
+    const bool can_zero = ((g_gemm_dbg_flags_host & 16384) || small) && !a.atomic && a.zero_bytes > 0 && !a.addend && !a.Chi && a.c_mul == 1;
+    const int max_slices = (g_gemm_dbg_flags_host & 16384) || can_red ? 1 << 20 : 2;
     if (g_use_split && !a.hc_fused && a.a_tma == 1 && a.b_mode == B_PACKED && (can_red || can_zero) && a.z_mode == Z_NONE && a.ytaps == 1) {
         const int P = GEMM_MAX_PAIRS, KB = a.ntaps * cdiv(a.Kc, GEMM_BK);
         const int rem = (int)(units % P);
         if (rem > 0) {
             int best_s = 1; long long best = (long long)KB + 1;
-            for (int sl = 2; sl <= KB / 4; ++sl) {
+            for (int sl = 2; sl <= KB / 4 && sl <= max_slices; ++sl) {
                 const long long cost = (long long)cdiv(rem * sl, P) * (cdiv(KB, sl) + 1);
                 if (cost < best) { best = cost; best_s = sl; }
             }
@@ -500,7 +547,10 @@ int launch_ln_act_bwd(const float* dy, long long lddy, const float* z, long long
         unsigned short* h = const_cast<unsigned short*>(dzmap->hi); unsigned short* l = const_cast<unsigned short*>(dzmap->lo);
         const int wpr = C / 256, groups = 8 / wpr, depth = 3;
         long long gl = (rows + groups * 4 - 1) / (groups * 4);
-        const int gridw = (int)(gl < 1 ? 1 : (gl > 296 ? 296 : gl));              // two 8-warp blocks per SM
+        // blocks of 8 warps: 3 per SM (80 registers, ~55 KB of shared memory each); 2 per SM with flag 4194304.  Same time
+        // per launch alone (25 us), but 6.48 vs 6.58 ms per training step: more, shorter-lived blocks beside the GEMMs
+        const int capw = (g_gemm_dbg_flags_host & 4194304) ? 296 : 444;
+        const int gridw = (int)(gl < 1 ? 1 : (gl > capw ? capw : gl));
         const size_t smw = (5 * (size_t)C + 32) * sizeof(float) + (size_t)8 * depth * LNB_SLOT;
         static bool attr_done = false;
         if (!attr_done) {
@@ -646,6 +696,25 @@ int oph_cache_config(int mode) {
     const cudaFuncCache m = mode == 1 ? cudaFuncCachePreferShared : mode == 2 ? cudaFuncCachePreferL1 : mode == 3 ? cudaFuncCachePreferEqual : cudaFuncCachePreferNone;
     if (cudaDeviceSetCacheConfig(m) != cudaSuccess) return check_launch("cudaDeviceSetCacheConfig");
     return OPH_OK;
+}
+
+// Self-test of the trap record: one block records a fake wait (warp 21 = the GEMM's copy-engine loader, barrier FULL_B[1])
+// and traps.  The CUDA context is unusable afterwards: run it in a process of its own (tests/test_gpu_ops.py).
+__global__ void trap_selftest_kernel() {
+    if (threadIdx.x == 21 * 32) { oph_record_trap(229376u + 8u * (BAR_FULL_B + 1), 1u); __trap(); }
+}
+int oph_debug_trap_selftest(oph_stream_t stream) {
+    ensure_trap_record();
+    trap_selftest_kernel<<<1, GEMM_THREADS, 0, S(stream)>>>();
+    cudaStreamSynchronize(S(stream));
+    return check_launch("trap_selftest_kernel");
+}
+
+// The record a bounded barrier wait left before it trapped (0 words = none): out[0..3] raw, text = the decoded sentence.
+int oph_last_trap(unsigned long long* out, char* text, int cap) {
+    if (out) for (int i = 0; i < 4; ++i) out[i] = g_trap_host ? g_trap_host[i] : 0ull;
+    if (text && cap > 0) { text[0] = 0; describe_trap(text, (size_t)cap); }
+    return (g_trap_host && g_trap_host[0] == OPH_TRAP_MAGIC) ? 1 : 0;
 }
 
 int oph_profile_begin(void) {
@@ -1125,6 +1194,7 @@ int oph_attention_fwd(const oph_act* Q, const oph_act* K, const oph_act* V, cons
             }
             const int units = B * cdiv(T, ATT_BM);
             ProfScope ps(OPH_TAG_ATTENTION, 4.0 * B * T * (double)N * d, S(stream));
+            ensure_trap_record();
             launch_cfg(units < 148 ? units : 148, ATT_THREADS, ATT_SMEM, S(stream))(attn_fused_kernel, a);
             return check_launch("attn_fused_kernel");
         }

@@ -33,12 +33,27 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol bug traps (launch fails with an error) instead of hanging the GPU.
+// Bounded wait: a protocol bug traps (launch fails with an error) instead of hanging the GPU.  Before the trap the
+// waiting thread leaves a record in mapped host memory (who waited on which barrier), which survives the failed context:
+// the host decodes it into the error message of the next library call (oph_last_trap / check_launch in capi.cu).
+__device__ unsigned long long* g_oph_trap_rec = nullptr;      // [4] in mapped pinned host memory, set once per device
+constexpr unsigned long long OPH_TRAP_MAGIC = 0x4f50485f54524150ULL;   // "OPH_TRAP"
+__device__ __noinline__ void oph_record_trap(uint32_t bar, uint32_t parity) {
+    unsigned long long* r = g_oph_trap_rec;
+    if (r) {
+        r[1] = ((unsigned long long)blockIdx.x << 32) | threadIdx.x;
+        r[2] = ((unsigned long long)bar << 32) | parity;
+        r[3] = ((unsigned long long)gridDim.x << 32) | blockDim.x;
+        __threadfence_system();
+        r[0] = OPH_TRAP_MAGIC;
+        __threadfence_system();
+    }
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) { __trap(); }
+        if (clock64() - t0 > 4000000000LL) { oph_record_trap(bar, parity); __trap(); }
     }
 }
 

@@ -7,6 +7,7 @@ libophelia_sm100.so.  Activations are fp32 CUDA tensors `[B, time, C]` whose row
 import contextlib
 import ctypes
 import gc
+import os
 
 import torch
 
@@ -31,8 +32,13 @@ def capture(graph):
     was_enabled = gc.isenabled()
     gc.disable()
     try:
-        with torch.cuda.graph(graph):
-            yield graph
+        prio = os.environ.get("OPH_CAPTURE_PRIORITY")     # diagnostics: priority of the capturing (main-chain) stream
+        if prio is not None:
+            with torch.cuda.graph(graph, stream=torch.cuda.Stream(priority=int(prio))):
+                yield graph
+        else:
+            with torch.cuda.graph(graph):
+                yield graph
     finally:
         if was_enabled:
             gc.enable()

@@ -179,3 +179,31 @@ def test_fused_attention_equals_three_launch_path(B, T, N, mono):
     pl1, pl0 = A1._oph_planes, A0._oph_planes
     assert float((pl1[0].float() + pl1[1].float() - A1).abs().max()) < 1e-5
     assert float((pl0[0].float() + pl0[1].float() - A0).abs().max()) < 1e-5
+
+
+def test_trapped_barrier_wait_leaves_a_decodable_record():
+    """Every in-kernel barrier wait is bounded (a protocol bug traps instead of hanging the GPU).  The waiting thread
+    leaves a record in mapped host memory that outlives the failed context; the library decodes it into the error message.
+    The self-test kernel records a fake wait of the GEMM's copy-engine loader on FULL_B[1] and traps -- in a process of
+    its own, because the CUDA context is unusable afterwards."""
+    import subprocess
+    import sys
+    code = r"""
+import ctypes, sys
+sys.path.insert(0, %r)
+import torch
+from ophelia_b200 import _lib
+lib = _lib.load()
+torch.cuda.init(); torch.zeros(1, device="cuda")
+rc = lib.oph_debug_trap_selftest(ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+raw = (ctypes.c_ulonglong * 4)()
+text = ctypes.create_string_buffer(512)
+have = lib.oph_last_trap(raw, text, 512)
+print("RC", rc, "HAVE", have)
+print("ERR", lib.oph_last_error().decode())
+print("TEXT", text.value.decode())
+""" % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300).stdout
+    assert "HAVE 1" in out and "RC 0" not in out, out
+    assert "copy-engine loader" in out and "FULL_B[1]" in out and "parity 1" in out, out
+    assert "ERR trap_selftest_kernel" in out and "bounded barrier wait trapped" in out.split("ERR", 1)[1], out
