@@ -419,6 +419,9 @@ class Graph(object):
         return dev
 
     def _launch_then_prefetch(self, inputs, fields):
+        if fields is not None and os.environ.get("OPH_PREFETCH_FIRST"):     # diagnostics: the previous order
+            self._prefetch_next(fields)
+            return self._step_maybe_graphed(*inputs)
         out = self._step_maybe_graphed(*inputs)
         if fields is not None:
             self._prefetch_next(fields)
