@@ -32,4 +32,7 @@ timeout 120 python tools/ar_probe.py --graph > gpurun_out/ar_probe_${R}.log 2>&1
 # in-kernel time stamps of every GEMM launch of one graph replay + the kernel timeline of that replay
 timeout 200 python tools/gemm_ring.py --out ${R}_gemm_ring.txt > /dev/null 2>&1
 timeout 200 python tools/timeline.py --tag ${R} > /dev/null 2>&1
+# per-launch table of one eager step (CUDA events around every launch, shapes from the launch code)
+OPH_PROF_DUMP=gpurun_out/prof_${R}.txt python bench.py --no-graph --no-sub --no-cpu-baseline --steps 1 --warmup 3 > /dev/null 2>&1
+python tools/launch_table.py gpurun_out/prof_${R}.txt > gpurun_out/${R}_launch_table.txt 2>&1; rm -f gpurun_out/prof_${R}.txt
 du -sh gpurun_out; ls gpurun_out | tail -30
