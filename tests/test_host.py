@@ -245,3 +245,34 @@ def test_header_is_plain_c_and_struct_layouts_match_the_ctypes_mirrors(tmp_path)
     for cname, cls in structs.items():
         expect = [ctypes.sizeof(cls)] + [getattr(cls, f[0]).offset for f in cls._fields_]
         assert seen[cname] == expect, (cname, seen[cname], expect)
+
+
+def test_fast_divisor_formula():
+    """csrc/gemm_tc.cuh make_fastdiv / fdiv: n / d as umulhi(n, mul) >> shr for every launch constant the GEMM kernel divides
+    by (row-tile pairs, column blocks, taps, slices, steps per item, k-blocks).  The formula, restated here, must be exact
+    for 0 <= n < 2^31 -- checked at the edges of every quotient step for small d and at random for large d."""
+    import random
+
+    def make(d):
+        if d <= 1:
+            return 0, 0
+        lg = (d - 1).bit_length()                      # ceil(log2 d)
+        p = 31 + lg
+        mul = ((1 << p) + d - 1) // d
+        assert mul < (1 << 32)
+        return mul, p - 32
+
+    def fdiv(n, f):
+        mul, shr = f
+        return ((n * mul) >> 32) >> shr if mul else n
+
+    rng = random.Random(0)
+    ds = list(range(1, 2049)) + [rng.randrange(2049, 1 << 20) for _ in range(500)] + [870, 27840, 55680, 111360, (1 << 31) - 1]
+    for d in ds:
+        f = make(d)
+        ns = {0, 1, d - 1, d, d + 1, (1 << 31) - 1, (1 << 31) - d, ((1 << 31) - 1) // d * d, ((1 << 31) - 1) // d * d - 1}
+        ns |= {rng.randrange(0, 1 << 31) for _ in range(40)}
+        ns |= {q * d + r for q in (1, 2, 3, 1000, 65535) for r in (0, d - 1) if q * d + r < (1 << 31)}
+        for n in ns:
+            if 0 <= n < (1 << 31):
+                assert fdiv(n, f) == n // d, (n, d)
