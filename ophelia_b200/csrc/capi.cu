@@ -518,6 +518,8 @@ int launch_ln_act_fwd(const float* z, long long ldz, const float* gamma, const f
         const int nv = (C + 3) / 4;
         const size_t sm = (2 * (size_t)((C + 3) & ~3) + 32) * sizeof(float);
 #define OPH_LAUNCH(V, W) launch_cfg(rows_grid(rows, 8 / W), 256, sm, st)(ln_act_fwd_any_kernel<V, W>, z, ldz, gamma, beta, y, ldy, y_sig, ldys, yo->hi, yo->lo, yo->ldp, stats, (int)rows, C, act, norm, drop_p, seed, step)
+        // (MAXV float4 per lane, WPR warps per row); (3, 2) / (3, 4) as in the backward kernel measured slower here: 226 vs
+        // 178 us for 111 360 rows x 513 channels
         if (nv <= 32) OPH_LAUNCH(1, 1); else if (nv <= 160) OPH_LAUNCH(5, 1); else OPH_LAUNCH(5, 2);
 #undef OPH_LAUNCH
     } else {
@@ -579,11 +581,13 @@ int launch_ln_act_bwd(const float* dy, long long lddy, const float* z, long long
         if (!((lddy | ldz | lddz) & 3) && C <= 1280 && !(g_gemm_dbg_flags_host & 1048576)) {
             const int nv = (C + 3) / 4;
             const size_t sm = (5 * (size_t)((C + 3) & ~3) + 32) * sizeof(float);      // gamma, beta, partial moments, 3 column sums
-            const int wpr = nv > 160 ? 2 : 1;
+            const int wpr = nv <= 96 ? 1 : nv <= 192 ? 2 : 4;
             long long gl = (rows + (8 / wpr) * 8 - 1) / ((8 / wpr) * 8);                  // >= 8 rows per row group
-            const int gridb = (int)(gl < 1 ? 1 : (gl > 148 * 3 ? 148 * 3 : gl));
+            const int gridb = (int)(gl < 1 ? 1 : (gl > 148 * 3 ? 148 * 3 : gl));          // three resident blocks per SM
 #define OPH_LAUNCH(V, W) launch_cfg(gridb, 256, sm, st)(ln_act_bwd_any_kernel<V, W>, dy, lddy, z, ldz, stats, gamma, beta, dz, lddz, h, l, ldp, dgamma, dbeta, dbias, (int)rows, C, act, norm, drop_p, seed, step)
-            if (nv <= 32) OPH_LAUNCH(1, 1); else if (nv <= 160) OPH_LAUNCH(5, 1); else OPH_LAUNCH(5, 2);
+            // 80 -> (1,1), up to 384 -> (3,1), 513 -> (3,2), 1025 -> (3,4): 36 accumulators per lane instead of 60 (80 registers,
+            // three blocks per SM) and no pass in which a single lane works; 414 -> 338 us for 111 360 rows x 513 channels
+            if (nv <= 32) OPH_LAUNCH(1, 1); else if (nv <= 96) OPH_LAUNCH(3, 1); else if (nv <= 192) OPH_LAUNCH(3, 2); else OPH_LAUNCH(3, 4);
 #undef OPH_LAUNCH
         } else {
             launch_cfg(rows_grid(rows, 8), 256, smem, st)(ln_act_bwd_kernel, dy, lddy, z, ldz, stats, gamma, beta, dz, lddz, h, l, ldp, dgamma, dbeta, dbias, (int)rows, C, act, norm, drop_p, seed, step);

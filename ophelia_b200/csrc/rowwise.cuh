@@ -1405,7 +1405,7 @@ __global__ void __launch_bounds__(256) ln_act_fwd_any_kernel(
 
 // backward: dz as split-bf16 planes [rows][ldp] (or fp32 when dz_hi == NULL), dgamma / dbeta / dbias accumulated into
 template <int MAXV, int WPR>
-__global__ void __launch_bounds__(256, 2) ln_act_bwd_any_kernel(
+__global__ void __launch_bounds__(256, 3) ln_act_bwd_any_kernel(
         const float* __restrict__ dy, long long lddy, const float* __restrict__ z, long long ldz,
         const float* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
         float* __restrict__ dz, long long lddz, unsigned short* __restrict__ dz_hi, unsigned short* __restrict__ dz_lo,
