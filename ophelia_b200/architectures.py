@@ -714,27 +714,46 @@ class Text2MelGraph(Graph):
             main.wait_event(zero_ev)                     # the zeroed gradient buffer (every other stream forks from main below)
             s_w1.wait_stream(main)
             keep = []
-            # data parallel: gradient buckets in flat-buffer order (TextEnc first half | second half | AudioEnc | AudioDec)
-            # are all-reduced on a communication stream as soon as their layers' backward kernels are enqueued
-            buckets = self._grad_buckets(["Text2Mel/TextEnc/", "Text2Mel/TextEnc/HC_10/", "Text2Mel/AudioEnc/",
-                                          "Text2Mel/AudioDec/"])
+            # data parallel, hp.overlap_allreduce:
+            #   1 = buckets in flat-buffer order (TextEnc first half | second half | AudioEnc | AudioDec) are all-reduced on a
+            #       communication stream as soon as their layers' backward kernels are enqueued (collides with the GEMMs, which
+            #       need every SM: no gain measured);
+            #   2 = "late" buckets: the highway layers of both encoders plus the whole decoder (98 % of the bytes) are
+            #       exchanged once their last highway layer's backward is enqueued, i.e. under the few small launches (1x1 convs,
+            #       embedding) that end the backward pass and do not fill the machine; the two small heads follow at the end.
+            late = int(getattr(hp, "overlap_allreduce", 0)) == 2
+            first_hc = ["Text2Mel/%s/HC_4/" % n for n in ("TextEnc", "AudioEnc")]
+            std = hp.text_encoder_type == 'DCTTS_standard' and all(any(v.startswith(p_) for v in st.offsets) for p_ in first_hc)
+            if late and std:
+                buckets = self._grad_buckets(["Text2Mel/TextEnc/", first_hc[0], "Text2Mel/AudioEnc/", first_hc[1]])
+            else:
+                late = False
+                buckets = self._grad_buckets(["Text2Mel/TextEnc/", "Text2Mel/TextEnc/HC_10/", "Text2Mel/AudioEnc/",
+                                              "Text2Mel/AudioDec/"])
+            n_hc_text = sum(1 for v in st.offsets if v.startswith("Text2Mel/TextEnc/HC_") and v.endswith("/conv1d/kernel"))
+            n_hc_aenc = sum(1 for v in st.offsets if v.startswith("Text2Mel/AudioEnc/HC_") and v.endswith("/conv1d/kernel"))
             try:
                 ops.set_wgrad_stream(s_w1)
                 dRp = t_dec.backward(dlogits, release=False)
-                if buckets:
+                if buckets and not late:
                     buckets.launch(3, after=(main, s_w1))
                 dQ, dKV = out["R"]._oph_attention_bwd(dRp, watt / n_att)
                 s_text.wait_stream(main)
                 s_w2.wait_stream(main)
                 with torch.cuda.stream(s_text):
                     ops.set_wgrad_stream(s_w2)
-                    marks = {6: lambda: buckets.launch(1, after=(s_text, s_w2))} if buckets else None   # HC_15..HC_10 done
+                    marks = None
+                    if buckets and late:        # the last n_hc_text tape steps are the highway layers HC_15 .. HC_4
+                        marks = {n_hc_text: lambda: buckets.launch(1, after=(s_text, s_w2))}
+                    elif buckets:
+                        marks = {6: lambda: buckets.launch(1, after=(s_text, s_w2))}            # HC_15..HC_10 done
                     t_text.backward(self._text_grad(dKV), release=False, marks=marks)
-                    if buckets:
+                    if buckets and not late:
                         buckets.launch(0, after=(s_text, s_w2))
                 ops.set_wgrad_stream(s_w1)
-                t_aenc.backward(dQ, release=False)
-                if buckets:
+                marks = {n_hc_aenc: lambda: buckets.launch(3, after=(main, s_w1))} if (buckets and late) else None
+                t_aenc.backward(dQ, release=False, marks=marks)
+                if buckets and not late:
                     buckets.launch(2, after=(main, s_w1))
             finally:
                 keep.append(ops.take_keepalive())
