@@ -276,3 +276,26 @@ def test_fast_divisor_formula():
         for n in ns:
             if 0 <= n < (1 << 31):
                 assert fdiv(n, f) == n // d, (n, d)
+
+
+def test_late_gradient_buckets_partition_the_text2mel_buffer():
+    """hp.overlap_allreduce = 2 (architectures.Text2MelGraph.train_step_device): the flat gradient buffer is cut at the first
+    highway layer of each encoder.  The four buckets must tile the buffer exactly, the two 'early' ones (highway layers of
+    TextEnc; highway layers of AudioEnc + the whole AudioDec) must hold ~98 % of the bytes, and the tape positions at which
+    they are launched are the numbers of highway layers of the two encoders (12 and 10, networks.py:121-284)."""
+    from ophelia_b200.architectures import text2mel_variables
+    from ophelia_b200.configuration import default_hparams
+    from ophelia_b200.parallel import GradBuckets
+    from ophelia_b200.variables import VariableStore
+    hp = default_hparams(max_N=180, max_T=870)
+    st = VariableStore("cpu").declare_all(text2mel_variables(hp)).finalize(with_optimizer=True)
+    gb = GradBuckets(st, ["Text2Mel/TextEnc/", "Text2Mel/TextEnc/HC_4/", "Text2Mel/AudioEnc/", "Text2Mel/AudioEnc/HC_4/"])
+    sizes = [s_.numel() for s_ in gb.slices]
+    assert sum(sizes) == st.numel
+    assert gb.slices[0].data_ptr() == st.grad_flat.data_ptr()
+    for a, b in zip(gb.slices[:-1], gb.slices[1:]):
+        assert a.data_ptr() + a.numel() * 4 == b.data_ptr()
+    assert (sizes[1] + sizes[3]) / float(st.numel) > 0.975 and sizes[0] < 400000 and sizes[2] < 200000
+    n_text = sum(1 for v in st.offsets if v.startswith("Text2Mel/TextEnc/HC_") and v.endswith("/conv1d/kernel"))
+    n_aenc = sum(1 for v in st.offsets if v.startswith("Text2Mel/AudioEnc/HC_") and v.endswith("/conv1d/kernel"))
+    assert (n_text, n_aenc) == (12, 10)
