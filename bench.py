@@ -373,28 +373,13 @@ def run_ours(args):
         g.train_step_device(*dev_in)
     sync_all()
     launches0 = lib.oph_launch_count()
-    ms, comps = timed(lambda: g.train_step_device(*dev_in), args.steps)
-    launches = (lib.oph_launch_count() - launches0) // args.steps
-    # per-launch durations: the same eager steps with CUDA events around every launch.  An eager step is host-bound (the host
-    # needs 8-12 ms to enqueue what the device runs in ~7), so without precaution an event interval also measures the
-    # device waiting for the host's next launch call.  Each profiled step is therefore enqueued behind a spin kernel:
-    # while the device spins, the host queues the step's ~210 launches and ~420 event records (below the ~1 K entries a
-    # stream queues), and the device then runs them back to back -- the intervals are kernel durations.
-    spin_cycles = int(0.015 * 1.9e9)
     lib.oph_profile_begin()
-    ms_serial = 0.0                       # device time of such a step: its kernels back to back on one stream
-    for _ in range(args.steps):
-        torch.cuda._sleep(spin_cycles)
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s0.record()
-        g.train_step_device(*dev_in)
-        s1.record()
-        torch.cuda.synchronize()
-        ms_serial += s0.elapsed_time(s1) / args.steps
+    ms, comps = timed(lambda: g.train_step_device(*dev_in), args.steps)
     prof = (ctypes.c_double * (NUM_TAGS * 3))()
     lib.oph_profile_end(prof)
     hp.use_side_streams = True
     hp.overlap_allreduce = saved_overlap
+    launches = (lib.oph_launch_count() - launches0) // args.steps
     last_loss = [float(c) for c in comps.cpu().numpy()]
 
     # ---- timed region 1b: the same steps replayed from one CUDA graph (kernel-for-kernel identical work)
@@ -477,13 +462,11 @@ def run_ours(args):
         "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
         "per_gpu": frames_per_step / world / (ms * 1e-3),
         "launch_mode": {"headline": "cuda_graph" if ms is ms_graph else "eager", "ms_per_step_eager": ms_eager,
-                        "ms_per_step_serial": ms_serial,
                         "ms_per_step_cuda_graph": ms_graph,
                         "gemm_ms_over_graph_step": (tot_ms / args.steps) / ms_graph if ms_graph else None,
-                        "note": "roofline/gemm_breakdown are CUDA-event timings of every launch of eager single-stream steps that "
-                                "were enqueued behind a 15 ms spin kernel (the host queues a whole step while the device spins, so "
-                                "the intervals are kernel durations, not waits for the host); the CUDA-graph steps run the same "
-                                "kernels with TextEnc and the weight-gradient GEMMs on side streams"},
+                        "note": "roofline/gemm_breakdown are CUDA-event timings of every GEMM launch in the eager single-stream "
+                                "steps; the CUDA-graph steps run the same kernels with TextEnc and the weight-gradient GEMMs "
+                                "on side streams"},
         "e2e": {"value": frames_per_step / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": src.bytes_per_batch(), "d2h_bytes_per_step": 4 * len(last_loss) + 8},
         "gpu_launches": int(launches) * args.steps,
@@ -494,7 +477,7 @@ def run_ours(args):
                      "traffic_detail": traffic.get("detail"),
                      "peak_source": pk["src"] + " bf16 cuBLAS sustained",
                      "launches_per_step": tot_n / args.steps, "avg_launch_ms": tot_ms / max(tot_n, 1),
-                     "share_of_step": (tot_ms / args.steps) / ms_serial,
+                     "share_of_step": (tot_ms / args.steps) / ms_eager,
                      "frac_of_3pass_ceiling": 3.0 * achieved / pk["tensor_sustained"],
                      "note": "achieved counts ALGORITHMIC FLOPs once; the split-bf16 scheme issues 3 tensor passes per "
                              "FLOP, so the ceiling of this number is peak/3"},
