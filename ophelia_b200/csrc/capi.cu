@@ -302,7 +302,8 @@ int launch_gemm(GemmArgs& a, int zdim, cudaStream_t st) {
     // autoregressive route: 4-8 units) are always split, but into TWO slices only: 0 + a + b does not depend on the arrival
     // order of the two REDs, so these results stay bit-reproducible.
     const bool small = units * 2 <= GEMM_MAX_PAIRS;
-    const bool can_zero = ((g_gemm_dbg_flags_host & 16384) || small) && !a.atomic && a.zero_bytes > 0 && !a.addend && !a.Chi && a.c_mul == 1;
+    const bool can_zero = ((g_gemm_dbg_flags_host & 16384) || small) && !a.atomic && a.zero_bytes > 0 && !a.addend && !a.Chi && a.c_mul == 1 &&
+                          !a.ln_fuse;      // (the fused conv tail normalises whole rows of the accumulator: no partial sums)
     const int max_slices = (g_gemm_dbg_flags_host & 16384) || can_red ? 1 << 20 : 2;
     if (g_use_split && !a.hc_fused && a.a_tma == 1 && a.b_mode == B_PACKED && (can_red || can_zero) && a.z_mode == Z_NONE && a.ytaps == 1) {
         const int P = GEMM_MAX_PAIRS, KB = a.ntaps * cdiv(a.Kc, GEMM_BK);
