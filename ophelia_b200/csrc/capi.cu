@@ -112,9 +112,11 @@ int fail(int code, const char* fmt, const char* detail = "") {   // fmt contains
 // ---- trap record of the bounded barrier waits (oph_ptx.cuh): 4 words of mapped pinned host memory per process
 unsigned long long* g_trap_host = nullptr;
 bool g_trap_armed[64] = {};
-void ensure_trap_record() {
+void ensure_trap_record(cudaStream_t st = nullptr) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || g_trap_armed[dev]) return;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;       // allocation + symbol copy are illegal inside a capture:
+    if (st && cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone) return;   // arm at a later launch
     g_trap_armed[dev] = true;
     if (!g_trap_host) {
         if (cudaHostAlloc(reinterpret_cast<void**>(&g_trap_host), 4 * sizeof(unsigned long long), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
@@ -212,7 +214,7 @@ bool g_use_attn_fuse = true; // networks.Attention forward as one kernel (oph_ge
 bool g_use_hc_fuse = true;   // highway tail in the epilogue phase of the conv GEMM (oph_gemm_debug_flags bit 131072 turns it off)
 
 int launch_gemm(GemmArgs& a, int zdim, cudaStream_t st) {
-    ensure_trap_record();
+    ensure_trap_record(st);
     static bool attr_done = false;
     if (!attr_done) {
         if (cudaFuncSetAttribute(gemm_bf16x3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM) != cudaSuccess ||
@@ -1199,7 +1201,7 @@ int oph_attention_fwd(const oph_act* Q, const oph_act* K, const oph_act* V, cons
             }
             const int units = B * cdiv(T, ATT_BM);
             ProfScope ps(OPH_TAG_ATTENTION, 4.0 * B * T * (double)N * d, S(stream));
-            ensure_trap_record();
+            ensure_trap_record(S(stream));
             launch_cfg(units < 148 ? units : 148, ATT_THREADS, ATT_SMEM, S(stream))(attn_fused_kernel, a);
             return check_launch("attn_fused_kernel");
         }
