@@ -484,6 +484,19 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
 #pragma unroll 1
             for (int cb = cg; cb < GEMM_BN / 16; cb += ncg) {
                 const int col0 = cb * 16;
+                // addend rows of this block (attention: dQ accumulates onto the decoder-input gradient): loaded BEFORE the
+                // accumulator is read, so that their latency runs under the tcgen05.ld and the staging (they used to be four
+                // dependent global loads per block on the epilogue's critical path: 25 us of a 42 us launch)
+                float4 adv[4];
+                const bool add_vec = addb && vec_ok && !atom && t.n0 + col0 + c4 * 4 + 4 <= p.N;
+                if (add_vec) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int rr = rsub + 8 * i;
+                        adv[i] = rr < nrows ? __ldg(reinterpret_cast<const float4*>(addb + (crow0 + (long long)rr * p.c_mul) * p.ld_add + t.n0 + col0 + c4 * 4))
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
                 uint32_t r[16];
                 tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + acc * GEMM_BN + col0, r);
                 tmem_ld_wait();
@@ -515,8 +528,8 @@ gemm_bf16x3_kernel(const __grid_constant__ GemmArgs p) {
                     if (full) {
                         if (atom) red_add_v4(dst, o[0], o[1], o[2], o[3]);
                         else {
-                            if (addb) {
-                                const float4 a = __ldg(reinterpret_cast<const float4*>(addb + (crow0 + (long long)rr * p.c_mul) * p.ld_add + gcol));
+                            if (addb) {                        // (full && !atom here, i.e. add_vec: loaded above)
+                                const float4 a = adv[i];
                                 o[0] += a.x; o[1] += a.y; o[2] += a.z; o[3] += a.w;
                             }
                             *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
