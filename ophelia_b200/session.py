@@ -52,6 +52,14 @@ class Session(object):
             # loss components and global_step come back through pinned buffers with ONE stream synchronisation (two blocking
             # reads cost two round trips during which the device idles).  global_step: value after the step (fetching it
             # alongside train_op is unordered in TF; the reference only logs it)
+            lo = g.__dict__.get("_loss_out") if getattr(g.hp, "early_loss_return", True) else None
+            if lo is not None and lo["n"] == comps_d.numel():
+                # the step published its losses at the end of the forward pass (Graph._publish_losses): wait for that
+                # event only; backward pass, exchange and optimiser step keep running while the caller prepares the next call
+                lo["event"].synchronize()
+                comps = lo["comps"][:lo["n"]].numpy().copy()
+                gs = int(lo["gs"][0]) + 1 if "global_step" in names else None
+                return {"train_op": None, "loss": float(comps[0]), "loss_components": [float(c) for c in comps], "global_step": gs}
             if not comps_d.is_cuda:
                 comps = comps_d.numpy()
                 gs = int(g.store.global_step.item()) if "global_step" in names else None
