@@ -514,6 +514,41 @@ def test_session_train_loop_with_changing_batch_shapes():
         sess.run([g1.global_step, g1.loss_components, g1.train_op])
 
 
+def test_session_returns_at_the_loss_event_and_later_reads_see_the_finished_step():
+    """A training Session.run returns when the loss components are on the host (end of the forward pass, an external event
+    inside the captured step); the backward pass and the optimiser may still be running.  Everything read afterwards must
+    see the finished step: the parameters fetched right after each call have moved by the optimiser step (constant learning
+    rate 1e-3 here, so a stale read would be off by ~1e-3 per element) and agree with a twin that waits for the whole
+    step (hp.early_loss_return = False) up to the summation order of the gradient atomics; losses and global_step agree."""
+    import copy
+    from ophelia_b200.session import Session
+    hp1 = make_hp(max_N=40, max_T=120, dropout_rate=0.0, decay_lr=False)
+    hp2 = copy.copy(hp1)
+    hp2.early_loss_return = False
+    P = oracle_params(hp1, "t2m", seed=5)
+    b = synthetic_batch(hp1, 3, 40, 120, seed=3, ragged=True)
+    batches = [{"text": torch.tensor(b["L"]), "mel": torch.tensor(b["mels"])} for _ in range(6)]
+    g1 = _graph(hp1, "train", P, data=iter(batches))
+    g2 = _graph(hp2, "train", P, data=iter(batches))
+    sess = Session()
+    prev = g1.store.flat.detach().cpu().numpy().copy()
+    for i in range(6):                                    # steps 4-6 replay the captured graph
+        out1 = sess.run([g1.global_step, g1.loss_components, g1.train_op])
+        w1 = g1.store.flat.detach().cpu().numpy().copy()  # stream-ordered behind the rest of the step
+        out2 = sess.run([g2.global_step, g2.loss_components, g2.train_op])
+        w2 = g2.store.flat.detach().cpu().numpy().copy()
+        assert out1[0] == out2[0] == i + 1
+        # (step 1 sees identical weights; afterwards the twins drift apart through the order of the gradient atomics and a
+        #  learning rate of 1e-3 on sign-like first Adam steps)
+        np.testing.assert_allclose(out1[1], out2[1], rtol=1e-6 if i == 0 else 5e-2, atol=1e-6)
+        moved = np.abs(w1 - prev)
+        assert float(np.mean(moved > 1e-4)) > 0.5, (i, float(np.mean(moved > 1e-4)))      # the step's update is in what we read (a stale read: 0)
+        assert float(np.mean(np.abs(w1 - w2) > 1e-4)) < 0.02, (i, float(np.mean(np.abs(w1 - w2) > 1e-4)))
+        prev = w1
+    assert g1.__dict__.get("_loss_out") is not None and g2.__dict__.get("_loss_out") is None
+    assert len(g1._graph_steps) == 1 and len(g2._graph_steps) == 1
+
+
 def test_norm_none_configuration_matches_oracle():
     """hp.norm = None (the reference's config/project/*.cfg): conv1d / hc run without layer norm (modules.py:47-75 returns
     its input), no normalize variables exist; forward and two optimiser steps against the oracles."""
